@@ -1,0 +1,212 @@
+// Fused small-sequence attention core for the UNet's deep levels (tokens T = h*w <= 256...1024,
+// 2 heads, d_head 128/256/512): softmax(q k^T / sqrt(d)) v for one (image, head, query block) per
+// CTA with the whole K (then the whole V) resident in shared memory -- single-pass softmax, no
+// T x T matrix in HBM.  Replaces the scaled-dot-product part of nn.MultiheadAttention
+// (Diffusion_model/src/unet/blocks.py:196-227; F.multi_head_attention_forward math: q scaled by
+// d^-1/2, softmax over keys, no mask, no dropout in eval).
+//
+// v1: fp32 CUDA-core math on bf16 (optionally hi+lo split) operands; the projections around it
+// (in_proj, out_proj o proj_out) run on the tcgen05 GEMM engine.  The core is ~1% of the UNet's
+// FLOPs.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/b2d.h"
+#include "b2d_internal.h"
+
+namespace b2d {
+
+constexpr int kAttnThreads = 128;
+constexpr int kQPW = 4;                                  // queries processed together by one warp
+constexpr int kQB = (kAttnThreads / 32) * kQPW;          // queries per CTA
+
+__device__ __forceinline__ float a_bflo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float a_bfhi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ void a_unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = a_bflo(u.x); f[1] = a_bfhi(u.x); f[2] = a_bflo(u.y); f[3] = a_bfhi(u.y);
+  f[4] = a_bflo(u.z); f[5] = a_bfhi(u.z); f[6] = a_bflo(u.w); f[7] = a_bfhi(u.w);
+}
+
+// stage rows [T][d] of one head (column offset col0 in the [N][T][3C] tensor) into smem, row pitch dp
+__device__ __forceinline__ void stage_rows(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* dst, int T, int d, int dp,
+                                           long long row_stride) {
+  const int vpr = d >> 3;
+  for (int i = threadIdx.x; i < T * vpr; i += blockDim.x) {
+    const int j = i / vpr, v = i - j * vpr;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (long long)j * row_stride) + v);
+    *reinterpret_cast<uint4*>(dst + (long long)j * dp + v * 8) = u;
+  }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                 const __nv_bfloat16* __restrict__ qkv_lo,
+                                                                 __nv_bfloat16* __restrict__ out,
+                                                                 __nv_bfloat16* __restrict__ out_lo, int T, int C, int heads,
+                                                                 float scale) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int d = C / heads;
+  const int dp = d + 8;  // +16 bytes per row: lanes reading different rows hit different banks
+  const int nh = blockIdx.y;
+  const int n = nh / heads, h = nh - n * heads;
+  const int q0 = blockIdx.x * kQB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  __nv_bfloat16* kv = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* kv_lo = kv + (size_t)T * dp;
+  float* sP = reinterpret_cast<float*>(kv + (size_t)T * dp * (SPLIT ? 2 : 1));  // [kQB][T]
+  float* sQ = sP + (size_t)kQB * T;                                             // [kQB][d]
+
+  const long long rs = 3LL * C;
+  const __nv_bfloat16* base = qkv + (long long)n * T * rs + (long long)h * d;
+  const __nv_bfloat16* base_lo = SPLIT ? qkv_lo + (long long)n * T * rs + (long long)h * d : nullptr;
+
+  // ---- phase 1: K resident, scores + softmax ------------------------------------------------
+  stage_rows(base + C, kv, T, d, dp, rs);
+  if (SPLIT) stage_rows(base_lo + C, kv_lo, T, d, dp, rs);
+  for (int i = threadIdx.x; i < kQB * d; i += blockDim.x) {
+    const int qi = i / d, c = i - qi * d;
+    float v = 0.f;
+    if (q0 + qi < T) {
+      v = __bfloat162float(base[(long long)(q0 + qi) * rs + c]);
+      if (SPLIT) v += __bfloat162float(base_lo[(long long)(q0 + qi) * rs + c]);
+    }
+    sQ[i] = v * scale;
+  }
+  __syncthreads();
+
+  const int qw = warp * kQPW;  // first local query of this warp
+  for (int j = lane; j < T; j += 32) {
+    float acc[kQPW] = {0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16* krow = kv + (size_t)j * dp;
+    const __nv_bfloat16* krow_lo = kv_lo + (size_t)j * dp;
+    for (int c = 0; c < d; c += 8) {
+      float kf[8];
+      a_unpack8(*reinterpret_cast<const uint4*>(krow + c), kf);
+      if (SPLIT) {
+        float kl[8];
+        a_unpack8(*reinterpret_cast<const uint4*>(krow_lo + c), kl);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) kf[e] += kl[e];
+      }
+#pragma unroll
+      for (int qq = 0; qq < kQPW; ++qq) {
+        const float4 qa = *reinterpret_cast<const float4*>(sQ + (size_t)(qw + qq) * d + c);
+        const float4 qb = *reinterpret_cast<const float4*>(sQ + (size_t)(qw + qq) * d + c + 4);
+        acc[qq] = fmaf(qa.x, kf[0], acc[qq]); acc[qq] = fmaf(qa.y, kf[1], acc[qq]);
+        acc[qq] = fmaf(qa.z, kf[2], acc[qq]); acc[qq] = fmaf(qa.w, kf[3], acc[qq]);
+        acc[qq] = fmaf(qb.x, kf[4], acc[qq]); acc[qq] = fmaf(qb.y, kf[5], acc[qq]);
+        acc[qq] = fmaf(qb.z, kf[6], acc[qq]); acc[qq] = fmaf(qb.w, kf[7], acc[qq]);
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < kQPW; ++qq) sP[(size_t)(qw + qq) * T + j] = acc[qq];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int qq = 0; qq < kQPW; ++qq) {
+    float* prow = sP + (size_t)(qw + qq) * T;
+    float m = -INFINITY;
+    for (int j = lane; j < T; j += 32) m = fmaxf(m, prow[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float e = __expf(prow[j] - m);
+      prow[j] = e;
+      s += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.f / s;
+    for (int j = lane; j < T; j += 32) prow[j] *= inv;
+  }
+  __syncthreads();
+
+  // ---- phase 2: V resident, out = P V ----------------------------------------------------------
+  stage_rows(base + 2 * C, kv, T, d, dp, rs);
+  if (SPLIT) stage_rows(base_lo + 2 * C, kv_lo, T, d, dp, rs);
+  __syncthreads();
+
+  constexpr int kMaxCI = 8;  // d <= 512: each lane owns channel pairs {2*lane + 64*i}
+  const int nci = d >> 6;
+  float o[kQPW][kMaxCI][2];
+#pragma unroll
+  for (int qq = 0; qq < kQPW; ++qq)
+#pragma unroll
+    for (int i = 0; i < kMaxCI; ++i) { o[qq][i][0] = 0.f; o[qq][i][1] = 0.f; }
+  for (int j = 0; j < T; ++j) {
+    float pj[kQPW];
+#pragma unroll
+    for (int qq = 0; qq < kQPW; ++qq) pj[qq] = sP[(size_t)(qw + qq) * T + j];
+#pragma unroll
+    for (int i = 0; i < kMaxCI; ++i) {
+      if (i < nci) {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(kv + (size_t)j * dp + 2 * lane + 64 * i);
+        float v0 = a_bflo(u), v1 = a_bfhi(u);
+        if (SPLIT) {
+          const uint32_t ul = *reinterpret_cast<const uint32_t*>(kv_lo + (size_t)j * dp + 2 * lane + 64 * i);
+          v0 += a_bflo(ul); v1 += a_bfhi(ul);
+        }
+#pragma unroll
+        for (int qq = 0; qq < kQPW; ++qq) {
+          o[qq][i][0] = fmaf(pj[qq], v0, o[qq][i][0]);
+          o[qq][i][1] = fmaf(pj[qq], v1, o[qq][i][1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int qq = 0; qq < kQPW; ++qq) {
+    const int q = q0 + qw + qq;
+    if (q < T) {
+#pragma unroll
+      for (int i = 0; i < kMaxCI; ++i) {
+        if (i < nci) {
+          const long long idx = ((long long)n * T + q) * C + (long long)h * d + 2 * lane + 64 * i;
+          const __nv_bfloat162 hv = __floats2bfloat162_rn(o[qq][i][0], o[qq][i][1]);
+          *reinterpret_cast<__nv_bfloat162*>(out + idx) = hv;
+          if (SPLIT && out_lo != nullptr) {
+            *reinterpret_cast<__nv_bfloat162*>(out_lo + idx) =
+                __floats2bfloat162_rn(o[qq][i][0] - __low2float(hv), o[qq][i][1] - __high2float(hv));
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+extern "C" int b2d_attention(const void* qkv, const void* qkv_lo, void* out, void* out_lo, int32_t N, int32_t T, int32_t C,
+                             int32_t heads, void* stream) {
+  if (!qkv || !out) return set_error(B2D_E_INVALID, "b2d_attention: null pointer");
+  if (N < 1 || T < 1 || heads < 1 || C < 1 || (C % heads)) return set_error(B2D_E_INVALID, "b2d_attention: bad shape");
+  const int d = C / heads;
+  if ((d % 64) || d > 512) return set_error(B2D_E_INVALID, "b2d_attention: d_head=%d must be a multiple of 64 and <= 512", d);
+  if ((long long)N * heads > 65535) return set_error(B2D_E_INVALID, "b2d_attention: N*heads too large");
+  const bool split = qkv_lo != nullptr;
+  const size_t smem = (size_t)T * (d + 8) * 2 * (split ? 2 : 1) + (size_t)kQB * T * 4 + (size_t)kQB * d * 4;
+  if (smem > 227 * 1024 - 1024) return set_error(B2D_E_INVALID, "b2d_attention: T=%d d=%d needs %zu bytes of shared memory", T, d, smem);
+  dim3 grid((T + kQB - 1) / kQB, N * heads);
+  const float scale = 1.0f / sqrtf((float)d);
+  // opt in to the full dynamic shared-memory carve-out once per kernel variant (not a stream operation)
+  static bool configured[2] = {false, false};
+  if (!configured[split ? 1 : 0]) {
+    cudaError_t e = split ? cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)
+                          : cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return set_error(B2D_E_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
+    configured[split ? 1 : 0] = true;
+  }
+  if (split) {
+    attention_kernel<true><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_lo, (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo, T, C, heads, scale);
+  } else {
+    attention_kernel<false><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)qkv, nullptr, (__nv_bfloat16*)out, nullptr, T, C, heads, scale);
+  }
+  return check_launch("attention_kernel");
+}

@@ -1,0 +1,295 @@
+// Memory-bound kernels around the conv engine: GroupNorm apply (+SiLU, +time-embedding add),
+// 2x2 max-pool with GroupNorm partial sums, nearest upsample, layout conversion at the module
+// boundary.  All are 16-byte vectorised over the channels-last innermost dimension and sized
+// as a multiple of the SM count.  Reference call sites are listed in include/b2d.h.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/b2d.h"
+#include "b2d_internal.h"
+
+namespace b2d {
+
+__device__ __forceinline__ float bflo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bfhi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t packbf(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bflo(u.x); f[1] = bfhi(u.x); f[2] = bflo(u.y); f[3] = bfhi(u.y);
+  f[4] = bflo(u.z); f[5] = bfhi(u.z); f[6] = bflo(u.w); f[7] = bfhi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(packbf(f[0], f[1]), packbf(f[2], f[3]), packbf(f[4], f[5]), packbf(f[6], f[7]));
+}
+// bf16 "lo" part of an fp32 value whose "hi" part is the packed word (hi/lo split, fp32x mode)
+__device__ __forceinline__ uint4 pack8_lo(const float (&f)[8], const uint4& hi) {
+  float h[8];
+  unpack8(hi, h);
+  float l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) l[i] = f[i] - h[i];
+  return pack8(l);
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// --------------------------------------------------------------------------- GroupNorm apply
+// grid = (blocks_per_image, N); block = 256.  Per-channel scale/shift/temb staged in smem.
+__global__ void __launch_bounds__(256) gn_apply_kernel(
+    const uint4* __restrict__ x, const uint4* __restrict__ x_lo, uint4* __restrict__ y, uint4* __restrict__ y_lo,
+    long long P, int C, const double* __restrict__ stats, int cpg, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, int act, const float* __restrict__ temb_table,
+    const int* __restrict__ temb_row, int temb_row_stride, int temb_ld, int temb_col, double* __restrict__ stats_out) {
+  extern __shared__ float sm[];
+  float* sa = sm;
+  float* sb = sm + C;
+  float* st = sm + 2 * C;
+  const int n = blockIdx.y;
+  const int G = C / cpg;
+  const double cnt = (double)cpg * (double)P;
+  const float* trow = nullptr;
+  if (temb_table != nullptr) {
+    const int row = temb_row ? temb_row[(long long)n * temb_row_stride] : 0;
+    trow = temb_table + (long long)row * temb_ld + temb_col;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double s = stats[((long long)n * G + g) * 2];
+    const double ss = stats[((long long)n * G + g) * 2 + 1];
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    sa[c] = rstd * ga;
+    sb[c] = be - (float)mean * rstd * ga;
+    st[c] = trow ? trow[c] : 0.f;
+  }
+  __syncthreads();
+
+  const int vpc = C >> 3;  // 16-byte vectors per pixel
+  const long long nvec = P * vpc;
+  const long long base = (long long)n * nvec;
+  float acc_s = 0.f, acc_ss = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpc) << 3;
+    float f[8];
+    unpack8(__ldg(x + base + i), f);
+    if (x_lo != nullptr) {
+      float l[8];
+      unpack8(__ldg(x_lo + base + i), l);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += l[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = fmaf(f[j], sa[c0 + j], sb[c0 + j]);
+      if (act) v = silu(v);
+      v += st[c0 + j];
+      f[j] = v;
+      acc_s += v;
+      acc_ss += v * v;
+    }
+    const uint4 hi = pack8(f);
+    y[base + i] = hi;
+    if (y_lo != nullptr) y_lo[base + i] = pack8_lo(f, hi);
+  }
+  if (stats_out != nullptr) {
+    __shared__ float red[2][8];
+    acc_s = warp_sum(acc_s);
+    acc_ss = warp_sum(acc_ss);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = acc_s; red[1][w] = acc_ss; }
+    __syncthreads();
+    if (w == 0) {
+      float a = l < (int)(blockDim.x >> 5) ? red[0][l] : 0.f;
+      float b = l < (int)(blockDim.x >> 5) ? red[1][l] : 0.f;
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (l == 0) {
+        atomicAdd(stats_out + (long long)n * 2, (double)a);
+        atomicAdd(stats_out + (long long)n * 2 + 1, (double)b);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- max-pool 2x2 + sums
+__global__ void __launch_bounds__(256) maxpool_stats_kernel(const uint4* __restrict__ x, const uint4* __restrict__ x_lo,
+                                                            uint4* __restrict__ y, uint4* __restrict__ y_lo, int H, int W,
+                                                            int C, double* __restrict__ stats) {
+  const int n = blockIdx.y;
+  const int OH = H >> 1, OW = W >> 1, vpc = C >> 3;
+  const long long nvec = (long long)OH * OW * vpc;
+  const uint4* xi = x + (long long)n * H * W * vpc;
+  const uint4* xl = x_lo ? x_lo + (long long)n * H * W * vpc : nullptr;
+  float acc_s = 0.f, acc_ss = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpc);
+    const long long pix = i / vpc;
+    const int ox = (int)(pix % OW), oy = (int)(pix / OW);
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long src = ((long long)(2 * oy + (q >> 1)) * W + (2 * ox + (q & 1))) * vpc + v;
+      float f[8];
+      unpack8(__ldg(xi + src), f);
+      if (xl) {
+        float l[8];
+        unpack8(__ldg(xl + src), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += l[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = q == 0 ? f[j] : fmaxf(m[j], f[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc_s += m[j]; acc_ss += m[j] * m[j]; }
+    const uint4 hi = pack8(m);
+    y[(long long)n * nvec + i] = hi;
+    if (y_lo) y_lo[(long long)n * nvec + i] = pack8_lo(m, hi);
+  }
+  __shared__ float red[2][8];
+  acc_s = warp_sum(acc_s);
+  acc_ss = warp_sum(acc_ss);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = acc_s; red[1][w] = acc_ss; }
+  __syncthreads();
+  if (w == 0) {
+    float a = l < (int)(blockDim.x >> 5) ? red[0][l] : 0.f;
+    float b = l < (int)(blockDim.x >> 5) ? red[1][l] : 0.f;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (l == 0 && stats != nullptr) {
+      atomicAdd(stats + (long long)n * 2, (double)a);
+      atomicAdd(stats + (long long)n * 2 + 1, (double)b);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- nearest 2x (in-plane)
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long ND,
+                                                         int H, int W, int vpc) {
+  const long long total = ND * (2LL * H) * (2LL * W) * vpc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpc);
+    long long pix = i / vpc;
+    const int ox = (int)(pix % (2 * W)); pix /= (2 * W);
+    const int oy = (int)(pix % (2 * H));
+    const long long nd = pix / (2 * H);
+    y[i] = __ldg(x + ((nd * H + (oy >> 1)) * W + (ox >> 1)) * vpc + v);
+  }
+}
+
+// --------------------------------------------------------------------------- layout conversion
+// planar fp32 [N][C][P] -> channels-last bf16 [N][P][cpad] at channel offset coff
+__global__ void __launch_bounds__(256) planar_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                           __nv_bfloat16* __restrict__ y_lo, int N, int C, long long P,
+                                                           int cpad, int coff, const float* __restrict__ div_scale) {
+  const long long total = (long long)N * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / P, p = i - n * P;
+    for (int c = 0; c < C; ++c) {
+      float v = __ldg(x + (n * C + c) * P + p);
+      if (div_scale) v = __fdiv_rn(v, __ldg(div_scale + c));
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      y[i * cpad + coff + c] = h;
+      if (y_lo) y_lo[i * cpad + coff + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+// channels-last bf16 [N][P][cstride] (channels coff..coff+C) -> planar fp32 [N][C][P]
+__global__ void __launch_bounds__(256) cl_to_planar_kernel(const __nv_bfloat16* __restrict__ x,
+                                                           const __nv_bfloat16* __restrict__ x_lo, float* __restrict__ y,
+                                                           int N, int C, long long P, int cstride, int coff) {
+  const long long total = (long long)N * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / P, p = i - n * P;
+    for (int c = 0; c < C; ++c) {
+      float v = __bfloat162float(x[i * cstride + coff + c]);
+      if (x_lo) v += __bfloat162float(x_lo[i * cstride + coff + c]);
+      y[(n * C + c) * P + p] = v;
+    }
+  }
+}
+
+static inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+extern "C" int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int64_t P, int32_t C,
+                            const double* stats, int32_t cpg, const float* gamma, const float* beta, float eps, int32_t act,
+                            const float* temb_table, const int32_t* temb_row, int32_t temb_row_stride, int32_t temb_ld,
+                            int32_t temb_col, double* stats_out, void* stream) {
+  if (!x || !y || !stats) return set_error(B2D_E_INVALID, "b2d_gn_apply: null pointer");
+  if (N < 1 || P < 1 || C < 8 || (C % 8) || cpg < 1 || (C % cpg)) return set_error(B2D_E_INVALID, "b2d_gn_apply: bad shape N=%d P=%lld C=%d cpg=%d", N, (long long)P, C, cpg);
+  if (3 * C * (int)sizeof(float) > 96 * 1024) return set_error(B2D_E_INVALID, "b2d_gn_apply: C=%d too large", C);
+  if (N > 65535) return set_error(B2D_E_INVALID, "b2d_gn_apply: N too large");
+  const long long nvec = (long long)P * (C / 8);
+  int bx = grid_for(nvec, 256 * 4);
+  int per_img_cap = (num_sms() * 8 + N - 1) / N;
+  if (bx > per_img_cap) bx = per_img_cap < 1 ? 1 : per_img_cap;
+  const size_t smem = 3 * (size_t)C * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cfg = true;
+  }
+  gn_apply_kernel<<<dim3(bx, N), 256, smem, (cudaStream_t)stream>>>(
+      (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, temb_table,
+      temb_row, temb_row_stride, temb_ld, temb_col, stats_out);
+  return check_launch("gn_apply_kernel");
+}
+
+extern "C" int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int32_t H, int32_t W,
+                                    int32_t C, double* stats, void* stream) {
+  if (!x || !y) return set_error(B2D_E_INVALID, "b2d_maxpool2x2_stats: null pointer");
+  if (N < 1 || N > 65535 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 8 || (C % 8))
+    return set_error(B2D_E_INVALID, "b2d_maxpool2x2_stats: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  const long long nvec = (long long)(H / 2) * (W / 2) * (C / 8);
+  int bx = grid_for(nvec, 256);
+  int per_img_cap = (num_sms() * 8 + N - 1) / N;
+  if (bx > per_img_cap) bx = per_img_cap < 1 ? 1 : per_img_cap;
+  maxpool_stats_kernel<<<dim3(bx, N), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)x_lo, (uint4*)y,
+                                                                       (uint4*)y_lo, H, W, C, stats);
+  return check_launch("maxpool_stats_kernel");
+}
+
+extern "C" int b2d_upsample2x_nearest(const void* x, void* y, int32_t ND, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!x || !y || ND < 1 || H < 1 || W < 1 || C < 8 || (C % 8)) return set_error(B2D_E_INVALID, "b2d_upsample2x_nearest: bad argument");
+  const long long total = (long long)ND * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256 * 2), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, ND, H, W, C / 8);
+  return check_launch("upsample2x_kernel");
+}
+
+extern "C" int b2d_planar_to_cl(const float* x, void* y, void* y_lo, int32_t N, int32_t C, int64_t P, int32_t cpad, int32_t coff,
+                                const float* div_scale, void* stream) {
+  if (!x || !y || N < 1 || C < 1 || P < 1 || coff < 0 || coff + C > cpad) return set_error(B2D_E_INVALID, "b2d_planar_to_cl: bad argument");
+  planar_to_cl_kernel<<<grid_for((long long)N * P, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)y, (__nv_bfloat16*)y_lo, N, C, P, cpad, coff, div_scale);
+  return check_launch("planar_to_cl_kernel");
+}
+
+extern "C" int b2d_cl_to_planar(const void* x, const void* x_lo, float* y, int32_t N, int32_t C, int64_t P, int32_t cstride,
+                                int32_t coff, void* stream) {
+  if (!x || !y || N < 1 || C < 1 || P < 1 || coff < 0 || coff + C > cstride) return set_error(B2D_E_INVALID, "b2d_cl_to_planar: bad argument");
+  cl_to_planar_kernel<<<grid_for((long long)N * P, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)x_lo, y, N, C, P, cstride, coff);
+  return check_launch("cl_to_planar_kernel");
+}

@@ -1,0 +1,263 @@
+"""Host-side plumbing over the C ABI: weight repacking (reference layouts -> K-major bf16 GEMM
+operands), conv plans, channels-last activation buffers and launch programs.
+
+PyTorch is used for device memory, streams and one-off weight preprocessing only; every
+per-step operation is a libb2d kernel launched through diffusion_model_project_b200._lib.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, call, ptr
+
+BF16 = torch.bfloat16
+
+
+def pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def split_hi_lo(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 -> (bf16 hi, bf16 lo) with hi + lo ~= w to ~2^-16 relative (the "fp32x" mode)."""
+    hi = w.to(BF16)
+    lo = (w - hi.float()).to(BF16)
+    return hi, lo
+
+
+@dataclass
+class Act:
+    """Channels-last activation [N, D, H, W, C] bf16 (C multiple of 64; `lo` only in fp32x mode)."""
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor] = None
+
+    @property
+    def shape(self):
+        return tuple(self.hi.shape)
+
+    @property
+    def C(self):
+        return self.hi.shape[-1]
+
+
+def new_act(N, D, H, W, C, device, split=False, zero=False) -> Act:
+    mk = torch.zeros if zero else torch.empty
+    hi = mk((N, D, H, W, C), dtype=BF16, device=device)
+    lo = mk((N, D, H, W, C), dtype=BF16, device=device) if split else None
+    return Act(hi, lo)
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing: [rows][K] with K = sum_seg ntaps * cin_pad[seg]; k = kbase[seg] + tap*cin_pad + c
+# ------------------------------------------------------------------------------------------------
+def _pack_taps(w_tap_last: torch.Tensor, seg_sizes: Sequence[int]) -> Tuple[torch.Tensor, List[int], List[int]]:
+    """w_tap_last: fp32 [rows, ntaps, cin_total].  Returns ([rows, K] fp32, kbase per seg, cin_pad per seg)."""
+    rows, ntaps, _ = w_tap_last.shape
+    blocks, kbase, cpads = [], [], []
+    c0, k = 0, 0
+    for cs in seg_sizes:
+        cp = pad64(cs)
+        blk = torch.zeros(rows, ntaps, cp, dtype=torch.float32, device=w_tap_last.device)
+        blk[:, :, :cs] = w_tap_last[:, :, c0:c0 + cs]
+        blocks.append(blk.reshape(rows, ntaps * cp))
+        kbase.append(k)
+        cpads.append(cp)
+        k += ntaps * cp
+        c0 += cs
+    return torch.cat(blocks, dim=1), kbase, cpads
+
+
+def taps_3x3():
+    return [(0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+
+
+def taps_3x3x3(pad_hw: int = 1):
+    """pad_hw=1: 'same' conv; pad_hw=0: the stride-(1,2,2) down conv after F.pad(0,1,0,1,1,1)."""
+    return [(kz - 1, ky - pad_hw, kx - pad_hw) for kz in range(3) for ky in range(3) for kx in range(3)]
+
+
+@dataclass
+class PackedWeight:
+    w: torch.Tensor            # bf16 [rows_pad, ktot]  (fp32x: K = [hi blocks | lo blocks])
+    kbase: List[int]           # per activation segment
+    cin_pad: List[int]
+    ktot: int
+    rows: int                  # valid rows (nphase * cout)
+    bias: Optional[torch.Tensor]
+    taps: List[Tuple[int, int, int]]
+    split: bool = False
+    kbase_lo: Optional[List[int]] = None
+
+
+def pack_weight(w_rows_taps_c: torch.Tensor, seg_sizes: Sequence[int], taps, bias, device, split=False, row_mult=16) -> PackedWeight:
+    """w_rows_taps_c: fp32 [rows, ntaps, cin_total] (CPU or GPU)."""
+    w_rows_taps_c = w_rows_taps_c.to(device=device, dtype=torch.float32)
+    mat, kbase, cpads = _pack_taps(w_rows_taps_c, seg_sizes)
+    rows = mat.shape[0]
+    rows_pad = (rows + row_mult - 1) // row_mult * row_mult
+    if rows_pad != rows:
+        mat = torch.cat([mat, torch.zeros(rows_pad - rows, mat.shape[1], device=device)], 0)
+    k1 = mat.shape[1]
+    kb_lo = None
+    if split:
+        hi, lo = split_hi_lo(mat)
+        wq = torch.cat([hi, lo], dim=1).contiguous()
+        kb_lo = [k + k1 for k in kbase]
+    else:
+        wq = mat.to(BF16).contiguous()
+    b = None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous()
+    return PackedWeight(wq, kbase, cpads, wq.shape[1], rows, b, list(taps), split, kb_lo)
+
+
+def pack_conv2d(w, seg_sizes, bias, device, split=False):
+    """nn.Conv2d weight [Cout, Cin, 3, 3] (unet/blocks.py:29-36)."""
+    co, ci, kh, kw = w.shape
+    assert (kh, kw) == (3, 3)
+    return pack_weight(w.permute(0, 2, 3, 1).reshape(co, 9, ci), seg_sizes, taps_3x3(), bias, device, split)
+
+
+def pack_conv3d(w, bias, device, split=False, down=False):
+    """nn.Conv3d weight [Cout, Cin, k, k, k], k in {1, 3} (vae/blocks.py:155-169, encoder.py:45,56)."""
+    co, ci, kd, kh, kw = w.shape
+    if kd == 1:
+        return pack_weight(w.reshape(co, 1, ci), [ci], [(0, 0, 0)], bias, device, split)
+    return pack_weight(w.permute(0, 2, 3, 4, 1).reshape(co, 27, ci), [ci], taps_3x3x3(0 if down else 1), bias, device, split)
+
+
+def pack_convT2x2(w, bias, device, split=False):
+    """nn.ConvTranspose2d k2 s2 weight [Cin, Cout, 2, 2] (unet/blocks.py:128-133): 4 phase GEMMs, rows phase-major."""
+    ci, co, kh, kw = w.shape
+    assert (kh, kw) == (2, 2)
+    return pack_weight(w.permute(2, 3, 1, 0).reshape(4 * co, 1, ci), [ci], [(0, 0, 0)], bias, device, split)
+
+
+def pack_linear(w, bias, device, split=False):
+    """nn.Linear / Conv1d-k1 weight [out, in]."""
+    return pack_weight(w.reshape(w.shape[0], 1, -1), [w.reshape(w.shape[0], -1).shape[1]], [(0, 0, 0)], bias, device, split)
+
+
+# ------------------------------------------------------------------------------------------------
+# conv plans
+# ------------------------------------------------------------------------------------------------
+class ConvPlan:
+    """Owns a b2d_conv_plan and keeps every tensor whose address is baked into it alive."""
+
+    def __init__(self, inputs: Sequence[Act], pw: PackedWeight, out, *, cout: int, nphase: int = 1, stride: int = 1,
+                 out_mode: int = 0, out_geom=None, residual: Optional[Act] = None, stats: Optional[torch.Tensor] = None,
+                 stats_cpg: int = 0, out_scale=None, out_mask=None, block_n: int = 0, out_cstride=None, out_coff: int = 0):
+        N, D, H, W, _ = inputs[0].shape
+        d = ConvDesc()
+        split = pw.split
+        segs: List[Tuple[torch.Tensor, int, int]] = []  # (tensor, cin_pad, kbase)
+        for i, a in enumerate(inputs):
+            assert a.shape[:4] == (N, D, H, W) and a.C == pw.cin_pad[i], (a.shape, pw.cin_pad, i)
+            segs.append((a.hi, a.C, pw.kbase[i]))
+        if split:
+            for i, a in enumerate(inputs):
+                assert a.lo is not None
+                segs.append((a.hi, a.C, pw.kbase_lo[i]))   # A_hi * W_lo
+                segs.append((a.lo, a.C, pw.kbase[i]))      # A_lo * W_hi
+        assert len(segs) <= _lib.B2D_MAX_SEG
+        d.nseg = len(segs)
+        for i, (t, c, kb) in enumerate(segs):
+            d.in_[i] = t.data_ptr()
+            d.cin[i] = c
+            d.kbase[i] = kb
+        d.N, d.D, d.H, d.W = N, D, H, W
+        d.ntaps = len(pw.taps)
+        for i, (dz, dy, dx) in enumerate(pw.taps):
+            d.tap_dz[i], d.tap_dy[i], d.tap_dx[i] = dz, dy, dx
+        d.stride_h = d.stride_w = stride
+        OH, OW = (H // stride, W // stride)
+        d.OH, d.OW = OH, OW
+        d.weight = pw.w.data_ptr()
+        d.wrows, d.ktot = pw.w.shape
+        d.cout, d.nphase = cout, nphase
+        d.bias = ptr(pw.bias)
+        out_hi = out.hi if isinstance(out, Act) else out
+        d.out = out_hi.data_ptr()
+        d.out_lo = ptr(out.lo) if isinstance(out, Act) else None
+        d.out_mode = out_mode
+        if out_geom is None:
+            up = 2 if nphase == 4 else 1
+            out_geom = (OH * up, OW * up, up, up, 0, 0)
+        d.out_H, d.out_W, d.out_sy, d.out_sx, d.out_oy, d.out_ox = out_geom
+        if out_cstride is None:
+            out_cstride = out_hi.shape[-1] if out_mode != 1 else cout
+        d.out_cstride, d.out_coff = out_cstride, out_coff
+        if residual is not None:
+            d.residual = residual.hi.data_ptr()
+            d.residual_lo = ptr(residual.lo)
+            d.res_cstride = residual.C
+        d.stats = ptr(stats)
+        d.stats_cpg = stats_cpg
+        d.out_scale = ptr(out_scale)
+        d.out_mask = ptr(out_mask)
+        d.block_n = block_n
+        self._keep = (inputs, pw, out, residual, stats, out_scale, out_mask)
+        self.desc = d
+        self.handle = C.c_void_p()
+        _lib.check(_lib.lib().b2d_conv_plan_create(C.byref(d), C.byref(self.handle)), "b2d_conv_plan_create")
+        self.flops = 2.0 * N * D * OH * OW * cout * nphase * sum(len(pw.taps) * c for (_, c, _) in segs[:len(inputs)])
+
+    def info(self):
+        gm, gn, bn, kb = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().b2d_conv_plan_info(self.handle, C.byref(gm), C.byref(gn), C.byref(bn), C.byref(kb)))
+        return dict(grid_m=gm.value, grid_n=gn.value, block_n=bn.value, kblocks=kb.value)
+
+    def run(self, stream: int):
+        call("b2d_conv_run", self.handle, stream)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().b2d_conv_plan_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise launches
+# ------------------------------------------------------------------------------------------------
+def gn_apply(x: Act, y: Act, stats: torch.Tensor, cpg: int, gamma, beta, act: bool, stream: int, *, temb=None, temb_row=None,
+             temb_row_stride=0, temb_col=0, stats_out=None, eps=1e-5):
+    N, D, H, W, Cc = x.shape
+    call("b2d_gn_apply", ptr(x.hi), ptr(x.lo), ptr(y.hi), ptr(y.lo), N, D * H * W, Cc, ptr(stats), cpg, ptr(gamma), ptr(beta),
+         eps, 1 if act else 0, ptr(temb), ptr(temb_row), temb_row_stride, 0 if temb is None else temb.shape[1], temb_col,
+         ptr(stats_out), stream)
+
+
+def maxpool_stats(x: Act, y: Act, stats: torch.Tensor, stream: int):
+    N, D, H, W, Cc = x.shape
+    assert D == 1
+    call("b2d_maxpool2x2_stats", ptr(x.hi), ptr(x.lo), ptr(y.hi), ptr(y.lo), N, H, W, Cc, ptr(stats), stream)
+
+
+def upsample2x(x: Act, y: Act, stream: int):
+    N, D, H, W, Cc = x.shape
+    call("b2d_upsample2x_nearest", ptr(x.hi), ptr(y.hi), N * D, H, W, Cc, stream)
+    if x.lo is not None:
+        call("b2d_upsample2x_nearest", ptr(x.lo), ptr(y.lo), N * D, H, W, Cc, stream)
+
+
+class Program:
+    """A recorded sequence of kernel launches over static buffers (replayable, graph-capturable)."""
+
+    def __init__(self):
+        self.steps: List[Tuple[str, Callable[[int], None]]] = []
+        self.flops = 0.0
+
+    def add(self, name: str, fn: Callable[[int], None]):
+        self.steps.append((name, fn))
+
+    def run(self, stream: int):
+        for _, fn in self.steps:
+            fn(stream)
+
+    def __len__(self):
+        return len(self.steps)

@@ -1,0 +1,240 @@
+"""B200DualVAE -- drop-in for the inference branches of the reference's DualBranchVAE
+(VAE_model/src/dual_vae/model.py:32-243; Encoder vae/encoder.py:9-145, Decoder vae/decoder.py:10-151,
+ResidualBlock vae/blocks.py:136-186): E2D `encode_2d_deterministic`, D3D `decode_3d`, plus
+E3D `encode_3d_deterministic` (same engine).  All Conv3d layers run on the tcgen05 implicit-GEMM
+engine in NDHWC bf16; GroupNorm(32) sums come out of the producing conv's epilogue.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, engine
+from .engine import Act, ConvPlan, Program, new_act, pad64
+
+
+class _Branch:
+    """Packed weights of one Encoder or Decoder."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, kind: str, device, split: bool):
+        self.kind = kind
+        self.w: Dict[str, object] = {}
+        g = lambda k: sd[prefix + k].detach().to("cpu", torch.float32)
+
+        def conv(name, down=False):
+            self.w[name] = engine.pack_conv3d(g(f"{name}.weight"), g(f"{name}.bias"), device, split, down=down)
+
+        def norm(name):
+            self.w[name] = (g(f"{name}.weight").to(device).contiguous(), g(f"{name}.bias").to(device).contiguous())
+
+        def res(name):
+            norm(f"{name}.norm1"); conv(f"{name}.conv1"); norm(f"{name}.norm2"); conv(f"{name}.conv2")
+            if (prefix + f"{name}.residual_layer.weight") in sd:
+                conv(f"{name}.residual_layer")
+
+        conv("conv_in")
+        for r in ("res1_1", "res1_2", "res2_1", "res2_2", "res3_1", "res3_2"):
+            res(r)
+        if kind == "encoder":
+            conv("down1", down=True); conv("down2", down=True)
+        else:
+            conv("conv_up1"); conv("conv_up2")
+        norm("norm_out"); conv("conv_out")
+        self.cin = g("conv_in.weight").shape[1]
+        self.cout = g("conv_out.weight").shape[0]
+
+
+class _Builder:
+    """Records a launch program for one branch over static NDHWC buffers."""
+
+    def __init__(self, B, device, split):
+        self.B, self.dev, self.split = B, device, split
+        self.prog = Program()
+        self.keep: List[object] = []
+        self.stats_buf = torch.zeros(B * 32 * 2 * 40, dtype=torch.float64, device=device)
+        self.stats_used = 0
+
+    def stats(self):
+        n = self.B * 32 * 2
+        v = self.stats_buf[self.stats_used:self.stats_used + n]
+        self.stats_used += n
+        assert self.stats_used <= self.stats_buf.numel()
+        return v
+
+    def conv(self, name, x: Act, pw, cout, *, stride=1, want_stats=True, residual=None, out=None, **kw):
+        N, D, H, W, _ = x.shape
+        if out is None:
+            out = new_act(N, D, H // stride, W // stride, cout, self.dev, self.split)
+        st = self.stats() if want_stats else None
+        plan = ConvPlan([x], pw, out, cout=cout, stride=stride, residual=residual, stats=st,
+                        stats_cpg=(cout // 32) if want_stats else 0, **kw)
+        self.prog.flops += plan.flops
+        self.prog.add(name, plan.run)
+        self.keep.append(plan)
+        return out, st
+
+    def gn_silu(self, name, x: Act, st, gnw, inplace: bool):
+        y = x if inplace else new_act(*x.shape, self.dev, self.split)
+        g, b = gnw
+        C = x.C
+        self.prog.add(name, lambda s: engine.gn_apply(x, y, st, C // 32, g, b, True, s))
+        return y
+
+    def res(self, w, name, x: Act, st_x, cin, cout, want_stats=True):
+        """vae/blocks.py:173-186."""
+        h = self.gn_silu(f"{name}.norm1", x, st_x, w[f"{name}.norm1"], inplace=False)
+        r, st_r = self.conv(f"{name}.conv1", h, w[f"{name}.conv1"], cout)
+        r = self.gn_silu(f"{name}.norm2", r, st_r, w[f"{name}.norm2"], inplace=True)
+        skip = x
+        if f"{name}.residual_layer" in w:
+            skip, _ = self.conv(f"{name}.residual_layer", x, w[f"{name}.residual_layer"], cout, want_stats=False)
+        # reuse h's storage for the block output when shapes allow (h is dead after conv1)
+        out = h if cin == cout else None
+        return self.conv(f"{name}.conv2", r, w[f"{name}.conv2"], cout, residual=skip, want_stats=want_stats, out=out)
+
+    def finish(self):
+        used, buf = self.stats_used, self.stats_buf
+        self.prog.steps = [("stats.zero", lambda s: _lib.call("b2d_zero", buf.data_ptr(), used * 8, s))] + self.prog.steps
+        return self.prog
+
+
+class B200DualVAE:
+    def __init__(self, in_channels: int = 3, latent_channels: int = 8, kernel_size: int = 3, share_encoders: bool = False,
+                 share_decoders: bool = False, *, precision: str = "bf16", device="cuda"):
+        if kernel_size != 3:
+            raise NotImplementedError("B200DualVAE: kernel_size must be 3")
+        if precision not in ("bf16", "fp32x"):
+            raise ValueError("precision must be 'bf16' or 'fp32x'")
+        self.in_channels, self.latent_channels = in_channels, latent_channels
+        self.split = precision == "fp32x"
+        self.precision = precision
+        self.device = torch.device(device)
+        self.branches: Dict[str, _Branch] = {}
+        self._cache: Dict[tuple, dict] = {}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False):
+        """Reference DualBranchVAE keys (`encoder_2d.*`, `decoder_3d.*`, optionally `encoder_3d.*`);
+        branches absent from `sd` are simply not available."""
+        for b, kind in (("encoder_2d", "encoder"), ("encoder_3d", "encoder"), ("decoder_3d", "decoder"), ("decoder_2d", "decoder")):
+            if any(k.startswith(b + ".") for k in sd):
+                self.branches[b] = _Branch(sd, b + ".", kind, self.device, self.split)
+        self._cache.clear()
+        return self
+
+    # ------------------------------------------------------------------------------ programs
+    def build_encoder(self, branch: str, B, D, H, W, *, x_in: Optional[Act] = None, out=None, out_mode=1, out_coff=0,
+                      out_cout=None) -> dict:
+        """encoder.py:83-145.  out: planar fp32 [B][D][2*latent][h][w] (mode 1) or a channels-last Act
+        receiving the first `out_cout` channels (mu) at channel offset out_coff (mode 0)."""
+        if H % 4 or W % 4:
+            raise ValueError("encoder input H, W must be divisible by 4")
+        br = self.branches[branch]
+        w = br.w
+        bd = _Builder(B, self.device, self.split)
+        if x_in is None:
+            x_in = new_act(B, D, H, W, pad64(br.cin), self.device, self.split, zero=True)
+        x, st = bd.conv("conv_in", x_in, w["conv_in"], 128)
+        x, st = bd.res(w, "res1_1", x, st, 128, 128)
+        x, _ = bd.res(w, "res1_2", x, st, 128, 128, want_stats=False)
+        x, st = bd.conv("down1", x, w["down1"], 128, stride=2)
+        x, st = bd.res(w, "res2_1", x, st, 128, 256)
+        x, _ = bd.res(w, "res2_2", x, st, 256, 256, want_stats=False)
+        x, st = bd.conv("down2", x, w["down2"], 256, stride=2)
+        x, st = bd.res(w, "res3_1", x, st, 256, 512)
+        x, st = bd.res(w, "res3_2", x, st, 512, 512)
+        x = bd.gn_silu("norm_out", x, st, w["norm_out"], inplace=True)
+        h, wd = H // 4, W // 4
+        cout = br.cout if out_cout is None else out_cout
+        if out is None:
+            out = torch.empty((B, D, br.cout, h, wd), dtype=torch.float32, device=self.device)
+        kw = dict(out_mode=out_mode, out_coff=out_coff)
+        if out_mode == 1:
+            kw["out_cstride"] = br.cout
+        bd.conv("conv_out", x, w["conv_out"], cout, want_stats=False, out=out, **kw)
+        return dict(program=bd.finish(), x_in=x_in, out=out, keep=bd.keep, stats=bd.stats_buf)
+
+    def build_decoder(self, branch: str, B, D, h, w_, *, z_in: Optional[Act] = None, out=None, out_scale=None, out_mask=None) -> dict:
+        """decoder.py:79-151.  out: planar fp32 [B][D][3][H][W] (optionally * out_scale[c] * out_mask)."""
+        br = self.branches[branch]
+        w = br.w
+        bd = _Builder(B, self.device, self.split)
+        if z_in is None:
+            z_in = new_act(B, D, h, w_, pad64(br.cin), self.device, self.split, zero=True)
+        x, st = bd.conv("conv_in", z_in, w["conv_in"], 512)
+        x, st = bd.res(w, "res1_1", x, st, 512, 512)
+        x, _ = bd.res(w, "res1_2", x, st, 512, 512, want_stats=False)
+        for stage, (cin, cout, r1, r2, last) in enumerate(((512, 256, "res2_1", "res2_2", False), (256, 128, "res3_1", "res3_2", True)), 1):
+            N_, D_, H_, W_, _ = x.shape
+            up = new_act(N_, D_, 2 * H_, 2 * W_, cin, self.device, self.split)
+            bd.prog.add(f"up{stage}", lambda s, x=x, up=up: engine.upsample2x(x, up, s))
+            x, st = bd.conv(f"conv_up{stage}", up, w[f"conv_up{stage}"], cout)
+            x, st = bd.res(w, r1, x, st, cout, cout)
+            x, st = bd.res(w, r2, x, st, cout, cout, want_stats=last)
+        x = bd.gn_silu("norm_out", x, st, w["norm_out"], inplace=True)
+        H, W = 4 * h, 4 * w_
+        if out is None:
+            out = torch.empty((B, D, br.cout, H, W), dtype=torch.float32, device=self.device)
+        bd.conv("conv_out", x, w["conv_out"], br.cout, want_stats=False, out=out, out_mode=1, out_cstride=br.cout,
+                out_scale=out_scale, out_mask=out_mask)
+        return dict(program=bd.finish(), z_in=z_in, out=out, keep=bd.keep, stats=bd.stats_buf)
+
+    # ------------------------------------------------------------------------------ module API
+    def _encode(self, branch: str, x: torch.Tensor):
+        if branch not in self.branches:
+            raise RuntimeError(f"B200DualVAE: no weights loaded for {branch}")
+        if not x.is_cuda:
+            raise RuntimeError("B200DualVAE runs on a CUDA device only (no CPU fallback)")
+        B, C, D, H, W = x.shape
+        key = (branch, B, D, H, W)
+        st = self._cache.get(key)
+        if st is None:
+            st = self.build_encoder(branch, B, D, H, W)
+            self._cache = {key: st}
+        s = _lib.stream_ptr()
+        xi = st["x_in"]
+        x = x.contiguous().float()
+        _lib.call("b2d_planar_to_cl", x.data_ptr(), _lib.ptr(xi.hi), _lib.ptr(xi.lo), B, C, D * H * W, xi.C, 0, None, s)
+        st["program"].run(s)
+        o = st["out"].permute(0, 2, 1, 3, 4).contiguous()  # [B][D][16][h][w] -> (B,16,D,h,w)
+        mu, logvar = torch.chunk(o, 2, dim=1)
+        return mu, logvar
+
+    def encoder_2d(self, x):
+        """Encoder.forward -> (mu, logvar)  (vae/encoder.py:83-145)."""
+        return self._encode("encoder_2d", x)
+
+    def encode_2d_deterministic(self, x):
+        """dual_vae/model.py:225-233."""
+        mu, logvar = self._encode("encoder_2d", x)
+        return mu, (mu, torch.clamp(logvar, -10.0, 10.0))
+
+    def encode_3d_deterministic(self, x):
+        """dual_vae/model.py:235-243."""
+        mu, logvar = self._encode("encoder_3d", x)
+        return mu, (mu, torch.clamp(logvar, -10.0, 10.0))
+
+    def decode_3d(self, z: torch.Tensor) -> torch.Tensor:
+        """dual_vae/model.py:211-223: (B, latent, D, h, w) -> (B, 3, D, 4h, 4w)."""
+        if "decoder_3d" not in self.branches:
+            raise RuntimeError("B200DualVAE: no weights loaded for decoder_3d")
+        if not z.is_cuda:
+            raise RuntimeError("B200DualVAE runs on a CUDA device only (no CPU fallback)")
+        B, C, D, h, w = z.shape
+        key = ("decoder_3d", B, D, h, w)
+        st = self._cache.get(key)
+        if st is None:
+            st = self.build_decoder("decoder_3d", B, D, h, w)
+            self._cache = {key: st}
+        s = _lib.stream_ptr()
+        zi = st["z_in"]
+        z = z.contiguous().float()
+        _lib.call("b2d_planar_to_cl", z.data_ptr(), _lib.ptr(zi.hi), _lib.ptr(zi.lo), B, C, D * h * w, zi.C, 0, None, s)
+        st["program"].run(s)
+        return st["out"].permute(0, 2, 1, 3, 4).contiguous()
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter(())

@@ -1,0 +1,176 @@
+/*
+ * b2d.h -- C ABI of libb2d.so, the sm_100a kernels behind the latent-diffusion sampling path.
+ *
+ * The reference (Ruby-004/Diffusion_model_project) is pure Python/PyTorch and has no FFI: its
+ * hot path calls torch.nn modules, i.e. ATen -> cuDNN/cuBLAS/oneDNN.  Each entry point below
+ * replaces the ATen call sites listed next to it (file:line relative to the reference root).
+ * The Python host mirror (diffusion_model_project_b200/*.py) binds these with ctypes; see
+ * INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (B2D_E_*); never throws, never exits;
+ *     b2d_last_error() returns a thread-local message for the last failure on this thread;
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch's allocator); the library
+ *     allocates and frees nothing on the device and retains no pointer past the call, except
+ *     conv plans, which record the pointers given at creation (TMA descriptors embed addresses);
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises, so every call can be
+ *     captured into a CUDA graph;
+ *   - activations are channels-last: [N][D][H][W][C] (D = 1 for the UNet's 2-D maps), bf16,
+ *     with the channel count padded to a multiple of 64 (pad channels hold zeros).
+ */
+#ifndef B2D_H_
+#define B2D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B2D_API __attribute__((visibility("default")))
+#else
+#define B2D_API
+#endif
+
+#define B2D_VERSION 1
+#define B2D_MAX_SEG 6
+#define B2D_MAX_TAPS 27
+
+#define B2D_OK 0
+#define B2D_E_INVALID (-1)     /* bad argument / unsupported shape */
+#define B2D_E_CUDA (-2)        /* CUDA runtime or driver error     */
+#define B2D_E_UNSUPPORTED (-3) /* not an sm_100 device, driver too old */
+
+B2D_API int b2d_version(void);
+B2D_API const char* b2d_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Scheduler step (DDPM p_sample / DDIM ddim_sample), one fused elementwise kernel.
+ * Replaces Diffusion_model/src/diffusion.py:152-188 (p_sample), :195-234 (ddim_sample),
+ * :103-125 (predict_x0_from_noise) -- ~10-12 ATen elementwise kernels + randn_like each.
+ *
+ *   x0  = clamp((x_t - b*eps) / a, clip_lo, clip_hi)            (clamp only if clip != 0)
+ *   out = c1*x0 + c2*(kind==0 ? x_t : eps)  [+ s*z if s != 0]
+ *
+ * coef: device array of rows {a, b, c1, c2, s, 0, 0, 0}; the row used is
+ * (step_idx ? *step_idx : 0) + step_off, so a captured graph can advance a device counter.
+ * z = noise[i] if noise != NULL, else (if s != 0) N(0,1) from Philox4x32-10(seed, row, i).
+ * Optional second output for the fused loop: x_bf16[(i / group) * group_stride + i % group].
+ * If step_inc != 0 the kernel's last block adds step_inc to *step_idx after all reads.
+ * ---------------------------------------------------------------------------------------- */
+B2D_API int b2d_scheduler_step(int kind, const float* x_t, const float* eps, const float* noise, float* x_out,
+                       int64_t n_elem, const float* coef, int* step_idx, int step_off, int step_inc,
+                       int clip, float clip_lo, float clip_hi, void* x_bf16, int group, int group_stride,
+                       uint64_t seed, void* stream);
+
+/* q_sample (diffusion.py:78-101): out = a*x0 + b*noise with per-image a,b (device [n_img]). */
+B2D_API int b2d_q_sample(const float* x0, const float* noise, float* out, const float* a, const float* b,
+                 int64_t n_img, int64_t per_img, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05/TMEM with TMA-staged (zero-filled halo) tiles.
+ * Replaces nn.Conv2d (unet/blocks.py:29-36, unet/models.py:120-128), nn.ConvTranspose2d k2 s2
+ * (unet/blocks.py:128-133), nn.Conv3d k3/k1, stride (1,1,1)/(1,2,2) (vae/blocks.py:155-169,
+ * vae/encoder.py:30,45,56,68, vae/decoder.py:31,47,59,71), nn.Linear / nn.Conv1d k1
+ * (unet/blocks.py:196-207: in_proj, out_proj, proj_out), torch.cat along channels
+ * (unet/models.py:177) and the residual add (vae/blocks.py:185, unet/blocks.py:234).
+ *
+ * GEMM view: M = output positions (tiles of 128 forming a box in (n,d,y,x)), N = cout,
+ * K = sum over segments s, taps t of cin[s]; weight row-major [rows][ktot] bf16 with
+ * k = kbase[s] + t*cin[s] + c; normally kbase[s] = ntaps * sum_{s'<s} cin[s'] (the hi/lo
+ * split "fp32x" mode points two activation segments at the same weight block).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct b2d_conv_desc {
+  int32_t nseg;                    /* channel segments (torch.cat without the copy)            */
+  const void* in[B2D_MAX_SEG];     /* bf16 [N][D][H][W][cin[s]]                                  */
+  int32_t cin[B2D_MAX_SEG];        /* multiple of 64                                            */
+  int32_t kbase[B2D_MAX_SEG];      /* K offset of the weight block multiplied with in[s]        */
+  int32_t N, D, H, W;              /* input extent                                              */
+  int32_t ntaps;
+  int8_t tap_dz[B2D_MAX_TAPS], tap_dy[B2D_MAX_TAPS], tap_dx[B2D_MAX_TAPS]; /* input offsets     */
+  int32_t stride_h, stride_w;      /* input coord = out*stride + tap offset                     */
+  int32_t OH, OW;                  /* conv output extent per (n,d)                              */
+  const void* weight;              /* bf16 [wrows][ktot]; wrows >= nphase*cout rounded to block_n */
+  int32_t wrows, ktot;
+  int32_t cout;                    /* valid output channels (per phase)                         */
+  int32_t nphase;                  /* 1, or 4: ConvTranspose2d k2 s2, weight rows phase-major   */
+  const float* bias;               /* [cout] or NULL                                            */
+  void* out;                       /* see out_mode                                              */
+  void* out_lo;                    /* optional bf16 residual part (x - bf16(x)), mode 0, or NULL */
+  int32_t out_mode;                /* 0 bf16 NDHWC, 1 fp32 planar [N][D][C][H][W], 2 fp32 NDHWC */
+  int32_t out_H, out_W;            /* extent of the output tensor                               */
+  int32_t out_sy, out_sx, out_oy, out_ox; /* out pixel = oy*out_sy + out_oy (+ phase)           */
+  int32_t out_cstride, out_coff;   /* channel stride / offset of the output tensor              */
+  const void* residual;            /* bf16, same geometry as out (cstride res_cstride) or NULL  */
+  const void* residual_lo;
+  int32_t res_cstride;
+  double* stats;                   /* [N][cout/stats_cpg][2] (sum, sumsq) atomically added, or NULL */
+  int32_t stats_cpg;               /* channels per GroupNorm group                              */
+  const float* out_scale;          /* per-channel multiplier (mode 1) or NULL                   */
+  const float* out_mask;           /* fp32 [N][D][out_H][out_W] multiplier (mode 1) or NULL     */
+  int32_t block_n;                 /* 0 = auto, else 16/64/128/256                              */
+  int32_t reserved[7];
+} b2d_conv_desc;
+
+typedef struct b2d_conv_plan b2d_conv_plan;
+B2D_API int b2d_conv_plan_create(const b2d_conv_desc* desc, b2d_conv_plan** plan);
+B2D_API int b2d_conv_plan_destroy(b2d_conv_plan* plan);
+B2D_API int b2d_conv_run(const b2d_conv_plan* plan, void* stream);
+/* number of CTAs / block_n the plan launches with (introspection for tests and the bench) */
+B2D_API int b2d_conv_plan_info(const b2d_conv_plan* plan, int32_t* grid_m, int32_t* grid_n, int32_t* block_n, int32_t* kblocks);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm apply (+SiLU, + time-embedding add), stats come from the producer's epilogue.
+ * Replaces nn.GroupNorm + nn.SiLU + the broadcast add (unet/blocks.py:37-47,98-105,134-143,
+ * 165-174,192-221; vae/blocks.py:152-161,177-183; vae/decoder.py:70,137-138; encoder.py:67,133-134).
+ *   y = act(gamma[c]*(x-mean_g)*rstd_g + beta[c]) + temb[row[n]*temb_ld + temb_col + c]
+ * x, y: bf16 [N][P][C] (C multiple of 8; cstride = C).  stats: [N][C/cpg][2] sums over
+ * count = cpg*P elements.  stats_out (optional): GN(1,C) sums of y, atomically added.
+ * ---------------------------------------------------------------------------------------- */
+B2D_API int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int64_t P, int32_t C,
+                 const double* stats, int32_t cpg, const float* gamma, const float* beta, float eps, int32_t act,
+                 const float* temb_table, const int32_t* temb_row, int32_t temb_row_stride, int32_t temb_ld,
+                 int32_t temb_col, double* stats_out, void* stream);
+
+/* MaxPool2d(2,2) (unet/blocks.py:161-164,170) + GN(1,C) sums of the pooled map. bf16 NHWC. */
+B2D_API int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int32_t H, int32_t W,
+                         int32_t C, double* stats, void* stream);
+
+/* nearest-neighbour (1,2,2) upsample, nn.Upsample (vae/decoder.py:46,58). bf16 NDHWC, ND = N*D. */
+B2D_API int b2d_upsample2x_nearest(const void* x, void* y, int32_t ND, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* layout/precision plumbing at the module boundary:
+ * planar fp32 [N][C][P] (optionally divided by scale[c], MaxNormalizer normalizer.py:46-51)
+ * -> channels-last bf16 [N][P][cpad] written at channel offset coff (pad channels untouched). */
+B2D_API int b2d_planar_to_cl(const float* x, void* y, void* y_lo, int32_t N, int32_t C, int64_t P, int32_t cpad, int32_t coff,
+                     const float* div_scale, void* stream);
+/* channels-last bf16 [N][P][cstride] (channels coff..coff+C) -> planar fp32 [N][C][P] */
+B2D_API int b2d_cl_to_planar(const void* x, const void* x_lo, float* y, int32_t N, int32_t C, int64_t P, int32_t cstride,
+                     int32_t coff, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused small-sequence attention core: softmax(q k^T / sqrt(d)) v per (image, head).
+ * Replaces the scaled-dot-product part of nn.MultiheadAttention (unet/blocks.py:196-227).
+ * qkv: bf16 [N][T][3C] (q | k | v, heads contiguous inside each), out: bf16 [N][T][C].
+ * ---------------------------------------------------------------------------------------- */
+B2D_API int b2d_attention(const void* qkv, const void* qkv_lo, void* out, void* out_lo, int32_t N, int32_t T, int32_t C,
+                  int32_t heads, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Exact Euclidean distance transform of binary images (distance of every non-zero pixel to the
+ * nearest zero pixel), replacing the SciPy host round trip (predictor.py:1096-1116), and the
+ * bilinear (align_corners=False) resize that follows it (predictor.py:951).
+ * ---------------------------------------------------------------------------------------- */
+/* out: 2*n_img*H*W floats -- the result in the first half, the second half is scratch. */
+B2D_API int b2d_edt2d(const float* img, float* out, int32_t n_img, int32_t H, int32_t W, void* stream);
+B2D_API int b2d_bilinear_resize(const float* x, float* y, int32_t n_img, int32_t H, int32_t W, int32_t OH, int32_t OW,
+                        void* stream);
+
+/* fill helpers used by the fused loop (graph-capturable) */
+B2D_API int b2d_zero(void* p, int64_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2D_H_ */

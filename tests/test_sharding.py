@@ -1,0 +1,55 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes shard a batch and gather it back."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from diffusion_model_project_b200 import sharding
+
+
+def test_shard_range_covers_batch():
+    for B in (1, 2, 7, 8, 64):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_range(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_range(4, 2, 2)
+
+
+class _FakePredictor:
+    def predict_ddim(self, img, v2d, noise=None, **kw):
+        return v2d * 2 + (0 if noise is None else noise.reshape(v2d.shape[0], v2d.shape[1], -1).sum(-1)[:, :, None, None, None])
+
+
+def _worker(rank, world, port, B):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        img = torch.rand(B, 3, 1, 4, 4, generator=g)
+        v2d = torch.rand(B, 3, 3, 4, 4, generator=g)
+        noise = torch.rand(B * 3, 2, 2, 2, generator=g)
+        full = sharding.predict_sharded(_FakePredictor(), img, v2d, noise)
+        ref = _FakePredictor().predict_ddim(img, v2d, noise)
+        assert full.shape == ref.shape and torch.allclose(full, ref)
+        only0 = sharding.predict_sharded(_FakePredictor(), img, v2d, None, dst=0)
+        assert (only0 is None) == (rank != 0)
+        if rank == 0:
+            assert torch.allclose(only0, v2d * 2)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [4, 5])
+def test_gloo_world2_shard_and_gather(B):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, B), nprocs=2, join=True)
