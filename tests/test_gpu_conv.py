@@ -1,0 +1,178 @@
+"""tcgen05 implicit-GEMM conv engine vs plain PyTorch fp32 (TF32 off) on bf16-rounded operands.
+Tolerance: the engine multiplies exact bf16 products and accumulates in fp32, so against an fp32
+reference on the same rounded operands max|err|/max|ref| <= 1e-2 is dominated by the bf16 rounding of
+the stored output (2^-9); fp32 outputs and the fp32x (hi/lo split) mode are held to 2e-4."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffusion_model_project_b200 import engine
+from diffusion_model_project_b200.engine import ConvPlan, new_act
+from util import bf16_round, from_act, no_tf32, rel_err, stats_ref, to_act
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda"
+TOL_BF16 = 1e-2
+TOL_F32 = 2e-4
+
+
+def _rnd(g, *shape, scale=1.0):
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("bn,cout,K", [(16, 8, 64), (16, 3, 128), (64, 64, 64), (64, 192, 256), (128, 256, 512), (256, 512, 192)])
+def test_gemm_block_n_variants(bn, cout, K):
+    no_tf32()
+    g = torch.Generator().manual_seed(bn + K)
+    x = bf16_round(_rnd(g, 3, K, 1, 16, 16))
+    w = bf16_round(_rnd(g, cout, K, scale=K ** -0.5))
+    b = _rnd(g, cout)
+    pw = engine.pack_linear(w, b, DEV)
+    out = torch.zeros(3, 16, 16, max(cout, 4), device=DEV)
+    plan = ConvPlan([to_act(x)], pw, out, cout=cout, out_mode=2, out_cstride=out.shape[-1], block_n=bn)
+    assert plan.info()["block_n"] == bn
+    plan.run(_stream())
+    ref = F.conv2d(x[:, :, 0], w[:, :, None, None], b)
+    assert rel_err(out[..., :cout].permute(0, 3, 1, 2), ref) < TOL_F32
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 128, 64, 64), (11, 128, 128, 4, 4), (5, 64, 64, 2, 2), (7, 64, 64, 1, 1),
+                                   (3, 256, 64, 8, 8), (2, 17, 64, 32, 32), (22, 512, 128, 4, 4), (1, 64, 64, 16, 48)])
+def test_conv2d_3x3_zero_padding_and_gn_sums(shape):
+    no_tf32()
+    N, ci, co, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = bf16_round(_rnd(g, N, ci, 1, H, W))
+    w = bf16_round(_rnd(g, co, ci, 3, 3, scale=(9 * ci) ** -0.5))
+    pw = engine.pack_conv2d(w, [ci], None, DEV)
+    out = new_act(N, 1, H, W, co, DEV)
+    st = torch.zeros(N, 1, 2, dtype=torch.float64, device=DEV)
+    ConvPlan([to_act(x)], pw, out, cout=co, stats=st, stats_cpg=co).run(_stream())
+    ref = F.conv2d(x[:, :, 0], w, None, padding=1)
+    assert rel_err(from_act(out, co)[:, :, 0], ref) < TOL_BF16
+    sref = stats_ref(ref[:, :, None], 1)
+    assert ((st - sref).abs().max() / sref.abs().max()).item() < 1e-4
+
+
+def test_concat_as_two_k_segments():
+    no_tf32()
+    g = torch.Generator().manual_seed(3)
+    N, c, H, W = 3, 128, 16, 16
+    skip, up = bf16_round(_rnd(g, N, c, 1, H, W)), bf16_round(_rnd(g, N, c, 1, H, W))
+    w = bf16_round(_rnd(g, c, 2 * c, 3, 3, scale=(18 * c) ** -0.5))
+    pw = engine.pack_conv2d(w, [c, c], None, DEV)
+    out = new_act(N, 1, H, W, c, DEV)
+    ConvPlan([to_act(skip), to_act(up)], pw, out, cout=c).run(_stream())
+    ref = F.conv2d(torch.cat((skip, up), 1)[:, :, 0], w, None, padding=1)  # unet/models.py:177
+    assert rel_err(from_act(out, c)[:, :, 0], ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("shape", [(3, 128, 64, 8, 8), (11, 2048, 1024, 2, 2), (2, 128, 64, 32, 32), (5, 256, 128, 1, 1)])
+def test_conv_transpose_2x2(shape):
+    no_tf32()
+    N, ci, co, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = bf16_round(_rnd(g, N, ci, 1, H, W))
+    w = bf16_round(_rnd(g, ci, co, 2, 2, scale=ci ** -0.5))
+    b = _rnd(g, co)
+    pw = engine.pack_convT2x2(w, b, DEV)
+    out = new_act(N, 1, 2 * H, 2 * W, co, DEV)
+    st = torch.zeros(N, 1, 2, dtype=torch.float64, device=DEV)
+    ConvPlan([to_act(x)], pw, out, cout=co, nphase=4, stats=st, stats_cpg=co).run(_stream())
+    ref = F.conv_transpose2d(x[:, :, 0], w, b, stride=2)
+    assert rel_err(from_act(out, co)[:, :, 0], ref) < TOL_BF16
+    sref = stats_ref(ref[:, :, None], 1)
+    assert ((st - sref).abs().max() / sref.abs().max()).item() < 1e-4
+
+
+@pytest.mark.parametrize("down", [False, True])
+@pytest.mark.parametrize("shape", [(2, 128, 128, 3, 16, 16), (1, 64, 256, 11, 8, 8), (2, 128, 128, 3, 4, 4), (1, 3, 128, 2, 32, 32),
+                                   (1, 512, 512, 2, 8, 8)])
+def test_conv3d_and_strided_down(shape, down):
+    no_tf32()
+    N, ci, co, D, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + down)
+    x = bf16_round(_rnd(g, N, ci, D, H, W))
+    w = bf16_round(_rnd(g, co, ci, 3, 3, 3, scale=(27 * ci) ** -0.5))
+    b = _rnd(g, co)
+    pw = engine.pack_conv3d(w, b, DEV, down=down)
+    s_ = 2 if down else 1
+    out = new_act(N, D, H // s_, W // s_, co, DEV)
+    st = torch.zeros(N, 32, 2, dtype=torch.float64, device=DEV)
+    ConvPlan([to_act(x)], pw, out, cout=co, stride=s_, stats=st, stats_cpg=co // 32).run(_stream())
+    ref = F.conv3d(F.pad(x, (0, 1, 0, 1, 1, 1)), w, b, stride=(1, 2, 2)) if down else F.conv3d(x, w, b, padding=1)
+    assert rel_err(from_act(out, co), ref) < TOL_BF16
+    sref = stats_ref(ref, 32)
+    assert ((st - sref).abs().max() / sref.abs().max()).item() < 1e-4
+
+
+def test_residual_add_and_1x1x1():
+    no_tf32()
+    g = torch.Generator().manual_seed(11)
+    N, ci, co, D, H, W = 2, 128, 256, 2, 8, 8
+    x = bf16_round(_rnd(g, N, ci, D, H, W))
+    r = bf16_round(_rnd(g, N, co, D, H, W))
+    w = bf16_round(_rnd(g, co, ci, 1, 1, 1, scale=ci ** -0.5))
+    b = _rnd(g, co)
+    pw = engine.pack_conv3d(w, b, DEV)
+    out = new_act(N, D, H, W, co, DEV)
+    ConvPlan([to_act(x)], pw, out, cout=co, residual=to_act(r)).run(_stream())
+    assert rel_err(from_act(out, co), F.conv3d(x, w, b) + r) < TOL_BF16
+
+
+def test_planar_output_with_scale_and_mask():
+    no_tf32()
+    g = torch.Generator().manual_seed(12)
+    N, ci, co, D, H, W = 2, 128, 3, 2, 16, 16
+    x = bf16_round(_rnd(g, N, ci, D, H, W))
+    w = bf16_round(_rnd(g, co, ci, 3, 3, 3, scale=(27 * ci) ** -0.5))
+    b = _rnd(g, co)
+    scale = torch.tensor([0.01, 0.005, 0.002], device=DEV)
+    mask = (torch.rand(N, D, H, W, generator=g) > 0.4).float().to(DEV)
+    out = torch.zeros(N, D, co, H, W, device=DEV)
+    ConvPlan([to_act(x)], engine.pack_conv3d(w, b, DEV), out, cout=co, out_mode=1, out_cstride=co, out_scale=scale,
+             out_mask=mask).run(_stream())
+    ref = F.conv3d(x, w, b, padding=1) * scale.view(1, 3, 1, 1, 1) * mask[:, None]
+    assert rel_err(out.permute(0, 2, 1, 3, 4), ref) < TOL_F32
+
+
+def test_channel_offset_output():
+    """E2D conv_out writes mu straight into channels [8,16) of the UNet input buffer."""
+    no_tf32()
+    g = torch.Generator().manual_seed(13)
+    N, ci, D, H, W = 1, 512, 2, 8, 8
+    x = bf16_round(_rnd(g, N, ci, D, H, W))
+    w = bf16_round(_rnd(g, 16, ci, 3, 3, 3, scale=(27 * ci) ** -0.5))
+    b = _rnd(g, 16)
+    out = new_act(N, D, H, W, 64, DEV, zero=True)
+    out.hi.fill_(7.0)
+    ConvPlan([to_act(x)], engine.pack_conv3d(w, b, DEV), out, cout=8, out_coff=8).run(_stream())
+    ref = F.conv3d(x, w, b, padding=1)[:, :8]
+    got = out.hi.float()
+    assert rel_err(got[..., 8:16].permute(0, 4, 1, 2, 3), ref) < TOL_BF16
+    assert (got[..., :8] == 7).all() and (got[..., 16:] == 7).all()
+
+
+def test_fp32x_split_mode():
+    no_tf32()
+    g = torch.Generator().manual_seed(14)
+    N, ci, co, H, W = 2, 128, 128, 16, 16
+    x = _rnd(g, N, ci, 1, H, W)
+    w = _rnd(g, co, ci, 3, 3, scale=(9 * ci) ** -0.5)
+    pw = engine.pack_conv2d(w, [ci], None, DEV, split=True)
+    out = new_act(N, 1, H, W, co, DEV, split=True)
+    ConvPlan([to_act(x, split=True)], pw, out, cout=co).run(_stream())
+    ref = F.conv2d(x[:, :, 0].double(), w.double(), None, padding=1).float()
+    assert rel_err(from_act(out, co)[:, :, 0], ref) < 1e-4
+
+
+def test_plan_rejects_bad_shapes():
+    x = new_act(1, 1, 8, 8, 64, DEV, zero=True)
+    w = torch.zeros(60, 64)
+    with pytest.raises(ValueError):
+        ConvPlan([x], engine.pack_linear(w, None, DEV), new_act(1, 1, 8, 8, 64, DEV), cout=60)  # cout not multiple of 64

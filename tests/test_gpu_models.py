@@ -1,0 +1,173 @@
+"""Model-level parity on the GPU: B200UNet / B200DualVAE / B200LatentDiffusionPredictor against the
+CPU oracle and the golden vectors generated from the reference itself.
+
+Tolerances are BASELINE.json's: per-step noise prediction max|err|/max|ref| <= 2e-2 in bf16 mode and
+<= 1e-3 in the fp32-class mode ("fp32x": bf16 hi/lo split operands, three tensor-core passes, fp32
+accumulation); final velocity field relative L2 <= 1e-2 against the reference's fp32 output."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffusion_model_project_b200 import synth
+from diffusion_model_project_b200.predictor import B200LatentDiffusionPredictor
+from diffusion_model_project_b200.unet import B200UNet
+from diffusion_model_project_b200.vae import B200DualVAE
+from oracle import predictor as opred
+from oracle import unet as ounet
+from oracle import vae as ovae
+from util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+TOL_EPS = {"bf16": 2e-2, "fp32x": 1e-3}
+
+
+@pytest.fixture(scope="module")
+def unet_sd():
+    return synth.synth_unet_state(seed=0)
+
+
+@pytest.fixture(scope="module")
+def vae_sd():
+    return synth.synth_vae_state(seed=1)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+def test_unet_forward_vs_golden_and_oracle(unet_sd, golden_dir, precision):
+    g = np.load(os.path.join(golden_dir, "unet.npz"))
+    m = B200UNet(**synth.UNET_KWARGS, precision=precision, device="cuda").load_state_dict(unet_sd)
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 17, 32, 32, generator=gen)
+    t = torch.from_numpy(g["t"])
+    eps = m(x.cuda(), t.cuda()).cpu()
+    ref = torch.from_numpy(g["eps"])
+    assert eps.shape == ref.shape
+    assert rel_err(eps, ref) <= TOL_EPS[precision], rel_err(eps, ref)
+    # a second shape / batch (N = 3, 64x32 latent), per-sample timesteps, vs the oracle
+    x2 = torch.randn(3, 17, 64, 32, generator=gen)
+    t2 = torch.tensor([0, 17, 998])
+    eps2 = m(x2.cuda(), t2.cuda()).cpu()
+    ref2 = ounet.unet_forward(unet_sd, x2, t2)
+    assert rel_err(eps2, ref2) <= TOL_EPS[precision], rel_err(eps2, ref2)
+
+
+def test_unet_rejects_bad_inputs(unet_sd):
+    m = B200UNet(**synth.UNET_KWARGS, device="cuda").load_state_dict(unet_sd)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 17, 32, 32, device="cuda"), None)            # models.py:139-140
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 17, 48, 48, device="cuda"), torch.zeros(1, dtype=torch.long, device="cuda"))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 16, 32, 32, device="cuda"), torch.zeros(1, dtype=torch.long, device="cuda"))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+def test_vae_branches_vs_golden(vae_sd, golden_dir, precision):
+    g = np.load(os.path.join(golden_dir, "vae.npz"))
+    vae = B200DualVAE(3, 8, precision=precision, device="cuda").load_state_dict(vae_sd)
+    gen = torch.Generator().manual_seed(13)
+    xv = torch.randn(1, 3, 3, 32, 32, generator=gen)
+    z, (mu, logvar) = vae.encode_2d_deterministic(xv.cuda())
+    zl = torch.randn(1, 8, 3, 8, 8, generator=gen)
+    dec = vae.decode_3d(zl.cuda())
+    tol = 3e-2 if precision == "bf16" else 1e-3
+    assert rel_err(mu.cpu(), torch.from_numpy(g["mu"])) <= tol
+    assert rel_err(logvar.cpu(), torch.from_numpy(g["logvar"])) <= tol
+    assert rel_err(dec.cpu(), torch.from_numpy(g["dec"])) <= tol
+    assert rel_l2(dec.cpu(), torch.from_numpy(g["dec"])) <= 1e-2
+    assert z is mu
+    mu2, _ = vae.encoder_2d(xv.cuda())
+    assert torch.equal(mu2, mu)
+
+
+def test_vae_ragged_depth_and_batch(vae_sd):
+    vae = B200DualVAE(3, 8, device="cuda").load_state_dict(vae_sd)
+    gen = torch.Generator().manual_seed(5)
+    zl = torch.randn(2, 8, 5, 4, 8, generator=gen)   # depth 5, non-square
+    dec = vae.decode_3d(zl.cuda()).cpu()
+    ref = ovae.decode_3d(vae_sd, zl)
+    assert dec.shape == ref.shape == (2, 3, 5, 16, 32)
+    assert rel_l2(dec, ref) <= 1e-2
+    xv = torch.randn(2, 3, 5, 16, 32, generator=gen)
+    mu, _ = vae.encoder_2d(xv.cuda())
+    mu_ref, _ = ovae.encoder_forward(vae_sd, xv)
+    assert rel_l2(mu.cpu(), mu_ref) <= 1e-2
+
+
+def _predictor(unet_sd, vae_sd, precision, T=1000, graph=True, S=2):
+    return B200LatentDiffusionPredictor(
+        "UNet", dict(synth.UNET_KWARGS), True, unet_state=unet_sd, vae_state=vae_sd, norm_factors=synth.NORM_FACTORS,
+        num_slices=S, num_timesteps=T, precision=precision, use_graph=graph, device="cuda")
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+def test_predict_ddim_vs_golden(unet_sd, vae_sd, golden_dir, precision):
+    g = np.load(os.path.join(golden_dir, "predict_ddim.npz"))
+    img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=2024)
+    noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=42)
+    p = _predictor(unet_sd, vae_sd, precision, graph=False)
+    rec = []
+    out = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=3, eta=0.0, noise=noise.cuda(), record=rec).cpu()
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape == (1, 2, 3, 128, 128)
+    eps_ref = torch.from_numpy(g["eps_steps"])
+    # step 0 sees identical inputs -> pure per-step eps tolerance; later steps see the accumulated trajectory
+    assert rel_err(rec[0][1].cpu(), eps_ref[0]) <= TOL_EPS[precision]
+    for i in range(3):
+        assert rel_err(rec[i][1].cpu(), eps_ref[i]) <= 3 * TOL_EPS[precision]
+    assert rel_l2(out, ref) <= 1e-2, rel_l2(out, ref)
+    # masked-out (solid) voxels are exactly zero, as in the reference (predictor.py:1021)
+    assert (out[(img == 0).expand_as(out)] == 0).all()
+    # graph-captured loop == eager loop
+    pg = _predictor(unet_sd, vae_sd, precision, graph=True)
+    out_g = pg.predict_ddim(img.cuda(), v2d.cuda(), num_steps=3, eta=0.0, noise=noise.cuda()).cpu()
+    assert torch.equal(out_g, out)
+    out_g2 = pg.predict_ddim(img.cuda(), v2d.cuda(), num_steps=3, eta=0.0, noise=noise.cuda()).cpu()
+    assert torch.equal(out_g2, out)  # idempotent across calls (session reuse, graph replay)
+
+
+def test_predict_ddim_eta_host_noise(unet_sd, vae_sd, golden_dir):
+    g = np.load(os.path.join(golden_dir, "predict_ddim.npz"))
+    img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=2024)
+    noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=42)
+    gen = torch.Generator().manual_seed(99)
+    zs = [torch.randn(2, 8, 32, 32, generator=gen) for _ in range(3)]
+    p = _predictor(unet_sd, vae_sd, "fp32x", graph=False)
+    out = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=3, eta=0.7, noise=noise.cuda(), step_noise=zs).cpu()
+    assert rel_l2(out, torch.from_numpy(g["out_eta07"])) <= 1e-2
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+def test_predict_ddpm_vs_golden(unet_sd, vae_sd, golden_dir, precision):
+    g = np.load(os.path.join(golden_dir, "predict_ddpm.npz"))
+    img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=2024)
+    noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=42)
+    gen = torch.Generator().manual_seed(100)
+    zs = [torch.randn(2, 8, 32, 32, generator=gen) for _ in range(12)]
+    p = _predictor(unet_sd, vae_sd, precision, T=12, graph=False)
+    out = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda(), step_noise=zs).cpu()
+    assert rel_l2(out, torch.from_numpy(g["out"])) <= 1e-2
+
+
+def test_predict_batch2_matches_per_sample(unet_sd, vae_sd):
+    """Samples are independent end to end: a batch of 2 == two batches of 1."""
+    img, v2d = synth.synth_inputs(2, num_slices=2, size=128, seed=7)
+    noise = synth.synth_noise(2, num_slices=2, latent_size=32, seed=1)
+    p = _predictor(unet_sd, vae_sd, "bf16")
+    both = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()
+    one = p.predict_ddim(img[1:].cuda(), v2d[1:].cuda(), num_steps=2, noise=noise[2:].cuda()).cpu()
+    assert rel_l2(both[1:], one) <= 2e-3
+
+
+def test_in_kernel_noise_ddpm_runs_and_is_seeded(unet_sd, vae_sd):
+    img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=3)
+    noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=2)
+    p = _predictor(unet_sd, vae_sd, "bf16", T=4)
+    torch.manual_seed(5)
+    a = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()
+    torch.manual_seed(5)
+    b = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()
+    assert torch.isfinite(a).all() and torch.equal(a, b)
