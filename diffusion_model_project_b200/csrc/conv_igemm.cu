@@ -426,9 +426,22 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   }
   if (reinterpret_cast<uintptr_t>(d->weight) & 15) return set_error(B2D_E_INVALID, "weight not 16-byte aligned");
 
+  // ---- M tiling: a 128-position box, widest along x -----------------------------------------
+  int lw = ilog2_ceil(d->OW); if (lw > 4) lw = 4;
+  int lh = ilog2_ceil(d->OH); if (lh > 7 - lw) lh = 7 - lw;
+  int ld = ilog2_ceil(d->D);  if (ld > 7 - lw - lh) ld = 7 - lw - lh;
+  int ln = 7 - lw - lh - ld;
+  const long long tiles_m = (long long)((d->OW + (1 << lw) - 1) >> lw) * ((d->OH + (1 << lh) - 1) >> lh) *
+                            ((d->D + (1 << ld) - 1) >> ld) * ((d->N + (1 << ln) - 1) >> ln);
+
   int bn = d->block_n;
   if (bn == 0) {
-    if (d->cout % 128 == 0) bn = 128;
+    // Widest N tile that still fills the machine: N=256 needs 96 B/clk of smem operand reads per MMA
+    // (128 B/clk at N=128), but small-M layers (deep UNet levels) need the CTA count more.
+    const long long cols = (long long)d->cout * d->nphase;
+    const int sms = num_sms();
+    if (d->cout % 256 == 0 && tiles_m * (cols / 256) >= 2LL * sms) bn = 256;
+    else if (d->cout % 128 == 0 && (tiles_m * (cols / 128) >= sms || d->cout % 64 != 0)) bn = 128;
     else if (d->cout % 64 == 0) bn = 64;
     else if (d->cout <= 16 && d->nphase == 1) bn = 16;
     else return set_error(B2D_E_INVALID, "cout=%d: need a multiple of 64 or <= 16", d->cout);
@@ -461,11 +474,6 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   ConvKParams& k = pl->kp;
   memset(&k, 0, sizeof(k));
 
-  // ---- M tiling: a 128-position box, widest along x -----------------------------------------
-  int lw = ilog2_ceil(d->OW); if (lw > 4) lw = 4;
-  int lh = ilog2_ceil(d->OH); if (lh > 7 - lw) lh = 7 - lw;
-  int ld = ilog2_ceil(d->D);  if (ld > 7 - lw - lh) ld = 7 - lw - lh;
-  int ln = 7 - lw - lh - ld;
   k.lbw = lw; k.lbh = lh; k.lbd = ld; k.lbn = ln;
   k.tiles_w = (d->OW + (1 << lw) - 1) >> lw;
   k.tiles_h = (d->OH + (1 << lh) - 1) >> lh;

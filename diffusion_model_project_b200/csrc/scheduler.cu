@@ -45,6 +45,9 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
 
 struct Coef { float a, b, c1, c2, s; };
 
+// ticket counter of the "last block advances the step index" protocol (one copy per device, no allocation)
+__device__ unsigned int g_done_counter = 0u;
+
 __device__ __forceinline__ float step_one(float x, float e, float z, const Coef& k, int kind, int clip, float lo, float hi,
                                           bool use_noise) {
   // x0 = (x_t - sqrt(1-abar) * eps) / sqrt(abar)               diffusion.py:124
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256) scheduler_step_kernel(
     int kind, const float4* __restrict__ x_t, const float4* __restrict__ eps, const float4* __restrict__ noise,
     float4* __restrict__ x_out, long long n_vec, long long n_elem, const float* __restrict__ coef, int* step_idx,
     int step_off, int step_inc, int clip, float clip_lo, float clip_hi, __nv_bfloat16* __restrict__ x_bf16, int group,
-    int group_stride, unsigned long long seed, unsigned int* done_counter) {
+    int group_stride, unsigned long long seed) {
   const int row = (step_idx ? *step_idx : 0) + step_off;
   Coef k;
   k.a = __ldg(coef + row * 8 + 0); k.b = __ldg(coef + row * 8 + 1); k.c1 = __ldg(coef + row * 8 + 2);
@@ -123,9 +126,9 @@ __global__ void __launch_bounds__(256) scheduler_step_kernel(
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
-      const unsigned int ticket = atomicAdd(done_counter, 1u);
+      const unsigned int ticket = atomicAdd(&g_done_counter, 1u);
       if (ticket == gridDim.x - 1) {
-        *done_counter = 0u;
+        g_done_counter = 0u;
         *step_idx = row - step_off + step_inc;
         __threadfence();
       }
@@ -144,18 +147,6 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__
   }
 }
 
-static unsigned int* done_counter_for_device() {
-  // one 4-byte ticket counter per device, allocated once (never freed: process lifetime)
-  static unsigned int* ctr[64] = {nullptr};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!ctr[dev]) {
-    if (cudaMalloc(&ctr[dev], sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    cudaMemset(ctr[dev], 0, sizeof(unsigned int));
-  }
-  return ctr[dev];
-}
-
 }  // namespace b2d
 
 using namespace b2d;
@@ -171,11 +162,6 @@ extern "C" int b2d_scheduler_step(int kind, const float* x_t, const float* eps, 
     return set_error(B2D_E_INVALID, "b2d_scheduler_step: pointers must be 16-byte aligned");
   if (x_bf16 && (group < 4 || (group % 4) || group_stride < group || (group_stride % 2) || ((uintptr_t)x_bf16 & 3)))
     return set_error(B2D_E_INVALID, "b2d_scheduler_step: bf16 copy needs group %%4==0 and stride>=group");
-  unsigned int* ctr = nullptr;
-  if (step_idx && step_inc) {
-    ctr = done_counter_for_device();
-    if (!ctr) return set_error(B2D_E_CUDA, "b2d_scheduler_step: cannot allocate ticket counter");
-  }
   const long long n_vec = n_elem / 4;
   long long blocks = (n_vec + 256 * 4 - 1) / (256 * 4);  // 4 vectors in flight per thread
   const long long cap = (long long)num_sms() * 8;
@@ -183,7 +169,7 @@ extern "C" int b2d_scheduler_step(int kind, const float* x_t, const float* eps, 
   if (blocks < 1) blocks = 1;
   scheduler_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
       kind, (const float4*)x_t, (const float4*)eps, (const float4*)noise, (float4*)x_out, n_vec, n_elem, coef, step_idx,
-      step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed, ctr);
+      step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed);
   return check_launch("scheduler_step_kernel");
 }
 
