@@ -241,6 +241,7 @@ def run_b200(args):
         sync_all()
         if sampler:
             sampler.start()
+            torch.cuda.profiler.start()  # no-op unless run under `ncu --profile-from-start off` (profiles/ launch list)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count
         e0.record()
@@ -248,6 +249,8 @@ def run_b200(args):
             fn()
         e1.record()
         sync_all()
+        if sampler:
+            torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
         t = torch.tensor([ms], device=dev, dtype=torch.float64)

@@ -42,7 +42,8 @@ class ConvDesc(C.Structure):
         ("stats_cpg", c_i32),
         ("out_scale", c_void_p), ("out_mask", c_void_p),
         ("block_n", c_i32),
-        ("reserved", c_i32 * 7),
+        ("out_f16", c_i32), ("res_f16", c_i32),
+        ("reserved", c_i32 * 5),
     ]
 
 
@@ -57,7 +58,7 @@ _SIGNATURES = {
     "b2d_conv_run": (c_int, [c_void_p, c_void_p]),
     "b2d_conv_plan_info": (c_int, [c_void_p, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32)]),
     "b2d_gn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_i32, c_void_p, c_i32, c_void_p, c_void_p,
-                             c_float, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p]),
+                             c_float, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32, c_void_p]),
     "b2d_maxpool2x2_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p]),
     "b2d_upsample2x_nearest": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_planar_to_cl": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_void_p, c_void_p]),

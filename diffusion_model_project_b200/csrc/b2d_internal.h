@@ -8,4 +8,6 @@ int set_error(int code, const char* fmt, ...);
 // Checks cudaGetLastError() after a launch.
 int check_launch(const char* what);
 int num_sms();
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency); nullptr if unavailable.
+void* tensor_map_encode_fn();
 }  // namespace b2d

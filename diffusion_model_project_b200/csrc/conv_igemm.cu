@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string.h>
 #include <new>
@@ -58,12 +59,20 @@ struct ConvKParams {
   const float* out_scale;
   const float* out_mask;
   int skip_z;
+  int out_f16, res_f16;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// two fp32 -> packed IEEE fp16, saturating to +-65504 (raw pre-GroupNorm storage must never produce inf)
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tcvt.rn.satfinite.f16.f32 lo, %1;\n\tcvt.rn.satfinite.f16.f32 hi, %2;\n\tmov.b32 %0, {lo, hi};\n\t}" : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
@@ -234,10 +243,16 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_igemm_kernel(const __grid
 #pragma unroll
         for (int q = 0; q < CW / 8; ++q) {
           uint4 u = __ldg(rp + q);
-          f[q * 8 + 0] += bf16_lo(u.x); f[q * 8 + 1] += bf16_hi(u.x);
-          f[q * 8 + 2] += bf16_lo(u.y); f[q * 8 + 3] += bf16_hi(u.y);
-          f[q * 8 + 4] += bf16_lo(u.z); f[q * 8 + 5] += bf16_hi(u.z);
-          f[q * 8 + 6] += bf16_lo(u.w); f[q * 8 + 7] += bf16_hi(u.w);
+          if (p.res_f16) {
+            const float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
+            f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+            f[q * 8 + 4] += c.x; f[q * 8 + 5] += c.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+          } else {
+            f[q * 8 + 0] += bf16_lo(u.x); f[q * 8 + 1] += bf16_hi(u.x);
+            f[q * 8 + 2] += bf16_lo(u.y); f[q * 8 + 3] += bf16_hi(u.y);
+            f[q * 8 + 4] += bf16_lo(u.z); f[q * 8 + 5] += bf16_hi(u.z);
+            f[q * 8 + 6] += bf16_lo(u.w); f[q * 8 + 7] += bf16_hi(u.w);
+          }
         }
         if (p.residual_lo != nullptr) {
           const uint4* rl = reinterpret_cast<const uint4*>(p.residual_lo + opix * p.res_cstride + co0);
@@ -290,14 +305,14 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_igemm_kernel(const __grid
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + p.out_coff + co0;
           uint32_t w[CW / 2];
 #pragma unroll
-          for (int j = 0; j < CW / 2; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+          for (int j = 0; j < CW / 2; ++j) w[j] = p.out_f16 ? pack_f16_sat(f[2 * j], f[2 * j + 1]) : pack_bf16(f[2 * j], f[2 * j + 1]);
           if (co0 + CW <= p.cout) {
 #pragma unroll
             for (int q = 0; q < CW / 8; ++q)
               reinterpret_cast<uint4*>(op)[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
           } else {
             for (int j = 0; j < CW; ++j)
-              if (co0 + j < p.cout) op[j] = __float2bfloat16_rn(f[j]);
+              if (co0 + j < p.cout) reinterpret_cast<uint16_t*>(op)[j] = (uint16_t)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu));
           }
           if (p.out_lo != nullptr) {
             __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + opix * p.out_cstride + p.out_coff + co0;
@@ -358,8 +373,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
+void* tensor_map_encode_fn() {
+  static void* fn = nullptr;
   if (fn) return fn;
   void* ptr = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -368,9 +383,10 @@ static PFN_encodeTiled get_encode_fn() {
     cudaGetLastError();
     return nullptr;
   }
-  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  fn = ptr;
   return fn;
 }
+static PFN_encodeTiled get_encode_fn() { return reinterpret_cast<PFN_encodeTiled>(tensor_map_encode_fn()); }
 
 static int ilog2_ceil(int x) {
   int l = 0;
@@ -459,6 +475,8 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   if (d->residual && (d->out_mode != 0 && d->out_mode != 2)) return set_error(B2D_E_INVALID, "residual needs out_mode 0/2");
   if (d->residual && ((d->res_cstride % 8) || (reinterpret_cast<uintptr_t>(d->residual) & 15) || bn == 16))
     return set_error(B2D_E_INVALID, "residual needs cstride multiple of 8, 16-byte alignment, block_n>=64");
+  if (d->out_f16 && (d->out_mode != 0 || d->out_lo)) return set_error(B2D_E_INVALID, "out_f16 needs out_mode 0 without a lo part");
+  if (d->res_f16 && (!d->residual || d->residual_lo)) return set_error(B2D_E_INVALID, "res_f16 needs a residual without a lo part");
   if (d->stats) {
     const int c = d->stats_cpg;
     if (!(c == 4 || c == 8 || c == 16 || (c >= 32 && c % 32 == 0)) || d->cout % c)
@@ -535,6 +553,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   k.res_cstride = d->res_cstride;
   k.stats = d->stats; k.stats_cpg = d->stats ? d->stats_cpg : 0;
   k.out_scale = d->out_scale; k.out_mask = d->out_mask;
+  k.out_f16 = d->out_f16 ? 1 : 0; k.res_f16 = d->res_f16 ? 1 : 0;
 
   pl->block_n = bn;
   pl->grid = dim3((unsigned)(k.tiles_w * k.tiles_h * k.tiles_d * k.tiles_n), (unsigned)(total_cols / bn), 1);

@@ -4,6 +4,7 @@
 // as a multiple of the SM count.  Reference call sites are listed in include/b2d.h.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/b2d.h"
@@ -20,6 +21,11 @@ __device__ __forceinline__ uint32_t packbf(float a, float b) {
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = bflo(u.x); f[1] = bfhi(u.x); f[2] = bflo(u.y); f[3] = bfhi(u.y);
   f[4] = bflo(u.z); f[5] = bfhi(u.z); f[6] = bflo(u.w); f[7] = bfhi(u.w);
+}
+__device__ __forceinline__ void unpack8_f16(const uint4& u, float (&f)[8]) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(packbf(f[0], f[1]), packbf(f[2], f[3]), packbf(f[4], f[5]), packbf(f[6], f[7]));
@@ -47,7 +53,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(
     const uint4* __restrict__ x, const uint4* __restrict__ x_lo, uint4* __restrict__ y, uint4* __restrict__ y_lo,
     long long P, int C, const double* __restrict__ stats, int cpg, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, int act, const float* __restrict__ temb_table,
-    const int* __restrict__ temb_row, int temb_row_stride, int temb_ld, int temb_col, double* __restrict__ stats_out) {
+    const int* __restrict__ temb_row, int temb_row_stride, int temb_ld, int temb_col, double* __restrict__ stats_out,
+    int in_f16) {
   extern __shared__ float sm[];
   float* sa = sm;
   float* sb = sm + C;
@@ -79,28 +86,62 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(
   const long long nvec = P * vpc;
   const long long base = (long long)n * nvec;
   float acc_s = 0.f, acc_ss = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % vpc) << 3;
-    float f[8];
-    unpack8(__ldg(x + base + i), f);
-    if (x_lo != nullptr) {
-      float l[8];
-      unpack8(__ldg(x_lo + base + i), l);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += l[j];
-    }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto transform = [&](float (&f)[8], const float* a, const float* b, const float* t) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = fmaf(f[j], sa[c0 + j], sb[c0 + j]);
+      float v = fmaf(f[j], a[j], b[j]);
       if (act) v = silu(v);
-      v += st[c0 + j];
+      v += t[j];
       f[j] = v;
       acc_s += v;
       acc_ss += v * v;
     }
-    const uint4 hi = pack8(f);
-    y[base + i] = hi;
-    if (y_lo != nullptr) y_lo[base + i] = pack8_lo(f, hi);
+  };
+  if ((blockDim.x % vpc) == 0 && x_lo == nullptr && y_lo == nullptr) {
+    // fast path: the grid stride is a multiple of the vectors-per-pixel count, so a thread always sees the
+    // same 8 channels -> coefficients live in registers and 4 independent 16-byte loads are in flight.
+    const int c0 = (threadIdx.x % vpc) << 3;
+    float a[8], b[8], t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = sa[c0 + j]; b[j] = sb[c0 + j]; t[j] = st[c0 + j]; }
+    const uint4* xp = x + base;
+    uint4* yp = y + base;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldcs(xp + i + k * stride);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        if (in_f16) unpack8_f16(u[k], f); else unpack8(u[k], f);
+        transform(f, a, b, t);
+        yp[i + k * stride] = pack8(f);
+      }
+    }
+    for (; i < nvec; i += stride) {
+      float f[8];
+      if (in_f16) unpack8_f16(__ldcs(xp + i), f); else unpack8(__ldcs(xp + i), f);
+      transform(f, a, b, t);
+      yp[i] = pack8(f);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+      const int c0 = (int)(i % vpc) << 3;
+      float f[8];
+      if (in_f16) unpack8_f16(__ldg(x + base + i), f); else unpack8(__ldg(x + base + i), f);
+      if (x_lo != nullptr) {
+        float l[8];
+        unpack8(__ldg(x_lo + base + i), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += l[j];
+      }
+      transform(f, sa + c0, sb + c0, st + c0);
+      const uint4 hi = pack8(f);
+      y[base + i] = hi;
+      if (y_lo != nullptr) y_lo[base + i] = pack8_lo(f, hi);
+    }
   }
   if (stats_out != nullptr) {
     __shared__ float red[2][8];
@@ -236,8 +277,9 @@ using namespace b2d;
 extern "C" int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int64_t P, int32_t C,
                             const double* stats, int32_t cpg, const float* gamma, const float* beta, float eps, int32_t act,
                             const float* temb_table, const int32_t* temb_row, int32_t temb_row_stride, int32_t temb_ld,
-                            int32_t temb_col, double* stats_out, void* stream) {
+                            int32_t temb_col, double* stats_out, int32_t in_f16, void* stream) {
   if (!x || !y || !stats) return set_error(B2D_E_INVALID, "b2d_gn_apply: null pointer");
+  if (in_f16 && x_lo) return set_error(B2D_E_INVALID, "b2d_gn_apply: fp16 input has no lo part");
   if (N < 1 || P < 1 || C < 8 || (C % 8) || cpg < 1 || (C % cpg)) return set_error(B2D_E_INVALID, "b2d_gn_apply: bad shape N=%d P=%lld C=%d cpg=%d", N, (long long)P, C, cpg);
   if (3 * C * (int)sizeof(float) > 96 * 1024) return set_error(B2D_E_INVALID, "b2d_gn_apply: C=%d too large", C);
   if (N > 65535) return set_error(B2D_E_INVALID, "b2d_gn_apply: N too large");
@@ -253,7 +295,7 @@ extern "C" int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo
   }
   gn_apply_kernel<<<dim3(bx, N), 256, smem, (cudaStream_t)stream>>>(
       (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, temb_table,
-      temb_row, temb_row_stride, temb_ld, temb_col, stats_out);
+      temb_row, temb_row_stride, temb_ld, temb_col, stats_out, in_f16 ? 1 : 0);
   return check_launch("gn_apply_kernel");
 }
 

@@ -31,9 +31,17 @@ def split_hi_lo(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 @dataclass
 class Act:
-    """Channels-last activation [N, D, H, W, C] bf16 (C multiple of 64; `lo` only in fp32x mode)."""
+    """Channels-last activation [N, D, H, W, C] bf16 (C multiple of 64; `lo` only in fp32x mode).
+
+    f16=True marks a raw pre-GroupNorm conv output / residual stream held as IEEE fp16 in the same
+    16-bit storage (bf16 mode only): it is read by gn_apply and by residual adds, never by an MMA."""
     hi: torch.Tensor
     lo: Optional[torch.Tensor] = None
+    f16: bool = False
+
+    def as_bf16(self) -> "Act":
+        """The same storage after an in-place GroupNorm apply (which writes bf16)."""
+        return Act(self.hi, self.lo, False)
 
     @property
     def shape(self):
@@ -44,11 +52,11 @@ class Act:
         return self.hi.shape[-1]
 
 
-def new_act(N, D, H, W, C, device, split=False, zero=False) -> Act:
+def new_act(N, D, H, W, C, device, split=False, zero=False, f16=False) -> Act:
     mk = torch.zeros if zero else torch.empty
     hi = mk((N, D, H, W, C), dtype=BF16, device=device)
     lo = mk((N, D, H, W, C), dtype=BF16, device=device) if split else None
-    return Act(hi, lo)
+    return Act(hi, lo, bool(f16) and not split)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -155,6 +163,7 @@ class ConvPlan:
         segs: List[Tuple[torch.Tensor, int, int]] = []  # (tensor, cin_pad, kbase)
         for i, a in enumerate(inputs):
             assert a.shape[:4] == (N, D, H, W) and a.C == pw.cin_pad[i], (a.shape, pw.cin_pad, i)
+            assert not a.f16, "an fp16 raw tensor cannot be an MMA operand"
             segs.append((a.hi, a.C, pw.kbase[i]))
         if split:
             for i, a in enumerate(inputs):
@@ -181,6 +190,7 @@ class ConvPlan:
         out_hi = out.hi if isinstance(out, Act) else out
         d.out = out_hi.data_ptr()
         d.out_lo = ptr(out.lo) if isinstance(out, Act) else None
+        d.out_f16 = 1 if (isinstance(out, Act) and out.f16) else 0
         d.out_mode = out_mode
         if out_geom is None:
             up = 2 if nphase == 4 else 1
@@ -193,6 +203,7 @@ class ConvPlan:
             d.residual = residual.hi.data_ptr()
             d.residual_lo = ptr(residual.lo)
             d.res_cstride = residual.C
+            d.res_f16 = 1 if residual.f16 else 0
         d.stats = ptr(stats)
         d.stats_cpg = stats_cpg
         d.out_scale = ptr(out_scale)
@@ -229,7 +240,7 @@ def gn_apply(x: Act, y: Act, stats: torch.Tensor, cpg: int, gamma, beta, act: bo
     N, D, H, W, Cc = x.shape
     call("b2d_gn_apply", ptr(x.hi), ptr(x.lo), ptr(y.hi), ptr(y.lo), N, D * H * W, Cc, ptr(stats), cpg, ptr(gamma), ptr(beta),
          eps, 1 if act else 0, ptr(temb), ptr(temb_row), temb_row_stride, 0 if temb is None else temb.shape[1], temb_col,
-         ptr(stats_out), stream)
+         ptr(stats_out), 1 if x.f16 else 0, stream)
 
 
 def maxpool_stats(x: Act, y: Act, stats: torch.Tensor, stream: int):

@@ -174,14 +174,17 @@ class B200UNet:
         def conv_gn_act(name, inputs, pw, cout, H, Wd, gnw, *, temb_col=None, stats_out=None, nphase=1):
             """conv (+GN sums in the epilogue) -> in-place GN apply + SiLU (+temb)."""
             up = 2 if nphase == 4 else 1
-            out = new_act(N, 1, H * up, Wd * up, cout, dev, sp)
+            # raw conv output: fp16 storage in bf16 mode (8x finer than bf16 ahead of the normalisation), rewritten
+            # in place as bf16 by the GroupNorm apply
+            raw = new_act(N, 1, H * up, Wd * up, cout, dev, sp, f16=True)
+            out = raw.as_bf16()
             st = stats_view(stats_alloc(1), N * 2)
-            plan = ConvPlan(inputs, pw, out, cout=cout, nphase=nphase, stats=st, stats_cpg=cout)
+            plan = ConvPlan(inputs, pw, raw, cout=cout, nphase=nphase, stats=st, stats_cpg=cout)
             prog.flops += plan.flops
             prog.add(f"{name}.conv", plan.run)
             g, b = gnw
-            prog.add(f"{name}.gn", lambda s, out=out, st=st, g=g, b=b, tc=temb_col, so=stats_out, cout=cout: engine.gn_apply(
-                out, out, st, cout, g, b, True, s, temb=temb_table if tc is not None else None,
+            prog.add(f"{name}.gn", lambda s, raw=raw, out=out, st=st, g=g, b=b, tc=temb_col, so=stats_out, cout=cout: engine.gn_apply(
+                raw, out, st, cout, g, b, True, s, temb=temb_table if tc is not None else None,
                 temb_row=temb_row if tc is not None else None, temb_row_stride=temb_row_stride, temb_col=tc or 0, stats_out=so))
             keep.append(plan)
             return out

@@ -62,10 +62,14 @@ class _Builder:
         assert self.stats_used <= self.stats_buf.numel()
         return v
 
-    def conv(self, name, x: Act, pw, cout, *, stride=1, want_stats=True, residual=None, out=None, **kw):
+    def conv(self, name, x: Act, pw, cout, *, stride=1, want_stats=True, residual=None, out=None, raw=False, **kw):
+        """raw=True: the output is only ever read by a GroupNorm apply or as a residual (never as an MMA operand),
+        so bf16 mode stores it as fp16 (finer rounding ahead of the normalisation, same 2 bytes)."""
         N, D, H, W, _ = x.shape
         if out is None:
-            out = new_act(N, D, H // stride, W // stride, cout, self.dev, self.split)
+            out = new_act(N, D, H // stride, W // stride, cout, self.dev, self.split, f16=raw)
+        elif isinstance(out, Act) and out.f16 != (raw and not self.split):
+            out = Act(out.hi, out.lo, raw and not self.split)
         st = self.stats() if want_stats else None
         plan = ConvPlan([x], pw, out, cout=cout, stride=stride, residual=residual, stats=st,
                         stats_cpg=(cout // 32) if want_stats else 0, **kw)
@@ -75,23 +79,24 @@ class _Builder:
         return out, st
 
     def gn_silu(self, name, x: Act, st, gnw, inplace: bool):
-        y = x if inplace else new_act(*x.shape, self.dev, self.split)
+        y = x.as_bf16() if inplace else new_act(*x.shape, self.dev, self.split)
         g, b = gnw
         C = x.C
         self.prog.add(name, lambda s: engine.gn_apply(x, y, st, C // 32, g, b, True, s))
         return y
 
-    def res(self, w, name, x: Act, st_x, cin, cout, want_stats=True):
-        """vae/blocks.py:173-186."""
+    def res(self, w, name, x: Act, st_x, cin, cout, want_stats=True, raw_out=True):
+        """vae/blocks.py:173-186.  raw_out=False when the block output feeds a conv directly (down / upsample+conv)."""
         h = self.gn_silu(f"{name}.norm1", x, st_x, w[f"{name}.norm1"], inplace=False)
-        r, st_r = self.conv(f"{name}.conv1", h, w[f"{name}.conv1"], cout)
+        r, st_r = self.conv(f"{name}.conv1", h, w[f"{name}.conv1"], cout, raw=True)
         r = self.gn_silu(f"{name}.norm2", r, st_r, w[f"{name}.norm2"], inplace=True)
         skip = x
         if f"{name}.residual_layer" in w:
-            skip, _ = self.conv(f"{name}.residual_layer", x, w[f"{name}.residual_layer"], cout, want_stats=False)
+            assert not x.f16
+            skip, _ = self.conv(f"{name}.residual_layer", x, w[f"{name}.residual_layer"], cout, want_stats=False, raw=True)
         # reuse h's storage for the block output when shapes allow (h is dead after conv1)
         out = h if cin == cout else None
-        return self.conv(f"{name}.conv2", r, w[f"{name}.conv2"], cout, residual=skip, want_stats=want_stats, out=out)
+        return self.conv(f"{name}.conv2", r, w[f"{name}.conv2"], cout, residual=skip, want_stats=want_stats, out=out, raw=raw_out)
 
     def finish(self):
         used, buf = self.stats_used, self.stats_buf
@@ -134,13 +139,13 @@ class B200DualVAE:
         bd = _Builder(B, self.device, self.split)
         if x_in is None:
             x_in = new_act(B, D, H, W, pad64(br.cin), self.device, self.split, zero=True)
-        x, st = bd.conv("conv_in", x_in, w["conv_in"], 128)
+        x, st = bd.conv("conv_in", x_in, w["conv_in"], 128, raw=True)
         x, st = bd.res(w, "res1_1", x, st, 128, 128)
-        x, _ = bd.res(w, "res1_2", x, st, 128, 128, want_stats=False)
-        x, st = bd.conv("down1", x, w["down1"], 128, stride=2)
+        x, _ = bd.res(w, "res1_2", x, st, 128, 128, want_stats=False, raw_out=False)   # -> down1 (MMA operand)
+        x, st = bd.conv("down1", x, w["down1"], 128, stride=2)                            # -> res2_1's 1x1x1 skip conv
         x, st = bd.res(w, "res2_1", x, st, 128, 256)
-        x, _ = bd.res(w, "res2_2", x, st, 256, 256, want_stats=False)
-        x, st = bd.conv("down2", x, w["down2"], 256, stride=2)
+        x, _ = bd.res(w, "res2_2", x, st, 256, 256, want_stats=False, raw_out=False)   # -> down2
+        x, st = bd.conv("down2", x, w["down2"], 256, stride=2)                            # -> res3_1's skip conv
         x, st = bd.res(w, "res3_1", x, st, 256, 512)
         x, st = bd.res(w, "res3_2", x, st, 512, 512)
         x = bd.gn_silu("norm_out", x, st, w["norm_out"], inplace=True)
@@ -161,16 +166,16 @@ class B200DualVAE:
         bd = _Builder(B, self.device, self.split)
         if z_in is None:
             z_in = new_act(B, D, h, w_, pad64(br.cin), self.device, self.split, zero=True)
-        x, st = bd.conv("conv_in", z_in, w["conv_in"], 512)
+        x, st = bd.conv("conv_in", z_in, w["conv_in"], 512, raw=True)
         x, st = bd.res(w, "res1_1", x, st, 512, 512)
-        x, _ = bd.res(w, "res1_2", x, st, 512, 512, want_stats=False)
+        x, _ = bd.res(w, "res1_2", x, st, 512, 512, want_stats=False, raw_out=False)   # -> upsample -> conv_up1
         for stage, (cin, cout, r1, r2, last) in enumerate(((512, 256, "res2_1", "res2_2", False), (256, 128, "res3_1", "res3_2", True)), 1):
             N_, D_, H_, W_, _ = x.shape
             up = new_act(N_, D_, 2 * H_, 2 * W_, cin, self.device, self.split)
             bd.prog.add(f"up{stage}", lambda s, x=x, up=up: engine.upsample2x(x, up, s))
-            x, st = bd.conv(f"conv_up{stage}", up, w[f"conv_up{stage}"], cout)
+            x, st = bd.conv(f"conv_up{stage}", up, w[f"conv_up{stage}"], cout, raw=True)
             x, st = bd.res(w, r1, x, st, cout, cout)
-            x, st = bd.res(w, r2, x, st, cout, cout, want_stats=last)
+            x, st = bd.res(w, r2, x, st, cout, cout, want_stats=last, raw_out=last)     # stage 1 -> upsample -> conv_up2
         x = bd.gn_silu("norm_out", x, st, w["norm_out"], inplace=True)
         H, W = 4 * h, 4 * w_
         if out is None:

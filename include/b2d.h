@@ -110,7 +110,10 @@ typedef struct b2d_conv_desc {
   const float* out_scale;          /* per-channel multiplier (mode 1) or NULL                   */
   const float* out_mask;           /* fp32 [N][D][out_H][out_W] multiplier (mode 1) or NULL     */
   int32_t block_n;                 /* 0 = auto, else 16/64/128/256                              */
-  int32_t reserved[7];
+  int32_t out_f16;                 /* mode 0: store IEEE fp16 (saturating) instead of bf16 -- for raw pre-GroupNorm
+                                      outputs / residual streams that are never an MMA operand            */
+  int32_t res_f16;                 /* residual tensor holds fp16 instead of bf16                         */
+  int32_t reserved[5];
 } b2d_conv_desc;
 
 typedef struct b2d_conv_plan b2d_conv_plan;
@@ -131,7 +134,7 @@ B2D_API int b2d_conv_plan_info(const b2d_conv_plan* plan, int32_t* grid_m, int32
 B2D_API int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int64_t P, int32_t C,
                  const double* stats, int32_t cpg, const float* gamma, const float* beta, float eps, int32_t act,
                  const float* temb_table, const int32_t* temb_row, int32_t temb_row_stride, int32_t temb_ld,
-                 int32_t temb_col, double* stats_out, void* stream);
+                 int32_t temb_col, double* stats_out, int32_t in_f16 /* x holds fp16 (see b2d_conv_desc.out_f16) */, void* stream);
 
 /* MaxPool2d(2,2) (unet/blocks.py:161-164,170) + GN(1,C) sums of the pooled map. bf16 NHWC. */
 B2D_API int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int32_t H, int32_t W,

@@ -1,0 +1,54 @@
+"""Per-launch timing of one UNet step (N slice-images of 64x64 latent) with CUDA events, eager (no graph).
+usage: python tools/profile_unet.py [N] [reps]   -- also the target of the ncu launch-list pass."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from diffusion_model_project_b200 import synth  # noqa: E402
+from diffusion_model_project_b200.unet import B200UNet  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 88
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+torch.set_grad_enabled(False)
+m = B200UNet(**synth.UNET_KWARGS, device="cuda").load_state_dict(synth.synth_unet_state(seed=0))
+st = m.build_program(N, 64, 64)
+st["x_in"].hi.copy_(torch.randn(N, 1, 64, 64, 64, device="cuda").to(torch.bfloat16))
+prog = st["program"]
+s = torch.cuda.current_stream().cuda_stream
+for _ in range(2):
+    prog.run(s)
+torch.cuda.synchronize()
+names = [n for n, _ in prog.steps]
+acc = [0.0] * len(names)
+for _ in range(reps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+    evs[0].record()
+    for i, (_, fn) in enumerate(prog.steps):
+        fn(s)
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    for i in range(len(names)):
+        acc[i] += evs[i].elapsed_time(evs[i + 1]) * 1e3 / reps
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(reps):
+    prog.run(s)
+b.record()
+torch.cuda.synchronize()
+total = a.elapsed_time(b) * 1e3 / reps
+print(f"UNet step N={N}: {total:.1f} us back-to-back, {sum(acc):.1f} us summed per-launch, {len(names)} launches, "
+      f"{prog.flops / total / 1e6:.1f} TFLOP/s")
+plans = {}
+for k in st["keep"]:
+    if hasattr(k, "info"):
+        plans[id(k)] = k
+for n, t in zip(names, acc):
+    print(f"{t:9.1f} us  {n}")
+kinds = {}
+for n, t in zip(names, acc):
+    k = n.rsplit(".", 1)[-1]
+    kinds[k] = kinds.get(k, 0.0) + t
+print({k: round(v, 1) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1])})
