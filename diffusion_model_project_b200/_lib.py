@@ -43,7 +43,9 @@ class ConvDesc(C.Structure):
         ("out_scale", c_void_p), ("out_mask", c_void_p),
         ("block_n", c_i32),
         ("out_f16", c_i32), ("res_f16", c_i32),
-        ("reserved", c_i32 * 5),
+        ("engine", c_i32),
+        ("workspace", c_void_p), ("workspace_bytes", c_i64),
+        ("reserved", c_i32 * 4),
     ]
 
 
@@ -57,6 +59,7 @@ _SIGNATURES = {
     "b2d_conv_plan_destroy": (c_int, [c_void_p]),
     "b2d_conv_run": (c_int, [c_void_p, c_void_p]),
     "b2d_conv_plan_info": (c_int, [c_void_p, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "b2d_conv_plan_info2": (c_int, [c_void_p, C.POINTER(c_i32)]),
     "b2d_gn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_i32, c_void_p, c_i32, c_void_p, c_void_p,
                              c_float, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32, c_void_p]),
     "b2d_maxpool2x2_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p]),
@@ -92,8 +95,8 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b2d_version() != 1:
-            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != 1; rebuild")
+        if l.b2d_version() != 2:
+            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != 2; rebuild")
         _lib = l
     return _lib
 

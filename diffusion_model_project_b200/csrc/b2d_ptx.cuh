@@ -82,6 +82,21 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// variants taking shared-memory addresses that are already 32-bit (uniform-datapath friendly)
+__device__ __forceinline__ void tma_load_2d_u(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_u(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3,
+                                              int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),

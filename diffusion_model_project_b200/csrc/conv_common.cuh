@@ -1,0 +1,338 @@
+// Shared definitions of the implicit-GEMM conv engines (conv_igemm.cu: one tile per CTA; conv_igemm2.cu:
+// persistent, halo-staged, split-K): kernel parameter block, packing helpers and the fused epilogue.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <type_traits>
+
+#include "../../include/b2d.h"
+#include "b2d_internal.h"
+#include "b2d_ptx.cuh"
+
+namespace b2d {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle atom
+constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kThreads = 192;
+
+struct ConvKParams {
+  CUtensorMap tmapA[B2D_MAX_SEG];
+  CUtensorMap tmapB;
+  int nseg;
+  int cchunks[B2D_MAX_SEG];
+  int kbase[B2D_MAX_SEG];
+  int cin[B2D_MAX_SEG];
+  int ntaps;
+  int8_t dz[B2D_MAX_TAPS], dy[B2D_MAX_TAPS], dx[B2D_MAX_TAPS];
+  int stride_h, stride_w;
+  int N, D, OH, OW;
+  int lbw, lbh, lbd, lbn;  // log2 box extents, bw*bh*bd*bn == 128
+  int tiles_w, tiles_h, tiles_d, tiles_n;
+  int cout, nphase;
+  const float* bias;
+  void* out;
+  void* out_lo;
+  int out_mode;
+  int out_H, out_W, out_sy, out_sx, out_oy, out_ox, out_cstride, out_coff;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* residual_lo;
+  int res_cstride;
+  double* stats;
+  int stats_cpg;
+  const float* out_scale;
+  const float* out_mask;
+  int skip_z;
+  int out_f16, res_f16;
+  // ---- persistent engine (conv_igemm2.cu) ----
+  int halo;          // 1: one 18x18 halo box feeds the 9 in-plane taps of two 8x16 M=128 halves
+  int ksplit;        // K-loop splits per output tile (fp32 partials in `ws`, last arriver reduces)
+  int ngroups;       // A-operand loads in the K loop: nseg x (halo ? z-taps : taps) x 64-channel chunks
+  int gtaps;         // weight tiles consumed per A load: halo ? 9 : 1
+  int goff[B2D_MAX_SEG + 1];  // first group of each segment
+  int tiles_ncol;    // N tiles
+  int num_units;     // tiles_m * tiles_ncol * ksplit
+  float* ws;         // [tile][ksplit][128][BLOCK_N] fp32 partial accumulators
+  int* counters;     // [tile] arrival counters (self-resetting)
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// two fp32 -> packed IEEE fp16, saturating to +-65504 (raw pre-GroupNorm storage must never produce inf)
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tcvt.rn.satfinite.f16.f32 lo, %1;\n\tcvt.rn.satfinite.f16.f32 hi, %2;\n\tmov.b32 %0, {lo, hi};\n\t}" : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+
+// ---------------------------------------------------------------------------------------------
+// Fused epilogue of one accumulator row (thread = output position, TMEM lane): + bias, + residual,
+// GroupNorm partial sums, store in the consumer's layout.  `load(col0, f)` fills CW raw fp32
+// accumulator columns starting at col0 (from TMEM, or from the split-K partials).
+// ---------------------------------------------------------------------------------------------
+struct EpiRow {
+  bool valid;        // the row maps to a real output position
+  int on;            // sample index (GroupNorm statistics are per sample)
+  long long img;     // (n * D + z)
+  long long opix;    // (img * out_H + out_y) * out_W + out_x
+  int out_y, out_x;
+};
+
+// Sum V values per lane across the 32 lanes of a warp with a transposing butterfly: each step exchanges
+// half of the remaining values, so V values cost (V - 1) + (5 - log2 V) shuffles instead of 5 V.
+// On return vals[0] of lane L holds the warp total of value index (L >> (5 - log2 V)) (bit-reversed pairing is
+// avoided by always keeping the half selected by the lane bit), i.e. lanes L with the low (5 - log2 V) bits
+// zero own one value each.
+template <int V>
+__device__ __forceinline__ void warp_transpose_sum(float (&vals)[V], int lane) {
+  static_assert(V >= 1 && V <= 32 && (V & (V - 1)) == 0, "V must be a power of two");
+  int off = 16;
+#pragma unroll
+  for (int cur = V; cur > 1; cur >>= 1) {
+    const int half = cur >> 1;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? vals[i] : vals[i + half];
+      const float keep = upper ? vals[i + half] : vals[i];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  for (; off > 0; off >>= 1) vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
+}
+
+// SMEM_STATS: the whole warp belongs to ONE sample (halo tiles) and GroupNorm sums go to per-CTA fp64
+// accumulators in shared memory (sm_stats[group][2]); the kernel pushes them to global memory when the
+// sample changes.  Otherwise sums go straight to global memory with fp64 atomics (rows of a warp may
+// belong to `32 / seg` different samples).
+template <int BLOCK_N, int CW, bool SMEM_STATS, class Loader>
+__device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const EpiRow& rw, int co_base, int lane, int seg,
+                                                  double* sm_stats, Loader&& load) {
+  const int cpg = p.stats_cpg;
+  const int groups_per_n = (cpg > 0) ? (p.cout / cpg) : 0;
+  float run_s = 0.f, run_ss = 0.f;
+  int run_g = -1;
+  int cur_g = 0, cur_rem = 0;  // group of column co0 and offset inside it, tracked without divisions
+  if (cpg >= CW) { cur_g = co_base / cpg; cur_rem = co_base - cur_g * cpg; }
+  const bool valid = rw.valid;
+  const int on = rw.on;
+  auto flush = [&](float s, float ss, int g) {
+    if constexpr (SMEM_STATS) {
+      float v2[2] = {s, ss};
+      warp_transpose_sum<2>(v2, lane);
+      if ((lane & 15) == 0 && g >= 0 && g < groups_per_n) atomicAdd(sm_stats + g * 2 + (lane >> 4), (double)v2[0]);
+    } else {
+      for (int off = seg >> 1; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      }
+      if ((lane & (seg - 1)) == 0 && on < p.N && g >= 0 && g < groups_per_n) {
+        double* dst = p.stats + ((long long)on * groups_per_n + g) * 2;
+        atomicAdd(dst, (double)s);
+        atomicAdd(dst + 1, (double)ss);
+      }
+    }
+  };
+  float mask_v = 1.f;
+  if (p.out_mode == 1 && p.out_mask != nullptr && valid) mask_v = p.out_mask[rw.opix];
+
+#pragma unroll 1
+  for (int col0 = 0; col0 < BLOCK_N; col0 += CW) {
+    float f[CW];
+    load(col0, f);
+    const int co0 = co_base + col0;
+    const bool full = co0 + CW <= p.cout;
+    if (p.bias != nullptr) {
+      if (full) {
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + q);
+          f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CW; ++j)
+          if (co0 + j < p.cout) f[j] += __ldg(p.bias + co0 + j);
+      }
+    }
+    if (p.residual != nullptr && valid) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rw.opix * p.res_cstride + co0);
+      if (p.res_f16) {
+#pragma unroll
+        for (int q = 0; q < CW / 8; ++q) {
+          const uint4 u = __ldg(rp + q);
+          const float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
+          f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+          f[q * 8 + 4] += c.x; f[q * 8 + 5] += c.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < CW / 8; ++q) {
+          const uint4 u = __ldg(rp + q);
+          f[q * 8 + 0] += bf16_lo(u.x); f[q * 8 + 1] += bf16_hi(u.x);
+          f[q * 8 + 2] += bf16_lo(u.y); f[q * 8 + 3] += bf16_hi(u.y);
+          f[q * 8 + 4] += bf16_lo(u.z); f[q * 8 + 5] += bf16_hi(u.z);
+          f[q * 8 + 6] += bf16_lo(u.w); f[q * 8 + 7] += bf16_hi(u.w);
+        }
+      }
+      if (p.residual_lo != nullptr) {
+        const uint4* rl = reinterpret_cast<const uint4*>(p.residual_lo + rw.opix * p.res_cstride + co0);
+#pragma unroll
+        for (int q = 0; q < CW / 8; ++q) {
+          const uint4 u = __ldg(rl + q);
+          f[q * 8 + 0] += bf16_lo(u.x); f[q * 8 + 1] += bf16_hi(u.x);
+          f[q * 8 + 2] += bf16_lo(u.y); f[q * 8 + 3] += bf16_hi(u.y);
+          f[q * 8 + 4] += bf16_lo(u.z); f[q * 8 + 5] += bf16_hi(u.z);
+          f[q * 8 + 6] += bf16_lo(u.w); f[q * 8 + 7] += bf16_hi(u.w);
+        }
+      }
+    }
+    // ---- GroupNorm partial sums -----------------------------------------------------------------
+    if (cpg > 0) {
+      if (cpg >= CW) {
+        // a chunk lies inside one group (cpg is a multiple of CW): running sums, reduced when the group ends
+        if (cur_g != run_g) {
+          if (run_g >= 0) flush(run_s, run_ss, run_g);
+          run_g = cur_g; run_s = 0.f; run_ss = 0.f;
+        }
+        if (valid) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) { run_s += f[j]; run_ss = fmaf(f[j], f[j], run_ss); }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+              if (co0 + j < p.cout) { run_s += f[j]; run_ss = fmaf(f[j], f[j], run_ss); }
+          }
+        }
+        cur_rem += CW;
+        if (cur_rem >= cpg) { cur_rem -= cpg; ++cur_g; }
+      } else {
+        // cpg in {4, 8, 16}: CW / cpg groups per chunk
+        auto small_groups = [&](auto cpg_c) {
+          constexpr int CPG = decltype(cpg_c)::value;
+          if constexpr (CPG <= CW) {
+            constexpr int G = CW / CPG;
+            if constexpr (SMEM_STATS) {
+              float vals[2 * G];
+#pragma unroll
+              for (int g0 = 0; g0 < G; ++g0) {
+                float s = 0.f, ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPG; ++j) { const float x = f[g0 * CPG + j]; s += x; ss = fmaf(x, x, ss); }
+                vals[g0] = valid ? s : 0.f;
+                vals[G + g0] = valid ? ss : 0.f;
+              }
+              warp_transpose_sum<2 * G>(vals, lane);
+              constexpr int SH = 5 - (G == 8 ? 4 : G == 4 ? 3 : G == 2 ? 2 : 1);  // 32 / (2G) lanes per value
+              if ((lane & ((1 << SH) - 1)) == 0) {
+                const int vi = lane >> SH;            // value index: [0,G) sums, [G,2G) sums of squares
+                const int g = co0 / CPG + (vi & (G - 1));
+                if (g < groups_per_n) atomicAdd(sm_stats + g * 2 + (vi >= G ? 1 : 0), (double)vals[0]);
+              }
+            } else {
+#pragma unroll
+              for (int g0 = 0; g0 < CW; g0 += CPG) {
+                float s = 0.f, ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPG; ++j) { float x = valid ? f[g0 + j] : 0.f; s += x; ss += x * x; }
+                flush(s, ss, (co0 + g0) / CPG);
+              }
+            }
+          }
+        };
+        if (cpg == 4) small_groups(std::integral_constant<int, 4>{});
+        else if (cpg == 8) small_groups(std::integral_constant<int, 8>{});
+        else small_groups(std::integral_constant<int, 16>{});
+      }
+    }
+    // ---- store -------------------------------------------------------------------------------
+    if (valid) {
+      if (p.out_mode == 0) {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + rw.opix * p.out_cstride + p.out_coff + co0;
+        uint32_t w[CW / 2];
+        if (p.out_f16) {
+#pragma unroll
+          for (int j = 0; j < CW / 2; ++j) w[j] = pack_f16_sat(f[2 * j], f[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW / 2; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+        }
+        if (full) {
+#pragma unroll
+          for (int q = 0; q < CW / 8; ++q)
+            reinterpret_cast<uint4*>(op)[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        } else {
+          for (int j = 0; j < CW; ++j)
+            if (co0 + j < p.cout) reinterpret_cast<uint16_t*>(op)[j] = (uint16_t)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu));
+        }
+        if (p.out_lo != nullptr) {
+          __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + rw.opix * p.out_cstride + p.out_coff + co0;
+          uint32_t wl[CW / 2];
+#pragma unroll
+          for (int j = 0; j < CW / 2; ++j)
+            wl[j] = pack_bf16(f[2 * j] - bf16_lo(w[j]), f[2 * j + 1] - bf16_hi(w[j]));
+          if (full) {
+#pragma unroll
+            for (int q = 0; q < CW / 8; ++q)
+              reinterpret_cast<uint4*>(ol)[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+          } else {
+            for (int j = 0; j < CW; ++j)
+              if (co0 + j < p.cout) ol[j] = __float2bfloat16_rn(f[j] - __bfloat162float(__float2bfloat16_rn(f[j])));
+          }
+        }
+      } else if (p.out_mode == 1) {
+        // planar fp32 [N][D][C][H][W]: lanes = consecutive x -> coalesced per channel
+        float* ob = reinterpret_cast<float*>(p.out);
+        const long long plane = (long long)p.out_H * p.out_W;
+        const long long pix = (long long)rw.out_y * p.out_W + rw.out_x;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          const int co = co0 + j;
+          if (co < p.cout) {
+            float sc = p.out_scale != nullptr ? __ldg(p.out_scale + co) : 1.f;
+            ob[(rw.img * p.out_cstride + p.out_coff + co) * plane + pix] = f[j] * sc * mask_v;
+          }
+        }
+      } else {
+        float* op = reinterpret_cast<float*>(p.out) + rw.opix * p.out_cstride + p.out_coff + co0;
+        if (full) {
+#pragma unroll
+          for (int q = 0; q < CW / 4; ++q)
+            reinterpret_cast<float4*>(op)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        } else {
+          for (int j = 0; j < CW; ++j)
+            if (co0 + j < p.cout) op[j] = f[j];
+        }
+      }
+    }
+  }
+  if (cpg >= CW && run_g >= 0) flush(run_s, run_ss, run_g);
+}
+
+}  // namespace b2d
+
+// One planned convolution: kernel parameters + launch geometry (opaque in include/b2d.h).
+struct b2d_conv_plan {
+  b2d::ConvKParams kp;
+  dim3 grid;
+  int block_n;
+  int kblocks;
+  int engine;          // 1: conv_igemm.cu (one tile per CTA), 2: conv_igemm2.cu (persistent)
+  long long ws_bytes;  // workspace bytes the plan uses (split-K partials + counters)
+};
+
+namespace b2d {
+// conv_igemm2.cu
+int launch_conv_v2(const b2d_conv_plan* plan, cudaStream_t st);
+}  // namespace b2d

@@ -12,69 +12,14 @@
 // Replaces (reference file:line): nn.Conv2d unet/blocks.py:29-36, models.py:120-128;
 // nn.ConvTranspose2d unet/blocks.py:128-133; nn.Conv3d vae/blocks.py:155-169, encoder.py:30-68,
 // decoder.py:31-71; nn.Linear/Conv1d projections of unet/blocks.py:196-207.
-#include <cuda.h>
-#include <cuda_runtime.h>
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <type_traits>
 
-#include "../../include/b2d.h"
-#include "b2d_internal.h"
-#include "b2d_ptx.cuh"
+#include "conv_common.cuh"
 
 namespace b2d {
-
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle atom
-constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kThreads = 192;
-
-struct ConvKParams {
-  CUtensorMap tmapA[B2D_MAX_SEG];
-  CUtensorMap tmapB;
-  int nseg;
-  int cchunks[B2D_MAX_SEG];
-  int kbase[B2D_MAX_SEG];
-  int cin[B2D_MAX_SEG];
-  int ntaps;
-  int8_t dz[B2D_MAX_TAPS], dy[B2D_MAX_TAPS], dx[B2D_MAX_TAPS];
-  int stride_h, stride_w;
-  int N, D, OH, OW;
-  int lbw, lbh, lbd, lbn;  // log2 box extents, bw*bh*bd*bn == 128
-  int tiles_w, tiles_h, tiles_d, tiles_n;
-  int cout, nphase;
-  const float* bias;
-  void* out;
-  void* out_lo;
-  int out_mode;
-  int out_H, out_W, out_sy, out_sx, out_oy, out_ox, out_cstride, out_coff;
-  const __nv_bfloat16* residual;
-  const __nv_bfloat16* residual_lo;
-  int res_cstride;
-  double* stats;
-  int stats_cpg;
-  const float* out_scale;
-  const float* out_mask;
-  int skip_z;
-  int out_f16, res_f16;
-};
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-// two fp32 -> packed IEEE fp16, saturating to +-65504 (raw pre-GroupNorm storage must never produce inf)
-__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
-  uint32_t r;
-  asm("{\n\t.reg .b16 lo, hi;\n\tcvt.rn.satfinite.f16.f32 lo, %1;\n\tcvt.rn.satfinite.f16.f32 hi, %2;\n\tmov.b32 %0, {lo, hi};\n\t}" : "=r"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ float2 unpack_f16(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 template <int BLOCK_N, int STAGES, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
@@ -198,164 +143,22 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_igemm_kernel(const __grid
     const long long img = (long long)on * p.D + oz;
     const long long opix = (img * p.out_H + out_y) * p.out_W + out_x;
 
-    // GroupNorm partial sums: segment of the warp that shares one sample
     const int rpi_log = p.lbw + p.lbh + p.lbd;  // rows per sample in the tile (log2)
     const int seg = rpi_log >= 5 ? 32 : (1 << rpi_log);
-    const int cpg = p.stats_cpg;
-    const int groups_per_n = (cpg > 0) ? (p.cout / cpg) : 0;
-    float run_s = 0.f, run_ss = 0.f;
-    int run_g = -1;
-
-    auto flush = [&](float s, float ss, int g) {
-      for (int off = seg >> 1; off > 0; off >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, off);
-        ss += __shfl_xor_sync(0xffffffffu, ss, off);
-      }
-      if ((lane & (seg - 1)) == 0 && on < p.N && g >= 0 && g < groups_per_n) {
-        double* dst = p.stats + ((long long)on * groups_per_n + g) * 2;
-        atomicAdd(dst, (double)s);
-        atomicAdd(dst + 1, (double)ss);
-      }
-    };
+    EpiRow rw;
+    rw.valid = valid; rw.on = on; rw.img = img; rw.opix = opix; rw.out_y = out_y; rw.out_x = out_x;
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-
-    float mask_v = 1.f;
-    if (p.out_mode == 1 && p.out_mask != nullptr && valid) mask_v = p.out_mask[opix];
-
-#pragma unroll 1
-    for (int col0 = 0; col0 < BLOCK_N; col0 += CW) {
+    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16);
+    auto load_tmem = [&](int col0, float (&f)[CW]) {
       uint32_t v[32];
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(col0);
-      if constexpr (CW == 32) tmem_ld_32x32(taddr, v); else tmem_ld_32x16(taddr, v);
+      if constexpr (CW == 32) tmem_ld_32x32(taddr + col0, v); else tmem_ld_32x16(taddr + col0, v);
       tmem_ld_wait();
-      const int co0 = co_base + col0;
-      float f[CW];
 #pragma unroll
-      for (int j = 0; j < CW; ++j) {
-        const int co = co0 + j;
-        float b = (p.bias != nullptr && co < p.cout) ? __ldg(p.bias + co) : 0.f;
-        f[j] = __uint_as_float(v[j]) + b;
-      }
-      if (p.residual != nullptr && valid) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + opix * p.res_cstride + co0);
-#pragma unroll
-        for (int q = 0; q < CW / 8; ++q) {
-          uint4 u = __ldg(rp + q);
-          if (p.res_f16) {
-            const float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
-            f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
-            f[q * 8 + 4] += c.x; f[q * 8 + 5] += c.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
-          } else {
-            f[q * 8 + 0] += bf16_lo(u.x); f[q * 8 + 1] += bf16_hi(u.x);
-            f[q * 8 + 2] += bf16_lo(u.y); f[q * 8 + 3] += bf16_hi(u.y);
-            f[q * 8 + 4] += bf16_lo(u.z); f[q * 8 + 5] += bf16_hi(u.z);
-            f[q * 8 + 6] += bf16_lo(u.w); f[q * 8 + 7] += bf16_hi(u.w);
-          }
-        }
-        if (p.residual_lo != nullptr) {
-          const uint4* rl = reinterpret_cast<const uint4*>(p.residual_lo + opix * p.res_cstride + co0);
-#pragma unroll
-          for (int q = 0; q < CW / 8; ++q) {
-            uint4 u = __ldg(rl + q);
-            f[q * 8 + 0] += bf16_lo(u.x); f[q * 8 + 1] += bf16_hi(u.x);
-            f[q * 8 + 2] += bf16_lo(u.y); f[q * 8 + 3] += bf16_hi(u.y);
-            f[q * 8 + 4] += bf16_lo(u.z); f[q * 8 + 5] += bf16_hi(u.z);
-            f[q * 8 + 6] += bf16_lo(u.w); f[q * 8 + 7] += bf16_hi(u.w);
-          }
-        }
-      }
-      // ---- GroupNorm partial sums (fp32 per thread, fp64 atomics per warp segment) -----------
-      if (cpg > 0) {
-        if (cpg >= CW) {
-          const int g = co0 / cpg;
-          if (g != run_g) {
-            if (run_g >= 0) flush(run_s, run_ss, run_g);
-            run_g = g; run_s = 0.f; run_ss = 0.f;
-          }
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) {
-              if (co0 + j < p.cout) { run_s += f[j]; run_ss += f[j] * f[j]; }
-            }
-          }
-        } else {
-          // cpg in {4, 8, 16}: several groups per chunk; compile-time trip counts keep f[] in registers
-          auto small_groups = [&](auto cpg_c) {
-            constexpr int CPG = decltype(cpg_c)::value;
-            if constexpr (CPG <= CW) {
-#pragma unroll
-              for (int g0 = 0; g0 < CW; g0 += CPG) {
-                float s = 0.f, ss = 0.f;
-#pragma unroll
-                for (int j = 0; j < CPG; ++j) { float x = valid ? f[g0 + j] : 0.f; s += x; ss += x * x; }
-                flush(s, ss, (co0 + g0) / CPG);
-              }
-            }
-          };
-          if (cpg == 4) small_groups(std::integral_constant<int, 4>{});
-          else if (cpg == 8) small_groups(std::integral_constant<int, 8>{});
-          else small_groups(std::integral_constant<int, 16>{});
-        }
-      }
-      // ---- store ---------------------------------------------------------------------------
-      if (valid) {
-        if (p.out_mode == 0) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + p.out_coff + co0;
-          uint32_t w[CW / 2];
-#pragma unroll
-          for (int j = 0; j < CW / 2; ++j) w[j] = p.out_f16 ? pack_f16_sat(f[2 * j], f[2 * j + 1]) : pack_bf16(f[2 * j], f[2 * j + 1]);
-          if (co0 + CW <= p.cout) {
-#pragma unroll
-            for (int q = 0; q < CW / 8; ++q)
-              reinterpret_cast<uint4*>(op)[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-          } else {
-            for (int j = 0; j < CW; ++j)
-              if (co0 + j < p.cout) reinterpret_cast<uint16_t*>(op)[j] = (uint16_t)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu));
-          }
-          if (p.out_lo != nullptr) {
-            __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + opix * p.out_cstride + p.out_coff + co0;
-            uint32_t wl[CW / 2];
-#pragma unroll
-            for (int j = 0; j < CW / 2; ++j)
-              wl[j] = pack_bf16(f[2 * j] - bf16_lo(w[j]), f[2 * j + 1] - bf16_hi(w[j]));
-            if (co0 + CW <= p.cout) {
-#pragma unroll
-              for (int q = 0; q < CW / 8; ++q)
-                reinterpret_cast<uint4*>(ol)[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
-            } else {
-              for (int j = 0; j < CW; ++j)
-                if (co0 + j < p.cout) ol[j] = __float2bfloat16_rn(f[j] - __bfloat162float(__float2bfloat16_rn(f[j])));
-            }
-          }
-        } else if (p.out_mode == 1) {
-          // planar fp32 [N][D][C][H][W]: lanes = consecutive x -> coalesced per channel
-          float* ob = reinterpret_cast<float*>(p.out);
-          const long long plane = (long long)p.out_H * p.out_W;
-          const long long pix = (long long)out_y * p.out_W + out_x;
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const int co = co0 + j;
-            if (co < p.cout) {
-              float sc = p.out_scale != nullptr ? __ldg(p.out_scale + co) : 1.f;
-              ob[(img * p.out_cstride + p.out_coff + co) * plane + pix] = f[j] * sc * mask_v;
-            }
-          }
-        } else {
-          float* op = reinterpret_cast<float*>(p.out) + opix * p.out_cstride + p.out_coff + co0;
-          if (co0 + CW <= p.cout) {
-#pragma unroll
-            for (int q = 0; q < CW / 4; ++q)
-              reinterpret_cast<float4*>(op)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-          } else {
-            for (int j = 0; j < CW; ++j)
-              if (co0 + j < p.cout) op[j] = f[j];
-          }
-        }
-      }
-    }
-    if (cpg >= CW && run_g >= 0) flush(run_s, run_ss, run_g);
+      for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
+    };
+    conv_epilogue_row<BLOCK_N, CW, false>(p, rw, co_base, lane, seg, nullptr, load_tmem);
   }
 
   tc_fence_before();
@@ -412,13 +215,6 @@ static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
 
 }  // namespace b2d
 
-struct b2d_conv_plan {
-  b2d::ConvKParams kp;
-  dim3 grid;
-  int block_n;
-  int kblocks;
-};
-
 using namespace b2d;
 
 extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_plan) {
@@ -450,7 +246,64 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   const long long tiles_m = (long long)((d->OW + (1 << lw) - 1) >> lw) * ((d->OH + (1 << lh) - 1) >> lh) *
                             ((d->D + (1 << ld) - 1) >> ld) * ((d->N + (1 << ln) - 1) >> ln);
 
+  // ---- engine selection -----------------------------------------------------------------------
+  static const int env_engine = [] { const char* e = getenv("B2D_CONV_ENGINE"); return e ? atoi(e) : 0; }();
+  const int engine = d->engine ? d->engine : (env_engine ? env_engine : 2);
+  if (engine != 1 && engine != 2) return set_error(B2D_E_INVALID, "engine=%d (0 auto, 1, 2)", engine);
+  // halo staging: canonical 3x3 / 3x3x3 'same' taps in (z, y, x) order, stride 1, 16x16 super-tiles, BLOCK_N <= 128
+  bool halo = false;
+  if (engine == 2 && d->stride_h == 1 && d->stride_w == 1 && d->nphase == 1 && (d->ntaps == 9 || d->ntaps == 27) &&
+      d->OW % 16 == 0 && d->OH % 16 == 0 && d->OW == d->W && d->OH == d->H && (d->cout <= 16 || d->cout % 64 == 0) &&
+      (d->block_n == 0 || d->block_n == 16 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256)) {
+    static const bool no_halo = getenv("B2D_CONV_NO_HALO") != nullptr;
+    halo = !no_halo;
+    for (int t = 0; t < d->ntaps && halo; ++t) {
+      const int ip = t % 9;
+      if (d->tap_dy[t] != ip / 3 - 1 || d->tap_dx[t] != ip % 3 - 1 || d->tap_dz[t] != d->tap_dz[(t / 9) * 9]) halo = false;
+    }
+  }
+  long long tiles_m2 = tiles_m;
+  if (halo) {
+    lw = 4; lh = 4; ld = 0; ln = 0;
+    tiles_m2 = (long long)(d->OW / 16) * (d->OH / 16) * d->D * d->N;
+  }
+
+  // ---- persistent engine: pick (BLOCK_N, K splits) by a small cost model -----------------------
+  // cost = waves over the SMs x (K-loop time of one unit + epilogue / split-K fix-up), in SM clocks.
   int bn = d->block_n;
+  int ksplit_pick = 1;
+  if (engine == 2) {
+    const int sms = num_sms();
+    const long long cols = (long long)d->cout * d->nphase;
+    long long ngroups = 0;
+    for (int s = 0; s < d->nseg; ++s) ngroups += (long long)(halo ? d->ntaps / 9 : d->ntaps) * (d->cin[s] / kBlockK);
+    bool all_dz0 = true;
+    for (int t = 0; t < d->ntaps; ++t) all_dz0 = all_dz0 && d->tap_dz[t] == 0;
+    static const bool no_split = getenv("B2D_CONV_NO_SPLITK") != nullptr;
+    const bool can_split = !no_split && all_dz0 && d->workspace && (reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0;
+    const int mt = halo ? 2 : 1;
+    const int cand[4] = {256, 128, 64, 16};
+    double best = 1e30;
+    int best_bn = 0;
+    for (int ci = 0; ci < 4; ++ci) {
+      const int b = cand[ci];
+      if (d->block_n && d->block_n != b) continue;
+      if (b == 16 ? (d->cout > 16 || d->nphase != 1) : (d->cout % b != 0)) continue;
+      const long long tiles = tiles_m2 * (b == 16 ? 1 : cols / b);
+      const double t_kb = b == 256 ? 512.0 : b == 128 ? 256.0 : b == 64 ? 192.0 : 128.0;
+      const double per_group = (halo ? 18.0 : 1.0) * t_kb;
+      for (int ks = 1; ks <= 16; ++ks) {
+        if (ks > 1 && (!can_split || ngroups / ks < 4 || tiles * mt > 4096 || tiles >= 2LL * sms ||
+                       16384 + tiles * ks * mt * 128LL * b * 4 > d->workspace_bytes)) break;
+        const double unit = (double)((ngroups + ks - 1) / ks) * per_group + 1500.0 + 8.0 * b * mt + (ks > 1 ? 2500.0 : 0.0);
+        const double waves = (double)((tiles * ks + sms - 1) / sms);
+        const double cost = waves * unit;
+        if (cost < best * 0.999) { best = cost; best_bn = b; ksplit_pick = ks; }
+      }
+    }
+    if (best_bn == 0) return set_error(B2D_E_INVALID, "cout=%d block_n=%d: need cout a multiple of 64 (or <= 16)", d->cout, d->block_n);
+    bn = best_bn;
+  }
   if (bn == 0) {
     // Widest N tile that still fills the machine: N=256 needs 96 B/clk of smem operand reads per MMA
     // (128 B/clk at N=128), but small-M layers (deep UNet levels) need the CTA count more.
@@ -509,6 +362,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     strides[3] = strides[2] * d->D;
     cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)((1 << lw) * d->stride_w), (cuuint32_t)((1 << lh) * d->stride_h),
                          (cuuint32_t)(1 << ld), (cuuint32_t)(1 << ln)};
+    if (halo) { box[1] = 18; box[2] = 18; box[3] = 1; box[4] = 1; }
     cuuint32_t estr[5] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1, 1};
     CUresult r = enc(&k.tmapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->in[s]), dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -560,6 +414,32 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   int kb = 0;
   for (int s = 0; s < d->nseg; ++s) kb += d->ntaps * k.cchunks[s];
   pl->kblocks = kb;
+  pl->engine = engine;
+  pl->ws_bytes = 0;
+  if (engine == 2) {
+    // ---- persistent engine: work units, K-loop groups, split-K ---------------------------------
+    k.halo = halo ? 1 : 0;
+    k.gtaps = halo ? 9 : 1;
+    const int tgroups = halo ? d->ntaps / 9 : d->ntaps;  // A loads per (segment, chunk)
+    k.goff[0] = 0;
+    for (int s = 0; s < d->nseg; ++s) k.goff[s + 1] = k.goff[s] + tgroups * k.cchunks[s];
+    k.ngroups = k.goff[d->nseg];
+    k.tiles_ncol = total_cols / bn;
+    const long long tiles = (long long)k.tiles_w * k.tiles_h * k.tiles_d * k.tiles_n * k.tiles_ncol;
+    if (tiles > 0x3fffffff) { delete pl; return set_error(B2D_E_INVALID, "too many tiles"); }
+    const int sms = num_sms();
+    const int mt = halo ? 2 : 1;
+    const int ksplit = ksplit_pick;
+    constexpr long long kCounterBytes = 16384;
+    k.ksplit = ksplit;
+    k.num_units = (int)(tiles * ksplit);
+    if (ksplit > 1) {
+      k.counters = reinterpret_cast<int*>(d->workspace);
+      k.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->workspace) + kCounterBytes);
+      pl->ws_bytes = kCounterBytes + tiles * ksplit * mt * 128LL * bn * 4;
+    }
+    pl->grid = dim3((unsigned)(k.num_units < sms ? k.num_units : sms), 1, 1);
+  }
   *out_plan = pl;
   return B2D_OK;
 }
@@ -581,6 +461,7 @@ extern "C" int b2d_conv_plan_info(const b2d_conv_plan* plan, int32_t* grid_m, in
 extern "C" int b2d_conv_run(const b2d_conv_plan* plan, void* stream) {
   if (!plan) return set_error(B2D_E_INVALID, "null plan");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (plan->engine == 2) return launch_conv_v2(plan, st);
   switch (plan->block_n) {
     // two co-resident CTAs per SM where shared memory allows: one CTA's epilogue overlaps the other's main loop
     case 16: return launch_conv<16, 5, 2>(plan->kp, plan->grid, st);
@@ -589,4 +470,17 @@ extern "C" int b2d_conv_run(const b2d_conv_plan* plan, void* stream) {
     case 256: return launch_conv<256, 4, 1>(plan->kp, plan->grid, st);
   }
   return set_error(B2D_E_INVALID, "bad block_n");
+}
+
+extern "C" int b2d_conv_plan_info2(const b2d_conv_plan* plan, int32_t* out8) {
+  if (!plan || !out8) return set_error(B2D_E_INVALID, "null argument");
+  out8[0] = plan->engine;
+  out8[1] = plan->kp.halo;
+  out8[2] = plan->engine == 2 ? plan->kp.ksplit : 1;
+  out8[3] = plan->engine == 2 ? plan->kp.num_units : (int32_t)(plan->grid.x * plan->grid.y);
+  out8[4] = (int32_t)(plan->grid.x * plan->grid.y);
+  out8[5] = plan->block_n;
+  out8[6] = plan->engine == 2 ? plan->kp.ngroups : plan->kblocks;
+  out8[7] = (int32_t)((plan->ws_bytes + 1023) / 1024);
+  return B2D_OK;
 }

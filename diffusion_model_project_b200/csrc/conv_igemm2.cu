@@ -1,0 +1,422 @@
+// Persistent implicit-GEMM convolution engine for sm_100a (second generation of conv_igemm.cu).
+//
+// One CTA per SM walks a static list of work units (output tile x N tile x K split):
+//   warp 0      TMA producer   -- activation ring (A) and weight ring (B), separate mbarrier pairs
+//   warp 1      MMA issuer     -- tcgen05.mma into one of TWO TMEM accumulator stages
+//   warps 2..   epilogue       -- drain the other accumulator stage (tcgen05.ld) while the next
+//                                 unit's main loop runs: bias, residual, GroupNorm sums, store
+//
+// Two ways of staging the A operand:
+//   * generic: one 128-row box per (tap, 64-channel chunk), as in the first engine (any stride,
+//     1x1 GEMMs, transposed-conv phases, small maps).
+//   * halo (stride-1 3x3 / 3x3x3, W,H multiples of 16): ONE TMA box of 18 x 18 pixels x 64 channels
+//     per (z-tap, chunk) serves all nine in-plane taps of a 16 x 16 output super-tile.  The tile is
+//     two M = 128 halves (8 px x 16 lines); a tap (dy,dx) is just a row offset into the staged box:
+//     UMMA descriptor start = box + ((1+dy)*18 + (1+dx) + 8*half) * 128 B, 8-row-group stride
+//     (SBO) = 18 * 128 B.  This relies on the 128B swizzle being a function of the absolute shared
+//     memory address (tools/probe/umma_probe.cu, profiles/r1_umma_swizzle_probe.txt), and cuts the
+//     L2 -> SM activation traffic 9x tap re-reads -> 1.27x (324 staged rows per 256 outputs).
+//
+// Split-K (deep UNet levels: M of a few hundred rows, K up to 18432): every split writes its fp32
+// partial tile to a workspace; the last split to arrive (atomic ticket, no spinning) sums all
+// partials in a fixed order -- deterministic -- and runs the fused epilogue.
+#include "conv_common.cuh"
+
+namespace b2d {
+
+template <int BN, bool HALO>
+struct V2Cfg {
+  static constexpr int MT = HALO ? 2 : 1;                       // M = 128 halves per unit
+  static constexpr int A_TILE = HALO ? 18 * 18 * 128 : kABytes;  // bytes landed per A load
+  static constexpr int A_STAGE = (A_TILE + 1023) / 1024 * 1024;
+  // weight taps per B stage: narrow N tiles batch several taps behind one mbarrier so the single
+  // MMA-issuing thread is not handshake-bound (an N = 16 MMA lasts ~32 clocks)
+  static constexpr int TPB = HALO ? (BN <= 16 ? 9 : BN <= 64 ? 3 : 1) : 1;
+  static constexpr int B_TILE = BN * kBlockK * 2;
+  static constexpr int B_STAGE = TPB * B_TILE;
+  static constexpr int NA = HALO ? (BN >= 128 ? 2 : 3) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
+  static constexpr int NB = HALO ? (BN == 256 ? 4 : BN == 128 ? 6 : BN == 64 ? 4 : 3) : NA;
+  static constexpr int BNC = BN < 32 ? 32 : BN;                  // TMEM columns of one M half
+  static constexpr int ACC_COLS = MT * BNC;                      // one accumulator stage
+  static constexpr int NACC = 2 * ACC_COLS <= 512 ? 2 : 1;       // BN = 256 halo: 512 columns, single-buffered
+  static constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : NACC * ACC_COLS <= 64 ? 64 : NACC * ACC_COLS <= 128 ? 128
+                                   : NACC * ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int EPI_WARPS = 4 * MT;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int NBARS = 2 * NA + 2 * NB + 4;
+  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 + 1024;
+  static_assert(NACC * ACC_COLS <= 512, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(!HALO || 9 % TPB == 0, "taps per stage must divide 9");
+};
+
+struct UnitCoord {
+  int x0, y0, z0, n0, gcol0, ks, tile;  // tile = m_tile * tiles_ncol + n_tile
+};
+
+__device__ __forceinline__ UnitCoord decode_unit(const ConvKParams& p, int u) {
+  UnitCoord c;
+  c.ks = u % p.ksplit;
+  int t = u / p.ksplit;
+  c.tile = t;
+  const int nt = t % p.tiles_ncol;
+  t /= p.tiles_ncol;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int td = t % p.tiles_d; t /= p.tiles_d;
+  c.x0 = tw << p.lbw; c.y0 = th << p.lbh; c.z0 = td << p.lbd; c.n0 = t << p.lbn;
+  c.gcol0 = nt;
+  return c;
+}
+
+// iterate the A-groups [g_lo, g_hi) of one unit as (segment, tap-or-ztap, chunk)
+struct GroupIter {
+  int s, t, c, g, g_hi;
+  __device__ __forceinline__ void init(const ConvKParams& p, int ks) {
+    g = (int)((long long)p.ngroups * ks / p.ksplit);
+    g_hi = (int)((long long)p.ngroups * (ks + 1) / p.ksplit);
+    s = 0;
+    while (s + 1 < p.nseg && g >= p.goff[s + 1]) ++s;
+    const int r = g - p.goff[s];
+    t = r / p.cchunks[s];
+    c = r - t * p.cchunks[s];
+  }
+  __device__ __forceinline__ bool done() const { return g >= g_hi; }
+  __device__ __forceinline__ void next(const ConvKParams& p) {
+    ++g;
+    if (++c == p.cchunks[s]) {
+      c = 0;
+      ++t;
+      if (g == p.goff[s + 1]) { t = 0; ++s; }
+    }
+  }
+};
+
+template <int BN, bool HALO>
+__global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(const __grid_constant__ ConvKParams p) {
+  using Cfg = V2Cfg<BN, HALO>;
+  constexpr int MT = Cfg::MT, NA = Cfg::NA, NB = Cfg::NB;
+  constexpr int CW = BN < 32 ? 16 : 32;
+
+  extern __shared__ uint8_t smem_raw2[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + NA * Cfg::A_STAGE;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + NB * Cfg::B_STAGE);
+  uint64_t* a_empty = a_full + NA;
+  uint64_t* b_full = a_empty + NA;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* t_full = b_empty + NB;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [MT]
+  double* sm_stats = reinterpret_cast<double*>(tmem_slot + 4);               // [64] per-CTA GroupNorm sums (halo mode)
+
+  // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], Cfg::EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) sm_stats[threadIdx.x - 64] = 0.0;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&p.tmapA[s]);
+    prefetch_tmap(&p.tmapB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer =========================================
+    // The whole warp walks the loop (uniform control flow and addresses); one elected lane issues.
+    int ast = 0, bst = 0;
+    uint32_t aph = 0, bph = 0;
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const UnitCoord uc = decode_unit(p, u);
+      const int gcol0 = uc.gcol0 * BN;
+      GroupIter it;
+      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
+        const int s = it.s;
+        if constexpr (HALO) {
+          const int zz = uc.z0 + p.dz[it.t * 9];
+          if (zz < 0 || zz >= p.D) continue;
+          mbar_wait(&a_empty[ast], aph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[ast], Cfg::A_TILE);
+            tma_load_5d_u(sA_u + ast * Cfg::A_STAGE, &p.tmapA[s], smem_u32(&a_full[ast]), it.c * kBlockK, uc.x0 - 1, uc.y0 - 1, zz, uc.n0);
+          }
+          __syncwarp();
+          if (++ast == NA) { ast = 0; aph ^= 1; }
+          const int kb = p.kbase[s] + it.t * 9 * p.cin[s] + it.c * kBlockK;
+#pragma unroll 1
+          for (int ip = 0; ip < 9; ip += Cfg::TPB) {
+            mbar_wait(&b_empty[bst], bph ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
+#pragma unroll
+              for (int j = 0; j < Cfg::TPB; ++j)
+                tma_load_2d_u(sB_u + bst * Cfg::B_STAGE + j * Cfg::B_TILE, &p.tmapB, smem_u32(&b_full[bst]), kb + (ip + j) * p.cin[s], gcol0);
+            }
+            __syncwarp();
+            if (++bst == NB) { bst = 0; bph ^= 1; }
+          }
+        } else {
+          const int tp = it.t;
+          const int zz = uc.z0 + p.dz[tp];
+          if (p.skip_z && (zz < 0 || zz >= p.D)) continue;
+          const int xx = uc.x0 * p.stride_w + p.dx[tp];
+          const int yy = uc.y0 * p.stride_h + p.dy[tp];
+          mbar_wait(&a_empty[ast], aph ^ 1);
+          mbar_wait(&b_empty[bst], bph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[ast], Cfg::A_TILE);
+            tma_load_5d_u(sA_u + ast * Cfg::A_STAGE, &p.tmapA[s], smem_u32(&a_full[ast]), it.c * kBlockK, xx, yy, zz, uc.n0);
+            mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
+            tma_load_2d_u(sB_u + bst * Cfg::B_STAGE, &p.tmapB, smem_u32(&b_full[bst]), p.kbase[s] + tp * p.cin[s] + it.c * kBlockK, gcol0);
+          }
+          __syncwarp();
+          if (++ast == NA) { ast = 0; aph ^= 1; }
+          if (++bst == NB) { bst = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===========================================
+    // Uniform loop; descriptors are 64-bit constants whose low word (start address >> 4) is the only
+    // thing that moves, so the per-MMA work is one 32-bit uniform add.
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+    const uint64_t adesc0 = umma_smem_desc(smem_u32(sA), HALO ? 18 * 128 : 1024, 2);
+    const uint64_t bdesc0 = umma_smem_desc(smem_u32(sB), 1024, 2);
+    const uint32_t adesc_hi = (uint32_t)(adesc0 >> 32), bdesc_hi = (uint32_t)(bdesc0 >> 32);
+    const uint32_t adesc_lo0 = (uint32_t)adesc0, bdesc_lo0 = (uint32_t)bdesc0;
+    int ast = 0, bst = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, accph = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const UnitCoord uc = decode_unit(p, u);
+      mbar_wait(&t_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+      uint32_t accum = 0;
+      GroupIter it;
+      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
+        if constexpr (HALO) {
+          const int zz = uc.z0 + p.dz[it.t * 9];
+          if (zz < 0 || zz >= p.D) continue;
+        } else {
+          const int zz = uc.z0 + p.dz[it.t];
+          if (p.skip_z && (zz < 0 || zz >= p.D)) continue;
+        }
+        mbar_wait(&a_full[ast], aph);
+        const uint32_t a_lo = adesc_lo0 + (uint32_t)(ast * (Cfg::A_STAGE >> 4));
+        constexpr int GT = HALO ? 9 : 1;
+#pragma unroll 1
+        for (int ip = 0; ip < GT; ip += Cfg::TPB) {
+          mbar_wait(&b_full[bst], bph);
+          tc_fence_after();
+          const uint32_t b_lo = bdesc_lo0 + (uint32_t)(bst * (Cfg::B_STAGE >> 4));
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < Cfg::TPB; ++j) {
+              // tap (dy,dx) = row offset ((1+dy)*18 + (1+dx)) * 128 B into the staged halo box (8 = 128 B >> 4)
+              const int tap = ip + j;
+              const uint32_t a_tap = HALO ? a_lo + (uint32_t)(((tap / 3) * 18 + (tap % 3)) * 8) : a_lo;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  const uint64_t ad = ((uint64_t)adesc_hi << 32) | (a_tap + (uint32_t)(mt * 64 + 2 * k));
+                  const uint64_t bd = ((uint64_t)bdesc_hi << 32) | (b_lo + (uint32_t)(j * (Cfg::B_TILE >> 4) + 2 * k));
+                  umma_bf16(d_tmem + mt * Cfg::BNC, ad, bd, idesc, (accum | (uint32_t)(j > 0)) | (uint32_t)(k > 0));
+                }
+              }
+            }
+            umma_commit(&b_empty[bst]);
+          }
+          __syncwarp();
+          accum = 1;
+          if (++bst == NB) { bst = 0; bph ^= 1; }
+        }
+        if (elect_one()) umma_commit(&a_empty[ast]);
+        __syncwarp();
+        if (++ast == NA) { ast = 0; aph ^= 1; }
+      }
+      if (elect_one()) umma_commit(&t_full[acc]);
+      __syncwarp();
+      if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
+    }
+  } else {
+    // ================================ epilogue ==============================================
+    const int ew = warp - 2;
+    const int mt = ew >> 2;      // M half handled by this group of four warps
+    const int quad = warp & 3;   // TMEM lane quadrant this warp may read
+    const int r = quad * 32 + lane;
+    const int rpi_log = HALO ? 7 : (p.lbw + p.lbh + p.lbd);
+    const int seg = rpi_log >= 5 ? 32 : (1 << rpi_log);
+    int acc = 0;
+    uint32_t accph = 0;
+    // halo mode: GroupNorm sums of the current sample accumulate in shared memory and reach global memory
+    // only when this CTA moves on to another sample (one fp64 atomic per group instead of one per warp per unit)
+    constexpr bool SMEM_STATS = HALO;
+    int cur_n = -1;
+    const int epi_tid = threadIdx.x - 64;
+    auto flush_stats = [&]() {
+      if constexpr (SMEM_STATS) {
+        if (p.stats_cpg > 0) {
+          const int ng2 = 2 * (p.cout / p.stats_cpg);
+          asm volatile("bar.sync 3, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
+          if (cur_n >= 0 && epi_tid < ng2) {
+            const double v = sm_stats[epi_tid];
+            if (v != 0.0) atomicAdd(p.stats + (long long)cur_n * ng2 + epi_tid, v);
+            sm_stats[epi_tid] = 0.0;
+          }
+          asm volatile("bar.sync 3, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
+        }
+      }
+    };
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const UnitCoord uc = decode_unit(p, u);
+      if constexpr (SMEM_STATS) {
+        if (uc.n0 != cur_n) { flush_stats(); cur_n = uc.n0; }
+      }
+      int ox, oy, oz, on;
+      if constexpr (HALO) {
+        ox = uc.x0 + mt * 8 + (r & 7);
+        oy = uc.y0 + (r >> 3);
+        oz = uc.z0;
+        on = uc.n0;
+      } else {
+        const int mw = (1 << p.lbw) - 1, mh = (1 << p.lbh) - 1, md = (1 << p.lbd) - 1;
+        ox = uc.x0 + (r & mw);
+        oy = uc.y0 + ((r >> p.lbw) & mh);
+        oz = uc.z0 + ((r >> (p.lbw + p.lbh)) & md);
+        on = uc.n0 + (r >> (p.lbw + p.lbh + p.lbd));
+      }
+      EpiRow rw;
+      rw.valid = ox < p.OW && oy < p.OH && oz < p.D && on < p.N;
+      rw.on = on;
+      const int gcol0 = uc.gcol0 * BN;
+      int phase_idx = 0, co_base = gcol0;
+      if (p.nphase > 1) { phase_idx = gcol0 / p.cout; co_base = gcol0 - phase_idx * p.cout; }
+      rw.out_y = oy * p.out_sy + p.out_oy + ((p.nphase > 1) ? (phase_idx >> 1) : 0);
+      rw.out_x = ox * p.out_sx + p.out_ox + ((p.nphase > 1) ? (phase_idx & 1) : 0);
+      rw.img = (long long)on * p.D + oz;
+      rw.opix = (rw.img * p.out_H + rw.out_y) * p.out_W + rw.out_x;
+
+      mbar_wait(&t_full[acc], accph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + mt * Cfg::BNC);
+      auto load_tmem = [&](int col0, float (&f)[CW]) {
+        uint32_t v[32];
+        if constexpr (CW == 32) tmem_ld_32x32(taddr + col0, v); else tmem_ld_32x16(taddr + col0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
+      };
+      if (p.ksplit == 1) {
+        conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats, load_tmem);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[acc]);
+      } else {
+        // ---- split-K: park the fp32 partial, the last split to arrive reduces in a fixed order ----
+        float* wrow = p.ws + (((long long)uc.tile * p.ksplit + uc.ks) * MT + mt) * (128LL * BN) + (long long)r * BN;
+#pragma unroll 1
+        for (int col0 = 0; col0 < BN; col0 += CW) {
+          float f[CW];
+          load_tmem(col0, f);
+#pragma unroll
+          for (int q = 0; q < CW / 4; ++q)
+            __stcg(reinterpret_cast<float4*>(wrow + col0) + q, make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[acc]);
+        __threadfence();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        if ((threadIdx.x & 127) == 64) {  // first thread of this four-warp group (warps 2.. start at thread 64)
+          const int old = atomicAdd(p.counters + uc.tile * MT + mt, 1);
+          const int last = (old == p.ksplit - 1) ? 1 : 0;
+          if (last) p.counters[uc.tile * MT + mt] = 0;  // self-reset for the next launch
+          last_flag[mt] = last;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        if (last_flag[mt]) {
+          __threadfence();
+          const float* wbase = p.ws + (((long long)uc.tile * p.ksplit) * MT + mt) * (128LL * BN) + (long long)r * BN;
+          const long long ks_stride = (long long)MT * 128 * BN;
+          auto load_ws = [&](int col0, float (&f)[CW]) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) f[j] = 0.f;
+            for (int ks = 0; ks < p.ksplit; ++ks) {
+              const float4* src = reinterpret_cast<const float4*>(wbase + ks * ks_stride + col0);
+#pragma unroll
+              for (int q = 0; q < CW / 4; ++q) {
+                const float4 v = __ldcg(src + q);
+                f[4 * q] += v.x; f[4 * q + 1] += v.y; f[4 * q + 2] += v.z; f[4 * q + 3] += v.w;
+              }
+            }
+          };
+          conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats, load_ws);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // last_flag is reused by the next unit
+      }
+      if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
+    }
+    flush_stats();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, bool HALO>
+static int launch_v2(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
+  using Cfg = V2Cfg<BN, HALO>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_v2_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  conv_v2_kernel<BN, HALO><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(kp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "conv_v2 launch: %s", cudaGetErrorString(e));
+  return B2D_OK;
+}
+
+int launch_conv_v2(const b2d_conv_plan* plan, cudaStream_t st) {
+  const ConvKParams& kp = plan->kp;
+  if (kp.halo) {
+    switch (plan->block_n) {
+      case 16: return launch_v2<16, true>(kp, plan->grid, st);
+      case 64: return launch_v2<64, true>(kp, plan->grid, st);
+      case 128: return launch_v2<128, true>(kp, plan->grid, st);
+      case 256: return launch_v2<256, true>(kp, plan->grid, st);
+    }
+  } else {
+    switch (plan->block_n) {
+      case 16: return launch_v2<16, false>(kp, plan->grid, st);
+      case 64: return launch_v2<64, false>(kp, plan->grid, st);
+      case 128: return launch_v2<128, false>(kp, plan->grid, st);
+      case 256: return launch_v2<256, false>(kp, plan->grid, st);
+    }
+  }
+  return set_error(B2D_E_INVALID, "conv v2: bad block_n %d (halo %d)", plan->block_n, kp.halo);
+}
+
+}  // namespace b2d

@@ -151,12 +151,27 @@ def pack_linear(w, bias, device, split=False):
 # ------------------------------------------------------------------------------------------------
 # conv plans
 # ------------------------------------------------------------------------------------------------
+_WORKSPACE: dict = {}
+WORKSPACE_BYTES = 64 << 20
+
+
+def workspace(device) -> torch.Tensor:
+    """Split-K scratch shared by every plan of a device (plans run back to back on one stream).  The first
+    16 KB are arrival counters: zero-initialised once, each kernel leaves them zero again."""
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _WORKSPACE:
+        _WORKSPACE[key] = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
+    return _WORKSPACE[key]
+
+
 class ConvPlan:
     """Owns a b2d_conv_plan and keeps every tensor whose address is baked into it alive."""
 
     def __init__(self, inputs: Sequence[Act], pw: PackedWeight, out, *, cout: int, nphase: int = 1, stride: int = 1,
                  out_mode: int = 0, out_geom=None, residual: Optional[Act] = None, stats: Optional[torch.Tensor] = None,
-                 stats_cpg: int = 0, out_scale=None, out_mask=None, block_n: int = 0, out_cstride=None, out_coff: int = 0):
+                 stats_cpg: int = 0, out_scale=None, out_mask=None, block_n: int = 0, out_cstride=None, out_coff: int = 0,
+                 engine: int = 0):
         N, D, H, W, _ = inputs[0].shape
         d = ConvDesc()
         split = pw.split
@@ -209,6 +224,10 @@ class ConvPlan:
         d.out_scale = ptr(out_scale)
         d.out_mask = ptr(out_mask)
         d.block_n = block_n
+        d.engine = engine
+        ws = workspace(inputs[0].hi.device)
+        d.workspace = ws.data_ptr()
+        d.workspace_bytes = ws.numel()
         self._keep = (inputs, pw, out, residual, stats, out_scale, out_mask)
         self.desc = d
         self.handle = C.c_void_p()
@@ -219,6 +238,11 @@ class ConvPlan:
         gm, gn, bn, kb = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         _lib.check(_lib.lib().b2d_conv_plan_info(self.handle, C.byref(gm), C.byref(gn), C.byref(bn), C.byref(kb)))
         return dict(grid_m=gm.value, grid_n=gn.value, block_n=bn.value, kblocks=kb.value)
+
+    def info2(self):
+        out = (C.c_int32 * 8)()
+        _lib.check(_lib.lib().b2d_conv_plan_info2(self.handle, out))
+        return dict(zip(("engine", "halo", "ksplit", "units", "ctas", "block_n", "kgroups", "ws_kib"), list(out)))
 
     def run(self, stream: int):
         call("b2d_conv_run", self.handle, stream)

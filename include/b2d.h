@@ -33,7 +33,7 @@ extern "C" {
 #define B2D_API
 #endif
 
-#define B2D_VERSION 1
+#define B2D_VERSION 2
 #define B2D_MAX_SEG 6
 #define B2D_MAX_TAPS 27
 
@@ -113,7 +113,11 @@ typedef struct b2d_conv_desc {
   int32_t out_f16;                 /* mode 0: store IEEE fp16 (saturating) instead of bf16 -- for raw pre-GroupNorm
                                       outputs / residual streams that are never an MMA operand            */
   int32_t res_f16;                 /* residual tensor holds fp16 instead of bf16                         */
-  int32_t reserved[5];
+  int32_t engine;                  /* 0 = auto, 1 = one tile per CTA (conv_igemm.cu), 2 = persistent (conv_igemm2.cu) */
+  void* workspace;                 /* optional caller-owned scratch for split-K (first 16 KB: zero-initialised arrival
+                                      counters, then fp32 partial tiles); shared by plans that run on one stream      */
+  int64_t workspace_bytes;
+  int32_t reserved[4];
 } b2d_conv_desc;
 
 typedef struct b2d_conv_plan b2d_conv_plan;
@@ -122,6 +126,8 @@ B2D_API int b2d_conv_plan_destroy(b2d_conv_plan* plan);
 B2D_API int b2d_conv_run(const b2d_conv_plan* plan, void* stream);
 /* number of CTAs / block_n the plan launches with (introspection for tests and the bench) */
 B2D_API int b2d_conv_plan_info(const b2d_conv_plan* plan, int32_t* grid_m, int32_t* grid_n, int32_t* block_n, int32_t* kblocks);
+/* out[8] = {engine, halo, ksplit, work units, CTAs launched, block_n, K-loop groups, workspace bytes used (KiB)} */
+B2D_API int b2d_conv_plan_info2(const b2d_conv_plan* plan, int32_t* out8);
 
 /* ------------------------------------------------------------------------------------------
  * GroupNorm apply (+SiLU, + time-embedding add), stats come from the producer's epilogue.

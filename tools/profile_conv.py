@@ -1,7 +1,8 @@
-"""Smallest program that launches the dominant kernel of the sampling path in its dominant shape:
-conv_igemm_kernel<128,...> on D3D's 128->128 3x3x3 conv at 11x256x256 (B samples).  Used under
-`ncu --set full -k regex:conv_igemm` and for quick timing of tile/stage variants.
-usage: python tools/profile_conv.py [B] [cin] [cout] [H] [block_n] [reps]"""
+"""Smallest program that launches one planned convolution of the sampling path, for quick timing of engine /
+tile variants and as the target of `ncu --set full -k regex:conv_`.
+usage: python tools/profile_conv.py kind N cin cout H [block_n] [engine] [reps]
+  kind = 3d  : Conv3d 3x3x3 on [N][11][H][H][cin]   (VAE; default 8 128 128 256 = D3D res3 conv)
+  kind = 2d  : Conv2d 3x3 on [N][1][H][H][cin]      (UNet; e.g. 88 64 64 64 = encoder.0 block2)"""
 import os
 import sys
 
@@ -12,31 +13,41 @@ sys.path.insert(0, ROOT)
 from diffusion_model_project_b200 import engine  # noqa: E402
 from diffusion_model_project_b200.engine import ConvPlan, new_act  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-cin = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-cout = int(sys.argv[3]) if len(sys.argv) > 3 else 128
-H = int(sys.argv[4]) if len(sys.argv) > 4 else 256
-bn = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-reps = int(sys.argv[6]) if len(sys.argv) > 6 else 5
-D = 11
+a = sys.argv[1:]
+kind = a[0] if len(a) > 0 else "3d"
+N = int(a[1]) if len(a) > 1 else 8
+cin = int(a[2]) if len(a) > 2 else 128
+cout = int(a[3]) if len(a) > 3 else 128
+H = int(a[4]) if len(a) > 4 else 256
+bn = int(a[5]) if len(a) > 5 else 0
+eng = int(a[6]) if len(a) > 6 else 0
+reps = int(a[7]) if len(a) > 7 else 5
+use_stats = int(a[8]) if len(a) > 8 else 1
+D = 11 if kind == "3d" else 1
 dev = "cuda"
 g = torch.Generator().manual_seed(0)
-x = new_act(B, D, H, H, cin, dev)
-x.hi.copy_(torch.randn(B, D, H, H, cin, generator=g).to(torch.bfloat16))
-w = torch.randn(cout, cin, 3, 3, 3, generator=g) * (27 * cin) ** -0.5
-pw = engine.pack_conv3d(w, torch.zeros(cout), dev)
-out = new_act(B, D, H, H, cout, dev)
-st = torch.zeros(B, 32, 2, dtype=torch.float64, device=dev)
-plan = ConvPlan([x], pw, out, cout=cout, stats=st, stats_cpg=cout // 32, block_n=bn)
+x = new_act(N, D, H, H, cin, dev)
+x.hi.copy_(torch.randn(N, D, H, H, cin, generator=g).to(torch.bfloat16))
+if kind == "3d":
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) * (27 * cin) ** -0.5
+    pw = engine.pack_conv3d(w, torch.zeros(cout), dev)
+    groups = 32
+else:
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (9 * cin) ** -0.5
+    pw = engine.pack_conv2d(w, [cin], None, dev)
+    groups = 1
+out = new_act(N, D, H, H, cout, dev)
+st = torch.zeros(N, groups, 2, dtype=torch.float64, device=dev)
+plan = ConvPlan([x], pw, out, cout=cout, stats=st if use_stats else None, stats_cpg=cout // groups if use_stats else 0, block_n=bn, engine=eng)
 s = torch.cuda.current_stream().cuda_stream
 for _ in range(2):
     plan.run(s)
 torch.cuda.synchronize()
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 for _ in range(reps):
     plan.run(s)
-b.record()
+e1.record()
 torch.cuda.synchronize()
-ms = a.elapsed_time(b) / reps
-print(f"conv3d {cin}->{cout} B={B} {D}x{H}x{H} {plan.info()} : {ms:.3f} ms/launch, {plan.flops / ms / 1e9:.1f} TFLOP/s")
+ms = e0.elapsed_time(e1) / reps
+print(f"stats={use_stats} conv{kind} {cin}->{cout} N={N} {D}x{H}x{H} {plan.info2()} : {ms * 1e3:.1f} us/launch, {plan.flops / ms / 1e9:.1f} TFLOP/s")

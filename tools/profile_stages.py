@@ -50,5 +50,5 @@ for stage in ("e2d", "unet", "d3d"):
         fn = dict(prog.steps)[n]
         owner = getattr(fn, "__self__", None)
         if owner is not None and hasattr(owner, "flops"):
-            extra = f"  {owner.flops / t / 1e6:7.1f} TFLOP/s  {owner.info()}"
+            i2 = owner.info2(); extra = f"  {owner.flops / t / 1e6:7.1f} TFLOP/s  e{i2["engine"]} halo{i2["halo"]} ks{i2["ksplit"]} units{i2["units"]} ctas{i2["ctas"]} bn{i2["block_n"]} kg{i2["kgroups"]}"
         print(f"{t:10.1f} us  {n}{extra}")
