@@ -45,7 +45,10 @@ class ConvDesc(C.Structure):
         ("out_f16", c_i32), ("res_f16", c_i32),
         ("engine", c_i32),
         ("workspace", c_void_p), ("workspace_bytes", c_i64),
-        ("reserved", c_i32 * 4),
+        ("in_stats", c_void_p), ("in_gamma", c_void_p), ("in_beta", c_void_p),
+        ("in_cpg", c_i32), ("in_creal", c_i32), ("in_f16", c_i32), ("in_act", c_i32),
+        ("in_eps", c_float),
+        ("reserved", c_i32 * 3),
     ]
 
 
@@ -95,8 +98,8 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b2d_version() != 2:
-            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != 2; rebuild")
+        if l.b2d_version() != 3:
+            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != 3; rebuild")
         _lib = l
     return _lib
 

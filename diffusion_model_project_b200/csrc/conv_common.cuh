@@ -57,6 +57,16 @@ struct ConvKParams {
   int num_units;     // tiles_m * tiles_ncol * ksplit
   float* ws;         // [tile][ksplit][128][BLOCK_N] fp32 partial accumulators
   int* counters;     // [tile] arrival counters (self-resetting)
+  // ---- fused input normalisation (halo mode): A tiles are raw pre-GroupNorm values; dedicated warps rewrite each
+  // staged tile in shared memory as bf16 silu(gamma * (x - mean) * rstd + beta) before the MMAs read it ----
+  int xform;                   // 1: enabled (single segment)
+  const double* in_stats;      // [N][cin / in_cpg][2] (sum, sumsq) of the producer
+  const float* in_gamma;       // [cin_real]
+  const float* in_beta;
+  int in_cpg, in_creal;        // channels per group, real (unpadded) channel count
+  int in_f16, in_act;          // raw values are fp16 (else bf16); apply SiLU
+  float in_eps;
+  double in_count;             // elements per (sample, group): in_cpg * D * H * W
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -291,11 +291,14 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
       if (b == 16 ? (d->cout > 16 || d->nphase != 1) : (d->cout % b != 0)) continue;
       const long long tiles = tiles_m2 * (b == 16 ? 1 : cols / b);
       const double t_kb = b == 256 ? 512.0 : b == 128 ? 256.0 : b == 64 ? 192.0 : 128.0;
-      const double per_group = (halo ? 18.0 : 1.0) * t_kb;
+      double per_group = (halo ? 18.0 : 1.0) * t_kb;
+      if (d->in_stats && per_group < 6000.0) per_group = 6000.0;  // fused input normalisation: the tile rewrite bounds a group
       for (int ks = 1; ks <= 16; ++ks) {
         if (ks > 1 && (!can_split || ngroups / ks < 4 || tiles * mt > 4096 || tiles >= 2LL * sms ||
                        16384 + tiles * ks * mt * 128LL * b * 4 > d->workspace_bytes)) break;
-        const double unit = (double)((ngroups + ks - 1) / ks) * per_group + 1500.0 + 8.0 * b * mt + (ks > 1 ? 2500.0 : 0.0);
+        // split-K fix-up: park the fp32 partial (coalesced), fence + ticket, and the last arriver re-reads ks partials
+        const double fix = ks > 1 ? 6000.0 + (1.0 + ks) * 12.0 * b * mt : 0.0;
+        const double unit = (double)((ngroups + ks - 1) / ks) * per_group + 1500.0 + 8.0 * b * mt + fix;
         const double waves = (double)((tiles * ks + sms - 1) / sms);
         const double cost = waves * unit;
         if (cost < best * 0.999) { best = cost; best_bn = b; ksplit_pick = ks; }
@@ -408,6 +411,18 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   k.stats = d->stats; k.stats_cpg = d->stats ? d->stats_cpg : 0;
   k.out_scale = d->out_scale; k.out_mask = d->out_mask;
   k.out_f16 = d->out_f16 ? 1 : 0; k.res_f16 = d->res_f16 ? 1 : 0;
+  if (d->in_stats) {
+    if (!halo || d->nseg != 1 || d->cin[0] > 512 || d->in_cpg < 1 || d->in_creal < 1 || d->in_creal > d->cin[0] || d->in_creal % d->in_cpg) {
+      delete pl;
+      return set_error(B2D_E_INVALID, "fused input normalisation needs the persistent halo engine, one segment, cin <= 512 "
+                       "(halo %d nseg %d cin %d cpg %d creal %d)", (int)halo, d->nseg, d->cin[0], d->in_cpg, d->in_creal);
+    }
+    k.xform = 1;
+    k.in_stats = d->in_stats; k.in_gamma = d->in_gamma; k.in_beta = d->in_beta;
+    k.in_cpg = d->in_cpg; k.in_creal = d->in_creal; k.in_f16 = d->in_f16 ? 1 : 0; k.in_act = d->in_act ? 1 : 0;
+    k.in_eps = d->in_eps;
+    k.in_count = (double)d->in_cpg * d->D * d->H * d->W;
+  }
 
   pl->block_n = bn;
   pl->grid = dim3((unsigned)(k.tiles_w * k.tiles_h * k.tiles_d * k.tiles_n), (unsigned)(total_cols / bn), 1);

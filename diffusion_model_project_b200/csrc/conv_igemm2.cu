@@ -24,8 +24,9 @@
 
 namespace b2d {
 
-template <int BN, bool HALO>
+template <int BN, bool HALO, bool XFORM = false>
 struct V2Cfg {
+  static_assert(HALO || !XFORM, "input transform needs halo staging");
   static constexpr int MT = HALO ? 2 : 1;                       // M = 128 halves per unit
   static constexpr int A_TILE = HALO ? 18 * 18 * 128 : kABytes;  // bytes landed per A load
   static constexpr int A_STAGE = (A_TILE + 1023) / 1024 * 1024;
@@ -34,7 +35,7 @@ struct V2Cfg {
   static constexpr int TPB = HALO ? (BN <= 16 ? 9 : BN <= 64 ? 3 : 1) : 1;
   static constexpr int B_TILE = BN * kBlockK * 2;
   static constexpr int B_STAGE = TPB * B_TILE;
-  static constexpr int NA = HALO ? (BN >= 128 ? 2 : 3) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
+  static constexpr int NA = HALO ? ((BN == 256 || (BN == 128 && !XFORM)) ? 2 : 3) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
   static constexpr int NB = HALO ? (BN == 256 ? 4 : BN == 128 ? 6 : BN == 64 ? 4 : 3) : NA;
   static constexpr int BNC = BN < 32 ? 32 : BN;                  // TMEM columns of one M half
   static constexpr int ACC_COLS = MT * BNC;                      // one accumulator stage
@@ -42,9 +43,12 @@ struct V2Cfg {
   static constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : NACC * ACC_COLS <= 64 ? 64 : NACC * ACC_COLS <= 128 ? 128
                                    : NACC * ACC_COLS <= 256 ? 256 : 512;
   static constexpr int EPI_WARPS = 4 * MT;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
-  static constexpr int NBARS = 2 * NA + 2 * NB + 4;
-  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 + 1024;
+  static constexpr int XF_WARPS = XFORM ? 4 : 0;                 // warps rewriting staged A tiles (GroupNorm + SiLU)
+  static constexpr int XF_MAXC = 512;                            // input channels the coefficient table holds
+  static constexpr int BP_WARP = HALO ? 2 + EPI_WARPS + XF_WARPS : -1;  // halo: the weight ring has its own producer warp
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (HALO ? 32 : 0);
+  static constexpr int NBARS = 3 * NA + 2 * NB + 4;
+  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 + (XFORM ? 2 * XF_MAXC * 4 + 16 : 0) + 1024;
   static_assert(NACC * ACC_COLS <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static_assert(!HALO || 9 % TPB == 0, "taps per stage must divide 9");
@@ -92,9 +96,9 @@ struct GroupIter {
   }
 };
 
-template <int BN, bool HALO>
-__global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(const __grid_constant__ ConvKParams p) {
-  using Cfg = V2Cfg<BN, HALO>;
+template <int BN, bool HALO, bool XFORM>
+__global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_kernel(const __grid_constant__ ConvKParams p) {
+  using Cfg = V2Cfg<BN, HALO, XFORM>;
   constexpr int MT = Cfg::MT, NA = Cfg::NA, NB = Cfg::NB;
   constexpr int CW = BN < 32 ? 16 : 32;
 
@@ -104,20 +108,22 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
   uint8_t* sB = smem + NA * Cfg::A_STAGE;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + NB * Cfg::B_STAGE);
   uint64_t* a_empty = a_full + NA;
-  uint64_t* b_full = a_empty + NA;
+  uint64_t* a_ready = a_empty + NA;  // XFORM: tile rewritten, visible to the tensor core
+  uint64_t* b_full = a_ready + NA;
   uint64_t* b_empty = b_full + NB;
   uint64_t* t_full = b_empty + NB;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [MT]
   double* sm_stats = reinterpret_cast<double*>(tmem_slot + 4);               // [64] per-CTA GroupNorm sums (halo mode)
+  float* sm_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_stats + 64) + 15) & ~uintptr_t(15));  // XFORM: [2][XF_MAXC] scale, shift
 
   // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], XFORM ? Cfg::XF_WARPS : 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], Cfg::EPI_WARPS); }
     fence_barrier_init();
@@ -149,6 +155,8 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
       for (it.init(p, uc.ks); !it.done(); it.next(p)) {
         const int s = it.s;
         if constexpr (HALO) {
+          // activation ring only: the weight ring is fed by its own warp (below) so that A tiles can be
+          // prefetched NA deep instead of being serialised behind the nine weight-tile loads of a group
           const int zz = uc.z0 + p.dz[it.t * 9];
           if (zz < 0 || zz >= p.D) continue;
           mbar_wait(&a_empty[ast], aph ^ 1);
@@ -158,19 +166,6 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
           }
           __syncwarp();
           if (++ast == NA) { ast = 0; aph ^= 1; }
-          const int kb = p.kbase[s] + it.t * 9 * p.cin[s] + it.c * kBlockK;
-#pragma unroll 1
-          for (int ip = 0; ip < 9; ip += Cfg::TPB) {
-            mbar_wait(&b_empty[bst], bph ^ 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
-#pragma unroll
-              for (int j = 0; j < Cfg::TPB; ++j)
-                tma_load_2d_u(sB_u + bst * Cfg::B_STAGE + j * Cfg::B_TILE, &p.tmapB, smem_u32(&b_full[bst]), kb + (ip + j) * p.cin[s], gcol0);
-            }
-            __syncwarp();
-            if (++bst == NB) { bst = 0; bph ^= 1; }
-          }
         } else {
           const int tp = it.t;
           const int zz = uc.z0 + p.dz[tp];
@@ -187,6 +182,34 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
           }
           __syncwarp();
           if (++ast == NA) { ast = 0; aph ^= 1; }
+          if (++bst == NB) { bst = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (HALO && warp == Cfg::BP_WARP) {
+    // ================================ weight (B) producer, halo mode ========================
+    int bst = 0;
+    uint32_t bph = 0;
+    const uint32_t sB_u = smem_u32(sB);
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const UnitCoord uc = decode_unit(p, u);
+      const int gcol0 = uc.gcol0 * BN;
+      GroupIter it;
+      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
+        const int s = it.s;
+        const int zz = uc.z0 + p.dz[it.t * 9];
+        if (zz < 0 || zz >= p.D) continue;
+        const int kb = p.kbase[s] + it.t * 9 * p.cin[s] + it.c * kBlockK;
+#pragma unroll 1
+        for (int ip = 0; ip < 9; ip += Cfg::TPB) {
+          mbar_wait(&b_empty[bst], bph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
+#pragma unroll
+            for (int j = 0; j < Cfg::TPB; ++j)
+              tma_load_2d_u(sB_u + bst * Cfg::B_STAGE + j * Cfg::B_TILE, &p.tmapB, smem_u32(&b_full[bst]), kb + (ip + j) * p.cin[s], gcol0);
+          }
+          __syncwarp();
           if (++bst == NB) { bst = 0; bph ^= 1; }
         }
       }
@@ -217,7 +240,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
           const int zz = uc.z0 + p.dz[it.t];
           if (p.skip_z && (zz < 0 || zz >= p.D)) continue;
         }
-        mbar_wait(&a_full[ast], aph);
+        mbar_wait(XFORM ? &a_ready[ast] : &a_full[ast], aph);
         const uint32_t a_lo = adesc_lo0 + (uint32_t)(ast * (Cfg::A_STAGE >> 4));
         constexpr int GT = HALO ? 9 : 1;
 #pragma unroll 1
@@ -255,7 +278,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
       __syncwarp();
       if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
     }
-  } else {
+  } else if (warp < 2 + Cfg::EPI_WARPS) {
     // ================================ epilogue ==============================================
     const int ew = warp - 2;
     const int mt = ew >> 2;      // M half handled by this group of four warps
@@ -330,14 +353,15 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
         if (lane == 0) mbar_arrive(&t_empty[acc]);
       } else {
         // ---- split-K: park the fp32 partial, the last split to arrive reduces in a fixed order ----
-        float* wrow = p.ws + (((long long)uc.tile * p.ksplit + uc.ks) * MT + mt) * (128LL * BN) + (long long)r * BN;
+        // partial tile layout [column quad][row][4 floats]: a warp's 16-byte accesses cover 512 contiguous bytes
+        float4* wq = reinterpret_cast<float4*>(p.ws + (((long long)uc.tile * p.ksplit + uc.ks) * MT + mt) * (128LL * BN)) + r;
 #pragma unroll 1
         for (int col0 = 0; col0 < BN; col0 += CW) {
           float f[CW];
           load_tmem(col0, f);
 #pragma unroll
           for (int q = 0; q < CW / 4; ++q)
-            __stcg(reinterpret_cast<float4*>(wrow + col0) + q, make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]));
+            __stcg(wq + (col0 / 4 + q) * 128, make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]));
         }
         tc_fence_before();
         __syncwarp();
@@ -353,16 +377,16 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
         if (last_flag[mt]) {
           __threadfence();
-          const float* wbase = p.ws + (((long long)uc.tile * p.ksplit) * MT + mt) * (128LL * BN) + (long long)r * BN;
-          const long long ks_stride = (long long)MT * 128 * BN;
+          const float4* wbase = reinterpret_cast<const float4*>(p.ws + (((long long)uc.tile * p.ksplit) * MT + mt) * (128LL * BN)) + r;
+          const long long ks_stride = (long long)MT * 32 * BN;  // float4 units between the partials of consecutive splits
           auto load_ws = [&](int col0, float (&f)[CW]) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) f[j] = 0.f;
             for (int ks = 0; ks < p.ksplit; ++ks) {
-              const float4* src = reinterpret_cast<const float4*>(wbase + ks * ks_stride + col0);
+              const float4* src = wbase + ks * ks_stride + (col0 / 4) * 128;
 #pragma unroll
               for (int q = 0; q < CW / 4; ++q) {
-                const float4 v = __ldcg(src + q);
+                const float4 v = __ldcg(src + q * 128);
                 f[4 * q] += v.x; f[4 * q + 1] += v.y; f[4 * q + 2] += v.z; f[4 * q + 3] += v.w;
               }
             }
@@ -374,6 +398,111 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
       if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
     }
     flush_stats();
+  } else if constexpr (XFORM) {
+    // ================================ A-tile transform =====================================
+    // Rewrite every staged 18x18x64 tile in place: raw (fp16 | bf16) -> bf16 silu(scale[c] * x + shift[c]).  Pixels
+    // outside the image stay zero (TMA zero fill == the conv's zero padding, applied AFTER the activation).
+    const int xt = threadIdx.x - (64 + 32 * Cfg::EPI_WARPS);  // 0..127
+    const int chunk_phys = xt & 7;                            // 16-byte chunk inside the 128-byte row
+    const int row0 = xt >> 3;                                 // 16 rows per pass
+    float* coef_a = sm_coef;
+    float* coef_b = sm_coef + Cfg::XF_MAXC;
+    const uint32_t coef_a_u = smem_u32(coef_a), coef_b_u = smem_u32(coef_b);
+    const int cin_pad = p.cin[0];
+    const int ngrp = p.in_creal / p.in_cpg;
+    const bool act_on = p.in_act != 0, in_f16 = p.in_f16 != 0;
+    int ast = 0, cur_n = -1;
+    uint32_t aph = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const UnitCoord uc = decode_unit(p, u);
+      if (uc.n0 != cur_n) {
+        // per-channel scale / shift of this sample from the producer's fp64 (sum, sumsq)
+        asm volatile("bar.sync 4, 128;" ::: "memory");  // everyone is done with the previous table
+        for (int c = xt; c < cin_pad; c += 128) {
+          float a = 0.f, b = 0.f;
+          if (c < p.in_creal) {
+            const int g = c / p.in_cpg;
+            const double* st = p.in_stats + ((long long)uc.n0 * ngrp + g) * 2;
+            const double mean = st[0] / p.in_count;
+            double var = st[1] / p.in_count - mean * mean;
+            if (var < 0) var = 0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)p.in_eps));
+            const float ga = p.in_gamma ? __ldg(p.in_gamma + c) : 1.f, be = p.in_beta ? __ldg(p.in_beta + c) : 0.f;
+            a = rstd * ga;
+            b = be - (float)mean * rstd * ga;
+          }
+          coef_a[c] = act_on ? 0.5f * a : a;
+          coef_b[c] = act_on ? 0.5f * b : b;
+        }
+        asm volatile("bar.sync 4, 128;" ::: "memory");
+        cur_n = uc.n0;
+      }
+      GroupIter it;
+      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
+        const int zz = uc.z0 + p.dz[it.t * 9];
+        if (zz < 0 || zz >= p.D) continue;
+        mbar_wait(&a_full[ast], aph);
+        const uint32_t tile_u = smem_u32(sA + ast * Cfg::A_STAGE);
+        const int cbase = it.c * kBlockK;
+        // silu(y) = h + h * tanh(h) with h = y / 2; the 1/2 is folded into the coefficients (one MUFU per element).
+        // Branch-free body, four independent 16-byte vectors in flight per thread (this warp is alone on its scheduler).
+        const bool border = uc.x0 == 0 || uc.y0 == 0 || uc.x0 + 16 >= p.OW || uc.y0 + 16 >= p.OH;
+        int yi = (row0 * 3641) >> 16;  // row0 / 18
+        int xi = row0 - yi * 18;
+#pragma unroll 1
+        for (int r = row0; r < 18 * 18; r += 64) {
+          uint4 raw[4];
+          uint32_t vaddr[4];
+          int c0[4];
+          bool live[4];
+          int yj = yi, xj = xi;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int rr = r + 16 * q;
+            const uint32_t row_u = tile_u + (uint32_t)rr * 128u;
+            vaddr[q] = row_u + (uint32_t)(chunk_phys * 16);
+            c0[q] = cbase + ((chunk_phys ^ (int)((row_u >> 7) & 7u)) << 3);  // undo the 128B swizzle: which 8 channels
+            live[q] = rr < 18 * 18;
+            if (border) {
+              const int gx = uc.x0 - 1 + xj, gy = uc.y0 - 1 + yj;
+              live[q] = live[q] && gx >= 0 && gx < p.OW && gy >= 0 && gy < p.OH;  // outside the image: stays zero (padding)
+            }
+            xj += 16;
+            if (xj >= 18) { xj -= 18; ++yj; }
+            raw[q] = live[q] ? lds128(vaddr[q]) : make_uint4(0u, 0u, 0u, 0u);
+          }
+          yi = yj; xi = xj;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+            if (in_f16) {
+              const float2 q0 = unpack_f16(raw[q].x), q1 = unpack_f16(raw[q].y), q2 = unpack_f16(raw[q].z), q3 = unpack_f16(raw[q].w);
+              f[0] = q0.x; f[1] = q0.y; f[2] = q1.x; f[3] = q1.y; f[4] = q2.x; f[5] = q2.y; f[6] = q3.x; f[7] = q3.y;
+            } else {
+              f[0] = bf16_lo(raw[q].x); f[1] = bf16_hi(raw[q].x); f[2] = bf16_lo(raw[q].y); f[3] = bf16_hi(raw[q].y);
+              f[4] = bf16_lo(raw[q].z); f[5] = bf16_hi(raw[q].z); f[6] = bf16_lo(raw[q].w); f[7] = bf16_hi(raw[q].w);
+            }
+            const float4 a0 = lds128f(coef_a_u + c0[q] * 4), a1 = lds128f(coef_a_u + c0[q] * 4 + 16);
+            const float4 b0 = lds128f(coef_b_u + c0[q] * 4), b1 = lds128f(coef_b_u + c0[q] * 4 + 16);
+            f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
+            f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
+            if (act_on) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(f[j]));
+                f[j] = fmaf(f[j], t, f[j]);
+              }
+            }
+            if (live[q]) sts128(vaddr[q], make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[ast]);
+        if (++ast == NA) { ast = 0; aph ^= 1; }
+      }
+    }
   }
 
   tc_fence_before();
@@ -384,16 +513,16 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO>::THREADS, 1) conv_v2_kernel(co
   }
 }
 
-template <int BN, bool HALO>
+template <int BN, bool HALO, bool XFORM = false>
 static int launch_v2(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
-  using Cfg = V2Cfg<BN, HALO>;
+  using Cfg = V2Cfg<BN, HALO, XFORM>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_v2_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_v2_kernel<BN, HALO, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  conv_v2_kernel<BN, HALO><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(kp);
+  conv_v2_kernel<BN, HALO, XFORM><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(kp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "conv_v2 launch: %s", cudaGetErrorString(e));
   return B2D_OK;
@@ -401,7 +530,14 @@ static int launch_v2(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
 
 int launch_conv_v2(const b2d_conv_plan* plan, cudaStream_t st) {
   const ConvKParams& kp = plan->kp;
-  if (kp.halo) {
+  if (kp.halo && kp.xform) {
+    switch (plan->block_n) {
+      case 16: return launch_v2<16, true, true>(kp, plan->grid, st);
+      case 64: return launch_v2<64, true, true>(kp, plan->grid, st);
+      case 128: return launch_v2<128, true, true>(kp, plan->grid, st);
+      case 256: return launch_v2<256, true, true>(kp, plan->grid, st);
+    }
+  } else if (kp.halo) {
     switch (plan->block_n) {
       case 16: return launch_v2<16, true>(kp, plan->grid, st);
       case 64: return launch_v2<64, true>(kp, plan->grid, st);

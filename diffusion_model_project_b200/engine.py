@@ -171,14 +171,16 @@ class ConvPlan:
     def __init__(self, inputs: Sequence[Act], pw: PackedWeight, out, *, cout: int, nphase: int = 1, stride: int = 1,
                  out_mode: int = 0, out_geom=None, residual: Optional[Act] = None, stats: Optional[torch.Tensor] = None,
                  stats_cpg: int = 0, out_scale=None, out_mask=None, block_n: int = 0, out_cstride=None, out_coff: int = 0,
-                 engine: int = 0):
+                 engine: int = 0, in_norm=None):
+        """in_norm = (stats, cpg, gamma, beta, act[, eps]): inputs[0] is a RAW pre-GroupNorm tensor and the kernel applies
+        GroupNorm (+SiLU) to each staged tile (persistent halo engine only; see include/b2d.h)."""
         N, D, H, W, _ = inputs[0].shape
         d = ConvDesc()
         split = pw.split
         segs: List[Tuple[torch.Tensor, int, int]] = []  # (tensor, cin_pad, kbase)
         for i, a in enumerate(inputs):
             assert a.shape[:4] == (N, D, H, W) and a.C == pw.cin_pad[i], (a.shape, pw.cin_pad, i)
-            assert not a.f16, "an fp16 raw tensor cannot be an MMA operand"
+            assert in_norm is not None or not a.f16, "an fp16 raw tensor cannot be an MMA operand without in_norm"
             segs.append((a.hi, a.C, pw.kbase[i]))
         if split:
             for i, a in enumerate(inputs):
@@ -225,10 +227,20 @@ class ConvPlan:
         d.out_mask = ptr(out_mask)
         d.block_n = block_n
         d.engine = engine
+        if in_norm is not None:
+            st_in, cpg_in, g_in, b_in, act_in = in_norm[:5]
+            assert len(inputs) == 1 and not split
+            d.in_stats = st_in.data_ptr()
+            d.in_gamma, d.in_beta = ptr(g_in), ptr(b_in)
+            d.in_cpg = cpg_in
+            d.in_creal = g_in.numel() if g_in is not None else inputs[0].C
+            d.in_f16 = 1 if inputs[0].f16 else 0
+            d.in_act = 1 if act_in else 0
+            d.in_eps = in_norm[5] if len(in_norm) > 5 else 1e-5
         ws = workspace(inputs[0].hi.device)
         d.workspace = ws.data_ptr()
         d.workspace_bytes = ws.numel()
-        self._keep = (inputs, pw, out, residual, stats, out_scale, out_mask)
+        self._keep = (inputs, pw, out, residual, stats, out_scale, out_mask, in_norm)
         self.desc = d
         self.handle = C.c_void_p()
         _lib.check(_lib.lib().b2d_conv_plan_create(C.byref(d), C.byref(self.handle)), "b2d_conv_plan_create")

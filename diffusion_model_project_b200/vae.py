@@ -6,6 +6,7 @@ engine in NDHWC bf16; GroupNorm(32) sums come out of the producing conv's epilog
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -85,18 +86,36 @@ class _Builder:
         self.prog.add(name, lambda s: engine.gn_apply(x, y, st, C // 32, g, b, True, s))
         return y
 
+    def fusable(self, x: Act, cout: int) -> bool:
+        """GroupNorm + SiLU can be applied by the consumer conv itself (persistent halo engine: stride-1 3x3x3,
+        in-plane extent a multiple of 16, <= 512 input channels, bf16 mode).  Only worth it with 256-wide N tiles:
+        the conv kernels sit at the shared-memory bandwidth roofline (tensor-core operand reads + TMA writes), and
+        at BLOCK_N = 128 the in-place tile rewrite costs more than the HBM pass it saves; at 256 it is a wash
+        (profiles/README.md), so the fused path is opt-in (B2D_NORM_FUSION=1) and the default is a separate pass."""
+        _, _, H, W, C = x.shape
+        return (not self.split) and H % 16 == 0 and W % 16 == 0 and C <= 512 and cout % 256 == 0 \
+            and os.environ.get("B2D_NORM_FUSION") == "1" \
+            and os.environ.get("B2D_CONV_ENGINE", "2") == "2" and os.environ.get("B2D_CONV_NO_HALO") is None
+
+    def norm_conv(self, name, norm_name, x: Act, st_x, gnw, pw, cout, *, inplace_norm: bool, **kw):
+        """conv(silu(GroupNorm32(x))): one launch when fusable (the conv normalises its staged input tiles in shared
+        memory), else a GroupNorm-apply pass followed by the conv."""
+        if self.fusable(x, cout):
+            g, b = gnw
+            return self.conv(name, x, pw, cout, in_norm=(st_x, x.C // 32, g, b, True), **kw)
+        h = self.gn_silu(norm_name, x, st_x, gnw, inplace=inplace_norm)
+        return self.conv(name, h, pw, cout, **kw)
+
     def res(self, w, name, x: Act, st_x, cin, cout, want_stats=True, raw_out=True):
         """vae/blocks.py:173-186.  raw_out=False when the block output feeds a conv directly (down / upsample+conv)."""
-        h = self.gn_silu(f"{name}.norm1", x, st_x, w[f"{name}.norm1"], inplace=False)
-        r, st_r = self.conv(f"{name}.conv1", h, w[f"{name}.conv1"], cout, raw=True)
-        r = self.gn_silu(f"{name}.norm2", r, st_r, w[f"{name}.norm2"], inplace=True)
+        r, st_r = self.norm_conv(f"{name}.conv1", f"{name}.norm1", x, st_x, w[f"{name}.norm1"], w[f"{name}.conv1"], cout,
+                                 inplace_norm=False, raw=True)
         skip = x
         if f"{name}.residual_layer" in w:
             assert not x.f16
             skip, _ = self.conv(f"{name}.residual_layer", x, w[f"{name}.residual_layer"], cout, want_stats=False, raw=True)
-        # reuse h's storage for the block output when shapes allow (h is dead after conv1)
-        out = h if cin == cout else None
-        return self.conv(f"{name}.conv2", r, w[f"{name}.conv2"], cout, residual=skip, want_stats=want_stats, out=out, raw=raw_out)
+        return self.norm_conv(f"{name}.conv2", f"{name}.norm2", r, st_r, w[f"{name}.norm2"], w[f"{name}.conv2"], cout,
+                              inplace_norm=True, residual=skip, want_stats=want_stats, raw=raw_out)
 
     def finish(self):
         used, buf = self.stats_used, self.stats_buf
@@ -148,7 +167,6 @@ class B200DualVAE:
         x, st = bd.conv("down2", x, w["down2"], 256, stride=2)                            # -> res3_1's skip conv
         x, st = bd.res(w, "res3_1", x, st, 256, 512)
         x, st = bd.res(w, "res3_2", x, st, 512, 512)
-        x = bd.gn_silu("norm_out", x, st, w["norm_out"], inplace=True)
         h, wd = H // 4, W // 4
         cout = br.cout if out_cout is None else out_cout
         if out is None:
@@ -156,7 +174,7 @@ class B200DualVAE:
         kw = dict(out_mode=out_mode, out_coff=out_coff)
         if out_mode == 1:
             kw["out_cstride"] = br.cout
-        bd.conv("conv_out", x, w["conv_out"], cout, want_stats=False, out=out, **kw)
+        bd.norm_conv("conv_out", "norm_out", x, st, w["norm_out"], w["conv_out"], cout, inplace_norm=True, want_stats=False, out=out, **kw)
         return dict(program=bd.finish(), x_in=x_in, out=out, keep=bd.keep, stats=bd.stats_buf)
 
     def build_decoder(self, branch: str, B, D, h, w_, *, z_in: Optional[Act] = None, out=None, out_scale=None, out_mask=None) -> dict:
@@ -176,12 +194,11 @@ class B200DualVAE:
             x, st = bd.conv(f"conv_up{stage}", up, w[f"conv_up{stage}"], cout, raw=True)
             x, st = bd.res(w, r1, x, st, cout, cout)
             x, st = bd.res(w, r2, x, st, cout, cout, want_stats=last, raw_out=last)     # stage 1 -> upsample -> conv_up2
-        x = bd.gn_silu("norm_out", x, st, w["norm_out"], inplace=True)
         H, W = 4 * h, 4 * w_
         if out is None:
             out = torch.empty((B, D, br.cout, H, W), dtype=torch.float32, device=self.device)
-        bd.conv("conv_out", x, w["conv_out"], br.cout, want_stats=False, out=out, out_mode=1, out_cstride=br.cout,
-                out_scale=out_scale, out_mask=out_mask)
+        bd.norm_conv("conv_out", "norm_out", x, st, w["norm_out"], w["conv_out"], br.cout, inplace_norm=True, want_stats=False, out=out,
+                     out_mode=1, out_cstride=br.cout, out_scale=out_scale, out_mask=out_mask)
         return dict(program=bd.finish(), z_in=z_in, out=out, keep=bd.keep, stats=bd.stats_buf)
 
     # ------------------------------------------------------------------------------ module API

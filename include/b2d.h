@@ -33,7 +33,7 @@ extern "C" {
 #define B2D_API
 #endif
 
-#define B2D_VERSION 2
+#define B2D_VERSION 3
 #define B2D_MAX_SEG 6
 #define B2D_MAX_TAPS 27
 
@@ -117,7 +117,17 @@ typedef struct b2d_conv_desc {
   void* workspace;                 /* optional caller-owned scratch for split-K (first 16 KB: zero-initialised arrival
                                       counters, then fp32 partial tiles); shared by plans that run on one stream      */
   int64_t workspace_bytes;
-  int32_t reserved[4];
+  /* Fused input normalisation (persistent engine, halo staging, one segment, cin <= 512): in[0] holds the RAW
+   * pre-GroupNorm output of the producer (fp16 if in_f16, else bf16) and the kernel applies
+   * silu?(gamma * (x - mean) * rstd + beta) to each staged tile in shared memory -- GroupNorm + SiLU of
+   * vae/blocks.py:173-183 without a separate pass over HBM.  in_stats = the producer's `stats` buffer. */
+  const double* in_stats;          /* [N][in_creal / in_cpg][2] or NULL (no fusion)                      */
+  const float* in_gamma;           /* [in_creal] or NULL                                                 */
+  const float* in_beta;
+  int32_t in_cpg, in_creal;        /* channels per group; real (unpadded) input channels                 */
+  int32_t in_f16, in_act;
+  float in_eps;
+  int32_t reserved[3];
 } b2d_conv_desc;
 
 typedef struct b2d_conv_plan b2d_conv_plan;

@@ -176,3 +176,40 @@ def test_plan_rejects_bad_shapes():
     w = torch.zeros(60, 64)
     with pytest.raises(ValueError):
         ConvPlan([x], engine.pack_linear(w, None, DEV), new_act(1, 1, 8, 8, 64, DEV), cout=60)  # cout not multiple of 64
+
+
+@pytest.mark.parametrize("ci,co,f16", [(128, 128, True), (256, 128, False), (512, 16, True)])
+def test_fused_input_groupnorm_silu(ci, co, f16):
+    """conv(silu(GroupNorm32(x))) with the normalisation applied to the staged tiles inside the conv kernel
+    (vae/blocks.py:173-183), raw input held as fp16 or bf16, vs PyTorch on the same rounded operands."""
+    no_tf32()
+    g = torch.Generator().manual_seed(21 + ci)
+    N, D, H, W = 2, 3, 32, 16
+    x = _rnd(g, N, ci, D, H, W) * 1.5 + 0.3
+    xr = x.to(torch.float16).float() if f16 else bf16_round(x)
+    gamma = (1 + 0.1 * torch.randn(ci, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(ci, generator=g)).to(DEV)
+    cout_real = co if co >= 64 else 3
+    w = bf16_round(_rnd(g, cout_real, ci, 3, 3, 3, scale=(27 * ci) ** -0.5))
+    b = _rnd(g, cout_real)
+    if f16:  # the same 16-bit storage, holding IEEE half values
+        cl = xr.permute(0, 2, 3, 4, 1).to(torch.float16).contiguous()
+        xa = engine.Act(cl.view(torch.bfloat16), None, True)
+    else:
+        xa = to_act(xr)
+    st = stats_ref(xr, 32).to(DEV).contiguous()
+    if cout_real >= 64:
+        out = new_act(N, D, H, W, co, DEV)
+        plan = ConvPlan([xa], engine.pack_conv3d(w, b, DEV), out, cout=co, in_norm=(st, ci // 32, gamma, beta, True))
+        plan.run(_stream())
+        got = from_act(out, co)
+    else:
+        out = torch.zeros(N, D, cout_real, H, W, device=DEV)
+        plan = ConvPlan([xa], engine.pack_conv3d(w, b, DEV), out, cout=cout_real, out_mode=1, out_cstride=cout_real,
+                        in_norm=(st, ci // 32, gamma, beta, True))
+        plan.run(_stream())
+        got = out.permute(0, 2, 1, 3, 4)
+    assert plan.info2()["halo"] == 1
+    h = bf16_round(F.silu(F.group_norm(xr, 32, gamma, beta, eps=1e-5)))
+    ref = F.conv3d(h, w, b, padding=1)
+    assert rel_err(got, ref) < (TOL_BF16 if cout_real >= 64 else 2e-3)
