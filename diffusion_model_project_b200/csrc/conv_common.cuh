@@ -122,7 +122,8 @@ __device__ __forceinline__ void warp_transpose_sum(float (&vals)[V], int lane) {
 }
 
 // SMEM_STATS: the whole warp belongs to ONE sample (halo tiles) and GroupNorm sums go to per-CTA fp64
-// accumulators in shared memory (sm_stats[group][2]); the kernel pushes them to global memory when the
+// accumulators in shared memory (sm_stats[group][2], one private copy per epilogue warp -- fp64 shared-memory atomics
+// are CAS loops and serialise badly); the kernel pushes them to global memory when the
 // sample changes.  Otherwise sums go straight to global memory with fp64 atomics (rows of a warp may
 // belong to `32 / seg` different samples).
 template <int BLOCK_N, int CW, bool SMEM_STATS, class Loader>
@@ -140,7 +141,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const Ep
     if constexpr (SMEM_STATS) {
       float v2[2] = {s, ss};
       warp_transpose_sum<2>(v2, lane);
-      if ((lane & 15) == 0 && g >= 0 && g < groups_per_n) atomicAdd(sm_stats + g * 2 + (lane >> 4), (double)v2[0]);
+      if ((lane & 15) == 0 && g >= 0 && g < groups_per_n) sm_stats[g * 2 + (lane >> 4)] += (double)v2[0];  // this warp's private slot: no atomics
     } else {
       for (int off = seg >> 1; off > 0; off >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -248,7 +249,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const Ep
               if ((lane & ((1 << SH) - 1)) == 0) {
                 const int vi = lane >> SH;            // value index: [0,G) sums, [G,2G) sums of squares
                 const int g = co0 / CPG + (vi & (G - 1));
-                if (g < groups_per_n) atomicAdd(sm_stats + g * 2 + (vi >= G ? 1 : 0), (double)vals[0]);
+                if (g < groups_per_n) sm_stats[g * 2 + (vi >= G ? 1 : 0)] += (double)vals[0];  // warp-private slot
               }
             } else {
 #pragma unroll

@@ -252,14 +252,19 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   if (engine != 1 && engine != 2) return set_error(B2D_E_INVALID, "engine=%d (0 auto, 1, 2)", engine);
   // halo staging: canonical 3x3 / 3x3x3 'same' taps in (z, y, x) order, stride 1, 16x16 super-tiles, BLOCK_N <= 128
   bool halo = false;
-  if (engine == 2 && d->stride_h == 1 && d->stride_w == 1 && d->nphase == 1 && (d->ntaps == 9 || d->ntaps == 27) &&
+  int gt = 0;  // in-plane taps per z group (taps are z-major): 9 = full 3x3, 4 = 2x2 of an upsample-folded conv
+  if (engine == 2 && d->stride_h == 1 && d->stride_w == 1 && d->nphase == 1 && d->ntaps >= 4 &&
       d->OW % 16 == 0 && d->OH % 16 == 0 && d->OW == d->W && d->OH == d->H && (d->cout <= 16 || d->cout % 64 == 0) &&
       (d->block_n == 0 || d->block_n == 16 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256)) {
     static const bool no_halo = getenv("B2D_CONV_NO_HALO") != nullptr;
-    halo = !no_halo;
+    while (gt < d->ntaps && d->tap_dz[gt] == d->tap_dz[0]) ++gt;
+    halo = !no_halo && (gt == 9 || gt == 4) && d->ntaps % gt == 0;
     for (int t = 0; t < d->ntaps && halo; ++t) {
-      const int ip = t % 9;
-      if (d->tap_dy[t] != ip / 3 - 1 || d->tap_dx[t] != ip % 3 - 1 || d->tap_dz[t] != d->tap_dz[(t / 9) * 9]) halo = false;
+      // every z group repeats the in-plane offsets of the first one, all within the 1-pixel halo
+      const int j = t % gt;
+      if (d->tap_dy[t] != d->tap_dy[j] || d->tap_dx[t] != d->tap_dx[j] || d->tap_dz[t] != d->tap_dz[(t / gt) * gt] ||
+          d->tap_dy[t] < -1 || d->tap_dy[t] > 1 || d->tap_dx[t] < -1 || d->tap_dx[t] > 1)
+        halo = false;
     }
   }
   long long tiles_m2 = tiles_m;
@@ -276,7 +281,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     const int sms = num_sms();
     const long long cols = (long long)d->cout * d->nphase;
     long long ngroups = 0;
-    for (int s = 0; s < d->nseg; ++s) ngroups += (long long)(halo ? d->ntaps / 9 : d->ntaps) * (d->cin[s] / kBlockK);
+    for (int s = 0; s < d->nseg; ++s) ngroups += (long long)(halo ? d->ntaps / gt : d->ntaps) * (d->cin[s] / kBlockK);
     bool all_dz0 = true;
     for (int t = 0; t < d->ntaps; ++t) all_dz0 = all_dz0 && d->tap_dz[t] == 0;
     static const bool no_split = getenv("B2D_CONV_NO_SPLITK") != nullptr;
@@ -289,9 +294,10 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
       const int b = cand[ci];
       if (d->block_n && d->block_n != b) continue;
       if (b == 16 ? (d->cout > 16 || d->nphase != 1) : (d->cout % b != 0)) continue;
+      if (halo && gt == 4 && b < 128) continue;  // narrow tiles batch 3 / 9 taps per weight stage
       const long long tiles = tiles_m2 * (b == 16 ? 1 : cols / b);
       const double t_kb = b == 256 ? 512.0 : b == 128 ? 256.0 : b == 64 ? 192.0 : 128.0;
-      double per_group = (halo ? 18.0 : 1.0) * t_kb;
+      double per_group = (halo ? 2.0 * gt : 1.0) * t_kb;
       if (d->in_stats && per_group < 6000.0) per_group = 6000.0;  // fused input normalisation: the tile rewrite bounds a group
       for (int ks = 1; ks <= 16; ++ks) {
         if (ks > 1 && (!can_split || ngroups / ks < 4 || tiles * mt > 4096 || tiles >= 2LL * sms ||
@@ -434,8 +440,8 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   if (engine == 2) {
     // ---- persistent engine: work units, K-loop groups, split-K ---------------------------------
     k.halo = halo ? 1 : 0;
-    k.gtaps = halo ? 9 : 1;
-    const int tgroups = halo ? d->ntaps / 9 : d->ntaps;  // A loads per (segment, chunk)
+    k.gtaps = halo ? gt : 1;
+    const int tgroups = halo ? d->ntaps / gt : d->ntaps;  // A loads per (segment, chunk)
     k.goff[0] = 0;
     for (int s = 0; s < d->nseg; ++s) k.goff[s + 1] = k.goff[s] + tgroups * k.cchunks[s];
     k.ngroups = k.goff[d->nseg];

@@ -35,7 +35,7 @@ struct V2Cfg {
   static constexpr int TPB = HALO ? (BN <= 16 ? 9 : BN <= 64 ? 3 : 1) : 1;
   static constexpr int B_TILE = BN * kBlockK * 2;
   static constexpr int B_STAGE = TPB * B_TILE;
-  static constexpr int NA = HALO ? ((BN == 256 || (BN == 128 && !XFORM)) ? 2 : 3) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
+  static constexpr int NA = HALO ? ((BN >= 128 || XFORM) ? 2 : 3) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
   static constexpr int NB = HALO ? (BN == 256 ? 4 : BN == 128 ? 6 : BN == 64 ? 4 : 3) : NA;
   static constexpr int BNC = BN < 32 ? 32 : BN;                  // TMEM columns of one M half
   static constexpr int ACC_COLS = MT * BNC;                      // one accumulator stage
@@ -48,7 +48,7 @@ struct V2Cfg {
   static constexpr int BP_WARP = HALO ? 2 + EPI_WARPS + XF_WARPS : -1;  // halo: the weight ring has its own producer warp
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (HALO ? 32 : 0);
   static constexpr int NBARS = 3 * NA + 2 * NB + 4;
-  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 + (XFORM ? 2 * XF_MAXC * 4 + 16 : 0) + 1024;
+  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 * EPI_WARPS + (XFORM ? 2 * XF_MAXC * 4 + 16 : 0) + 1024;
   static_assert(NACC * ACC_COLS <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static_assert(!HALO || 9 % TPB == 0, "taps per stage must divide 9");
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [MT]
-  double* sm_stats = reinterpret_cast<double*>(tmem_slot + 4);               // [64] per-CTA GroupNorm sums (halo mode)
-  float* sm_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_stats + 64) + 15) & ~uintptr_t(15));  // XFORM: [2][XF_MAXC] scale, shift
+  double* sm_stats = reinterpret_cast<double*>(tmem_slot + 4);               // [EPI_WARPS][64] per-warp GroupNorm sums (halo mode)
+  float* sm_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_stats + 64 * Cfg::EPI_WARPS) + 15) & ~uintptr_t(15));  // XFORM: [2][XF_MAXC] scale, shift
 
   // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], Cfg::EPI_WARPS); }
     fence_barrier_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) sm_stats[threadIdx.x - 64] = 0.0;
+  for (int i = threadIdx.x; i < 64 * Cfg::EPI_WARPS; i += blockDim.x) sm_stats[i] = 0.0;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&p.tmapA[s]);
     prefetch_tmap(&p.tmapB);
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
         if constexpr (HALO) {
           // activation ring only: the weight ring is fed by its own warp (below) so that A tiles can be
           // prefetched NA deep instead of being serialised behind the nine weight-tile loads of a group
-          const int zz = uc.z0 + p.dz[it.t * 9];
+          const int zz = uc.z0 + p.dz[it.t * p.gtaps];
           if (zz < 0 || zz >= p.D) continue;
           mbar_wait(&a_empty[ast], aph ^ 1);
           if (elect_one()) {
@@ -197,11 +197,11 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
       GroupIter it;
       for (it.init(p, uc.ks); !it.done(); it.next(p)) {
         const int s = it.s;
-        const int zz = uc.z0 + p.dz[it.t * 9];
+        const int zz = uc.z0 + p.dz[it.t * p.gtaps];
         if (zz < 0 || zz >= p.D) continue;
-        const int kb = p.kbase[s] + it.t * 9 * p.cin[s] + it.c * kBlockK;
+        const int kb = p.kbase[s] + it.t * p.gtaps * p.cin[s] + it.c * kBlockK;
 #pragma unroll 1
-        for (int ip = 0; ip < 9; ip += Cfg::TPB) {
+        for (int ip = 0; ip < p.gtaps; ip += Cfg::TPB) {
           mbar_wait(&b_empty[bst], bph ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
       GroupIter it;
       for (it.init(p, uc.ks); !it.done(); it.next(p)) {
         if constexpr (HALO) {
-          const int zz = uc.z0 + p.dz[it.t * 9];
+          const int zz = uc.z0 + p.dz[it.t * p.gtaps];
           if (zz < 0 || zz >= p.D) continue;
         } else {
           const int zz = uc.z0 + p.dz[it.t];
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
         }
         mbar_wait(XFORM ? &a_ready[ast] : &a_full[ast], aph);
         const uint32_t a_lo = adesc_lo0 + (uint32_t)(ast * (Cfg::A_STAGE >> 4));
-        constexpr int GT = HALO ? 9 : 1;
+        const int GT = HALO ? p.gtaps : 1;  // in-plane taps fed by one staged box (9, or 4 for the upsample-folded convs)
 #pragma unroll 1
         for (int ip = 0; ip < GT; ip += Cfg::TPB) {
           mbar_wait(&b_full[bst], bph);
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
             for (int j = 0; j < Cfg::TPB; ++j) {
               // tap (dy,dx) = row offset ((1+dy)*18 + (1+dx)) * 128 B into the staged halo box (8 = 128 B >> 4)
               const int tap = ip + j;
-              const uint32_t a_tap = HALO ? a_lo + (uint32_t)(((tap / 3) * 18 + (tap % 3)) * 8) : a_lo;
+              const uint32_t a_tap = HALO ? a_lo + (uint32_t)(((1 + p.dy[tap]) * 18 + (1 + p.dx[tap])) * 8) : a_lo;
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -299,9 +299,10 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
           const int ng2 = 2 * (p.cout / p.stats_cpg);
           asm volatile("bar.sync 3, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
           if (cur_n >= 0 && epi_tid < ng2) {
-            const double v = sm_stats[epi_tid];
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < Cfg::EPI_WARPS; ++w) { v += sm_stats[w * 64 + epi_tid]; sm_stats[w * 64 + epi_tid] = 0.0; }
             if (v != 0.0) atomicAdd(p.stats + (long long)cur_n * ng2 + epi_tid, v);
-            sm_stats[epi_tid] = 0.0;
           }
           asm volatile("bar.sync 3, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
         }
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
         for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
       };
       if (p.ksplit == 1) {
-        conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats, load_tmem);
+        conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
               }
             }
           };
-          conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats, load_ws);
+          conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // last_flag is reused by the next unit
       }
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
       }
       GroupIter it;
       for (it.init(p, uc.ks); !it.done(); it.next(p)) {
-        const int zz = uc.z0 + p.dz[it.t * 9];
+        const int zz = uc.z0 + p.dz[it.t * p.gtaps];
         if (zz < 0 || zz >= p.D) continue;
         mbar_wait(&a_full[ast], aph);
         const uint32_t tile_u = smem_u32(sA + ast * Cfg::A_STAGE);

@@ -49,7 +49,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // --------------------------------------------------------------------------- GroupNorm apply
 // grid = (blocks_per_image, N); block = 256.  Per-channel scale/shift/temb staged in smem.
-__global__ void __launch_bounds__(256) gn_apply_kernel(
+template <bool TEMB>
+__global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
     const uint4* __restrict__ x, const uint4* __restrict__ x_lo, uint4* __restrict__ y, uint4* __restrict__ y_lo,
     long long P, int C, const double* __restrict__ stats, int cpg, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, int act, const float* __restrict__ temb_table,
@@ -67,17 +68,24 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(
     const int row = temb_row ? temb_row[(long long)n * temb_row_stride] : 0;
     trow = temb_table + (long long)row * temb_ld + temb_col;
   }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
+  // per-group mean / rstd once (fp64: E[x^2] - mean^2 cancels), then fp32 per-channel scale / shift
+  __shared__ float s_mean[64], s_rstd[64];
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
     const double s = stats[((long long)n * G + g) * 2];
     const double ss = stats[((long long)n * G + g) * 2 + 1];
     const double mean = s / cnt;
     double var = ss / cnt - mean * mean;
     if (var < 0) var = 0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float rstd = s_rstd[g], mean = s_mean[g];
     const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
     sa[c] = rstd * ga;
-    sb[c] = be - (float)mean * rstd * ga;
+    sb[c] = be - mean * rstd * ga;
     st[c] = trow ? trow[c] : 0.f;
   }
   __syncthreads();
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(
     for (int j = 0; j < 8; ++j) {
       float v = fmaf(f[j], a[j], b[j]);
       if (act) v = silu(v);
-      v += t[j];
+      if (TEMB) v += t[j];
       f[j] = v;
       acc_s += v;
       acc_ss += v * v;
@@ -280,7 +288,7 @@ extern "C" int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo
                             int32_t temb_col, double* stats_out, int32_t in_f16, void* stream) {
   if (!x || !y || !stats) return set_error(B2D_E_INVALID, "b2d_gn_apply: null pointer");
   if (in_f16 && x_lo) return set_error(B2D_E_INVALID, "b2d_gn_apply: fp16 input has no lo part");
-  if (N < 1 || P < 1 || C < 8 || (C % 8) || cpg < 1 || (C % cpg)) return set_error(B2D_E_INVALID, "b2d_gn_apply: bad shape N=%d P=%lld C=%d cpg=%d", N, (long long)P, C, cpg);
+  if (N < 1 || P < 1 || C < 8 || (C % 8) || cpg < 1 || (C % cpg) || C / cpg > 64) return set_error(B2D_E_INVALID, "b2d_gn_apply: bad shape N=%d P=%lld C=%d cpg=%d", N, (long long)P, C, cpg);
   if (3 * C * (int)sizeof(float) > 96 * 1024) return set_error(B2D_E_INVALID, "b2d_gn_apply: C=%d too large", C);
   if (N > 65535) return set_error(B2D_E_INVALID, "b2d_gn_apply: N too large");
   const long long nvec = (long long)P * (C / 8);
@@ -290,12 +298,18 @@ extern "C" int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo
   const size_t smem = 3 * (size_t)C * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
-    cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(gn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cfg = true;
   }
-  gn_apply_kernel<<<dim3(bx, N), 256, smem, (cudaStream_t)stream>>>(
-      (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, temb_table,
-      temb_row, temb_row_stride, temb_ld, temb_col, stats_out, in_f16 ? 1 : 0);
+  if (temb_table != nullptr)
+    gn_apply_kernel<true><<<dim3(bx, N), 256, smem, (cudaStream_t)stream>>>(
+        (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, temb_table,
+        temb_row, temb_row_stride, temb_ld, temb_col, stats_out, in_f16 ? 1 : 0);
+  else
+    gn_apply_kernel<false><<<dim3(bx, N), 256, smem, (cudaStream_t)stream>>>(
+        (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, nullptr,
+        nullptr, 0, 0, 0, stats_out, in_f16 ? 1 : 0);
   return check_launch("gn_apply_kernel");
 }
 

@@ -41,6 +41,11 @@ class _Branch:
             conv("down1", down=True); conv("down2", down=True)
         else:
             conv("conv_up1"); conv("conv_up2")
+            if not split:  # upsample folded into the conv: four phase convs on the low-resolution map
+                for name in ("conv_up1", "conv_up2"):
+                    for ph in range(4):
+                        self.w[f"{name}.phase{ph}"] = engine.pack_conv3d_upsampled(g(f"{name}.weight"), g(f"{name}.bias"), device,
+                                                                                  ph >> 1, ph & 1)
         norm("norm_out"); conv("conv_out")
         self.cin = g("conv_in.weight").shape[1]
         self.cout = g("conv_out.weight").shape[0]
@@ -189,9 +194,21 @@ class B200DualVAE:
         x, _ = bd.res(w, "res1_2", x, st, 512, 512, want_stats=False, raw_out=False)   # -> upsample -> conv_up1
         for stage, (cin, cout, r1, r2, last) in enumerate(((512, 256, "res2_1", "res2_2", False), (256, 128, "res3_1", "res3_2", True)), 1):
             N_, D_, H_, W_, _ = x.shape
-            up = new_act(N_, D_, 2 * H_, 2 * W_, cin, self.device, self.split)
-            bd.prog.add(f"up{stage}", lambda s, x=x, up=up: engine.upsample2x(x, up, s))
-            x, st = bd.conv(f"conv_up{stage}", up, w[f"conv_up{stage}"], cout, raw=True)
+            if f"conv_up{stage}.phase0" in w and H_ % 16 == 0 and W_ % 16 == 0 and os.environ.get("B2D_NO_UPSAMPLE_FOLD") is None:
+                # nn.Upsample(scale=(1,2,2)) + Conv3d == 4 phase convs with 2x2x3 taps on the low-resolution map
+                y = new_act(N_, D_, 2 * H_, 2 * W_, cout, self.device, self.split, f16=True)
+                st = bd.stats()
+                for ph in range(4):
+                    plan = ConvPlan([x], w[f"conv_up{stage}.phase{ph}"], y, cout=cout, stats=st, stats_cpg=cout // 32,
+                                    out_geom=(2 * H_, 2 * W_, 2, 2, ph >> 1, ph & 1))
+                    bd.prog.flops += plan.flops
+                    bd.prog.add(f"conv_up{stage}.phase{ph}", plan.run)
+                    bd.keep.append(plan)
+                x = y
+            else:
+                up = new_act(N_, D_, 2 * H_, 2 * W_, cin, self.device, self.split)
+                bd.prog.add(f"up{stage}", lambda s, x=x, up=up: engine.upsample2x(x, up, s))
+                x, st = bd.conv(f"conv_up{stage}", up, w[f"conv_up{stage}"], cout, raw=True)
             x, st = bd.res(w, r1, x, st, cout, cout)
             x, st = bd.res(w, r2, x, st, cout, cout, want_stats=last, raw_out=last)     # stage 1 -> upsample -> conv_up2
         H, W = 4 * h, 4 * w_

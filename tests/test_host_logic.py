@@ -159,3 +159,27 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.B2DError):
         _lib.lib()
+
+
+def test_upsample_folded_conv_weights_match_reference_math():
+    """decoder.py:46-47: Conv3d(Upsample(scale=(1,2,2))(x)) == four phase convs with 2x2x3 taps on the low-res map
+    (engine.pack_conv3d_upsampled).  Checked on the CPU with the packed matrices themselves."""
+    import torch.nn.functional as F
+    from diffusion_model_project_b200 import engine
+    g = torch.Generator().manual_seed(3)
+    ci, co = 64, 64
+    w = torch.randn(co, ci, 3, 3, 3, generator=g) * 0.05
+    b = torch.randn(co, generator=g)
+    x = torch.randn(1, ci, 3, 6, 5, generator=g)
+    ref = F.conv3d(F.interpolate(x, scale_factor=(1, 2, 2), mode="nearest"), w, b, padding=1)
+    for ph in range(4):
+        py, px = ph >> 1, ph & 1
+        pw = engine.pack_conv3d_upsampled(w, b, "cpu", py, px)
+        assert len(pw.taps) == 12 and pw.ktot == 12 * 64
+        wk = torch.zeros(co, ci, 3, 3, 3)
+        mat = pw.w.float()[:co].reshape(co, 12, 64)
+        for t, (dz, dy, dx) in enumerate(pw.taps):
+            wk[:, :, dz + 1, dy + 1, dx + 1] = mat[:, t, :ci]
+        got = F.conv3d(x, wk, b, padding=1)
+        want = ref[:, :, :, py::2, px::2]
+        assert (got - want).abs().max() <= 2e-2 * want.abs().max()  # bf16-rounded packed weights
