@@ -284,7 +284,7 @@ def run_b200(args):
 
     t_e2d = time_launches(lambda: ses["e2d"]["program"].run(s), 3)
     t_d3d = time_launches(lambda: ses["d3d"]["program"].run(s), 3)
-    t_unet = time_launches(lambda: ses["unet"]["program"].run(s), 10)
+    t_unet = time_launches(lambda: pred._run_unet(ses, s), 10)
     # dominant kernel: the tcgen05 implicit-GEMM conv engine (>= 85 % of the step's device time).  Its roofline
     # launch is the heaviest single launch of the step (D3D conv_up: 3x3x3 on the upsampled map), timed alone with
     # CUDA events on the launch stream -> burst peak.
@@ -299,6 +299,14 @@ def run_b200(args):
     dd = dom.desc
     dom_label = (f"conv_v{di['engine']}_kernel<BN={di['block_n']},halo={di['halo']}> (D3D {dom_name}: {sum(dd.cin[i] for i in range(1))}->{dd.cout} "
                  f"3x3x3 @ {B}x{dd.D}x{dd.H}x{dd.W}, timed alone: burst peak)")
+    # DRAM bytes of that launch from the committed `ncu --set full` capture of the same shape (profiles/), if present
+    traffic = None
+    shape_key = f"3d {B} {dd.cin[0]} {dd.cout} {dd.H}"
+    tpath = os.path.join(ROOT, "profiles", "r1_dominant_kernel_ncu.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("shape", "").startswith(shape_key):
+            traffic = tj.get("dram_traffic_bytes")
     # scheduler kernel on >= 64 samples' worth of latent (369 MB > L2) for an HBM-bound number
     n_el = ELEMS_PER_SAMPLE * 64
     xs, es, zs = (torch.randn(n_el, device=dev) for _ in range(3))
@@ -324,7 +332,7 @@ def run_b200(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": tc_ach, "peak": peaks["tc_burst"], "unit": "TFLOP/s", "frac": tc_ach / peaks["tc_burst"],
-                         "traffic": None, "kernel": dom_label,
+                         "traffic": traffic, "kernel": dom_label,
                          "peak_source": peaks["src"], "flops_per_launch": dom.flops, "ms_per_launch": t_dom},
             "roofline_scheduler": {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm"],
                                    "bytes_per_launch": 16.0 * n_el, "ms_per_launch": t_sched,

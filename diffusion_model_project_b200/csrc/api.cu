@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/b2d.h"
 #include "b2d_internal.h"
@@ -21,6 +22,11 @@ int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return B2D_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("B2D_PDL"); return e ? atoi(e) != 0 : false; }();
+  return on;
 }
 
 int num_sms() {

@@ -234,6 +234,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (threadIdx.x == 0) {
     // ---- loads: Q tile + whole K on one barrier, whole V on another (lands while S is computed) ----
@@ -404,7 +406,7 @@ static int launch_attention_tc(const void* qkv, void* out, int N, int T, int C, 
     configured = true;
   }
   dim3 grid((T + 127) / 128, N * heads);
-  attention_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
+  launch_pdl(attention_tc_kernel, grid, dim3(kTcThreads), smem, st, p);
   return check_launch("attention_tc_kernel");
 }
 

@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // the next kernel may start its own prologue ...
+  griddep_wait();               // ... and this one touches global memory only after its predecessor has completed
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
@@ -523,8 +525,8 @@ static int launch_v2(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
     if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  conv_v2_kernel<BN, HALO, XFORM><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(kp);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(conv_v2_kernel<BN, HALO, XFORM>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM, st, kp);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "conv_v2 launch: %s", cudaGetErrorString(e));
   return B2D_OK;
 }

@@ -9,6 +9,7 @@
 
 #include "../../include/b2d.h"
 #include "b2d_internal.h"
+#include "b2d_ptx.cuh"
 
 namespace b2d {
 
@@ -56,6 +57,8 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
     const float* __restrict__ beta, float eps, int act, const float* __restrict__ temb_table,
     const int* __restrict__ temb_row, int temb_row_stride, int temb_ld, int temb_col, double* __restrict__ stats_out,
     int in_f16) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ float sm[];
   float* sa = sm;
   float* sb = sm + C;
@@ -95,11 +98,18 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
   const long long base = (long long)n * nvec;
   float acc_s = 0.f, acc_ss = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  auto transform = [&](float (&f)[8], const float* a, const float* b, const float* t) {
+  // silu(v) = h + h * tanh(h), h = v / 2 (one MUFU op per element; the 1/2 is folded into the coefficients by the
+  // fast path).  tanh.approx.f32 is good to ~2^-11, below the 2^-9 rounding of the bf16 result.
+  auto transform = [&](float (&f)[8], const float* a, const float* b, const float* t, bool half_folded) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = fmaf(f[j], a[j], b[j]);
-      if (act) v = silu(v);
+      if (act) {
+        const float h = half_folded ? v : 0.5f * v;
+        float th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+        v = fmaf(h, th, h);
+      }
       if (TEMB) v += t[j];
       f[j] = v;
       acc_s += v;
@@ -112,7 +122,9 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
     const int c0 = (threadIdx.x % vpc) << 3;
     float a[8], b[8], t[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a[j] = sa[c0 + j]; b[j] = sb[c0 + j]; t[j] = st[c0 + j]; }
+    const float fold = act ? 0.5f : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = fold * sa[c0 + j]; b[j] = fold * sb[c0 + j]; t[j] = st[c0 + j]; }
     const uint4* xp = x + base;
     uint4* yp = y + base;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,14 +136,14 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
       for (int k = 0; k < 4; ++k) {
         float f[8];
         if (in_f16) unpack8_f16(u[k], f); else unpack8(u[k], f);
-        transform(f, a, b, t);
+        transform(f, a, b, t, true);
         yp[i + k * stride] = pack8(f);
       }
     }
     for (; i < nvec; i += stride) {
       float f[8];
       if (in_f16) unpack8_f16(__ldcs(xp + i), f); else unpack8(__ldcs(xp + i), f);
-      transform(f, a, b, t);
+      transform(f, a, b, t, true);
       yp[i] = pack8(f);
     }
   } else {
@@ -145,7 +157,7 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] += l[j];
       }
-      transform(f, sa + c0, sb + c0, st + c0);
+      transform(f, sa + c0, sb + c0, st + c0, false);
       const uint4 hi = pack8(f);
       y[base + i] = hi;
       if (y_lo != nullptr) y_lo[base + i] = pack8_lo(f, hi);
@@ -175,6 +187,8 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
 __global__ void __launch_bounds__(256) maxpool_stats_kernel(const uint4* __restrict__ x, const uint4* __restrict__ x_lo,
                                                             uint4* __restrict__ y, uint4* __restrict__ y_lo, int H, int W,
                                                             int C, double* __restrict__ stats) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int n = blockIdx.y;
   const int OH = H >> 1, OW = W >> 1, vpc = C >> 3;
   const long long nvec = (long long)OH * OW * vpc;
@@ -303,13 +317,13 @@ extern "C" int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo
     cfg = true;
   }
   if (temb_table != nullptr)
-    gn_apply_kernel<true><<<dim3(bx, N), 256, smem, (cudaStream_t)stream>>>(
+    launch_pdl(gn_apply_kernel<true>, dim3(bx, N), dim3(256), smem, (cudaStream_t)stream,
         (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, temb_table,
         temb_row, temb_row_stride, temb_ld, temb_col, stats_out, in_f16 ? 1 : 0);
   else
-    gn_apply_kernel<false><<<dim3(bx, N), 256, smem, (cudaStream_t)stream>>>(
-        (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, nullptr,
-        nullptr, 0, 0, 0, stats_out, in_f16 ? 1 : 0);
+    launch_pdl(gn_apply_kernel<false>, dim3(bx, N), dim3(256), smem, (cudaStream_t)stream,
+        (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act,
+        (const float*)nullptr, (const int*)nullptr, 0, 0, 0, stats_out, in_f16 ? 1 : 0);
   return check_launch("gn_apply_kernel");
 }
 
@@ -322,7 +336,7 @@ extern "C" int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, vo
   int bx = grid_for(nvec, 256);
   int per_img_cap = (num_sms() * 8 + N - 1) / N;
   if (bx > per_img_cap) bx = per_img_cap < 1 ? 1 : per_img_cap;
-  maxpool_stats_kernel<<<dim3(bx, N), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)x_lo, (uint4*)y,
+  launch_pdl(maxpool_stats_kernel, dim3(bx, N), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)x_lo, (uint4*)y,
                                                                        (uint4*)y_lo, H, W, C, stats);
   return check_launch("maxpool_stats_kernel");
 }

@@ -173,13 +173,31 @@ def pack_linear(w, bias, device, split=False):
 # ------------------------------------------------------------------------------------------------
 _WORKSPACE: dict = {}
 WORKSPACE_BYTES = 64 << 20
+_WORKSPACE_SLOT = [0]
+
+
+class workspace_slot:
+    """Plans created inside `with workspace_slot(k):` use the k-th split-K scratch buffer.  Plans that may run
+    CONCURRENTLY (two launch chains on two streams) must not share one; plans of one chain run back to back and do."""
+
+    def __init__(self, slot: int):
+        self.slot = slot
+
+    def __enter__(self):
+        self.prev = _WORKSPACE_SLOT[0]
+        _WORKSPACE_SLOT[0] = self.slot
+        return self
+
+    def __exit__(self, *exc):
+        _WORKSPACE_SLOT[0] = self.prev
+        return False
 
 
 def workspace(device) -> torch.Tensor:
-    """Split-K scratch shared by every plan of a device (plans run back to back on one stream).  The first
+    """Split-K scratch shared by every plan of a device and slot (plans run back to back on one stream).  The first
     16 KB are arrival counters: zero-initialised once, each kernel leaves them zero again."""
     dev = torch.device(device)
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), _WORKSPACE_SLOT[0])
     if key not in _WORKSPACE:
         _WORKSPACE[key] = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
     return _WORKSPACE[key]

@@ -45,7 +45,7 @@ class B200LatentDiffusionPredictor:
     def __init__(self, model_name="UNet", model_kwargs: Optional[dict] = None, distance_transform=True, *,
                  unet_state: Dict[str, torch.Tensor], vae_state: Dict[str, torch.Tensor], norm_factors: Sequence[float],
                  num_slices: int = 11, num_timesteps: int = 1000, precision: str = "bf16", use_graph: bool = True,
-                 device="cuda"):
+                 unet_chains: Optional[int] = None, device="cuda"):
         if model_name != "UNet":
             raise ValueError("only the 'UNet' denoiser exists in the reference (predictor.py:136)")
         if not torch.cuda.is_available():
@@ -58,6 +58,13 @@ class B200LatentDiffusionPredictor:
         self.precision = precision
         self.split = precision == "fp32x"
         self.use_graph = use_graph
+        # The UNet step at 8 samples/GPU is a chain of ~90 small launches, each with a fixed latency floor
+        # (launch, prologue, first TMA round trip, drain).  Slices are independent, so the batch can be cut into
+        # `unet_chains` groups whose launch chains run on separate streams (separate graph branches) and hide each
+        # other's floors.  Default from B2D_UNET_CHAINS (1 = single chain).
+        import os
+        self.unet_chains = int(os.environ.get("B2D_UNET_CHAINS", "1")) if unet_chains is None else int(unet_chains)
+        self._side_streams: List[torch.cuda.Stream] = []
         self.model = B200UNet(**model_kwargs, precision=precision, num_timesteps=num_timesteps, device=device)
         self.model.load_state_dict(unet_state)
         self.scheduler = B200Scheduler(num_timesteps=num_timesteps, device=device)
@@ -116,8 +123,24 @@ class B200LatentDiffusionPredictor:
         idx = torch.tensor(timesteps, dtype=torch.long, device=self.device)
         temb_steps = self.model.temb_table.index_select(0, idx).contiguous()
         ses["unet"] = None  # release the previous program's buffers first
-        ses["unet"] = self.model.build_program(ses["N"], ses["h"], ses["w"], x_in=ses["unet_in"], eps_out=ses["eps"], eps_mode=2,
-                                               temb_row=ses["step_idx"], temb_row_stride=0, temb_table=temb_steps)
+        ses["unet_parts"] = None
+        N = ses["N"]
+        chains = self.unet_chains if (self.unet_chains > 1 and N % self.unet_chains == 0 and N // self.unet_chains >= 8) else 1
+        if chains == 1:
+            ses["unet"] = self.model.build_program(N, ses["h"], ses["w"], x_in=ses["unet_in"], eps_out=ses["eps"], eps_mode=2,
+                                                   temb_row=ses["step_idx"], temb_row_stride=0, temb_table=temb_steps)
+        else:
+            parts, n = [], N // chains
+            ui = ses["unet_in"]
+            for c in range(chains):
+                xin = Act(ui.hi[c * n:(c + 1) * n], None if ui.lo is None else ui.lo[c * n:(c + 1) * n])
+                with engine.workspace_slot(c):
+                    parts.append(self.model.build_program(n, ses["h"], ses["w"], x_in=xin, eps_out=ses["eps"][c * n:(c + 1) * n],
+                                                          eps_mode=2, temb_row=ses["step_idx"], temb_row_stride=0, temb_table=temb_steps))
+            ses["unet_parts"] = parts
+            ses["unet"] = parts[0]
+            while len(self._side_streams) < chains - 1:
+                self._side_streams.append(torch.cuda.Stream(device=self.device))
         ses["temb_steps"] = temb_steps
         ses["temb_key"] = key
         ses["graph"] = None
@@ -151,8 +174,24 @@ class B200LatentDiffusionPredictor:
         ui = ses["unet_in"]
         _lib.call("b2d_planar_to_cl", ses["x"].data_ptr(), _lib.ptr(ui.hi), _lib.ptr(ui.lo), N * h * w, lat, 1, ui.C, 0, None, s)
 
+    def _run_unet(self, ses, s):
+        parts = ses.get("unet_parts")
+        if not parts:
+            ses["unet"]["program"].run(s)
+            return
+        # fork: chains 1.. on side streams, chain 0 on the caller's stream; join before the scheduler step
+        cur = torch.cuda.current_stream()
+        assert cur.cuda_stream == s, "multi-chain UNet step must be launched on the current stream"
+        for st in self._side_streams[:len(parts) - 1]:
+            st.wait_stream(cur)
+        for part, st in zip(parts[1:], self._side_streams):
+            part["program"].run(st.cuda_stream)
+        parts[0]["program"].run(s)
+        for st in self._side_streams[:len(parts) - 1]:
+            cur.wait_stream(st)
+
     def _one_step(self, ses, kind, coef, noise_step, clip_range, s, advance=True):
-        ses["unet"]["program"].run(s)
+        self._run_unet(ses, s)
         ui = ses["unet_in"]
         x = ses["x"]
         _lib.call("b2d_scheduler_step", kind, x.data_ptr(), ses["eps"].data_ptr(), _lib.ptr(noise_step), x.data_ptr(), x.numel(),
@@ -199,7 +238,8 @@ class B200LatentDiffusionPredictor:
         g = ses["graph"][1]
         for _ in range(n_steps):
             g.replay()
-        _lib.launch_count += n_steps * (len(ses["unet"]["program"]) + 1)
+        n_unet = sum(len(p_["program"]) for p_ in ses["unet_parts"]) if ses.get("unet_parts") else len(ses["unet"]["program"])
+        _lib.launch_count += n_steps * (n_unet + 1)
 
     def _decode(self, ses, s):
         """predictor.py:993-1021."""

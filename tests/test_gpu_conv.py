@@ -213,3 +213,80 @@ def test_fused_input_groupnorm_silu(ci, co, f16):
     h = bf16_round(F.silu(F.group_norm(xr, 32, gamma, beta, eps=1e-5)))
     ref = F.conv3d(h, w, b, padding=1)
     assert rel_err(got, ref) < (TOL_BF16 if cout_real >= 64 else 2e-3)
+
+
+def _conv2d_case(g, N, ci, co, H, W):
+    x = bf16_round(_rnd(g, N, ci, 1, H, W))
+    w = bf16_round(_rnd(g, co, ci, 3, 3, scale=(9 * ci) ** -0.5))
+    return x, w
+
+
+@pytest.mark.parametrize("N,ci,co,H,W", [(3, 64, 64, 32, 16), (2, 128, 256, 16, 16), (5, 256, 128, 8, 8), (7, 512, 512, 4, 4)])
+def test_persistent_engine_matches_first_engine(N, ci, co, H, W):
+    """engine=2 (persistent: halo staging where W,H % 16 == 0, split-K where the tile count is small) against
+    engine=1 (one tile per CTA) on the same operands: both accumulate bf16 products in fp32, only the summation
+    order differs."""
+    no_tf32()
+    g = torch.Generator().manual_seed(31 + ci)
+    x, w = _conv2d_case(g, N, ci, co, H, W)
+    pw = engine.pack_conv2d(w, [ci], None, DEV)
+    outs, stats, infos = [], [], []
+    for eng in (1, 2):
+        out = new_act(N, 1, H, W, co, DEV)
+        st = torch.zeros(N, 2, dtype=torch.float64, device=DEV)
+        plan = ConvPlan([to_act(x)], pw, out, cout=co, stats=st, stats_cpg=co, engine=eng)
+        plan.run(_stream())
+        outs.append(from_act(out, co)); stats.append(st.clone()); infos.append(plan.info2())
+    assert infos[0]["engine"] == 1 and infos[1]["engine"] == 2
+    assert infos[1]["halo"] == (1 if H % 16 == 0 and W % 16 == 0 else 0)
+    ref = F.conv2d(x[:, :, 0], w, None, padding=1)[:, :, None]
+    assert rel_err(outs[1], ref) < TOL_BF16
+    assert rel_err(outs[1], outs[0]) < 8e-3  # one bf16 ulp of the output at most
+    assert ((stats[1] - stats[0]).abs().max() / stats[0].abs().max()).item() < 1e-5
+
+
+def test_split_k_is_deterministic_and_reuses_workspace():
+    """Deep UNet level shape (M = 7*4 rows, K = 9*2048): the plan splits K, partials go through the shared workspace,
+    the last arriver reduces in a fixed order -> repeated launches are bit-identical and the counters self-reset."""
+    no_tf32()
+    g = torch.Generator().manual_seed(41)
+    N, ci, co = 7, 2048, 1024
+    x, w = _conv2d_case(g, N, ci, co, 2, 2)
+    pw = engine.pack_conv2d(w, [ci], None, DEV)
+    out = new_act(N, 1, 2, 2, co, DEV)
+    st = torch.zeros(N, 2, dtype=torch.float64, device=DEV)
+    plan = ConvPlan([to_act(x)], pw, out, cout=co, stats=st, stats_cpg=co)
+    info = plan.info2()
+    assert info["ksplit"] > 1 and info["ws_kib"] > 0, info
+    plan.run(_stream())
+    first = out.hi.clone()
+    for _ in range(3):
+        out.hi.zero_()
+        plan.run(_stream())
+        assert torch.equal(out.hi, first)
+    ref = F.conv2d(x[:, :, 0], w, None, padding=1)[:, :, None]
+    assert rel_err(from_act(out, co), ref) < TOL_BF16
+    assert int(engine.workspace(DEV)[:16384].view(torch.int32).abs().sum()) == 0  # arrival counters back to zero
+
+
+@pytest.mark.parametrize("ci,co", [(256, 128), (128, 256)])
+def test_upsample_folded_conv_matches_upsample_then_conv(ci, co):
+    """decoder.py:46-47 / 58-59: Conv3d(nn.Upsample(scale=(1,2,2))(x)) as four phase convs on the low-res map."""
+    no_tf32()
+    g = torch.Generator().manual_seed(51 + ci)
+    N, D, H, W = 2, 3, 16, 32
+    x = bf16_round(_rnd(g, N, ci, D, H, W))
+    w = _rnd(g, co, ci, 3, 3, 3, scale=(27 * ci) ** -0.5).cpu()
+    b = _rnd(g, co).cpu()
+    out = new_act(N, D, 2 * H, 2 * W, co, DEV)
+    st = torch.zeros(N, 32, 2, dtype=torch.float64, device=DEV)
+    xa = to_act(x)
+    for ph in range(4):
+        pw = engine.pack_conv3d_upsampled(w, b, DEV, ph >> 1, ph & 1)
+        plan = ConvPlan([xa], pw, out, cout=co, stats=st, stats_cpg=co // 32, out_geom=(2 * H, 2 * W, 2, 2, ph >> 1, ph & 1))
+        assert plan.info2()["halo"] == 1 and plan.info2()["kgroups"] == 3 * ci // 64
+        plan.run(_stream())
+    ref = F.conv3d(F.interpolate(x, scale_factor=(1, 2, 2), mode="nearest"), w.to(DEV), b.to(DEV), padding=1)
+    assert rel_err(from_act(out, co), ref) < 1.5e-2  # summed-then-rounded weights vs rounded-then-summed
+    sref = stats_ref(ref, 32)
+    assert ((st - sref).abs().max() / sref.abs().max()).item() < 2e-2
