@@ -171,3 +171,19 @@ def test_in_kernel_noise_ddpm_runs_and_is_seeded(unet_sd, vae_sd):
     torch.manual_seed(5)
     b = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()
     assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_e3d_encoder_and_sanity_roundtrip():
+    """`encode_3d_deterministic` (dual_vae/model.py:235-243) on the same engine, and the reference's
+    VAE sanity path GT -> E3D -> D3D (scripts/eval_testset_end2end.py:734-776), against the CPU oracle."""
+    vsd = synth.synth_vae_state(seed=1, branches=("encoder_2d", "encoder_3d", "decoder_3d"))
+    vae = B200DualVAE(3, 8, device="cuda").load_state_dict(vsd)
+    gen = torch.Generator().manual_seed(17)
+    x = torch.randn(1, 3, 3, 32, 32, generator=gen)
+    z, (mu, logvar) = vae.encode_3d_deterministic(x.cuda())
+    mu_ref, logvar_ref = ovae.encoder_forward(vsd, x, "encoder_3d.")
+    assert z is mu and rel_l2(mu.cpu(), mu_ref) <= 1e-2
+    assert rel_l2(logvar.cpu(), torch.clamp(logvar_ref, -10.0, 10.0)) <= 1e-2
+    rec = vae.decode_3d(mu).cpu()
+    rec_ref = ovae.decode_3d(vsd, mu_ref)
+    assert rec.shape == x.shape and rel_l2(rec, rec_ref) <= 1.5e-2  # two bf16 networks back to back
