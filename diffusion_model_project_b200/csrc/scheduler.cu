@@ -43,7 +43,7 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   z1 = r * s;
 }
 
-struct Coef { float a, b, c1, c2, s; };
+struct Coef { float a, b, c1, c2, s; double inv_a; };
 
 // ticket counter of the "last block advances the step index" protocol (one copy per device, no allocation)
 __device__ unsigned int g_done_counter = 0u;
@@ -51,7 +51,10 @@ __device__ unsigned int g_done_counter = 0u;
 __device__ __forceinline__ float step_one(float x, float e, float z, const Coef& k, int kind, int clip, float lo, float hi,
                                           bool use_noise) {
   // x0 = (x_t - sqrt(1-abar) * eps) / sqrt(abar)               diffusion.py:124
-  float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.b, e)), k.a);
+  // The IEEE fp32 quotient through fp64: n * (1/a) in double is within 2^-52 of n/a, far inside the 2^-49 gap that
+  // separates an fp32 quotient from a rounding midpoint, so the final rounding is the correctly rounded n/a --
+  // bit-identical to the reference's division at a third of div.rn.f32's instruction count.
+  float x0 = __double2float_rn(__dmul_rn((double)__fsub_rn(x, __fmul_rn(k.b, e)), k.inv_a));
   if (clip) x0 = fminf(fmaxf(x0, lo), hi);                      // torch.clamp, diffusion.py:169 / :219
   // DDPM: c1*x0 + c2*x_t (diffusion.py:148); DDIM: sqrt(abar')*x0 + sqrt(1-abar'-s^2)*eps (:225-228)
   const float second = (kind == 0) ? __fmul_rn(k.c2, x) : __fmul_rn(k.c2, e);
@@ -60,7 +63,8 @@ __device__ __forceinline__ float step_one(float x, float e, float z, const Coef&
   return out;
 }
 
-__global__ void __launch_bounds__(256) scheduler_step_kernel(
+template <bool PHILOX>
+__global__ void __launch_bounds__(256, PHILOX ? 2 : 4) scheduler_step_kernel(
     int kind, const float4* __restrict__ x_t, const float4* __restrict__ eps, const float4* __restrict__ noise,
     float4* __restrict__ x_out, long long n_vec, long long n_elem, const float* __restrict__ coef, int* step_idx,
     int step_off, int step_inc, int clip, float clip_lo, float clip_hi, __nv_bfloat16* __restrict__ x_bf16, int group,
@@ -69,28 +73,23 @@ __global__ void __launch_bounds__(256) scheduler_step_kernel(
   Coef k;
   k.a = __ldg(coef + row * 8 + 0); k.b = __ldg(coef + row * 8 + 1); k.c1 = __ldg(coef + row * 8 + 2);
   k.c2 = __ldg(coef + row * 8 + 3); k.s = __ldg(coef + row * 8 + 4);
+  k.inv_a = 1.0 / (double)k.a;
   const bool use_noise = (k.s != 0.f);
+  if (!PHILOX && use_noise && noise == nullptr) __trap();  // caller promised a noise-free row (seed == 0)
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-    const float4 x = __ldg(x_t + i);
-    const float4 e = __ldg(eps + i);
-    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (use_noise) {
-      if (noise != nullptr) {
-        z = __ldg(noise + i);
-      } else {
-        uint32_t r[4];
-        philox4x32_10((uint64_t)i, (uint32_t)row, seed, r);
-        box_muller(r[0], r[1], z.x, z.y);
-        box_muller(r[2], r[3], z.z, z.w);
-      }
+  auto one_vec = [&](long long i, const float4& x, const float4& e, float4 z) {
+    if (PHILOX && use_noise && noise == nullptr) {
+      uint32_t r[4];
+      philox4x32_10((uint64_t)i, (uint32_t)row, seed, r);
+      box_muller(r[0], r[1], z.x, z.y);
+      box_muller(r[2], r[3], z.z, z.w);
     }
     float4 o;
     o.x = step_one(x.x, e.x, z.x, k, kind, clip, clip_lo, clip_hi, use_noise);
     o.y = step_one(x.y, e.y, z.y, k, kind, clip, clip_lo, clip_hi, use_noise);
     o.z = step_one(x.z, e.z, z.z, k, kind, clip, clip_lo, clip_hi, use_noise);
     o.w = step_one(x.w, e.w, z.w, k, kind, clip, clip_lo, clip_hi, use_noise);
-    x_out[i] = o;
+    __stcs(x_out + i, o);
     if (x_bf16 != nullptr) {
       const long long e0 = i * 4;
       const long long g = e0 / group;
@@ -99,7 +98,19 @@ __global__ void __launch_bounds__(256) scheduler_step_kernel(
       dst[0] = __floats2bfloat162_rn(o.x, o.y);
       dst[1] = __floats2bfloat162_rn(o.z, o.w);
     }
+  };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool ld_noise = use_noise && noise != nullptr;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // two independent vectors per iteration: all six 16-byte loads are issued before the (IEEE) divisions start
+  for (; i + stride < n_vec; i += 2 * stride) {
+    const float4 x0 = __ldcs(x_t + i), x1 = __ldcs(x_t + i + stride);
+    const float4 e0 = __ldcs(eps + i), e1 = __ldcs(eps + i + stride);
+    const float4 z0 = ld_noise ? __ldcs(noise + i) : zero4, z1 = ld_noise ? __ldcs(noise + i + stride) : zero4;
+    one_vec(i, x0, e0, z0);
+    one_vec(i + stride, x1, e1, z1);
   }
+  for (; i < n_vec; i += stride) one_vec(i, __ldcs(x_t + i), __ldcs(eps + i), ld_noise ? __ldcs(noise + i) : zero4);
   // scalar tail (n_elem not a multiple of 4)
   if (blockIdx.x == 0 && threadIdx.x < (n_elem & 3)) {
     const long long i = n_vec * 4 + threadIdx.x;
@@ -108,7 +119,7 @@ __global__ void __launch_bounds__(256) scheduler_step_kernel(
     float z = 0.f;
     if (use_noise) {
       if (noise != nullptr) z = reinterpret_cast<const float*>(noise)[i];
-      else {
+      else if (PHILOX) {
         uint32_t r[4];
         philox4x32_10((uint64_t)n_vec, (uint32_t)row, seed, r);
         float z0, z1, z2, z3;
@@ -167,9 +178,16 @@ extern "C" int b2d_scheduler_step(int kind, const float* x_t, const float* eps, 
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  scheduler_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-      kind, (const float4*)x_t, (const float4*)eps, (const float4*)noise, (float4*)x_out, n_vec, n_elem, coef, step_idx,
-      step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed);
+  // in-kernel Philox noise only when no noise tensor is given AND a seed is: seed == 0 asserts that the rows used
+  // have s == 0 (deterministic DDIM) -- the lean kernel traps if that is violated
+  if (noise == nullptr && seed != 0)
+    scheduler_step_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        kind, (const float4*)x_t, (const float4*)eps, (const float4*)noise, (float4*)x_out, n_vec, n_elem, coef, step_idx,
+        step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed);
+  else
+    scheduler_step_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        kind, (const float4*)x_t, (const float4*)eps, (const float4*)noise, (float4*)x_out, n_vec, n_elem, coef, step_idx,
+        step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed);
   return check_launch("scheduler_step_kernel");
 }
 

@@ -271,7 +271,8 @@ class B200LatentDiffusionPredictor:
         if noise is None:
             noise = torch.randn(ses["N"], self.latent_channels, ses["h"], ses["w"], device=self.device)
         self._set_latent(ses, noise, s)
-        self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFF
+        # eta == 0: no row draws noise -> seed 0 selects the scheduler kernel without the Philox generator
+        self.seed = 0 if (eta == 0.0 or step_noise is not None) else (int(torch.initial_seed()) & 0xFFFFFFFFFFFF) | 1
         self._run_loop(ses, 1, ses["coef"], num_steps, step_noise, (-30.0, 30.0), record)
         return self._decode(ses, s)
 
@@ -298,7 +299,7 @@ class B200LatentDiffusionPredictor:
         if noise is None:
             noise = torch.randn(ses["N"], self.latent_channels, ses["h"], ses["w"], device=self.device)
         self._set_latent(ses, noise, s)
-        self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFF
+        self.seed = (int(torch.initial_seed()) & 0xFFFFFFFFFFFF) | 1
         self._run_loop(ses, 0, ses["coef"], T, step_noise, (-30.0, 30.0), record)
         return self._decode(ses, s)
 

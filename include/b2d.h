@@ -55,7 +55,8 @@ B2D_API const char* b2d_last_error(void);
  *
  * coef: device array of rows {a, b, c1, c2, s, 0, 0, 0}; the row used is
  * (step_idx ? *step_idx : 0) + step_off, so a captured graph can advance a device counter.
- * z = noise[i] if noise != NULL, else (if s != 0) N(0,1) from Philox4x32-10(seed, row, i).
+ * z = noise[i] if noise != NULL, else (if s != 0) N(0,1) from Philox4x32-10(seed, row, i); seed == 0 with
+ * noise == NULL asserts s == 0 for the rows used (deterministic DDIM) and selects the kernel without the generator.
  * Optional second output for the fused loop: x_bf16[(i / group) * group_stride + i % group].
  * If step_inc != 0 the kernel's last block adds step_inc to *step_idx after all reads.
  * ---------------------------------------------------------------------------------------- */
