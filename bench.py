@@ -195,6 +195,7 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     peaks = load_peaks()
 

@@ -19,6 +19,23 @@ constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle atom
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kThreads = 192;
 
+// Division by a launch-constant through a precomputed multiplier (valid for 0 <= n < 2^31): the unit decode runs once
+// per work unit in every warp role, and a hardware-emulated integer division costs ~25 instructions.
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __host__ void set(uint32_t div) {
+    d = div;
+    if (div <= 1) { mul = 0; shr = 0; return; }
+    uint32_t lg = 0;
+    while ((1u << lg) < div) ++lg;  // ceil(log2(div))
+    const uint32_t p = 31 + lg;
+    mul = (uint32_t)(((1ull << p) + div - 1) / div);
+    shr = p - 32;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d <= 1 ? n : (__umulhi(n, mul) >> shr); }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 struct ConvKParams {
   CUtensorMap tmapA[B2D_MAX_SEG];
   CUtensorMap tmapB;
@@ -57,6 +74,7 @@ struct ConvKParams {
   int num_units;     // tiles_m * tiles_ncol * ksplit
   float* ws;         // [tile][ksplit][128][BLOCK_N] fp32 partial accumulators
   int* counters;     // [tile] arrival counters (self-resetting)
+  FastDiv fd_ksplit, fd_ncol, fd_w, fd_h, fd_d;  // unit index -> (split, N tile, x, y, z, n tile)
   // ---- fused input normalisation (halo mode): A tiles are raw pre-GroupNorm values; dedicated warps rewrite each
   // staged tile in shared memory as bf16 silu(gamma * (x - mean) * rstd + beta) before the MMAs read it ----
   int xform;                   // 1: enabled (single segment)

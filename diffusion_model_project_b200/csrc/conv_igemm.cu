@@ -454,6 +454,9 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     constexpr long long kCounterBytes = 16384;
     k.ksplit = ksplit;
     k.num_units = (int)(tiles * ksplit);
+    k.fd_ksplit.set((uint32_t)ksplit); k.fd_ncol.set((uint32_t)k.tiles_ncol);
+    k.fd_w.set((uint32_t)k.tiles_w); k.fd_h.set((uint32_t)k.tiles_h); k.fd_d.set((uint32_t)k.tiles_d);
+    if ((long long)k.ngroups * (ksplit + 1) >= (1LL << 31)) { delete pl; return set_error(B2D_E_INVALID, "K loop too long"); }
     if (ksplit > 1) {
       k.counters = reinterpret_cast<int*>(d->workspace);
       k.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->workspace) + kCounterBytes);

@@ -60,16 +60,19 @@ struct UnitCoord {
 
 __device__ __forceinline__ UnitCoord decode_unit(const ConvKParams& p, int u) {
   UnitCoord c;
-  c.ks = u % p.ksplit;
-  int t = u / p.ksplit;
-  c.tile = t;
-  const int nt = t % p.tiles_ncol;
-  t /= p.tiles_ncol;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h; t /= p.tiles_h;
-  const int td = t % p.tiles_d; t /= p.tiles_d;
-  c.x0 = tw << p.lbw; c.y0 = th << p.lbh; c.z0 = td << p.lbd; c.n0 = t << p.lbn;
-  c.gcol0 = nt;
+  uint32_t t, r;
+  p.fd_ksplit.divmod((uint32_t)u, t, r);
+  c.ks = (int)r;
+  c.tile = (int)t;
+  p.fd_ncol.divmod(t, t, r);
+  c.gcol0 = (int)r;
+  p.fd_w.divmod(t, t, r);
+  c.x0 = (int)r << p.lbw;
+  p.fd_h.divmod(t, t, r);
+  c.y0 = (int)r << p.lbh;
+  p.fd_d.divmod(t, t, r);
+  c.z0 = (int)r << p.lbd;
+  c.n0 = (int)t << p.lbn;
   return c;
 }
 
@@ -77,8 +80,12 @@ __device__ __forceinline__ UnitCoord decode_unit(const ConvKParams& p, int u) {
 struct GroupIter {
   int s, t, c, g, g_hi;
   __device__ __forceinline__ void init(const ConvKParams& p, int ks) {
-    g = (int)((long long)p.ngroups * ks / p.ksplit);
-    g_hi = (int)((long long)p.ngroups * (ks + 1) / p.ksplit);
+    if (p.ksplit == 1) {  // the common case: the whole K loop, no divisions
+      g = 0; g_hi = p.ngroups; s = 0; t = 0; c = 0;
+      return;
+    }
+    g = (int)p.fd_ksplit.div((uint32_t)(p.ngroups * ks));
+    g_hi = (int)p.fd_ksplit.div((uint32_t)(p.ngroups * (ks + 1)));
     s = 0;
     while (s + 1 < p.nseg && g >= p.goff[s + 1]) ++s;
     const int r = g - p.goff[s];
