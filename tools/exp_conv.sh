@@ -1,10 +1,6 @@
-python tools/profile_conv.py 2d 88 512 256 16 0 2 20 1
-python tools/profile_conv.py 2d 88 512 512 8 0 2 20 1
-python tools/profile_conv.py 2d 88 512 512 8 256 2 20 1
-python tools/profile_conv.py 2d 88 1024 512 8 0 2 20 1
-python tools/profile_conv.py 2d 88 1024 1024 4 0 2 20 1
-python tools/profile_conv.py 2d 88 1024 1024 4 128 2 20 1
-python tools/profile_conv.py 2d 88 2048 1024 4 0 2 20 1
-python tools/profile_conv.py 2d 88 2048 2048 2 0 2 20 1
-python tools/profile_conv.py 2d 88 2048 2048 2 256 2 20 1
-python tools/profile_conv.py 2d 88 1024 2048 2 0 2 20 1
+python tools/profile_conv.py 2d 1 64 64 16 0 2 50 1
+python tools/profile_conv.py 2d 1 64 64 16 0 2 50 0
+python tools/profile_conv.py 2d 1 64 64 16 0 1 50 1
+python tools/profile_conv.py 2d 8 64 64 64 0 2 50 1
+python tools/profile_conv.py 2d 16 1024 1024 4 0 2 50 1
+python tools/profile_conv.py 2d 88 256 256 16 0 2 50 1
