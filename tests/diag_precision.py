@@ -1,5 +1,5 @@
 """Error attribution of the bf16 path on the golden predict_ddim case (1 x 2 x 128 x 128, 3 DDIM steps):
-per-stage errors against the CPU oracle.  usage: python tools/diag_precision.py [precision]"""
+per-stage errors against the CPU oracle.  usage: python tests/diag_precision.py [precision]"""
 import os
 import sys
 
@@ -7,7 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from diffusion_model_project_b200 import synth  # noqa: E402
 from diffusion_model_project_b200.predictor import B200LatentDiffusionPredictor  # noqa: E402
 from oracle import predictor as opred, vae as ovae  # noqa: E402

@@ -3,7 +3,7 @@
   * per-step noise-prediction error  max|eps - eps_ref| / max|eps_ref|  with the ORACLE's UNet evaluated on the GPU
     path's own x_t (every --every-th step), north-star bound 1e-3;
   * final velocity-field relative L2 against the oracle's own 1000-step trajectory, bound 1e-2.
-usage: python tools/parity_ddpm1000.py [--batch 1] [--steps 1000] [--every 25] [--precision fp32x]"""
+usage: python tests/parity_ddpm1000.py [--batch 1] [--steps 1000] [--every 25] [--precision fp32x]"""
 import argparse
 import os
 import sys
@@ -13,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from diffusion_model_project_b200 import synth  # noqa: E402
 from diffusion_model_project_b200.predictor import B200LatentDiffusionPredictor  # noqa: E402
 from oracle import predictor as opred, unet as ounet  # noqa: E402
