@@ -23,6 +23,7 @@
 #include "../../include/b2d.h"
 #include "b2d_internal.h"
 #include "b2d_ptx.cuh"
+#include "attention_tc.cuh"
 
 namespace b2d {
 
@@ -188,192 +189,12 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
 
 
 // ============================================================================================
-// tensor-core path (bf16)
+// tensor-core path (bf16): device body in attention_tc.cuh
 // ============================================================================================
-constexpr int kTcThreads = 128;       // one thread per query row / TMEM lane
-constexpr int kTcTmemCols = 512;      // S: columns [0, T), O: columns [256, 256 + min(d, 256))
-constexpr int kTcOCol = 256;
-constexpr int kQChunkBytes = 128 * 128;  // one 64-channel chunk of a 128-row K-major tile
-
-struct AttnTcParams {
-  CUtensorMap tmap;  // bf16 [N][T][3C], box {64, RB, 1}, 128B swizzle
-  __nv_bfloat16* out;
-  int T, C, heads, d;
-  int RB;            // rows per TMA box = min(128, T)
-  float scale_log2e;
-};
-
 __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw_attn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_attn) + 1023) & ~uintptr_t(1023));
-  const int T = p.T, d = p.d, C = p.C;
-  const int dch = d >> 6;                     // 64-channel chunks per head
-  const int kv_chunk = T * 128;               // bytes of one [T x 64] chunk tile
-  uint8_t* sQ = smem;                         // dch x [128 x 128 B]  (rows >= RB never read into valid output)
-  uint8_t* sK = sQ + dch * kQChunkBytes;      // dch x [T x 128 B]
-  uint8_t* sV = sK + dch * kv_chunk;          // dch x [T x 128 B]
-  uint8_t* sP = smem;                         // ceil(T/64) x [128 x 128 B], aliases Q/K once S is complete
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + dch * kv_chunk);  // qk, v, s, o
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int nh = blockIdx.y;
-  const int n = nh / p.heads, h = nh - n * p.heads;
-  const int m0 = blockIdx.x * 128;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
-    fence_barrier_init();
-    prefetch_tmap(&p.tmap);
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, kTcTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  griddep_launch_dependents();
-  griddep_wait();
-
-  if (threadIdx.x == 0) {
-    // ---- loads: Q tile + whole K on one barrier, whole V on another (lands while S is computed) ----
-    const int RB = p.RB;
-    mbar_arrive_expect_tx(&bars[0], (uint32_t)(dch * RB * 128 + dch * kv_chunk));
-    for (int c = 0; c < dch; ++c) tma_load_3d(sQ + c * kQChunkBytes, &p.tmap, &bars[0], h * d + c * 64, m0, n);
-    for (int c = 0; c < dch; ++c)
-      for (int r = 0; r < T; r += RB) tma_load_3d(sK + c * kv_chunk + r * 128, &p.tmap, &bars[0], C + h * d + c * 64, r, n);
-    mbar_arrive_expect_tx(&bars[1], (uint32_t)(dch * kv_chunk));
-    for (int c = 0; c < dch; ++c)
-      for (int r = 0; r < T; r += RB) tma_load_3d(sV + c * kv_chunk + r * 128, &p.tmap, &bars[1], 2 * C + h * d + c * 64, r, n);
-    // ---- S[128 x T] = Q K^T ---------------------------------------------------------------------
-    mbar_wait(&bars[0], 0);
-    tc_fence_after();
-    const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)T);
-    uint32_t accum = 0;
-    for (int c = 0; c < dch; ++c) {
-      const uint64_t adesc = umma_smem_desc(smem_u32(sQ + c * kQChunkBytes), 1024, 2);
-      const uint64_t bdesc = umma_smem_desc(smem_u32(sK + c * kv_chunk), 1024, 2);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc_s, accum);
-        accum = 1;
-      }
-    }
-    umma_commit(&bars[2]);
-  }
-  __syncwarp();
-
-  // ---- softmax over the keys: thread = query row, two passes over the TMEM-resident scores --------
-  const int row = threadIdx.x;
-  const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
-  mbar_wait(&bars[2], 0);
-  tc_fence_after();
-  float mx = -INFINITY;
-  if (T >= 32) {
-    for (int c0 = 0; c0 < T; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(lane_addr + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-  } else {
-    uint32_t v[32];
-    tmem_ld_32x16(lane_addr, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-  }
-  const float sc = p.scale_log2e;
-  const float mxs = mx * sc;
-  float sum = 0.f;
-  uint8_t* prow = sP + row * 128;
-  const int sw = row & 7;
-  auto emit = [&](const uint32_t* v, int c0, int ncol) {
-    // ncol consecutive keys starting at c0 (c0 % 8 == 0): bf16 pairs into the swizzled K-major P tile
-#pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-      if (j8 * 8 < ncol) {
-        uint32_t w[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float e0 = exp2f(fmaf(__uint_as_float(v[j8 * 8 + 2 * q]), sc, -mxs));
-          const float e1 = exp2f(fmaf(__uint_as_float(v[j8 * 8 + 2 * q + 1]), sc, -mxs));
-          __nv_bfloat162 hv = __floats2bfloat162_rn(e0, e1);
-          sum += __low2float(hv) + __high2float(hv);
-          w[q] = *reinterpret_cast<uint32_t*>(&hv);
-        }
-        const int key = c0 + j8 * 8;
-        const int chunk16 = (key & 63) >> 3;
-        *reinterpret_cast<uint4*>(prow + (key >> 6) * kQChunkBytes + ((chunk16 ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
-  };
-  if (T >= 32) {
-    for (int c0 = 0; c0 < T; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(lane_addr + c0, v);
-      tmem_ld_wait();
-      emit(v, c0, 32);
-    }
-  } else {
-    uint32_t v[32];
-    tmem_ld_32x16(lane_addr, v);
-    tmem_ld_wait();
-    emit(v, 0, 16);
-  }
-  const float inv = 1.f / sum;
-  fence_proxy_async();  // P (generic-proxy stores) must be visible to the tensor core's async-proxy reads
-  tc_fence_before();
-  __syncthreads();
-
-  // ---- O[128 x d] = P V, at most 256 output columns per pass -------------------------------------
-  const int DC = d < 256 ? d : 256;
-  const int q = m0 + row;
-  for (int g = 0; g * DC < d; ++g) {
-    if (threadIdx.x == 0) {
-      tc_fence_after();
-      if (g == 0) { mbar_wait(&bars[1], 0); tc_fence_after(); }
-      const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)DC) | kUmmaBMajorMN;
-      uint32_t accum = 0;
-      for (int k0 = 0; k0 < T; k0 += 16) {
-        const uint64_t adesc = umma_smem_desc(smem_u32(sP + (k0 >> 6) * kQChunkBytes), 1024, 2) + 2 * ((k0 & 63) >> 4);
-        const uint64_t bdesc = umma_smem_desc_mn(smem_u32(sV + (g * (DC >> 6)) * kv_chunk + k0 * 128), (uint32_t)kv_chunk, 1024, 2);
-        umma_bf16(tmem_base + kTcOCol, adesc, bdesc, idesc_o, accum);
-        accum = 1;
-      }
-      umma_commit(&bars[3]);
-    }
-    __syncwarp();
-    mbar_wait(&bars[3], g & 1);
-    tc_fence_after();
-    __nv_bfloat16* orow = p.out + ((long long)n * T + q) * C + (long long)h * d + g * DC;
-    for (int c0 = 0; c0 < DC; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(lane_addr + kTcOCol + c0, v);
-      tmem_ld_wait();
-      if (q < T) {
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(v[j8 * 8 + 2 * e]) * inv, __uint_as_float(v[j8 * 8 + 2 * e + 1]) * inv);
-            w[e] = *reinterpret_cast<uint32_t*>(&hv);
-          }
-          *reinterpret_cast<uint4*>(orow + c0 + j8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();  // every row has drained O before the next pass overwrites it / before dealloc
-  }
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTcTmemCols);
-  }
+  attention_tc_item<false>(p, p, (int)blockIdx.x, (int)blockIdx.y, smem, 0u);
 }
 
 typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -20,507 +20,15 @@
 // Split-K (deep UNet levels: M of a few hundred rows, K up to 18432): every split writes its fp32
 // partial tile to a workspace; the last split to arrive (atomic ticket, no spinning) sums all
 // partials in a fixed order -- deterministic -- and runs the fused epilogue.
-#include "conv_common.cuh"
+#include "conv_v2.cuh"
 
 namespace b2d {
 
-template <int BN, bool HALO, bool XFORM = false>
-struct V2Cfg {
-  static_assert(HALO || !XFORM, "input transform needs halo staging");
-  static constexpr int MT = HALO ? 2 : 1;                       // M = 128 halves per unit
-  static constexpr int A_TILE = HALO ? 18 * 18 * 128 : kABytes;  // bytes landed per A load
-  static constexpr int A_STAGE = (A_TILE + 1023) / 1024 * 1024;
-  // weight taps per B stage: narrow N tiles batch several taps behind one mbarrier so the single
-  // MMA-issuing thread is not handshake-bound (an N = 16 MMA lasts ~32 clocks)
-  static constexpr int TPB = HALO ? (BN <= 16 ? 9 : BN <= 64 ? 3 : 1) : 1;
-  static constexpr int B_TILE = BN * kBlockK * 2;
-  static constexpr int B_STAGE = TPB * B_TILE;
-  static constexpr int NA = HALO ? ((BN >= 128 || XFORM) ? 2 : 3) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
-  static constexpr int NB = HALO ? (BN == 256 ? 4 : BN == 128 ? 6 : BN == 64 ? 4 : 3) : NA;
-  static constexpr int BNC = BN < 32 ? 32 : BN;                  // TMEM columns of one M half
-  static constexpr int ACC_COLS = MT * BNC;                      // one accumulator stage
-  static constexpr int NACC = 2 * ACC_COLS <= 512 ? 2 : 1;       // BN = 256 halo: 512 columns, single-buffered
-  static constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : NACC * ACC_COLS <= 64 ? 64 : NACC * ACC_COLS <= 128 ? 128
-                                   : NACC * ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int EPI_WARPS = 4 * MT;
-  static constexpr int XF_WARPS = XFORM ? 4 : 0;                 // warps rewriting staged A tiles (GroupNorm + SiLU)
-  static constexpr int XF_MAXC = 512;                            // input channels the coefficient table holds
-  static constexpr int BP_WARP = HALO ? 2 + EPI_WARPS + XF_WARPS : -1;  // halo: the weight ring has its own producer warp
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (HALO ? 32 : 0);
-  static constexpr int NBARS = 3 * NA + 2 * NB + 4;
-  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 * EPI_WARPS + (XFORM ? 2 * XF_MAXC * 4 + 16 : 0) + 1024;
-  static_assert(NACC * ACC_COLS <= 512, "TMEM budget");
-  static_assert(SMEM <= 227 * 1024, "shared memory budget");
-  static_assert(!HALO || 9 % TPB == 0, "taps per stage must divide 9");
-};
-
-struct UnitCoord {
-  int x0, y0, z0, n0, gcol0, ks, tile;  // tile = m_tile * tiles_ncol + n_tile
-};
-
-__device__ __forceinline__ UnitCoord decode_unit(const ConvKParams& p, int u) {
-  UnitCoord c;
-  uint32_t t, r;
-  p.fd_ksplit.divmod((uint32_t)u, t, r);
-  c.ks = (int)r;
-  c.tile = (int)t;
-  p.fd_ncol.divmod(t, t, r);
-  c.gcol0 = (int)r;
-  p.fd_w.divmod(t, t, r);
-  c.x0 = (int)r << p.lbw;
-  p.fd_h.divmod(t, t, r);
-  c.y0 = (int)r << p.lbh;
-  p.fd_d.divmod(t, t, r);
-  c.z0 = (int)r << p.lbd;
-  c.n0 = (int)t << p.lbn;
-  return c;
-}
-
-// iterate the A-groups [g_lo, g_hi) of one unit as (segment, tap-or-ztap, chunk)
-struct GroupIter {
-  int s, t, c, g, g_hi;
-  __device__ __forceinline__ void init(const ConvKParams& p, int ks) {
-    if (p.ksplit == 1) {  // the common case: the whole K loop, no divisions
-      g = 0; g_hi = p.ngroups; s = 0; t = 0; c = 0;
-      return;
-    }
-    g = (int)p.fd_ksplit.div((uint32_t)(p.ngroups * ks));
-    g_hi = (int)p.fd_ksplit.div((uint32_t)(p.ngroups * (ks + 1)));
-    s = 0;
-    while (s + 1 < p.nseg && g >= p.goff[s + 1]) ++s;
-    const int r = g - p.goff[s];
-    t = r / p.cchunks[s];
-    c = r - t * p.cchunks[s];
-  }
-  __device__ __forceinline__ bool done() const { return g >= g_hi; }
-  __device__ __forceinline__ void next(const ConvKParams& p) {
-    ++g;
-    if (++c == p.cchunks[s]) {
-      c = 0;
-      ++t;
-      if (g == p.goff[s + 1]) { t = 0; ++s; }
-    }
-  }
-};
-
 template <int BN, bool HALO, bool XFORM>
 __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_kernel(const __grid_constant__ ConvKParams p) {
-  using Cfg = V2Cfg<BN, HALO, XFORM>;
-  constexpr int MT = Cfg::MT, NA = Cfg::NA, NB = Cfg::NB;
-  constexpr int CW = BN < 32 ? 16 : 32;
-
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + NA * Cfg::A_STAGE;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + NB * Cfg::B_STAGE);
-  uint64_t* a_empty = a_full + NA;
-  uint64_t* a_ready = a_empty + NA;  // XFORM: tile rewritten, visible to the tensor core
-  uint64_t* b_full = a_ready + NA;
-  uint64_t* b_empty = b_full + NB;
-  uint64_t* t_full = b_empty + NB;
-  uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [MT]
-  double* sm_stats = reinterpret_cast<double*>(tmem_slot + 4);               // [EPI_WARPS][64] per-warp GroupNorm sums (halo mode)
-  float* sm_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_stats + 64 * Cfg::EPI_WARPS) + 15) & ~uintptr_t(15));  // XFORM: [2][XF_MAXC] scale, shift
-
-  // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], XFORM ? Cfg::XF_WARPS : 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], Cfg::EPI_WARPS); }
-    fence_barrier_init();
-  }
-  for (int i = threadIdx.x; i < 64 * Cfg::EPI_WARPS; i += blockDim.x) sm_stats[i] = 0.0;
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&p.tmapA[s]);
-    prefetch_tmap(&p.tmapB);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  griddep_launch_dependents();  // the next kernel may start its own prologue ...
-  griddep_wait();               // ... and this one touches global memory only after its predecessor has completed
-
-  if (warp == 0) {
-    // ================================ TMA producer =========================================
-    // The whole warp walks the loop (uniform control flow and addresses); one elected lane issues.
-    int ast = 0, bst = 0;
-    uint32_t aph = 0, bph = 0;
-    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const UnitCoord uc = decode_unit(p, u);
-      const int gcol0 = uc.gcol0 * BN;
-      GroupIter it;
-      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
-        const int s = it.s;
-        if constexpr (HALO) {
-          // activation ring only: the weight ring is fed by its own warp (below) so that A tiles can be
-          // prefetched NA deep instead of being serialised behind the nine weight-tile loads of a group
-          const int zz = uc.z0 + p.dz[it.t * p.gtaps];
-          if (zz < 0 || zz >= p.D) continue;
-          mbar_wait(&a_empty[ast], aph ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&a_full[ast], Cfg::A_TILE);
-            tma_load_5d_u(sA_u + ast * Cfg::A_STAGE, &p.tmapA[s], smem_u32(&a_full[ast]), it.c * kBlockK, uc.x0 - 1, uc.y0 - 1, zz, uc.n0);
-          }
-          __syncwarp();
-          if (++ast == NA) { ast = 0; aph ^= 1; }
-        } else {
-          const int tp = it.t;
-          const int zz = uc.z0 + p.dz[tp];
-          if (p.skip_z && (zz < 0 || zz >= p.D)) continue;
-          const int xx = uc.x0 * p.stride_w + p.dx[tp];
-          const int yy = uc.y0 * p.stride_h + p.dy[tp];
-          mbar_wait(&a_empty[ast], aph ^ 1);
-          mbar_wait(&b_empty[bst], bph ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&a_full[ast], Cfg::A_TILE);
-            tma_load_5d_u(sA_u + ast * Cfg::A_STAGE, &p.tmapA[s], smem_u32(&a_full[ast]), it.c * kBlockK, xx, yy, zz, uc.n0);
-            mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
-            tma_load_2d_u(sB_u + bst * Cfg::B_STAGE, &p.tmapB, smem_u32(&b_full[bst]), p.kbase[s] + tp * p.cin[s] + it.c * kBlockK, gcol0);
-          }
-          __syncwarp();
-          if (++ast == NA) { ast = 0; aph ^= 1; }
-          if (++bst == NB) { bst = 0; bph ^= 1; }
-        }
-      }
-    }
-  } else if (HALO && warp == Cfg::BP_WARP) {
-    // ================================ weight (B) producer, halo mode ========================
-    int bst = 0;
-    uint32_t bph = 0;
-    const uint32_t sB_u = smem_u32(sB);
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const UnitCoord uc = decode_unit(p, u);
-      const int gcol0 = uc.gcol0 * BN;
-      GroupIter it;
-      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
-        const int s = it.s;
-        const int zz = uc.z0 + p.dz[it.t * p.gtaps];
-        if (zz < 0 || zz >= p.D) continue;
-        const int kb = p.kbase[s] + it.t * p.gtaps * p.cin[s] + it.c * kBlockK;
-#pragma unroll 1
-        for (int ip = 0; ip < p.gtaps; ip += Cfg::TPB) {
-          mbar_wait(&b_empty[bst], bph ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
-#pragma unroll
-            for (int j = 0; j < Cfg::TPB; ++j)
-              tma_load_2d_u(sB_u + bst * Cfg::B_STAGE + j * Cfg::B_TILE, &p.tmapB, smem_u32(&b_full[bst]), kb + (ip + j) * p.cin[s], gcol0);
-          }
-          __syncwarp();
-          if (++bst == NB) { bst = 0; bph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ===========================================
-    // Uniform loop; descriptors are 64-bit constants whose low word (start address >> 4) is the only
-    // thing that moves, so the per-MMA work is one 32-bit uniform add.
-    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
-    const uint64_t adesc0 = umma_smem_desc(smem_u32(sA), HALO ? 18 * 128 : 1024, 2);
-    const uint64_t bdesc0 = umma_smem_desc(smem_u32(sB), 1024, 2);
-    const uint32_t adesc_hi = (uint32_t)(adesc0 >> 32), bdesc_hi = (uint32_t)(bdesc0 >> 32);
-    const uint32_t adesc_lo0 = (uint32_t)adesc0, bdesc_lo0 = (uint32_t)bdesc0;
-    int ast = 0, bst = 0, acc = 0;
-    uint32_t aph = 0, bph = 0, accph = 0;
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const UnitCoord uc = decode_unit(p, u);
-      mbar_wait(&t_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator stage
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
-      uint32_t accum = 0;
-      GroupIter it;
-      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
-        if constexpr (HALO) {
-          const int zz = uc.z0 + p.dz[it.t * p.gtaps];
-          if (zz < 0 || zz >= p.D) continue;
-        } else {
-          const int zz = uc.z0 + p.dz[it.t];
-          if (p.skip_z && (zz < 0 || zz >= p.D)) continue;
-        }
-        mbar_wait(XFORM ? &a_ready[ast] : &a_full[ast], aph);
-        const uint32_t a_lo = adesc_lo0 + (uint32_t)(ast * (Cfg::A_STAGE >> 4));
-        const int GT = HALO ? p.gtaps : 1;  // in-plane taps fed by one staged box (9, or 4 for the upsample-folded convs)
-#pragma unroll 1
-        for (int ip = 0; ip < GT; ip += Cfg::TPB) {
-          mbar_wait(&b_full[bst], bph);
-          tc_fence_after();
-          const uint32_t b_lo = bdesc_lo0 + (uint32_t)(bst * (Cfg::B_STAGE >> 4));
-          if (elect_one()) {
-#pragma unroll
-            for (int j = 0; j < Cfg::TPB; ++j) {
-              // tap (dy,dx) = row offset ((1+dy)*18 + (1+dx)) * 128 B into the staged halo box (8 = 128 B >> 4)
-              const int tap = ip + j;
-              const uint32_t a_tap = HALO ? a_lo + (uint32_t)(((1 + p.dy[tap]) * 18 + (1 + p.dx[tap])) * 8) : a_lo;
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                  const uint64_t ad = ((uint64_t)adesc_hi << 32) | (a_tap + (uint32_t)(mt * 64 + 2 * k));
-                  const uint64_t bd = ((uint64_t)bdesc_hi << 32) | (b_lo + (uint32_t)(j * (Cfg::B_TILE >> 4) + 2 * k));
-                  umma_bf16(d_tmem + mt * Cfg::BNC, ad, bd, idesc, (accum | (uint32_t)(j > 0)) | (uint32_t)(k > 0));
-                }
-              }
-            }
-            umma_commit(&b_empty[bst]);
-          }
-          __syncwarp();
-          accum = 1;
-          if (++bst == NB) { bst = 0; bph ^= 1; }
-        }
-        if (elect_one()) umma_commit(&a_empty[ast]);
-        __syncwarp();
-        if (++ast == NA) { ast = 0; aph ^= 1; }
-      }
-      if (elect_one()) umma_commit(&t_full[acc]);
-      __syncwarp();
-      if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
-    }
-  } else if (warp < 2 + Cfg::EPI_WARPS) {
-    // ================================ epilogue ==============================================
-    const int ew = warp - 2;
-    const int mt = ew >> 2;      // M half handled by this group of four warps
-    const int quad = warp & 3;   // TMEM lane quadrant this warp may read
-    const int r = quad * 32 + lane;
-    const int rpi_log = HALO ? 7 : (p.lbw + p.lbh + p.lbd);
-    const int seg = rpi_log >= 5 ? 32 : (1 << rpi_log);
-    int acc = 0;
-    uint32_t accph = 0;
-    // halo mode: GroupNorm sums of the current sample accumulate in shared memory and reach global memory
-    // only when this CTA moves on to another sample (one fp64 atomic per group instead of one per warp per unit)
-    constexpr bool SMEM_STATS = HALO;
-    int cur_n = -1;
-    const int epi_tid = threadIdx.x - 64;
-    auto flush_stats = [&]() {
-      if constexpr (SMEM_STATS) {
-        if (p.stats_cpg > 0) {
-          const int ng2 = 2 * (p.cout / p.stats_cpg);
-          asm volatile("bar.sync 3, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
-          if (cur_n >= 0 && epi_tid < ng2) {
-            double v = 0.0;
-#pragma unroll
-            for (int w = 0; w < Cfg::EPI_WARPS; ++w) { v += sm_stats[w * 64 + epi_tid]; sm_stats[w * 64 + epi_tid] = 0.0; }
-            if (v != 0.0) atomicAdd(p.stats + (long long)cur_n * ng2 + epi_tid, v);
-          }
-          asm volatile("bar.sync 3, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
-        }
-      }
-    };
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const UnitCoord uc = decode_unit(p, u);
-      if constexpr (SMEM_STATS) {
-        if (uc.n0 != cur_n) { flush_stats(); cur_n = uc.n0; }
-      }
-      int ox, oy, oz, on;
-      if constexpr (HALO) {
-        ox = uc.x0 + mt * 8 + (r & 7);
-        oy = uc.y0 + (r >> 3);
-        oz = uc.z0;
-        on = uc.n0;
-      } else {
-        const int mw = (1 << p.lbw) - 1, mh = (1 << p.lbh) - 1, md = (1 << p.lbd) - 1;
-        ox = uc.x0 + (r & mw);
-        oy = uc.y0 + ((r >> p.lbw) & mh);
-        oz = uc.z0 + ((r >> (p.lbw + p.lbh)) & md);
-        on = uc.n0 + (r >> (p.lbw + p.lbh + p.lbd));
-      }
-      EpiRow rw;
-      rw.valid = ox < p.OW && oy < p.OH && oz < p.D && on < p.N;
-      rw.on = on;
-      const int gcol0 = uc.gcol0 * BN;
-      int phase_idx = 0, co_base = gcol0;
-      if (p.nphase > 1) { phase_idx = gcol0 / p.cout; co_base = gcol0 - phase_idx * p.cout; }
-      rw.out_y = oy * p.out_sy + p.out_oy + ((p.nphase > 1) ? (phase_idx >> 1) : 0);
-      rw.out_x = ox * p.out_sx + p.out_ox + ((p.nphase > 1) ? (phase_idx & 1) : 0);
-      rw.img = (long long)on * p.D + oz;
-      rw.opix = (rw.img * p.out_H + rw.out_y) * p.out_W + rw.out_x;
-
-      mbar_wait(&t_full[acc], accph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + mt * Cfg::BNC);
-      auto load_tmem = [&](int col0, float (&f)[CW]) {
-        uint32_t v[32];
-        if constexpr (CW == 32) tmem_ld_32x32(taddr + col0, v); else tmem_ld_32x16(taddr + col0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
-      };
-      if (p.ksplit == 1) {
-        conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[acc]);
-      } else {
-        // ---- split-K: park the fp32 partial, the last split to arrive reduces in a fixed order ----
-        // partial tile layout [column quad][row][4 floats]: a warp's 16-byte accesses cover 512 contiguous bytes
-        float4* wq = reinterpret_cast<float4*>(p.ws + (((long long)uc.tile * p.ksplit + uc.ks) * MT + mt) * (128LL * BN)) + r;
-#pragma unroll 1
-        for (int col0 = 0; col0 < BN; col0 += CW) {
-          float f[CW];
-          load_tmem(col0, f);
-#pragma unroll
-          for (int q = 0; q < CW / 4; ++q)
-            __stcg(wq + (col0 / 4 + q) * 128, make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[acc]);
-        __threadfence();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
-        if ((threadIdx.x & 127) == 64) {  // first thread of this four-warp group (warps 2.. start at thread 64)
-          const int old = atomicAdd(p.counters + uc.tile * MT + mt, 1);
-          const int last = (old == p.ksplit - 1) ? 1 : 0;
-          if (last) p.counters[uc.tile * MT + mt] = 0;  // self-reset for the next launch
-          last_flag[mt] = last;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
-        if (last_flag[mt]) {
-          __threadfence();
-          const float4* wbase = reinterpret_cast<const float4*>(p.ws + (((long long)uc.tile * p.ksplit) * MT + mt) * (128LL * BN)) + r;
-          const long long ks_stride = (long long)MT * 32 * BN;  // float4 units between the partials of consecutive splits
-          auto load_ws = [&](int col0, float (&f)[CW]) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) f[j] = 0.f;
-            for (int ks = 0; ks < p.ksplit; ++ks) {
-              const float4* src = wbase + ks * ks_stride + (col0 / 4) * 128;
-#pragma unroll
-              for (int q = 0; q < CW / 4; ++q) {
-                const float4 v = __ldcg(src + q * 128);
-                f[4 * q] += v.x; f[4 * q + 1] += v.y; f[4 * q + 2] += v.z; f[4 * q + 3] += v.w;
-              }
-            }
-          };
-          conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws);
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // last_flag is reused by the next unit
-      }
-      if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
-    }
-    flush_stats();
-  } else if constexpr (XFORM) {
-    // ================================ A-tile transform =====================================
-    // Rewrite every staged 18x18x64 tile in place: raw (fp16 | bf16) -> bf16 silu(scale[c] * x + shift[c]).  Pixels
-    // outside the image stay zero (TMA zero fill == the conv's zero padding, applied AFTER the activation).
-    const int xt = threadIdx.x - (64 + 32 * Cfg::EPI_WARPS);  // 0..127
-    const int chunk_phys = xt & 7;                            // 16-byte chunk inside the 128-byte row
-    const int row0 = xt >> 3;                                 // 16 rows per pass
-    float* coef_a = sm_coef;
-    float* coef_b = sm_coef + Cfg::XF_MAXC;
-    const uint32_t coef_a_u = smem_u32(coef_a), coef_b_u = smem_u32(coef_b);
-    const int cin_pad = p.cin[0];
-    const int ngrp = p.in_creal / p.in_cpg;
-    const bool act_on = p.in_act != 0, in_f16 = p.in_f16 != 0;
-    int ast = 0, cur_n = -1;
-    uint32_t aph = 0;
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const UnitCoord uc = decode_unit(p, u);
-      if (uc.n0 != cur_n) {
-        // per-channel scale / shift of this sample from the producer's fp64 (sum, sumsq)
-        asm volatile("bar.sync 4, 128;" ::: "memory");  // everyone is done with the previous table
-        for (int c = xt; c < cin_pad; c += 128) {
-          float a = 0.f, b = 0.f;
-          if (c < p.in_creal) {
-            const int g = c / p.in_cpg;
-            const double* st = p.in_stats + ((long long)uc.n0 * ngrp + g) * 2;
-            const double mean = st[0] / p.in_count;
-            double var = st[1] / p.in_count - mean * mean;
-            if (var < 0) var = 0;
-            const float rstd = (float)(1.0 / sqrt(var + (double)p.in_eps));
-            const float ga = p.in_gamma ? __ldg(p.in_gamma + c) : 1.f, be = p.in_beta ? __ldg(p.in_beta + c) : 0.f;
-            a = rstd * ga;
-            b = be - (float)mean * rstd * ga;
-          }
-          coef_a[c] = act_on ? 0.5f * a : a;
-          coef_b[c] = act_on ? 0.5f * b : b;
-        }
-        asm volatile("bar.sync 4, 128;" ::: "memory");
-        cur_n = uc.n0;
-      }
-      GroupIter it;
-      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
-        const int zz = uc.z0 + p.dz[it.t * p.gtaps];
-        if (zz < 0 || zz >= p.D) continue;
-        mbar_wait(&a_full[ast], aph);
-        const uint32_t tile_u = smem_u32(sA + ast * Cfg::A_STAGE);
-        const int cbase = it.c * kBlockK;
-        // silu(y) = h + h * tanh(h) with h = y / 2; the 1/2 is folded into the coefficients (one MUFU per element).
-        // Branch-free body, four independent 16-byte vectors in flight per thread (this warp is alone on its scheduler).
-        const bool border = uc.x0 == 0 || uc.y0 == 0 || uc.x0 + 16 >= p.OW || uc.y0 + 16 >= p.OH;
-        int yi = (row0 * 3641) >> 16;  // row0 / 18
-        int xi = row0 - yi * 18;
-#pragma unroll 1
-        for (int r = row0; r < 18 * 18; r += 64) {
-          uint4 raw[4];
-          uint32_t vaddr[4];
-          int c0[4];
-          bool live[4];
-          int yj = yi, xj = xi;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int rr = r + 16 * q;
-            const uint32_t row_u = tile_u + (uint32_t)rr * 128u;
-            vaddr[q] = row_u + (uint32_t)(chunk_phys * 16);
-            c0[q] = cbase + ((chunk_phys ^ (int)((row_u >> 7) & 7u)) << 3);  // undo the 128B swizzle: which 8 channels
-            live[q] = rr < 18 * 18;
-            if (border) {
-              const int gx = uc.x0 - 1 + xj, gy = uc.y0 - 1 + yj;
-              live[q] = live[q] && gx >= 0 && gx < p.OW && gy >= 0 && gy < p.OH;  // outside the image: stays zero (padding)
-            }
-            xj += 16;
-            if (xj >= 18) { xj -= 18; ++yj; }
-            raw[q] = live[q] ? lds128(vaddr[q]) : make_uint4(0u, 0u, 0u, 0u);
-          }
-          yi = yj; xi = xj;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float f[8];
-            if (in_f16) {
-              const float2 q0 = unpack_f16(raw[q].x), q1 = unpack_f16(raw[q].y), q2 = unpack_f16(raw[q].z), q3 = unpack_f16(raw[q].w);
-              f[0] = q0.x; f[1] = q0.y; f[2] = q1.x; f[3] = q1.y; f[4] = q2.x; f[5] = q2.y; f[6] = q3.x; f[7] = q3.y;
-            } else {
-              f[0] = bf16_lo(raw[q].x); f[1] = bf16_hi(raw[q].x); f[2] = bf16_lo(raw[q].y); f[3] = bf16_hi(raw[q].y);
-              f[4] = bf16_lo(raw[q].z); f[5] = bf16_hi(raw[q].z); f[6] = bf16_lo(raw[q].w); f[7] = bf16_hi(raw[q].w);
-            }
-            const float4 a0 = lds128f(coef_a_u + c0[q] * 4), a1 = lds128f(coef_a_u + c0[q] * 4 + 16);
-            const float4 b0 = lds128f(coef_b_u + c0[q] * 4), b1 = lds128f(coef_b_u + c0[q] * 4 + 16);
-            f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
-            f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
-            if (act_on) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float t;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(f[j]));
-                f[j] = fmaf(f[j], t, f[j]);
-              }
-            }
-            if (live[q]) sts128(vaddr[q], make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
-          }
-        }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[ast]);
-        if (++ast == NA) { ast = 0; aph ^= 1; }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
+  conv_v2_layer<BN, HALO, XFORM, false>(p, p, smem, 0u);
 }
 
 template <int BN, bool HALO, bool XFORM = false>
