@@ -73,6 +73,18 @@ _SIGNATURES = {
     "b2d_edt2d": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_bilinear_resize": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_zero": (c_int, [c_void_p, c_i64, c_void_p]),
+    "b2d_chain_create": (c_int, [C.POINTER(c_void_p)]),
+    "b2d_chain_destroy": (c_int, [c_void_p]),
+    "b2d_chain_op_bytes": (c_i64, []),
+    "b2d_chain_num_ops": (c_i32, [c_void_p]),
+    "b2d_chain_add_conv": (c_int, [c_void_p, c_void_p]),
+    "b2d_chain_add_gn": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_i32, c_void_p, c_i32, c_void_p, c_void_p, c_float, c_i32,
+                                 c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32]),
+    "b2d_chain_add_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
+    "b2d_chain_add_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32]),
+    "b2d_chain_add_zero": (c_int, [c_void_p, c_void_p, c_i64]),
+    "b2d_chain_bind": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "b2d_chain_run": (c_int, [c_void_p, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())
@@ -98,8 +110,8 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b2d_version() != 3:
-            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != 3; rebuild")
+        if l.b2d_version() != 4:
+            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != 4; rebuild")
         _lib = l
     return _lib
 

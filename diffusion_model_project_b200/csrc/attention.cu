@@ -201,11 +201,21 @@ typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int launch_attention_tc(const void* qkv, void* out, int N, int T, int C, int heads, cudaStream_t st) {
+size_t attention_tc_smem(int T, int C, int heads) {
+  const int dch = (C / heads) / 64;
+  return (size_t)dch * kQChunkBytes + 2 * (size_t)dch * T * 128 + 64 + 1024;
+}
+
+int attention_tc_params(const void* qkv, void* out, int N, int T, int C, int heads, AttnTcParams* pp) {
+  const int d = C / heads;
+  const int dch = d / 64;
+  const size_t p_bytes = (size_t)((T + 63) / 64) * kQChunkBytes;
+  if ((d % 64) || d > 512 || T % 16 || T < 16 || T > 256 || (T > 128 && T % 128) || attention_tc_smem(T, C, heads) > 220 * 1024 ||
+      p_bytes > (size_t)dch * kQChunkBytes + (size_t)dch * T * 128 || ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15))
+    return set_error(B2D_E_UNSUPPORTED, "attention: T=%d d_head=%d not eligible for the tensor-core kernel", T, d);
   PFN_encodeTiledA enc = reinterpret_cast<PFN_encodeTiledA>(tensor_map_encode_fn());
   if (!enc) return set_error(B2D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available (no CUDA driver / too old)");
-  AttnTcParams p;
-  const int d = C / heads;
+  AttnTcParams& p = *pp;
   const int RB = T < 128 ? T : 128;
   cuuint64_t dims[3] = {(cuuint64_t)(3 * C), (cuuint64_t)T, (cuuint64_t)N};
   cuuint64_t strides[2] = {(cuuint64_t)(3 * C) * 2, (cuuint64_t)(3 * C) * 2 * (cuuint64_t)T};
@@ -218,8 +228,14 @@ static int launch_attention_tc(const void* qkv, void* out, int N, int T, int C, 
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.T = T; p.C = C; p.heads = heads; p.d = d; p.RB = RB;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)d);
-  const int dch = d / 64;
-  const size_t smem = (size_t)dch * kQChunkBytes + 2 * (size_t)dch * T * 128 + 64 + 1024;
+  return B2D_OK;
+}
+
+static int launch_attention_tc(const void* qkv, void* out, int N, int T, int C, int heads, cudaStream_t st) {
+  AttnTcParams p;
+  const int rc = attention_tc_params(qkv, out, N, T, C, heads, &p);
+  if (rc != B2D_OK) return rc;
+  const size_t smem = attention_tc_smem(T, C, heads);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

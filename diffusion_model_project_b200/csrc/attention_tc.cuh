@@ -211,4 +211,9 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, const A
 }
 
 
+// host: fill `p` (TMA descriptor over qkv [N][T][3C], shapes, scale) after checking that the tensor-core path applies
+int attention_tc_params(const void* qkv, void* out, int N, int T, int C, int heads, AttnTcParams* p);
+// dynamic shared memory one item needs
+size_t attention_tc_smem(int T, int C, int heads);
+
 }  // namespace b2d

@@ -331,14 +331,17 @@ def upsample2x(x: Act, y: Act, stream: int):
 
 
 class Program:
-    """A recorded sequence of kernel launches over static buffers (replayable, graph-capturable)."""
+    """A recorded sequence of kernel launches over static buffers (replayable, graph-capturable).  Each step may also
+    carry a structured description (`op`) from which the same sequence can be compiled into a Chain."""
 
     def __init__(self):
         self.steps: List[Tuple[str, Callable[[int], None]]] = []
+        self.ops: List[Optional[tuple]] = []
         self.flops = 0.0
 
-    def add(self, name: str, fn: Callable[[int], None]):
+    def add(self, name: str, fn: Callable[[int], None], op: Optional[tuple] = None):
         self.steps.append((name, fn))
+        self.ops.append(op)
 
     def run(self, stream: int):
         for _, fn in self.steps:
@@ -346,3 +349,62 @@ class Program:
 
     def __len__(self):
         return len(self.steps)
+
+
+class Chain:
+    """A Program compiled into ONE cooperative persistent kernel (csrc/conv_chain.cu): the same layers, a grid barrier
+    in place of every kernel boundary.  Needs every step of the program to carry an `op` description (bf16 mode)."""
+
+    def __init__(self, prog: Program, device, max_ops: Optional[int] = None, first_op: int = 0):
+        lib = _lib.lib()
+        self.handle = C.c_void_p()
+        _lib.check(lib.b2d_chain_create(C.byref(self.handle)), "b2d_chain_create")
+        self._keep = []
+        for (name, _), op in list(zip(prog.steps, prog.ops))[first_op:max_ops]:
+            if op is None:
+                raise ValueError(f"program step {name!r} has no chain description")
+            kind = op[0]
+            if kind == "conv":
+                _lib.check(lib.b2d_chain_add_conv(self.handle, op[1].handle), f"chain add {name}")
+            elif kind == "gn":
+                (x, y, stats, cpg, gamma, beta, act, temb, temb_row, temb_row_stride, temb_col, stats_out, eps) = op[1:]
+                N, D, H, W, Cc = x.shape
+                _lib.check(lib.b2d_chain_add_gn(self.handle, ptr(x.hi), ptr(y.hi), N, D * H * W, Cc, ptr(stats), cpg, ptr(gamma), ptr(beta),
+                                                eps, 1 if act else 0, ptr(temb), ptr(temb_row), temb_row_stride,
+                                                0 if temb is None else temb.shape[1], temb_col, ptr(stats_out), 1 if x.f16 else 0),
+                           f"chain add {name}")
+            elif kind == "pool":
+                x, y, stats = op[1:]
+                N, D, H, W, Cc = x.shape
+                _lib.check(lib.b2d_chain_add_pool(self.handle, ptr(x.hi), ptr(y.hi), N, H, W, Cc, ptr(stats)), f"chain add {name}")
+            elif kind == "attn":
+                qkv, out, N, T, Cc, heads = op[1:]
+                _lib.check(lib.b2d_chain_add_attention(self.handle, ptr(qkv.hi), ptr(out.hi), N, T, Cc, heads), f"chain add {name}")
+            elif kind == "zero":
+                buf, nbytes = op[1:]
+                _lib.check(lib.b2d_chain_add_zero(self.handle, buf.data_ptr(), (nbytes + 15) // 16 * 16), f"chain add {name}")
+            else:
+                raise ValueError(f"unknown chain op {kind!r}")
+            self._keep.append(op)
+        self.num_ops = lib.b2d_chain_num_ops(self.handle)
+        nbytes = self.num_ops * lib.b2d_chain_op_bytes()
+        self._buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        off = (-self._buf.data_ptr()) % 128
+        self._bar = torch.zeros(2 + 2 * (self.num_ops + 1), dtype=torch.int32, device=device)
+        _lib.check(lib.b2d_chain_bind(self.handle, self._buf.data_ptr() + off, nbytes, self._bar.data_ptr(), _lib.stream_ptr()), "b2d_chain_bind")
+
+    def run(self, stream: int):
+        call("b2d_chain_run", self.handle, stream)
+
+    def op_times_us(self) -> List[float]:
+        """Device time of every op of the last run (op + the grid barrier after it), from the kernel's %globaltimer stamps."""
+        t = self._bar[2:].view(torch.int64).cpu().tolist()
+        return [(t[i + 1] - t[i]) / 1e3 for i in range(self.num_ops)]
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().b2d_chain_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass

@@ -65,6 +65,8 @@ class B200LatentDiffusionPredictor:
         import os
         self.unet_chains = int(os.environ.get("B2D_UNET_CHAINS", "1")) if unet_chains is None else int(unet_chains)
         self._side_streams: List[torch.cuda.Stream] = []
+        # B2D_UNET_CHAIN=1: the whole UNet step as ONE cooperative persistent kernel (engine.Chain), bf16 mode
+        self.unet_chain = os.environ.get("B2D_UNET_CHAIN", "0") == "1" and precision == "bf16"
         self.model = B200UNet(**model_kwargs, precision=precision, num_timesteps=num_timesteps, device=device)
         self.model.load_state_dict(unet_state)
         self.scheduler = B200Scheduler(num_timesteps=num_timesteps, device=device)
@@ -124,6 +126,7 @@ class B200LatentDiffusionPredictor:
         temb_steps = self.model.temb_table.index_select(0, idx).contiguous()
         ses["unet"] = None  # release the previous program's buffers first
         ses["unet_parts"] = None
+        ses["unet_chain"] = None
         N = ses["N"]
         chains = self.unet_chains if (self.unet_chains > 1 and N % self.unet_chains == 0 and N // self.unet_chains >= 8) else 1
         if chains == 1:
@@ -141,6 +144,7 @@ class B200LatentDiffusionPredictor:
             ses["unet"] = parts[0]
             while len(self._side_streams) < chains - 1:
                 self._side_streams.append(torch.cuda.Stream(device=self.device))
+        ses["unet_chain"] = engine.Chain(ses["unet"]["program"], self.device) if (self.unet_chain and chains == 1) else None
         ses["temb_steps"] = temb_steps
         ses["temb_key"] = key
         ses["graph"] = None
@@ -175,6 +179,9 @@ class B200LatentDiffusionPredictor:
         _lib.call("b2d_planar_to_cl", ses["x"].data_ptr(), _lib.ptr(ui.hi), _lib.ptr(ui.lo), N * h * w, lat, 1, ui.C, 0, None, s)
 
     def _run_unet(self, ses, s):
+        if ses.get("unet_chain") is not None:
+            ses["unet_chain"].run(s)
+            return
         parts = ses.get("unet_parts")
         if not parts:
             ses["unet"]["program"].run(s)
@@ -239,6 +246,8 @@ class B200LatentDiffusionPredictor:
         for _ in range(n_steps):
             g.replay()
         n_unet = sum(len(p_["program"]) for p_ in ses["unet_parts"]) if ses.get("unet_parts") else len(ses["unet"]["program"])
+        if ses.get("unet_chain") is not None:
+            n_unet = 1  # the whole step is one cooperative launch
         _lib.launch_count += n_steps * (n_unet + 1)
 
     def _decode(self, ses, s):

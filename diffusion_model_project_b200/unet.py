@@ -181,11 +181,14 @@ class B200UNet:
             st = stats_view(stats_alloc(1), N * 2)
             plan = ConvPlan(inputs, pw, raw, cout=cout, nphase=nphase, stats=st, stats_cpg=cout)
             prog.flops += plan.flops
-            prog.add(f"{name}.conv", plan.run)
+            prog.add(f"{name}.conv", plan.run, op=("conv", plan))
             g, b = gnw
+            tt = temb_table if temb_col is not None else None
+            tr = temb_row if temb_col is not None else None
             prog.add(f"{name}.gn", lambda s, raw=raw, out=out, st=st, g=g, b=b, tc=temb_col, so=stats_out, cout=cout: engine.gn_apply(
                 raw, out, st, cout, g, b, True, s, temb=temb_table if tc is not None else None,
-                temb_row=temb_row if tc is not None else None, temb_row_stride=temb_row_stride, temb_col=tc or 0, stats_out=so))
+                temb_row=temb_row if tc is not None else None, temb_row_stride=temb_row_stride, temb_col=tc or 0, stats_out=so),
+                op=("gn", raw, out, st, cout, g, b, True, tt, tr, temb_row_stride, temb_col or 0, stats_out, 1e-5))
             keep.append(plan)
             return out
 
@@ -199,15 +202,16 @@ class B200UNet:
             T = H * Wd
             g, b = W_[f"{prefix}.norm"]
             xn = new_act(N, 1, H, Wd, c, dev, sp)
-            prog.add(f"{prefix}.gn", lambda s: engine.gn_apply(x, xn, st_in, c, g, b, False, s))
+            prog.add(f"{prefix}.gn", lambda s: engine.gn_apply(x, xn, st_in, c, g, b, False, s),
+                     op=("gn", x, xn, st_in, c, g, b, False, None, None, 0, 0, None, 1e-5))
             qkv = new_act(N, 1, H, Wd, 3 * c, dev, sp)
             p1 = ConvPlan([xn], W_[f"{prefix}.in_proj"], qkv, cout=3 * c)
-            prog.add(f"{prefix}.in_proj", p1.run)
+            prog.add(f"{prefix}.in_proj", p1.run, op=("conv", p1))
             ao = new_act(N, 1, H, Wd, c, dev, sp)
             prog.add(f"{prefix}.core", lambda s: _lib.call("b2d_attention", _lib.ptr(qkv.hi), _lib.ptr(qkv.lo), _lib.ptr(ao.hi),
-                                                            _lib.ptr(ao.lo), N, T, c, heads, s))
+                                                            _lib.ptr(ao.lo), N, T, c, heads, s), op=("attn", qkv, ao, N, T, c, heads))
             p2 = ConvPlan([ao], W_[f"{prefix}.out"], x, cout=c, residual=x)
-            prog.add(f"{prefix}.out_proj", p2.run)
+            prog.add(f"{prefix}.out_proj", p2.run, op=("conv", p2))
             prog.flops += p1.flops + p2.flops + 4.0 * N * T * T * c
             keep.extend([p1, p2, xn, qkv, ao])
             return x
@@ -225,8 +229,10 @@ class B200UNet:
             pooled = new_act(N, 1, H // 2, Wd // 2, c, dev, sp)
             st = stats_view(stats_alloc(1), N * 2)
             g, b = W_[f"encoder.{lvl}.2.norm"]
-            prog.add(f"encoder.{lvl}.2.pool", lambda s, x=x, pooled=pooled, st=st: engine.maxpool_stats(x, pooled, st, s))
-            prog.add(f"encoder.{lvl}.2.gn", lambda s, pooled=pooled, st=st, g=g, b=b, c=c: engine.gn_apply(pooled, pooled, st, c, g, b, True, s))
+            prog.add(f"encoder.{lvl}.2.pool", lambda s, x=x, pooled=pooled, st=st: engine.maxpool_stats(x, pooled, st, s),
+                     op=("pool", x, pooled, st))
+            prog.add(f"encoder.{lvl}.2.gn", lambda s, pooled=pooled, st=st, g=g, b=b, c=c: engine.gn_apply(pooled, pooled, st, c, g, b, True, s),
+                     op=("gn", pooled, pooled, st, c, g, b, True, None, None, 0, 0, None, 1e-5))
             x = pooled
             H, Wd = H // 2, Wd // 2
         x = double("bottleneck", [x], 2 * f[-1], 2 * f[-1], H, Wd)
@@ -242,12 +248,13 @@ class B200UNet:
         pf = ConvPlan([x], W_["final_conv"], eps_out, cout=self.out_channels, out_mode=eps_mode,
                       out_cstride=self.out_channels)
         prog.flops += pf.flops
-        prog.add("final_conv", pf.run)
+        prog.add("final_conv", pf.run, op=("conv", pf))
         keep.append(pf)
         assert stats_total[0] <= stats_buf.numel()
         used = stats_total[0]
         steps = prog.steps
         prog.steps = [("stats.zero", lambda s: _lib.call("b2d_zero", stats_buf.data_ptr(), used * 8, s))] + steps
+        prog.ops = [("zero", stats_buf, used * 8)] + prog.ops
         return dict(program=prog, x_in=x_in, eps=eps_out, temb_row=temb_row, keep=keep, stats=stats_buf, skips=skips,
                     temb_table=temb_table)
 

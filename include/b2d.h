@@ -33,7 +33,7 @@ extern "C" {
 #define B2D_API
 #endif
 
-#define B2D_VERSION 3
+#define B2D_VERSION 4
 #define B2D_MAX_SEG 6
 #define B2D_MAX_TAPS 27
 
@@ -189,6 +189,32 @@ B2D_API int b2d_bilinear_resize(const float* x, float* y, int32_t n_img, int32_t
 
 /* fill helpers used by the fused loop (graph-capturable) */
 B2D_API int b2d_zero(void* p, int64_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Chain: a run of dependent layers executed inside ONE cooperative persistent kernel, with a grid
+ * barrier in place of every kernel boundary (csrc/conv_chain.cu).  Ops are appended in execution
+ * order from already-created conv plans (persistent engine) and from the same arguments the
+ * stand-alone entry points take; bf16 mode only.  b2d_chain_bind copies the op list into a
+ * caller-owned device buffer (num_ops * b2d_chain_op_bytes(), 128-byte aligned) and takes a
+ * zero-initialised int32 buffer of 2 + 2 * (num_ops + 1) words: two barrier counters, then one 64-bit
+ * %globaltimer stamp per op boundary (diagnostics); b2d_chain_run launches it (graph-capturable).
+ * ---------------------------------------------------------------------------------------- */
+enum b2d_chain_op_kind { B2D_CHAIN_CONV = 1, B2D_CHAIN_GN = 2, B2D_CHAIN_POOL = 3, B2D_CHAIN_ATTN = 4, B2D_CHAIN_ZERO = 5 };
+typedef struct b2d_chain b2d_chain;
+B2D_API int b2d_chain_create(b2d_chain** chain);
+B2D_API int b2d_chain_destroy(b2d_chain* chain);
+B2D_API int64_t b2d_chain_op_bytes(void);
+B2D_API int32_t b2d_chain_num_ops(const b2d_chain* chain);
+B2D_API int b2d_chain_add_conv(b2d_chain* chain, const b2d_conv_plan* plan);
+B2D_API int b2d_chain_add_gn(b2d_chain* chain, const void* x, void* y, int32_t N, int64_t P, int32_t C, const double* stats,
+                     int32_t cpg, const float* gamma, const float* beta, float eps, int32_t act, const float* temb_table,
+                     const int32_t* temb_row, int32_t temb_row_stride, int32_t temb_ld, int32_t temb_col, double* stats_out,
+                     int32_t in_f16);
+B2D_API int b2d_chain_add_pool(b2d_chain* chain, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, double* stats);
+B2D_API int b2d_chain_add_attention(b2d_chain* chain, const void* qkv, void* out, int32_t N, int32_t T, int32_t C, int32_t heads);
+B2D_API int b2d_chain_add_zero(b2d_chain* chain, void* p, int64_t bytes);
+B2D_API int b2d_chain_bind(b2d_chain* chain, void* dev_ops, int64_t dev_bytes, int32_t* barrier2, void* stream);
+B2D_API int b2d_chain_run(const b2d_chain* chain, void* stream);
 
 #ifdef __cplusplus
 }
