@@ -72,6 +72,7 @@ struct ConvKParams {
   int goff[B2D_MAX_SEG + 1];  // first group of each segment
   int tiles_ncol;    // N tiles
   int num_units;     // tiles_m * tiles_ncol * ksplit
+  int contig;        // 1: a CTA walks a contiguous range of units (few sample changes -> few GroupNorm flushes)
   float* ws;         // [tile][ksplit][128][BLOCK_N] fp32 partial accumulators
   int* counters;     // [tile] arrival counters (self-resetting)
   FastDiv fd_ksplit, fd_ncol, fd_w, fd_h, fd_d;  // unit index -> (split, N tile, x, y, z, n tile)
@@ -146,7 +147,7 @@ __device__ __forceinline__ void warp_transpose_sum(float (&vals)[V], int lane) {
 // belong to `32 / seg` different samples).
 template <int BLOCK_N, int CW, bool SMEM_STATS, class Loader>
 __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const EpiRow& rw, int co_base, int lane, int seg,
-                                                  double* sm_stats, Loader&& load) {
+                                                  double* sm_stats, Loader&& load, double* thr_acc = nullptr) {
   const int cpg = p.stats_cpg;
   const int groups_per_n = (cpg > 0) ? (p.cout / cpg) : 0;
   float run_s = 0.f, run_ss = 0.f;
@@ -346,7 +347,14 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const Ep
       }
     }
   }
-  if (cpg >= CW && run_g >= 0) flush(run_s, run_ss, run_g);
+  if (cpg >= CW && run_g >= 0) {
+    if (thr_acc != nullptr) {  // one group per sample: the caller reduces across lanes when the sample changes
+      thr_acc[0] += (double)run_s;
+      thr_acc[1] += (double)run_ss;
+    } else {
+      flush(run_s, run_ss, run_g);
+    }
+  }
 }
 
 }  // namespace b2d

@@ -463,6 +463,11 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
       pl->ws_bytes = kCounterBytes + tiles * ksplit * mt * 128LL * bn * 4;
     }
     pl->grid = dim3((unsigned)(k.num_units < sms ? k.num_units : sms), 1, 1);
+    // a strided walk changes sample at every unit when a sample has fewer units than the grid has CTAs (UNet levels):
+    // every change costs a GroupNorm flush (two epilogue barriers + global atomics); walk contiguous ranges instead
+    static const int env_contig = [] { const char* e = getenv("B2D_CONV_CONTIG"); return e ? atoi(e) : -1; }();
+    const long long units_per_n = k.tiles_n > 0 ? k.num_units / k.tiles_n : k.num_units;
+    k.contig = env_contig >= 0 ? env_contig : (units_per_n < (long long)pl->grid.x && k.num_units > (int)pl->grid.x) ? 1 : 0;
   }
   *out_plan = pl;
   return B2D_OK;

@@ -58,6 +58,20 @@ __device__ __forceinline__ UnitCoord decode_unit(const ConvKParams& p, int u) {
   return c;
 }
 
+// the units one CTA executes: strided over the grid, or (contig) one contiguous range
+struct UnitWalk { int u, end, step; };
+__device__ __forceinline__ UnitWalk unit_walk(const ConvKParams& p) {
+  UnitWalk w;
+  if (p.contig) {
+    w.u = (int)((long long)blockIdx.x * p.num_units / gridDim.x);
+    w.end = (int)((long long)(blockIdx.x + 1) * p.num_units / gridDim.x);
+    w.step = 1;
+  } else {
+    w.u = blockIdx.x; w.end = p.num_units; w.step = gridDim.x;
+  }
+  return w;
+}
+
 // iterate the A-groups [g_lo, g_hi) of one unit as (segment, tap-or-ztap, chunk)
 struct GroupIter {
   int s, t, c, g, g_hi;
@@ -112,6 +126,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
   // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const UnitWalk uw = unit_walk(p);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], XFORM ? Cfg::XF_WARPS : 1); }
@@ -145,7 +160,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
     int ast = 0, bst = 0;
     uint32_t aph = 0, bph = 0;
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+    for (int u = uw.u; u < uw.end; u += uw.step) {
       const UnitCoord uc = decode_unit(p, u);
       const int gcol0 = uc.gcol0 * BN;
       GroupIter it;
@@ -188,7 +203,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
     int bst = 0;
     uint32_t bph = 0;
     const uint32_t sB_u = smem_u32(sB);
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+    for (int u = uw.u; u < uw.end; u += uw.step) {
       const UnitCoord uc = decode_unit(p, u);
       const int gcol0 = uc.gcol0 * BN;
       GroupIter it;
@@ -222,7 +237,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
     const uint32_t adesc_lo0 = (uint32_t)adesc0, bdesc_lo0 = (uint32_t)bdesc0;
     int ast = 0, bst = 0, acc = 0;
     uint32_t aph = 0, bph = 0, accph = 0;
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+    for (int u = uw.u; u < uw.end; u += uw.step) {
       const UnitCoord uc = decode_unit(p, u);
       mbar_wait(&t_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator stage
       tc_fence_after();
@@ -290,10 +305,23 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
     constexpr bool SMEM_STATS = HALO;
     int cur_n = -1;
     const int epi_tid = threadIdx.x - 64;
+    // one group per sample (the UNet's GroupNorm(1, C)): per-thread fp64 sums live in registers across the units of a
+    // sample and meet the other lanes only when the sample changes
+    const bool one_group = SMEM_STATS && p.stats_cpg >= p.cout && p.stats_cpg > 0;
+    double thr_acc[2] = {0.0, 0.0};
     auto flush_stats = [&]() {
       if constexpr (SMEM_STATS) {
         if (p.stats_cpg > 0) {
           const int ng2 = 2 * (p.cout / p.stats_cpg);
+          if (one_group) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+              thr_acc[0] += __shfl_xor_sync(0xffffffffu, thr_acc[0], off);
+              thr_acc[1] += __shfl_xor_sync(0xffffffffu, thr_acc[1], off);
+            }
+            if (lane < 2) sm_stats[ew * 64 + lane] += lane == 0 ? thr_acc[0] : thr_acc[1];
+            thr_acc[0] = 0.0; thr_acc[1] = 0.0;
+          }
           asm volatile("bar.sync 3, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
           if (cur_n >= 0 && epi_tid < ng2) {
             double v = 0.0;
@@ -305,7 +333,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         }
       }
     };
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+    for (int u = uw.u; u < uw.end; u += uw.step) {
       const UnitCoord uc = decode_unit(p, u);
       if constexpr (SMEM_STATS) {
         if (uc.n0 != cur_n) { flush_stats(); cur_n = uc.n0; }
@@ -345,7 +373,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
       };
       if (p.ksplit == 1) {
-        conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem);
+        conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, one_group ? thr_acc : nullptr);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
@@ -389,7 +417,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
               }
             }
           };
-          conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws);
+          conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, one_group ? thr_acc : nullptr);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // last_flag is reused by the next unit
       }
@@ -411,7 +439,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
     const bool act_on = p.in_act != 0, in_f16 = p.in_f16 != 0;
     int ast = 0, cur_n = -1;
     uint32_t aph = 0;
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+    for (int u = uw.u; u < uw.end; u += uw.step) {
       const UnitCoord uc = decode_unit(p, u);
       if (uc.n0 != cur_n) {
         // per-channel scale / shift of this sample from the producer's fp64 (sum, sumsq)
