@@ -73,6 +73,8 @@ _SIGNATURES = {
     "b2d_edt2d": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_bilinear_resize": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_zero": (c_int, [c_void_p, c_i64, c_void_p]),
+    "b2d_zfold_combine": (c_int, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
+                          c_void_p]),
     "b2d_chain_create": (c_int, [C.POINTER(c_void_p)]),
     "b2d_chain_destroy": (c_int, [c_void_p]),
     "b2d_chain_op_bytes": (c_i64, []),
@@ -110,8 +112,8 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b2d_version() != 4:
-            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != 4; rebuild")
+        if l.b2d_version() != 5:
+            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != 5; rebuild")
         _lib = l
     return _lib
 

@@ -284,6 +284,37 @@ __global__ void __launch_bounds__(256) cl_to_planar_kernel(const __nv_bfloat16* 
   }
 }
 
+// z-folded small-Cout Conv3d (vae/decoder.py:71): the 3x3x3 conv runs as a 3x3 conv per z slice whose output rows are
+// (kz, co) -- P[n][zi][y][x][kz*4 + co] = sum_{ky,kx,c} w[co][c][kz][ky][kx] * x[n][zi][y+ky-1][x+kx-1][c] -- and this
+// pass gathers the three z contributions: out[n][z][co] = bias[co] + sum_kz P[n][z+kz-1][..][kz*4+co] (zero padding in
+// z), times the per-channel scale and the mask, written planar fp32 [N*D][cstride][H][W] at channel offset coff.
+__global__ void zfold_combine_kernel(const float4* __restrict__ P, int D, long long plane, long long total, int co,
+                                     const float* __restrict__ bias, const float* __restrict__ scale,
+                                     const float* __restrict__ mask, float* __restrict__ out, int out_cstride, int out_coff) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / plane;
+    const long long pix = i - img * plane;
+    const int z = (int)(img % D);
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz) {
+      const int zi = z + kz - 1;
+      if (zi < 0 || zi >= D) continue;
+      const float4 v = __ldcs(P + ((img + (kz - 1)) * plane + pix) * 3 + kz);
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z;
+    }
+    const float m = mask != nullptr ? __ldg(mask + i) : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c < co) {
+        const float b = bias != nullptr ? __ldg(bias + c) : 0.f;
+        const float sc = scale != nullptr ? __ldg(scale + c) : 1.f;
+        __stcs(out + (img * out_cstride + out_coff + c) * plane + pix, (acc[c] + b) * sc * m);
+      }
+    }
+  }
+}
+
 static inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
   long long b = (work_items + per_block - 1) / per_block;
   const long long cap = (long long)num_sms() * max_waves;
@@ -339,6 +370,18 @@ extern "C" int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, vo
   launch_pdl(maxpool_stats_kernel, dim3(bx, N), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)x_lo, (uint4*)y,
                                                                        (uint4*)y_lo, H, W, C, stats);
   return check_launch("maxpool_stats_kernel");
+}
+
+extern "C" int b2d_zfold_combine(const float* P, int32_t ND, int32_t D, int32_t H, int32_t W, int32_t co, const float* bias,
+                                 const float* scale, const float* mask, float* out, int32_t out_cstride, int32_t out_coff,
+                                 void* stream) {
+  if (!P || !out || ND < 1 || D < 1 || (ND % D) || H < 1 || W < 1 || co < 1 || co > 3 || out_coff < 0 || out_coff + co > out_cstride ||
+      (reinterpret_cast<uintptr_t>(P) & 15))
+    return set_error(B2D_E_INVALID, "b2d_zfold_combine: bad argument");
+  const long long plane = (long long)H * W, total = (long long)ND * plane;
+  zfold_combine_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)P, D, plane, total, co, bias, scale,
+                                                                               mask, out, out_cstride, out_coff);
+  return check_launch("zfold_combine_kernel");
 }
 
 extern "C" int b2d_upsample2x_nearest(const void* x, void* y, int32_t ND, int32_t H, int32_t W, int32_t C, void* stream) {

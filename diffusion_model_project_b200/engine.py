@@ -136,6 +136,19 @@ def pack_conv3d(w, bias, device, split=False, down=False):
     return pack_weight(w.permute(0, 2, 3, 4, 1).reshape(co, 27, ci), [ci], taps_3x3x3(0 if down else 1), bias, device, split)
 
 
+def pack_conv3d_zfold(w, device):
+    """Conv3d 3x3x3 with Cout <= 3 (decoder.py:71) as a per-slice 3x3 conv with rows (kz, co): row kz*4 + co holds
+    w[co, :, kz] -- 9 taps and one N = 16 tile instead of 27 taps (an N = 16 MMA costs as much as an N = 64 one, so the
+    tap count is what matters); b2d_zfold_combine sums the three z contributions and adds the bias."""
+    co, ci = w.shape[:2]
+    assert co <= 3 and tuple(w.shape[2:]) == (3, 3, 3)
+    rows = torch.zeros(12, 9, ci, dtype=torch.float32)
+    for kz in range(3):
+        rows[kz * 4:kz * 4 + co] = w[:, :, kz].float().permute(0, 2, 3, 1).reshape(co, 9, ci)
+    taps = [(0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    return pack_weight(rows, [ci], taps, None, device)
+
+
 def pack_conv3d_upsampled(w, bias, device, py: int, px: int, split=False):
     """Conv3d 3x3x3 applied to a nearest-2x (in-plane) upsampled map (decoder.py:46-47, 58-59), output phase (py, px):
     out[2y+py, 2x+px] reads only a 2x2 in-plane neighbourhood of the LOW-resolution map, with the 3x3 weights that land

@@ -47,6 +47,9 @@ class _Branch:
                         self.w[f"{name}.phase{ph}"] = engine.pack_conv3d_upsampled(g(f"{name}.weight"), g(f"{name}.bias"), device,
                                                                                   ph >> 1, ph & 1)
         norm("norm_out"); conv("conv_out")
+        if kind == "decoder" and not split and g("conv_out.weight").shape[0] <= 3:
+            self.w["conv_out.zfold"] = engine.pack_conv3d_zfold(g("conv_out.weight"), device)
+            self.w["conv_out.bias"] = g("conv_out.bias").to(device=device, dtype=torch.float32).contiguous()
         self.cin = g("conv_in.weight").shape[1]
         self.cout = g("conv_out.weight").shape[0]
 
@@ -214,8 +217,20 @@ class B200DualVAE:
         H, W = 4 * h, 4 * w_
         if out is None:
             out = torch.empty((B, D, br.cout, H, W), dtype=torch.float32, device=self.device)
-        bd.norm_conv("conv_out", "norm_out", x, st, w["norm_out"], w["conv_out"], br.cout, inplace_norm=True, want_stats=False, out=out,
-                     out_mode=1, out_cstride=br.cout, out_scale=out_scale, out_mask=out_mask)
+        if "conv_out.zfold" in w and H % 16 == 0 and W % 16 == 0 and os.environ.get("B2D_NO_ZFOLD") is None:
+            # Conv3d 128 -> 3: nine in-plane taps per slice with rows (kz, co), then a gather over z (engine.pack_conv3d_zfold)
+            hn = bd.gn_silu("norm_out", x, st, w["norm_out"], inplace=True)
+            P = torch.empty((B, D, H, W, 12), dtype=torch.float32, device=self.device)
+            plan = ConvPlan([hn], w["conv_out.zfold"], P, cout=12, out_mode=2, out_cstride=12)
+            bd.prog.flops += plan.flops
+            bd.prog.add("conv_out.zfold", plan.run)
+            bd.keep.append((plan, P))
+            bias, co = w["conv_out.bias"], br.cout
+            bd.prog.add("conv_out.combine", lambda s: _lib.call("b2d_zfold_combine", P.data_ptr(), B * D, D, H, W, co, _lib.ptr(bias),
+                                                                _lib.ptr(out_scale), _lib.ptr(out_mask), out.data_ptr(), co, 0, s))
+        else:
+            bd.norm_conv("conv_out", "norm_out", x, st, w["norm_out"], w["conv_out"], br.cout, inplace_norm=True, want_stats=False,
+                         out=out, out_mode=1, out_cstride=br.cout, out_scale=out_scale, out_mask=out_mask)
         return dict(program=bd.finish(), z_in=z_in, out=out, keep=bd.keep, stats=bd.stats_buf)
 
     # ------------------------------------------------------------------------------ module API

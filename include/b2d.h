@@ -33,7 +33,7 @@ extern "C" {
 #define B2D_API
 #endif
 
-#define B2D_VERSION 4
+#define B2D_VERSION 5
 #define B2D_MAX_SEG 6
 #define B2D_MAX_TAPS 27
 
@@ -159,6 +159,13 @@ B2D_API int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, void*
 
 /* nearest-neighbour (1,2,2) upsample, nn.Upsample (vae/decoder.py:46,58). bf16 NDHWC, ND = N*D. */
 B2D_API int b2d_upsample2x_nearest(const void* x, void* y, int32_t ND, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* Second half of the z-folded conv_out (vae/decoder.py:71, Conv3d C -> co <= 3): the conv engine runs the 3x3x3 conv as a
+ * 3x3 conv per z slice with output rows (kz, co) -- P: fp32 [ND][H][W][12], entry kz*4 + co -- and this pass sums the three
+ * z contributions (zero padding in z), adds the bias and writes out[(img*out_cstride + out_coff + c)][H][W] =
+ * (sum + bias[c]) * scale[c] * mask[img][y][x] (scale, mask, bias optional).  ND = N*D images, D slices per sample. */
+B2D_API int b2d_zfold_combine(const float* P, int32_t ND, int32_t D, int32_t H, int32_t W, int32_t co, const float* bias,
+                      const float* scale, const float* mask, float* out, int32_t out_cstride, int32_t out_coff, void* stream);
 
 /* layout/precision plumbing at the module boundary:
  * planar fp32 [N][C][P] (optionally divided by scale[c], MaxNormalizer normalizer.py:46-51)

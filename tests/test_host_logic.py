@@ -124,7 +124,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.b2d_version() == 4
+    assert lib.b2d_version() == 5
 
 
 def test_abi_rejects_bad_arguments_without_a_gpu():
@@ -183,3 +183,31 @@ def test_upsample_folded_conv_weights_match_reference_math():
         got = F.conv3d(x, wk, b, padding=1)
         want = ref[:, :, :, py::2, px::2]
         assert (got - want).abs().max() <= 2e-2 * want.abs().max()  # bf16-rounded packed weights
+
+
+def test_zfold_conv_out_weights_match_reference_math():
+    """decoder.py:71: Conv3d(C -> 3, k3, pad 1) == a per-slice 3x3 conv with rows (kz, co) followed by a gather over z
+    (engine.pack_conv3d_zfold + b2d_zfold_combine).  Checked on the CPU with the packed matrix itself."""
+    import torch.nn.functional as F
+    from diffusion_model_project_b200 import engine
+    g = torch.Generator().manual_seed(5)
+    ci, co, D = 64, 3, 4
+    w = torch.randn(co, ci, 3, 3, 3, generator=g) * 0.05
+    b = torch.randn(co, generator=g)
+    x = torch.randn(1, ci, D, 6, 5, generator=g)
+    ref = F.conv3d(x, w, b, padding=1)
+    pw = engine.pack_conv3d_zfold(w, "cpu")
+    assert len(pw.taps) == 9 and all(dz == 0 for dz, _, _ in pw.taps) and pw.ktot == 9 * 64 and pw.bias is None
+    mat = pw.w.float()[:12].reshape(12, 9, 64)
+    w2d = torch.zeros(12, ci, 3, 3)
+    for t, (_, dy, dx) in enumerate(pw.taps):
+        w2d[:, :, dy + 1, dx + 1] = mat[:, t, :ci]
+    P = torch.stack([F.conv2d(x[:, :, z], w2d, padding=1) for z in range(D)], dim=2)  # [1, 12, D, H, W]
+    got = torch.zeros_like(ref)
+    for z in range(D):
+        for kz in range(3):
+            zi = z + kz - 1
+            if 0 <= zi < D:
+                got[:, :, z] += P[:, kz * 4:kz * 4 + co, zi]
+    got += b.view(1, co, 1, 1, 1)
+    assert (got - ref).abs().max() <= 2e-2 * ref.abs().max()  # bf16-rounded packed weights
