@@ -315,6 +315,33 @@ __global__ void zfold_combine_kernel(const float4* __restrict__ P, int D, long l
   }
 }
 
+// z-stacked conv_in input (vae/encoder.py:30, decoder.py:31: Conv3d with C <= 21 input channels): the three z taps become
+// channels -- y[b][z][p][kz*C + c] = x[b][z+kz-1][p][c] (zero outside the sample) -- so the conv runs 9 in-plane taps on one
+// 64-channel chunk instead of 27 taps on a chunk that is mostly padding.  bf16 channels-last, pad channels of y untouched.
+template <int C>
+__global__ void __launch_bounds__(256) zstack_cl_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int D, long long P,
+                                                        long long total, int cvec) {
+  constexpr int LV = (C + 7) / 8, OV = (3 * C + 7) / 8;  // 16-byte vectors read per source row / written per output row
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)((i / P) % D);
+    union { uint4 v[OV]; uint16_t h[OV * 8]; } o;
+#pragma unroll
+    for (int j = 0; j < OV; ++j) o.v[j] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz) {
+      const int zi = z + kz - 1;
+      if (zi < 0 || zi >= D) continue;
+      union { uint4 v[LV]; uint16_t h[LV * 8]; } in;
+#pragma unroll
+      for (int j = 0; j < LV; ++j) in.v[j] = __ldg(x + (i + (long long)(kz - 1) * P) * cvec + j);
+#pragma unroll
+      for (int c = 0; c < C; ++c) o.h[kz * C + c] = in.h[c];
+    }
+#pragma unroll
+    for (int j = 0; j < OV; ++j) y[i * cvec + j] = o.v[j];
+  }
+}
+
 static inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
   long long b = (work_items + per_block - 1) / per_block;
   const long long cap = (long long)num_sms() * max_waves;
@@ -370,6 +397,19 @@ extern "C" int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, vo
   launch_pdl(maxpool_stats_kernel, dim3(bx, N), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)x_lo, (uint4*)y,
                                                                        (uint4*)y_lo, H, W, C, stats);
   return check_launch("maxpool_stats_kernel");
+}
+
+extern "C" int b2d_zstack_cl(const void* x, void* y, int32_t ND, int32_t D, int64_t P, int32_t C, int32_t cpad, void* stream) {
+  if (!x || !y || x == y || ND < 1 || D < 1 || (ND % D) || P < 1 || 3 * C > cpad || (cpad % 8) ||
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15))
+    return set_error(B2D_E_INVALID, "b2d_zstack_cl: bad argument");
+  const long long total = (long long)ND * P;
+  const int g = grid_for(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 3) zstack_cl_kernel<3><<<g, 256, 0, st>>>((const uint4*)x, (uint4*)y, D, P, total, cpad / 8);
+  else if (C == 8) zstack_cl_kernel<8><<<g, 256, 0, st>>>((const uint4*)x, (uint4*)y, D, P, total, cpad / 8);
+  else return set_error(B2D_E_UNSUPPORTED, "b2d_zstack_cl: C=%d (3 or 8: the VAE branches' input channels)", C);
+  return check_launch("zstack_cl_kernel");
 }
 
 extern "C" int b2d_zfold_combine(const float* P, int32_t ND, int32_t D, int32_t H, int32_t W, int32_t co, const float* bias,

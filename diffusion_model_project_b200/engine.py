@@ -136,6 +136,17 @@ def pack_conv3d(w, bias, device, split=False, down=False):
     return pack_weight(w.permute(0, 2, 3, 4, 1).reshape(co, 27, ci), [ci], taps_3x3x3(0 if down else 1), bias, device, split)
 
 
+def pack_conv3d_zstack(w, bias, device):
+    """Conv3d 3x3x3 with few input channels (encoder.py:30: 3, decoder.py:31: 8) over a z-stacked input (b2d_zstack_cl:
+    channel kz*Cin + c holds slice z+kz-1): 9 in-plane taps on ONE 64-channel chunk instead of 27 taps on a chunk that is
+    mostly zero padding -- a third of the MMAs."""
+    co, ci = w.shape[:2]
+    assert 3 * ci <= 64 and tuple(w.shape[2:]) == (3, 3, 3)
+    rows = w.float().permute(0, 3, 4, 2, 1).reshape(co, 9, 3 * ci)   # [co][ky,kx][kz*ci + c]
+    taps = [(0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    return pack_weight(rows, [3 * ci], taps, bias, device)
+
+
 def pack_conv3d_zfold(w, device):
     """Conv3d 3x3x3 with Cout <= 3 (decoder.py:71) as a per-slice 3x3 conv with rows (kz, co): row kz*4 + co holds
     w[co, :, kz] -- 9 taps and one N = 16 tile instead of 27 taps (an N = 16 MMA costs as much as an N = 64 one, so the

@@ -35,6 +35,8 @@ class _Branch:
                 conv(f"{name}.residual_layer")
 
         conv("conv_in")
+        if not split and g("conv_in.weight").shape[1] in (3, 8):
+            self.w["conv_in.zstack"] = engine.pack_conv3d_zstack(g("conv_in.weight"), g("conv_in.bias"), device)
         for r in ("res1_1", "res1_2", "res2_1", "res2_2", "res3_1", "res3_2"):
             res(r)
         if kind == "encoder":
@@ -125,6 +127,17 @@ class _Builder:
         return self.norm_conv(f"{name}.conv2", f"{name}.norm2", r, st_r, w[f"{name}.norm2"], w[f"{name}.conv2"], cout,
                               inplace_norm=True, residual=skip, want_stats=want_stats, raw=raw_out)
 
+    def conv_in(self, w, x_in: Act, cin: int, cout: int):
+        """First conv of a branch (encoder.py:30 / decoder.py:31).  With few input channels the three z taps are moved into
+        the channel dimension first (b2d_zstack_cl + engine.pack_conv3d_zstack): a third of the MMAs."""
+        if "conv_in.zstack" in w and os.environ.get("B2D_NO_ZSTACK") is None:
+            N, D, H, W, C = x_in.shape
+            xs = new_act(N, D, H, W, C, self.dev, False, zero=True)
+            self.keep.append(xs)
+            self.prog.add("conv_in.zstack", lambda s: _lib.call("b2d_zstack_cl", _lib.ptr(x_in.hi), _lib.ptr(xs.hi), N * D, D, H * W, cin, C, s))
+            return self.conv("conv_in", xs, w["conv_in.zstack"], cout, raw=True)
+        return self.conv("conv_in", x_in, w["conv_in"], cout, raw=True)
+
     def finish(self):
         used, buf = self.stats_used, self.stats_buf
         self.prog.steps = [("stats.zero", lambda s: _lib.call("b2d_zero", buf.data_ptr(), used * 8, s))] + self.prog.steps
@@ -166,7 +179,7 @@ class B200DualVAE:
         bd = _Builder(B, self.device, self.split)
         if x_in is None:
             x_in = new_act(B, D, H, W, pad64(br.cin), self.device, self.split, zero=True)
-        x, st = bd.conv("conv_in", x_in, w["conv_in"], 128, raw=True)
+        x, st = bd.conv_in(w, x_in, br.cin, 128)
         x, st = bd.res(w, "res1_1", x, st, 128, 128)
         x, _ = bd.res(w, "res1_2", x, st, 128, 128, want_stats=False, raw_out=False)   # -> down1 (MMA operand)
         x, st = bd.conv("down1", x, w["down1"], 128, stride=2)                            # -> res2_1's 1x1x1 skip conv
@@ -192,7 +205,7 @@ class B200DualVAE:
         bd = _Builder(B, self.device, self.split)
         if z_in is None:
             z_in = new_act(B, D, h, w_, pad64(br.cin), self.device, self.split, zero=True)
-        x, st = bd.conv("conv_in", z_in, w["conv_in"], 512, raw=True)
+        x, st = bd.conv_in(w, z_in, br.cin, 512)
         x, st = bd.res(w, "res1_1", x, st, 512, 512)
         x, _ = bd.res(w, "res1_2", x, st, 512, 512, want_stats=False, raw_out=False)   # -> upsample -> conv_up1
         for stage, (cin, cout, r1, r2, last) in enumerate(((512, 256, "res2_1", "res2_2", False), (256, 128, "res3_1", "res3_2", True)), 1):

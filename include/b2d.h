@@ -167,6 +167,11 @@ B2D_API int b2d_upsample2x_nearest(const void* x, void* y, int32_t ND, int32_t H
 B2D_API int b2d_zfold_combine(const float* P, int32_t ND, int32_t D, int32_t H, int32_t W, int32_t co, const float* bias,
                       const float* scale, const float* mask, float* out, int32_t out_cstride, int32_t out_coff, void* stream);
 
+/* z-stacked input of the VAE conv_in layers (vae/encoder.py:30, decoder.py:31; C = 3 or 8 input channels): y[img][p][kz*C + c] =
+ * x[img + kz - 1][p][c] for kz = 0..2, zero where the slice z + kz - 1 falls outside its sample (D slices per sample).
+ * bf16 channels-last [ND][P][cpad], 3*C <= cpad; the conv then runs 9 in-plane taps instead of 27. */
+B2D_API int b2d_zstack_cl(const void* x, void* y, int32_t ND, int32_t D, int64_t P, int32_t C, int32_t cpad, void* stream);
+
 /* layout/precision plumbing at the module boundary:
  * planar fp32 [N][C][P] (optionally divided by scale[c], MaxNormalizer normalizer.py:46-51)
  * -> channels-last bf16 [N][P][cpad] written at channel offset coff (pad channels untouched). */

@@ -189,9 +189,10 @@ def test_e3d_encoder_and_sanity_roundtrip():
     assert rec.shape == x.shape and rel_l2(rec, rec_ref) <= 1.5e-2  # two bf16 networks back to back
 
 
-def test_zfold_conv_out_matches_direct_conv(vae_sd, monkeypatch):
-    """decoder.py:71 conv_out (128 -> 3): the z-folded path (9 taps with rows (kz, co) + b2d_zfold_combine) against the
-    direct 27-tap conv of the same engine, and both against the CPU oracle; ragged depth (edge slices use zero padding)."""
+def test_zfold_conv_out_and_zstack_conv_in_match_direct_convs(vae_sd, monkeypatch):
+    """decoder.py:71 conv_out (128 -> 3) as a z-folded conv (9 taps with rows (kz, co) + b2d_zfold_combine) and decoder.py:31
+    / encoder.py:30 conv_in over a z-stacked input (b2d_zstack_cl), against the direct 27-tap convs of the same engine,
+    and both against the CPU oracle; ragged depth (edge slices use zero padding)."""
     gen = torch.Generator().manual_seed(23)
     z = torch.randn(2, 8, 5, 8, 8, generator=gen)
     ref = ovae.decode_3d(vae_sd, z)
@@ -199,13 +200,19 @@ def test_zfold_conv_out_matches_direct_conv(vae_sd, monkeypatch):
     for mode in ("zfold", "direct"):
         if mode == "direct":
             monkeypatch.setenv("B2D_NO_ZFOLD", "1")
+            monkeypatch.setenv("B2D_NO_ZSTACK", "1")
         vae = B200DualVAE(3, 8, device="cuda").load_state_dict(vae_sd)
         st = vae.build_decoder("decoder_3d", 2, 5, 8, 8)
         names = [n for n, _ in st["program"].steps]
-        assert ("conv_out.zfold" in names) == (mode == "zfold")
+        assert ("conv_out.zfold" in names) == (mode == "zfold") and ("conv_in.zstack" in names) == (mode == "zfold")
         outs[mode] = vae.decode_3d(z.cuda()).cpu()
         assert rel_l2(outs[mode], ref) <= 1e-2
-    assert rel_l2(outs["zfold"], outs["direct"]) <= 2e-3
+        x = torch.randn(2, 3, 5, 32, 32, generator=torch.Generator().manual_seed(29))
+        mu, _ = vae.encoder_2d(x.cuda())
+        outs[mode + ".mu"] = mu.cpu()
+        assert rel_l2(outs[mode + ".mu"], ovae.encoder_forward(vae_sd, x, "encoder_2d.")[0]) <= 1e-2
+    assert rel_l2(outs["zfold"], outs["direct"]) <= 1e-2  # two bf16 evaluation orders of the whole decoder
+    assert rel_l2(outs["zfold.mu"], outs["direct.mu"]) <= 1e-2
 
 
 def test_full_size_properties(unet_sd, vae_sd):

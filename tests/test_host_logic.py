@@ -211,3 +211,26 @@ def test_zfold_conv_out_weights_match_reference_math():
                 got[:, :, z] += P[:, kz * 4:kz * 4 + co, zi]
     got += b.view(1, co, 1, 1, 1)
     assert (got - ref).abs().max() <= 2e-2 * ref.abs().max()  # bf16-rounded packed weights
+
+
+def test_zstack_conv_in_weights_match_reference_math():
+    """encoder.py:30 / decoder.py:31: Conv3d(C <= 21 -> Cout, k3, pad 1) == a 3x3 in-plane conv over the z-stacked input
+    (channel kz*C + c = slice z+kz-1; engine.pack_conv3d_zstack + b2d_zstack_cl).  CPU check with the packed matrix."""
+    import torch.nn.functional as F
+    from diffusion_model_project_b200 import engine
+    g = torch.Generator().manual_seed(7)
+    ci, co, D = 3, 16, 4
+    w = torch.randn(co, ci, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(co, generator=g)
+    x = torch.randn(1, ci, D, 6, 5, generator=g)
+    ref = F.conv3d(x, w, b, padding=1)
+    pw = engine.pack_conv3d_zstack(w, b, "cpu")
+    assert len(pw.taps) == 9 and pw.ktot == 9 * 64 and pw.cin_pad == [64]
+    mat = pw.w.float()[:co].reshape(co, 9, 64)
+    w2d = torch.zeros(co, 3 * ci, 3, 3)
+    for t, (_, dy, dx) in enumerate(pw.taps):
+        w2d[:, :, dy + 1, dx + 1] = mat[:, t, :3 * ci]
+    xp = F.pad(x, (0, 0, 0, 0, 1, 1))                                                 # zero slices at z = -1 and z = D
+    xs = torch.cat([xp[:, :, kz:kz + D] for kz in range(3)], dim=1)                     # [1, 3*ci, D, H, W], channel kz*ci + c
+    got = torch.stack([F.conv2d(xs[:, :, z], w2d, b, padding=1) for z in range(D)], dim=2)
+    assert (got - ref).abs().max() <= 2e-2 * ref.abs().max()  # bf16-rounded packed weights
