@@ -73,6 +73,9 @@ _SIGNATURES = {
     "b2d_edt2d": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_bilinear_resize": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_zero": (c_int, [c_void_p, c_i64, c_void_p]),
+    "b2d_gn_gn_apply": (c_int, [c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i64, c_i32, c_void_p, c_void_p, c_void_p, c_float, c_i32,
+                        c_void_p, c_void_p, c_float, c_i32, c_void_p]),
+    "b2d_maxpool2x2_gn": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_float, c_i32, c_void_p]),
     "b2d_zstack_cl": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_void_p]),
     "b2d_zfold_combine": (c_int, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
                           c_void_p]),

@@ -238,6 +238,181 @@ __global__ void __launch_bounds__(256) maxpool_stats_kernel(const uint4* __restr
   }
 }
 
+// --------------------------------------------------------------------------- per-sample fused GroupNorm(1, C) ops
+// One 1024-thread CTA per sample keeps the sample (<= 65536 elements) in registers, so a normalisation whose statistics
+// depend on values produced in the same kernel needs no second launch:
+//   gn_gn_kernel      y1 = silu(GN(x; stats1)),  y2 = GN(y1)        (DoubleBlock's last norm + the attention pre-norm,
+//                                                                    unet/blocks.py:37-47 and 192,214)
+//   maxpool_gn_kernel y  = silu(GN(maxpool2x2(x)))                  (Down, unet/blocks.py:161-174)
+__device__ __forceinline__ float silu_tanh(float v) {
+  const float h = 0.5f * v;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
+
+// sum of (s, ss) over the CTA, fp64, result broadcast to every thread
+__device__ __forceinline__ void block_sum2(double& s, double& ss, double (*red)[2]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[w][0] = s; red[w][1] = ss; }
+  __syncthreads();
+  s = 0.0; ss = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s += red[i][0]; ss += red[i][1]; }  // same order in every thread
+}
+
+// KEEP: the sample fits the register file (<= 32 elements per thread); otherwise the second pass re-reads what the thread
+// itself wrote (y1) / pooled (x) -- L2 hits, no cross-thread dependence.
+template <int VPT, bool KEEP>
+__global__ void __launch_bounds__(1024) gn_gn_kernel(const uint4* __restrict__ x, int in_f16, uint4* __restrict__ y1,
+                                                     uint4* __restrict__ y2, int nvec, int C, const double* __restrict__ stats1,
+                                                     const float* __restrict__ g1, const float* __restrict__ b1, float eps1, int act1,
+                                                     const float* __restrict__ g2, const float* __restrict__ b2, float eps2, int act2) {
+  griddep_launch_dependents();
+  griddep_wait();
+  __shared__ double red[32][2];
+  const int n = blockIdx.x;
+  const int vpc = C >> 3;
+  const int c0 = (threadIdx.x % vpc) << 3;  // blockDim.x is a multiple of vpc: a thread sees the same 8 channels
+  const double cnt = (double)nvec * 8.0;
+  const double m1 = stats1[2 * n] / cnt;
+  double var1 = stats1[2 * n + 1] / cnt - m1 * m1;
+  if (var1 < 0) var1 = 0;
+  const float mean1 = (float)m1, rstd1 = (float)(1.0 / sqrt(var1 + (double)eps1));
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float ga = g1 ? __ldg(g1 + c0 + j) : 1.f, be = b1 ? __ldg(b1 + c0 + j) : 0.f;
+    a[j] = rstd1 * ga;
+    b[j] = be - mean1 * rstd1 * ga;
+  }
+  const uint4* xp = x + (long long)n * nvec;
+  uint4* y1p = y1 + (long long)n * nvec;
+  constexpr int KV = KEEP ? VPT : 1;
+  float f[KV][8];
+  float ps = 0.f, pss = 0.f;
+#pragma unroll
+  for (int k0 = 0; k0 < VPT; k0 += 4) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4 && k0 + k < VPT; ++k) {
+      const int v = threadIdx.x + (k0 + k) * 1024;
+      u[k] = v < nvec ? __ldcs(xp + v) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4 && k0 + k < VPT; ++k) {
+      const int v = threadIdx.x + (k0 + k) * 1024;
+      float (&fk)[8] = f[KEEP ? k0 + k : 0];
+      if (in_f16) unpack8_f16(u[k], fk); else unpack8(u[k], fk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(fk[j], a[j], b[j]);
+        if (act1) t = silu_tanh(t);
+        fk[j] = t;
+        if (v < nvec) { ps += t; pss = fmaf(t, t, pss); }
+      }
+      if (v < nvec) y1p[v] = pack8(fk);
+    }
+  }
+  double s = (double)ps, ss = (double)pss;
+  block_sum2(s, ss, red);
+  const double m2 = s / cnt;
+  double var2 = ss / cnt - m2 * m2;
+  if (var2 < 0) var2 = 0;
+  const float mean2 = (float)m2, rstd2 = (float)(1.0 / sqrt(var2 + (double)eps2));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float ga = g2 ? __ldg(g2 + c0 + j) : 1.f, be = b2 ? __ldg(b2 + c0 + j) : 0.f;
+    a[j] = rstd2 * ga;
+    b[j] = be - mean2 * rstd2 * ga;
+  }
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int v = threadIdx.x + k * 1024;
+    float (&fk)[8] = f[KEEP ? k : 0];
+    if (!KEEP) unpack8(v < nvec ? y1p[v] : make_uint4(0u, 0u, 0u, 0u), fk);  // this thread's own store, bf16-rounded
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(fk[j], a[j], b[j]);
+      if (act2) t = silu_tanh(t);
+      fk[j] = t;
+    }
+    if (v < nvec) y2[(long long)n * nvec + v] = pack8(fk);
+  }
+}
+
+template <int VPT, bool KEEP>
+__global__ void __launch_bounds__(1024) maxpool_gn_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C,
+                                                          const float* __restrict__ g, const float* __restrict__ be, float eps,
+                                                          int act) {
+  griddep_launch_dependents();
+  griddep_wait();
+  __shared__ double red[32][2];
+  const int n = blockIdx.x;
+  const int OW = W >> 1, vpc = C >> 3;
+  const int nvec = (H >> 1) * OW * vpc;
+  const int cv = threadIdx.x % vpc;
+  const uint4* xi = x + (long long)n * H * W * vpc;
+  constexpr int KV = KEEP ? VPT : 1;
+  float f[KV][8];
+  float ps = 0.f, pss = 0.f;
+  auto pool = [&](int v, float (&m)[8]) {
+    const int pix = v < nvec ? v / vpc : 0;
+    const int ox = pix % OW, oy = pix / OW;
+    uint4 q[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) q[t] = __ldg(xi + ((long long)(2 * oy + (t >> 1)) * W + (2 * ox + (t & 1))) * vpc + cv);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float e[8];
+      unpack8(q[t], e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = t == 0 ? e[j] : fmaxf(m[j], e[j]);
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int v = threadIdx.x + k * 1024;
+    float (&fk)[8] = f[KEEP ? k : 0];
+    pool(v, fk);
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ps += fk[j]; pss = fmaf(fk[j], fk[j], pss); }
+    }
+  }
+  double s = (double)ps, ss = (double)pss;
+  block_sum2(s, ss, red);
+  const double cnt = (double)nvec * 8.0;
+  const double m = s / cnt;
+  double var = ss / cnt - m * m;
+  if (var < 0) var = 0;
+  const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float ga = g ? __ldg(g + cv * 8 + j) : 1.f, bb = be ? __ldg(be + cv * 8 + j) : 0.f;
+    a[j] = rstd * ga;
+    b[j] = bb - mean * rstd * ga;
+  }
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int v = threadIdx.x + k * 1024;
+    float (&fk)[8] = f[KEEP ? k : 0];
+    if (!KEEP) pool(v, fk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(fk[j], a[j], b[j]);
+      if (act) t = silu_tanh(t);
+      fk[j] = t;
+    }
+    if (v < nvec) y[(long long)n * nvec + v] = pack8(fk);
+  }
+}
+
 // --------------------------------------------------------------------------- nearest 2x (in-plane)
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long ND,
                                                          int H, int W, int vpc) {
@@ -422,6 +597,42 @@ extern "C" int b2d_zfold_combine(const float* P, int32_t ND, int32_t D, int32_t 
   zfold_combine_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)P, D, plane, total, co, bias, scale,
                                                                                mask, out, out_cstride, out_coff);
   return check_launch("zfold_combine_kernel");
+}
+
+// per-sample fused ops: one CTA per sample, the sample (<= 65536 elements, one GroupNorm group) lives in registers
+static int fused_vpt(long long nvec) { return nvec <= 1024 ? 1 : nvec <= 2048 ? 2 : nvec <= 4096 ? 4 : nvec <= 8192 ? 8 : 0; }
+
+extern "C" int b2d_gn_gn_apply(const void* x, int32_t in_f16, void* y1, void* y2, int32_t N, int64_t P, int32_t C, const double* stats1,
+                               const float* gamma1, const float* beta1, float eps1, int32_t act1, const float* gamma2,
+                               const float* beta2, float eps2, int32_t act2, void* stream) {
+  if (!x || !y1 || !y2 || !stats1 || N < 1 || P < 1 || C < 8 || (C % 8)) return set_error(B2D_E_INVALID, "b2d_gn_gn_apply: bad argument");
+  const long long nvec = P * (C / 8);
+  const int vpt = fused_vpt(nvec);
+  if (vpt == 0 || (1024 % (C / 8)) != 0)
+    return set_error(B2D_E_UNSUPPORTED, "b2d_gn_gn_apply: sample of %lld elements / C=%d (max 65536 elements, C/8 dividing 1024)", nvec * 8, C);
+  cudaStream_t st = (cudaStream_t)stream;
+#define B2D_GG(V, K) launch_pdl(gn_gn_kernel<V, K>, dim3(N), dim3(1024), 0, st, (const uint4*)x, (int)in_f16, (uint4*)y1, (uint4*)y2, (int)nvec, \
+                             (int)C, stats1, gamma1, beta1, eps1, (int)act1, gamma2, beta2, eps2, (int)act2)
+  if (vpt == 1) B2D_GG(1, true); else if (vpt == 2) B2D_GG(2, true); else if (vpt == 4) B2D_GG(4, true); else B2D_GG(8, false);
+#undef B2D_GG
+  return check_launch("gn_gn_kernel");
+}
+
+extern "C" int b2d_maxpool2x2_gn(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, const float* gamma,
+                                 const float* beta, float eps, int32_t act, void* stream) {
+  if (!x || !y || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 8 || (C % 8))
+    return set_error(B2D_E_INVALID, "b2d_maxpool2x2_gn: bad argument");
+  const long long nvec = (long long)(H / 2) * (W / 2) * (C / 8);
+  const int vpt = fused_vpt(nvec);
+  if (vpt == 0 || (1024 % (C / 8)) != 0)
+    return set_error(B2D_E_UNSUPPORTED, "b2d_maxpool2x2_gn: pooled sample of %lld elements / C=%d (max 65536 elements, C/8 dividing 1024)",
+                     nvec * 8, C);
+  cudaStream_t st = (cudaStream_t)stream;
+#define B2D_PG(V, K) launch_pdl(maxpool_gn_kernel<V, K>, dim3(N), dim3(1024), 0, st, (const uint4*)x, (uint4*)y, (int)H, (int)W, (int)C, gamma, beta, \
+                             eps, (int)act)
+  if (vpt == 1) B2D_PG(1, true); else if (vpt == 2) B2D_PG(2, true); else if (vpt == 4) B2D_PG(4, true); else B2D_PG(8, false);
+#undef B2D_PG
+  return check_launch("maxpool_gn_kernel");
 }
 
 extern "C" int b2d_upsample2x_nearest(const void* x, void* y, int32_t ND, int32_t H, int32_t W, int32_t C, void* stream) {

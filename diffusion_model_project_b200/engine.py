@@ -341,6 +341,24 @@ def gn_apply(x: Act, y: Act, stats: torch.Tensor, cpg: int, gamma, beta, act: bo
          ptr(stats_out), 1 if x.f16 else 0, stream)
 
 
+def fused_gn_ok(x: Act, elems_per_sample: int) -> bool:
+    """The per-sample fused GroupNorm kernels (b2d_gn_gn_apply, b2d_maxpool2x2_gn) apply: bf16 mode, a sample of at most
+    65536 elements, C/8 dividing 1024."""
+    return x.lo is None and elems_per_sample <= 65536 and 1024 % (x.C // 8) == 0
+
+
+def gn_gn_apply(x: Act, y1: Act, y2: Act, stats1: torch.Tensor, g1, b1, act1: bool, g2, b2, act2: bool, stream: int, eps=1e-5):
+    N, D, H, W, Cc = x.shape
+    call("b2d_gn_gn_apply", ptr(x.hi), 1 if x.f16 else 0, ptr(y1.hi), ptr(y2.hi), N, D * H * W, Cc, ptr(stats1), ptr(g1), ptr(b1), eps,
+         1 if act1 else 0, ptr(g2), ptr(b2), eps, 1 if act2 else 0, stream)
+
+
+def maxpool_gn(x: Act, y: Act, g, b, act: bool, stream: int, eps=1e-5):
+    N, D, H, W, Cc = x.shape
+    assert D == 1
+    call("b2d_maxpool2x2_gn", ptr(x.hi), ptr(y.hi), N, H, W, Cc, ptr(g), ptr(b), eps, 1 if act else 0, stream)
+
+
 def maxpool_stats(x: Act, y: Act, stats: torch.Tensor, stream: int):
     N, D, H, W, Cc = x.shape
     assert D == 1
@@ -407,6 +425,8 @@ class Chain:
             elif kind == "zero":
                 buf, nbytes = op[1:]
                 _lib.check(lib.b2d_chain_add_zero(self.handle, buf.data_ptr(), (nbytes + 15) // 16 * 16), f"chain add {name}")
+            elif kind == "unsupported":
+                raise ValueError(f"program step {name!r} ({op[1]}) has no chain form: build the program with fuse_small=False")
             else:
                 raise ValueError(f"unknown chain op {kind!r}")
             self._keep.append(op)

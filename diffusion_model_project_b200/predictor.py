@@ -131,7 +131,8 @@ class B200LatentDiffusionPredictor:
         chains = self.unet_chains if (self.unet_chains > 1 and N % self.unet_chains == 0 and N // self.unet_chains >= 8) else 1
         if chains == 1:
             ses["unet"] = self.model.build_program(N, ses["h"], ses["w"], x_in=ses["unet_in"], eps_out=ses["eps"], eps_mode=2,
-                                                   temb_row=ses["step_idx"], temb_row_stride=0, temb_table=temb_steps)
+                                                   temb_row=ses["step_idx"], temb_row_stride=0, temb_table=temb_steps,
+                                                   fuse_small=False if self.unet_chain else None)
         else:
             parts, n = [], N // chains
             ui = ses["unet_in"]

@@ -12,6 +12,7 @@ are loaded (models.py:14-26,72-82, blocks.py:89-95).
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -129,8 +130,12 @@ class B200UNet:
     # ------------------------------------------------------------------------------ program
     def build_program(self, N: int, h: int, w: int, *, x_in: Optional[Act] = None, eps_out: Optional[torch.Tensor] = None,
                       eps_mode: int = 1, temb_row: Optional[torch.Tensor] = None, temb_row_stride: int = 1,
-                      temb_table: Optional[torch.Tensor] = None) -> dict:
+                      temb_table: Optional[torch.Tensor] = None, fuse_small: Optional[bool] = None) -> dict:
         """Allocate static buffers and conv plans for a batch of N (h x w) maps and record the launch list.
+
+        fuse_small (default: env B2D_UNET_FUSE_GN != "0"): where a sample has at most 65536 elements, the last norm of a
+        DoubleBlock + the attention pre-norm, and max-pool + norm, each run as ONE per-sample launch (engine.gn_gn_apply,
+        engine.maxpool_gn) instead of two launches that meet through global statistics.
 
         x_in: channels-last input [N,1,h,w,pad64(in_channels)] (allocated if None);
         eps_out: fp32 output, planar [N,out,h,w] (eps_mode 1) or channels-last [N,h,w,out] (eps_mode 2).
@@ -138,6 +143,8 @@ class B200UNet:
         if not self._w:
             raise RuntimeError("B200UNet: load_state_dict() must be called before forward()")
         dev, sp, f = self.device, self.split, self.features
+        if fuse_small is None:
+            fuse_small = os.environ.get("B2D_UNET_FUSE_GN", "1") != "0"
         nl = len(f)
         if h % (1 << nl) or w % (1 << nl):
             raise ValueError(f"B200UNet: input {h}x{w} must be divisible by {1 << nl} (five 2x2 max-pools)")
@@ -171,8 +178,9 @@ class B200UNet:
                                   dtype=torch.float32, device=dev)
         keep = []
 
-        def conv_gn_act(name, inputs, pw, cout, H, Wd, gnw, *, temb_col=None, stats_out=None, nphase=1):
-            """conv (+GN sums in the epilogue) -> in-place GN apply + SiLU (+temb)."""
+        def conv_gn_act(name, inputs, pw, cout, H, Wd, gnw, *, temb_col=None, stats_out=None, nphase=1, second=None):
+            """conv (+GN sums in the epilogue) -> in-place GN apply + SiLU (+temb).  second = (name2, y2, gamma2, beta2): the
+            same launch also writes y2 = GN(out; gamma2, beta2) (the attention pre-norm), per-sample fused form."""
             up = 2 if nphase == 4 else 1
             # raw conv output: fp16 storage in bf16 mode (8x finer than bf16 ahead of the normalisation), rewritten
             # in place as bf16 by the GroupNorm apply
@@ -185,6 +193,13 @@ class B200UNet:
             g, b = gnw
             tt = temb_table if temb_col is not None else None
             tr = temb_row if temb_col is not None else None
+            if second is not None:
+                assert temb_col is None and stats_out is None
+                name2, y2, g2, b2 = second
+                prog.add(f"{name}.gn+{name2}", lambda s: engine.gn_gn_apply(raw, out, y2, st, g, b, True, g2, b2, False, s),
+                         op=("unsupported", "gn_gn"))
+                keep.append(plan)
+                return out
             prog.add(f"{name}.gn", lambda s, raw=raw, out=out, st=st, g=g, b=b, tc=temb_col, so=stats_out, cout=cout: engine.gn_apply(
                 raw, out, st, cout, g, b, True, s, temb=temb_table if tc is not None else None,
                 temb_row=temb_row if tc is not None else None, temb_row_stride=temb_row_stride, temb_col=tc or 0, stats_out=so),
@@ -192,18 +207,34 @@ class B200UNet:
             keep.append(plan)
             return out
 
-        def double(prefix, inputs, cmid, cout, H, Wd, stats_out=None):
+        def double(prefix, inputs, cmid, cout, H, Wd, stats_out=None, second=None):
             tc = self._temb_cols.get(prefix) if temb_table is not None else None
             a = conv_gn_act(f"{prefix}.block1", inputs, W_[f"{prefix}.block1.conv"], cmid, H, Wd, W_[f"{prefix}.block1.norm"], temb_col=tc)
-            return conv_gn_act(f"{prefix}.block2", [a], W_[f"{prefix}.block2.conv"], cout, H, Wd, W_[f"{prefix}.block2.norm"], stats_out=stats_out)
+            return conv_gn_act(f"{prefix}.block2", [a], W_[f"{prefix}.block2.conv"], cout, H, Wd, W_[f"{prefix}.block2.norm"],
+                               stats_out=stats_out, second=second)
 
-        def attention(prefix, x: Act, c, H, Wd, heads, st_in):
-            """x <- x + (Wp Wo) softmax(q k^T/sqrt(d)) v + b, q,k,v = in_proj(GN(x))  (blocks.py:209-235)."""
+        def double_attention(prefix_d, prefix_a, inputs, c, H, Wd, heads):
+            """DoubleBlock followed by the level's SelfAttention (if any); their two norms share a launch when fusable."""
+            if heads is None:
+                return double(prefix_d, inputs, c, c, H, Wd)
+            if fuse_small and not sp and H * Wd * c <= 65536 and 1024 % (c // 8) == 0:
+                xn = new_act(N, 1, H, Wd, c, dev, sp)
+                g2, b2 = W_[f"{prefix_a}.norm"]
+                x = double(prefix_d, inputs, c, c, H, Wd, second=(f"{prefix_a}.gn", xn, g2, b2))
+                return attention(prefix_a, x, c, H, Wd, heads, None, xn=xn)
+            st_attn = stats_view(stats_alloc(1), N * 2)
+            x = double(prefix_d, inputs, c, c, H, Wd, stats_out=st_attn)
+            return attention(prefix_a, x, c, H, Wd, heads, st_attn)
+
+        def attention(prefix, x: Act, c, H, Wd, heads, st_in, xn=None):
+            """x <- x + (Wp Wo) softmax(q k^T/sqrt(d)) v + b, q,k,v = in_proj(GN(x))  (blocks.py:209-235).
+            xn given: the pre-norm GN(x) was already written by the producer's fused launch."""
             T = H * Wd
             g, b = W_[f"{prefix}.norm"]
-            xn = new_act(N, 1, H, Wd, c, dev, sp)
-            prog.add(f"{prefix}.gn", lambda s: engine.gn_apply(x, xn, st_in, c, g, b, False, s),
-                     op=("gn", x, xn, st_in, c, g, b, False, None, None, 0, 0, None, 1e-5))
+            if xn is None:
+                xn = new_act(N, 1, H, Wd, c, dev, sp)
+                prog.add(f"{prefix}.gn", lambda s: engine.gn_apply(x, xn, st_in, c, g, b, False, s),
+                         op=("gn", x, xn, st_in, c, g, b, False, None, None, 0, 0, None, 1e-5))
             qkv = new_act(N, 1, H, Wd, 3 * c, dev, sp)
             p1 = ConvPlan([xn], W_[f"{prefix}.in_proj"], qkv, cout=3 * c)
             prog.add(f"{prefix}.in_proj", p1.run, op=("conv", p1))
@@ -221,14 +252,17 @@ class B200UNet:
         H, Wd = h, w
         for lvl, c in enumerate(f):
             heads = self._heads[lvl]
-            st_attn = stats_view(stats_alloc(1), N * 2) if heads is not None else None
-            x = double(f"encoder.{lvl}.0", [x], c, c, H, Wd, stats_out=st_attn)
-            if heads is not None:
-                x = attention(f"encoder.{lvl}.1", x, c, H, Wd, heads, st_attn)
+            x = double_attention(f"encoder.{lvl}.0", f"encoder.{lvl}.1", [x], c, H, Wd, heads)
             skips.append(x)
             pooled = new_act(N, 1, H // 2, Wd // 2, c, dev, sp)
-            st = stats_view(stats_alloc(1), N * 2)
             g, b = W_[f"encoder.{lvl}.2.norm"]
+            if fuse_small and engine.fused_gn_ok(x, (H // 2) * (Wd // 2) * c):
+                prog.add(f"encoder.{lvl}.2.pool+gn", lambda s, x=x, pooled=pooled, g=g, b=b: engine.maxpool_gn(x, pooled, g, b, True, s),
+                         op=("unsupported", "maxpool_gn"))
+                x = pooled
+                H, Wd = H // 2, Wd // 2
+                continue
+            st = stats_view(stats_alloc(1), N * 2)
             prog.add(f"encoder.{lvl}.2.pool", lambda s, x=x, pooled=pooled, st=st: engine.maxpool_stats(x, pooled, st, s),
                      op=("pool", x, pooled, st))
             prog.add(f"encoder.{lvl}.2.gn", lambda s, pooled=pooled, st=st, g=g, b=b, c=c: engine.gn_apply(pooled, pooled, st, c, g, b, True, s),
@@ -241,10 +275,7 @@ class B200UNet:
             up = conv_gn_act(f"decoder.{lvl}.0", [x], W_[f"decoder.{lvl}.0.conv"], c, H, Wd, W_[f"decoder.{lvl}.0.norm"], nphase=4)
             H, Wd = H * 2, Wd * 2
             heads = rheads[lvl]
-            st_attn = stats_view(stats_alloc(1), N * 2) if heads is not None else None
-            x = double(f"decoder.{lvl}.1", [skips[nl - 1 - lvl], up], c, c, H, Wd, stats_out=st_attn)
-            if heads is not None:
-                x = attention(f"decoder.{lvl}.2", x, c, H, Wd, heads, st_attn)
+            x = double_attention(f"decoder.{lvl}.1", f"decoder.{lvl}.2", [skips[nl - 1 - lvl], up], c, H, Wd, heads)
         pf = ConvPlan([x], W_["final_conv"], eps_out, cout=self.out_channels, out_mode=eps_mode,
                       out_cstride=self.out_channels)
         prog.flops += pf.flops

@@ -157,6 +157,17 @@ B2D_API int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo, i
 B2D_API int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int32_t H, int32_t W,
                          int32_t C, double* stats, void* stream);
 
+/* Per-sample fused forms for small maps (one CTA per sample; a sample of at most 65536 elements, one GroupNorm group,
+ * C/8 dividing 1024; bf16 channels-last, no hi/lo split).  B2D_E_UNSUPPORTED otherwise -- the caller uses the two-launch form.
+ *   b2d_gn_gn_apply:   y1 = act1(GN(x; stats1, gamma1, beta1)),  y2 = act2(GN(y1; gamma2, beta2))  -- the last norm of a
+ *                      DoubleBlock followed by the attention pre-norm (unet/blocks.py:37-47, 192, 214); x may alias y1.
+ *   b2d_maxpool2x2_gn: y = act(GN(maxpool2x2(x); gamma, beta))  -- Down (unet/blocks.py:161-174). */
+B2D_API int b2d_gn_gn_apply(const void* x, int32_t in_f16, void* y1, void* y2, int32_t N, int64_t P, int32_t C, const double* stats1,
+                    const float* gamma1, const float* beta1, float eps1, int32_t act1, const float* gamma2, const float* beta2,
+                    float eps2, int32_t act2, void* stream);
+B2D_API int b2d_maxpool2x2_gn(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, const float* gamma, const float* beta,
+                      float eps, int32_t act, void* stream);
+
 /* nearest-neighbour (1,2,2) upsample, nn.Upsample (vae/decoder.py:46,58). bf16 NDHWC, ND = N*D. */
 B2D_API int b2d_upsample2x_nearest(const void* x, void* y, int32_t ND, int32_t H, int32_t W, int32_t C, void* stream);
 

@@ -16,7 +16,7 @@ def test_chain_matches_program(N):
     torch.set_grad_enabled(False)
     h = 64  # the chain needs the full latent size: its attention items are the tensor-core ones (T >= 16 tokens)
     m = B200UNet(**synth.UNET_KWARGS, device="cuda").load_state_dict(synth.synth_unet_state(seed=0))
-    st = m.build_program(N, h, h)
+    st = m.build_program(N, h, h, fuse_small=False)
     g = torch.Generator().manual_seed(3)
     st["x_in"].hi.copy_(torch.randn(N, 1, h, h, 64, generator=g).to(torch.bfloat16))
     st["x_in"].hi[..., 17:] = 0

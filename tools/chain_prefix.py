@@ -6,7 +6,7 @@ from diffusion_model_project_b200.unet import B200UNet
 torch.set_grad_enabled(False)
 k = int(sys.argv[1]); f0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 m = B200UNet(**synth.UNET_KWARGS, device="cuda").load_state_dict(synth.synth_unet_state(seed=0))
-st = m.build_program(4, 64, 64)
+st = m.build_program(4, 64, 64, fuse_small=False)
 st["x_in"].hi.copy_(torch.randn(4, 1, 64, 64, 64, device="cuda").to(torch.bfloat16))
 prog = st["program"]
 names = [n for n, _ in prog.steps]

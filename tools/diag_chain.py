@@ -15,7 +15,7 @@ h = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 torch.set_grad_enabled(False)
 m = B200UNet(**synth.UNET_KWARGS, device="cuda").load_state_dict(synth.synth_unet_state(seed=0))
-st = m.build_program(N, h, h)
+st = m.build_program(N, h, h, fuse_small=False)
 st["x_in"].hi.copy_(torch.randn(N, 1, h, h, 64, device="cuda").to(torch.bfloat16))
 st["x_in"].hi[..., 17:] = 0
 prog = st["program"]

@@ -52,3 +52,15 @@ for n, t in zip(names, acc):
     k = n.rsplit(".", 1)[-1]
     kinds[k] = kinds.get(k, 0.0) + t
 print({k: round(v, 1) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1])})
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    prog.run(torch.cuda.current_stream().cuda_stream)
+for _ in range(3):
+    g.replay()
+torch.cuda.synchronize()
+a.record()
+for _ in range(reps * 4):
+    g.replay()
+b.record()
+torch.cuda.synchronize()
+print(f"graph-replayed step: {a.elapsed_time(b) * 1e3 / (reps * 4):.1f} us ({len(names)} launches)")
