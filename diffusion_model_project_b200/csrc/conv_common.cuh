@@ -147,7 +147,10 @@ __device__ __forceinline__ void warp_transpose_sum(float (&vals)[V], int lane) {
 // belong to `32 / seg` different samples).
 template <int BLOCK_N, int CW, bool SMEM_STATS, class Loader>
 __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const EpiRow& rw, int co_base, int lane, int seg,
-                                                  double* sm_stats, Loader&& load, double* thr_acc = nullptr) {
+                                                  double* sm_stats, Loader&& load, double* thr_acc = nullptr,
+                                                  uint32_t sm_bias = 0u) {
+  // sm_bias != 0: shared-memory address of the tile's BLOCK_N bias values (staged by the caller while it waited for the
+  // accumulator; zero beyond cout) -- a global bias load after the TMEM wait exposed a full L2 round trip per chunk
   const int cpg = p.stats_cpg;
   const int groups_per_n = (cpg > 0) ? (p.cout / cpg) : 0;
   float run_s = 0.f, run_ss = 0.f;
@@ -175,14 +178,28 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const Ep
   };
   float mask_v = 1.f;
   if (p.out_mode == 1 && p.out_mask != nullptr && valid) mask_v = p.out_mask[rw.opix];
+  // residual: requested BEFORE the accumulator load so that its L2 round trip overlaps the TMEM load and wait
+  const bool has_res = p.residual != nullptr && valid;
+  const uint4* res_row = has_res ? reinterpret_cast<const uint4*>(p.residual + rw.opix * p.res_cstride + co_base) : nullptr;
 
 #pragma unroll 1
   for (int col0 = 0; col0 < BLOCK_N; col0 += CW) {
+    uint4 rcur[CW / 8];
+    if (has_res) {
+#pragma unroll
+      for (int q = 0; q < CW / 8; ++q) rcur[q] = __ldg(res_row + col0 / 8 + q);
+    }
     float f[CW];
     load(col0, f);
     const int co0 = co_base + col0;
     const bool full = co0 + CW <= p.cout;
-    if (p.bias != nullptr) {
+    if (p.bias != nullptr && sm_bias != 0u) {
+#pragma unroll
+      for (int q = 0; q < CW / 4; ++q) {
+        const float4 b = lds128f(sm_bias + (uint32_t)(col0 + 4 * q) * 4u);
+        f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
+      }
+    } else if (p.bias != nullptr) {
       if (full) {
 #pragma unroll
         for (int q = 0; q < CW / 4; ++q) {
@@ -195,12 +212,11 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const Ep
           if (co0 + j < p.cout) f[j] += __ldg(p.bias + co0 + j);
       }
     }
-    if (p.residual != nullptr && valid) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rw.opix * p.res_cstride + co0);
+    if (has_res) {
       if (p.res_f16) {
 #pragma unroll
         for (int q = 0; q < CW / 8; ++q) {
-          const uint4 u = __ldg(rp + q);
+          const uint4 u = rcur[q];
           const float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
           f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
           f[q * 8 + 4] += c.x; f[q * 8 + 5] += c.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
@@ -208,7 +224,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const Ep
       } else {
 #pragma unroll
         for (int q = 0; q < CW / 8; ++q) {
-          const uint4 u = __ldg(rp + q);
+          const uint4 u = rcur[q];
           f[q * 8 + 0] += bf16_lo(u.x); f[q * 8 + 1] += bf16_hi(u.x);
           f[q * 8 + 2] += bf16_lo(u.y); f[q * 8 + 3] += bf16_hi(u.y);
           f[q * 8 + 4] += bf16_lo(u.z); f[q * 8 + 5] += bf16_hi(u.z);

@@ -30,7 +30,8 @@ struct V2Cfg {
   static constexpr int BP_WARP = HALO ? 2 + EPI_WARPS + XF_WARPS : -1;  // halo: the weight ring has its own producer warp
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (HALO ? 32 : 0);
   static constexpr int NBARS = 3 * NA + 2 * NB + 4;
-  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 * EPI_WARPS + (XFORM ? 2 * XF_MAXC * 4 + 16 : 0) + 1024;
+  static constexpr int BIAS_BYTES = MT * BN * 4;                // per four-warp epilogue group: the tile's bias
+  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 * EPI_WARPS + (XFORM ? 2 * XF_MAXC * 4 + 16 : 0) + BIAS_BYTES + 16 + 1024;
   static_assert(NACC * ACC_COLS <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static_assert(!HALO || 9 % TPB == 0, "taps per stage must divide 9");
@@ -122,6 +123,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
   volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [MT]
   double* sm_stats = reinterpret_cast<double*>(tmem_slot + 4);               // [EPI_WARPS][64] per-warp GroupNorm sums (halo mode)
   float* sm_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_stats + 64 * Cfg::EPI_WARPS) + 15) & ~uintptr_t(15));  // XFORM: [2][XF_MAXC] scale, shift
+  float* sm_bias = sm_coef + (XFORM ? 2 * Cfg::XF_MAXC : 0);  // [MT][BN], 16-byte aligned
 
   // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -362,6 +364,17 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
       rw.img = (long long)on * p.D + oz;
       rw.opix = (rw.img * p.out_H + rw.out_y) * p.out_W + rw.out_x;
 
+      // stage the tile's bias in shared memory while the accumulator is still being produced (first barrier: every warp
+      // of the group is done with the previous unit's values; second: the new ones are visible)
+      uint32_t sm_bias_u = 0u;
+      if (p.bias != nullptr) {
+        float* sb = sm_bias + mt * BN;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        for (int i = (threadIdx.x - 64) & 127; i < BN; i += 128) sb[i] = (co_base + i < p.cout) ? __ldg(p.bias + co_base + i) : 0.f;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        sm_bias_u = smem_u32(sb);
+      }
+
       mbar_wait(&t_full[acc], accph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + mt * Cfg::BNC);
@@ -373,7 +386,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
       };
       if (p.ksplit == 1) {
-        conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, one_group ? thr_acc : nullptr);
+        conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, one_group ? thr_acc : nullptr, sm_bias_u);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
@@ -417,7 +430,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
               }
             }
           };
-          conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, one_group ? thr_acc : nullptr);
+          conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, one_group ? thr_acc : nullptr, sm_bias_u);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // last_flag is reused by the next unit
       }

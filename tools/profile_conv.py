@@ -2,7 +2,8 @@
 tile variants and as the target of `ncu --set full -k regex:conv_`.
 usage: python tools/profile_conv.py kind N cin cout H [block_n] [engine] [reps]
   kind = 3d  : Conv3d 3x3x3 on [N][11][H][H][cin]   (VAE; default 8 128 128 256 = D3D res3 conv)
-  kind = 2d  : Conv2d 3x3 on [N][1][H][H][cin]      (UNet; e.g. 88 64 64 64 = encoder.0 block2)"""
+  kind = 2d  : Conv2d 3x3 on [N][1][H][H][cin]      (UNet; e.g. 88 64 64 64 = encoder.0 block2)
+  kind = 1x1 : Linear on [N][1][H][H][cin]          (UNet attention projections; e.g. 88 256 768 16 = enc2 in_proj)"""
 import os
 import sys
 
@@ -32,6 +33,11 @@ if kind == "3d":
     w = torch.randn(cout, cin, 3, 3, 3, generator=g) * (27 * cin) ** -0.5
     pw = engine.pack_conv3d(w, torch.zeros(cout), dev)
     groups = 32
+elif kind == "1x1":  # attention projections (UNet in_proj / out_proj): bias, no GroupNorm sums
+    w = torch.randn(cout, cin, generator=g) * cin ** -0.5
+    pw = engine.pack_linear(w, torch.zeros(cout), dev)
+    groups = 1
+    use_stats = 0
 else:
     w = torch.randn(cout, cin, 3, 3, generator=g) * (9 * cin) ** -0.5
     pw = engine.pack_conv2d(w, [cin], None, dev)
