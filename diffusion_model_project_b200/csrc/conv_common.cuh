@@ -145,10 +145,13 @@ __device__ __forceinline__ void warp_transpose_sum(float (&vals)[V], int lane) {
 // are CAS loops and serialise badly); the kernel pushes them to global memory when the
 // sample changes.  Otherwise sums go straight to global memory with fp64 atomics (rows of a warp may
 // belong to `32 / seg` different samples).
-template <int BLOCK_N, int CW, bool SMEM_STATS, class Loader>
+template <int BLOCK_N, int CW, bool SMEM_STATS, bool STAGE = false, class Loader>
 __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const EpiRow& rw, int co_base, int lane, int seg,
                                                   double* sm_stats, Loader&& load, double* thr_acc = nullptr,
-                                                  uint32_t sm_bias = 0u) {
+                                                  uint32_t sm_bias = 0u, uint32_t sm_stage = 0u) {
+  // sm_stage != 0: shared-memory address of this warp's 2 KB staging tile.  16-bit channels-last stores then go through
+  // it so that four lanes write one row's 64 contiguous bytes (full 32-byte sectors) instead of every lane writing 16
+  // bytes of its own row -- thin-K layers (1x1 projections, transposed convs) were bound by those partial-sector stores.
   // sm_bias != 0: shared-memory address of the tile's BLOCK_N bias values (staged by the caller while it waited for the
   // accumulator; zero beyond cout) -- a global bias load after the TMEM wait exposed a full L2 round trip per chunk
   const int cpg = p.stats_cpg;
@@ -181,6 +184,19 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const Ep
   // residual: requested BEFORE the accumulator load so that its L2 round trip overlaps the TMEM load and wait
   const bool has_res = p.residual != nullptr && valid;
   const uint4* res_row = has_res ? reinterpret_cast<const uint4*>(p.residual + rw.opix * p.res_cstride + co_base) : nullptr;
+
+  const bool stage = STAGE && CW == 32 && sm_stage != 0u && p.out_mode == 0 && p.out_lo == nullptr;  // warp-uniform
+  long long st_base[4] = {0, 0, 0, 0};
+  uint32_t st_ok = 0u;
+  if constexpr (STAGE) if (stage) {
+    const long long my_base = rw.opix * p.out_cstride + p.out_coff + co_base;  // 16-bit elements
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int src = it * 8 + (lane >> 2);
+      st_base[it] = __shfl_sync(0xffffffffu, my_base, src);
+      st_ok |= (uint32_t)__shfl_sync(0xffffffffu, (int)valid, src) << it;
+    }
+  }
 
 #pragma unroll 1
   for (int col0 = 0; col0 < BLOCK_N; col0 += CW) {
@@ -303,7 +319,34 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const Ep
       }
     }
     // ---- store -------------------------------------------------------------------------------
-    if (valid) {
+    bool staged = false;
+    if constexpr (STAGE && CW == 32) {
+      if (stage && full) {
+        uint32_t w[16];
+        if (p.out_f16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_f16_sat(f[2 * j], f[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+        }
+        // row-per-lane in, 16-byte slots XOR-swizzled so that both phases are bank-conflict free
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          sts128(sm_stage + (uint32_t)(lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)), make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
+        __syncwarp();
+        uint16_t* ob = reinterpret_cast<uint16_t*>(p.out);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + (lane >> 2), vec = lane & 3;
+          const uint4 v = lds128(sm_stage + (uint32_t)(row * 64 + ((vec ^ ((row >> 1) & 3)) << 4)));
+          if ((st_ok >> it) & 1u) reinterpret_cast<uint4*>(ob + st_base[it] + col0)[vec] = v;
+        }
+        __syncwarp();
+        staged = true;
+      }
+    }
+    if (valid && !staged) {
       if (p.out_mode == 0) {
         __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + rw.opix * p.out_cstride + p.out_coff + co0;
         uint32_t w[CW / 2];

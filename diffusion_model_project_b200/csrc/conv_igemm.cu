@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_igemm_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
     };
-    conv_epilogue_row<BLOCK_N, CW, false>(p, rw, co_base, lane, seg, nullptr, load_tmem);
+    conv_epilogue_row<BLOCK_N, CW, false, false>(p, rw, co_base, lane, seg, nullptr, load_tmem);
   }
 
   tc_fence_before();

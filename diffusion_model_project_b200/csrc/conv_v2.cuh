@@ -30,8 +30,9 @@ struct V2Cfg {
   static constexpr int BP_WARP = HALO ? 2 + EPI_WARPS + XF_WARPS : -1;  // halo: the weight ring has its own producer warp
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (HALO ? 32 : 0);
   static constexpr int NBARS = 3 * NA + 2 * NB + 4;
+  static constexpr int STAGE_BYTES = HALO ? 0 : 2048 * EPI_WARPS; // generic tiles: per-warp store staging (coalesced 16-bit stores)
   static constexpr int BIAS_BYTES = MT * BN * 4;                // per four-warp epilogue group: the tile's bias
-  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 * EPI_WARPS + (XFORM ? 2 * XF_MAXC * 4 + 16 : 0) + BIAS_BYTES + 16 + 1024;
+  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 * EPI_WARPS + (XFORM ? 2 * XF_MAXC * 4 + 16 : 0) + BIAS_BYTES + STAGE_BYTES + 16 + 1024;
   static_assert(NACC * ACC_COLS <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static_assert(!HALO || 9 % TPB == 0, "taps per stage must divide 9");
@@ -124,6 +125,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
   double* sm_stats = reinterpret_cast<double*>(tmem_slot + 4);               // [EPI_WARPS][64] per-warp GroupNorm sums (halo mode)
   float* sm_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_stats + 64 * Cfg::EPI_WARPS) + 15) & ~uintptr_t(15));  // XFORM: [2][XF_MAXC] scale, shift
   float* sm_bias = sm_coef + (XFORM ? 2 * Cfg::XF_MAXC : 0);  // [MT][BN], 16-byte aligned
+  uint8_t* sm_stage = reinterpret_cast<uint8_t*>(sm_bias + MT * BN);  // [EPI_WARPS][2048], generic tiles only
 
   // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -307,6 +309,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
     constexpr bool SMEM_STATS = HALO;
     int cur_n = -1;
     const int epi_tid = threadIdx.x - 64;
+    const uint32_t sm_stage_u = HALO ? 0u : smem_u32(sm_stage + ew * 2048);
     // one group per sample (the UNet's GroupNorm(1, C)): per-thread fp64 sums live in registers across the units of a
     // sample and meet the other lanes only when the sample changes
     const bool one_group = SMEM_STATS && p.stats_cpg >= p.cout && p.stats_cpg > 0;
@@ -386,7 +389,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
       };
       if (p.ksplit == 1) {
-        conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, one_group ? thr_acc : nullptr, sm_bias_u);
+        conv_epilogue_row<BN, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, one_group ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
@@ -430,7 +433,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
               }
             }
           };
-          conv_epilogue_row<BN, CW, SMEM_STATS>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, one_group ? thr_acc : nullptr, sm_bias_u);
+          conv_epilogue_row<BN, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, one_group ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // last_flag is reused by the next unit
       }
