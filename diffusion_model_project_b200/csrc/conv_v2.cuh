@@ -338,6 +338,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         }
       }
     };
+    int bias_cobase = -1;
     for (int u = uw.u; u < uw.end; u += uw.step) {
       const UnitCoord uc = decode_unit(p, u);
       if constexpr (SMEM_STATS) {
@@ -368,13 +369,17 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
       rw.opix = (rw.img * p.out_H + rw.out_y) * p.out_W + rw.out_x;
 
       // stage the tile's bias in shared memory while the accumulator is still being produced (first barrier: every warp
-      // of the group is done with the previous unit's values; second: the new ones are visible)
+      // of the group is done with the previous unit's values; second: the new ones are visible); units of one CTA often
+      // share their N tile, then the staged values are simply kept
       uint32_t sm_bias_u = 0u;
       if (p.bias != nullptr) {
         float* sb = sm_bias + mt * BN;
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
-        for (int i = (threadIdx.x - 64) & 127; i < BN; i += 128) sb[i] = (co_base + i < p.cout) ? __ldg(p.bias + co_base + i) : 0.f;
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        if (co_base != bias_cobase) {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+          for (int i = (threadIdx.x - 64) & 127; i < BN; i += 128) sb[i] = (co_base + i < p.cout) ? __ldg(p.bias + co_base + i) : 0.f;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+          bias_cobase = co_base;
+        }
         sm_bias_u = smem_u32(sb);
       }
 
