@@ -313,7 +313,21 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
     // one group per sample (the UNet's GroupNorm(1, C)): per-thread fp64 sums live in registers across the units of a
     // sample and meet the other lanes only when the sample changes
     const bool one_group = SMEM_STATS && p.stats_cpg >= p.cout && p.stats_cpg > 0;
+    // generic tiles whose warps each lie inside one image (>= 32 rows per image): the same, flushed per warp
+    const bool one_group_w = !SMEM_STATS && p.stats_cpg >= p.cout && p.stats_cpg > 0 && seg == 32;
+    int cur_on = -1;
     double thr_acc[2] = {0.0, 0.0};
+    auto flush_warp = [&]() {
+      if (cur_on >= 0 && cur_on < p.N) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          thr_acc[0] += __shfl_xor_sync(0xffffffffu, thr_acc[0], off);
+          thr_acc[1] += __shfl_xor_sync(0xffffffffu, thr_acc[1], off);
+        }
+        if (lane < 2) atomicAdd(p.stats + (long long)cur_on * 2 + lane, lane == 0 ? thr_acc[0] : thr_acc[1]);
+      }
+      thr_acc[0] = 0.0; thr_acc[1] = 0.0;
+    };
     auto flush_stats = [&]() {
       if constexpr (SMEM_STATS) {
         if (p.stats_cpg > 0) {
@@ -357,6 +371,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         oz = uc.z0 + ((r >> (p.lbw + p.lbh)) & md);
         on = uc.n0 + (r >> (p.lbw + p.lbh + p.lbd));
       }
+      if (one_group_w && on != cur_on) { flush_warp(); cur_on = on; }
       EpiRow rw;
       rw.valid = ox < p.OW && oy < p.OH && oz < p.D && on < p.N;
       rw.on = on;
@@ -394,7 +409,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
       };
       if (p.ksplit == 1) {
-        conv_epilogue_row<BN, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, one_group ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
+        conv_epilogue_row<BN, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
@@ -438,12 +453,13 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
               }
             }
           };
-          conv_epilogue_row<BN, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, one_group ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
+          conv_epilogue_row<BN, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // last_flag is reused by the next unit
       }
       if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
     }
+    if (one_group_w) flush_warp();
     flush_stats();
   } else if constexpr (XFORM) {
     // ================================ A-tile transform =====================================

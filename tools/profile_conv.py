@@ -33,6 +33,10 @@ if kind == "3d":
     w = torch.randn(cout, cin, 3, 3, 3, generator=g) * (27 * cin) ** -0.5
     pw = engine.pack_conv3d(w, torch.zeros(cout), dev)
     groups = 32
+elif kind == "convT":  # ConvTranspose2d k2 s2 (UNet Up): 4 phase GEMMs, bias, GroupNorm(1, C) sums
+    w = torch.randn(cin, cout, 2, 2, generator=g) * cin ** -0.5
+    pw = engine.pack_convT2x2(w, torch.zeros(cout), dev)
+    groups = 1
 elif kind == "1x1":  # attention projections (UNet in_proj / out_proj): bias, no GroupNorm sums
     w = torch.randn(cout, cin, generator=g) * cin ** -0.5
     pw = engine.pack_linear(w, torch.zeros(cout), dev)
@@ -42,9 +46,11 @@ else:
     w = torch.randn(cout, cin, 3, 3, generator=g) * (9 * cin) ** -0.5
     pw = engine.pack_conv2d(w, [cin], None, dev)
     groups = 1
-out = new_act(N, D, H, H, cout, dev)
+up = 2 if kind == "convT" else 1
+out = new_act(N, D, H * up, H * up, cout, dev, f16=(kind == "convT"))
 st = torch.zeros(N, groups, 2, dtype=torch.float64, device=dev)
-plan = ConvPlan([x], pw, out, cout=cout, stats=st if use_stats else None, stats_cpg=cout // groups if use_stats else 0, block_n=bn, engine=eng)
+plan = ConvPlan([x], pw, out, cout=cout, nphase=4 if kind == "convT" else 1, stats=st if use_stats else None,
+                stats_cpg=cout // groups if use_stats else 0, block_n=bn, engine=eng)
 s = torch.cuda.current_stream().cuda_stream
 for _ in range(2):
     plan.run(s)
