@@ -8,4 +8,6 @@ python tools/profile_stages.py 8 3 > gpurun_out/r1_stages_eventtimes_final.txt 2
 python tools/profile_scheduler.py > gpurun_out/r1_scheduler.txt 2>&1
 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_for_ncu.json 2> gpurun_out/bench_for_ncu.err && \
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r1_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+python tools/profile_unet.py 88 5 > gpurun_out/r1_unet_step_eventtimes_final.txt 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv --log-file gpurun_out/r1_launches_unet_step_warm.csv python tools/profile_unet.py 88 1 nograph > gpurun_out/ncu_unet.log 2>&1
 ls -la gpurun_out | tail -5
