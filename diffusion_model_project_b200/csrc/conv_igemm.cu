@@ -300,7 +300,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
       double per_group = (halo ? 2.0 * gt : 1.0) * t_kb;
       if (d->in_stats && per_group < 6000.0) per_group = 6000.0;  // fused input normalisation: the tile rewrite bounds a group
       for (int ks = 1; ks <= 16; ++ks) {
-        if (ks > 1 && (!can_split || ngroups / ks < 4 || tiles * mt > 4096 || tiles >= 2LL * sms ||
+        if (ks > 1 && (!can_split || ngroups / ks < 4 || tiles * 2 > 4096 || tiles >= 2LL * sms ||
                        16384 + tiles * ks * mt * 128LL * b * 4 > d->workspace_bytes)) break;
         // split-K fix-up: park the fp32 partial (coalesced), fence + ticket, and the last arriver re-reads ks partials
         const double fix = ks > 1 ? 6000.0 + (1.0 + ks) * 12.0 * b * mt : 0.0;

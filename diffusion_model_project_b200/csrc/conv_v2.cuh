@@ -24,7 +24,11 @@ struct V2Cfg {
   static constexpr int NACC = 2 * ACC_COLS <= 512 ? 2 : 1;       // BN = 256 halo: 512 columns, single-buffered
   static constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : NACC * ACC_COLS <= 64 ? 64 : NACC * ACC_COLS <= 128 ? 128
                                    : NACC * ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int EPI_WARPS = 4 * MT;
+  // generic tiles: two four-warp epilogue groups split the tile's columns (two warps per scheduler hide each other's
+  // TMEM-load / store latencies; thin-K layers are epilogue-bound)
+  static constexpr int NCG = (!HALO && BN >= 64) ? 2 : 1;
+  static constexpr int BNG = BN / NCG;                            // columns one epilogue group handles
+  static constexpr int EPI_WARPS = 4 * MT * NCG;
   static constexpr int XF_WARPS = XFORM ? 4 : 0;                 // warps rewriting staged A tiles (GroupNorm + SiLU)
   static constexpr int XF_MAXC = 512;                            // input channels the coefficient table holds
   static constexpr int BP_WARP = HALO ? 2 + EPI_WARPS + XF_WARPS : -1;  // halo: the weight ring has its own producer warp
@@ -121,7 +125,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
   uint64_t* t_full = b_empty + NB;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [MT]
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [epilogue groups <= 2]
   double* sm_stats = reinterpret_cast<double*>(tmem_slot + 4);               // [EPI_WARPS][64] per-warp GroupNorm sums (halo mode)
   float* sm_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_stats + 64 * Cfg::EPI_WARPS) + 15) & ~uintptr_t(15));  // XFORM: [2][XF_MAXC] scale, shift
   float* sm_bias = sm_coef + (XFORM ? 2 * Cfg::XF_MAXC : 0);  // [MT][BN], 16-byte aligned
@@ -297,7 +301,10 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
   } else if (warp < 2 + Cfg::EPI_WARPS) {
     // ================================ epilogue ==============================================
     const int ew = warp - 2;
-    const int mt = ew >> 2;      // M half handled by this group of four warps
+    const int grp = ew >> 2;                 // four-warp epilogue group
+    const int mt = HALO ? grp : 0;           // halo: the M half this group handles
+    const int col_off = HALO ? 0 : grp * Cfg::BNG;  // generic: its share of the tile's columns
+    constexpr int BNG = Cfg::BNG;
     const int quad = warp & 3;   // TMEM lane quadrant this warp may read
     const int r = quad * 32 + lane;
     const int rpi_log = HALO ? 7 : (p.lbw + p.lbh + p.lbd);
@@ -378,6 +385,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
       const int gcol0 = uc.gcol0 * BN;
       int phase_idx = 0, co_base = gcol0;
       if (p.nphase > 1) { phase_idx = gcol0 / p.cout; co_base = gcol0 - phase_idx * p.cout; }
+      co_base += col_off;
       rw.out_y = oy * p.out_sy + p.out_oy + ((p.nphase > 1) ? (phase_idx >> 1) : 0);
       rw.out_x = ox * p.out_sx + p.out_ox + ((p.nphase > 1) ? (phase_idx & 1) : 0);
       rw.img = (long long)on * p.D + oz;
@@ -388,11 +396,11 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
       // share their N tile, then the staged values are simply kept
       uint32_t sm_bias_u = 0u;
       if (p.bias != nullptr) {
-        float* sb = sm_bias + mt * BN;
+        float* sb = sm_bias + grp * BNG;
         if (co_base != bias_cobase) {
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
-          for (int i = (threadIdx.x - 64) & 127; i < BN; i += 128) sb[i] = (co_base + i < p.cout) ? __ldg(p.bias + co_base + i) : 0.f;
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          for (int i = (threadIdx.x - 64) & 127; i < BNG; i += 128) sb[i] = (co_base + i < p.cout) ? __ldg(p.bias + co_base + i) : 0.f;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           bias_cobase = co_base;
         }
         sm_bias_u = smem_u32(sb);
@@ -400,7 +408,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
 
       mbar_wait(&t_full[acc], accph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + mt * Cfg::BNC);
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + mt * Cfg::BNC + col_off);
       auto load_tmem = [&](int col0, float (&f)[CW]) {
         uint32_t v[32];
         if constexpr (CW == 32) tmem_ld_32x32(taddr + col0, v); else tmem_ld_32x16(taddr + col0, v);
@@ -409,7 +417,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
       };
       if (p.ksplit == 1) {
-        conv_epilogue_row<BN, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
+        conv_epilogue_row<BNG, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
@@ -418,26 +426,27 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         // partial tile layout [column quad][row][4 floats]: a warp's 16-byte accesses cover 512 contiguous bytes
         float4* wq = reinterpret_cast<float4*>(p.ws + (((long long)uc.tile * p.ksplit + uc.ks) * MT + mt) * (128LL * BN)) + r;
 #pragma unroll 1
-        for (int col0 = 0; col0 < BN; col0 += CW) {
+        for (int col0 = 0; col0 < BNG; col0 += CW) {
           float f[CW];
           load_tmem(col0, f);
 #pragma unroll
           for (int q = 0; q < CW / 4; ++q)
-            __stcg(wq + (col0 / 4 + q) * 128, make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]));
+            __stcg(wq + ((col_off + col0) / 4 + q) * 128, make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]));
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
         __threadfence();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         if ((threadIdx.x & 127) == 64) {  // first thread of this four-warp group (warps 2.. start at thread 64)
-          const int old = atomicAdd(p.counters + uc.tile * MT + mt, 1);
+          int* ctr = p.counters + (uc.tile * MT + mt) * Cfg::NCG + (HALO ? 0 : grp);  // one ticket per (tile, M half, column group)
+          const int old = atomicAdd(ctr, 1);
           const int last = (old == p.ksplit - 1) ? 1 : 0;
-          if (last) p.counters[uc.tile * MT + mt] = 0;  // self-reset for the next launch
-          last_flag[mt] = last;
+          if (last) *ctr = 0;  // self-reset for the next launch
+          last_flag[grp] = last;
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");
-        if (last_flag[mt]) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (last_flag[grp]) {
           __threadfence();
           const float4* wbase = reinterpret_cast<const float4*>(p.ws + (((long long)uc.tile * p.ksplit) * MT + mt) * (128LL * BN)) + r;
           const long long ks_stride = (long long)MT * 32 * BN;  // float4 units between the partials of consecutive splits
@@ -445,7 +454,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
 #pragma unroll
             for (int j = 0; j < CW; ++j) f[j] = 0.f;
             for (int ks = 0; ks < p.ksplit; ++ks) {
-              const float4* src = wbase + ks * ks_stride + (col0 / 4) * 128;
+              const float4* src = wbase + ks * ks_stride + ((col_off + col0) / 4) * 128;
 #pragma unroll
               for (int q = 0; q < CW / 4; ++q) {
                 const float4 v = __ldcg(src + q * 128);
@@ -453,9 +462,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
               }
             }
           };
-          conv_epilogue_row<BN, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
+          conv_epilogue_row<BNG, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + mt) : "memory");  // last_flag is reused by the next unit
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // last_flag is reused by the next unit
       }
       if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
     }
