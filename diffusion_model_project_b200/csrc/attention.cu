@@ -236,11 +236,10 @@ static int launch_attention_tc(const void* qkv, void* out, int N, int T, int C, 
   const int rc = attention_tc_params(qkv, out, N, T, C, heads, &p);
   if (rc != B2D_OK) return rc;
   const size_t smem = attention_tc_smem(T, C, heads);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static unsigned long long configured = 0;
+  {
+    cudaError_t e = smem_attr_once(attention_tc_kernel, 227 * 1024, configured);
     if (e != cudaSuccess) return set_error(B2D_E_CUDA, "attention_tc smem attr: %s", cudaGetErrorString(e));
-    configured = true;
   }
   dim3 grid((T + 127) / 128, N * heads);
   launch_pdl(attention_tc_kernel, grid, dim3(kTcThreads), smem, st, p);
@@ -274,12 +273,11 @@ extern "C" int b2d_attention(const void* qkv, const void* qkv_lo, void* out, voi
   dim3 grid((T + kQB - 1) / kQB, N * heads);
   const float scale = 1.0f / sqrtf((float)d);
   // opt in to the full dynamic shared-memory carve-out once per kernel variant (not a stream operation)
-  static bool configured[2] = {false, false};
-  if (!configured[split ? 1 : 0]) {
-    cudaError_t e = split ? cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)
-                          : cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  static unsigned long long configured[2] = {0, 0};
+  {
+    cudaError_t e = split ? smem_attr_once(attention_kernel<true>, 226 * 1024, configured[1])
+                          : smem_attr_once(attention_kernel<false>, 226 * 1024, configured[0]);
     if (e != cudaSuccess) return set_error(B2D_E_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
-    configured[split ? 1 : 0] = true;
   }
   if (split) {
     attention_kernel<true><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(

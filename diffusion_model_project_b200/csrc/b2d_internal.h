@@ -24,4 +24,16 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: opt in once per (kernel, device).
+// `mask` is the caller's static per-kernel bit set (bit = device ordinal; devices >= 64 simply set it every time).
+template <typename F>
+inline cudaError_t smem_attr_once(F kernel, int bytes, unsigned long long& mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && ((mask >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) mask |= 1ull << dev;
+  return e;
+}
 }  // namespace b2d

@@ -424,12 +424,11 @@ extern "C" int b2d_chain_bind(b2d_chain* c, void* dev_ops, int64_t dev_bytes, in
 extern "C" int b2d_chain_run(const b2d_chain* c, void* stream) {
   if (!c || !c->dev) return set_error(B2D_E_INVALID, "chain not bound");
   if (c->nops_bound == 0) return B2D_OK;
-  static bool configured = false;
+  static unsigned long long configured = 0;
   const size_t smem = kChainSmem;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = smem_attr_once(chain_kernel, (int)smem, configured);
     if (e != cudaSuccess) return set_error(B2D_E_CUDA, "chain smem attr: %s", cudaGetErrorString(e));
-    configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)num_sms()); cfg.blockDim = dim3(kChainThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;

@@ -201,14 +201,11 @@ template <int BN, int ST, int MINB>
 static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
   constexpr int smem = ST * (kABytes + BN * kBlockK * 2) + 1024 + 256;
   static_assert(MINB * (smem + 1024) <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  cudaError_t e = smem_attr_once(conv_igemm_kernel<BN, ST, MINB>, smem, configured);
+  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
   conv_igemm_kernel<BN, ST, MINB><<<grid, kThreads, smem, st>>>(kp);
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
   return B2D_OK;
 }

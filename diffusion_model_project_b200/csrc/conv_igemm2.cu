@@ -34,13 +34,10 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
 template <int BN, bool HALO, bool XFORM = false>
 static int launch_v2(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
   using Cfg = V2Cfg<BN, HALO, XFORM>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_v2_kernel<BN, HALO, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
-    configured = true;
-  }
-  cudaError_t e = launch_pdl(conv_v2_kernel<BN, HALO, XFORM>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM, st, kp);
+  static unsigned long long configured = 0;
+  cudaError_t e = smem_attr_once(conv_v2_kernel<BN, HALO, XFORM>, Cfg::SMEM, configured);
+  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
+  e = launch_pdl(conv_v2_kernel<BN, HALO, XFORM>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM, st, kp);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "conv_v2 launch: %s", cudaGetErrorString(e));
   return B2D_OK;
