@@ -10,4 +10,6 @@ Pinning: the reference ships no golden vectors or known-answer tests for this pa
 oracle is pinned against outputs of the reference itself, generated in the build
 container by importing /root/reference (tests/golden/make_golden.py) and committed
 under tests/golden/*.npz, plus the scheduler known-answer values of SURVEY.md 8(c).
+`oracle/train.py` restates one UNet training step (the next row; no kernels yet) and is pinned
+the same way (tests/golden/make_train_golden.py -> train_step.npz).
 """

@@ -1,0 +1,79 @@
+"""Golden vectors for ONE UNet training step, produced by the UNMODIFIED reference modules
+imported from /root/reference: UNet (src/unet/models.py), DiffusionScheduler.q_sample (src/diffusion.py), the default
+criterion normalized_mse_loss_per_component (src/unet/metrics.py) and torch.optim.Adam as configured by train.py:144-148.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_train_golden.py
+
+Output (committed): tests/golden/train_step.npz -- loss, noise prediction, the L2 norm of every parameter gradient, a few
+full gradient tensors and their post-Adam parameter deltas.  Weights and inputs are regenerated from synth on both sides.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path[:0] = ["/root/reference", "/root/reference/Diffusion_model"]
+os.environ["PYTHONDONTWRITEBYTECODE"] = "1"
+sys.dont_write_bytecode = True
+
+from diffusion_model_project_b200 import synth  # noqa: E402
+
+FULL = ("final_conv.weight", "final_conv.bias", "encoder.0.0.block1.conv.weight", "encoder.0.0.time_mlp.1.weight",
+        "time_mlp.0.weight", "bottleneck.block2.norm.weight", "encoder.2.1.mha.in_proj_weight", "decoder.4.0.conv.weight",
+        "decoder.0.2.proj_out.bias")
+
+
+def train_inputs():
+    """Shared with tests/test_oracle_golden.py: N = 2 slices of a 32x32 latent (the smallest size five max-pools allow)."""
+    g = torch.Generator().manual_seed(31)
+    x_start = torch.randn(2, 8, 32, 32, generator=g)
+    cond = torch.randn(2, 8, 32, 32, generator=g)
+    feats = torch.rand(2, 1, 32, 32, generator=g)
+    noise = torch.randn(2, 8, 32, 32, generator=g)
+    t = torch.tensor([741, 12], dtype=torch.long)
+    return x_start, cond, feats, noise, t
+
+
+def main():
+    from src.unet.models import UNet
+    from src.diffusion import DiffusionScheduler
+    from src.unet.metrics import cost_function
+
+    torch.manual_seed(0)
+    unet = UNet(**synth.UNET_KWARGS)
+    unet.load_state_dict(synth.synth_unet_state(seed=0))
+    unet.train()  # dropout p = 0: identical to eval, but this is what helper.py:273 does
+    sch = DiffusionScheduler(1000, device="cpu")
+    criterion = cost_function("normalized_mse_loss_per_component")
+    opt = torch.optim.Adam(unet.parameters(), lr=1e-4, weight_decay=0.0)
+    x_start, cond, feats, noise, t = train_inputs()
+    before = {k: v.detach().clone() for k, v in unet.named_parameters()}
+    x_t = sch.q_sample(x_start, t, noise)
+    pred = unet(torch.cat([x_t, cond, feats], dim=1), t)
+    loss = criterion(output=pred, target=noise)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    out = {"loss": np.float64(loss.item()), "pred": pred.detach().numpy(), "t": t.numpy()}
+    names, norms = [], []
+    for k, p in unet.named_parameters():
+        names.append(k)
+        norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array(norms)
+    params = dict(unet.named_parameters())
+    for k in FULL:
+        out[f"grad::{k}"] = params[k].grad.numpy()
+        out[f"delta::{k}"] = (params[k].detach() - before[k]).numpy()
+    np.savez_compressed(os.path.join(HERE, "train_step.npz"), **out)
+    print("loss", loss.item(), "params", len(names), "max grad norm", max(norms))
+
+
+if __name__ == "__main__":
+    main()

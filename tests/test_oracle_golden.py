@@ -1,6 +1,7 @@
 """Pin the CPU oracle against vectors produced by the unmodified reference
 (tests/golden/make_golden.py) and the known-answer values of SURVEY.md section 8(c)."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -106,3 +107,48 @@ def test_predict_ddpm_vs_reference(golden_dir):
     out = opred.predict(usd, vsd, img, v2d, noise, zs, norm_factors=synth.NORM_FACTORS, num_timesteps=12)
     ref = torch.from_numpy(g["out"])
     assert ((out - ref).norm() / ref.norm()).item() <= 1e-4
+
+
+def test_training_step_vs_reference(golden_dir):
+    """SURVEY.md section 8 row f4 (next row): loss, noise prediction, parameter gradients and the Adam update of ONE UNet
+    training step, oracle (autograd through the functional oracle UNet + restated loss / Adam) against the unmodified
+    reference modules (tests/golden/make_train_golden.py)."""
+    import importlib.util
+    from oracle import train as otrain
+    spec = importlib.util.spec_from_file_location("make_train_golden", os.path.join(golden_dir, "make_train_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    saved = list(sys.path)
+    try:
+        spec.loader.exec_module(mod)  # only train_inputs() / FULL are used; the reference is not imported at module level
+    finally:
+        sys.path[:] = saved
+    g = _load(golden_dir, "train_step.npz")
+    sd = synth.synth_unet_state(seed=0)
+    x_start, cond, feats, noise, t = mod.train_inputs()
+    assert np.array_equal(t.numpy(), g["t"])
+    loss, grads, pred = otrain.training_loss_and_grads(sd, x_start, cond, feats, t, noise)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    ref_pred = torch.from_numpy(g["pred"])
+    assert (pred - ref_pred).abs().max().item() <= 2e-5 * ref_pred.abs().max().item()
+    names = [str(n) for n in g["grad_names"]]
+    assert set(names) == set(sd.keys())
+    for n, ref_norm in zip(names, g["grad_norms"]):
+        got = float(grads[n].double().norm())
+        assert abs(got - ref_norm) <= 2e-3 * max(ref_norm, 1e-6), (n, got, ref_norm)
+    for k in mod.FULL:
+        ref_g = torch.from_numpy(g[f"grad::{k}"])
+        assert (grads[k] - ref_g).abs().max().item() <= 2e-3 * max(ref_g.abs().max().item(), 1e-12), k
+        # the Adam restatement in isolation: reference gradient in, reference parameter delta out
+        p0 = sd[k]
+        p1, m, v = otrain.adam_step(p0, ref_g, torch.zeros_like(p0), torch.zeros_like(p0), step=1, lr=1e-4)
+        ref_d = torch.from_numpy(g[f"delta::{k}"])
+        assert ((p1 - p0) - ref_d).abs().max().item() <= 2e-8, k
+    # the loss restatement on its own, 5-D form and channel weights (metrics.py:362-396)
+    a = torch.randn(2, 3, 4, 5, 6, generator=torch.Generator().manual_seed(1))
+    b = torch.randn(2, 3, 4, 5, 6, generator=torch.Generator().manual_seed(2))
+    w = torch.tensor([1.0, 2.0, 0.5])
+    mse = ((a - b) ** 2).mean(dim=(-3, -2, -1)) / ((b ** 2).mean(dim=(-3, -2, -1)) + 1e-8)
+    want = (mse * w[None] / w.sum()).mean(dim=-1).mean()
+    assert torch.allclose(otrain.normalized_mse_loss_per_component(a, b, weight_per_channel=w), want, rtol=1e-6, atol=0)
+    with pytest.raises(ValueError):
+        otrain.normalized_mse_loss_per_component(a[0, 0], b[0, 0])
