@@ -285,6 +285,8 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     const bool can_split = !no_split && all_dz0 && d->workspace && (reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0;
     const int mt = halo ? 2 : 1;
     const int cand[4] = {256, 128, 64, 16};
+    const char* fks = getenv("B2D_CONV_KSPLIT");  // read per plan (not cached): a tuning knob, unset in production
+    const int force_ks = fks ? atoi(fks) : 0;
     double best = 1e30;
     int best_bn = 0;
     for (int ci = 0; ci < 4; ++ci) {
@@ -297,6 +299,8 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
       double per_group = (halo ? 2.0 * gt : 1.0) * t_kb;
       if (d->in_stats && per_group < 6000.0) per_group = 6000.0;  // fused input normalisation: the tile rewrite bounds a group
       for (int ks = 1; ks <= 16; ++ks) {
+        if (force_ks > 0 && ks < force_ks) continue;  // tools/tune_conv.py: measure a given split count
+        if (force_ks > 0 && ks > force_ks) break;
         if (ks > 1 && (!can_split || ngroups / ks < 4 || tiles * 2 > 4096 || tiles >= 2LL * sms ||
                        16384 + tiles * ks * mt * 128LL * b * 4 > d->workspace_bytes)) break;
         // split-K fix-up: park the fp32 partial (coalesced), fence + ticket, and the last arriver re-reads ks partials
@@ -307,7 +311,9 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
         if (cost < best * 0.999) { best = cost; best_bn = b; ksplit_pick = ks; }
       }
     }
-    if (best_bn == 0) return set_error(B2D_E_INVALID, "cout=%d block_n=%d: need cout a multiple of 64 (or <= 16)", d->cout, d->block_n);
+    if (best_bn == 0)
+      return set_error(B2D_E_INVALID, "cout=%d block_n=%d%s: need cout a multiple of 64 (or <= 16)", d->cout, d->block_n,
+                       force_ks > 0 ? " (B2D_CONV_KSPLIT not applicable to this layer)" : "");
     bn = best_bn;
   }
   if (bn == 0) {
