@@ -265,6 +265,18 @@ class B200LatentDiffusionPredictor:
             raise ValueError(f"shape mismatch: img {tuple(img.shape)} velocity_2d {tuple(velocity_2d.shape)}")
         return B, S, img.shape[3], img.shape[4]
 
+    def encode_target(self, velocity_3d: torch.Tensor, velocity_2d: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """predictor.py:1042-1085: 3D velocity target (B, S, 3, H, W) -> E3D latents (B, S, latent, H/4, W/4): permute to
+        (B, 3, S, H, W), MaxNormalizer (fused into the layout pass), deterministic E3D encoding (mu), permute back.
+        `velocity_2d` is unused, as in the reference."""
+        if velocity_3d.dim() != 5 or velocity_3d.shape[2] != 3:
+            raise ValueError(f"expected velocity_3d (batch, num_slices, 3, H, W), got {tuple(velocity_3d.shape)}")
+        if not velocity_3d.is_cuda:
+            raise RuntimeError("B200LatentDiffusionPredictor runs on a CUDA device only (no CPU fallback)")
+        x = velocity_3d.permute(0, 2, 1, 3, 4).contiguous().float()
+        mu, _ = self.vae.encode_3d_deterministic(x, div_scale=self.normalizer["output"].scale_factors)
+        return mu.permute(0, 2, 1, 3, 4)
+
     def predict_ddim(self, img, velocity_2d, num_steps: int = 50, eta: float = 0.0, noise=None, *, step_noise=None, record=None):
         """predictor.py:898-1023."""
         B, S, H, W = self._check_inputs(img, velocity_2d)

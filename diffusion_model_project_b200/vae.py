@@ -247,7 +247,8 @@ class B200DualVAE:
         return dict(program=bd.finish(), z_in=z_in, out=out, keep=bd.keep, stats=bd.stats_buf)
 
     # ------------------------------------------------------------------------------ module API
-    def _encode(self, branch: str, x: torch.Tensor):
+    def _encode(self, branch: str, x: torch.Tensor, div_scale: Optional[torch.Tensor] = None):
+        """div_scale (fp32 [C] on the device): divide channel c by div_scale[c] in the layout pass (MaxNormalizer fused)."""
         if branch not in self.branches:
             raise RuntimeError(f"B200DualVAE: no weights loaded for {branch}")
         if not x.is_cuda:
@@ -261,7 +262,7 @@ class B200DualVAE:
         s = _lib.stream_ptr()
         xi = st["x_in"]
         x = x.contiguous().float()
-        _lib.call("b2d_planar_to_cl", x.data_ptr(), _lib.ptr(xi.hi), _lib.ptr(xi.lo), B, C, D * H * W, xi.C, 0, None, s)
+        _lib.call("b2d_planar_to_cl", x.data_ptr(), _lib.ptr(xi.hi), _lib.ptr(xi.lo), B, C, D * H * W, xi.C, 0, _lib.ptr(div_scale), s)
         st["program"].run(s)
         o = st["out"].permute(0, 2, 1, 3, 4).contiguous()  # [B][D][16][h][w] -> (B,16,D,h,w)
         mu, logvar = torch.chunk(o, 2, dim=1)
@@ -276,9 +277,9 @@ class B200DualVAE:
         mu, logvar = self._encode("encoder_2d", x)
         return mu, (mu, torch.clamp(logvar, -10.0, 10.0))
 
-    def encode_3d_deterministic(self, x):
-        """dual_vae/model.py:235-243."""
-        mu, logvar = self._encode("encoder_3d", x)
+    def encode_3d_deterministic(self, x, *, div_scale: Optional[torch.Tensor] = None):
+        """dual_vae/model.py:235-243.  div_scale: optional per-channel divisor applied to x on the way in."""
+        mu, logvar = self._encode("encoder_3d", x, div_scale)
         return mu, (mu, torch.clamp(logvar, -10.0, 10.0))
 
     def decode_3d(self, z: torch.Tensor) -> torch.Tensor:

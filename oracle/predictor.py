@@ -42,6 +42,15 @@ def conditioning(vae_sd, img, velocity_2d, norm_factors, use_edt=True):
     return v_lat, f3.reshape(B * ld, 1, lh, lw)
 
 
+def encode_target(vae_sd, velocity_3d, norm_factors):
+    """predictor.py:1042-1085: (B,S,3,H,W) -> permute, MaxNormalizer (normalizer.py:46-51: x / s[c]), E3D mu, permute back
+    to (B,S,latent,H/4,W/4)."""
+    s = torch.tensor(norm_factors, dtype=torch.float32).view(1, -1, 1, 1, 1)
+    x = velocity_3d.permute(0, 2, 1, 3, 4) / s
+    mu, _ = ovae.encoder_forward(vae_sd, x, "encoder_3d.")
+    return mu.permute(0, 2, 1, 3, 4)
+
+
 def decode(vae_sd, x, B, img, norm_factors):
     """predictor.py:993-1021: reshape, D3D decode, denormalise, mask."""
     N, lc, lh, lw = x.shape

@@ -75,5 +75,28 @@ def main():
     print("loss", loss.item(), "params", len(names), "max grad norm", max(norms))
 
 
+def target_inputs():
+    """Shared with the tests: a 3D velocity target of 2 samples x 3 slices at 32x32, physical units."""
+    g = torch.Generator().manual_seed(37)
+    return torch.randn(2, 3, 3, 32, 32, generator=g) * torch.tensor(synth.NORM_FACTORS).view(1, 1, 3, 1, 1)
+
+
+def main_encode_target():
+    """LatentDiffusionPredictor.encode_target (predictor.py:1042-1085) of the unmodified
+    reference with the seeded E3D weights -> tests/golden/encode_target.npz."""
+    import tempfile
+    sys.path.insert(0, HERE)
+    from make_golden import build_reference_predictor
+    vsd = synth.synth_vae_state(seed=1, branches=("encoder_2d", "encoder_3d", "decoder_3d"))
+    with tempfile.TemporaryDirectory() as tmp:
+        pred = build_reference_predictor(tmp, num_slices=3)
+    pred.vae.encoder_3d.load_state_dict({k[len("encoder_3d."):]: v for k, v in vsd.items() if k.startswith("encoder_3d.")})
+    with torch.no_grad():
+        lat = pred.encode_target(target_inputs())
+    np.savez_compressed(os.path.join(HERE, "encode_target.npz"), latents=lat.numpy())
+    print("encode_target", tuple(lat.shape), lat.abs().max().item())
+
+
 if __name__ == "__main__":
     main()
+    main_encode_target()

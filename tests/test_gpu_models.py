@@ -215,6 +215,27 @@ def test_zfold_conv_out_and_zstack_conv_in_match_direct_convs(vae_sd, monkeypatc
     assert rel_l2(outs["zfold.mu"], outs["direct.mu"]) <= 1e-2
 
 
+def test_encode_target_vs_golden(unet_sd, golden_dir):
+    """`encode_target` (predictor.py:1042-1085: permute, MaxNormalizer, E3D mu, permute) against the
+    reference's own output (tests/golden/encode_target.npz) and the reference's error behaviour for a bad shape."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("make_train_golden", os.path.join(golden_dir, "make_train_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    saved = list(sys.path)
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path[:] = saved
+    vsd = synth.synth_vae_state(seed=1, branches=("encoder_2d", "encoder_3d", "decoder_3d"))
+    p = _predictor(unet_sd, vsd, "bf16", S=3)
+    lat = p.encode_target(mod.target_inputs().cuda()).cpu()
+    ref = torch.from_numpy(np.load(os.path.join(golden_dir, "encode_target.npz"))["latents"])
+    assert lat.shape == ref.shape and rel_l2(lat, ref) <= 1e-2
+    with pytest.raises(ValueError):
+        p.encode_target(torch.zeros(1, 3, 2, 32, 32, device="cuda"))
+
+
 def test_full_size_properties(unet_sd, vae_sd):
     """BASELINE.json's full size (11 slices of 256x256, the CPU oracle would take minutes): size-independent
     properties instead -- determinism across calls (graph replay), sample independence, exact zeros on solid voxels,

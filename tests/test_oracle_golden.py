@@ -152,3 +152,27 @@ def test_training_step_vs_reference(golden_dir):
     assert torch.allclose(otrain.normalized_mse_loss_per_component(a, b, weight_per_channel=w), want, rtol=1e-6, atol=0)
     with pytest.raises(ValueError):
         otrain.normalized_mse_loss_per_component(a[0, 0], b[0, 0])
+
+
+def _load_train_golden_module(golden_dir):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_train_golden", os.path.join(golden_dir, "make_train_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    saved = list(sys.path)
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path[:] = saved
+    return mod
+
+
+def test_encode_target_vs_reference(golden_dir):
+    """LatentDiffusionPredictor.encode_target (predictor.py:1042-1085) -- oracle restatement
+    against the unmodified reference with the seeded E3D weights (tests/golden/make_train_golden.py)."""
+    mod = _load_train_golden_module(golden_dir)
+    g = _load(golden_dir, "encode_target.npz")
+    vsd = synth.synth_vae_state(seed=1, branches=("encoder_2d", "encoder_3d", "decoder_3d"))
+    lat = opred.encode_target(vsd, mod.target_inputs(), synth.NORM_FACTORS)
+    ref = torch.from_numpy(g["latents"])
+    assert lat.shape == ref.shape == (2, 3, 8, 8, 8)
+    assert (lat - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
