@@ -7,9 +7,13 @@
 
 One "step" = one full `predict_ddim` (E2D encode -> 50 DDIM steps of the conditioned UNet -> D3D
 decode) over this rank's batch of synthetic 256x256x11 microstructures, bf16, random-init weights of
-the named architecture (no dataset/checkpoint is reachable offline).  Weak scaling: every rank owns
-`--batch-per-gpu` samples; no collective on the sampling path, one gather of the decoded fields at
-the end.  Prints ONE JSON line on rank 0.
+the named architecture (no dataset/checkpoint is reachable offline).  Default: weak scaling, every
+rank owns `--batch-per-gpu` samples (BASELINE configs[2]: 64 samples over 8 GPUs = 8 per GPU); the
+same line also carries `strong`: a FIXED global batch (`--strong-batch`, default 64 = configs[3], the
+"test-set-sized batch") sharded B/N per rank, micro-batched through the VAE on each GPU.
+`--global-batch G` makes that fixed batch the primary measurement (`"scaling": "strong"`).  No
+collective on the sampling path, one gather of the decoded fields at the end.  Prints ONE JSON line
+on rank 0.
 """
 from __future__ import annotations
 
@@ -40,6 +44,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=8)
+    ap.add_argument("--global-batch", type=int, default=0, help="fixed global batch sharded over the ranks (strong scaling) as the primary measurement")
+    ap.add_argument("--strong-batch", type=int, default=64, help="fixed global batch of the secondary `strong` object (0 = skip)")
+    ap.add_argument("--vae-chunk", type=int, default=8)
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x"])
     ap.add_argument("--size", type=int, default=256)
@@ -108,47 +115,37 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of predictor.predict_ddim on host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_sample(size: int, slices: int, ddim_steps: int, sample_slices: int = 3, unet_steps: int = 2):
-    """Time a bounded sample of the reference's CPU path (its own op sequence, predictor.py:898-1023,
-    including the shape-probe E2D pass on zeros, :916-925) and scale to one full prediction.
-    Returns (predictions_per_s, detail dict)."""
+_CPU_CASE = {}
+
+
+def cpu_reference_prediction(size: int, slices: int, ddim_steps: int):
+    """ONE full prediction of the reference's CPU path: its own op sequence (predictor.py:898-1023, including the
+    shape-probe E2D pass on zeros, :916-925) restated by the oracle, B = 1, all host cores, nothing scaled.
+    Returns (seconds, detail dict)."""
     import torch
     from diffusion_model_project_b200 import synth
-    from oracle import predictor as opred, unet as ounet, vae as ovae
-    from oracle.scheduler import OracleScheduler, ddim_timesteps
+    from oracle import predictor as opred, vae as ovae
 
     torch.set_grad_enabled(False)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    usd, vsd = synth.synth_unet_state(seed=0), synth.synth_vae_state(seed=1)
-    S = min(sample_slices, slices)
-    img, v2d = synth.synth_inputs(1, num_slices=S, size=size, seed=2024)
-    noise = synth.synth_noise(1, num_slices=S, latent_size=size // 4, seed=42)
+    key = (size, slices)
+    if key not in _CPU_CASE:
+        usd, vsd = synth.synth_unet_state(seed=0), synth.synth_vae_state(seed=1)
+        img, v2d = synth.synth_inputs(1, num_slices=slices, size=size, seed=2024)
+        noise = synth.synth_noise(1, num_slices=slices, latent_size=size // 4, seed=42)
+        _CPU_CASE[key] = (usd, vsd, img, v2d, noise)
+    usd, vsd, img, v2d, noise = _CPU_CASE[key]
     t0 = time.perf_counter()
-    ovae.encoder_forward(vsd, torch.zeros(1, 3, S, size, size), "encoder_2d.")           # predictor.py:916-925
+    ovae.encoder_forward(vsd, torch.zeros(1, 3, slices, size, size), "encoder_2d.")       # predictor.py:916-925
     t_probe = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    v_lat, feats = opred.conditioning(vsd, img, v2d, synth.NORM_FACTORS, use_edt=True)   # :927-962
-    t_cond = time.perf_counter() - t0
-    sch = OracleScheduler(1000)
-    ts = ddim_timesteps(1000, ddim_steps)
-    x = noise.reshape(v_lat.shape)
-    for i in range(unet_steps + 1):  # the first step is untimed: it pays one-off allocator / primitive-creation costs
-        if i == 1:
-            t0 = time.perf_counter()
-        tb = torch.full((x.shape[0],), ts[i], dtype=torch.long)
-        eps = ounet.unet_forward(usd, torch.cat([x, v_lat, feats], 1), tb)                # :982-985
-        x = sch.ddim_sample(eps, x, ts[i], ts[i + 1], 0.0, (-30.0, 30.0))                 # :988
-    t_unet = (time.perf_counter() - t0) / unet_steps
-    t0 = time.perf_counter()
-    opred.decode(vsd, x, 1, img, synth.NORM_FACTORS)                                      # :993-1021
-    t_dec = time.perf_counter() - t0
-    scale = slices / S
-    t_pred = (t_probe + t_cond + t_dec + ddim_steps * t_unet) * scale
-    detail = dict(cores=cores, threads=torch.get_num_threads(), t_probe_e2d_s=t_probe, t_conditioning_s=t_cond, t_unet_step_s=t_unet,
-                  t_decode_s=t_dec, sample=f"1 sample, {S} of {slices} slices at {size}x{size}, E2D probe + E2D + EDT + {unet_steps} (warm) of "
-                  f"{ddim_steps} DDIM steps + D3D timed; scaled linearly to {slices} slices and {ddim_steps} steps")
-    return 1.0 / t_pred, detail
+    out = opred.predict_ddim(usd, vsd, img, v2d, noise, num_steps=ddim_steps, eta=0.0, norm_factors=synth.NORM_FACTORS)
+    t_all = time.perf_counter() - t0
+    assert out.shape == (1, slices, 3, size, size)
+    detail = dict(cores=cores, threads=torch.get_num_threads(), t_probe_e2d_s=t_probe, t_prediction_s=t_all,
+                  sample=f"one full predict_ddim (E2D shape probe + E2D + EDT + {ddim_steps} DDIM steps + D3D), 1 sample of "
+                         f"{slices}x{size}x{size}, fp32, {cores} threads; nothing scaled")
+    return t_all, detail
 
 
 def run_reference(args):
@@ -156,22 +153,23 @@ def run_reference(args):
     if rank != 0:
         return
     t_all = time.perf_counter()
-    vals = []
+    times = []
     detail = None
-    for i in range(args.warmup + args.steps):
-        v, detail = cpu_reference_sample(args.size, args.slices, args.ddim_steps)
+    for i in range(args.warmup + args.steps):  # every step, warm-up included, is one full prediction
+        t, detail = cpu_reference_prediction(args.size, args.slices, args.ddim_steps)
         if i >= args.warmup:
-            vals.append(v)
-    val = statistics.mean(vals)
+            times.append(t)
+    sec = statistics.mean(times)
+    val = 1.0 / sec
     line = {
         "impl": "reference", "metric": "3D flow-field predictions/sec", "value": val, "unit": "predictions/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sec, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"predict_ddim DDIM-{args.ddim_steps} end to end (E2D -> UNet loop -> D3D), {args.size}x{args.size}x{args.slices}, "
-                               "reference op sequence on host CPU (oracle port; /root/reference is not present on the GPU box)"},
+        "config": workload_config(args),
+        "arm": {"samples_per_step": 1, "path": "reference op sequence on host CPU (oracle port; /root/reference is not present on the GPU box)"},
         "cpu_baseline": {"value": val, "unit": "predictions/s", "cores": detail["cores"], "kind": "port", "sample": detail["sample"]},
         "e2e": {"value": val, "unit": "predictions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "detail": {k: v for k, v in detail.items() if k != "sample"}, "wall_s": time.perf_counter() - t_all,
+        "detail": {k: v for k, v in detail.items() if k != "sample"}, "step_seconds": times, "wall_s": time.perf_counter() - t_all,
     }
     print(json.dumps(line), flush=True)
 
@@ -179,6 +177,14 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------------------
+def workload_config(args):
+    """The workload both arms are quoted on (identical dict in the two JSON lines); arm-specific run details go to `arm`."""
+    return {"workload": f"predict_ddim DDIM-{args.ddim_steps} end to end (E2D encode -> conditioned-UNet loop -> D3D decode) on synthetic "
+                        f"microstructures of {args.slices}x{args.size}x{args.size}, UNet in17/out8 k3 zeros-pad attn 3..2 + dual-branch VAE, "
+                        "random-init weights (BASELINE.json configs[2]/[3])",
+            "ddim_steps": args.ddim_steps, "slices": args.slices, "size": args.size}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -201,37 +207,15 @@ def run_b200(args):
 
     cpu_base = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
-        v, det = cpu_reference_sample(args.size, args.slices, args.ddim_steps)
-        cpu_base = {"value": v, "unit": "predictions/s", "cores": det["cores"], "kind": "port", "sample": det["sample"]}
+        sec, det = cpu_reference_prediction(args.size, args.slices, args.ddim_steps)
+        cpu_base = {"value": 1.0 / sec, "unit": "predictions/s", "cores": det["cores"], "kind": "port", "sample": det["sample"]}
 
-    B, S, H = args.batch_per_gpu, args.slices, args.size
+    S, H = args.slices, args.size
     usd, vsd = synth.synth_unet_state(seed=0), synth.synth_vae_state(seed=1)
     pred = B200LatentDiffusionPredictor("UNet", dict(synth.UNET_KWARGS), True, unet_state=usd, vae_state=vsd,
                                         norm_factors=synth.NORM_FACTORS, num_slices=S, num_timesteps=1000, precision=args.precision,
-                                        use_graph=not args.no_graph, device=dev)
+                                        use_graph=not args.no_graph, vae_chunk=args.vae_chunk, device=dev)
     del usd, vsd
-    # rank-local slice of the synthetic global batch (no communication)
-    img, v2d = synth.synth_inputs(B, num_slices=S, size=H, seed=2024 + rank)
-    noise = synth.synth_noise(B, num_slices=S, latent_size=H // 4, seed=42 + rank * B)
-    img_h, v2d_h, noise_h = img.pin_memory(), v2d.pin_memory(), noise.pin_memory()
-    img_d, v2d_d, noise_d = img.to(dev), v2d.to(dev), noise.to(dev)
-    out_h = torch.empty(B, S, 3, H, H, dtype=torch.float32).pin_memory()
-    h2d_bytes = img_h.numel() * 4 + v2d_h.numel() * 4 + noise_h.numel() * 4
-    d2h_bytes = out_h.numel() * 4
-
-    def step_resident():
-        out = pred.predict_ddim(img_d, v2d_d, num_steps=args.ddim_steps, eta=0.0, noise=noise_d)
-        return sharding.gather_predictions(out, B * world, dst=0) if world > 1 else out
-
-    def step_e2e():
-        a = img_h.to(dev, non_blocking=True)
-        b = v2d_h.to(dev, non_blocking=True)
-        c = noise_h.to(dev, non_blocking=True)
-        out = pred.predict_ddim(a, b, num_steps=args.ddim_steps, eta=0.0, noise=c)
-        if world > 1:
-            sharding.gather_predictions(out, B * world, dst=0)
-        out_h.copy_(out, non_blocking=True)
-        return out
 
     def sync_all():
         if world > 1:
@@ -259,17 +243,63 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), _lib.launch_count - l0, clocks
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    ms, launches, clocks = timed(step_resident, args.steps, ClockSampler(local))
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
-    ms_step = ms / args.steps
-    value = B * world / (ms_step / 1e3)
-    e2e_val = B * world / (ms_e2e / args.steps / 1e3)
+    def measure(global_batch, per_rank, warmup, steps, sampler=None):
+        """Whole-job throughput of `global_batch` samples per step: this rank's shard is `per_rank` samples (the rank-local
+        slice of the synthetic global batch, no communication).  Returns resident and end-to-end numbers."""
+        B = per_rank
+        lo = sum(sharding.shard_range(global_batch, r, world)[1] - sharding.shard_range(global_batch, r, world)[0] for r in range(rank))
+        img, v2d = synth.synth_inputs(B, num_slices=S, size=H, seed=2024 + lo)
+        noise = synth.synth_noise(B, num_slices=S, latent_size=H // 4, seed=42 + lo)
+        img_h, v2d_h, noise_h = img.pin_memory(), v2d.pin_memory(), noise.pin_memory()
+        img_d, v2d_d, noise_d = img.to(dev), v2d.to(dev), noise.to(dev)
+        n_out = global_batch if (world > 1 and rank == 0) else B  # rank 0 reads the GATHERED fields back at N > 1
+        out_h = torch.empty(n_out, S, 3, H, H, dtype=torch.float32).pin_memory()
+        h2d = (img_h.numel() + v2d_h.numel() + noise_h.numel()) * 4
+        d2h = out_h.numel() * 4
 
-    # ---- stage breakdown + rooflines (rank 0, measured live with CUDA events on the launch stream) ----
+        def step_resident():
+            out = pred.predict_ddim(img_d, v2d_d, num_steps=args.ddim_steps, eta=0.0, noise=noise_d)
+            return sharding.gather_predictions(out, global_batch, dst=0) if world > 1 else out
+
+        def step_e2e():
+            a = img_h.to(dev, non_blocking=True)
+            b = v2d_h.to(dev, non_blocking=True)
+            c = noise_h.to(dev, non_blocking=True)
+            out = pred.predict_ddim(a, b, num_steps=args.ddim_steps, eta=0.0, noise=c)
+            if world > 1:
+                out = sharding.gather_predictions(out, global_batch, dst=0)
+            if out is not None:
+                out_h.copy_(out, non_blocking=True)
+
+        for _ in range(warmup):
+            step_resident()
+        ms, launches, clocks = timed(step_resident, steps, sampler)
+        for _ in range(min(2, warmup)):
+            step_e2e()
+        ms_e2e, _, _ = timed(step_e2e, steps)
+        t_h2d = torch.tensor([float(h2d)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_h2d)  # whole-job H2D bytes per step
+        return dict(ms_per_step=ms / steps, value=global_batch / (ms / steps / 1e3), e2e_ms_per_step=ms_e2e / steps,
+                    e2e_value=global_batch / (ms_e2e / steps / 1e3), launches=launches, clocks=clocks,
+                    h2d_bytes=int(t_h2d.item()), d2h_bytes=int(d2h if world == 1 else global_batch * S * 3 * H * H * 4), per_rank=B)
+
+    # ---- primary measurement --------------------------------------------------------------------------------------
+    strong_primary = args.global_batch > 0
+    if strong_primary:
+        G = args.global_batch
+        lo, hi = sharding.shard_range(G, rank, world)
+        B = hi - lo
+        if B < 1:
+            raise SystemExit(f"--global-batch {G} leaves rank {rank} of {world} without a sample")
+    else:
+        B = args.batch_per_gpu
+        G = B * world
+    warm = max(args.warmup, 3)
+    m = measure(G, B, warm, args.steps, ClockSampler(local))
+    ms_step, value = m["ms_per_step"], m["value"]
+
+    # ---- stage breakdown + rooflines (measured live with CUDA events on the launch stream, primary session) ----------
     ses = pred._session
     s = _lib.stream_ptr()
 
@@ -283,12 +313,33 @@ def run_b200(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    t_e2d = time_launches(lambda: ses["e2d"]["program"].run(s), 3)
-    t_d3d = time_launches(lambda: ses["d3d"]["program"].run(s), 3)
-    t_unet = time_launches(lambda: pred._run_unet(ses, s), 10)
-    # dominant kernel: the tcgen05 implicit-GEMM conv engine (>= 85 % of the step's device time).  Its roofline
-    # launch is the heaviest single launch of the step (D3D conv_up: 3x3x3 on the upsampled map), timed alone with
-    # CUDA events on the launch stream -> burst peak.
+    nchunk = len(ses["starts"])
+    t_e2d = time_launches(lambda: [ses["e2d"]["program"].run(s, variant=i) for i in range(nchunk)], 3)
+    t_d3d = time_launches(lambda: [ses["d3d"]["program"].run(s, variant=i) for i in range(nchunk)], 3)
+    img_d, v2d_d = ses["img"].clone(), ses["v2d"].clone()
+    noise_d = torch.randn(ses["N"], 8, ses["h"], ses["w"], device=dev)
+    t_cond = time_launches(lambda: pred._conditioning(ses, img_d, v2d_d, s), 3)        # copies + E2D + EDT + bilinear
+    t_dec = time_launches(lambda: pred._decode(ses, s), 3)                               # D3D + the returned copy
+    # the UNet step exactly as the hot path runs it: replays of the captured timestep graph (UNet body + final_conv fused
+    # with the sampler update); one loop = ddim_steps replays from step index 0
+    graph = ses["graph"][1] if ses.get("graph") else None
+
+    def one_loop():
+        pred._set_latent(ses, noise_d, s)
+        ses["state"][0:2].zero_()
+        if graph is not None:
+            for _ in range(args.ddim_steps):
+                graph.replay()
+        else:
+            for _ in range(args.ddim_steps):
+                pred._one_step(ses, 1, ses["coef"], (-30.0, 30.0), s)
+    t_loop = time_launches(one_loop, 3)
+    t_set = time_launches(lambda: pred._set_latent(ses, noise_d, s), 3)
+    t_unet = (t_loop - t_set) / args.ddim_steps
+    stage_sum = t_cond + t_loop + t_dec
+    # dominant kernel: the tcgen05 implicit-GEMM conv engine (~80 % of the step's device time).  Its roofline launch is
+    # the heaviest single launch of the step (a D3D 3x3x3 conv), timed alone with CUDA events on the launch stream ->
+    # burst peak.
     dom, dom_name = None, ""
     for name, fn in ses["d3d"]["program"].steps:
         plan = getattr(fn, "__self__", None)
@@ -298,40 +349,75 @@ def run_b200(args):
     tc_ach = dom.flops / (t_dom * 1e-3) / 1e12
     di = dom.info2()
     dd = dom.desc
-    dom_label = (f"conv_v{di['engine']}_kernel<BN={di['block_n']},halo={di['halo']}> (D3D {dom_name}: {sum(dd.cin[i] for i in range(1))}->{dd.cout} "
-                 f"3x3x3 @ {B}x{dd.D}x{dd.H}x{dd.W}, timed alone: burst peak)")
+    dom_label = (f"conv_v2_kernel<BN={di['block_n']},halo={di['halo']}> (D3D {dom_name}: {dd.cin[0]}->{dd.cout} "
+                 f"3x3x3 @ {dd.N}x{dd.D}x{dd.H}x{dd.W}, timed alone: burst peak)")
     # DRAM bytes of that launch from the committed `ncu --set full` capture of the same shape (profiles/), if present
     traffic = None
-    shape_key = f"3d {B} {dd.cin[0]} {dd.cout} {dd.H}"
-    tpath = os.path.join(ROOT, "profiles", "r1_dominant_kernel_ncu.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if tj.get("shape", "").startswith(shape_key):
-            traffic = tj.get("dram_traffic_bytes")
+    shape_key = f"3d {dd.N} {dd.cin[0]} {dd.cout} {dd.H}"
+    for tname in ("r2_dominant_kernel_ncu.json", "r1_dominant_kernel_ncu.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("shape", "").startswith(shape_key):
+                traffic = tj.get("dram_traffic_bytes")
+                break
     # scheduler kernel on >= 64 samples' worth of latent (369 MB > L2) for an HBM-bound number
     n_el = ELEMS_PER_SAMPLE * 64
     xs, es, zs = (torch.randn(n_el, device=dev) for _ in range(3))
     coef = pred.scheduler._ddpm_table
     t_sched = time_launches(lambda: _lib.call("b2d_scheduler_step", 0, xs.data_ptr(), es.data_ptr(), zs.data_ptr(), xs.data_ptr(),
-                                              n_el, coef.data_ptr(), None, 500, 0, 1, -30.0, 30.0, None, 0, 0, 0, s), 20)
+                                              n_el, coef.data_ptr(), None, 500, 0, 1, -30.0, 30.0, None, 0, 0, 0, None, None, s), 20)
     hbm_ach = 16.0 * n_el / (t_sched * 1e-3) / 1e9
     del xs, es, zs
+    scale = (S / 11.0) * (H / 256.0) ** 2
+    unet_slices = ses["N"]
+
+    # ---- secondary: fixed global batch (strong scaling), micro-batched on each GPU -----------------------------------
+    strong = None
+    if not strong_primary and args.strong_batch > 0 and args.strong_batch >= world:
+        Gs = args.strong_batch
+        lo, hi = sharding.shard_range(Gs, rank, world)
+        Bs = hi - lo
+        if Bs == B and Gs == G:
+            sm = m  # the same configuration as the primary measurement (64 samples on 8 GPUs)
+            t_unet_s = t_unet
+        else:
+            sm = measure(Gs, Bs, 1, max(2, min(args.steps, 3)))
+            ses2 = pred._session
+            g2 = ses2["graph"][1] if ses2.get("graph") else None
+            nz = torch.randn(ses2["N"], 8, ses2["h"], ses2["w"], device=dev)
+
+            def loop2():
+                pred._set_latent(ses2, nz, s)
+                ses2["state"][0:2].zero_()
+                for _ in range(args.ddim_steps):
+                    g2.replay() if g2 is not None else pred._one_step(ses2, 1, ses2["coef"], (-30.0, 30.0), s)
+            t_unet_s = (time_launches(loop2, 2) - time_launches(lambda: pred._set_latent(ses2, nz, s), 2)) / args.ddim_steps
+        strong = {"scaling": "strong", "global_batch": Gs, "samples_per_gpu": sm["per_rank"], "value": sm["value"], "unit": "predictions/s",
+                  "ms_per_step": sm["ms_per_step"], "e2e": {"value": sm["e2e_value"], "unit": "predictions/s", "ms_per_step": sm["e2e_ms_per_step"],
+                                                           "h2d_bytes_per_step": sm["h2d_bytes"], "d2h_bytes_per_step": sm["d2h_bytes"]},
+                  "unet_step_ms": t_unet_s, "unet_slices_per_launch": sm["per_rank"] * S,
+                  "unet_tflops": sm["per_rank"] * FLOP_UNET_STEP * scale / (t_unet_s * 1e-3) / 1e12,
+                  "unet_frac_of_sustained_peak": sm["per_rank"] * FLOP_UNET_STEP * scale / (t_unet_s * 1e-3) / 1e12 / peaks["tc_sustained"],
+                  "vae_chunk": args.vae_chunk}
 
     if rank == 0:
-        flop_step = B * (FLOP_E2D + FLOP_D3D + args.ddim_steps * FLOP_UNET_STEP) * (S / 11.0) * (H / 256.0) ** 2
+        flop_step = B * (FLOP_E2D + FLOP_D3D + args.ddim_steps * FLOP_UNET_STEP) * scale
+        unet_tf = B * FLOP_UNET_STEP * scale / (t_unet * 1e-3) / 1e12
         line = {
             "metric": "3D flow-field predictions/sec", "value": value, "unit": "predictions/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong_primary else "weak",
+            "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-class hi/lo split)", "data": "synthetic",
-            "config": {"workload": f"predict_ddim DDIM-{args.ddim_steps} end to end (E2D encode -> conditioned-UNet loop -> D3D decode), "
-                                   f"{B} samples/GPU of {S}x{H}x{H}, UNet in17/out8 k3 zeros-pad attn 3..2, CUDA-graphed timestep loop, "
-                                   "random-init weights (BASELINE.json configs[2]/[3] shape, 8 samples per GPU)",
-                       "global_batch": B * world, "parallelism": f"batch-sharded x{world}, final gather only",
-                       "l2": "working set (>= 1.4 GB per activation tensor) far exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_val, "unit": "predictions/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
-            "clocks": clocks,
+            "config": workload_config(args),
+            "arm": {"samples_per_gpu": B, "global_batch": G, "parallelism": f"batch-sharded x{world}, final gather only",
+                    "loop": "CUDA-graphed timestep (UNet body + final_conv fused with the sampler update)" if graph is not None else "eager",
+                    "vae_chunk": args.vae_chunk,
+                    "l2": "working set (>= 1.4 GB per activation tensor) far exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": m["e2e_value"], "unit": "predictions/s", "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"],
+                    "ms_per_step": m["e2e_ms_per_step"]},
+            "gpu_launches": m["launches"],
+            "clocks": m["clocks"],
             "roofline": {"bound": "tensor", "achieved": tc_ach, "peak": peaks["tc_burst"], "unit": "TFLOP/s", "frac": tc_ach / peaks["tc_burst"],
                          "traffic": traffic, "kernel": dom_label,
                          "peak_source": peaks["src"], "flops_per_launch": dom.flops, "ms_per_launch": t_dom},
@@ -339,11 +425,16 @@ def run_b200(args):
                                    "bytes_per_launch": 16.0 * n_el, "ms_per_launch": t_sched,
                                    "note": "DDPM step with host noise, 16 B/element, 64 samples (369 MB > L2)"},
             "stages": {"e2d_ms": t_e2d, "unet_step_ms": t_unet, "d3d_ms": t_d3d,
-                       "e2d_tflops": B * FLOP_E2D * (S / 11.0) * (H / 256.0) ** 2 / (t_e2d * 1e-3) / 1e12,
-                       "unet_tflops": B * FLOP_UNET_STEP * (S / 11.0) * (H / 256.0) ** 2 / (t_unet * 1e-3) / 1e12,
-                       "d3d_tflops": B * FLOP_D3D * (S / 11.0) * (H / 256.0) ** 2 / (t_d3d * 1e-3) / 1e12,
+                       "unet_step_note": f"replayed timestep graph, {unet_slices} slice-images per launch",
+                       "conditioning_ms": t_cond, "loop_ms": t_loop, "decode_ms": t_dec, "sum_ms": stage_sum,
+                       "sum_over_ms_per_step": stage_sum / ms_step,
+                       "e2d_tflops": B * FLOP_E2D * scale / (t_e2d * 1e-3) / 1e12,
+                       "unet_tflops": unet_tf, "unet_frac_of_sustained_peak": unet_tf / peaks["tc_sustained"],
+                       "d3d_tflops": B * FLOP_D3D * scale / (t_d3d * 1e-3) / 1e12,
                        "step_tflops": flop_step / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop_step / (ms_step * 1e-3) / 1e12 / peaks["tc_sustained"]},
         }
+        if strong is not None:
+            line["strong"] = strong
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)

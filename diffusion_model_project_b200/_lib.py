@@ -9,6 +9,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2d.so")
 
+ABI_VERSION = 6
 B2D_MAX_SEG = 6
 B2D_MAX_TAPS = 27
 
@@ -43,20 +44,33 @@ class ConvDesc(C.Structure):
         ("out_scale", c_void_p), ("out_mask", c_void_p),
         ("block_n", c_i32),
         ("out_f16", c_i32), ("res_f16", c_i32),
-        ("engine", c_i32),
+        ("tune_ksplit", c_i32),
         ("workspace", c_void_p), ("workspace_bytes", c_i64),
         ("in_stats", c_void_p), ("in_gamma", c_void_p), ("in_beta", c_void_p),
         ("in_cpg", c_i32), ("in_creal", c_i32), ("in_f16", c_i32), ("in_act", c_i32),
         ("in_eps", c_float),
+        ("tune_flags", c_i32),
+        ("sched_kind", c_i32),
+        ("sched_x", c_void_p), ("sched_noise", c_void_p), ("sched_coef", c_void_p),
+        ("sched_step_idx", c_void_p), ("sched_ticket", c_void_p), ("sched_seed_dev", c_void_p),
+        ("sched_seed", c_u64),
+        ("sched_step_off", c_i32), ("sched_step_inc", c_i32),
+        ("sched_clip", c_i32),
+        ("sched_clip_lo", c_float), ("sched_clip_hi", c_float),
+        ("sched_x_bf16", c_void_p), ("sched_x_bf16_lo", c_void_p),
+        ("sched_bf16_stride", c_i32),
         ("reserved", c_i32 * 3),
     ]
+
+
+TUNE_NO_HALO, TUNE_NO_SPLITK, TUNE_CONTIG, TUNE_STRIDED = 1, 2, 4, 8
 
 
 _SIGNATURES = {
     "b2d_version": (c_int, []),
     "b2d_last_error": (C.c_char_p, []),
     "b2d_scheduler_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int,
-                                   c_int, c_float, c_float, c_void_p, c_int, c_int, c_u64, c_void_p]),
+                                   c_int, c_float, c_float, c_void_p, c_int, c_int, c_u64, c_void_p, c_void_p, c_void_p]),
     "b2d_q_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
     "b2d_conv_plan_create": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_void_p)]),
     "b2d_conv_plan_destroy": (c_int, [c_void_p]),
@@ -79,18 +93,6 @@ _SIGNATURES = {
     "b2d_zstack_cl": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_void_p]),
     "b2d_zfold_combine": (c_int, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
                           c_void_p]),
-    "b2d_chain_create": (c_int, [C.POINTER(c_void_p)]),
-    "b2d_chain_destroy": (c_int, [c_void_p]),
-    "b2d_chain_op_bytes": (c_i64, []),
-    "b2d_chain_num_ops": (c_i32, [c_void_p]),
-    "b2d_chain_add_conv": (c_int, [c_void_p, c_void_p]),
-    "b2d_chain_add_gn": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_i32, c_void_p, c_i32, c_void_p, c_void_p, c_float, c_i32,
-                                 c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32]),
-    "b2d_chain_add_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
-    "b2d_chain_add_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32]),
-    "b2d_chain_add_zero": (c_int, [c_void_p, c_void_p, c_i64]),
-    "b2d_chain_bind": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
-    "b2d_chain_run": (c_int, [c_void_p, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())
@@ -116,8 +118,8 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b2d_version() != 5:
-            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != 5; rebuild")
+        if l.b2d_version() != ABI_VERSION:
+            raise B2DError(f"libb2d.so ABI version {l.b2d_version()} != {ABI_VERSION}; rebuild")
         _lib = l
     return _lib
 

@@ -24,11 +24,6 @@ int check_launch(const char* what) {
   return B2D_OK;
 }
 
-bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("B2D_PDL"); return e ? atoi(e) != 0 : false; }();
-  return on;
-}
-
 int num_sms() {
   static int n = 0;
   if (n == 0) {

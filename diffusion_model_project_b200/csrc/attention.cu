@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
 __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw_attn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_attn) + 1023) & ~uintptr_t(1023));
-  attention_tc_item<false>(p, p, (int)blockIdx.x, (int)blockIdx.y, smem, 0u);
+  attention_tc_item(p, (int)blockIdx.x, (int)blockIdx.y, smem);
 }
 
 typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -242,7 +242,7 @@ static int launch_attention_tc(const void* qkv, void* out, int N, int T, int C, 
     if (e != cudaSuccess) return set_error(B2D_E_CUDA, "attention_tc smem attr: %s", cudaGetErrorString(e));
   }
   dim3 grid((T + 127) / 128, N * heads);
-  launch_pdl(attention_tc_kernel, grid, dim3(kTcThreads), smem, st, p);
+  attention_tc_kernel<<<grid, dim3(kTcThreads), smem, st>>>(p);
   return check_launch("attention_tc_kernel");
 }
 

@@ -1,5 +1,4 @@
-// Tensor-core attention core, device-side body (see attention.cu): shared by the stand-alone kernel and the
-// cross-layer chain kernel (conv_chain.cu).
+// Tensor-core attention core, device-side body (see attention.cu).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -23,16 +22,9 @@ struct AttnTcParams {
   float scale_log2e;
 };
 
-// One (image, head, 128-query tile) by 128 threads (threadIdx.x < 128 of the CTA).  `tm` = the copy of the parameters
-// whose TMA descriptor is addressed.  CHAINED (conv_chain.cu): TMEM is pre-allocated, the four mbarriers are created
-// and invalidated per item, and the 128 threads synchronise on named barrier 5 (the CTA has more warps).
-template <bool CHAINED>
-__device__ __forceinline__ void attn_sync() {
-  if constexpr (CHAINED) asm volatile("bar.sync 5, 128;" ::: "memory"); else __syncthreads();
-}
-template <bool CHAINED>
-__device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, const AttnTcParams& tm, int mtile, int nh, uint8_t* smem,
-                                                  uint32_t tmem_chain) {
+// One (image, head, 128-query tile) by the 128 threads of the CTA (`p` lives in the kernel's parameter space).
+__device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, int mtile, int nh, uint8_t* smem) {
+  const AttnTcParams& tm = p;
   const int T = p.T, d = p.d, C = p.C;
   const int dch = d >> 6;                     // 64-channel chunks per head
   const int kv_chunk = T * 128;               // bytes of one [T x 64] chunk tile
@@ -52,20 +44,14 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, const A
     fence_barrier_init();
     prefetch_tmap(&tm.tmap);
   }
-  if constexpr (!CHAINED) {
-    if (warp == 0) {
-      tmem_alloc(tmem_slot, kTcTmemCols);
-      tmem_relinquish();
-    }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, kTcTmemCols);
+    tmem_relinquish();
   }
   tc_fence_before();
-  attn_sync<CHAINED>();
+  __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = CHAINED ? tmem_chain : *tmem_slot;
-  if constexpr (!CHAINED) {
-    griddep_launch_dependents();
-    griddep_wait();
-  }
+  const uint32_t tmem_base = *tmem_slot;
 
   if (threadIdx.x == 0) {
     // ---- loads: Q tile + whole K on one barrier, whole V on another (lands while S is computed) ----
@@ -157,7 +143,7 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, const A
   const float inv = 1.f / sum;
   fence_proxy_async();  // P (generic-proxy stores) must be visible to the tensor core's async-proxy reads
   tc_fence_before();
-  attn_sync<CHAINED>();
+  __syncthreads();
 
   // ---- O[128 x d] = P V, at most 256 output columns per pass -------------------------------------
   const int DC = d < 256 ? d : 256;
@@ -198,13 +184,9 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, const A
       }
     }
     tc_fence_before();
-    attn_sync<CHAINED>();  // every row has drained O before the next pass overwrites it / before dealloc
+    __syncthreads();  // every row has drained O before the next pass overwrites it / before dealloc
   }
-  if constexpr (CHAINED) {
-    if (threadIdx.x == 0) for (int i = 0; i < 4; ++i) mbar_inval(&bars[i]);
-    tc_fence_after();
-    attn_sync<CHAINED>();
-  } else if (warp == 0) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTcTmemCols);
   }

@@ -10,20 +10,6 @@ int check_launch(const char* what);
 int num_sms();
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency); nullptr if unavailable.
 void* tensor_map_encode_fn();
-// Programmatic dependent launch (B2D_PDL=0 disables): the kernel may start while its stream predecessor is still
-// draining, runs its prologue (barrier init, TMEM allocation, descriptor prefetch) and blocks in
-// `griddepcontrol.wait` before its first access to global memory.  Only kernels that contain that wait use this.
-bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: opt in once per (kernel, device).
 // `mask` is the caller's static per-kernel bit set (bit = device ordinal; devices >= 64 simply set it every time).
 template <typename F>

@@ -38,8 +38,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 }
 
 // ------------------------------------------------------------------ programmatic dependent launch
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

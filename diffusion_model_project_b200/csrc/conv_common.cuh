@@ -1,5 +1,5 @@
-// Shared definitions of the implicit-GEMM conv engines (conv_igemm.cu: one tile per CTA; conv_igemm2.cu:
-// persistent, halo-staged, split-K): kernel parameter block, packing helpers and the fused epilogue.
+// Shared definitions of the implicit-GEMM conv engine (conv_plan.cu: planning; conv_engine.cu / conv_v2.cuh: the
+// persistent, halo-staged, split-K kernel): kernel parameter block, packing helpers and the fused epilogue.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -11,6 +11,7 @@
 #include "../../include/b2d.h"
 #include "b2d_internal.h"
 #include "b2d_ptx.cuh"
+#include "scheduler_math.cuh"
 
 namespace b2d {
 
@@ -35,6 +36,11 @@ struct FastDiv {
   __device__ __forceinline__ uint32_t div(uint32_t n) const { return d <= 1 ? n : (__umulhi(n, mul) >> shr); }
   __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
 };
+
+__device__ __forceinline__ uint32_t pack_bf16_(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
 struct ConvKParams {
   CUtensorMap tmapA[B2D_MAX_SEG];
@@ -64,7 +70,7 @@ struct ConvKParams {
   const float* out_mask;
   int skip_z;
   int out_f16, res_f16;
-  // ---- persistent engine (conv_igemm2.cu) ----
+  // ---- work units of the persistent kernel ----
   int halo;          // 1: one 18x18 halo box feeds the 9 in-plane taps of two 8x16 M=128 halves
   int ksplit;        // K-loop splits per output tile (fp32 partials in `ws`, last arriver reduces)
   int ngroups;       // A-operand loads in the K loop: nseg x (halo ? z-taps : taps) x 64-channel chunks
@@ -86,12 +92,71 @@ struct ConvKParams {
   int in_f16, in_act;          // raw values are fp16 (else bf16); apply SiLU
   float in_eps;
   double in_count;             // elements per (sample, group): in_cpg * D * H * W
+  // ---- out_mode 3: fused sampler update (b2d_conv_desc.sched_*) ----
+  float* sch_x;
+  const float* sch_noise;
+  const float* sch_coef;
+  int* sch_step;
+  unsigned int* sch_ticket;
+  const unsigned long long* sch_seed_dev;
+  unsigned long long sch_seed;
+  int sch_kind, sch_step_off, sch_step_inc, sch_clip;
+  float sch_lo, sch_hi;
+  __nv_bfloat16* sch_bf16;
+  __nv_bfloat16* sch_bf16_lo;
+  int sch_bf16_stride;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+// per-kernel constants of the fused sampler update (out_mode 3), loaded once by every epilogue thread
+struct SchedCtx {
+  Coef k;
+  unsigned long long seed;
+  int row;
+  bool use_noise;
+};
+__device__ __forceinline__ SchedCtx sched_ctx_load(const ConvKParams& p) {
+  SchedCtx sc;
+  sc.row = (p.sch_step ? *p.sch_step : 0) + p.sch_step_off;
+  sc.k = load_coef(p.sch_coef, sc.row);
+  sc.seed = p.sch_seed_dev ? *p.sch_seed_dev : p.sch_seed;
+  sc.use_noise = sc.k.s != 0.f;
+  return sc;
 }
+// One pixel's channels: eps = f[0 .. cout) -> x <- step(x, eps, z), in the operation order of scheduler_step_kernel
+// (element index = pixel * cout + c, Philox counter = element index / 4: the same noise as the stand-alone kernel).
+template <int CW>
+__device__ __forceinline__ void sched_update_row(const ConvKParams& p, const SchedCtx& sc, long long opix, const float (&f)[CW]) {
+  const int C = p.cout;
+  float* xr = p.sch_x + opix * C;
+#pragma unroll
+  for (int q = 0; q < CW / 4; ++q) {
+    if (4 * q < C) {
+      const float4 x = *reinterpret_cast<const float4*>(xr + 4 * q);
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sc.use_noise) {
+        if (p.sch_noise != nullptr) z = __ldg(reinterpret_cast<const float4*>(p.sch_noise + opix * C + 4 * q));
+        else z = philox_normal4((uint64_t)((opix * C) / 4 + q), (uint32_t)sc.row, sc.seed);
+      }
+      float4 o;
+      o.x = step_one(x.x, f[4 * q + 0], z.x, sc.k, p.sch_kind, p.sch_clip, p.sch_lo, p.sch_hi, sc.use_noise);
+      o.y = step_one(x.y, f[4 * q + 1], z.y, sc.k, p.sch_kind, p.sch_clip, p.sch_lo, p.sch_hi, sc.use_noise);
+      o.z = step_one(x.z, f[4 * q + 2], z.z, sc.k, p.sch_kind, p.sch_clip, p.sch_lo, p.sch_hi, sc.use_noise);
+      o.w = step_one(x.w, f[4 * q + 3], z.w, sc.k, p.sch_kind, p.sch_clip, p.sch_lo, p.sch_hi, sc.use_noise);
+      *reinterpret_cast<float4*>(xr + 4 * q) = o;
+      if (p.sch_bf16 != nullptr) {
+        const uint32_t w0 = pack_bf16_(o.x, o.y), w1 = pack_bf16_(o.z, o.w);
+        *reinterpret_cast<uint2*>(p.sch_bf16 + opix * p.sch_bf16_stride + 4 * q) = make_uint2(w0, w1);
+        if (p.sch_bf16_lo != nullptr) {
+          const uint32_t l0 = pack_bf16_(o.x - __uint_as_float(w0 << 16), o.y - __uint_as_float(w0 & 0xFFFF0000u));
+          const uint32_t l1 = pack_bf16_(o.z - __uint_as_float(w1 << 16), o.w - __uint_as_float(w1 & 0xFFFF0000u));
+          *reinterpret_cast<uint2*>(p.sch_bf16_lo + opix * p.sch_bf16_stride + 4 * q) = make_uint2(l0, l1);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) { return pack_bf16_(a, b); }
 // two fp32 -> packed IEEE fp16, saturating to +-65504 (raw pre-GroupNorm storage must never produce inf)
 __device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
   uint32_t r;
@@ -148,7 +213,7 @@ __device__ __forceinline__ void warp_transpose_sum(float (&vals)[V], int lane) {
 template <int BLOCK_N, int CW, bool SMEM_STATS, bool STAGE = false, class Loader>
 __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const EpiRow& rw, int co_base, int lane, int seg,
                                                   double* sm_stats, Loader&& load, double* thr_acc = nullptr,
-                                                  uint32_t sm_bias = 0u, uint32_t sm_stage = 0u) {
+                                                  uint32_t sm_bias = 0u, uint32_t sm_stage = 0u, const SchedCtx* sched = nullptr) {
   // sm_stage != 0: shared-memory address of this warp's 2 KB staging tile.  16-bit channels-last stores then go through
   // it so that four lanes write one row's 64 contiguous bytes (full 32-byte sectors) instead of every lane writing 16
   // bytes of its own row -- thin-K layers (1x1 projections, transposed convs) were bound by those partial-sector stores.
@@ -394,8 +459,11 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvKParams& p, const Ep
           }
         }
       } else {
+        // mode 3: the sampler update consumes eps right here; the fp32 eps store below is optional (p.out may be NULL)
+        if (p.out_mode == 3 && sched != nullptr) sched_update_row<CW>(p, *sched, rw.opix, f);
         float* op = reinterpret_cast<float*>(p.out) + rw.opix * p.out_cstride + p.out_coff + co0;
-        if (full) {
+        if (p.out == nullptr) {
+        } else if (full) {
 #pragma unroll
           for (int q = 0; q < CW / 4; ++q)
             reinterpret_cast<float4*>(op)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
@@ -424,11 +492,10 @@ struct b2d_conv_plan {
   dim3 grid;
   int block_n;
   int kblocks;
-  int engine;          // 1: conv_igemm.cu (one tile per CTA), 2: conv_igemm2.cu (persistent)
   long long ws_bytes;  // workspace bytes the plan uses (split-K partials + counters)
 };
 
 namespace b2d {
-// conv_igemm2.cu
+// conv_engine.cu
 int launch_conv_v2(const b2d_conv_plan* plan, cudaStream_t st);
 }  // namespace b2d

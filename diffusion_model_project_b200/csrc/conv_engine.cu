@@ -1,4 +1,5 @@
-// Persistent implicit-GEMM convolution engine for sm_100a (second generation of conv_igemm.cu).
+// Persistent implicit-GEMM convolution engine for sm_100a: TMA box loads (zero-filled halo == zero padding) ->
+// 128B-swizzled smem rings -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> fused epilogue.  Planning: conv_plan.cu.
 //
 // One CTA per SM walks a static list of work units (output tile x N tile x K split):
 //   warp 0      TMA producer   -- activation ring (A) and weight ring (B), separate mbarrier pairs
@@ -7,7 +8,7 @@
 //                                 unit's main loop runs: bias, residual, GroupNorm sums, store
 //
 // Two ways of staging the A operand:
-//   * generic: one 128-row box per (tap, 64-channel chunk), as in the first engine (any stride,
+//   * generic: one 128-row box per (tap, 64-channel chunk), (any stride,
 //     1x1 GEMMs, transposed-conv phases, small maps).
 //   * halo (stride-1 3x3 / 3x3x3, W,H multiples of 16): ONE TMA box of 18 x 18 pixels x 64 channels
 //     per (z-tap, chunk) serves all nine in-plane taps of a 16 x 16 output super-tile.  The tile is
@@ -28,7 +29,7 @@ template <int BN, bool HALO, bool XFORM>
 __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
-  conv_v2_layer<BN, HALO, XFORM, false>(p, p, smem, 0u);
+  conv_v2_layer<BN, HALO, XFORM>(p, smem);
 }
 
 template <int BN, bool HALO, bool XFORM = false>
@@ -37,8 +38,8 @@ static int launch_v2(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
   static unsigned long long configured = 0;
   cudaError_t e = smem_attr_once(conv_v2_kernel<BN, HALO, XFORM>, Cfg::SMEM, configured);
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(v2, smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
-  e = launch_pdl(conv_v2_kernel<BN, HALO, XFORM>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM, st, kp);
-  if (e == cudaSuccess) e = cudaGetLastError();
+  conv_v2_kernel<BN, HALO, XFORM><<<grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM, st>>>(kp);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "conv_v2 launch: %s", cudaGetErrorString(e));
   return B2D_OK;
 }

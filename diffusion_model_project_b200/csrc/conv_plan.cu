@@ -1,13 +1,6 @@
-// Implicit-GEMM convolution engine for sm_100a: TMA box loads (zero-filled halo == zero padding)
-// -> 128B-swizzled smem ring -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> fused epilogue
-// (bias, residual add, GroupNorm partial sums, layout/precision of the consumer).
-//
-// One CTA computes a 128 x BLOCK_N output tile: 128 output positions forming a box
-// (bn x bd x bh x bw) in (n, z, y, x), BLOCK_N output channels.  The K loop runs over
-// (channel segment, tap, 64-channel chunk); for each step the A operand is ONE 5-D TMA box load
-// of the activation tensor at the tap-shifted coordinates, the B operand one 2-D box of the
-// pre-packed weight matrix.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quadrant each).
+// Planning of the implicit-GEMM convolution engine for sm_100a (kernel: conv_v2.cuh / conv_engine.cu): validates a
+// b2d_conv_desc, picks the M tiling (halo super-tiles or generic 128-row boxes), BLOCK_N and the K split by a small cost
+// model, encodes the TMA descriptors and records the launch geometry.
 //
 // Replaces (reference file:line): nn.Conv2d unet/blocks.py:29-36, models.py:120-128;
 // nn.ConvTranspose2d unet/blocks.py:128-133; nn.Conv3d vae/blocks.py:155-169, encoder.py:30-68,
@@ -21,157 +14,6 @@
 
 namespace b2d {
 
-template <int BLOCK_N, int STAGES, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
-  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
-  constexpr int CW = BLOCK_N < 32 ? 16 : 32;  // epilogue column chunk
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates ------------------------------------------------------------------
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h; t /= p.tiles_h;
-  const int td = t % p.tiles_d; t /= p.tiles_d;
-  const int tn = t;
-  const int x0 = tw << p.lbw, y0 = th << p.lbh, z0 = td << p.lbd, n0 = tn << p.lbn;
-  const int gcol0 = blockIdx.y * BLOCK_N;  // row of the weight matrix
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&p.tmapA[s]);
-    prefetch_tmap(&p.tmapB);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ================================ TMA producer =========================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const int cch = p.cchunks[s];
-        for (int tp = 0; tp < p.ntaps; ++tp) {
-          const int zz = z0 + p.dz[tp];
-          if (p.skip_z && (zz < 0 || zz >= p.D)) continue;
-          const int xx = x0 * p.stride_w + p.dx[tp];
-          const int yy = y0 * p.stride_h + p.dy[tp];
-          const int kb = p.kbase[s] + tp * p.cin[s];
-          for (int c = 0; c < cch; ++c) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-            uint8_t* a_dst = smem + stage * kStageBytes;
-            tma_load_5d(a_dst, &p.tmapA[s], &full_bar[stage], c * kBlockK, xx, yy, zz, n0);
-            tma_load_2d(a_dst + kABytes, &p.tmapB, &full_bar[stage], kb + c * kBlockK, gcol0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ===========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t accum = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const int cch = p.cchunks[s];
-        for (int tp = 0; tp < p.ntaps; ++tp) {
-          const int zz = z0 + p.dz[tp];
-          if (p.skip_z && (zz < 0 || zz >= p.D)) continue;
-          for (int c = 0; c < cch; ++c) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-            const uint64_t adesc = umma_smem_desc(a_addr, 1024, 2);
-            const uint64_t bdesc = umma_smem_desc(a_addr + kABytes, 1024, 2);
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-              umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-              accum = 1;
-            }
-            umma_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-      umma_commit(tmem_full_bar);
-    }
-  } else {
-    // ================================ epilogue ==============================================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int r = quad * 32 + lane;
-    const int mw = (1 << p.lbw) - 1, mh = (1 << p.lbh) - 1, md = (1 << p.lbd) - 1;
-    const int ox = x0 + (r & mw);
-    const int oy = y0 + ((r >> p.lbw) & mh);
-    const int oz = z0 + ((r >> (p.lbw + p.lbh)) & md);
-    const int on = n0 + (r >> (p.lbw + p.lbh + p.lbd));
-    const bool valid = ox < p.OW && oy < p.OH && oz < p.D && on < p.N;
-
-    int phase_idx = 0, co_base = gcol0;
-    if (p.nphase > 1) { phase_idx = gcol0 / p.cout; co_base = gcol0 - phase_idx * p.cout; }
-    const int py = (p.nphase > 1) ? (phase_idx >> 1) : 0;
-    const int px = (p.nphase > 1) ? (phase_idx & 1) : 0;
-    const int out_y = oy * p.out_sy + p.out_oy + py;
-    const int out_x = ox * p.out_sx + p.out_ox + px;
-    const long long img = (long long)on * p.D + oz;
-    const long long opix = (img * p.out_H + out_y) * p.out_W + out_x;
-
-    const int rpi_log = p.lbw + p.lbh + p.lbd;  // rows per sample in the tile (log2)
-    const int seg = rpi_log >= 5 ? 32 : (1 << rpi_log);
-    EpiRow rw;
-    rw.valid = valid; rw.on = on; rw.img = img; rw.opix = opix; rw.out_y = out_y; rw.out_x = out_x;
-
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16);
-    auto load_tmem = [&](int col0, float (&f)[CW]) {
-      uint32_t v[32];
-      if constexpr (CW == 32) tmem_ld_32x32(taddr + col0, v); else tmem_ld_32x16(taddr + col0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
-    };
-    conv_epilogue_row<BLOCK_N, CW, false, false>(p, rw, co_base, lane, seg, nullptr, load_tmem);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-// ============================================================================================
-// host side
-// ============================================================================================
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -197,19 +39,6 @@ static int ilog2_ceil(int x) {
   return l;
 }
 
-template <int BN, int ST, int MINB>
-static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
-  constexpr int smem = ST * (kABytes + BN * kBlockK * 2) + 1024 + 256;
-  static_assert(MINB * (smem + 1024) <= 227 * 1024, "shared memory budget");
-  static unsigned long long configured = 0;
-  cudaError_t e = smem_attr_once(conv_igemm_kernel<BN, ST, MINB>, smem, configured);
-  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
-  conv_igemm_kernel<BN, ST, MINB><<<grid, kThreads, smem, st>>>(kp);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
-  return B2D_OK;
-}
-
 }  // namespace b2d
 
 using namespace b2d;
@@ -224,7 +53,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   if (d->stride_h < 1 || d->stride_h > 2 || d->stride_w < 1 || d->stride_w > 2)
     return set_error(B2D_E_INVALID, "stride must be 1 or 2");
   if (d->cout < 1 || (d->nphase != 1 && d->nphase != 4)) return set_error(B2D_E_INVALID, "bad cout/nphase");
-  if (!d->weight || !d->out) return set_error(B2D_E_INVALID, "null weight/out");
+  if (!d->weight || (!d->out && d->out_mode != 3)) return set_error(B2D_E_INVALID, "null weight/out");
   if (d->ktot % kBlockK) return set_error(B2D_E_INVALID, "ktot=%d must be a multiple of 64", d->ktot);
   for (int s = 0; s < d->nseg; ++s) {
     if (!d->in[s]) return set_error(B2D_E_INVALID, "null input segment %d", s);
@@ -243,17 +72,14 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   const long long tiles_m = (long long)((d->OW + (1 << lw) - 1) >> lw) * ((d->OH + (1 << lh) - 1) >> lh) *
                             ((d->D + (1 << ld) - 1) >> ld) * ((d->N + (1 << ln) - 1) >> ln);
 
-  // ---- engine selection -----------------------------------------------------------------------
-  static const int env_engine = [] { const char* e = getenv("B2D_CONV_ENGINE"); return e ? atoi(e) : 0; }();
-  const int engine = d->engine ? d->engine : (env_engine ? env_engine : 2);
-  if (engine != 1 && engine != 2) return set_error(B2D_E_INVALID, "engine=%d (0 auto, 1, 2)", engine);
+  if (d->tune_ksplit < 0 || d->tune_ksplit > 16) return set_error(B2D_E_INVALID, "tune_ksplit=%d (0 auto, 1..16)", d->tune_ksplit);
   // halo staging: canonical 3x3 / 3x3x3 'same' taps in (z, y, x) order, stride 1, 16x16 super-tiles, BLOCK_N <= 128
   bool halo = false;
   int gt = 0;  // in-plane taps per z group (taps are z-major): 9 = full 3x3, 4 = 2x2 of an upsample-folded conv
-  if (engine == 2 && d->stride_h == 1 && d->stride_w == 1 && d->nphase == 1 && d->ntaps >= 4 &&
+  if (d->stride_h == 1 && d->stride_w == 1 && d->nphase == 1 && d->ntaps >= 4 &&
       d->OW % 16 == 0 && d->OH % 16 == 0 && d->OW == d->W && d->OH == d->H && (d->cout <= 16 || d->cout % 64 == 0) &&
       (d->block_n == 0 || d->block_n == 16 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256)) {
-    static const bool no_halo = getenv("B2D_CONV_NO_HALO") != nullptr;
+    const bool no_halo = (d->tune_flags & B2D_TUNE_NO_HALO) != 0;
     while (gt < d->ntaps && d->tap_dz[gt] == d->tap_dz[0]) ++gt;
     halo = !no_halo && (gt == 9 || gt == 4) && d->ntaps % gt == 0;
     for (int t = 0; t < d->ntaps && halo; ++t) {
@@ -274,19 +100,18 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   // cost = waves over the SMs x (K-loop time of one unit + epilogue / split-K fix-up), in SM clocks.
   int bn = d->block_n;
   int ksplit_pick = 1;
-  if (engine == 2) {
+  {
     const int sms = num_sms();
     const long long cols = (long long)d->cout * d->nphase;
     long long ngroups = 0;
     for (int s = 0; s < d->nseg; ++s) ngroups += (long long)(halo ? d->ntaps / gt : d->ntaps) * (d->cin[s] / kBlockK);
     bool all_dz0 = true;
     for (int t = 0; t < d->ntaps; ++t) all_dz0 = all_dz0 && d->tap_dz[t] == 0;
-    static const bool no_split = getenv("B2D_CONV_NO_SPLITK") != nullptr;
-    const bool can_split = !no_split && all_dz0 && d->workspace && (reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0;
+    const bool no_split = (d->tune_flags & B2D_TUNE_NO_SPLITK) != 0;
+    const bool can_split = !no_split && all_dz0 && d->out_mode != 3 && d->workspace && (reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0;
     const int mt = halo ? 2 : 1;
     const int cand[4] = {256, 128, 64, 16};
-    const char* fks = getenv("B2D_CONV_KSPLIT");  // read per plan (not cached): a tuning knob, unset in production
-    const int force_ks = fks ? atoi(fks) : 0;
+    const int force_ks = d->tune_ksplit;  // tools/tune_conv.py: measure a given split count (0 = cost model)
     double best = 1e30;
     int best_bn = 0;
     for (int ci = 0; ci < 4; ++ci) {
@@ -313,26 +138,32 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     }
     if (best_bn == 0)
       return set_error(B2D_E_INVALID, "cout=%d block_n=%d%s: need cout a multiple of 64 (or <= 16)", d->cout, d->block_n,
-                       force_ks > 0 ? " (B2D_CONV_KSPLIT not applicable to this layer)" : "");
+                       force_ks > 0 ? " (tune_ksplit not applicable to this layer)" : "");
     bn = best_bn;
-  }
-  if (bn == 0) {
-    // Widest N tile that still fills the machine: N=256 needs 96 B/clk of smem operand reads per MMA
-    // (128 B/clk at N=128), but small-M layers (deep UNet levels) need the CTA count more.
-    const long long cols = (long long)d->cout * d->nphase;
-    const int sms = num_sms();
-    if (d->cout % 256 == 0 && tiles_m * (cols / 256) >= 2LL * sms) bn = 256;
-    else if (d->cout % 128 == 0 && (tiles_m * (cols / 128) >= sms || d->cout % 64 != 0)) bn = 128;
-    else if (d->cout % 64 == 0) bn = 64;
-    else if (d->cout <= 16 && d->nphase == 1) bn = 16;
-    else return set_error(B2D_E_INVALID, "cout=%d: need a multiple of 64 or <= 16", d->cout);
   }
   if (bn != 16 && bn != 64 && bn != 128 && bn != 256) return set_error(B2D_E_INVALID, "block_n=%d unsupported", bn);
   if (bn >= 64 && d->cout % bn) return set_error(B2D_E_INVALID, "cout=%d not a multiple of block_n=%d", d->cout, bn);
   if (bn == 16 && (d->cout > 16 || d->nphase != 1)) return set_error(B2D_E_INVALID, "block_n=16 needs cout<=16");
   const int total_cols = (bn == 16) ? 16 : d->cout * d->nphase;
   if (d->wrows < total_cols) return set_error(B2D_E_INVALID, "wrows=%d < %d", d->wrows, total_cols);
-  if (d->out_mode < 0 || d->out_mode > 2) return set_error(B2D_E_INVALID, "out_mode");
+  if (d->out_mode < 0 || d->out_mode > 3) return set_error(B2D_E_INVALID, "out_mode");
+  if (d->out_mode == 3) {
+    if (bn != 16 || d->cout > 16 || (d->cout % 4) || d->nphase != 1 || d->stride_h != 1 || d->stride_w != 1)
+      return set_error(B2D_E_INVALID, "out_mode 3 (fused sampler update) needs cout in {4,8,12,16}, stride 1, one phase (cout=%d block_n=%d)", d->cout, bn);
+    if (!d->sched_x || !d->sched_coef || (d->sched_kind != 0 && d->sched_kind != 1))
+      return set_error(B2D_E_INVALID, "out_mode 3: sched_x / sched_coef / sched_kind");
+    if (d->sched_step_idx && d->sched_step_inc != 0 && !d->sched_ticket)
+      return set_error(B2D_E_INVALID, "out_mode 3: sched_step_inc != 0 needs a caller-owned, zero-initialised sched_ticket");
+    if ((reinterpret_cast<uintptr_t>(d->sched_x) | reinterpret_cast<uintptr_t>(d->sched_noise)) & 15)
+      return set_error(B2D_E_INVALID, "out_mode 3: sched_x / sched_noise must be 16-byte aligned");
+    if (d->sched_x_bf16 && ((d->sched_bf16_stride % 4) || d->sched_bf16_stride < d->cout ||
+                            ((reinterpret_cast<uintptr_t>(d->sched_x_bf16) | reinterpret_cast<uintptr_t>(d->sched_x_bf16_lo)) & 7)))
+      return set_error(B2D_E_INVALID, "out_mode 3: bf16 copy needs a channel stride that is a multiple of 4 and 8-byte alignment");
+    if (d->out_H != d->OH || d->out_W != d->OW || d->out_sy != 1 || d->out_sx != 1 || d->out_oy != 0 || d->out_ox != 0)
+      return set_error(B2D_E_INVALID, "out_mode 3: the latent has the conv's own output geometry");
+    if (d->out && ((d->out_cstride % 4) || (d->out_coff % 4) || (reinterpret_cast<uintptr_t>(d->out) & 15)))
+      return set_error(B2D_E_INVALID, "out_mode 3: eps output needs cstride/coff multiples of 4");
+  }
   if (d->out_mode == 0 && ((d->out_cstride % 8) || (d->out_coff % 8) || (reinterpret_cast<uintptr_t>(d->out) & 15)))
     return set_error(B2D_E_INVALID, "bf16 output needs cstride/coff multiples of 8 and 16-byte alignment");
   if (d->out_mode == 2 && ((d->out_cstride % 4) || (d->out_coff % 4) || (reinterpret_cast<uintptr_t>(d->out) & 15)))
@@ -420,6 +251,17 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   k.stats = d->stats; k.stats_cpg = d->stats ? d->stats_cpg : 0;
   k.out_scale = d->out_scale; k.out_mask = d->out_mask;
   k.out_f16 = d->out_f16 ? 1 : 0; k.res_f16 = d->res_f16 ? 1 : 0;
+  if (d->out_mode == 3) {
+    k.sch_x = d->sched_x; k.sch_noise = d->sched_noise; k.sch_coef = d->sched_coef;
+    k.sch_step = d->sched_step_idx; k.sch_ticket = d->sched_ticket;
+    k.sch_seed_dev = reinterpret_cast<const unsigned long long*>(d->sched_seed_dev);
+    k.sch_seed = (unsigned long long)d->sched_seed;
+    k.sch_kind = d->sched_kind; k.sch_step_off = d->sched_step_off; k.sch_step_inc = d->sched_step_inc;
+    k.sch_clip = d->sched_clip ? 1 : 0; k.sch_lo = d->sched_clip_lo; k.sch_hi = d->sched_clip_hi;
+    k.sch_bf16 = reinterpret_cast<__nv_bfloat16*>(d->sched_x_bf16);
+    k.sch_bf16_lo = reinterpret_cast<__nv_bfloat16*>(d->sched_x_bf16_lo);
+    k.sch_bf16_stride = d->sched_bf16_stride;
+  }
   if (d->in_stats) {
     if (!halo || d->nseg != 1 || d->cin[0] > 512 || d->in_cpg < 1 || d->in_creal < 1 || d->in_creal > d->cin[0] || d->in_creal % d->in_cpg) {
       delete pl;
@@ -438,9 +280,8 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   int kb = 0;
   for (int s = 0; s < d->nseg; ++s) kb += d->ntaps * k.cchunks[s];
   pl->kblocks = kb;
-  pl->engine = engine;
   pl->ws_bytes = 0;
-  if (engine == 2) {
+  {
     // ---- persistent engine: work units, K-loop groups, split-K ---------------------------------
     k.halo = halo ? 1 : 0;
     k.gtaps = halo ? gt : 1;
@@ -468,7 +309,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     pl->grid = dim3((unsigned)(k.num_units < sms ? k.num_units : sms), 1, 1);
     // a strided walk changes sample at every unit when a sample has fewer units than the grid has CTAs (UNet levels):
     // every change costs a GroupNorm flush (two epilogue barriers + global atomics); walk contiguous ranges instead
-    static const int env_contig = [] { const char* e = getenv("B2D_CONV_CONTIG"); return e ? atoi(e) : -1; }();
+    const int env_contig = (d->tune_flags & B2D_TUNE_CONTIG) ? 1 : (d->tune_flags & B2D_TUNE_STRIDED) ? 0 : -1;
     const long long units_per_n = k.tiles_n > 0 ? k.num_units / k.tiles_n : k.num_units;
     k.contig = env_contig >= 0 ? env_contig : (units_per_n < (long long)pl->grid.x && k.num_units > (int)pl->grid.x) ? 1 : 0;
   }
@@ -493,26 +334,18 @@ extern "C" int b2d_conv_plan_info(const b2d_conv_plan* plan, int32_t* grid_m, in
 extern "C" int b2d_conv_run(const b2d_conv_plan* plan, void* stream) {
   if (!plan) return set_error(B2D_E_INVALID, "null plan");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (plan->engine == 2) return launch_conv_v2(plan, st);
-  switch (plan->block_n) {
-    // two co-resident CTAs per SM where shared memory allows: one CTA's epilogue overlaps the other's main loop
-    case 16: return launch_conv<16, 5, 2>(plan->kp, plan->grid, st);
-    case 64: return launch_conv<64, 4, 2>(plan->kp, plan->grid, st);
-    case 128: return launch_conv<128, 3, 2>(plan->kp, plan->grid, st);
-    case 256: return launch_conv<256, 4, 1>(plan->kp, plan->grid, st);
-  }
-  return set_error(B2D_E_INVALID, "bad block_n");
+  return launch_conv_v2(plan, st);
 }
 
 extern "C" int b2d_conv_plan_info2(const b2d_conv_plan* plan, int32_t* out8) {
   if (!plan || !out8) return set_error(B2D_E_INVALID, "null argument");
-  out8[0] = plan->engine;
+  out8[0] = 2;  // engine generation (the one-tile-per-CTA first engine was retired in ABI 6)
   out8[1] = plan->kp.halo;
-  out8[2] = plan->engine == 2 ? plan->kp.ksplit : 1;
-  out8[3] = plan->engine == 2 ? plan->kp.num_units : (int32_t)(plan->grid.x * plan->grid.y);
+  out8[2] = plan->kp.ksplit;
+  out8[3] = plan->kp.num_units;
   out8[4] = (int32_t)(plan->grid.x * plan->grid.y);
   out8[5] = plan->block_n;
-  out8[6] = plan->engine == 2 ? plan->kp.ngroups : plan->kblocks;
+  out8[6] = plan->kp.ngroups;
   out8[7] = (int32_t)((plan->ws_bytes + 1023) / 1024);
   return B2D_OK;
 }

@@ -1,5 +1,4 @@
-// Device-side body of the persistent implicit-GEMM conv engine (see conv_igemm2.cu for the design notes): shared by
-// the stand-alone kernels (conv_igemm2.cu) and the cross-layer chain kernel (conv_chain.cu).
+// Device-side body of the persistent implicit-GEMM conv engine (see conv_engine.cu for the design notes).
 #pragma once
 #include "conv_common.cuh"
 
@@ -105,12 +104,11 @@ struct GroupIter {
   }
 };
 
-// One planned convolution executed by the whole CTA.  `p` holds the scalars, `tm` the copy whose TMA descriptors are
-// addressed (param space for a stand-alone launch; global memory inside a chain, where `p` is a shared-memory copy).
-// CHAINED: called from the cross-layer persistent kernel (conv_chain.cu): TMEM is already allocated (`tmem_chain`),
-// the mbarriers are created and invalidated per layer, no programmatic-launch handshake.
-template <int BN, bool HALO, bool XFORM, bool CHAINED>
-__device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKParams& tm, uint8_t* smem, uint32_t tmem_chain) {
+// One planned convolution executed by the whole CTA (`p` lives in the kernel's parameter space: its TMA descriptors are
+// addressed in place).
+template <int BN, bool HALO, bool XFORM>
+__device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* smem) {
+  const ConvKParams& tm = p;
   using Cfg = V2Cfg<BN, HALO, XFORM>;
   constexpr int MT = Cfg::MT, NA = Cfg::NA, NB = Cfg::NB;
   constexpr int CW = BN < 32 ? 16 : 32;
@@ -147,20 +145,14 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
     for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&tm.tmapA[s]);
     prefetch_tmap(&tm.tmapB);
   }
-  if constexpr (!CHAINED) {
-    if (warp == 1) {
-      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-      tmem_relinquish();
-    }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = CHAINED ? tmem_chain : *tmem_slot;
-  if constexpr (!CHAINED) {
-    griddep_launch_dependents();  // the next kernel may start its own prologue ...
-    griddep_wait();               // ... and this one touches global memory only after its predecessor has completed
-  }
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
@@ -360,6 +352,11 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
       }
     };
     int bias_cobase = -1;
+    SchedCtx sched_ctx;
+    const SchedCtx* sched = nullptr;
+    if constexpr (BN == 16) {
+      if (p.out_mode == 3) { sched_ctx = sched_ctx_load(p); sched = &sched_ctx; }
+    }
     for (int u = uw.u; u < uw.end; u += uw.step) {
       const UnitCoord uc = decode_unit(p, u);
       if constexpr (SMEM_STATS) {
@@ -417,7 +414,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
         for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
       };
       if (p.ksplit == 1) {
-        conv_epilogue_row<BNG, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
+        conv_epilogue_row<BNG, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u, sched);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
@@ -579,18 +576,21 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, const ConvKP
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (CHAINED) {
-    // the next layer lays its own barriers over this memory
-    if (threadIdx.x == 0) {
-      for (int i = 0; i < NA; ++i) { mbar_inval(&a_full[i]); mbar_inval(&a_empty[i]); mbar_inval(&a_ready[i]); }
-      for (int i = 0; i < NB; ++i) { mbar_inval(&b_full[i]); mbar_inval(&b_empty[i]); }
-      for (int i = 0; i < 2; ++i) { mbar_inval(&t_full[i]); mbar_inval(&t_empty[i]); }
-    }
-    tc_fence_after();
-    __syncthreads();
-  } else if (warp == 1) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+  if constexpr (BN == 16) {
+    // fused sampler update: the last CTA to finish advances the device step counter (every CTA has read it by then)
+    if (p.out_mode == 3 && p.sch_step != nullptr && p.sch_step_inc != 0 && threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int ticket = atomicAdd(p.sch_ticket, 1u);
+      if (ticket == gridDim.x - 1) {
+        *p.sch_ticket = 0u;
+        *p.sch_step = *p.sch_step + p.sch_step_inc;
+        __threadfence();
+      }
+    }
   }
 }
 

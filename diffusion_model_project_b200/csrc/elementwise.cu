@@ -57,8 +57,6 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
     const float* __restrict__ beta, float eps, int act, const float* __restrict__ temb_table,
     const int* __restrict__ temb_row, int temb_row_stride, int temb_ld, int temb_col, double* __restrict__ stats_out,
     int in_f16) {
-  griddep_launch_dependents();
-  griddep_wait();
   extern __shared__ float sm[];
   float* sa = sm;
   float* sb = sm + C;
@@ -121,7 +119,6 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
     // same 8 channels -> coefficients live in registers and 4 independent 16-byte loads are in flight.
     const int c0 = (threadIdx.x % vpc) << 3;
     float a[8], b[8], t[8];
-#pragma unroll
     const float fold = act ? 0.5f : 1.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] = fold * sa[c0 + j]; b[j] = fold * sb[c0 + j]; t[j] = st[c0 + j]; }
@@ -187,8 +184,6 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
 __global__ void __launch_bounds__(256) maxpool_stats_kernel(const uint4* __restrict__ x, const uint4* __restrict__ x_lo,
                                                             uint4* __restrict__ y, uint4* __restrict__ y_lo, int H, int W,
                                                             int C, double* __restrict__ stats) {
-  griddep_launch_dependents();
-  griddep_wait();
   const int n = blockIdx.y;
   const int OH = H >> 1, OW = W >> 1, vpc = C >> 3;
   const long long nvec = (long long)OH * OW * vpc;
@@ -272,8 +267,6 @@ __global__ void __launch_bounds__(1024) gn_gn_kernel(const uint4* __restrict__ x
                                                      uint4* __restrict__ y2, int nvec, int C, const double* __restrict__ stats1,
                                                      const float* __restrict__ g1, const float* __restrict__ b1, float eps1, int act1,
                                                      const float* __restrict__ g2, const float* __restrict__ b2, float eps2, int act2) {
-  griddep_launch_dependents();
-  griddep_wait();
   __shared__ double red[32][2];
   const int n = blockIdx.x;
   const int vpc = C >> 3;
@@ -349,8 +342,6 @@ template <int VPT, bool KEEP>
 __global__ void __launch_bounds__(1024) maxpool_gn_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C,
                                                           const float* __restrict__ g, const float* __restrict__ be, float eps,
                                                           int act) {
-  griddep_launch_dependents();
-  griddep_wait();
   __shared__ double red[32][2];
   const int n = blockIdx.x;
   const int OW = W >> 1, vpc = C >> 3;
@@ -543,18 +534,17 @@ extern "C" int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo
   int per_img_cap = (num_sms() * 8 + N - 1) / N;
   if (bx > per_img_cap) bx = per_img_cap < 1 ? 1 : per_img_cap;
   const size_t smem = 3 * (size_t)C * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
-    cudaFuncSetAttribute(gn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cfg = true;
-  }
+  if (smem > 96 * 1024) return set_error(B2D_E_INVALID, "b2d_gn_apply: C=%d too large (3*C floats of shared memory, max 96 KB)", C);
+  static unsigned long long cfg_t = 0, cfg_f = 0;  // per-(kernel, device) opt-in to the dynamic shared-memory carve-out
+  cudaError_t ea = temb_table != nullptr ? smem_attr_once(gn_apply_kernel<true>, 96 * 1024, cfg_t)
+                                         : smem_attr_once(gn_apply_kernel<false>, 96 * 1024, cfg_f);
+  if (ea != cudaSuccess) return set_error(B2D_E_CUDA, "b2d_gn_apply: cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
   if (temb_table != nullptr)
-    launch_pdl(gn_apply_kernel<true>, dim3(bx, N), dim3(256), smem, (cudaStream_t)stream,
+    gn_apply_kernel<true><<<dim3(bx, N), dim3(256), smem, (cudaStream_t)stream>>>(
         (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, temb_table,
         temb_row, temb_row_stride, temb_ld, temb_col, stats_out, in_f16 ? 1 : 0);
   else
-    launch_pdl(gn_apply_kernel<false>, dim3(bx, N), dim3(256), smem, (cudaStream_t)stream,
+    gn_apply_kernel<false><<<dim3(bx, N), dim3(256), smem, (cudaStream_t)stream>>>(
         (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act,
         (const float*)nullptr, (const int*)nullptr, 0, 0, 0, stats_out, in_f16 ? 1 : 0);
   return check_launch("gn_apply_kernel");
@@ -569,8 +559,8 @@ extern "C" int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, vo
   int bx = grid_for(nvec, 256);
   int per_img_cap = (num_sms() * 8 + N - 1) / N;
   if (bx > per_img_cap) bx = per_img_cap < 1 ? 1 : per_img_cap;
-  launch_pdl(maxpool_stats_kernel, dim3(bx, N), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)x_lo, (uint4*)y,
-                                                                       (uint4*)y_lo, H, W, C, stats);
+  maxpool_stats_kernel<<<dim3(bx, N), dim3(256), 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, H, W, C,
+                                                                            stats);
   return check_launch("maxpool_stats_kernel");
 }
 
@@ -611,7 +601,7 @@ extern "C" int b2d_gn_gn_apply(const void* x, int32_t in_f16, void* y1, void* y2
   if (vpt == 0 || (1024 % (C / 8)) != 0)
     return set_error(B2D_E_UNSUPPORTED, "b2d_gn_gn_apply: sample of %lld elements / C=%d (max 65536 elements, C/8 dividing 1024)", nvec * 8, C);
   cudaStream_t st = (cudaStream_t)stream;
-#define B2D_GG(V, K) launch_pdl(gn_gn_kernel<V, K>, dim3(N), dim3(1024), 0, st, (const uint4*)x, (int)in_f16, (uint4*)y1, (uint4*)y2, (int)nvec, \
+#define B2D_GG(V, K) gn_gn_kernel<V, K><<<dim3(N), dim3(1024), 0, st>>>((const uint4*)x, (int)in_f16, (uint4*)y1, (uint4*)y2, (int)nvec, \
                              (int)C, stats1, gamma1, beta1, eps1, (int)act1, gamma2, beta2, eps2, (int)act2)
   if (vpt == 1) B2D_GG(1, true); else if (vpt == 2) B2D_GG(2, true); else if (vpt == 4) B2D_GG(4, true); else B2D_GG(8, false);
 #undef B2D_GG
@@ -628,7 +618,7 @@ extern "C" int b2d_maxpool2x2_gn(const void* x, void* y, int32_t N, int32_t H, i
     return set_error(B2D_E_UNSUPPORTED, "b2d_maxpool2x2_gn: pooled sample of %lld elements / C=%d (max 65536 elements, C/8 dividing 1024)",
                      nvec * 8, C);
   cudaStream_t st = (cudaStream_t)stream;
-#define B2D_PG(V, K) launch_pdl(maxpool_gn_kernel<V, K>, dim3(N), dim3(1024), 0, st, (const uint4*)x, (uint4*)y, (int)H, (int)W, (int)C, gamma, beta, \
+#define B2D_PG(V, K) maxpool_gn_kernel<V, K><<<dim3(N), dim3(1024), 0, st>>>((const uint4*)x, (uint4*)y, (int)H, (int)W, (int)C, gamma, beta, \
                              eps, (int)act)
   if (vpt == 1) B2D_PG(1, true); else if (vpt == 2) B2D_PG(2, true); else if (vpt == 4) B2D_PG(4, true); else B2D_PG(8, false);
 #undef B2D_PG

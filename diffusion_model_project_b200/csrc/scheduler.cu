@@ -12,78 +12,24 @@
 
 #include "../../include/b2d.h"
 #include "b2d_internal.h"
+#include "scheduler_math.cuh"
 
 namespace b2d {
-
-// ---- Philox4x32-10 (Salmon et al. 2011), counter = element index / 4, key = (seed, step row) ----
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-}
-__device__ __forceinline__ void philox4x32_10(uint64_t ctr, uint32_t stream_id, uint64_t seed, uint32_t (&out)[4]) {
-  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), stream_id, 0u};
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-}
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-  const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float r = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
-}
-
-struct Coef { float a, b, c1, c2, s; double inv_a; };
-
-// ticket counter of the "last block advances the step index" protocol (one copy per device, no allocation)
-__device__ unsigned int g_done_counter = 0u;
-
-__device__ __forceinline__ float step_one(float x, float e, float z, const Coef& k, int kind, int clip, float lo, float hi,
-                                          bool use_noise) {
-  // x0 = (x_t - sqrt(1-abar) * eps) / sqrt(abar)               diffusion.py:124
-  // The IEEE fp32 quotient through fp64: n * (1/a) in double is within 2^-52 of n/a, far inside the 2^-49 gap that
-  // separates an fp32 quotient from a rounding midpoint, so the final rounding is the correctly rounded n/a --
-  // bit-identical to the reference's division at a third of div.rn.f32's instruction count.
-  float x0 = __double2float_rn(__dmul_rn((double)__fsub_rn(x, __fmul_rn(k.b, e)), k.inv_a));
-  if (clip) x0 = fminf(fmaxf(x0, lo), hi);                      // torch.clamp, diffusion.py:169 / :219
-  // DDPM: c1*x0 + c2*x_t (diffusion.py:148); DDIM: sqrt(abar')*x0 + sqrt(1-abar'-s^2)*eps (:225-228)
-  const float second = (kind == 0) ? __fmul_rn(k.c2, x) : __fmul_rn(k.c2, e);
-  float out = __fadd_rn(__fmul_rn(k.c1, x0), second);
-  if (use_noise) out = __fadd_rn(out, __fmul_rn(k.s, z));       // diffusion.py:181 / :232
-  return out;
-}
 
 template <bool PHILOX>
 __global__ void __launch_bounds__(256, PHILOX ? 2 : 4) scheduler_step_kernel(
     int kind, const float4* __restrict__ x_t, const float4* __restrict__ eps, const float4* __restrict__ noise,
     float4* __restrict__ x_out, long long n_vec, long long n_elem, const float* __restrict__ coef, int* step_idx,
     int step_off, int step_inc, int clip, float clip_lo, float clip_hi, __nv_bfloat16* __restrict__ x_bf16, int group,
-    int group_stride, unsigned long long seed) {
+    int group_stride, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, unsigned int* ticket_ctr) {
   const int row = (step_idx ? *step_idx : 0) + step_off;
-  Coef k;
-  k.a = __ldg(coef + row * 8 + 0); k.b = __ldg(coef + row * 8 + 1); k.c1 = __ldg(coef + row * 8 + 2);
-  k.c2 = __ldg(coef + row * 8 + 3); k.s = __ldg(coef + row * 8 + 4);
-  k.inv_a = 1.0 / (double)k.a;
+  const Coef k = load_coef(coef, row);
+  if (PHILOX && seed_dev != nullptr) seed = *seed_dev;
   const bool use_noise = (k.s != 0.f);
   if (!PHILOX && use_noise && noise == nullptr) __trap();  // caller promised a noise-free row (seed == 0)
   const long long stride = (long long)gridDim.x * blockDim.x;
   auto one_vec = [&](long long i, const float4& x, const float4& e, float4 z) {
-    if (PHILOX && use_noise && noise == nullptr) {
-      uint32_t r[4];
-      philox4x32_10((uint64_t)i, (uint32_t)row, seed, r);
-      box_muller(r[0], r[1], z.x, z.y);
-      box_muller(r[2], r[3], z.z, z.w);
-    }
+    if (PHILOX && use_noise && noise == nullptr) z = philox_normal4((uint64_t)i, (uint32_t)row, seed);
     float4 o;
     o.x = step_one(x.x, e.x, z.x, k, kind, clip, clip_lo, clip_hi, use_noise);
     o.y = step_one(x.y, e.y, z.y, k, kind, clip, clip_lo, clip_hi, use_noise);
@@ -120,12 +66,8 @@ __global__ void __launch_bounds__(256, PHILOX ? 2 : 4) scheduler_step_kernel(
     if (use_noise) {
       if (noise != nullptr) z = reinterpret_cast<const float*>(noise)[i];
       else if (PHILOX) {
-        uint32_t r[4];
-        philox4x32_10((uint64_t)n_vec, (uint32_t)row, seed, r);
-        float z0, z1, z2, z3;
-        box_muller(r[0], r[1], z0, z1);
-        box_muller(r[2], r[3], z2, z3);
-        z = threadIdx.x == 0 ? z0 : (threadIdx.x == 1 ? z1 : z2);
+        const float4 z4 = philox_normal4((uint64_t)n_vec, (uint32_t)row, seed);
+        z = threadIdx.x == 0 ? z4.x : (threadIdx.x == 1 ? z4.y : z4.z);
       }
     }
     const float o = step_one(xs[i], es[i], z, k, kind, clip, clip_lo, clip_hi, use_noise);
@@ -137,9 +79,9 @@ __global__ void __launch_bounds__(256, PHILOX ? 2 : 4) scheduler_step_kernel(
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
-      const unsigned int ticket = atomicAdd(&g_done_counter, 1u);
+      const unsigned int ticket = atomicAdd(ticket_ctr, 1u);
       if (ticket == gridDim.x - 1) {
-        g_done_counter = 0u;
+        *ticket_ctr = 0u;
         *step_idx = row - step_off + step_inc;
         __threadfence();
       }
@@ -165,10 +107,13 @@ using namespace b2d;
 extern "C" int b2d_scheduler_step(int kind, const float* x_t, const float* eps, const float* noise, float* x_out,
                                   int64_t n_elem, const float* coef, int* step_idx, int step_off, int step_inc, int clip,
                                   float clip_lo, float clip_hi, void* x_bf16, int group, int group_stride, uint64_t seed,
-                                  void* stream) {
+                                  const uint64_t* seed_dev, unsigned int* ticket, void* stream) {
   if (!x_t || !eps || !x_out || !coef) return set_error(B2D_E_INVALID, "b2d_scheduler_step: null pointer");
   if (kind != 0 && kind != 1) return set_error(B2D_E_INVALID, "b2d_scheduler_step: kind must be 0 (DDPM) or 1 (DDIM)");
   if (n_elem < 1) return set_error(B2D_E_INVALID, "b2d_scheduler_step: n_elem=%lld", (long long)n_elem);
+  if (step_idx && step_inc != 0 && !ticket)
+    return set_error(B2D_E_INVALID, "b2d_scheduler_step: step_inc != 0 needs a caller-owned ticket word (zero-initialised)");
+  if (((uintptr_t)seed_dev & 7) || ((uintptr_t)ticket & 3)) return set_error(B2D_E_INVALID, "b2d_scheduler_step: misaligned seed_dev / ticket");
   if (((uintptr_t)x_t | (uintptr_t)eps | (uintptr_t)x_out | (uintptr_t)noise) & 15)
     return set_error(B2D_E_INVALID, "b2d_scheduler_step: pointers must be 16-byte aligned");
   if (x_bf16 && (group < 4 || (group % 4) || group_stride < group || (group_stride % 2) || ((uintptr_t)x_bf16 & 3)))
@@ -180,14 +125,16 @@ extern "C" int b2d_scheduler_step(int kind, const float* x_t, const float* eps, 
   if (blocks < 1) blocks = 1;
   // in-kernel Philox noise only when no noise tensor is given AND a seed is: seed == 0 asserts that the rows used
   // have s == 0 (deterministic DDIM) -- the lean kernel traps if that is violated
-  if (noise == nullptr && seed != 0)
+  if (noise == nullptr && (seed != 0 || seed_dev != nullptr))
     scheduler_step_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         kind, (const float4*)x_t, (const float4*)eps, (const float4*)noise, (float4*)x_out, n_vec, n_elem, coef, step_idx,
-        step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed);
+        step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed,
+        (const unsigned long long*)seed_dev, ticket);
   else
     scheduler_step_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         kind, (const float4*)x_t, (const float4*)eps, (const float4*)noise, (float4*)x_out, n_vec, n_elem, coef, step_idx,
-        step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed);
+        step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed,
+        (const unsigned long long*)seed_dev, ticket);
   return check_launch("scheduler_step_kernel");
 }
 

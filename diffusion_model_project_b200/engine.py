@@ -195,36 +195,25 @@ def pack_linear(w, bias, device, split=False):
 # ------------------------------------------------------------------------------------------------
 # conv plans
 # ------------------------------------------------------------------------------------------------
-_WORKSPACE: dict = {}
 WORKSPACE_BYTES = 64 << 20
-_WORKSPACE_SLOT = [0]
+_DEFAULT_WS: dict = {}
 
 
-class workspace_slot:
-    """Plans created inside `with workspace_slot(k):` use the k-th split-K scratch buffer.  Plans that may run
-    CONCURRENTLY (two launch chains on two streams) must not share one; plans of one chain run back to back and do."""
-
-    def __init__(self, slot: int):
-        self.slot = slot
-
-    def __enter__(self):
-        self.prev = _WORKSPACE_SLOT[0]
-        _WORKSPACE_SLOT[0] = self.slot
-        return self
-
-    def __exit__(self, *exc):
-        _WORKSPACE_SLOT[0] = self.prev
-        return False
+def new_workspace(device, nbytes: int = WORKSPACE_BYTES) -> torch.Tensor:
+    """A split-K scratch buffer (first 16 KB: arrival counters, zero-initialised once; every kernel leaves them zero).
+    Plans that share one must run back to back on ONE stream: each predictor session / module program owns its own, so
+    sampling loops on different streams never touch the same counters or partial tiles."""
+    return torch.zeros(nbytes, dtype=torch.uint8, device=torch.device(device))
 
 
-def workspace(device) -> torch.Tensor:
-    """Split-K scratch shared by every plan of a device and slot (plans run back to back on one stream).  The first
-    16 KB are arrival counters: zero-initialised once, each kernel leaves them zero again."""
+def default_workspace(device) -> torch.Tensor:
+    """Scratch for plans created without an explicit workspace (unit tests, tools): one per (device, current stream)."""
     dev = torch.device(device)
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), _WORKSPACE_SLOT[0])
-    if key not in _WORKSPACE:
-        _WORKSPACE[key] = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
-    return _WORKSPACE[key]
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    if key not in _DEFAULT_WS:
+        _DEFAULT_WS[key] = new_workspace(torch.device("cuda", idx))
+    return _DEFAULT_WS[key]
 
 
 class ConvPlan:
@@ -233,9 +222,14 @@ class ConvPlan:
     def __init__(self, inputs: Sequence[Act], pw: PackedWeight, out, *, cout: int, nphase: int = 1, stride: int = 1,
                  out_mode: int = 0, out_geom=None, residual: Optional[Act] = None, stats: Optional[torch.Tensor] = None,
                  stats_cpg: int = 0, out_scale=None, out_mask=None, block_n: int = 0, out_cstride=None, out_coff: int = 0,
-                 engine: int = 0, in_norm=None):
+                 in_norm=None, workspace: Optional[torch.Tensor] = None, tune_flags: int = 0, tune_ksplit: int = 0,
+                 sched: Optional[dict] = None):
         """in_norm = (stats, cpg, gamma, beta, act[, eps]): inputs[0] is a RAW pre-GroupNorm tensor and the kernel applies
-        GroupNorm (+SiLU) to each staged tile (persistent halo engine only; see include/b2d.h)."""
+        GroupNorm (+SiLU) to each staged tile (halo staging only; see include/b2d.h).
+        workspace: split-K scratch (new_workspace); default: the (device, current stream) one.
+        sched: out_mode 3 -- fuse the sampler update into the epilogue (b2d_conv_desc.sched_*): dict(kind, x, coef, state
+        [int32: step index, ticket, 64-bit seed at word 2], noise=None, clip=(lo, hi) or None, x_bf16: Act or None,
+        step_inc=1, philox=bool); `out` may then be None (eps is not stored)."""
         N, D, H, W, _ = inputs[0].shape
         d = ConvDesc()
         split = pw.split
@@ -267,7 +261,7 @@ class ConvPlan:
         d.cout, d.nphase = cout, nphase
         d.bias = ptr(pw.bias)
         out_hi = out.hi if isinstance(out, Act) else out
-        d.out = out_hi.data_ptr()
+        d.out = ptr(out_hi)
         d.out_lo = ptr(out.lo) if isinstance(out, Act) else None
         d.out_f16 = 1 if (isinstance(out, Act) and out.f16) else 0
         d.out_mode = out_mode
@@ -276,7 +270,7 @@ class ConvPlan:
             out_geom = (OH * up, OW * up, up, up, 0, 0)
         d.out_H, d.out_W, d.out_sy, d.out_sx, d.out_oy, d.out_ox = out_geom
         if out_cstride is None:
-            out_cstride = out_hi.shape[-1] if out_mode != 1 else cout
+            out_cstride = cout if (out_mode == 1 or out_hi is None) else out_hi.shape[-1]
         d.out_cstride, d.out_coff = out_cstride, out_coff
         if residual is not None:
             d.residual = residual.hi.data_ptr()
@@ -288,7 +282,27 @@ class ConvPlan:
         d.out_scale = ptr(out_scale)
         d.out_mask = ptr(out_mask)
         d.block_n = block_n
-        d.engine = engine
+        d.tune_flags, d.tune_ksplit = tune_flags, tune_ksplit
+        if sched is not None:
+            assert out_mode == 3
+            st = sched["state"]
+            assert st.dtype == torch.int32 and st.numel() >= 4 and st.data_ptr() % 8 == 0
+            d.sched_kind = sched["kind"]
+            d.sched_x = sched["x"].data_ptr()
+            d.sched_noise = ptr(sched.get("noise"))
+            d.sched_coef = sched["coef"].data_ptr()
+            d.sched_step_idx = st.data_ptr()
+            d.sched_ticket = st.data_ptr() + 4
+            d.sched_seed_dev = (st.data_ptr() + 8) if sched.get("philox") else None
+            d.sched_seed = 0
+            d.sched_step_off = 0
+            d.sched_step_inc = sched.get("step_inc", 1)
+            clip = sched.get("clip")
+            d.sched_clip = 0 if clip is None else 1
+            d.sched_clip_lo, d.sched_clip_hi = (0.0, 0.0) if clip is None else (float(clip[0]), float(clip[1]))
+            xb = sched.get("x_bf16")
+            if xb is not None:
+                d.sched_x_bf16, d.sched_x_bf16_lo, d.sched_bf16_stride = xb.hi.data_ptr(), ptr(xb.lo), xb.C
         if in_norm is not None:
             st_in, cpg_in, g_in, b_in, act_in = in_norm[:5]
             assert len(inputs) == 1 and not split
@@ -299,10 +313,10 @@ class ConvPlan:
             d.in_f16 = 1 if inputs[0].f16 else 0
             d.in_act = 1 if act_in else 0
             d.in_eps = in_norm[5] if len(in_norm) > 5 else 1e-5
-        ws = workspace(inputs[0].hi.device)
+        ws = workspace if workspace is not None else default_workspace(inputs[0].hi.device)
         d.workspace = ws.data_ptr()
         d.workspace_bytes = ws.numel()
-        self._keep = (inputs, pw, out, residual, stats, out_scale, out_mask, in_norm)
+        self._keep = (inputs, pw, out, residual, stats, out_scale, out_mask, in_norm, ws, sched)
         self.desc = d
         self.handle = C.c_void_p()
         _lib.check(_lib.lib().b2d_conv_plan_create(C.byref(d), C.byref(self.handle)), "b2d_conv_plan_create")
@@ -373,82 +387,20 @@ def upsample2x(x: Act, y: Act, stream: int):
 
 
 class Program:
-    """A recorded sequence of kernel launches over static buffers (replayable, graph-capturable).  Each step may also
-    carry a structured description (`op`) from which the same sequence can be compiled into a Chain."""
+    """A recorded sequence of kernel launches over static buffers (replayable, graph-capturable).  A step is a callable
+    `fn(stream)`, or a list of them -- one per VARIANT: the same launch bound to different caller buffers (the chunks of a
+    micro-batched VAE pass, whose first and last layers read / write a different slice of the big batch each time)."""
 
     def __init__(self):
-        self.steps: List[Tuple[str, Callable[[int], None]]] = []
-        self.ops: List[Optional[tuple]] = []
+        self.steps: List[Tuple[str, object]] = []
         self.flops = 0.0
 
-    def add(self, name: str, fn: Callable[[int], None], op: Optional[tuple] = None):
+    def add(self, name: str, fn):
         self.steps.append((name, fn))
-        self.ops.append(op)
 
-    def run(self, stream: int):
+    def run(self, stream: int, variant: int = 0):
         for _, fn in self.steps:
-            fn(stream)
+            (fn[variant] if isinstance(fn, (list, tuple)) else fn)(stream)
 
     def __len__(self):
         return len(self.steps)
-
-
-class Chain:
-    """A Program compiled into ONE cooperative persistent kernel (csrc/conv_chain.cu): the same layers, a grid barrier
-    in place of every kernel boundary.  Needs every step of the program to carry an `op` description (bf16 mode)."""
-
-    def __init__(self, prog: Program, device, max_ops: Optional[int] = None, first_op: int = 0):
-        lib = _lib.lib()
-        self.handle = C.c_void_p()
-        _lib.check(lib.b2d_chain_create(C.byref(self.handle)), "b2d_chain_create")
-        self._keep = []
-        for (name, _), op in list(zip(prog.steps, prog.ops))[first_op:max_ops]:
-            if op is None:
-                raise ValueError(f"program step {name!r} has no chain description")
-            kind = op[0]
-            if kind == "conv":
-                _lib.check(lib.b2d_chain_add_conv(self.handle, op[1].handle), f"chain add {name}")
-            elif kind == "gn":
-                (x, y, stats, cpg, gamma, beta, act, temb, temb_row, temb_row_stride, temb_col, stats_out, eps) = op[1:]
-                N, D, H, W, Cc = x.shape
-                _lib.check(lib.b2d_chain_add_gn(self.handle, ptr(x.hi), ptr(y.hi), N, D * H * W, Cc, ptr(stats), cpg, ptr(gamma), ptr(beta),
-                                                eps, 1 if act else 0, ptr(temb), ptr(temb_row), temb_row_stride,
-                                                0 if temb is None else temb.shape[1], temb_col, ptr(stats_out), 1 if x.f16 else 0),
-                           f"chain add {name}")
-            elif kind == "pool":
-                x, y, stats = op[1:]
-                N, D, H, W, Cc = x.shape
-                _lib.check(lib.b2d_chain_add_pool(self.handle, ptr(x.hi), ptr(y.hi), N, H, W, Cc, ptr(stats)), f"chain add {name}")
-            elif kind == "attn":
-                qkv, out, N, T, Cc, heads = op[1:]
-                _lib.check(lib.b2d_chain_add_attention(self.handle, ptr(qkv.hi), ptr(out.hi), N, T, Cc, heads), f"chain add {name}")
-            elif kind == "zero":
-                buf, nbytes = op[1:]
-                _lib.check(lib.b2d_chain_add_zero(self.handle, buf.data_ptr(), (nbytes + 15) // 16 * 16), f"chain add {name}")
-            elif kind == "unsupported":
-                raise ValueError(f"program step {name!r} ({op[1]}) has no chain form: build the program with fuse_small=False")
-            else:
-                raise ValueError(f"unknown chain op {kind!r}")
-            self._keep.append(op)
-        self.num_ops = lib.b2d_chain_num_ops(self.handle)
-        nbytes = self.num_ops * lib.b2d_chain_op_bytes()
-        self._buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
-        off = (-self._buf.data_ptr()) % 128
-        self._bar = torch.zeros(2 + 2 * (self.num_ops + 1), dtype=torch.int32, device=device)
-        _lib.check(lib.b2d_chain_bind(self.handle, self._buf.data_ptr() + off, nbytes, self._bar.data_ptr(), _lib.stream_ptr()), "b2d_chain_bind")
-
-    def run(self, stream: int):
-        call("b2d_chain_run", self.handle, stream)
-
-    def op_times_us(self) -> List[float]:
-        """Device time of every op of the last run (op + the grid barrier after it), from the kernel's %globaltimer stamps."""
-        t = self._bar[2:].view(torch.int64).cpu().tolist()
-        return [(t[i + 1] - t[i]) / 1e3 for i in range(self.num_ops)]
-
-    def __del__(self):
-        try:
-            if self.handle:
-                _lib.lib().b2d_chain_destroy(self.handle)
-                self.handle = C.c_void_p()
-        except Exception:
-            pass

@@ -17,7 +17,11 @@ What differs from the reference's control flow (results are unaffected):
     timestep (UNet + scheduler, ~95 launches) is captured into a CUDA graph and replayed;
   * the Euclidean distance transform runs on the GPU (csrc/edt.cu) instead of SciPy on the host
     (predictor.py:1096-1116);
-  * denormalisation and the mask multiply are the D3D `conv_out` epilogue (predictor.py:1005-1021).
+  * denormalisation and the mask multiply are the D3D `conv_out` epilogue (predictor.py:1005-1021);
+  * the sampler update (p_sample / ddim_sample) runs inside final_conv's epilogue: eps never reaches HBM and the step
+    costs one launch less (`fuse_scheduler`);
+  * large batches are micro-batched: E2D and D3D run in chunks of `vae_chunk` samples over one reusable set of
+    activation buffers, while the UNet loop runs over ALL B x num_slices slice-images per launch.
 """
 from __future__ import annotations
 
@@ -25,7 +29,7 @@ from typing import Dict, List, Optional, Sequence
 
 import torch
 
-from . import _lib, engine
+from . import _lib, checkpoint, engine
 from .engine import Act, new_act
 from .scheduler import B200Scheduler
 from .unet import B200UNet
@@ -45,11 +49,15 @@ class B200LatentDiffusionPredictor:
     def __init__(self, model_name="UNet", model_kwargs: Optional[dict] = None, distance_transform=True, *,
                  unet_state: Dict[str, torch.Tensor], vae_state: Dict[str, torch.Tensor], norm_factors: Sequence[float],
                  num_slices: int = 11, num_timesteps: int = 1000, precision: str = "bf16", use_graph: bool = True,
-                 unet_chains: Optional[int] = None, device="cuda"):
+                 fuse_scheduler: bool = True, vae_chunk: int = 8, vae_options: Optional[dict] = None, device="cuda"):
         if model_name != "UNet":
             raise ValueError("only the 'UNet' denoiser exists in the reference (predictor.py:136)")
         if not torch.cuda.is_available():
             raise RuntimeError("B200LatentDiffusionPredictor needs a CUDA device (sm_100a); there is no CPU fallback")
+        if len(list(norm_factors)) != 3:
+            raise ValueError(f"norm_factors must hold one scale per velocity component (3), got {list(norm_factors)}")
+        if vae_chunk < 1:
+            raise ValueError("vae_chunk must be >= 1")
         model_kwargs = dict(model_kwargs or {})
         model_kwargs.setdefault("time_embedding_dim", 64)  # predictor.py:317-318
         self.device = torch.device(device)
@@ -58,26 +66,36 @@ class B200LatentDiffusionPredictor:
         self.precision = precision
         self.split = precision == "fp32x"
         self.use_graph = use_graph
-        # The UNet step at 8 samples/GPU is a chain of ~90 small launches, each with a fixed latency floor
-        # (launch, prologue, first TMA round trip, drain).  Slices are independent, so the batch can be cut into
-        # `unet_chains` groups whose launch chains run on separate streams (separate graph branches) and hide each
-        # other's floors.  Default from B2D_UNET_CHAINS (1 = single chain).
-        import os
-        self.unet_chains = int(os.environ.get("B2D_UNET_CHAINS", "1")) if unet_chains is None else int(unet_chains)
-        self._side_streams: List[torch.cuda.Stream] = []
-        # B2D_UNET_CHAIN=1: the whole UNet step as ONE cooperative persistent kernel (engine.Chain), bf16 mode
-        self.unet_chain = os.environ.get("B2D_UNET_CHAIN", "0") == "1" and precision == "bf16"
+        self.fuse_scheduler = fuse_scheduler
+        self.vae_chunk = int(vae_chunk)
         self.model = B200UNet(**model_kwargs, precision=precision, num_timesteps=num_timesteps, device=device)
         self.model.load_state_dict(unet_state)
         self.scheduler = B200Scheduler(num_timesteps=num_timesteps, device=device)
         lat = model_kwargs.get("out_channels", 4)
         self.latent_channels = lat
-        self.vae = B200DualVAE(3, lat, precision=precision, device=device)
+        self.vae = B200DualVAE(3, lat, precision=precision, device=device, options=vae_options)
         self.vae.load_state_dict(vae_state)
         self.vae_is_dual = True
         self.normalizer = {"input": MaxNormalizerParams([1], device), "output": MaxNormalizerParams(norm_factors, device)}
         self._session: Optional[dict] = None
-        self.seed = 0
+
+    # ------------------------------------------------------------------------------ construction from the reference
+    @classmethod
+    def from_spec(cls, spec: "checkpoint.PredictorSpec", **kw) -> "B200LatentDiffusionPredictor":
+        return cls("UNet", dict(spec.model_kwargs), spec.distance_transform, unet_state=spec.unet_state, vae_state=spec.vae_state,
+                   norm_factors=spec.norm_factors, num_slices=spec.num_slices, num_timesteps=spec.num_timesteps, **kw)
+
+    @classmethod
+    def from_reference(cls, predictor, **kw) -> "B200LatentDiffusionPredictor":
+        """Build from a constructed reference `LatentDiffusionPredictor` (its modules' own state_dicts, norm factors,
+        num_slices, num_timesteps); the PyTorch modules stay untouched.  This is the body of INTEGRATION.md's `use_b200()`."""
+        return cls.from_spec(checkpoint.spec_from_reference(predictor), **kw)
+
+    @classmethod
+    def from_directory(cls, folder: str, device: str = "cuda", **kw) -> "B200LatentDiffusionPredictor":
+        """`Predictor.from_directory(folder, device)` (predictor.py:222-250) for this path: `log.json` + `model.pt` in
+        `folder`, the frozen dual VAE from the `vae_encoder_path` / `vae_decoder_path` directories named in the log."""
+        return cls.from_spec(checkpoint.load_directory(folder), device=device, **kw)
 
     # ------------------------------------------------------------------------------ session
     def _get_session(self, B, S, H, W) -> dict:
@@ -91,28 +109,43 @@ class B200LatentDiffusionPredictor:
             raise ValueError(f"in-plane size {H}x{W} must be a multiple of 128 (latent /4, five UNet poolings)")
         h, w = H // 4, W // 4
         N = B * S
-        ses = dict(key=key, B=B, S=S, H=H, W=W, h=h, w=w, N=N)
+        # micro-batching: the VAE passes run over `chunk` samples at a time against ONE set of activation buffers
+        # (25 GB per 8 samples of 11x256x256); a ragged tail re-runs the last `chunk` samples (idempotent)
+        chunk = min(B, self.vae_chunk)
+        starts = list(range(0, B - chunk + 1, chunk))
+        if starts[-1] + chunk < B:
+            starts.append(B - chunk)
+        ses = dict(key=key, B=B, S=S, H=H, W=W, h=h, w=w, N=N, chunk=chunk, starts=starts)
+        # everything two concurrent sampling loops must not share lives in the session: split-K scratch + arrival
+        # counters, and the loop state {step index, ticket, 64-bit Philox seed} the kernels read and advance
+        ses["workspace"] = engine.new_workspace(dev)
+        ses["state"] = torch.zeros(8, dtype=torch.int32, device=dev)
         cin_pad = engine.pad64(self.model.in_channels)
         ses["unet_in"] = new_act(N, 1, h, w, cin_pad, dev, sp, zero=True)
         ses["x"] = torch.zeros(N, h, w, lat, dtype=torch.float32, device=dev)      # fp32 master latent, channels-last
         ses["eps"] = torch.zeros(N, h, w, lat, dtype=torch.float32, device=dev)
-        ses["step_idx"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        ses["z"] = None                                                             # host-injected step noise (lazy)
         ses["img"] = torch.zeros(B, S, 1, H, W, dtype=torch.float32, device=dev)
         ses["v2d"] = torch.zeros(B, S, 3, H, W, dtype=torch.float32, device=dev)
         ses["edt"] = torch.zeros(2, N, H, W, dtype=torch.float32, device=dev)
         ses["feats"] = torch.zeros(N, h, w, dtype=torch.float32, device=dev)
         ses["out"] = torch.zeros(B, S, 3, H, W, dtype=torch.float32, device=dev)
-        # E2D: (B,S,3,H,W)/s -> NDHWC bf16 -> mu written straight into unet_in channels [lat, 2*lat)
-        ses["e2d_in"] = new_act(B, S, H, W, 64, dev, sp, zero=True)
-        enc_out = Act(ses["unet_in"].hi.view(B, S, h, w, cin_pad), None if not sp else ses["unet_in"].lo.view(B, S, h, w, cin_pad))
-        ses["e2d"] = self.vae.build_encoder("encoder_2d", B, S, H, W, x_in=ses["e2d_in"], out=enc_out, out_mode=0, out_coff=lat,
-                                            out_cout=lat)
+        ui = ses["unet_in"]
+        hi5 = ui.hi.view(B, S, h, w, cin_pad)
+        lo5 = None if not sp else ui.lo.view(B, S, h, w, cin_pad)
+        lat_views = [Act(hi5[c0:c0 + chunk], None if lo5 is None else lo5[c0:c0 + chunk]) for c0 in starts]
+        # E2D: (chunk,S,3,H,W)/s -> NDHWC bf16 -> mu written straight into unet_in channels [lat, 2*lat)
+        ses["e2d_in"] = new_act(chunk, S, H, W, 64, dev, sp, zero=True)
+        ses["e2d"] = self.vae.build_encoder("encoder_2d", chunk, S, H, W, x_in=ses["e2d_in"], out=lat_views, out_mode=0, out_coff=lat,
+                                            out_cout=lat, workspace=ses["workspace"])
         # D3D: reads the latent out of unet_in (conv_in's packed weight is zero beyond channel `lat`)
         scale = self.normalizer["output"].scale_factors
-        ses["d3d"] = self.vae.build_decoder("decoder_3d", B, S, h, w, z_in=enc_out, out=ses["out"], out_scale=scale,
-                                            out_mask=ses["img"])
+        ses["d3d"] = self.vae.build_decoder("decoder_3d", chunk, S, h, w, z_in=lat_views, out=[ses["out"][c0:c0 + chunk] for c0 in starts],
+                                            out_scale=scale, out_mask=[ses["img"][c0:c0 + chunk] for c0 in starts],
+                                            workspace=ses["workspace"])
         ses["unet"] = None
         ses["temb_key"] = None
+        ses["final"] = {}
         ses["graph"] = None
         self._session = ses
         return ses
@@ -125,42 +158,43 @@ class B200LatentDiffusionPredictor:
         idx = torch.tensor(timesteps, dtype=torch.long, device=self.device)
         temb_steps = self.model.temb_table.index_select(0, idx).contiguous()
         ses["unet"] = None  # release the previous program's buffers first
-        ses["unet_parts"] = None
-        ses["unet_chain"] = None
-        N = ses["N"]
-        chains = self.unet_chains if (self.unet_chains > 1 and N % self.unet_chains == 0 and N // self.unet_chains >= 8) else 1
-        if chains == 1:
-            ses["unet"] = self.model.build_program(N, ses["h"], ses["w"], x_in=ses["unet_in"], eps_out=ses["eps"], eps_mode=2,
-                                                   temb_row=ses["step_idx"], temb_row_stride=0, temb_table=temb_steps,
-                                                   fuse_small=False if self.unet_chain else None)
-        else:
-            parts, n = [], N // chains
-            ui = ses["unet_in"]
-            for c in range(chains):
-                xin = Act(ui.hi[c * n:(c + 1) * n], None if ui.lo is None else ui.lo[c * n:(c + 1) * n])
-                with engine.workspace_slot(c):
-                    parts.append(self.model.build_program(n, ses["h"], ses["w"], x_in=xin, eps_out=ses["eps"][c * n:(c + 1) * n],
-                                                          eps_mode=2, temb_row=ses["step_idx"], temb_row_stride=0, temb_table=temb_steps))
-            ses["unet_parts"] = parts
-            ses["unet"] = parts[0]
-            while len(self._side_streams) < chains - 1:
-                self._side_streams.append(torch.cuda.Stream(device=self.device))
-        ses["unet_chain"] = engine.Chain(ses["unet"]["program"], self.device) if (self.unet_chain and chains == 1) else None
+        ses["final"] = {}
+        ses["unet"] = self.model.build_program(ses["N"], ses["h"], ses["w"], x_in=ses["unet_in"], temb_row=ses["state"], temb_row_stride=0,
+                                               temb_table=temb_steps, workspace=ses["workspace"], final=False)
         ses["temb_steps"] = temb_steps
         ses["temb_key"] = key
         ses["graph"] = None
+
+    def _final(self, ses, kind, coef, clip_range, host_noise: bool, philox: bool, want_eps: bool):
+        """final_conv of the step: fused with the sampler update (default), or the plain eps-producing launch."""
+        fkey = (self.fuse_scheduler, kind, coef.data_ptr(), tuple(clip_range), host_noise, philox, want_eps)
+        plan = ses["final"].get(fkey)
+        if plan is None:
+            if self.fuse_scheduler:
+                sched = dict(kind=kind, x=ses["x"], coef=coef, state=ses["state"], noise=ses["z"] if host_noise else None,
+                             clip=clip_range, x_bf16=ses["unet_in"], step_inc=1, philox=philox)
+                plan = self.model.final_plan(ses["unet"], eps_out=ses["eps"] if want_eps else None, sched=sched)
+            else:
+                plan = self.model.final_plan(ses["unet"], eps_out=ses["eps"], eps_mode=2)
+            ses["final"][fkey] = plan
+        return plan
 
     # ------------------------------------------------------------------------------ stages
     def _conditioning(self, ses, img, velocity_2d, s):
         """predictor.py:927-962: normalise, E2D mu, EDT + bilinear features -> channels 8..16 of unet_in."""
         B, S, H, W, h, w, N = (ses[k] for k in ("B", "S", "H", "W", "h", "w", "N"))
         lat = self.latent_channels
+        if img.shape[1] == 1 and S > 1:
+            img = img.expand(B, S, 1, H, W)  # one mask for every slice (the broadcast of predictor.py:887-894)
         ses["img"].copy_(img.reshape(B, S, 1, H, W), non_blocking=True)
         ses["v2d"].copy_(velocity_2d, non_blocking=True)
         xi = ses["e2d_in"]
-        _lib.call("b2d_planar_to_cl", ses["v2d"].data_ptr(), _lib.ptr(xi.hi), _lib.ptr(xi.lo), N, 3, H * W, xi.C, 0,
-                  self.normalizer["output"].scale_factors.data_ptr(), s)
-        ses["e2d"]["program"].run(s)
+        chunk = ses["chunk"]
+        scale = self.normalizer["output"].scale_factors.data_ptr()
+        for i, c0 in enumerate(ses["starts"]):
+            _lib.call("b2d_planar_to_cl", ses["v2d"][c0:c0 + chunk].data_ptr(), _lib.ptr(xi.hi), _lib.ptr(xi.lo), chunk * S, 3, H * W, xi.C, 0,
+                      scale, s)
+            ses["e2d"]["program"].run(s, variant=i)
         if self.distance_transform:
             _lib.call("b2d_edt2d", ses["img"].data_ptr(), ses["edt"].data_ptr(), N, H, W, s, launches=2)
             src = ses["edt"][0]
@@ -179,81 +213,85 @@ class B200LatentDiffusionPredictor:
         ui = ses["unet_in"]
         _lib.call("b2d_planar_to_cl", ses["x"].data_ptr(), _lib.ptr(ui.hi), _lib.ptr(ui.lo), N * h * w, lat, 1, ui.C, 0, None, s)
 
-    def _run_unet(self, ses, s):
-        if ses.get("unet_chain") is not None:
-            ses["unet_chain"].run(s)
-            return
-        parts = ses.get("unet_parts")
-        if not parts:
-            ses["unet"]["program"].run(s)
-            return
-        # fork: chains 1.. on side streams, chain 0 on the caller's stream; join before the scheduler step
-        cur = torch.cuda.current_stream()
-        assert cur.cuda_stream == s, "multi-chain UNet step must be launched on the current stream"
-        for st in self._side_streams[:len(parts) - 1]:
-            st.wait_stream(cur)
-        for part, st in zip(parts[1:], self._side_streams):
-            part["program"].run(st.cuda_stream)
-        parts[0]["program"].run(s)
-        for st in self._side_streams[:len(parts) - 1]:
-            cur.wait_stream(st)
+    def _new_seed(self, ses):
+        """A fresh 64-bit Philox key per call, drawn from torch's default generator (so torch.manual_seed makes a run
+        reproducible and consecutive calls draw different noise, like the reference's randn_like).  It lives in the
+        session's device state: a captured graph reads it at replay time."""
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item()) | 1
+        ses["state"][2:4].copy_(torch.tensor([seed], dtype=torch.int64).view(torch.int32))
+        return seed
 
-    def _one_step(self, ses, kind, coef, noise_step, clip_range, s, advance=True):
+    def _run_unet(self, ses, s):
+        ses["unet"]["program"].run(s)
+
+    def _one_step(self, ses, kind, coef, clip_range, s, *, host_noise=False, philox=False, want_eps=False, advance=True):
+        """One sampling step: UNet body, then final_conv + sampler update (one launch when fused)."""
         self._run_unet(ses, s)
-        ui = ses["unet_in"]
-        x = ses["x"]
-        _lib.call("b2d_scheduler_step", kind, x.data_ptr(), ses["eps"].data_ptr(), _lib.ptr(noise_step), x.data_ptr(), x.numel(),
-                  coef.data_ptr(), ses["step_idx"].data_ptr(), 0, 1 if advance else 0, 1, float(clip_range[0]), float(clip_range[1]),
-                  None if self.split else ui.hi.data_ptr(), self.latent_channels, ui.C, self.seed, s)
+        plan = self._final(ses, kind, coef, clip_range, host_noise, philox, want_eps)
+        if self.fuse_scheduler:
+            if not advance:
+                raise RuntimeError("the fused step always advances the device step counter")
+            plan.run(s)
+            return
+        plan.run(s)
+        ui, x, st = ses["unet_in"], ses["x"], ses["state"]
+        _lib.call("b2d_scheduler_step", kind, x.data_ptr(), ses["eps"].data_ptr(), _lib.ptr(ses["z"]) if host_noise else None, x.data_ptr(),
+                  x.numel(), coef.data_ptr(), st.data_ptr(), 0, 1 if advance else 0, 1, float(clip_range[0]), float(clip_range[1]),
+                  None if self.split else ui.hi.data_ptr(), self.latent_channels, ui.C, 0, (st.data_ptr() + 8) if philox else None,
+                  st.data_ptr() + 4, s)
         if self.split:
             N, h, w = ses["N"], ses["h"], ses["w"]
             _lib.call("b2d_planar_to_cl", x.data_ptr(), _lib.ptr(ui.hi), _lib.ptr(ui.lo), N * h * w, self.latent_channels, 1, ui.C, 0, None, s)
 
-    def _run_loop(self, ses, kind, coef, n_steps, step_noise, clip_range, record):
+    def _run_loop(self, ses, kind, coef, n_steps, step_noise, clip_range, record, philox):
         s = _lib.stream_ptr()
-        ses["step_idx"].zero_()
+        ses["state"][0:2].zero_()  # step index and ticket (an aborted run may have left the ticket mid-count)
         graphable = self.use_graph and step_noise is None and record is None
+        n_launch = len(ses["unet"]["program"]) + (1 if self.fuse_scheduler else (3 if self.split else 2))
         if not graphable:
+            host_noise = step_noise is not None
+            if host_noise and ses["z"] is None:
+                ses["z"] = torch.zeros_like(ses["x"])
             for i in range(n_steps):
-                z = None
-                if step_noise is not None:
-                    z = step_noise[i].to(self.device, torch.float32).reshape(ses["N"], self.latent_channels, ses["h"], ses["w"]).permute(0, 2, 3, 1).contiguous()
+                if host_noise:
+                    ses["z"].copy_(step_noise[i].to(self.device, torch.float32).reshape(ses["N"], self.latent_channels, ses["h"], ses["w"])
+                                   .permute(0, 2, 3, 1))
                 x_before = ses["x"].clone() if record is not None else None
-                self._one_step(ses, kind, coef, z, clip_range, s)
+                self._one_step(ses, kind, coef, clip_range, s, host_noise=host_noise, philox=philox and not host_noise,
+                               want_eps=record is not None)
                 if record is not None:
                     record.append((x_before.permute(0, 3, 1, 2).contiguous(), ses["eps"].permute(0, 3, 1, 2).contiguous(),
                                    ses["x"].permute(0, 3, 1, 2).contiguous()))
             return
-        gkey = (kind, coef.data_ptr(), tuple(clip_range))
+        gkey = (kind, coef.data_ptr(), tuple(clip_range), philox, self.fuse_scheduler)
         if ses["graph"] is None or ses["graph"][0] != gkey:
-            # warm-up outside capture (lazy cudaFuncSetAttribute / ticket-counter allocation), then capture one timestep
+            # warm-up outside capture (lazy cudaFuncSetAttribute), then capture one timestep
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 saved = ses["x"].clone()
                 saved_in = ses["unet_in"].hi.clone()
                 saved_lo = ses["unet_in"].lo.clone() if self.split else None
-                self._one_step(ses, kind, coef, None, clip_range, side.cuda_stream, advance=False)
+                self._one_step(ses, kind, coef, clip_range, side.cuda_stream, philox=philox)
                 ses["x"].copy_(saved)
                 ses["unet_in"].hi.copy_(saved_in)
                 if self.split:
                     ses["unet_in"].lo.copy_(saved_lo)
+                ses["state"][0:2].zero_()
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._one_step(ses, kind, coef, None, clip_range, _lib.stream_ptr())
+                self._one_step(ses, kind, coef, clip_range, _lib.stream_ptr(), philox=philox)
             ses["graph"] = (gkey, g)
         g = ses["graph"][1]
         for _ in range(n_steps):
             g.replay()
-        n_unet = sum(len(p_["program"]) for p_ in ses["unet_parts"]) if ses.get("unet_parts") else len(ses["unet"]["program"])
-        if ses.get("unet_chain") is not None:
-            n_unet = 1  # the whole step is one cooperative launch
-        _lib.launch_count += n_steps * (n_unet + 1)
+        _lib.launch_count += n_steps * n_launch
 
     def _decode(self, ses, s):
         """predictor.py:993-1021."""
-        ses["d3d"]["program"].run(s)
+        for i in range(len(ses["starts"])):
+            ses["d3d"]["program"].run(s, variant=i)
         return ses["out"].clone()
 
     # ------------------------------------------------------------------------------ public API
@@ -261,7 +299,8 @@ class B200LatentDiffusionPredictor:
         if img.dim() != 5 or velocity_2d.dim() != 5:
             raise ValueError("img must be (batch, num_slices, 1, H, W) and velocity_2d (batch, num_slices, 3, H, W)")
         B, S = velocity_2d.shape[0], velocity_2d.shape[1]
-        if velocity_2d.shape[2] != 3 or img.shape[2] != 1 or img.shape[0] != B or img.shape[1] != S:
+        if velocity_2d.shape[2] != 3 or img.shape[2] != 1 or img.shape[0] != B or img.shape[1] not in (S, 1) \
+                or tuple(img.shape[3:]) != tuple(velocity_2d.shape[3:]):
             raise ValueError(f"shape mismatch: img {tuple(img.shape)} velocity_2d {tuple(velocity_2d.shape)}")
         return B, S, img.shape[3], img.shape[4]
 
@@ -277,25 +316,33 @@ class B200LatentDiffusionPredictor:
         mu, _ = self.vae.encode_3d_deterministic(x, div_scale=self.normalizer["output"].scale_factors)
         return mu.permute(0, 2, 1, 3, 4)
 
+    def ddim_timesteps(self, num_steps: int) -> List[int]:
+        """predictor.py:965: `torch.linspace(T-1, 0, num_steps, device=device).long()` -- built on the CUDA device like
+        the reference's production path, so the integer rounding is the same kernel's."""
+        return torch.linspace(self.num_timesteps - 1, 0, num_steps, device=self.device).long().tolist()
+
     def predict_ddim(self, img, velocity_2d, num_steps: int = 50, eta: float = 0.0, noise=None, *, step_noise=None, record=None):
         """predictor.py:898-1023."""
         B, S, H, W = self._check_inputs(img, velocity_2d)
         ses = self._get_session(B, S, H, W)
         s = _lib.stream_ptr()
-        timesteps = torch.linspace(self.num_timesteps - 1, 0, num_steps, dtype=torch.long).tolist()  # predictor.py:965
+        timesteps = self.ddim_timesteps(num_steps)
         self._bind_unet(ses, timesteps)
         ckey = ("ddim", tuple(timesteps), float(eta))
         if ses.get("coef_key") != ckey:
             ses["coef"] = self.scheduler.ddim_coef_rows(timesteps, eta).to(self.device)
             ses["coef_key"] = ckey
             ses["graph"] = None
+            ses["final"] = {}
         self._conditioning(ses, img.to(self.device), velocity_2d.to(self.device), s)
         if noise is None:
             noise = torch.randn(ses["N"], self.latent_channels, ses["h"], ses["w"], device=self.device)
         self._set_latent(ses, noise, s)
-        # eta == 0: no row draws noise -> seed 0 selects the scheduler kernel without the Philox generator
-        self.seed = 0 if (eta == 0.0 or step_noise is not None) else (int(torch.initial_seed()) & 0xFFFFFFFFFFFF) | 1
-        self._run_loop(ses, 1, ses["coef"], num_steps, step_noise, (-30.0, 30.0), record)
+        # eta == 0: no row draws noise -> the kernels without the Philox generator
+        philox = eta != 0.0 and step_noise is None
+        if philox:
+            self._new_seed(ses)
+        self._run_loop(ses, 1, ses["coef"], num_steps, step_noise, (-30.0, 30.0), record, philox)
         return self._decode(ses, s)
 
     def predict(self, img, velocity_2d, noise=None, *, step_noise=None, record=None):
@@ -317,12 +364,15 @@ class B200LatentDiffusionPredictor:
                 ses["coef"] = self.scheduler.ddpm_coef_rows(timesteps).to(self.device)
             ses["coef_key"] = ckey
             ses["graph"] = None
+            ses["final"] = {}
         self._conditioning(ses, img.to(self.device), velocity_2d.to(self.device), s)
         if noise is None:
             noise = torch.randn(ses["N"], self.latent_channels, ses["h"], ses["w"], device=self.device)
         self._set_latent(ses, noise, s)
-        self.seed = (int(torch.initial_seed()) & 0xFFFFFFFFFFFF) | 1
-        self._run_loop(ses, 0, ses["coef"], T, step_noise, (-30.0, 30.0), record)
+        philox = step_noise is None and T > 1
+        if philox:
+            self._new_seed(ses)
+        self._run_loop(ses, 0, ses["coef"], T, step_noise, (-30.0, 30.0), record, philox)
         return self._decode(ses, s)
 
     def eval(self):

@@ -99,12 +99,11 @@ class B200Scheduler:
             noise = noise.contiguous().float()
         if out is None:
             out = torch.empty_like(x_t)
-        # no noise tensor: the kernel draws N(0,1) itself (Philox) wherever the row's s != 0; a non-zero seed selects
-        # the kernel variant that carries the generator (include/b2d.h)
-        seed = 0 if noise is not None else (int(torch.initial_seed()) & 0xFFFFFFFFFFFF) | 1
+        # every caller below passes a noise tensor wherever the row's s != 0 (drawn from torch's generator like the
+        # reference's randn_like), so the lean kernel without the Philox generator is selected (seed 0)
         _lib.call("b2d_scheduler_step", kind, x_t.data_ptr(), eps.data_ptr(), _lib.ptr(noise), out.data_ptr(), x_t.numel(),
                   row_table.data_ptr(), None, int(row), 0, 1 if clip else 0, float(clip_range[0]), float(clip_range[1]),
-                  None, 0, 0, seed, _lib.stream_ptr())
+                  None, 0, 0, 0, None, None, _lib.stream_ptr())
         return out
 
     @staticmethod

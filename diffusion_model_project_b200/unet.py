@@ -12,7 +12,6 @@ are loaded (models.py:14-26,72-82, blocks.py:89-95).
 from __future__ import annotations
 
 import math
-import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -130,12 +129,16 @@ class B200UNet:
     # ------------------------------------------------------------------------------ program
     def build_program(self, N: int, h: int, w: int, *, x_in: Optional[Act] = None, eps_out: Optional[torch.Tensor] = None,
                       eps_mode: int = 1, temb_row: Optional[torch.Tensor] = None, temb_row_stride: int = 1,
-                      temb_table: Optional[torch.Tensor] = None, fuse_small: Optional[bool] = None) -> dict:
+                      temb_table: Optional[torch.Tensor] = None, fuse_small: bool = True, workspace: Optional[torch.Tensor] = None,
+                      final: bool = True) -> dict:
         """Allocate static buffers and conv plans for a batch of N (h x w) maps and record the launch list.
 
-        fuse_small (default: env B2D_UNET_FUSE_GN != "0"): where a sample has at most 65536 elements, the last norm of a
-        DoubleBlock + the attention pre-norm, and max-pool + norm, each run as ONE per-sample launch (engine.gn_gn_apply,
-        engine.maxpool_gn) instead of two launches that meet through global statistics.
+        fuse_small: where a sample has at most 65536 elements, the last norm of a DoubleBlock + the attention pre-norm,
+        and max-pool + norm, each run as ONE per-sample launch (engine.gn_gn_apply, engine.maxpool_gn) instead of two
+        launches that meet through global statistics.
+        workspace: split-K scratch of this program (engine.new_workspace; allocated if None).
+        final=False: stop before final_conv (unet/models.py:185); the caller appends it with `final_plan` -- the sampling
+        loop fuses the DDPM / DDIM update into that launch.
 
         x_in: channels-last input [N,1,h,w,pad64(in_channels)] (allocated if None);
         eps_out: fp32 output, planar [N,out,h,w] (eps_mode 1) or channels-last [N,h,w,out] (eps_mode 2).
@@ -143,8 +146,7 @@ class B200UNet:
         if not self._w:
             raise RuntimeError("B200UNet: load_state_dict() must be called before forward()")
         dev, sp, f = self.device, self.split, self.features
-        if fuse_small is None:
-            fuse_small = os.environ.get("B2D_UNET_FUSE_GN", "1") != "0"
+        ws = workspace if workspace is not None else engine.new_workspace(dev)
         nl = len(f)
         if h % (1 << nl) or w % (1 << nl):
             raise ValueError(f"B200UNet: input {h}x{w} must be divisible by {1 << nl} (five 2x2 max-pools)")
@@ -173,7 +175,7 @@ class B200UNet:
         if temb_row is None:
             temb_row = torch.zeros(N, dtype=torch.int32, device=dev)
             temb_row_stride = 1
-        if eps_out is None:
+        if eps_out is None and final:
             eps_out = torch.empty((N, self.out_channels, h, w) if eps_mode == 1 else (N, h, w, self.out_channels),
                                   dtype=torch.float32, device=dev)
         keep = []
@@ -187,23 +189,19 @@ class B200UNet:
             raw = new_act(N, 1, H * up, Wd * up, cout, dev, sp, f16=True)
             out = raw.as_bf16()
             st = stats_view(stats_alloc(1), N * 2)
-            plan = ConvPlan(inputs, pw, raw, cout=cout, nphase=nphase, stats=st, stats_cpg=cout)
+            plan = ConvPlan(inputs, pw, raw, cout=cout, nphase=nphase, stats=st, stats_cpg=cout, workspace=ws)
             prog.flops += plan.flops
-            prog.add(f"{name}.conv", plan.run, op=("conv", plan))
+            prog.add(f"{name}.conv", plan.run)
             g, b = gnw
-            tt = temb_table if temb_col is not None else None
-            tr = temb_row if temb_col is not None else None
             if second is not None:
                 assert temb_col is None and stats_out is None
                 name2, y2, g2, b2 = second
-                prog.add(f"{name}.gn+{name2}", lambda s: engine.gn_gn_apply(raw, out, y2, st, g, b, True, g2, b2, False, s),
-                         op=("unsupported", "gn_gn"))
+                prog.add(f"{name}.gn+{name2}", lambda s: engine.gn_gn_apply(raw, out, y2, st, g, b, True, g2, b2, False, s))
                 keep.append(plan)
                 return out
             prog.add(f"{name}.gn", lambda s, raw=raw, out=out, st=st, g=g, b=b, tc=temb_col, so=stats_out, cout=cout: engine.gn_apply(
                 raw, out, st, cout, g, b, True, s, temb=temb_table if tc is not None else None,
-                temb_row=temb_row if tc is not None else None, temb_row_stride=temb_row_stride, temb_col=tc or 0, stats_out=so),
-                op=("gn", raw, out, st, cout, g, b, True, tt, tr, temb_row_stride, temb_col or 0, stats_out, 1e-5))
+                temb_row=temb_row if tc is not None else None, temb_row_stride=temb_row_stride, temb_col=tc or 0, stats_out=so))
             keep.append(plan)
             return out
 
@@ -233,16 +231,15 @@ class B200UNet:
             g, b = W_[f"{prefix}.norm"]
             if xn is None:
                 xn = new_act(N, 1, H, Wd, c, dev, sp)
-                prog.add(f"{prefix}.gn", lambda s: engine.gn_apply(x, xn, st_in, c, g, b, False, s),
-                         op=("gn", x, xn, st_in, c, g, b, False, None, None, 0, 0, None, 1e-5))
+                prog.add(f"{prefix}.gn", lambda s: engine.gn_apply(x, xn, st_in, c, g, b, False, s))
             qkv = new_act(N, 1, H, Wd, 3 * c, dev, sp)
-            p1 = ConvPlan([xn], W_[f"{prefix}.in_proj"], qkv, cout=3 * c)
-            prog.add(f"{prefix}.in_proj", p1.run, op=("conv", p1))
+            p1 = ConvPlan([xn], W_[f"{prefix}.in_proj"], qkv, cout=3 * c, workspace=ws)
+            prog.add(f"{prefix}.in_proj", p1.run)
             ao = new_act(N, 1, H, Wd, c, dev, sp)
             prog.add(f"{prefix}.core", lambda s: _lib.call("b2d_attention", _lib.ptr(qkv.hi), _lib.ptr(qkv.lo), _lib.ptr(ao.hi),
-                                                            _lib.ptr(ao.lo), N, T, c, heads, s), op=("attn", qkv, ao, N, T, c, heads))
-            p2 = ConvPlan([ao], W_[f"{prefix}.out"], x, cout=c, residual=x)
-            prog.add(f"{prefix}.out_proj", p2.run, op=("conv", p2))
+                                                            _lib.ptr(ao.lo), N, T, c, heads, s))
+            p2 = ConvPlan([ao], W_[f"{prefix}.out"], x, cout=c, residual=x, workspace=ws)
+            prog.add(f"{prefix}.out_proj", p2.run)
             prog.flops += p1.flops + p2.flops + 4.0 * N * T * T * c
             keep.extend([p1, p2, xn, qkv, ao])
             return x
@@ -257,16 +254,13 @@ class B200UNet:
             pooled = new_act(N, 1, H // 2, Wd // 2, c, dev, sp)
             g, b = W_[f"encoder.{lvl}.2.norm"]
             if fuse_small and engine.fused_gn_ok(x, (H // 2) * (Wd // 2) * c):
-                prog.add(f"encoder.{lvl}.2.pool+gn", lambda s, x=x, pooled=pooled, g=g, b=b: engine.maxpool_gn(x, pooled, g, b, True, s),
-                         op=("unsupported", "maxpool_gn"))
+                prog.add(f"encoder.{lvl}.2.pool+gn", lambda s, x=x, pooled=pooled, g=g, b=b: engine.maxpool_gn(x, pooled, g, b, True, s))
                 x = pooled
                 H, Wd = H // 2, Wd // 2
                 continue
             st = stats_view(stats_alloc(1), N * 2)
-            prog.add(f"encoder.{lvl}.2.pool", lambda s, x=x, pooled=pooled, st=st: engine.maxpool_stats(x, pooled, st, s),
-                     op=("pool", x, pooled, st))
-            prog.add(f"encoder.{lvl}.2.gn", lambda s, pooled=pooled, st=st, g=g, b=b, c=c: engine.gn_apply(pooled, pooled, st, c, g, b, True, s),
-                     op=("gn", pooled, pooled, st, c, g, b, True, None, None, 0, 0, None, 1e-5))
+            prog.add(f"encoder.{lvl}.2.pool", lambda s, x=x, pooled=pooled, st=st: engine.maxpool_stats(x, pooled, st, s))
+            prog.add(f"encoder.{lvl}.2.gn", lambda s, pooled=pooled, st=st, g=g, b=b, c=c: engine.gn_apply(pooled, pooled, st, c, g, b, True, s))
             x = pooled
             H, Wd = H // 2, Wd // 2
         x = double("bottleneck", [x], 2 * f[-1], 2 * f[-1], H, Wd)
@@ -276,18 +270,27 @@ class B200UNet:
             H, Wd = H * 2, Wd * 2
             heads = rheads[lvl]
             x = double_attention(f"decoder.{lvl}.1", f"decoder.{lvl}.2", [skips[nl - 1 - lvl], up], c, H, Wd, heads)
-        pf = ConvPlan([x], W_["final_conv"], eps_out, cout=self.out_channels, out_mode=eps_mode,
-                      out_cstride=self.out_channels)
-        prog.flops += pf.flops
-        prog.add("final_conv", pf.run, op=("conv", pf))
-        keep.append(pf)
         assert stats_total[0] <= stats_buf.numel()
         used = stats_total[0]
-        steps = prog.steps
-        prog.steps = [("stats.zero", lambda s: _lib.call("b2d_zero", stats_buf.data_ptr(), used * 8, s))] + steps
-        prog.ops = [("zero", stats_buf, used * 8)] + prog.ops
-        return dict(program=prog, x_in=x_in, eps=eps_out, temb_row=temb_row, keep=keep, stats=stats_buf, skips=skips,
-                    temb_table=temb_table)
+        prog.steps = [("stats.zero", lambda s: _lib.call("b2d_zero", stats_buf.data_ptr(), used * 8, s))] + prog.steps
+        st = dict(program=prog, x_in=x_in, eps=eps_out, temb_row=temb_row, keep=keep, stats=stats_buf, skips=skips,
+                  temb_table=temb_table, final_in=x, workspace=ws, eps_mode=eps_mode)
+        # algorithmic FLOPs of final_conv belong to the step whether or not the caller fuses the sampler update into it
+        prog.flops += 2.0 * N * h * w * self.out_channels * 9 * x.C
+        if final:
+            pf = self.final_plan(st, eps_out=eps_out, eps_mode=eps_mode)
+            prog.add("final_conv", pf.run)
+            keep.append(pf)
+        return st
+
+    def final_plan(self, st: dict, *, eps_out: Optional[torch.Tensor] = None, eps_mode: int = 2, sched: Optional[dict] = None) -> ConvPlan:
+        """final_conv (unet/models.py:185) over the program's last activation.  sched: fuse the DDPM / DDIM update that
+        consumes eps into the epilogue (engine.ConvPlan `sched`; eps is stored only if eps_out is given, channels-last)."""
+        if sched is not None:
+            return ConvPlan([st["final_in"]], self._w["final_conv"], eps_out, cout=self.out_channels, out_mode=3,
+                            out_cstride=self.out_channels, workspace=st["workspace"], sched=sched)
+        return ConvPlan([st["final_in"]], self._w["final_conv"], eps_out, cout=self.out_channels, out_mode=eps_mode,
+                        out_cstride=self.out_channels, workspace=st["workspace"])
 
     # ------------------------------------------------------------------------------ module API
     def forward(self, x: torch.Tensor, time: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -299,6 +302,14 @@ class B200UNet:
         if not x.is_cuda:
             raise RuntimeError("B200UNet runs on a CUDA device only (no CPU fallback)")
         N, _, h, w = x.shape
+        if time is not None:
+            time = torch.as_tensor(time)
+            if time.numel() != N:
+                raise ValueError(f"time must hold one timestep per image ({N}), got {tuple(time.shape)}")
+            if self.temb_table is not None and (int(time.min()) < 0 or int(time.max()) >= self.num_timesteps):
+                # the reference evaluates the sinusoid for any t (models.py:14-26); this path reads a table built for
+                # t in [0, num_timesteps) -- refuse instead of reading outside it
+                raise ValueError(f"timesteps must lie in [0, {self.num_timesteps}), got [{int(time.min())}, {int(time.max())}]")
         key = (N, h, w)
         st = self._programs.get(key)
         if st is None:

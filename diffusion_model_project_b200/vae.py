@@ -6,8 +6,7 @@ engine in NDHWC bf16; GroupNorm(32) sums come out of the producing conv's epilog
 """
 from __future__ import annotations
 
-import os
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Sequence, Union
 
 import torch
 
@@ -56,11 +55,27 @@ class _Branch:
         self.cout = g("conv_out.weight").shape[0]
 
 
+# Lowering choices of the VAE programs.  The defaults are the measured-best forms; tests switch them off one at a time to
+# compare each fused form against the direct one.
+DEFAULT_OPTIONS = dict(
+    zstack=True,          # conv_in over a z-stacked input: 9 taps instead of 27 (bf16 mode)
+    zfold=True,           # conv_out (C -> 3) as a per-slice 3x3 conv with rows (kz, co) + a gather over z
+    upsample_fold=True,   # nn.Upsample + Conv3d as four phase convs on the low-resolution map
+    norm_fusion=False,    # GroupNorm + SiLU applied by the consumer conv to its staged tiles (256-wide N tiles only)
+)
+
+
+def _as_list(v, n):
+    return list(v) if isinstance(v, (list, tuple)) else [v] * n
+
+
 class _Builder:
     """Records a launch program for one branch over static NDHWC buffers."""
 
-    def __init__(self, B, device, split):
+    def __init__(self, B, device, split, workspace=None, options=None):
         self.B, self.dev, self.split = B, device, split
+        self.ws = workspace if workspace is not None else engine.new_workspace(device)
+        self.opt = dict(DEFAULT_OPTIONS, **(options or {}))
         self.prog = Program()
         self.keep: List[object] = []
         self.stats_buf = torch.zeros(B * 32 * 2 * 40, dtype=torch.float64, device=device)
@@ -75,7 +90,17 @@ class _Builder:
 
     def conv(self, name, x: Act, pw, cout, *, stride=1, want_stats=True, residual=None, out=None, raw=False, **kw):
         """raw=True: the output is only ever read by a GroupNorm apply or as a residual (never as an MMA operand),
-        so bf16 mode stores it as fp16 (finer rounding ahead of the normalisation, same 2 bytes)."""
+        so bf16 mode stores it as fp16 (finer rounding ahead of the normalisation, same 2 bytes).
+        x / out / out_mask may be lists: one plan per chunk variant (same weights, same intermediate buffers)."""
+        if isinstance(x, (list, tuple)) or isinstance(out, (list, tuple)) or isinstance(kw.get("out_mask"), (list, tuple)):
+            assert not want_stats and residual is None
+            nv = max(len(v) for v in (x, out, kw.get("out_mask")) if isinstance(v, (list, tuple)))
+            xs, outs, masks = _as_list(x, nv), _as_list(out, nv), _as_list(kw.pop("out_mask", None), nv)
+            plans = [ConvPlan([xs[i]], pw, outs[i], cout=cout, stride=stride, out_mask=masks[i], workspace=self.ws, **kw) for i in range(nv)]
+            self.prog.flops += plans[0].flops
+            self.prog.add(name, [pl.run for pl in plans])
+            self.keep.append(plans)
+            return outs, None
         N, D, H, W, _ = x.shape
         if out is None:
             out = new_act(N, D, H // stride, W // stride, cout, self.dev, self.split, f16=raw)
@@ -83,7 +108,7 @@ class _Builder:
             out = Act(out.hi, out.lo, raw and not self.split)
         st = self.stats() if want_stats else None
         plan = ConvPlan([x], pw, out, cout=cout, stride=stride, residual=residual, stats=st,
-                        stats_cpg=(cout // 32) if want_stats else 0, **kw)
+                        stats_cpg=(cout // 32) if want_stats else 0, workspace=self.ws, **kw)
         self.prog.flops += plan.flops
         self.prog.add(name, plan.run)
         self.keep.append(plan)
@@ -101,11 +126,9 @@ class _Builder:
         in-plane extent a multiple of 16, <= 512 input channels, bf16 mode).  Only worth it with 256-wide N tiles:
         the conv kernels sit at the shared-memory bandwidth roofline (tensor-core operand reads + TMA writes), and
         at BLOCK_N = 128 the in-place tile rewrite costs more than the HBM pass it saves; at 256 it is a wash
-        (profiles/README.md), so the fused path is opt-in (B2D_NORM_FUSION=1) and the default is a separate pass."""
+        (profiles/README.md), so the fused path is opt-in (options["norm_fusion"]) and the default is a separate pass."""
         _, _, H, W, C = x.shape
-        return (not self.split) and H % 16 == 0 and W % 16 == 0 and C <= 512 and cout % 256 == 0 \
-            and os.environ.get("B2D_NORM_FUSION") == "1" \
-            and os.environ.get("B2D_CONV_ENGINE", "2") == "2" and os.environ.get("B2D_CONV_NO_HALO") is None
+        return self.opt["norm_fusion"] and (not self.split) and H % 16 == 0 and W % 16 == 0 and C <= 512 and cout % 256 == 0
 
     def norm_conv(self, name, norm_name, x: Act, st_x, gnw, pw, cout, *, inplace_norm: bool, **kw):
         """conv(silu(GroupNorm32(x))): one launch when fusable (the conv normalises its staged input tiles in shared
@@ -127,16 +150,28 @@ class _Builder:
         return self.norm_conv(f"{name}.conv2", f"{name}.norm2", r, st_r, w[f"{name}.norm2"], w[f"{name}.conv2"], cout,
                               inplace_norm=True, residual=skip, want_stats=want_stats, raw=raw_out)
 
-    def conv_in(self, w, x_in: Act, cin: int, cout: int):
+    def conv_in(self, w, x_in: Union[Act, Sequence[Act]], cin: int, cout: int):
         """First conv of a branch (encoder.py:30 / decoder.py:31).  With few input channels the three z taps are moved into
-        the channel dimension first (b2d_zstack_cl + engine.pack_conv3d_zstack): a third of the MMAs."""
-        if "conv_in.zstack" in w and os.environ.get("B2D_NO_ZSTACK") is None:
-            N, D, H, W, C = x_in.shape
+        the channel dimension first (b2d_zstack_cl + engine.pack_conv3d_zstack): a third of the MMAs.
+        x_in may be a list (chunk variants: the same program reads a different slice of the caller's batch each run)."""
+        xl = list(x_in) if isinstance(x_in, (list, tuple)) else [x_in]
+        N, D, H, W, C = xl[0].shape
+        if "conv_in.zstack" in w and self.opt["zstack"]:
             xs = new_act(N, D, H, W, C, self.dev, False, zero=True)
-            self.keep.append(xs)
-            self.prog.add("conv_in.zstack", lambda s: _lib.call("b2d_zstack_cl", _lib.ptr(x_in.hi), _lib.ptr(xs.hi), N * D, D, H * W, cin, C, s))
+            self.keep.append((xs, xl))
+            self.prog.add("conv_in.zstack", [lambda s, xi=xi: _lib.call("b2d_zstack_cl", _lib.ptr(xi.hi), _lib.ptr(xs.hi), N * D, D, H * W, cin, C, s)
+                                             for xi in xl])
             return self.conv("conv_in", xs, w["conv_in.zstack"], cout, raw=True)
-        return self.conv("conv_in", x_in, w["conv_in"], cout, raw=True)
+        if len(xl) == 1:
+            return self.conv("conv_in", xl[0], w["conv_in"], cout, raw=True)
+        # chunk variants without the z-stack pass (fp32x mode): one plan per chunk input, one shared output + statistics
+        out = new_act(N, D, H, W, cout, self.dev, self.split, f16=True)
+        st = self.stats()
+        plans = [ConvPlan([xi], w["conv_in"], out, cout=cout, stats=st, stats_cpg=cout // 32, workspace=self.ws) for xi in xl]
+        self.prog.flops += plans[0].flops
+        self.prog.add("conv_in", [pl.run for pl in plans])
+        self.keep.append(plans)
+        return out, st
 
     def finish(self):
         used, buf = self.stats_used, self.stats_buf
@@ -146,7 +181,7 @@ class _Builder:
 
 class B200DualVAE:
     def __init__(self, in_channels: int = 3, latent_channels: int = 8, kernel_size: int = 3, share_encoders: bool = False,
-                 share_decoders: bool = False, *, precision: str = "bf16", device="cuda"):
+                 share_decoders: bool = False, *, precision: str = "bf16", device="cuda", options: Optional[dict] = None):
         if kernel_size != 3:
             raise NotImplementedError("B200DualVAE: kernel_size must be 3")
         if precision not in ("bf16", "fp32x"):
@@ -155,6 +190,7 @@ class B200DualVAE:
         self.split = precision == "fp32x"
         self.precision = precision
         self.device = torch.device(device)
+        self.options = dict(DEFAULT_OPTIONS, **(options or {}))
         self.branches: Dict[str, _Branch] = {}
         self._cache: Dict[tuple, dict] = {}
 
@@ -169,14 +205,15 @@ class B200DualVAE:
 
     # ------------------------------------------------------------------------------ programs
     def build_encoder(self, branch: str, B, D, H, W, *, x_in: Optional[Act] = None, out=None, out_mode=1, out_coff=0,
-                      out_cout=None) -> dict:
+                      out_cout=None, workspace=None) -> dict:
         """encoder.py:83-145.  out: planar fp32 [B][D][2*latent][h][w] (mode 1) or a channels-last Act
-        receiving the first `out_cout` channels (mu) at channel offset out_coff (mode 0)."""
+        receiving the first `out_cout` channels (mu) at channel offset out_coff (mode 0); a LIST of outputs makes the
+        program's last launch a chunk variant (program.run(stream, variant=i) writes out[i])."""
         if H % 4 or W % 4:
             raise ValueError("encoder input H, W must be divisible by 4")
         br = self.branches[branch]
         w = br.w
-        bd = _Builder(B, self.device, self.split)
+        bd = _Builder(B, self.device, self.split, workspace, self.options)
         if x_in is None:
             x_in = new_act(B, D, H, W, pad64(br.cin), self.device, self.split, zero=True)
         x, st = bd.conv_in(w, x_in, br.cin, 128)
@@ -198,11 +235,12 @@ class B200DualVAE:
         bd.norm_conv("conv_out", "norm_out", x, st, w["norm_out"], w["conv_out"], cout, inplace_norm=True, want_stats=False, out=out, **kw)
         return dict(program=bd.finish(), x_in=x_in, out=out, keep=bd.keep, stats=bd.stats_buf)
 
-    def build_decoder(self, branch: str, B, D, h, w_, *, z_in: Optional[Act] = None, out=None, out_scale=None, out_mask=None) -> dict:
-        """decoder.py:79-151.  out: planar fp32 [B][D][3][H][W] (optionally * out_scale[c] * out_mask)."""
+    def build_decoder(self, branch: str, B, D, h, w_, *, z_in=None, out=None, out_scale=None, out_mask=None, workspace=None) -> dict:
+        """decoder.py:79-151.  out: planar fp32 [B][D][3][H][W] (optionally * out_scale[c] * out_mask).
+        z_in / out / out_mask may be equally long lists: chunk variants of the first and last launches."""
         br = self.branches[branch]
         w = br.w
-        bd = _Builder(B, self.device, self.split)
+        bd = _Builder(B, self.device, self.split, workspace, self.options)
         if z_in is None:
             z_in = new_act(B, D, h, w_, pad64(br.cin), self.device, self.split, zero=True)
         x, st = bd.conv_in(w, z_in, br.cin, 512)
@@ -210,13 +248,13 @@ class B200DualVAE:
         x, _ = bd.res(w, "res1_2", x, st, 512, 512, want_stats=False, raw_out=False)   # -> upsample -> conv_up1
         for stage, (cin, cout, r1, r2, last) in enumerate(((512, 256, "res2_1", "res2_2", False), (256, 128, "res3_1", "res3_2", True)), 1):
             N_, D_, H_, W_, _ = x.shape
-            if f"conv_up{stage}.phase0" in w and H_ % 16 == 0 and W_ % 16 == 0 and os.environ.get("B2D_NO_UPSAMPLE_FOLD") is None:
+            if f"conv_up{stage}.phase0" in w and H_ % 16 == 0 and W_ % 16 == 0 and self.options["upsample_fold"]:
                 # nn.Upsample(scale=(1,2,2)) + Conv3d == 4 phase convs with 2x2x3 taps on the low-resolution map
                 y = new_act(N_, D_, 2 * H_, 2 * W_, cout, self.device, self.split, f16=True)
                 st = bd.stats()
                 for ph in range(4):
                     plan = ConvPlan([x], w[f"conv_up{stage}.phase{ph}"], y, cout=cout, stats=st, stats_cpg=cout // 32,
-                                    out_geom=(2 * H_, 2 * W_, 2, 2, ph >> 1, ph & 1))
+                                    out_geom=(2 * H_, 2 * W_, 2, 2, ph >> 1, ph & 1), workspace=bd.ws)
                     bd.prog.flops += plan.flops
                     bd.prog.add(f"conv_up{stage}.phase{ph}", plan.run)
                     bd.keep.append(plan)
@@ -230,17 +268,21 @@ class B200DualVAE:
         H, W = 4 * h, 4 * w_
         if out is None:
             out = torch.empty((B, D, br.cout, H, W), dtype=torch.float32, device=self.device)
-        if "conv_out.zfold" in w and H % 16 == 0 and W % 16 == 0 and os.environ.get("B2D_NO_ZFOLD") is None:
+        if "conv_out.zfold" in w and H % 16 == 0 and W % 16 == 0 and self.options["zfold"]:
             # Conv3d 128 -> 3: nine in-plane taps per slice with rows (kz, co), then a gather over z (engine.pack_conv3d_zfold)
             hn = bd.gn_silu("norm_out", x, st, w["norm_out"], inplace=True)
             P = torch.empty((B, D, H, W, 12), dtype=torch.float32, device=self.device)
-            plan = ConvPlan([hn], w["conv_out.zfold"], P, cout=12, out_mode=2, out_cstride=12)
+            plan = ConvPlan([hn], w["conv_out.zfold"], P, cout=12, out_mode=2, out_cstride=12, workspace=bd.ws)
             bd.prog.flops += plan.flops
             bd.prog.add("conv_out.zfold", plan.run)
             bd.keep.append((plan, P))
             bias, co = w["conv_out.bias"], br.cout
-            bd.prog.add("conv_out.combine", lambda s: _lib.call("b2d_zfold_combine", P.data_ptr(), B * D, D, H, W, co, _lib.ptr(bias),
-                                                                _lib.ptr(out_scale), _lib.ptr(out_mask), out.data_ptr(), co, 0, s))
+            nv = len(out) if isinstance(out, (list, tuple)) else 1
+            outs, masks = _as_list(out, nv), _as_list(out_mask, nv)
+            bd.keep.append((outs, masks))
+            bd.prog.add("conv_out.combine", [lambda s, o=o, m=m: _lib.call("b2d_zfold_combine", P.data_ptr(), B * D, D, H, W, co, _lib.ptr(bias),
+                                                                            _lib.ptr(out_scale), _lib.ptr(m), o.data_ptr(), co, 0, s)
+                                             for o, m in zip(outs, masks)])
         else:
             bd.norm_conv("conv_out", "norm_out", x, st, w["norm_out"], w["conv_out"], br.cout, inplace_norm=True, want_stats=False,
                          out=out, out_mode=1, out_cstride=br.cout, out_scale=out_scale, out_mask=out_mask)

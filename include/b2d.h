@@ -33,7 +33,7 @@ extern "C" {
 #define B2D_API
 #endif
 
-#define B2D_VERSION 5
+#define B2D_VERSION 6
 #define B2D_MAX_SEG 6
 #define B2D_MAX_TAPS 27
 
@@ -57,13 +57,17 @@ B2D_API const char* b2d_last_error(void);
  * (step_idx ? *step_idx : 0) + step_off, so a captured graph can advance a device counter.
  * z = noise[i] if noise != NULL, else (if s != 0) N(0,1) from Philox4x32-10(seed, row, i); seed == 0 with
  * noise == NULL asserts s == 0 for the rows used (deterministic DDIM) and selects the kernel without the generator.
+ * seed_dev != NULL: the Philox key is read from that device word at run time (and the generator kernel is selected), so a
+ * captured graph draws fresh noise on every call without being re-captured; `seed` is then ignored.
  * Optional second output for the fused loop: x_bf16[(i / group) * group_stride + i % group].
- * If step_inc != 0 the kernel's last block adds step_inc to *step_idx after all reads.
+ * If step_inc != 0 the kernel's last block adds step_inc to *step_idx after all reads; `ticket` is the caller-owned,
+ * zero-initialised arrival counter of that protocol (one per sampling loop: loops on different streams never share
+ * state; the kernel leaves it zero).  Required when step_inc != 0.
  * ---------------------------------------------------------------------------------------- */
 B2D_API int b2d_scheduler_step(int kind, const float* x_t, const float* eps, const float* noise, float* x_out,
                        int64_t n_elem, const float* coef, int* step_idx, int step_off, int step_inc,
                        int clip, float clip_lo, float clip_hi, void* x_bf16, int group, int group_stride,
-                       uint64_t seed, void* stream);
+                       uint64_t seed, const uint64_t* seed_dev, unsigned int* ticket, void* stream);
 
 /* q_sample (diffusion.py:78-101): out = a*x0 + b*noise with per-image a,b (device [n_img]). */
 B2D_API int b2d_q_sample(const float* x0, const float* noise, float* out, const float* a, const float* b,
@@ -99,7 +103,8 @@ typedef struct b2d_conv_desc {
   const float* bias;               /* [cout] or NULL                                            */
   void* out;                       /* see out_mode                                              */
   void* out_lo;                    /* optional bf16 residual part (x - bf16(x)), mode 0, or NULL */
-  int32_t out_mode;                /* 0 bf16 NDHWC, 1 fp32 planar [N][D][C][H][W], 2 fp32 NDHWC */
+  int32_t out_mode;                /* 0 bf16 NDHWC, 1 fp32 planar [N][D][C][H][W], 2 fp32 NDHWC,
+                                      3 fused scheduler update (see sched_* below; `out` optionally receives eps as mode 2) */
   int32_t out_H, out_W;            /* extent of the output tensor                               */
   int32_t out_sy, out_sx, out_oy, out_ox; /* out pixel = oy*out_sy + out_oy (+ phase)           */
   int32_t out_cstride, out_coff;   /* channel stride / offset of the output tensor              */
@@ -114,9 +119,10 @@ typedef struct b2d_conv_desc {
   int32_t out_f16;                 /* mode 0: store IEEE fp16 (saturating) instead of bf16 -- for raw pre-GroupNorm
                                       outputs / residual streams that are never an MMA operand            */
   int32_t res_f16;                 /* residual tensor holds fp16 instead of bf16                         */
-  int32_t engine;                  /* 0 = auto, 1 = one tile per CTA (conv_igemm.cu), 2 = persistent (conv_igemm2.cu) */
+  int32_t tune_ksplit;             /* 0 = cost model, 1..16 = force this K split (tools/tune_conv.py)                  */
   void* workspace;                 /* optional caller-owned scratch for split-K (first 16 KB: zero-initialised arrival
-                                      counters, then fp32 partial tiles); shared by plans that run on one stream      */
+                                      counters, then fp32 partial tiles).  Plans that share one must run back to back on
+                                      ONE stream; give concurrent sampling loops their own                            */
   int64_t workspace_bytes;
   /* Fused input normalisation (persistent engine, halo staging, one segment, cin <= 512): in[0] holds the RAW
    * pre-GroupNorm output of the producer (fp16 if in_f16, else bf16) and the kernel applies
@@ -128,8 +134,34 @@ typedef struct b2d_conv_desc {
   int32_t in_cpg, in_creal;        /* channels per group; real (unpadded) input channels                 */
   int32_t in_f16, in_act;
   float in_eps;
+  int32_t tune_flags;              /* B2D_TUNE_* bits (comparison arms of the tests / tools; 0 in production)      */
+  /* out_mode 3 -- the UNet's final_conv (unet/models.py:185) fused with the sampler update that consumes it
+   * (diffusion.py:152-188 / :195-234): the epilogue computes eps = conv + bias for the cout (4, 8, 12 or 16) channels of
+   * a pixel and applies b2d_scheduler_step's arithmetic (same operation order, same Philox counters: bit-identical to
+   * the two-launch form) to the fp32 master latent sched_x [pixels][cout] in place, so eps never reaches HBM (unless
+   * `out` != NULL).  The bf16 copy goes to sched_x_bf16[pixel * sched_bf16_stride + c] (+ the hi/lo remainder to
+   * sched_x_bf16_lo).  The last CTA to finish adds sched_step_inc to *sched_step_idx (ticket protocol as above). */
+  int32_t sched_kind;              /* 0 DDPM, 1 DDIM                                                               */
+  float* sched_x;                  /* fp32 [N*D*OH*OW][cout], read and rewritten                                    */
+  const float* sched_noise;        /* same shape, or NULL (in-kernel Philox when the row's s != 0)                   */
+  const float* sched_coef;         /* rows {a, b, c1, c2, s, 0, 0, 0}                                               */
+  int32_t* sched_step_idx;         /* device step counter (row = *idx + sched_step_off), or NULL                    */
+  uint32_t* sched_ticket;          /* zero-initialised arrival counter, required when sched_step_inc != 0           */
+  const uint64_t* sched_seed_dev;  /* Philox key read at run time, or NULL: sched_seed (0 = rows never draw noise)  */
+  uint64_t sched_seed;
+  int32_t sched_step_off, sched_step_inc;
+  int32_t sched_clip;
+  float sched_clip_lo, sched_clip_hi;
+  void* sched_x_bf16;              /* optional bf16 copy of the new latent (the UNet's input buffer)                */
+  void* sched_x_bf16_lo;           /* optional x - bf16(x) (fp32x mode)                                             */
+  int32_t sched_bf16_stride;       /* channel stride of that buffer                                                 */
   int32_t reserved[3];
 } b2d_conv_desc;
+
+#define B2D_TUNE_NO_HALO 1    /* generic tiles even where halo staging applies   */
+#define B2D_TUNE_NO_SPLITK 2  /* never split the K loop                          */
+#define B2D_TUNE_CONTIG 4     /* CTAs walk contiguous unit ranges                */
+#define B2D_TUNE_STRIDED 8    /* CTAs walk the unit list strided over the grid   */
 
 typedef struct b2d_conv_plan b2d_conv_plan;
 B2D_API int b2d_conv_plan_create(const b2d_conv_desc* desc, b2d_conv_plan** plan);
@@ -137,7 +169,7 @@ B2D_API int b2d_conv_plan_destroy(b2d_conv_plan* plan);
 B2D_API int b2d_conv_run(const b2d_conv_plan* plan, void* stream);
 /* number of CTAs / block_n the plan launches with (introspection for tests and the bench) */
 B2D_API int b2d_conv_plan_info(const b2d_conv_plan* plan, int32_t* grid_m, int32_t* grid_n, int32_t* block_n, int32_t* kblocks);
-/* out[8] = {engine, halo, ksplit, work units, CTAs launched, block_n, K-loop groups, workspace bytes used (KiB)} */
+/* out[8] = {engine generation (2), halo, ksplit, work units, CTAs launched, block_n, K-loop groups, workspace bytes used (KiB)} */
 B2D_API int b2d_conv_plan_info2(const b2d_conv_plan* plan, int32_t* out8);
 
 /* ------------------------------------------------------------------------------------------
@@ -212,32 +244,6 @@ B2D_API int b2d_bilinear_resize(const float* x, float* y, int32_t n_img, int32_t
 
 /* fill helpers used by the fused loop (graph-capturable) */
 B2D_API int b2d_zero(void* p, int64_t bytes, void* stream);
-
-/* ------------------------------------------------------------------------------------------
- * Chain: a run of dependent layers executed inside ONE cooperative persistent kernel, with a grid
- * barrier in place of every kernel boundary (csrc/conv_chain.cu).  Ops are appended in execution
- * order from already-created conv plans (persistent engine) and from the same arguments the
- * stand-alone entry points take; bf16 mode only.  b2d_chain_bind copies the op list into a
- * caller-owned device buffer (num_ops * b2d_chain_op_bytes(), 128-byte aligned) and takes a
- * zero-initialised int32 buffer of 2 + 2 * (num_ops + 1) words: two barrier counters, then one 64-bit
- * %globaltimer stamp per op boundary (diagnostics); b2d_chain_run launches it (graph-capturable).
- * ---------------------------------------------------------------------------------------- */
-enum b2d_chain_op_kind { B2D_CHAIN_CONV = 1, B2D_CHAIN_GN = 2, B2D_CHAIN_POOL = 3, B2D_CHAIN_ATTN = 4, B2D_CHAIN_ZERO = 5 };
-typedef struct b2d_chain b2d_chain;
-B2D_API int b2d_chain_create(b2d_chain** chain);
-B2D_API int b2d_chain_destroy(b2d_chain* chain);
-B2D_API int64_t b2d_chain_op_bytes(void);
-B2D_API int32_t b2d_chain_num_ops(const b2d_chain* chain);
-B2D_API int b2d_chain_add_conv(b2d_chain* chain, const b2d_conv_plan* plan);
-B2D_API int b2d_chain_add_gn(b2d_chain* chain, const void* x, void* y, int32_t N, int64_t P, int32_t C, const double* stats,
-                     int32_t cpg, const float* gamma, const float* beta, float eps, int32_t act, const float* temb_table,
-                     const int32_t* temb_row, int32_t temb_row_stride, int32_t temb_ld, int32_t temb_col, double* stats_out,
-                     int32_t in_f16);
-B2D_API int b2d_chain_add_pool(b2d_chain* chain, const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, double* stats);
-B2D_API int b2d_chain_add_attention(b2d_chain* chain, const void* qkv, void* out, int32_t N, int32_t T, int32_t C, int32_t heads);
-B2D_API int b2d_chain_add_zero(b2d_chain* chain, void* p, int64_t bytes);
-B2D_API int b2d_chain_bind(b2d_chain* chain, void* dev_ops, int64_t dev_bytes, int32_t* barrier2, void* stream);
-B2D_API int b2d_chain_run(const b2d_chain* chain, void* stream);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from diffusion_model_project_b200 import engine
+from diffusion_model_project_b200 import _lib, engine
 from diffusion_model_project_b200.engine import ConvPlan, new_act
 from util import bf16_round, from_act, no_tf32, rel_err, stats_ref, to_act
 
@@ -222,27 +222,46 @@ def _conv2d_case(g, N, ci, co, H, W):
 
 
 @pytest.mark.parametrize("N,ci,co,H,W", [(3, 64, 64, 32, 16), (2, 128, 256, 16, 16), (5, 256, 128, 8, 8), (7, 512, 512, 4, 4)])
-def test_persistent_engine_matches_first_engine(N, ci, co, H, W):
-    """engine=2 (persistent: halo staging where W,H % 16 == 0, split-K where the tile count is small) against
-    engine=1 (one tile per CTA) on the same operands: both accumulate bf16 products in fp32, only the summation
-    order differs."""
+def test_tiling_variants_agree(N, ci, co, H, W):
+    """The plan's own choices (halo staging where W,H % 16 == 0, split-K where the tile count is small, contiguous unit
+    walk) against the plain comparison arm selected through b2d_conv_desc.tune_flags (generic 128-row tiles, no K split,
+    strided walk) on the same operands: both accumulate bf16 products in fp32, only the summation order differs."""
     no_tf32()
     g = torch.Generator().manual_seed(31 + ci)
     x, w = _conv2d_case(g, N, ci, co, H, W)
     pw = engine.pack_conv2d(w, [ci], None, DEV)
     outs, stats, infos = [], [], []
-    for eng in (1, 2):
+    plain = _lib.TUNE_NO_HALO | _lib.TUNE_NO_SPLITK | _lib.TUNE_STRIDED
+    for flags in (plain, 0):
         out = new_act(N, 1, H, W, co, DEV)
         st = torch.zeros(N, 2, dtype=torch.float64, device=DEV)
-        plan = ConvPlan([to_act(x)], pw, out, cout=co, stats=st, stats_cpg=co, engine=eng)
+        plan = ConvPlan([to_act(x)], pw, out, cout=co, stats=st, stats_cpg=co, tune_flags=flags)
         plan.run(_stream())
         outs.append(from_act(out, co)); stats.append(st.clone()); infos.append(plan.info2())
-    assert infos[0]["engine"] == 1 and infos[1]["engine"] == 2
+    assert infos[0]["halo"] == 0 and infos[0]["ksplit"] == 1
     assert infos[1]["halo"] == (1 if H % 16 == 0 and W % 16 == 0 else 0)
     ref = F.conv2d(x[:, :, 0], w, None, padding=1)[:, :, None]
     assert rel_err(outs[1], ref) < TOL_BF16
     assert rel_err(outs[1], outs[0]) < 8e-3  # one bf16 ulp of the output at most
     assert ((stats[1] - stats[0]).abs().max() / stats[0].abs().max()).item() < 1e-5
+
+
+def test_forced_k_split_matches_cost_model_choice():
+    """b2d_conv_desc.tune_ksplit (tools/tune_conv.py) forces a split count; the result does not depend on it beyond fp32
+    summation order."""
+    no_tf32()
+    g = torch.Generator().manual_seed(43)
+    N, ci, co = 5, 512, 512
+    x, w = _conv2d_case(g, N, ci, co, 4, 4)
+    pw = engine.pack_conv2d(w, [ci], None, DEV)
+    outs = []
+    for ks in (1, 3, 8):
+        out = new_act(N, 1, 4, 4, co, DEV)
+        plan = ConvPlan([to_act(x)], pw, out, cout=co, tune_ksplit=ks)
+        assert plan.info2()["ksplit"] == ks
+        plan.run(_stream())
+        outs.append(from_act(out, co))
+    assert rel_err(outs[1], outs[0]) < 8e-3 and rel_err(outs[2], outs[0]) < 8e-3
 
 
 def test_split_k_is_deterministic_and_reuses_workspace():
@@ -255,7 +274,8 @@ def test_split_k_is_deterministic_and_reuses_workspace():
     pw = engine.pack_conv2d(w, [ci], None, DEV)
     out = new_act(N, 1, 2, 2, co, DEV)
     st = torch.zeros(N, 2, dtype=torch.float64, device=DEV)
-    plan = ConvPlan([to_act(x)], pw, out, cout=co, stats=st, stats_cpg=co)
+    ws = engine.new_workspace(DEV)
+    plan = ConvPlan([to_act(x)], pw, out, cout=co, stats=st, stats_cpg=co, workspace=ws)
     info = plan.info2()
     assert info["ksplit"] > 1 and info["ws_kib"] > 0, info
     plan.run(_stream())
@@ -266,7 +286,7 @@ def test_split_k_is_deterministic_and_reuses_workspace():
         assert torch.equal(out.hi, first)
     ref = F.conv2d(x[:, :, 0], w, None, padding=1)[:, :, None]
     assert rel_err(from_act(out, co), ref) < TOL_BF16
-    assert int(engine.workspace(DEV)[:16384].view(torch.int32).abs().sum()) == 0  # arrival counters back to zero
+    assert int(ws[:16384].view(torch.int32).abs().sum()) == 0  # arrival counters back to zero
 
 
 @pytest.mark.parametrize("ci,co", [(256, 128), (128, 256)])

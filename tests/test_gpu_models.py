@@ -97,10 +97,10 @@ def test_vae_ragged_depth_and_batch(vae_sd):
     assert rel_l2(mu.cpu(), mu_ref) <= 1e-2
 
 
-def _predictor(unet_sd, vae_sd, precision, T=1000, graph=True, S=2):
+def _predictor(unet_sd, vae_sd, precision, T=1000, graph=True, S=2, **kw):
     return B200LatentDiffusionPredictor(
         "UNet", dict(synth.UNET_KWARGS), True, unet_state=unet_sd, vae_state=vae_sd, norm_factors=synth.NORM_FACTORS,
-        num_slices=S, num_timesteps=T, precision=precision, use_graph=graph, device="cuda")
+        num_slices=S, num_timesteps=T, precision=precision, use_graph=graph, device="cuda", **kw)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32x"])
@@ -162,15 +162,132 @@ def test_predict_batch2_matches_per_sample(unet_sd, vae_sd):
     assert rel_l2(both[1:], one) <= 2e-3
 
 
-def test_in_kernel_noise_ddpm_runs_and_is_seeded(unet_sd, vae_sd):
+@pytest.mark.parametrize("fuse", [True, False])
+def test_in_kernel_noise_is_seeded_and_fresh_per_call(unet_sd, vae_sd, fuse):
+    """The reference draws torch.randn_like in every step of every call (diffusion.py:175).  The in-kernel Philox key is
+    drawn from torch's generator per call and read from the session's device state by the CAPTURED graph: the same
+    manual_seed reproduces a run, consecutive calls and different seeds give different fields, without re-capture."""
     img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=3)
     noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=2)
-    p = _predictor(unet_sd, vae_sd, "bf16", T=4)
+    p = _predictor(unet_sd, vae_sd, "bf16", T=4, fuse_scheduler=fuse)
     torch.manual_seed(5)
     a = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()
+    graph = p._session["graph"][1]
+    a2 = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()          # generator advanced: new noise
     torch.manual_seed(5)
     b = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()
+    torch.manual_seed(6)
+    c = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()
+    assert p._session["graph"][1] is graph                                     # one capture served all four calls
     assert torch.isfinite(a).all() and torch.equal(a, b)
+    assert not torch.equal(a, a2) and not torch.equal(a, c)
+    # DDIM with eta > 0 draws in-kernel noise too
+    torch.manual_seed(7)
+    d1 = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=3, eta=0.5, noise=noise.cuda()).cpu()
+    d2 = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=3, eta=0.5, noise=noise.cuda()).cpu()
+    assert torch.isfinite(d1).all() and not torch.equal(d1, d2)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+def test_fused_sampler_update_is_bit_identical_to_two_launches(unet_sd, vae_sd, precision):
+    """final_conv (unet/models.py:185) with the DDPM / DDIM update (diffusion.py:152-234) in its epilogue
+    against final_conv -> eps in HBM -> b2d_scheduler_step: same fp32 operation order, same Philox counters, so the
+    latent trajectory, the recorded eps and the decoded field are bit-identical."""
+    img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=5)
+    noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=6)
+    gen = torch.Generator().manual_seed(101)
+    zs = [torch.randn(2, 8, 32, 32, generator=gen) for _ in range(5)]
+    res = {}
+    for fuse in (True, False):
+        p = _predictor(unet_sd, vae_sd, precision, T=5, graph=False, fuse_scheduler=fuse)
+        rec = []
+        ddpm = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda(), step_noise=zs, record=rec).cpu()
+        rec2 = []
+        ddim = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=4, eta=0.0, noise=noise.cuda(), record=rec2).cpu()
+        pg = _predictor(unet_sd, vae_sd, precision, T=5, graph=True, fuse_scheduler=fuse)
+        torch.manual_seed(11)
+        philox = pg.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()      # in-kernel noise, captured graph
+        ddim_g = pg.predict_ddim(img.cuda(), v2d.cuda(), num_steps=4, eta=0.0, noise=noise.cuda()).cpu()
+        res[fuse] = (ddpm, rec, ddim, rec2, philox, ddim_g)
+    f, u = res[True], res[False]
+    assert torch.equal(f[0], u[0]) and torch.equal(f[2], u[2]) and torch.equal(f[4], u[4]) and torch.equal(f[5], u[5])
+    assert torch.equal(f[2], f[5])                                               # graph == eager
+    for rf, ru in ((f[1], u[1]), (f[3], u[3])):
+        assert len(rf) == len(ru)
+        for a, b in zip(rf, ru):
+            assert all(torch.equal(x, y) for x, y in zip(a, b))                  # x_t, eps, x_{t-1} of every step
+
+
+def test_predict_one_shot_branch(unet_sd, vae_sd):
+    """num_timesteps == 1 (predictor.py:823-838): one UNet call at t = 0 and x0 = clamp((x - sqrt(1-abar) eps)/sqrt(abar))."""
+    img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=8)
+    noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=9)
+    ref = opred.predict(unet_sd, vae_sd, img, v2d, noise, None, norm_factors=synth.NORM_FACTORS, num_timesteps=1)
+    for fuse in (True, False):
+        p = _predictor(unet_sd, vae_sd, "fp32x", T=1, fuse_scheduler=fuse)
+        out = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()
+        assert rel_l2(out, ref) <= 1e-3, rel_l2(out, ref)
+
+
+def test_micro_batched_vae_matches_single_pass(unet_sd, vae_sd):
+    """Large batches: E2D / D3D run in chunks of `vae_chunk` samples over one set of activation buffers (a ragged tail
+    re-runs the last chunk), the UNet loop over all slices at once.  B = 3 in chunks of 2 == one pass over 3."""
+    img, v2d = synth.synth_inputs(3, num_slices=2, size=128, seed=12)
+    noise = synth.synth_noise(3, num_slices=2, latent_size=32, seed=13)
+    outs = []
+    for chunk, precision in ((3, "bf16"), (2, "bf16"), (1, "bf16"), (3, "fp32x"), (2, "fp32x")):
+        p = _predictor(unet_sd, vae_sd, precision, vae_chunk=chunk)
+        outs.append(p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu())
+        assert p._session["starts"] == {3: [0], 2: [0, 1], 1: [0, 1, 2]}[chunk]
+    # a different chunk size changes the VAE tile / split choices (fp32 summation order) only
+    assert rel_l2(outs[1], outs[0]) <= 2e-3 and rel_l2(outs[2], outs[0]) <= 2e-3
+    assert rel_l2(outs[4], outs[3]) <= 1e-4
+    ref = opred.predict_ddim(unet_sd, vae_sd, img, v2d, noise, num_steps=2, norm_factors=synth.NORM_FACTORS)
+    assert rel_l2(outs[1], ref) <= 1e-2 and rel_l2(outs[4], ref) <= 1e-3
+
+
+def test_two_sampling_loops_on_two_streams(unet_sd, vae_sd):
+    """Re-entrancy of the boundary (include/b2d.h): every piece of mutable device state -- split-K scratch and arrival
+    counters, the step index, its ticket and the Philox key -- belongs to a predictor session, so two predictors
+    sampling CONCURRENTLY on two streams of one device give exactly their serial results."""
+    cases = []
+    for k in range(2):
+        img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=20 + k)
+        noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=30 + k)
+        p = _predictor(unet_sd, vae_sd, "bf16", T=6)
+        cases.append((p, img.cuda(), v2d.cuda(), noise.cuda()))
+    serial = []
+    for k, (p, img, v2d, noise) in enumerate(cases):
+        torch.manual_seed(40 + k)
+        serial.append((p.predict_ddim(img, v2d, num_steps=12, noise=noise).clone(), p.predict(img, v2d, noise=noise).clone()))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rounds in range(3):
+        got = [None, None]
+        for k, (p, img, v2d, noise) in enumerate(cases):
+            streams[k].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[k]):
+                torch.manual_seed(40 + k)
+                got[k] = (p.predict_ddim(img, v2d, num_steps=12, noise=noise), p.predict(img, v2d, noise=noise))
+        torch.cuda.synchronize()
+        for k in range(2):
+            assert torch.equal(got[k][0], serial[k][0]) and torch.equal(got[k][1], serial[k][1])
+
+
+def test_broadcast_mask_and_input_validation(unet_sd, vae_sd):
+    img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=14)
+    img[:, 1] = img[:, 0]
+    noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=15)
+    p = _predictor(unet_sd, vae_sd, "bf16")
+    full = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()
+    one = p.predict_ddim(img[:, :1].cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()   # (B,1,1,H,W) mask
+    assert torch.equal(full, one)
+    with pytest.raises(ValueError):
+        p.predict_ddim(img.cuda()[..., :64], v2d.cuda(), num_steps=2)
+    m = p.model
+    with pytest.raises(ValueError):   # the time-embedding table covers [0, num_timesteps)
+        m(torch.zeros(1, 17, 32, 32, device="cuda"), torch.tensor([1000], device="cuda"))
+    assert p.ddim_timesteps(50) == torch.linspace(999, 0, 50).long().tolist() and p.ddim_timesteps(50)[-3:] == [40, 20, 0]
 
 
 def test_e3d_encoder_and_sanity_roundtrip():
@@ -189,7 +306,7 @@ def test_e3d_encoder_and_sanity_roundtrip():
     assert rec.shape == x.shape and rel_l2(rec, rec_ref) <= 1.5e-2  # two bf16 networks back to back
 
 
-def test_zfold_conv_out_and_zstack_conv_in_match_direct_convs(vae_sd, monkeypatch):
+def test_zfold_conv_out_and_zstack_conv_in_match_direct_convs(vae_sd):
     """decoder.py:71 conv_out (128 -> 3) as a z-folded conv (9 taps with rows (kz, co) + b2d_zfold_combine) and decoder.py:31
     / encoder.py:30 conv_in over a z-stacked input (b2d_zstack_cl), against the direct 27-tap convs of the same engine,
     and both against the CPU oracle; ragged depth (edge slices use zero padding)."""
@@ -198,10 +315,8 @@ def test_zfold_conv_out_and_zstack_conv_in_match_direct_convs(vae_sd, monkeypatc
     ref = ovae.decode_3d(vae_sd, z)
     outs = {}
     for mode in ("zfold", "direct"):
-        if mode == "direct":
-            monkeypatch.setenv("B2D_NO_ZFOLD", "1")
-            monkeypatch.setenv("B2D_NO_ZSTACK", "1")
-        vae = B200DualVAE(3, 8, device="cuda").load_state_dict(vae_sd)
+        opts = dict(zfold=False, zstack=False) if mode == "direct" else None
+        vae = B200DualVAE(3, 8, device="cuda", options=opts).load_state_dict(vae_sd)
         st = vae.build_decoder("decoder_3d", 2, 5, 8, 8)
         names = [n for n, _ in st["program"].steps]
         assert ("conv_out.zfold" in names) == (mode == "zfold") and ("conv_in.zstack" in names) == (mode == "zfold")

@@ -1,6 +1,6 @@
 """Smallest program that launches one planned convolution of the sampling path, for quick timing of engine /
 tile variants and as the target of `ncu --set full -k regex:conv_`.
-usage: python tools/profile_conv.py kind N cin cout H [block_n] [engine] [reps]
+usage: python tools/profile_conv.py kind N cin cout H [block_n] [tune_flags] [reps]
   kind = 3d  : Conv3d 3x3x3 on [N][11][H][H][cin]   (VAE; default 8 128 128 256 = D3D res3 conv)
   kind = 2d  : Conv2d 3x3 on [N][1][H][H][cin]      (UNet; e.g. 88 64 64 64 = encoder.0 block2)
   kind = 1x1 : Linear on [N][1][H][H][cin]          (UNet attention projections; e.g. 88 256 768 16 = enc2 in_proj)"""
@@ -21,7 +21,7 @@ cin = int(a[2]) if len(a) > 2 else 128
 cout = int(a[3]) if len(a) > 3 else 128
 H = int(a[4]) if len(a) > 4 else 256
 bn = int(a[5]) if len(a) > 5 else 0
-eng = int(a[6]) if len(a) > 6 else 0
+flags = int(a[6]) if len(a) > 6 else 0  # b2d_conv_desc.tune_flags (B2D_TUNE_*)
 reps = int(a[7]) if len(a) > 7 else 5
 use_stats = int(a[8]) if len(a) > 8 else 1
 D = 11 if kind == "3d" else 1
@@ -50,7 +50,7 @@ up = 2 if kind == "convT" else 1
 out = new_act(N, D, H * up, H * up, cout, dev, f16=(kind == "convT"))
 st = torch.zeros(N, groups, 2, dtype=torch.float64, device=dev)
 plan = ConvPlan([x], pw, out, cout=cout, nphase=4 if kind == "convT" else 1, stats=st if use_stats else None,
-                stats_cpg=cout // groups if use_stats else 0, block_n=bn, engine=eng)
+                stats_cpg=cout // groups if use_stats else 0, block_n=bn, tune_flags=flags)
 s = torch.cuda.current_stream().cuda_stream
 for _ in range(2):
     plan.run(s)

@@ -1,7 +1,7 @@
 """Sweep (BLOCK_N, K splits) for every distinct conv shape of one UNet step and print the measured time next to what the
-plan's cost model picks -- the data for recalibrating the model in csrc/conv_igemm.cu (b2d_conv_plan_create).
+plan's cost model picks -- the data for recalibrating the model in csrc/conv_plan.cu (b2d_conv_plan_create).
 usage (on a GPU box): python tools/tune_conv.py [N] [reps]          N = slice-images (default 88 = 8 samples)
-Forces the variants through ConvDesc.block_n and the B2D_CONV_KSPLIT tuning knob; infeasible combinations are skipped."""
+Forces the variants through b2d_conv_desc.block_n / tune_ksplit; infeasible combinations are skipped."""
 import os
 import sys
 
@@ -60,22 +60,19 @@ for kind, cins, cout, H in shapes:
     out = new_act(N, 1, H * up, H * up, cout, dev, f16=(kind != "1x1"))
     st = torch.zeros(N, 1, 2, dtype=torch.float64, device=dev) if kind != "1x1" else None
     kw = dict(cout=cout, nphase=nphase, stats=st, stats_cpg=cout if st is not None else 0)
-    os.environ.pop("B2D_CONV_KSPLIT", None)
     auto = ConvPlan(xs, pw, out, **kw)
     t_auto, info = timed(auto), auto.info2()
     rows = []
     for bn in (64, 128, 256):
         for ks in (1, 2, 3, 4, 6, 8):
-            os.environ["B2D_CONV_KSPLIT"] = str(ks)
             try:
-                p = ConvPlan(xs, pw, out, block_n=bn, **kw)
+                p = ConvPlan(xs, pw, out, block_n=bn, tune_ksplit=ks, **kw)
             except (B2DError, ValueError, RuntimeError):
                 continue
             i2 = p.info2()
             if i2["block_n"] != bn or i2["ksplit"] != ks:
                 continue
             rows.append((timed(p), bn, ks, i2["units"]))
-    os.environ.pop("B2D_CONV_KSPLIT", None)
     rows.sort()
     best = rows[0] if rows else (float("nan"), 0, 0, 0)
     print(f"{kind:5s} {'+'.join(map(str, cins)):>9s}->{cout:<4d} @{H:<2d}  auto bn{info['block_n']} ks{info['ksplit']} halo{info['halo']} "
