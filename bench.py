@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--strong-batch", type=int, default=64, help="fixed global batch of the secondary `strong` object (0 = skip)")
     ap.add_argument("--vae-chunk", type=int, default=8)
     ap.add_argument("--ddim-steps", type=int, default=50)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x"])
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "fp32x"])
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--slices", type=int, default=11)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -366,7 +366,7 @@ def run_b200(args):
     xs, es, zs = (torch.randn(n_el, device=dev) for _ in range(3))
     coef = pred.scheduler._ddpm_table
     t_sched = time_launches(lambda: _lib.call("b2d_scheduler_step", 0, xs.data_ptr(), es.data_ptr(), zs.data_ptr(), xs.data_ptr(),
-                                              n_el, coef.data_ptr(), None, 500, 0, 1, -30.0, 30.0, None, 0, 0, 0, None, None, s), 20)
+                                              n_el, coef.data_ptr(), None, 500, 0, 1, -30.0, 30.0, None, 0, 0, 0, None, None, 0, s), 20)
     hbm_ach = 16.0 * n_el / (t_sched * 1e-3) / 1e9
     del xs, es, zs
     scale = (S / 11.0) * (H / 256.0) ** 2
@@ -408,7 +408,8 @@ def run_b200(args):
             "metric": "3D flow-field predictions/sec", "value": value, "unit": "predictions/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong_primary else "weak",
             "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-class hi/lo split)", "data": "synthetic",
+            "dtype": {"f16": "f16 (IEEE fp16 operands, fp32 accumulate)", "bf16": "bf16",
+                      "fp32x": "bf16x3 (fp32-class hi/lo split)"}[args.precision], "data": "synthetic",
             "config": workload_config(args),
             "arm": {"samples_per_gpu": B, "global_batch": G, "parallelism": f"batch-sharded x{world}, final gather only",
                     "loop": "CUDA-graphed timestep (UNet body + final_conv fused with the sampler update)" if graph is not None else "eager",

@@ -50,6 +50,7 @@ class ConvDesc(C.Structure):
         ("in_cpg", c_i32), ("in_creal", c_i32), ("in_f16", c_i32), ("in_act", c_i32),
         ("in_eps", c_float),
         ("tune_flags", c_i32),
+        ("op_f16", c_i32),
         ("sched_kind", c_i32),
         ("sched_x", c_void_p), ("sched_noise", c_void_p), ("sched_coef", c_void_p),
         ("sched_step_idx", c_void_p), ("sched_ticket", c_void_p), ("sched_seed_dev", c_void_p),
@@ -59,7 +60,7 @@ class ConvDesc(C.Structure):
         ("sched_clip_lo", c_float), ("sched_clip_hi", c_float),
         ("sched_x_bf16", c_void_p), ("sched_x_bf16_lo", c_void_p),
         ("sched_bf16_stride", c_i32),
-        ("reserved", c_i32 * 3),
+        ("reserved", c_i32 * 2),
     ]
 
 
@@ -70,7 +71,7 @@ _SIGNATURES = {
     "b2d_version": (c_int, []),
     "b2d_last_error": (C.c_char_p, []),
     "b2d_scheduler_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int,
-                                   c_int, c_float, c_float, c_void_p, c_int, c_int, c_u64, c_void_p, c_void_p, c_void_p]),
+                                   c_int, c_float, c_float, c_void_p, c_int, c_int, c_u64, c_void_p, c_void_p, c_int, c_void_p]),
     "b2d_q_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
     "b2d_conv_plan_create": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_void_p)]),
     "b2d_conv_plan_destroy": (c_int, [c_void_p]),
@@ -78,18 +79,18 @@ _SIGNATURES = {
     "b2d_conv_plan_info": (c_int, [c_void_p, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32)]),
     "b2d_conv_plan_info2": (c_int, [c_void_p, C.POINTER(c_i32)]),
     "b2d_gn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_i32, c_void_p, c_i32, c_void_p, c_void_p,
-                             c_float, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32, c_void_p]),
-    "b2d_maxpool2x2_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p]),
+                             c_float, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32, c_i32, c_void_p]),
+    "b2d_maxpool2x2_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_i32, c_void_p]),
     "b2d_upsample2x_nearest": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
-    "b2d_planar_to_cl": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_void_p, c_void_p]),
-    "b2d_cl_to_planar": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_void_p]),
-    "b2d_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
+    "b2d_planar_to_cl": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_void_p, c_i32, c_void_p]),
+    "b2d_cl_to_planar": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_void_p]),
+    "b2d_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_edt2d": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_bilinear_resize": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p]),
     "b2d_zero": (c_int, [c_void_p, c_i64, c_void_p]),
     "b2d_gn_gn_apply": (c_int, [c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i64, c_i32, c_void_p, c_void_p, c_void_p, c_float, c_i32,
-                        c_void_p, c_void_p, c_float, c_i32, c_void_p]),
-    "b2d_maxpool2x2_gn": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_float, c_i32, c_void_p]),
+                        c_void_p, c_void_p, c_float, c_i32, c_i32, c_void_p]),
+    "b2d_maxpool2x2_gn": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_float, c_i32, c_i32, c_void_p]),
     "b2d_zstack_cl": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_void_p]),
     "b2d_zfold_combine": (c_int, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
                           c_void_p]),

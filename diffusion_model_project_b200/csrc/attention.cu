@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -38,6 +39,15 @@ __device__ __forceinline__ void a_unpack8(const uint4& u, float (&f)[8]) {
   f[4] = a_bflo(u.z); f[5] = a_bfhi(u.z); f[6] = a_bflo(u.w); f[7] = a_bfhi(u.w);
 }
 
+// 16-bit pair / 8-vector -> fp32 in the tensor's storage format (f16: IEEE fp16, else bf16)
+__device__ __forceinline__ void a_unpack2(uint32_t u, int f16, float& lo, float& hi) {
+  if (f16) { const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&u)); lo = v.x; hi = v.y; }
+  else { lo = a_bflo(u); hi = a_bfhi(u); }
+}
+__device__ __forceinline__ void a_unpack8f(const uint4& u, float (&f)[8], int f16) {
+  a_unpack2(u.x, f16, f[0], f[1]); a_unpack2(u.y, f16, f[2], f[3]); a_unpack2(u.z, f16, f[4], f[5]); a_unpack2(u.w, f16, f[6], f[7]);
+}
+
 // stage rows [T][d] of one head (column offset col0 in the [N][T][3C] tensor) into smem, row pitch dp
 __device__ __forceinline__ void stage_rows(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* dst, int T, int d, int dp,
                                            long long row_stride) {
@@ -54,7 +64,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
                                                                  const __nv_bfloat16* __restrict__ qkv_lo,
                                                                  __nv_bfloat16* __restrict__ out,
                                                                  __nv_bfloat16* __restrict__ out_lo, int T, int C, int heads,
-                                                                 float scale) {
+                                                                 float scale, int f16) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int d = C / heads;
   const int dp = d + 8;  // +16 bytes per row: lanes reading different rows hit different banks
@@ -79,7 +89,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
     const int qi = i / d, c = i - qi * d;
     float v = 0.f;
     if (q0 + qi < T) {
-      v = __bfloat162float(base[(long long)(q0 + qi) * rs + c]);
+      v = f16 ? __half2float(reinterpret_cast<const __half*>(base)[(long long)(q0 + qi) * rs + c]) : __bfloat162float(base[(long long)(q0 + qi) * rs + c]);
       if (SPLIT) v += __bfloat162float(base_lo[(long long)(q0 + qi) * rs + c]);
     }
     sQ[i] = v * scale;
@@ -93,7 +103,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
     const __nv_bfloat16* krow_lo = kv_lo + (size_t)j * dp;
     for (int c = 0; c < d; c += 8) {
       float kf[8];
-      a_unpack8(*reinterpret_cast<const uint4*>(krow + c), kf);
+      a_unpack8f(*reinterpret_cast<const uint4*>(krow + c), kf, f16);
       if (SPLIT) {
         float kl[8];
         a_unpack8(*reinterpret_cast<const uint4*>(krow_lo + c), kl);
@@ -154,7 +164,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
     for (int i = 0; i < kMaxCI; ++i) {
       if (i < nci) {
         const uint32_t u = *reinterpret_cast<const uint32_t*>(kv + (size_t)j * dp + 2 * lane + 64 * i);
-        float v0 = a_bflo(u), v1 = a_bfhi(u);
+        float v0, v1;
+        a_unpack2(u, f16, v0, v1);
         if (SPLIT) {
           const uint32_t ul = *reinterpret_cast<const uint32_t*>(kv_lo + (size_t)j * dp + 2 * lane + 64 * i);
           v0 += a_bflo(ul); v1 += a_bfhi(ul);
@@ -175,6 +186,10 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
       for (int i = 0; i < kMaxCI; ++i) {
         if (i < nci) {
           const long long idx = ((long long)n * T + q) * C + (long long)h * d + 2 * lane + 64 * i;
+          if (f16) {
+            *reinterpret_cast<__half2*>(out + idx) = __floats2half2_rn(o[qq][i][0], o[qq][i][1]);
+            continue;
+          }
           const __nv_bfloat162 hv = __floats2bfloat162_rn(o[qq][i][0], o[qq][i][1]);
           *reinterpret_cast<__nv_bfloat162*>(out + idx) = hv;
           if (SPLIT && out_lo != nullptr) {
@@ -206,7 +221,7 @@ size_t attention_tc_smem(int T, int C, int heads) {
   return (size_t)dch * kQChunkBytes + 2 * (size_t)dch * T * 128 + 64 + 1024;
 }
 
-int attention_tc_params(const void* qkv, void* out, int N, int T, int C, int heads, AttnTcParams* pp) {
+int attention_tc_params(const void* qkv, void* out, int N, int T, int C, int heads, int f16, AttnTcParams* pp) {
   const int d = C / heads;
   const int dch = d / 64;
   const size_t p_bytes = (size_t)((T + 63) / 64) * kQChunkBytes;
@@ -226,14 +241,14 @@ int attention_tc_params(const void* qkv, void* out, int N, int T, int C, int hea
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(B2D_E_CUDA, "b2d_attention: cuTensorMapEncodeTiled failed: %d", (int)r);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.T = T; p.C = C; p.heads = heads; p.d = d; p.RB = RB;
+  p.T = T; p.C = C; p.heads = heads; p.d = d; p.RB = RB; p.f16 = f16 ? 1 : 0;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)d);
   return B2D_OK;
 }
 
-static int launch_attention_tc(const void* qkv, void* out, int N, int T, int C, int heads, cudaStream_t st) {
+static int launch_attention_tc(const void* qkv, void* out, int N, int T, int C, int heads, int f16, cudaStream_t st) {
   AttnTcParams p;
-  const int rc = attention_tc_params(qkv, out, N, T, C, heads, &p);
+  const int rc = attention_tc_params(qkv, out, N, T, C, heads, f16, &p);
   if (rc != B2D_OK) return rc;
   const size_t smem = attention_tc_smem(T, C, heads);
   static unsigned long long configured = 0;
@@ -251,22 +266,22 @@ static int launch_attention_tc(const void* qkv, void* out, int N, int T, int C, 
 using namespace b2d;
 
 extern "C" int b2d_attention(const void* qkv, const void* qkv_lo, void* out, void* out_lo, int32_t N, int32_t T, int32_t C,
-                             int32_t heads, void* stream) {
+                             int32_t heads, int32_t f16, void* stream) {
   if (!qkv || !out) return set_error(B2D_E_INVALID, "b2d_attention: null pointer");
+  if (f16 && (qkv_lo || out_lo)) return set_error(B2D_E_INVALID, "b2d_attention: an fp16 tensor has no lo part");
   if (N < 1 || T < 1 || heads < 1 || C < 1 || (C % heads)) return set_error(B2D_E_INVALID, "b2d_attention: bad shape");
   const int d = C / heads;
   if ((d % 64) || d > 512) return set_error(B2D_E_INVALID, "b2d_attention: d_head=%d must be a multiple of 64 and <= 512", d);
   if ((long long)N * heads > 65535) return set_error(B2D_E_INVALID, "b2d_attention: N*heads too large");
   const bool split = qkv_lo != nullptr;
-  static const bool tc_off = getenv("B2D_ATTN_FP32") != nullptr;  // diagnostics: force the CUDA-core kernel
-  if (!split && !tc_off) {
+  if (!split) {
     // tensor-core path: T keys as one UMMA N extent, P tile aliasing the Q/K staging area
     const int dch = d / 64;
     const size_t need = (size_t)dch * kQChunkBytes + 2 * (size_t)dch * T * 128 + 64 + 1024;
     const size_t p_bytes = (size_t)((T + 63) / 64) * kQChunkBytes;
     if (T % 16 == 0 && T >= 16 && T <= 256 && (T <= 128 || T % 128 == 0) && need <= 227 * 1024 &&
         p_bytes <= (size_t)dch * kQChunkBytes + (size_t)dch * T * 128 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
-      return launch_attention_tc(qkv, out, N, T, C, heads, (cudaStream_t)stream);
+      return launch_attention_tc(qkv, out, N, T, C, heads, f16, (cudaStream_t)stream);
   }
   const size_t smem = (size_t)T * (d + 8) * 2 * (split ? 2 : 1) + (size_t)kQB * T * 4 + (size_t)kQB * d * 4;
   if (smem > 227 * 1024 - 1024) return set_error(B2D_E_INVALID, "b2d_attention: T=%d d=%d needs %zu bytes of shared memory", T, d, smem);
@@ -281,10 +296,10 @@ extern "C" int b2d_attention(const void* qkv, const void* qkv_lo, void* out, voi
   }
   if (split) {
     attention_kernel<true><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_lo, (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo, T, C, heads, scale);
+        (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_lo, (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo, T, C, heads, scale, 0);
   } else {
     attention_kernel<false><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)qkv, nullptr, (__nv_bfloat16*)out, nullptr, T, C, heads, scale);
+        (const __nv_bfloat16*)qkv, nullptr, (__nv_bfloat16*)out, nullptr, T, C, heads, scale, f16 ? 1 : 0);
   }
   return check_launch("attention_kernel");
 }

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "b2d_ptx.cuh"
@@ -19,6 +20,7 @@ struct AttnTcParams {
   __nv_bfloat16* out;
   int T, C, heads, d;
   int RB;            // rows per TMA box = min(128, T)
+  int f16;           // qkv / out / P hold IEEE fp16 instead of bf16
   float scale_log2e;
 };
 
@@ -66,7 +68,7 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, int mti
     // ---- S[128 x T] = Q K^T ---------------------------------------------------------------------
     mbar_wait(&bars[0], 0);
     tc_fence_after();
-    const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)T);
+    const uint32_t idesc_s = umma_idesc_16(128, (uint32_t)T, p.f16);
     uint32_t accum = 0;
     for (int c = 0; c < dch; ++c) {
       const uint64_t adesc = umma_smem_desc(smem_u32(sQ + c * kQChunkBytes), 1024, 2);
@@ -107,6 +109,7 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, int mti
   float sum = 0.f;
   uint8_t* prow = sP + row * 128;
   const int sw = row & 7;
+  const int f16 = p.f16;
   auto emit = [&](const uint32_t* v, int c0, int ncol) {
     // ncol consecutive keys starting at c0 (c0 % 8 == 0): bf16 pairs into the swizzled K-major P tile
 #pragma unroll
@@ -117,9 +120,15 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, int mti
         for (int q = 0; q < 4; ++q) {
           const float e0 = exp2f(fmaf(__uint_as_float(v[j8 * 8 + 2 * q]), sc, -mxs));
           const float e1 = exp2f(fmaf(__uint_as_float(v[j8 * 8 + 2 * q + 1]), sc, -mxs));
-          __nv_bfloat162 hv = __floats2bfloat162_rn(e0, e1);
-          sum += __low2float(hv) + __high2float(hv);
-          w[q] = *reinterpret_cast<uint32_t*>(&hv);
+          if (f16) {
+            __half2 hv = __floats2half2_rn(e0, e1);
+            sum += __low2float(hv) + __high2float(hv);
+            w[q] = *reinterpret_cast<uint32_t*>(&hv);
+          } else {
+            __nv_bfloat162 hv = __floats2bfloat162_rn(e0, e1);
+            sum += __low2float(hv) + __high2float(hv);
+            w[q] = *reinterpret_cast<uint32_t*>(&hv);
+          }
         }
         const int key = c0 + j8 * 8;
         const int chunk16 = (key & 63) >> 3;
@@ -152,7 +161,7 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, int mti
     if (threadIdx.x == 0) {
       tc_fence_after();
       if (g == 0) { mbar_wait(&bars[1], 0); tc_fence_after(); }
-      const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)DC) | kUmmaBMajorMN;
+      const uint32_t idesc_o = umma_idesc_16(128, (uint32_t)DC, p.f16) | kUmmaBMajorMN;
       uint32_t accum = 0;
       for (int k0 = 0; k0 < T; k0 += 16) {
         const uint64_t adesc = umma_smem_desc(smem_u32(sP + (k0 >> 6) * kQChunkBytes), 1024, 2) + 2 * ((k0 & 63) >> 4);
@@ -176,8 +185,14 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, int mti
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(v[j8 * 8 + 2 * e]) * inv, __uint_as_float(v[j8 * 8 + 2 * e + 1]) * inv);
-            w[e] = *reinterpret_cast<uint32_t*>(&hv);
+            const float o0 = __uint_as_float(v[j8 * 8 + 2 * e]) * inv, o1 = __uint_as_float(v[j8 * 8 + 2 * e + 1]) * inv;
+            if (f16) {
+              __half2 hv = __floats2half2_rn(o0, o1);
+              w[e] = *reinterpret_cast<uint32_t*>(&hv);
+            } else {
+              __nv_bfloat162 hv = __floats2bfloat162_rn(o0, o1);
+              w[e] = *reinterpret_cast<uint32_t*>(&hv);
+            }
           }
           *reinterpret_cast<uint4*>(orow + c0 + j8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -194,7 +209,7 @@ __device__ __forceinline__ void attention_tc_item(const AttnTcParams& p, int mti
 
 
 // host: fill `p` (TMA descriptor over qkv [N][T][3C], shapes, scale) after checking that the tensor-core path applies
-int attention_tc_params(const void* qkv, void* out, int N, int T, int C, int heads, AttnTcParams* p);
+int attention_tc_params(const void* qkv, void* out, int N, int T, int C, int heads, int f16, AttnTcParams* p);
 // dynamic shared memory one item needs
 size_t attention_tc_smem(int T, int C, int heads);
 

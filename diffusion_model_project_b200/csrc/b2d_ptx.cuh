@@ -206,4 +206,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
          | ((m >> 4) << 24);  // m_dim
 }
 
+// the same with A = B = IEEE fp16 (format code 0) when f16 != 0: same tensor-core rate, 10-bit mantissa operands
+__host__ __device__ constexpr uint32_t umma_idesc_16(uint32_t m, uint32_t n, int f16) {
+  return f16 ? ((1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24)) : umma_idesc_bf16(m, n);
+}
+
 }  // namespace b2d

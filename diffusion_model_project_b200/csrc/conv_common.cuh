@@ -105,6 +105,7 @@ struct ConvKParams {
   __nv_bfloat16* sch_bf16;
   __nv_bfloat16* sch_bf16_lo;
   int sch_bf16_stride;
+  int op_f16;                  // MMA operands (and the fused sampler update's 16-bit copy) are fp16 instead of bf16
 };
 
 // per-kernel constants of the fused sampler update (out_mode 3), loaded once by every epilogue thread
@@ -144,9 +145,9 @@ __device__ __forceinline__ void sched_update_row(const ConvKParams& p, const Sch
       o.w = step_one(x.w, f[4 * q + 3], z.w, sc.k, p.sch_kind, p.sch_clip, p.sch_lo, p.sch_hi, sc.use_noise);
       *reinterpret_cast<float4*>(xr + 4 * q) = o;
       if (p.sch_bf16 != nullptr) {
-        const uint32_t w0 = pack_bf16_(o.x, o.y), w1 = pack_bf16_(o.z, o.w);
+        const uint32_t w0 = pack16(o.x, o.y, p.op_f16), w1 = pack16(o.z, o.w, p.op_f16);
         *reinterpret_cast<uint2*>(p.sch_bf16 + opix * p.sch_bf16_stride + 4 * q) = make_uint2(w0, w1);
-        if (p.sch_bf16_lo != nullptr) {
+        if (p.sch_bf16_lo != nullptr) {  // hi/lo split (fp32x mode): bf16 only, checked at plan creation
           const uint32_t l0 = pack_bf16_(o.x - __uint_as_float(w0 << 16), o.y - __uint_as_float(w0 & 0xFFFF0000u));
           const uint32_t l1 = pack_bf16_(o.z - __uint_as_float(w1 << 16), o.w - __uint_as_float(w1 & 0xFFFF0000u));
           *reinterpret_cast<uint2*>(p.sch_bf16_lo + opix * p.sch_bf16_stride + 4 * q) = make_uint2(l0, l1);

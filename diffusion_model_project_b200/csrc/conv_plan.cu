@@ -171,6 +171,8 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   if (d->residual && (d->out_mode != 0 && d->out_mode != 2)) return set_error(B2D_E_INVALID, "residual needs out_mode 0/2");
   if (d->residual && ((d->res_cstride % 8) || (reinterpret_cast<uintptr_t>(d->residual) & 15) || bn == 16))
     return set_error(B2D_E_INVALID, "residual needs cstride multiple of 8, 16-byte alignment, block_n>=64");
+  if (d->op_f16 && (d->out_lo || d->residual_lo || d->sched_x_bf16_lo))
+    return set_error(B2D_E_INVALID, "op_f16 (fp16 operands) excludes the bf16 hi/lo split outputs");
   if (d->out_f16 && (d->out_mode != 0 || d->out_lo)) return set_error(B2D_E_INVALID, "out_f16 needs out_mode 0 without a lo part");
   if (d->res_f16 && (!d->residual || d->residual_lo)) return set_error(B2D_E_INVALID, "res_f16 needs a residual without a lo part");
   if (d->stats) {
@@ -251,6 +253,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   k.stats = d->stats; k.stats_cpg = d->stats ? d->stats_cpg : 0;
   k.out_scale = d->out_scale; k.out_mask = d->out_mask;
   k.out_f16 = d->out_f16 ? 1 : 0; k.res_f16 = d->res_f16 ? 1 : 0;
+  k.op_f16 = d->op_f16 ? 1 : 0;
   if (d->out_mode == 3) {
     k.sch_x = d->sched_x; k.sch_noise = d->sched_noise; k.sch_coef = d->sched_coef;
     k.sch_step = d->sched_step_idx; k.sch_ticket = d->sched_ticket;

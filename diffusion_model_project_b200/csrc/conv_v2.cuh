@@ -230,7 +230,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     // ================================ MMA issuer ===========================================
     // Uniform loop; descriptors are 64-bit constants whose low word (start address >> 4) is the only
     // thing that moves, so the per-MMA work is one 32-bit uniform add.
-    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+    const uint32_t idesc = umma_idesc_16(kBlockM, BN, p.op_f16);
     const uint64_t adesc0 = umma_smem_desc(smem_u32(sA), HALO ? 18 * 128 : 1024, 2);
     const uint64_t bdesc0 = umma_smem_desc(smem_u32(sB), 1024, 2);
     const uint32_t adesc_hi = (uint32_t)(adesc0 >> 32), bdesc_hi = (uint32_t)(bdesc0 >> 32);
@@ -480,6 +480,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     const int cin_pad = p.cin[0];
     const int ngrp = p.in_creal / p.in_cpg;
     const bool act_on = p.in_act != 0, in_f16 = p.in_f16 != 0;
+    const int op_f16 = p.op_f16;
     int ast = 0, cur_n = -1;
     uint32_t aph = 0;
     for (int u = uw.u; u < uw.end; u += uw.step) {
@@ -563,7 +564,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
                 f[j] = fmaf(f[j], t, f[j]);
               }
             }
-            if (live[q]) sts128(vaddr[q], make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+            if (live[q]) sts128(vaddr[q], make_uint4(pack16(f[0], f[1], op_f16), pack16(f[2], f[3], op_f16), pack16(f[4], f[5], op_f16), pack16(f[6], f[7], op_f16)));
           }
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads

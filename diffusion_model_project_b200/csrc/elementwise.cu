@@ -31,6 +31,19 @@ __device__ __forceinline__ void unpack8_f16(const uint4& u, float (&f)[8]) {
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(packbf(f[0], f[1]), packbf(f[2], f[3]), packbf(f[4], f[5]), packbf(f[6], f[7]));
 }
+__device__ __forceinline__ uint32_t packh_sat(float a, float b) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tcvt.rn.satfinite.f16.f32 lo, %1;\n\tcvt.rn.satfinite.f16.f32 hi, %2;\n\tmov.b32 %0, {lo, hi};\n\t}" : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8_f16(const float (&f)[8]) {
+  return make_uint4(packh_sat(f[0], f[1]), packh_sat(f[2], f[3]), packh_sat(f[4], f[5]), packh_sat(f[6], f[7]));
+}
+// 16-bit storage format of an activation tensor: IEEE fp16 (f16 != 0) or bf16 -- warp-uniform runtime flag
+__device__ __forceinline__ void unpack8_fmt(const uint4& u, float (&f)[8], int f16) {
+  if (f16) unpack8_f16(u, f); else unpack8(u, f);
+}
+__device__ __forceinline__ uint4 pack8_fmt(const float (&f)[8], int f16) { return f16 ? pack8_f16(f) : pack8(f); }
 // bf16 "lo" part of an fp32 value whose "hi" part is the packed word (hi/lo split, fp32x mode)
 __device__ __forceinline__ uint4 pack8_lo(const float (&f)[8], const uint4& hi) {
   float h[8];
@@ -40,7 +53,9 @@ __device__ __forceinline__ uint4 pack8_lo(const float (&f)[8], const uint4& hi) 
   for (int i = 0; i < 8; ++i) l[i] = f[i] - h[i];
   return pack8(l);
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+// SiLU good to ~1e-6 relative (ex2.approx + rcp.approx): used where the result is stored as fp16 (2^-11 rounding), for
+// which tanh.approx's ~2^-11 error would no longer be negligible
+__device__ __forceinline__ float silu_acc(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -50,13 +65,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // --------------------------------------------------------------------------- GroupNorm apply
 // grid = (blocks_per_image, N); block = 256.  Per-channel scale/shift/temb staged in smem.
-template <bool TEMB>
+template <bool TEMB, bool ACC>
 __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
     const uint4* __restrict__ x, const uint4* __restrict__ x_lo, uint4* __restrict__ y, uint4* __restrict__ y_lo,
     long long P, int C, const double* __restrict__ stats, int cpg, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, int act, const float* __restrict__ temb_table,
     const int* __restrict__ temb_row, int temb_row_stride, int temb_ld, int temb_col, double* __restrict__ stats_out,
-    int in_f16) {
+    int in_f16, int out_f16) {
   extern __shared__ float sm[];
   float* sa = sm;
   float* sb = sm + C;
@@ -103,10 +118,14 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
     for (int j = 0; j < 8; ++j) {
       float v = fmaf(f[j], a[j], b[j]);
       if (act) {
-        const float h = half_folded ? v : 0.5f * v;
-        float th;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-        v = fmaf(h, th, h);
+        if constexpr (ACC) {
+          v = silu_acc(v);
+        } else {
+          const float h = half_folded ? v : 0.5f * v;
+          float th;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+          v = fmaf(h, th, h);
+        }
       }
       if (TEMB) v += t[j];
       f[j] = v;
@@ -119,7 +138,7 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
     // same 8 channels -> coefficients live in registers and 4 independent 16-byte loads are in flight.
     const int c0 = (threadIdx.x % vpc) << 3;
     float a[8], b[8], t[8];
-    const float fold = act ? 0.5f : 1.f;
+    const float fold = (act && !ACC) ? 0.5f : 1.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] = fold * sa[c0 + j]; b[j] = fold * sb[c0 + j]; t[j] = st[c0 + j]; }
     const uint4* xp = x + base;
@@ -132,22 +151,22 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float f[8];
-        if (in_f16) unpack8_f16(u[k], f); else unpack8(u[k], f);
+        unpack8_fmt(u[k], f, in_f16);
         transform(f, a, b, t, true);
-        yp[i + k * stride] = pack8(f);
+        yp[i + k * stride] = pack8_fmt(f, out_f16);
       }
     }
     for (; i < nvec; i += stride) {
       float f[8];
-      if (in_f16) unpack8_f16(__ldcs(xp + i), f); else unpack8(__ldcs(xp + i), f);
+      unpack8_fmt(__ldcs(xp + i), f, in_f16);
       transform(f, a, b, t, true);
-      yp[i] = pack8(f);
+      yp[i] = pack8_fmt(f, out_f16);
     }
   } else {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
       const int c0 = (int)(i % vpc) << 3;
       float f[8];
-      if (in_f16) unpack8_f16(__ldg(x + base + i), f); else unpack8(__ldg(x + base + i), f);
+      unpack8_fmt(__ldg(x + base + i), f, in_f16);
       if (x_lo != nullptr) {
         float l[8];
         unpack8(__ldg(x_lo + base + i), l);
@@ -155,9 +174,9 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
         for (int j = 0; j < 8; ++j) f[j] += l[j];
       }
       transform(f, sa + c0, sb + c0, st + c0, false);
-      const uint4 hi = pack8(f);
+      const uint4 hi = pack8_fmt(f, out_f16);
       y[base + i] = hi;
-      if (y_lo != nullptr) y_lo[base + i] = pack8_lo(f, hi);
+      if (y_lo != nullptr) y_lo[base + i] = pack8_lo(f, hi);  // hi/lo split: bf16 only (checked by the launcher)
     }
   }
   if (stats_out != nullptr) {
@@ -183,7 +202,7 @@ __global__ void __launch_bounds__(256, TEMB ? 3 : 4) gn_apply_kernel(
 // --------------------------------------------------------------------------- max-pool 2x2 + sums
 __global__ void __launch_bounds__(256) maxpool_stats_kernel(const uint4* __restrict__ x, const uint4* __restrict__ x_lo,
                                                             uint4* __restrict__ y, uint4* __restrict__ y_lo, int H, int W,
-                                                            int C, double* __restrict__ stats) {
+                                                            int C, double* __restrict__ stats, int f16) {
   const int n = blockIdx.y;
   const int OH = H >> 1, OW = W >> 1, vpc = C >> 3;
   const long long nvec = (long long)OH * OW * vpc;
@@ -199,7 +218,7 @@ __global__ void __launch_bounds__(256) maxpool_stats_kernel(const uint4* __restr
     for (int q = 0; q < 4; ++q) {
       const long long src = ((long long)(2 * oy + (q >> 1)) * W + (2 * ox + (q & 1))) * vpc + v;
       float f[8];
-      unpack8(__ldg(xi + src), f);
+      unpack8_fmt(__ldg(xi + src), f, f16);
       if (xl) {
         float l[8];
         unpack8(__ldg(xl + src), l);
@@ -211,7 +230,7 @@ __global__ void __launch_bounds__(256) maxpool_stats_kernel(const uint4* __restr
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc_s += m[j]; acc_ss += m[j] * m[j]; }
-    const uint4 hi = pack8(m);
+    const uint4 hi = pack8_fmt(m, f16);
     y[(long long)n * nvec + i] = hi;
     if (y_lo) y_lo[(long long)n * nvec + i] = pack8_lo(m, hi);
   }
@@ -245,6 +264,8 @@ __device__ __forceinline__ float silu_tanh(float v) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
   return fmaf(h, th, h);
 }
+// fp16 results get the accurate form (see silu_acc); these per-sample kernels are latency-bound, not MUFU-bound
+__device__ __forceinline__ float silu_sel(float v, int f16) { return f16 ? silu_acc(v) : silu_tanh(v); }
 
 // sum of (s, ss) over the CTA, fp64, result broadcast to every thread
 __device__ __forceinline__ void block_sum2(double& s, double& ss, double (*red)[2]) {
@@ -266,7 +287,8 @@ template <int VPT, bool KEEP>
 __global__ void __launch_bounds__(1024) gn_gn_kernel(const uint4* __restrict__ x, int in_f16, uint4* __restrict__ y1,
                                                      uint4* __restrict__ y2, int nvec, int C, const double* __restrict__ stats1,
                                                      const float* __restrict__ g1, const float* __restrict__ b1, float eps1, int act1,
-                                                     const float* __restrict__ g2, const float* __restrict__ b2, float eps2, int act2) {
+                                                     const float* __restrict__ g2, const float* __restrict__ b2, float eps2, int act2,
+                                                     int out_f16) {
   __shared__ double red[32][2];
   const int n = blockIdx.x;
   const int vpc = C >> 3;
@@ -300,15 +322,15 @@ __global__ void __launch_bounds__(1024) gn_gn_kernel(const uint4* __restrict__ x
     for (int k = 0; k < 4 && k0 + k < VPT; ++k) {
       const int v = threadIdx.x + (k0 + k) * 1024;
       float (&fk)[8] = f[KEEP ? k0 + k : 0];
-      if (in_f16) unpack8_f16(u[k], fk); else unpack8(u[k], fk);
+      unpack8_fmt(u[k], fk, in_f16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float t = fmaf(fk[j], a[j], b[j]);
-        if (act1) t = silu_tanh(t);
+        if (act1) t = silu_sel(t, out_f16);
         fk[j] = t;
         if (v < nvec) { ps += t; pss = fmaf(t, t, pss); }
       }
-      if (v < nvec) y1p[v] = pack8(fk);
+      if (v < nvec) y1p[v] = pack8_fmt(fk, out_f16);
     }
   }
   double s = (double)ps, ss = (double)pss;
@@ -327,21 +349,21 @@ __global__ void __launch_bounds__(1024) gn_gn_kernel(const uint4* __restrict__ x
   for (int k = 0; k < VPT; ++k) {
     const int v = threadIdx.x + k * 1024;
     float (&fk)[8] = f[KEEP ? k : 0];
-    if (!KEEP) unpack8(v < nvec ? y1p[v] : make_uint4(0u, 0u, 0u, 0u), fk);  // this thread's own store, bf16-rounded
+    if (!KEEP) unpack8_fmt(v < nvec ? y1p[v] : make_uint4(0u, 0u, 0u, 0u), fk, out_f16);  // this thread's own store, rounded
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float t = fmaf(fk[j], a[j], b[j]);
-      if (act2) t = silu_tanh(t);
+      if (act2) t = silu_sel(t, out_f16);
       fk[j] = t;
     }
-    if (v < nvec) y2[(long long)n * nvec + v] = pack8(fk);
+    if (v < nvec) y2[(long long)n * nvec + v] = pack8_fmt(fk, out_f16);
   }
 }
 
 template <int VPT, bool KEEP>
 __global__ void __launch_bounds__(1024) maxpool_gn_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C,
                                                           const float* __restrict__ g, const float* __restrict__ be, float eps,
-                                                          int act) {
+                                                          int act, int f16) {
   __shared__ double red[32][2];
   const int n = blockIdx.x;
   const int OW = W >> 1, vpc = C >> 3;
@@ -360,7 +382,7 @@ __global__ void __launch_bounds__(1024) maxpool_gn_kernel(const uint4* __restric
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       float e[8];
-      unpack8(q[t], e);
+      unpack8_fmt(q[t], e, f16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) m[j] = t == 0 ? e[j] : fmaxf(m[j], e[j]);
     }
@@ -397,10 +419,10 @@ __global__ void __launch_bounds__(1024) maxpool_gn_kernel(const uint4* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float t = fmaf(fk[j], a[j], b[j]);
-      if (act) t = silu_tanh(t);
+      if (act) t = silu_sel(t, f16);
       fk[j] = t;
     }
-    if (v < nvec) y[(long long)n * nvec + v] = pack8(fk);
+    if (v < nvec) y[(long long)n * nvec + v] = pack8_fmt(fk, f16);
   }
 }
 
@@ -419,31 +441,35 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
 }
 
 // --------------------------------------------------------------------------- layout conversion
-// planar fp32 [N][C][P] -> channels-last bf16 [N][P][cpad] at channel offset coff
+// planar fp32 [N][C][P] -> channels-last 16-bit (bf16, or fp16 if f16) [N][P][cpad] at channel offset coff
 __global__ void __launch_bounds__(256) planar_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                            __nv_bfloat16* __restrict__ y_lo, int N, int C, long long P,
-                                                           int cpad, int coff, const float* __restrict__ div_scale) {
+                                                           int cpad, int coff, const float* __restrict__ div_scale, int f16) {
   const long long total = (long long)N * P;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / P, p = i - n * P;
     for (int c = 0; c < C; ++c) {
       float v = __ldg(x + (n * C + c) * P + p);
       if (div_scale) v = __fdiv_rn(v, __ldg(div_scale + c));
+      if (f16) {
+        reinterpret_cast<uint16_t*>(y)[i * cpad + coff + c] = (uint16_t)(packh_sat(v, 0.f) & 0xFFFFu);
+        continue;
+      }
       const __nv_bfloat16 h = __float2bfloat16_rn(v);
       y[i * cpad + coff + c] = h;
       if (y_lo) y_lo[i * cpad + coff + c] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
   }
 }
-// channels-last bf16 [N][P][cstride] (channels coff..coff+C) -> planar fp32 [N][C][P]
+// channels-last 16-bit [N][P][cstride] (channels coff..coff+C) -> planar fp32 [N][C][P]
 __global__ void __launch_bounds__(256) cl_to_planar_kernel(const __nv_bfloat16* __restrict__ x,
                                                            const __nv_bfloat16* __restrict__ x_lo, float* __restrict__ y,
-                                                           int N, int C, long long P, int cstride, int coff) {
+                                                           int N, int C, long long P, int cstride, int coff, int f16) {
   const long long total = (long long)N * P;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / P, p = i - n * P;
     for (int c = 0; c < C; ++c) {
-      float v = __bfloat162float(x[i * cstride + coff + c]);
+      float v = f16 ? __half2float(reinterpret_cast<const __half*>(x)[i * cstride + coff + c]) : __bfloat162float(x[i * cstride + coff + c]);
       if (x_lo) v += __bfloat162float(x_lo[i * cstride + coff + c]);
       y[(n * C + c) * P + p] = v;
     }
@@ -523,11 +549,10 @@ using namespace b2d;
 extern "C" int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int64_t P, int32_t C,
                             const double* stats, int32_t cpg, const float* gamma, const float* beta, float eps, int32_t act,
                             const float* temb_table, const int32_t* temb_row, int32_t temb_row_stride, int32_t temb_ld,
-                            int32_t temb_col, double* stats_out, int32_t in_f16, void* stream) {
+                            int32_t temb_col, double* stats_out, int32_t in_f16, int32_t out_f16, void* stream) {
   if (!x || !y || !stats) return set_error(B2D_E_INVALID, "b2d_gn_apply: null pointer");
-  if (in_f16 && x_lo) return set_error(B2D_E_INVALID, "b2d_gn_apply: fp16 input has no lo part");
+  if ((in_f16 && x_lo) || (out_f16 && y_lo)) return set_error(B2D_E_INVALID, "b2d_gn_apply: an fp16 tensor has no lo part");
   if (N < 1 || P < 1 || C < 8 || (C % 8) || cpg < 1 || (C % cpg) || C / cpg > 64) return set_error(B2D_E_INVALID, "b2d_gn_apply: bad shape N=%d P=%lld C=%d cpg=%d", N, (long long)P, C, cpg);
-  if (3 * C * (int)sizeof(float) > 96 * 1024) return set_error(B2D_E_INVALID, "b2d_gn_apply: C=%d too large", C);
   if (N > 65535) return set_error(B2D_E_INVALID, "b2d_gn_apply: N too large");
   const long long nvec = (long long)P * (C / 8);
   int bx = grid_for(nvec, 256 * 4);
@@ -535,24 +560,26 @@ extern "C" int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo
   if (bx > per_img_cap) bx = per_img_cap < 1 ? 1 : per_img_cap;
   const size_t smem = 3 * (size_t)C * sizeof(float);
   if (smem > 96 * 1024) return set_error(B2D_E_INVALID, "b2d_gn_apply: C=%d too large (3*C floats of shared memory, max 96 KB)", C);
-  static unsigned long long cfg_t = 0, cfg_f = 0;  // per-(kernel, device) opt-in to the dynamic shared-memory carve-out
-  cudaError_t ea = temb_table != nullptr ? smem_attr_once(gn_apply_kernel<true>, 96 * 1024, cfg_t)
-                                         : smem_attr_once(gn_apply_kernel<false>, 96 * 1024, cfg_f);
+  // four variants (time-embedding add x accurate SiLU for fp16 results): per-(kernel, device) opt-in to the carve-out
+  static unsigned long long cfg[4] = {0, 0, 0, 0};
+  const int te = temb_table != nullptr ? 1 : 0, ac = out_f16 ? 1 : 0;
+  cudaError_t ea = te ? (ac ? smem_attr_once(gn_apply_kernel<true, true>, 96 * 1024, cfg[3]) : smem_attr_once(gn_apply_kernel<true, false>, 96 * 1024, cfg[2]))
+                      : (ac ? smem_attr_once(gn_apply_kernel<false, true>, 96 * 1024, cfg[1]) : smem_attr_once(gn_apply_kernel<false, false>, 96 * 1024, cfg[0]));
   if (ea != cudaSuccess) return set_error(B2D_E_CUDA, "b2d_gn_apply: cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
-  if (temb_table != nullptr)
-    gn_apply_kernel<true><<<dim3(bx, N), dim3(256), smem, (cudaStream_t)stream>>>(
-        (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, temb_table,
-        temb_row, temb_row_stride, temb_ld, temb_col, stats_out, in_f16 ? 1 : 0);
-  else
-    gn_apply_kernel<false><<<dim3(bx, N), dim3(256), smem, (cudaStream_t)stream>>>(
-        (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act,
-        (const float*)nullptr, (const int*)nullptr, 0, 0, 0, stats_out, in_f16 ? 1 : 0);
+#define B2D_GNA(T, A)                                                                                                          \
+  gn_apply_kernel<T, A><<<dim3(bx, N), dim3(256), smem, (cudaStream_t)stream>>>(                                               \
+      (const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, P, C, stats, cpg, gamma, beta, eps, act, temb_table, temb_row, \
+      temb_row_stride, temb_ld, temb_col, stats_out, in_f16 ? 1 : 0, out_f16 ? 1 : 0)
+  if (te) { if (ac) B2D_GNA(true, true); else B2D_GNA(true, false); }
+  else { if (ac) B2D_GNA(false, true); else B2D_GNA(false, false); }
+#undef B2D_GNA
   return check_launch("gn_apply_kernel");
 }
 
 extern "C" int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int32_t H, int32_t W,
-                                    int32_t C, double* stats, void* stream) {
+                                    int32_t C, double* stats, int32_t f16, void* stream) {
   if (!x || !y) return set_error(B2D_E_INVALID, "b2d_maxpool2x2_stats: null pointer");
+  if (f16 && (x_lo || y_lo)) return set_error(B2D_E_INVALID, "b2d_maxpool2x2_stats: an fp16 tensor has no lo part");
   if (N < 1 || N > 65535 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 8 || (C % 8))
     return set_error(B2D_E_INVALID, "b2d_maxpool2x2_stats: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
   const long long nvec = (long long)(H / 2) * (W / 2) * (C / 8);
@@ -560,7 +587,7 @@ extern "C" int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, vo
   int per_img_cap = (num_sms() * 8 + N - 1) / N;
   if (bx > per_img_cap) bx = per_img_cap < 1 ? 1 : per_img_cap;
   maxpool_stats_kernel<<<dim3(bx, N), dim3(256), 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)x_lo, (uint4*)y, (uint4*)y_lo, H, W, C,
-                                                                            stats);
+                                                                            stats, f16 ? 1 : 0);
   return check_launch("maxpool_stats_kernel");
 }
 
@@ -594,7 +621,7 @@ static int fused_vpt(long long nvec) { return nvec <= 1024 ? 1 : nvec <= 2048 ? 
 
 extern "C" int b2d_gn_gn_apply(const void* x, int32_t in_f16, void* y1, void* y2, int32_t N, int64_t P, int32_t C, const double* stats1,
                                const float* gamma1, const float* beta1, float eps1, int32_t act1, const float* gamma2,
-                               const float* beta2, float eps2, int32_t act2, void* stream) {
+                               const float* beta2, float eps2, int32_t act2, int32_t out_f16, void* stream) {
   if (!x || !y1 || !y2 || !stats1 || N < 1 || P < 1 || C < 8 || (C % 8)) return set_error(B2D_E_INVALID, "b2d_gn_gn_apply: bad argument");
   const long long nvec = P * (C / 8);
   const int vpt = fused_vpt(nvec);
@@ -602,14 +629,14 @@ extern "C" int b2d_gn_gn_apply(const void* x, int32_t in_f16, void* y1, void* y2
     return set_error(B2D_E_UNSUPPORTED, "b2d_gn_gn_apply: sample of %lld elements / C=%d (max 65536 elements, C/8 dividing 1024)", nvec * 8, C);
   cudaStream_t st = (cudaStream_t)stream;
 #define B2D_GG(V, K) gn_gn_kernel<V, K><<<dim3(N), dim3(1024), 0, st>>>((const uint4*)x, (int)in_f16, (uint4*)y1, (uint4*)y2, (int)nvec, \
-                             (int)C, stats1, gamma1, beta1, eps1, (int)act1, gamma2, beta2, eps2, (int)act2)
+                             (int)C, stats1, gamma1, beta1, eps1, (int)act1, gamma2, beta2, eps2, (int)act2, out_f16 ? 1 : 0)
   if (vpt == 1) B2D_GG(1, true); else if (vpt == 2) B2D_GG(2, true); else if (vpt == 4) B2D_GG(4, true); else B2D_GG(8, false);
 #undef B2D_GG
   return check_launch("gn_gn_kernel");
 }
 
 extern "C" int b2d_maxpool2x2_gn(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, const float* gamma,
-                                 const float* beta, float eps, int32_t act, void* stream) {
+                                 const float* beta, float eps, int32_t act, int32_t f16, void* stream) {
   if (!x || !y || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 8 || (C % 8))
     return set_error(B2D_E_INVALID, "b2d_maxpool2x2_gn: bad argument");
   const long long nvec = (long long)(H / 2) * (W / 2) * (C / 8);
@@ -619,7 +646,7 @@ extern "C" int b2d_maxpool2x2_gn(const void* x, void* y, int32_t N, int32_t H, i
                      nvec * 8, C);
   cudaStream_t st = (cudaStream_t)stream;
 #define B2D_PG(V, K) maxpool_gn_kernel<V, K><<<dim3(N), dim3(1024), 0, st>>>((const uint4*)x, (uint4*)y, (int)H, (int)W, (int)C, gamma, beta, \
-                             eps, (int)act)
+                             eps, (int)act, f16 ? 1 : 0)
   if (vpt == 1) B2D_PG(1, true); else if (vpt == 2) B2D_PG(2, true); else if (vpt == 4) B2D_PG(4, true); else B2D_PG(8, false);
 #undef B2D_PG
   return check_launch("maxpool_gn_kernel");
@@ -633,17 +660,17 @@ extern "C" int b2d_upsample2x_nearest(const void* x, void* y, int32_t ND, int32_
 }
 
 extern "C" int b2d_planar_to_cl(const float* x, void* y, void* y_lo, int32_t N, int32_t C, int64_t P, int32_t cpad, int32_t coff,
-                                const float* div_scale, void* stream) {
-  if (!x || !y || N < 1 || C < 1 || P < 1 || coff < 0 || coff + C > cpad) return set_error(B2D_E_INVALID, "b2d_planar_to_cl: bad argument");
+                                const float* div_scale, int32_t f16, void* stream) {
+  if (!x || !y || N < 1 || C < 1 || P < 1 || coff < 0 || coff + C > cpad || (f16 && y_lo)) return set_error(B2D_E_INVALID, "b2d_planar_to_cl: bad argument");
   planar_to_cl_kernel<<<grid_for((long long)N * P, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, (__nv_bfloat16*)y, (__nv_bfloat16*)y_lo, N, C, P, cpad, coff, div_scale);
+      x, (__nv_bfloat16*)y, (__nv_bfloat16*)y_lo, N, C, P, cpad, coff, div_scale, f16 ? 1 : 0);
   return check_launch("planar_to_cl_kernel");
 }
 
 extern "C" int b2d_cl_to_planar(const void* x, const void* x_lo, float* y, int32_t N, int32_t C, int64_t P, int32_t cstride,
-                                int32_t coff, void* stream) {
-  if (!x || !y || N < 1 || C < 1 || P < 1 || coff < 0 || coff + C > cstride) return set_error(B2D_E_INVALID, "b2d_cl_to_planar: bad argument");
+                                int32_t coff, int32_t f16, void* stream) {
+  if (!x || !y || N < 1 || C < 1 || P < 1 || coff < 0 || coff + C > cstride || (f16 && x_lo)) return set_error(B2D_E_INVALID, "b2d_cl_to_planar: bad argument");
   cl_to_planar_kernel<<<grid_for((long long)N * P, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)x_lo, y, N, C, P, cstride, coff);
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)x_lo, y, N, C, P, cstride, coff, f16 ? 1 : 0);
   return check_launch("cl_to_planar_kernel");
 }

@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(256, PHILOX ? 2 : 4) scheduler_step_kernel(
     int kind, const float4* __restrict__ x_t, const float4* __restrict__ eps, const float4* __restrict__ noise,
     float4* __restrict__ x_out, long long n_vec, long long n_elem, const float* __restrict__ coef, int* step_idx,
     int step_off, int step_inc, int clip, float clip_lo, float clip_hi, __nv_bfloat16* __restrict__ x_bf16, int group,
-    int group_stride, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, unsigned int* ticket_ctr) {
+    int group_stride, unsigned long long seed, const unsigned long long* __restrict__ seed_dev, unsigned int* ticket_ctr,
+    int x16_f16) {
   const int row = (step_idx ? *step_idx : 0) + step_off;
   const Coef k = load_coef(coef, row);
   if (PHILOX && seed_dev != nullptr) seed = *seed_dev;
@@ -40,9 +41,9 @@ __global__ void __launch_bounds__(256, PHILOX ? 2 : 4) scheduler_step_kernel(
       const long long e0 = i * 4;
       const long long g = e0 / group;
       const int r0 = (int)(e0 - g * group);  // group is a multiple of 4: the vector stays inside one group
-      __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(x_bf16 + g * group_stride + r0);
-      dst[0] = __floats2bfloat162_rn(o.x, o.y);
-      dst[1] = __floats2bfloat162_rn(o.z, o.w);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(x_bf16 + g * group_stride + r0);
+      dst[0] = pack16(o.x, o.y, x16_f16);
+      dst[1] = pack16(o.z, o.w, x16_f16);
     }
   };
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(256, PHILOX ? 2 : 4) scheduler_step_kernel(
     }
     const float o = step_one(xs[i], es[i], z, k, kind, clip, clip_lo, clip_hi, use_noise);
     reinterpret_cast<float*>(x_out)[i] = o;
-    if (x_bf16 != nullptr) x_bf16[(i / group) * group_stride + (i % group)] = __float2bfloat16_rn(o);
+    if (x_bf16 != nullptr)
+      reinterpret_cast<uint16_t*>(x_bf16)[(i / group) * group_stride + (i % group)] = (uint16_t)(pack16(o, 0.f, x16_f16) & 0xFFFFu);
   }
   // advance the device step counter once every block has read it
   if (step_idx != nullptr && step_inc != 0) {
@@ -107,7 +109,7 @@ using namespace b2d;
 extern "C" int b2d_scheduler_step(int kind, const float* x_t, const float* eps, const float* noise, float* x_out,
                                   int64_t n_elem, const float* coef, int* step_idx, int step_off, int step_inc, int clip,
                                   float clip_lo, float clip_hi, void* x_bf16, int group, int group_stride, uint64_t seed,
-                                  const uint64_t* seed_dev, unsigned int* ticket, void* stream) {
+                                  const uint64_t* seed_dev, unsigned int* ticket, int x16_f16, void* stream) {
   if (!x_t || !eps || !x_out || !coef) return set_error(B2D_E_INVALID, "b2d_scheduler_step: null pointer");
   if (kind != 0 && kind != 1) return set_error(B2D_E_INVALID, "b2d_scheduler_step: kind must be 0 (DDPM) or 1 (DDIM)");
   if (n_elem < 1) return set_error(B2D_E_INVALID, "b2d_scheduler_step: n_elem=%lld", (long long)n_elem);
@@ -129,12 +131,12 @@ extern "C" int b2d_scheduler_step(int kind, const float* x_t, const float* eps, 
     scheduler_step_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         kind, (const float4*)x_t, (const float4*)eps, (const float4*)noise, (float4*)x_out, n_vec, n_elem, coef, step_idx,
         step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed,
-        (const unsigned long long*)seed_dev, ticket);
+        (const unsigned long long*)seed_dev, ticket, x16_f16 ? 1 : 0);
   else
     scheduler_step_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         kind, (const float4*)x_t, (const float4*)eps, (const float4*)noise, (float4*)x_out, n_vec, n_elem, coef, step_idx,
         step_off, step_inc, clip, clip_lo, clip_hi, (__nv_bfloat16*)x_bf16, group, group_stride, (unsigned long long)seed,
-        (const unsigned long long*)seed_dev, ticket);
+        (const unsigned long long*)seed_dev, ticket, x16_f16 ? 1 : 0);
   return check_launch("scheduler_step_kernel");
 }
 

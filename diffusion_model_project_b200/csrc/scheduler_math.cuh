@@ -3,6 +3,7 @@
 // in the reference's operation order (Diffusion_model/src/diffusion.py:103-125, :152-188, :195-234).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace b2d {
@@ -33,6 +34,18 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   __sincosf(6.283185307179586f * u2, &s, &c);
   z0 = r * c;
   z1 = r * s;
+}
+
+// two fp32 -> one packed 16-bit pair: IEEE fp16 (saturating) or bf16, round to nearest
+__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
+  uint32_t r;
+  if (f16) {
+    asm("{\n\t.reg .b16 lo, hi;\n\tcvt.rn.satfinite.f16.f32 lo, %1;\n\tcvt.rn.satfinite.f16.f32 hi, %2;\n\tmov.b32 %0, {lo, hi};\n\t}" : "=r"(r) : "f"(a), "f"(b));
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    r = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return r;
 }
 
 struct Coef { float a, b, c1, c2, s; double inv_a; };

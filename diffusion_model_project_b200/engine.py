@@ -16,6 +16,9 @@ from . import _lib
 from ._lib import ConvDesc, call, ptr
 
 BF16 = torch.bfloat16
+# precision modes of the modules: 16-bit operands in IEEE fp16 ("f16", the default: 10-bit mantissa) or bf16 ("bf16"), or the
+# fp32-class mode "fp32x" (bf16 hi + lo operands, three tensor-core passes)
+PRECISIONS = ("f16", "bf16", "fp32x")
 
 
 def pad64(c: int) -> int:
@@ -31,17 +34,19 @@ def split_hi_lo(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 @dataclass
 class Act:
-    """Channels-last activation [N, D, H, W, C] bf16 (C multiple of 64; `lo` only in fp32x mode).
+    """Channels-last activation [N, D, H, W, C], 16-bit storage (C multiple of 64; `lo` only in fp32x mode).
 
-    f16=True marks a raw pre-GroupNorm conv output / residual stream held as IEEE fp16 in the same
-    16-bit storage (bf16 mode only): it is read by gn_apply and by residual adds, never by an MMA."""
+    f16=True: the storage holds IEEE fp16 rather than bf16 (the tensors are allocated as torch.bfloat16 either way: torch
+    only provides the memory).  In the "f16" precision mode every activation is fp16; in the "bf16" mode only the raw
+    pre-GroupNorm conv outputs / residual streams are (read by gn_apply and residual adds, never by an MMA); the fp32x
+    mode (bf16 hi + lo) has none."""
     hi: torch.Tensor
     lo: Optional[torch.Tensor] = None
     f16: bool = False
 
-    def as_bf16(self) -> "Act":
-        """The same storage after an in-place GroupNorm apply (which writes bf16)."""
-        return Act(self.hi, self.lo, False)
+    def as_fmt(self, f16: bool) -> "Act":
+        """The same storage after an in-place GroupNorm apply (which rewrites it in the operand format)."""
+        return Act(self.hi, self.lo, bool(f16) and self.lo is None)
 
     @property
     def shape(self):
@@ -99,10 +104,13 @@ class PackedWeight:
     taps: List[Tuple[int, int, int]]
     split: bool = False
     kbase_lo: Optional[List[int]] = None
+    f16: bool = False          # `w` holds IEEE fp16 bit patterns (viewed as bfloat16 storage)
 
 
-def pack_weight(w_rows_taps_c: torch.Tensor, seg_sizes: Sequence[int], taps, bias, device, split=False, row_mult=16) -> PackedWeight:
-    """w_rows_taps_c: fp32 [rows, ntaps, cin_total] (CPU or GPU)."""
+def pack_weight(w_rows_taps_c: torch.Tensor, seg_sizes: Sequence[int], taps, bias, device, split=False, row_mult=16,
+                f16=False) -> PackedWeight:
+    """w_rows_taps_c: fp32 [rows, ntaps, cin_total] (CPU or GPU).  f16: round to IEEE fp16 instead of bf16."""
+    assert not (split and f16)
     w_rows_taps_c = w_rows_taps_c.to(device=device, dtype=torch.float32)
     mat, kbase, cpads = _pack_taps(w_rows_taps_c, seg_sizes)
     rows = mat.shape[0]
@@ -115,28 +123,30 @@ def pack_weight(w_rows_taps_c: torch.Tensor, seg_sizes: Sequence[int], taps, bia
         hi, lo = split_hi_lo(mat)
         wq = torch.cat([hi, lo], dim=1).contiguous()
         kb_lo = [k + k1 for k in kbase]
+    elif f16:
+        wq = mat.to(torch.float16).contiguous().view(BF16)
     else:
         wq = mat.to(BF16).contiguous()
     b = None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous()
-    return PackedWeight(wq, kbase, cpads, wq.shape[1], rows, b, list(taps), split, kb_lo)
+    return PackedWeight(wq, kbase, cpads, wq.shape[1], rows, b, list(taps), split, kb_lo, bool(f16))
 
 
-def pack_conv2d(w, seg_sizes, bias, device, split=False):
+def pack_conv2d(w, seg_sizes, bias, device, split=False, f16=False):
     """nn.Conv2d weight [Cout, Cin, 3, 3] (unet/blocks.py:29-36)."""
     co, ci, kh, kw = w.shape
     assert (kh, kw) == (3, 3)
-    return pack_weight(w.permute(0, 2, 3, 1).reshape(co, 9, ci), seg_sizes, taps_3x3(), bias, device, split)
+    return pack_weight(w.permute(0, 2, 3, 1).reshape(co, 9, ci), seg_sizes, taps_3x3(), bias, device, split, f16=f16)
 
 
-def pack_conv3d(w, bias, device, split=False, down=False):
+def pack_conv3d(w, bias, device, split=False, down=False, f16=False):
     """nn.Conv3d weight [Cout, Cin, k, k, k], k in {1, 3} (vae/blocks.py:155-169, encoder.py:45,56)."""
     co, ci, kd, kh, kw = w.shape
     if kd == 1:
-        return pack_weight(w.reshape(co, 1, ci), [ci], [(0, 0, 0)], bias, device, split)
-    return pack_weight(w.permute(0, 2, 3, 4, 1).reshape(co, 27, ci), [ci], taps_3x3x3(0 if down else 1), bias, device, split)
+        return pack_weight(w.reshape(co, 1, ci), [ci], [(0, 0, 0)], bias, device, split, f16=f16)
+    return pack_weight(w.permute(0, 2, 3, 4, 1).reshape(co, 27, ci), [ci], taps_3x3x3(0 if down else 1), bias, device, split, f16=f16)
 
 
-def pack_conv3d_zstack(w, bias, device):
+def pack_conv3d_zstack(w, bias, device, f16=False):
     """Conv3d 3x3x3 with few input channels (encoder.py:30: 3, decoder.py:31: 8) over a z-stacked input (b2d_zstack_cl:
     channel kz*Cin + c holds slice z+kz-1): 9 in-plane taps on ONE 64-channel chunk instead of 27 taps on a chunk that is
     mostly zero padding -- a third of the MMAs."""
@@ -144,10 +154,10 @@ def pack_conv3d_zstack(w, bias, device):
     assert 3 * ci <= 64 and tuple(w.shape[2:]) == (3, 3, 3)
     rows = w.float().permute(0, 3, 4, 2, 1).reshape(co, 9, 3 * ci)   # [co][ky,kx][kz*ci + c]
     taps = [(0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
-    return pack_weight(rows, [3 * ci], taps, bias, device)
+    return pack_weight(rows, [3 * ci], taps, bias, device, f16=f16)
 
 
-def pack_conv3d_zfold(w, device):
+def pack_conv3d_zfold(w, device, f16=False):
     """Conv3d 3x3x3 with Cout <= 3 (decoder.py:71) as a per-slice 3x3 conv with rows (kz, co): row kz*4 + co holds
     w[co, :, kz] -- 9 taps and one N = 16 tile instead of 27 taps (an N = 16 MMA costs as much as an N = 64 one, so the
     tap count is what matters); b2d_zfold_combine sums the three z contributions and adds the bias."""
@@ -157,10 +167,10 @@ def pack_conv3d_zfold(w, device):
     for kz in range(3):
         rows[kz * 4:kz * 4 + co] = w[:, :, kz].float().permute(0, 2, 3, 1).reshape(co, 9, ci)
     taps = [(0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
-    return pack_weight(rows, [ci], taps, None, device)
+    return pack_weight(rows, [ci], taps, None, device, f16=f16)
 
 
-def pack_conv3d_upsampled(w, bias, device, py: int, px: int, split=False):
+def pack_conv3d_upsampled(w, bias, device, py: int, px: int, split=False, f16=False):
     """Conv3d 3x3x3 applied to a nearest-2x (in-plane) upsampled map (decoder.py:46-47, 58-59), output phase (py, px):
     out[2y+py, 2x+px] reads only a 2x2 in-plane neighbourhood of the LOW-resolution map, with the 3x3 weights that land
     on the same source pixel summed (fp32) -- 12 taps instead of 27 on 4x the pixels (2.25x fewer MACs, no upsampled
@@ -177,19 +187,19 @@ def pack_conv3d_upsampled(w, bias, device, py: int, px: int, split=False):
                     for kx in kxs:
                         acc += w[:, :, kz, ky, kx].float()
                 cols.append(acc)
-    return pack_weight(torch.stack(cols, dim=1), [ci], taps, bias, device, split)
+    return pack_weight(torch.stack(cols, dim=1), [ci], taps, bias, device, split, f16=f16)
 
 
-def pack_convT2x2(w, bias, device, split=False):
+def pack_convT2x2(w, bias, device, split=False, f16=False):
     """nn.ConvTranspose2d k2 s2 weight [Cin, Cout, 2, 2] (unet/blocks.py:128-133): 4 phase GEMMs, rows phase-major."""
     ci, co, kh, kw = w.shape
     assert (kh, kw) == (2, 2)
-    return pack_weight(w.permute(2, 3, 1, 0).reshape(4 * co, 1, ci), [ci], [(0, 0, 0)], bias, device, split)
+    return pack_weight(w.permute(2, 3, 1, 0).reshape(4 * co, 1, ci), [ci], [(0, 0, 0)], bias, device, split, f16=f16)
 
 
-def pack_linear(w, bias, device, split=False):
+def pack_linear(w, bias, device, split=False, f16=False):
     """nn.Linear / Conv1d-k1 weight [out, in]."""
-    return pack_weight(w.reshape(w.shape[0], 1, -1), [w.reshape(w.shape[0], -1).shape[1]], [(0, 0, 0)], bias, device, split)
+    return pack_weight(w.reshape(w.shape[0], 1, -1), [w.reshape(w.shape[0], -1).shape[1]], [(0, 0, 0)], bias, device, split, f16=f16)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,7 +246,7 @@ class ConvPlan:
         segs: List[Tuple[torch.Tensor, int, int]] = []  # (tensor, cin_pad, kbase)
         for i, a in enumerate(inputs):
             assert a.shape[:4] == (N, D, H, W) and a.C == pw.cin_pad[i], (a.shape, pw.cin_pad, i)
-            assert in_norm is not None or not a.f16, "an fp16 raw tensor cannot be an MMA operand without in_norm"
+            assert in_norm is not None or a.f16 == pw.f16, "an MMA operand must be stored in the weights' 16-bit format"
             segs.append((a.hi, a.C, pw.kbase[i]))
         if split:
             for i, a in enumerate(inputs):
@@ -283,6 +293,7 @@ class ConvPlan:
         d.out_mask = ptr(out_mask)
         d.block_n = block_n
         d.tune_flags, d.tune_ksplit = tune_flags, tune_ksplit
+        d.op_f16 = 1 if pw.f16 else 0
         if sched is not None:
             assert out_mode == 3
             st = sched["state"]
@@ -302,6 +313,7 @@ class ConvPlan:
             d.sched_clip_lo, d.sched_clip_hi = (0.0, 0.0) if clip is None else (float(clip[0]), float(clip[1]))
             xb = sched.get("x_bf16")
             if xb is not None:
+                assert xb.f16 == pw.f16
                 d.sched_x_bf16, d.sched_x_bf16_lo, d.sched_bf16_stride = xb.hi.data_ptr(), ptr(xb.lo), xb.C
         if in_norm is not None:
             st_in, cpg_in, g_in, b_in, act_in = in_norm[:5]
@@ -352,11 +364,16 @@ def gn_apply(x: Act, y: Act, stats: torch.Tensor, cpg: int, gamma, beta, act: bo
     N, D, H, W, Cc = x.shape
     call("b2d_gn_apply", ptr(x.hi), ptr(x.lo), ptr(y.hi), ptr(y.lo), N, D * H * W, Cc, ptr(stats), cpg, ptr(gamma), ptr(beta),
          eps, 1 if act else 0, ptr(temb), ptr(temb_row), temb_row_stride, 0 if temb is None else temb.shape[1], temb_col,
-         ptr(stats_out), 1 if x.f16 else 0, stream)
+         ptr(stats_out), 1 if x.f16 else 0, 1 if y.f16 else 0, stream)
+
+
+def planar_to_cl(x: torch.Tensor, y: Act, N: int, C: int, P: int, coff: int, div_scale, stream: int):
+    """planar fp32 [N][C][P] (optionally / div_scale[c]) -> channels coff.. of the channels-last Act y, in y's format."""
+    call("b2d_planar_to_cl", x.data_ptr(), ptr(y.hi), ptr(y.lo), N, C, P, y.C, coff, ptr(div_scale), 1 if y.f16 else 0, stream)
 
 
 def fused_gn_ok(x: Act, elems_per_sample: int) -> bool:
-    """The per-sample fused GroupNorm kernels (b2d_gn_gn_apply, b2d_maxpool2x2_gn) apply: bf16 mode, a sample of at most
+    """The per-sample fused GroupNorm kernels (b2d_gn_gn_apply, b2d_maxpool2x2_gn) apply: 16-bit modes, a sample of at most
     65536 elements, C/8 dividing 1024."""
     return x.lo is None and elems_per_sample <= 65536 and 1024 % (x.C // 8) == 0
 
@@ -364,19 +381,21 @@ def fused_gn_ok(x: Act, elems_per_sample: int) -> bool:
 def gn_gn_apply(x: Act, y1: Act, y2: Act, stats1: torch.Tensor, g1, b1, act1: bool, g2, b2, act2: bool, stream: int, eps=1e-5):
     N, D, H, W, Cc = x.shape
     call("b2d_gn_gn_apply", ptr(x.hi), 1 if x.f16 else 0, ptr(y1.hi), ptr(y2.hi), N, D * H * W, Cc, ptr(stats1), ptr(g1), ptr(b1), eps,
-         1 if act1 else 0, ptr(g2), ptr(b2), eps, 1 if act2 else 0, stream)
+         1 if act1 else 0, ptr(g2), ptr(b2), eps, 1 if act2 else 0, 1 if y1.f16 else 0, stream)
 
 
 def maxpool_gn(x: Act, y: Act, g, b, act: bool, stream: int, eps=1e-5):
     N, D, H, W, Cc = x.shape
     assert D == 1
-    call("b2d_maxpool2x2_gn", ptr(x.hi), ptr(y.hi), N, H, W, Cc, ptr(g), ptr(b), eps, 1 if act else 0, stream)
+    assert x.f16 == y.f16
+    call("b2d_maxpool2x2_gn", ptr(x.hi), ptr(y.hi), N, H, W, Cc, ptr(g), ptr(b), eps, 1 if act else 0, 1 if x.f16 else 0, stream)
 
 
 def maxpool_stats(x: Act, y: Act, stats: torch.Tensor, stream: int):
     N, D, H, W, Cc = x.shape
     assert D == 1
-    call("b2d_maxpool2x2_stats", ptr(x.hi), ptr(x.lo), ptr(y.hi), ptr(y.lo), N, H, W, Cc, ptr(stats), stream)
+    assert x.f16 == y.f16
+    call("b2d_maxpool2x2_stats", ptr(x.hi), ptr(x.lo), ptr(y.hi), ptr(y.lo), N, H, W, Cc, ptr(stats), 1 if x.f16 else 0, stream)
 
 
 def upsample2x(x: Act, y: Act, stream: int):
@@ -400,7 +419,9 @@ class Program:
 
     def run(self, stream: int, variant: int = 0):
         for _, fn in self.steps:
-            (fn[variant] if isinstance(fn, (list, tuple)) else fn)(stream)
+            if isinstance(fn, (list, tuple)):
+                fn = fn[variant if len(fn) > 1 else 0]  # a one-entry list does not depend on the variant
+            fn(stream)
 
     def __len__(self):
         return len(self.steps)

@@ -48,7 +48,7 @@ class B200LatentDiffusionPredictor:
 
     def __init__(self, model_name="UNet", model_kwargs: Optional[dict] = None, distance_transform=True, *,
                  unet_state: Dict[str, torch.Tensor], vae_state: Dict[str, torch.Tensor], norm_factors: Sequence[float],
-                 num_slices: int = 11, num_timesteps: int = 1000, precision: str = "bf16", use_graph: bool = True,
+                 num_slices: int = 11, num_timesteps: int = 1000, precision: str = "f16", use_graph: bool = True,
                  fuse_scheduler: bool = True, vae_chunk: int = 8, vae_options: Optional[dict] = None, device="cuda"):
         if model_name != "UNet":
             raise ValueError("only the 'UNet' denoiser exists in the reference (predictor.py:136)")
@@ -65,6 +65,7 @@ class B200LatentDiffusionPredictor:
         self.distance_transform = distance_transform
         self.precision = precision
         self.split = precision == "fp32x"
+        self.f16 = precision == "f16"
         self.use_graph = use_graph
         self.fuse_scheduler = fuse_scheduler
         self.vae_chunk = int(vae_chunk)
@@ -121,7 +122,7 @@ class B200LatentDiffusionPredictor:
         ses["workspace"] = engine.new_workspace(dev)
         ses["state"] = torch.zeros(8, dtype=torch.int32, device=dev)
         cin_pad = engine.pad64(self.model.in_channels)
-        ses["unet_in"] = new_act(N, 1, h, w, cin_pad, dev, sp, zero=True)
+        ses["unet_in"] = new_act(N, 1, h, w, cin_pad, dev, sp, zero=True, f16=self.f16)
         ses["x"] = torch.zeros(N, h, w, lat, dtype=torch.float32, device=dev)      # fp32 master latent, channels-last
         ses["eps"] = torch.zeros(N, h, w, lat, dtype=torch.float32, device=dev)
         ses["z"] = None                                                             # host-injected step noise (lazy)
@@ -133,9 +134,9 @@ class B200LatentDiffusionPredictor:
         ui = ses["unet_in"]
         hi5 = ui.hi.view(B, S, h, w, cin_pad)
         lo5 = None if not sp else ui.lo.view(B, S, h, w, cin_pad)
-        lat_views = [Act(hi5[c0:c0 + chunk], None if lo5 is None else lo5[c0:c0 + chunk]) for c0 in starts]
+        lat_views = [Act(hi5[c0:c0 + chunk], None if lo5 is None else lo5[c0:c0 + chunk], self.f16) for c0 in starts]
         # E2D: (chunk,S,3,H,W)/s -> NDHWC bf16 -> mu written straight into unet_in channels [lat, 2*lat)
-        ses["e2d_in"] = new_act(chunk, S, H, W, 64, dev, sp, zero=True)
+        ses["e2d_in"] = new_act(chunk, S, H, W, 64, dev, sp, zero=True, f16=self.f16)
         ses["e2d"] = self.vae.build_encoder("encoder_2d", chunk, S, H, W, x_in=ses["e2d_in"], out=lat_views, out_mode=0, out_coff=lat,
                                             out_cout=lat, workspace=ses["workspace"])
         # D3D: reads the latent out of unet_in (conv_in's packed weight is zero beyond channel `lat`)
@@ -190,10 +191,9 @@ class B200LatentDiffusionPredictor:
         ses["v2d"].copy_(velocity_2d, non_blocking=True)
         xi = ses["e2d_in"]
         chunk = ses["chunk"]
-        scale = self.normalizer["output"].scale_factors.data_ptr()
+        scale = self.normalizer["output"].scale_factors
         for i, c0 in enumerate(ses["starts"]):
-            _lib.call("b2d_planar_to_cl", ses["v2d"][c0:c0 + chunk].data_ptr(), _lib.ptr(xi.hi), _lib.ptr(xi.lo), chunk * S, 3, H * W, xi.C, 0,
-                      scale, s)
+            engine.planar_to_cl(ses["v2d"][c0:c0 + chunk], xi, chunk * S, 3, H * W, 0, scale, s)
             ses["e2d"]["program"].run(s, variant=i)
         if self.distance_transform:
             _lib.call("b2d_edt2d", ses["img"].data_ptr(), ses["edt"].data_ptr(), N, H, W, s, launches=2)
@@ -202,7 +202,7 @@ class B200LatentDiffusionPredictor:
             src = ses["img"]
         _lib.call("b2d_bilinear_resize", src.data_ptr(), ses["feats"].data_ptr(), N, H, W, h, w, s)
         ui = ses["unet_in"]
-        _lib.call("b2d_planar_to_cl", ses["feats"].data_ptr(), _lib.ptr(ui.hi), _lib.ptr(ui.lo), N, 1, h * w, ui.C, 2 * lat, None, s)
+        engine.planar_to_cl(ses["feats"], ui, N, 1, h * w, 2 * lat, None, s)
 
     def _set_latent(self, ses, noise, s):
         """x <- noise (N, C, h, w) planar; fp32 master is channels-last, bf16 copy goes to unet_in[..., :C]."""
@@ -211,7 +211,7 @@ class B200LatentDiffusionPredictor:
         noise = noise.to(self.device, torch.float32).reshape(N, lat, h, w)
         ses["x"].copy_(noise.permute(0, 2, 3, 1))
         ui = ses["unet_in"]
-        _lib.call("b2d_planar_to_cl", ses["x"].data_ptr(), _lib.ptr(ui.hi), _lib.ptr(ui.lo), N * h * w, lat, 1, ui.C, 0, None, s)
+        engine.planar_to_cl(ses["x"], ui, N * h * w, lat, 1, 0, None, s)
 
     def _new_seed(self, ses):
         """A fresh 64-bit Philox key per call, drawn from torch's default generator (so torch.manual_seed makes a run
@@ -238,10 +238,10 @@ class B200LatentDiffusionPredictor:
         _lib.call("b2d_scheduler_step", kind, x.data_ptr(), ses["eps"].data_ptr(), _lib.ptr(ses["z"]) if host_noise else None, x.data_ptr(),
                   x.numel(), coef.data_ptr(), st.data_ptr(), 0, 1 if advance else 0, 1, float(clip_range[0]), float(clip_range[1]),
                   None if self.split else ui.hi.data_ptr(), self.latent_channels, ui.C, 0, (st.data_ptr() + 8) if philox else None,
-                  st.data_ptr() + 4, s)
+                  st.data_ptr() + 4, 1 if self.f16 else 0, s)
         if self.split:
             N, h, w = ses["N"], ses["h"], ses["w"]
-            _lib.call("b2d_planar_to_cl", x.data_ptr(), _lib.ptr(ui.hi), _lib.ptr(ui.lo), N * h * w, self.latent_channels, 1, ui.C, 0, None, s)
+            engine.planar_to_cl(x, ui, N * h * w, self.latent_channels, 1, 0, None, s)
 
     def _run_loop(self, ses, kind, coef, n_steps, step_noise, clip_range, record, philox):
         s = _lib.stream_ptr()

@@ -103,7 +103,7 @@ class B200Scheduler:
         # reference's randn_like), so the lean kernel without the Philox generator is selected (seed 0)
         _lib.call("b2d_scheduler_step", kind, x_t.data_ptr(), eps.data_ptr(), _lib.ptr(noise), out.data_ptr(), x_t.numel(),
                   row_table.data_ptr(), None, int(row), 0, 1 if clip else 0, float(clip_range[0]), float(clip_range[1]),
-                  None, 0, 0, 0, None, None, _lib.stream_ptr())
+                  None, 0, 0, 0, None, None, 0, _lib.stream_ptr())
         return out
 
     @staticmethod

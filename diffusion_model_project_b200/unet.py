@@ -24,7 +24,7 @@ from .synth import attention_heads
 class B200UNet:
     def __init__(self, in_channels=9, out_channels=4, features: Sequence[int] = (64, 128, 256, 512), kernel_size=3,
                  padding_mode="reflect", activation="silu", final_activation=None, attention: str = "", dropout: float = 0.0,
-                 time_embedding_dim: Optional[int] = None, *, precision: str = "bf16", num_timesteps: int = 1000,
+                 time_embedding_dim: Optional[int] = None, *, precision: str = "f16", num_timesteps: int = 1000,
                  device="cuda"):
         # same argument validation surface as the reference for the configurations this path supports
         if kernel_size != 3:
@@ -35,8 +35,8 @@ class B200UNet:
             raise NotImplementedError("B200UNet: activation must be 'silu' and final_activation None")
         if dropout != 0.0:
             raise NotImplementedError("B200UNet: inference path, dropout must be 0")
-        if precision not in ("bf16", "fp32x"):
-            raise ValueError("precision must be 'bf16' or 'fp32x'")
+        if precision not in engine.PRECISIONS:
+            raise ValueError(f"precision must be one of {engine.PRECISIONS}")
         self.in_channels, self.out_channels = in_channels, out_channels
         self.features = list(features)
         self.attention = attention
@@ -44,6 +44,7 @@ class B200UNet:
         self.time_embedding_dim = time_embedding_dim
         self.precision = precision
         self.split = precision == "fp32x"
+        self.f16 = precision == "f16"   # 16-bit operand format: IEEE fp16 ("f16") or bf16 ("bf16"; fp32x: bf16 hi + lo)
         self.num_timesteps = num_timesteps
         self.device = torch.device(device)
         self._w: Dict[str, object] = {}
@@ -55,7 +56,7 @@ class B200UNet:
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
         """Consumes the reference UNet's state dict (keys of unet/models.py, unet/blocks.py) and
         repacks it once; the given tensors are never modified."""
-        dev, sp = self.device, self.split
+        dev, sp, f16 = self.device, self.split, self.f16
         sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
         f = self.features
         w = {}
@@ -64,19 +65,19 @@ class B200UNet:
             return (sd[f"{prefix}.weight"].to(dev).contiguous(), sd[f"{prefix}.bias"].to(dev).contiguous())
 
         def double(prefix, seg_sizes):
-            w[f"{prefix}.block1.conv"] = engine.pack_conv2d(sd[f"{prefix}.block1.conv.weight"], seg_sizes, None, dev, sp)
+            w[f"{prefix}.block1.conv"] = engine.pack_conv2d(sd[f"{prefix}.block1.conv.weight"], seg_sizes, None, dev, sp, f16)
             w[f"{prefix}.block1.norm"] = gn(f"{prefix}.block1.norm")
             cmid = sd[f"{prefix}.block1.conv.weight"].shape[0]
-            w[f"{prefix}.block2.conv"] = engine.pack_conv2d(sd[f"{prefix}.block2.conv.weight"], [cmid], None, dev, sp)
+            w[f"{prefix}.block2.conv"] = engine.pack_conv2d(sd[f"{prefix}.block2.conv.weight"], [cmid], None, dev, sp, f16)
             w[f"{prefix}.block2.norm"] = gn(f"{prefix}.block2.norm")
 
         def attn(prefix, c):
             w[f"{prefix}.norm"] = gn(f"{prefix}.norm")
-            w[f"{prefix}.in_proj"] = engine.pack_linear(sd[f"{prefix}.mha.in_proj_weight"], sd[f"{prefix}.mha.in_proj_bias"], dev, sp)
+            w[f"{prefix}.in_proj"] = engine.pack_linear(sd[f"{prefix}.mha.in_proj_weight"], sd[f"{prefix}.mha.in_proj_bias"], dev, sp, f16)
             # proj_out(out_proj(a)) = (Wp Wo) a + (Wp bo + bp): fold the two C x C projections offline (fp64)
             wo, bo = sd[f"{prefix}.mha.out_proj.weight"].double(), sd[f"{prefix}.mha.out_proj.bias"].double()
             wp, bp = sd[f"{prefix}.proj_out.weight"][:, :, 0].double(), sd[f"{prefix}.proj_out.bias"].double()
-            w[f"{prefix}.out"] = engine.pack_linear((wp @ wo).float(), (wp @ bo + bp).float(), dev, sp)
+            w[f"{prefix}.out"] = engine.pack_linear((wp @ wo).float(), (wp @ bo + bp).float(), dev, sp, f16)
 
         cin = self.in_channels
         for lvl, c in enumerate(f):
@@ -88,12 +89,12 @@ class B200UNet:
         double("bottleneck", [f[-1]])
         rheads = list(reversed(self._heads))
         for lvl, c in enumerate(reversed(f)):
-            w[f"decoder.{lvl}.0.conv"] = engine.pack_convT2x2(sd[f"decoder.{lvl}.0.conv.weight"], sd[f"decoder.{lvl}.0.conv.bias"], dev, sp)
+            w[f"decoder.{lvl}.0.conv"] = engine.pack_convT2x2(sd[f"decoder.{lvl}.0.conv.weight"], sd[f"decoder.{lvl}.0.conv.bias"], dev, sp, f16)
             w[f"decoder.{lvl}.0.norm"] = gn(f"decoder.{lvl}.0.norm")
             double(f"decoder.{lvl}.1", [c, c])
             if rheads[lvl] is not None:
                 attn(f"decoder.{lvl}.2", c)
-        w["final_conv"] = engine.pack_conv2d(sd["final_conv.weight"], [f[0]], sd["final_conv.bias"], dev, sp)
+        w["final_conv"] = engine.pack_conv2d(sd["final_conv.weight"], [f[0]], sd["final_conv.bias"], dev, sp, f16)
         self._w = w
         self._build_time_table(sd)
         self._programs.clear()
@@ -145,7 +146,7 @@ class B200UNet:
         """
         if not self._w:
             raise RuntimeError("B200UNet: load_state_dict() must be called before forward()")
-        dev, sp, f = self.device, self.split, self.features
+        dev, sp, f, F16 = self.device, self.split, self.features, self.f16
         ws = workspace if workspace is not None else engine.new_workspace(dev)
         nl = len(f)
         if h % (1 << nl) or w % (1 << nl):
@@ -171,7 +172,7 @@ class B200UNet:
             return stats_buf[off:off + size]
 
         if x_in is None:
-            x_in = new_act(N, 1, h, w, pad64(self.in_channels), dev, sp, zero=True)
+            x_in = new_act(N, 1, h, w, pad64(self.in_channels), dev, sp, zero=True, f16=F16)
         if temb_row is None:
             temb_row = torch.zeros(N, dtype=torch.int32, device=dev)
             temb_row_stride = 1
@@ -184,10 +185,10 @@ class B200UNet:
             """conv (+GN sums in the epilogue) -> in-place GN apply + SiLU (+temb).  second = (name2, y2, gamma2, beta2): the
             same launch also writes y2 = GN(out; gamma2, beta2) (the attention pre-norm), per-sample fused form."""
             up = 2 if nphase == 4 else 1
-            # raw conv output: fp16 storage in bf16 mode (8x finer than bf16 ahead of the normalisation), rewritten
-            # in place as bf16 by the GroupNorm apply
+            # raw conv output: fp16 storage in both 16-bit modes (8x finer than bf16 ahead of the normalisation), rewritten
+            # in place in the operand format by the GroupNorm apply
             raw = new_act(N, 1, H * up, Wd * up, cout, dev, sp, f16=True)
-            out = raw.as_bf16()
+            out = raw.as_fmt(F16)
             st = stats_view(stats_alloc(1), N * 2)
             plan = ConvPlan(inputs, pw, raw, cout=cout, nphase=nphase, stats=st, stats_cpg=cout, workspace=ws)
             prog.flops += plan.flops
@@ -216,7 +217,7 @@ class B200UNet:
             if heads is None:
                 return double(prefix_d, inputs, c, c, H, Wd)
             if fuse_small and not sp and H * Wd * c <= 65536 and 1024 % (c // 8) == 0:
-                xn = new_act(N, 1, H, Wd, c, dev, sp)
+                xn = new_act(N, 1, H, Wd, c, dev, sp, f16=F16)
                 g2, b2 = W_[f"{prefix_a}.norm"]
                 x = double(prefix_d, inputs, c, c, H, Wd, second=(f"{prefix_a}.gn", xn, g2, b2))
                 return attention(prefix_a, x, c, H, Wd, heads, None, xn=xn)
@@ -230,14 +231,14 @@ class B200UNet:
             T = H * Wd
             g, b = W_[f"{prefix}.norm"]
             if xn is None:
-                xn = new_act(N, 1, H, Wd, c, dev, sp)
+                xn = new_act(N, 1, H, Wd, c, dev, sp, f16=F16)
                 prog.add(f"{prefix}.gn", lambda s: engine.gn_apply(x, xn, st_in, c, g, b, False, s))
-            qkv = new_act(N, 1, H, Wd, 3 * c, dev, sp)
+            qkv = new_act(N, 1, H, Wd, 3 * c, dev, sp, f16=F16)
             p1 = ConvPlan([xn], W_[f"{prefix}.in_proj"], qkv, cout=3 * c, workspace=ws)
             prog.add(f"{prefix}.in_proj", p1.run)
-            ao = new_act(N, 1, H, Wd, c, dev, sp)
+            ao = new_act(N, 1, H, Wd, c, dev, sp, f16=F16)
             prog.add(f"{prefix}.core", lambda s: _lib.call("b2d_attention", _lib.ptr(qkv.hi), _lib.ptr(qkv.lo), _lib.ptr(ao.hi),
-                                                            _lib.ptr(ao.lo), N, T, c, heads, s))
+                                                            _lib.ptr(ao.lo), N, T, c, heads, 1 if F16 else 0, s))
             p2 = ConvPlan([ao], W_[f"{prefix}.out"], x, cout=c, residual=x, workspace=ws)
             prog.add(f"{prefix}.out_proj", p2.run)
             prog.flops += p1.flops + p2.flops + 4.0 * N * T * T * c
@@ -251,7 +252,7 @@ class B200UNet:
             heads = self._heads[lvl]
             x = double_attention(f"encoder.{lvl}.0", f"encoder.{lvl}.1", [x], c, H, Wd, heads)
             skips.append(x)
-            pooled = new_act(N, 1, H // 2, Wd // 2, c, dev, sp)
+            pooled = new_act(N, 1, H // 2, Wd // 2, c, dev, sp, f16=F16)
             g, b = W_[f"encoder.{lvl}.2.norm"]
             if fuse_small and engine.fused_gn_ok(x, (H // 2) * (Wd // 2) * c):
                 prog.add(f"encoder.{lvl}.2.pool+gn", lambda s, x=x, pooled=pooled, g=g, b=b: engine.maxpool_gn(x, pooled, g, b, True, s))
@@ -318,7 +319,7 @@ class B200UNet:
         s = _lib.stream_ptr()
         x = x.contiguous().float()
         xi = st["x_in"]
-        _lib.call("b2d_planar_to_cl", x.data_ptr(), _lib.ptr(xi.hi), _lib.ptr(xi.lo), N, self.in_channels, h * w, xi.C, 0, None, s)
+        engine.planar_to_cl(x, xi, N, self.in_channels, h * w, 0, None, s)
         if time is not None:
             st["temb_row"].copy_(time.to(device=self.device, dtype=torch.int32).reshape(N), non_blocking=True)
         st["program"].run(s)

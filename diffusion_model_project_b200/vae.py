@@ -17,13 +17,13 @@ from .engine import Act, ConvPlan, Program, new_act, pad64
 class _Branch:
     """Packed weights of one Encoder or Decoder."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, kind: str, device, split: bool):
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, kind: str, device, split: bool, f16: bool = False):
         self.kind = kind
         self.w: Dict[str, object] = {}
         g = lambda k: sd[prefix + k].detach().to("cpu", torch.float32)
 
         def conv(name, down=False):
-            self.w[name] = engine.pack_conv3d(g(f"{name}.weight"), g(f"{name}.bias"), device, split, down=down)
+            self.w[name] = engine.pack_conv3d(g(f"{name}.weight"), g(f"{name}.bias"), device, split, down=down, f16=f16)
 
         def norm(name):
             self.w[name] = (g(f"{name}.weight").to(device).contiguous(), g(f"{name}.bias").to(device).contiguous())
@@ -35,7 +35,7 @@ class _Branch:
 
         conv("conv_in")
         if not split and g("conv_in.weight").shape[1] in (3, 8):
-            self.w["conv_in.zstack"] = engine.pack_conv3d_zstack(g("conv_in.weight"), g("conv_in.bias"), device)
+            self.w["conv_in.zstack"] = engine.pack_conv3d_zstack(g("conv_in.weight"), g("conv_in.bias"), device, f16=f16)
         for r in ("res1_1", "res1_2", "res2_1", "res2_2", "res3_1", "res3_2"):
             res(r)
         if kind == "encoder":
@@ -46,10 +46,10 @@ class _Branch:
                 for name in ("conv_up1", "conv_up2"):
                     for ph in range(4):
                         self.w[f"{name}.phase{ph}"] = engine.pack_conv3d_upsampled(g(f"{name}.weight"), g(f"{name}.bias"), device,
-                                                                                  ph >> 1, ph & 1)
+                                                                                  ph >> 1, ph & 1, f16=f16)
         norm("norm_out"); conv("conv_out")
         if kind == "decoder" and not split and g("conv_out.weight").shape[0] <= 3:
-            self.w["conv_out.zfold"] = engine.pack_conv3d_zfold(g("conv_out.weight"), device)
+            self.w["conv_out.zfold"] = engine.pack_conv3d_zfold(g("conv_out.weight"), device, f16=f16)
             self.w["conv_out.bias"] = g("conv_out.bias").to(device=device, dtype=torch.float32).contiguous()
         self.cin = g("conv_in.weight").shape[1]
         self.cout = g("conv_out.weight").shape[0]
@@ -72,8 +72,8 @@ def _as_list(v, n):
 class _Builder:
     """Records a launch program for one branch over static NDHWC buffers."""
 
-    def __init__(self, B, device, split, workspace=None, options=None):
-        self.B, self.dev, self.split = B, device, split
+    def __init__(self, B, device, split, workspace=None, options=None, f16=False):
+        self.B, self.dev, self.split, self.f16 = B, device, split, f16
         self.ws = workspace if workspace is not None else engine.new_workspace(device)
         self.opt = dict(DEFAULT_OPTIONS, **(options or {}))
         self.prog = Program()
@@ -102,10 +102,11 @@ class _Builder:
             self.keep.append(plans)
             return outs, None
         N, D, H, W, _ = x.shape
+        fmt = (raw or self.f16) and not self.split  # raw outputs are fp16 in both 16-bit modes
         if out is None:
-            out = new_act(N, D, H // stride, W // stride, cout, self.dev, self.split, f16=raw)
-        elif isinstance(out, Act) and out.f16 != (raw and not self.split):
-            out = Act(out.hi, out.lo, raw and not self.split)
+            out = new_act(N, D, H // stride, W // stride, cout, self.dev, self.split, f16=fmt)
+        elif isinstance(out, Act) and out.f16 != fmt:
+            out = Act(out.hi, out.lo, fmt)
         st = self.stats() if want_stats else None
         plan = ConvPlan([x], pw, out, cout=cout, stride=stride, residual=residual, stats=st,
                         stats_cpg=(cout // 32) if want_stats else 0, workspace=self.ws, **kw)
@@ -115,7 +116,7 @@ class _Builder:
         return out, st
 
     def gn_silu(self, name, x: Act, st, gnw, inplace: bool):
-        y = x.as_bf16() if inplace else new_act(*x.shape, self.dev, self.split)
+        y = x.as_fmt(self.f16) if inplace else new_act(*x.shape, self.dev, self.split, f16=self.f16)
         g, b = gnw
         C = x.C
         self.prog.add(name, lambda s: engine.gn_apply(x, y, st, C // 32, g, b, True, s))
@@ -145,7 +146,7 @@ class _Builder:
                                  inplace_norm=False, raw=True)
         skip = x
         if f"{name}.residual_layer" in w:
-            assert not x.f16
+            assert x.f16 == self.f16
             skip, _ = self.conv(f"{name}.residual_layer", x, w[f"{name}.residual_layer"], cout, want_stats=False, raw=True)
         return self.norm_conv(f"{name}.conv2", f"{name}.norm2", r, st_r, w[f"{name}.norm2"], w[f"{name}.conv2"], cout,
                               inplace_norm=True, residual=skip, want_stats=want_stats, raw=raw_out)
@@ -157,7 +158,7 @@ class _Builder:
         xl = list(x_in) if isinstance(x_in, (list, tuple)) else [x_in]
         N, D, H, W, C = xl[0].shape
         if "conv_in.zstack" in w and self.opt["zstack"]:
-            xs = new_act(N, D, H, W, C, self.dev, False, zero=True)
+            xs = new_act(N, D, H, W, C, self.dev, False, zero=True, f16=self.f16)
             self.keep.append((xs, xl))
             self.prog.add("conv_in.zstack", [lambda s, xi=xi: _lib.call("b2d_zstack_cl", _lib.ptr(xi.hi), _lib.ptr(xs.hi), N * D, D, H * W, cin, C, s)
                                              for xi in xl])
@@ -181,13 +182,14 @@ class _Builder:
 
 class B200DualVAE:
     def __init__(self, in_channels: int = 3, latent_channels: int = 8, kernel_size: int = 3, share_encoders: bool = False,
-                 share_decoders: bool = False, *, precision: str = "bf16", device="cuda", options: Optional[dict] = None):
+                 share_decoders: bool = False, *, precision: str = "f16", device="cuda", options: Optional[dict] = None):
         if kernel_size != 3:
             raise NotImplementedError("B200DualVAE: kernel_size must be 3")
-        if precision not in ("bf16", "fp32x"):
-            raise ValueError("precision must be 'bf16' or 'fp32x'")
+        if precision not in engine.PRECISIONS:
+            raise ValueError(f"precision must be one of {engine.PRECISIONS}")
         self.in_channels, self.latent_channels = in_channels, latent_channels
         self.split = precision == "fp32x"
+        self.f16 = precision == "f16"
         self.precision = precision
         self.device = torch.device(device)
         self.options = dict(DEFAULT_OPTIONS, **(options or {}))
@@ -199,7 +201,7 @@ class B200DualVAE:
         branches absent from `sd` are simply not available."""
         for b, kind in (("encoder_2d", "encoder"), ("encoder_3d", "encoder"), ("decoder_3d", "decoder"), ("decoder_2d", "decoder")):
             if any(k.startswith(b + ".") for k in sd):
-                self.branches[b] = _Branch(sd, b + ".", kind, self.device, self.split)
+                self.branches[b] = _Branch(sd, b + ".", kind, self.device, self.split, self.f16)
         self._cache.clear()
         return self
 
@@ -213,9 +215,9 @@ class B200DualVAE:
             raise ValueError("encoder input H, W must be divisible by 4")
         br = self.branches[branch]
         w = br.w
-        bd = _Builder(B, self.device, self.split, workspace, self.options)
+        bd = _Builder(B, self.device, self.split, workspace, self.options, self.f16)
         if x_in is None:
-            x_in = new_act(B, D, H, W, pad64(br.cin), self.device, self.split, zero=True)
+            x_in = new_act(B, D, H, W, pad64(br.cin), self.device, self.split, zero=True, f16=self.f16)
         x, st = bd.conv_in(w, x_in, br.cin, 128)
         x, st = bd.res(w, "res1_1", x, st, 128, 128)
         x, _ = bd.res(w, "res1_2", x, st, 128, 128, want_stats=False, raw_out=False)   # -> down1 (MMA operand)
@@ -240,9 +242,9 @@ class B200DualVAE:
         z_in / out / out_mask may be equally long lists: chunk variants of the first and last launches."""
         br = self.branches[branch]
         w = br.w
-        bd = _Builder(B, self.device, self.split, workspace, self.options)
+        bd = _Builder(B, self.device, self.split, workspace, self.options, self.f16)
         if z_in is None:
-            z_in = new_act(B, D, h, w_, pad64(br.cin), self.device, self.split, zero=True)
+            z_in = new_act(B, D, h, w_, pad64(br.cin), self.device, self.split, zero=True, f16=self.f16)
         x, st = bd.conv_in(w, z_in, br.cin, 512)
         x, st = bd.res(w, "res1_1", x, st, 512, 512)
         x, _ = bd.res(w, "res1_2", x, st, 512, 512, want_stats=False, raw_out=False)   # -> upsample -> conv_up1
@@ -260,7 +262,7 @@ class B200DualVAE:
                     bd.keep.append(plan)
                 x = y
             else:
-                up = new_act(N_, D_, 2 * H_, 2 * W_, cin, self.device, self.split)
+                up = new_act(N_, D_, 2 * H_, 2 * W_, cin, self.device, self.split, f16=self.f16)
                 bd.prog.add(f"up{stage}", lambda s, x=x, up=up: engine.upsample2x(x, up, s))
                 x, st = bd.conv(f"conv_up{stage}", up, w[f"conv_up{stage}"], cout, raw=True)
             x, st = bd.res(w, r1, x, st, cout, cout)
@@ -304,7 +306,7 @@ class B200DualVAE:
         s = _lib.stream_ptr()
         xi = st["x_in"]
         x = x.contiguous().float()
-        _lib.call("b2d_planar_to_cl", x.data_ptr(), _lib.ptr(xi.hi), _lib.ptr(xi.lo), B, C, D * H * W, xi.C, 0, _lib.ptr(div_scale), s)
+        engine.planar_to_cl(x, xi, B, C, D * H * W, 0, div_scale, s)
         st["program"].run(s)
         o = st["out"].permute(0, 2, 1, 3, 4).contiguous()  # [B][D][16][h][w] -> (B,16,D,h,w)
         mu, logvar = torch.chunk(o, 2, dim=1)
@@ -339,7 +341,7 @@ class B200DualVAE:
         s = _lib.stream_ptr()
         zi = st["z_in"]
         z = z.contiguous().float()
-        _lib.call("b2d_planar_to_cl", z.data_ptr(), _lib.ptr(zi.hi), _lib.ptr(zi.lo), B, C, D * h * w, zi.C, 0, None, s)
+        engine.planar_to_cl(z, zi, B, C, D * h * w, 0, None, s)
         st["program"].run(s)
         return st["out"].permute(0, 2, 1, 3, 4).contiguous()
 

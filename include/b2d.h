@@ -15,8 +15,9 @@
  *     conv plans, which record the pointers given at creation (TMA descriptors embed addresses);
  *   - `stream` is a cudaStream_t passed as void*; no call synchronises, so every call can be
  *     captured into a CUDA graph;
- *   - activations are channels-last: [N][D][H][W][C] (D = 1 for the UNet's 2-D maps), bf16,
- *     with the channel count padded to a multiple of 64 (pad channels hold zeros).
+ *   - activations are channels-last: [N][D][H][W][C] (D = 1 for the UNet's 2-D maps), 16-bit
+ *     (bf16, or IEEE fp16 where a call's f16 flag says so), with the channel count padded to a
+ *     multiple of 64 (pad channels hold zeros).
  */
 #ifndef B2D_H_
 #define B2D_H_
@@ -67,7 +68,8 @@ B2D_API const char* b2d_last_error(void);
 B2D_API int b2d_scheduler_step(int kind, const float* x_t, const float* eps, const float* noise, float* x_out,
                        int64_t n_elem, const float* coef, int* step_idx, int step_off, int step_inc,
                        int clip, float clip_lo, float clip_hi, void* x_bf16, int group, int group_stride,
-                       uint64_t seed, const uint64_t* seed_dev, unsigned int* ticket, void* stream);
+                       uint64_t seed, const uint64_t* seed_dev, unsigned int* ticket, int x16_f16 /* the 16-bit copy is fp16 */,
+                       void* stream);
 
 /* q_sample (diffusion.py:78-101): out = a*x0 + b*noise with per-image a,b (device [n_img]). */
 B2D_API int b2d_q_sample(const float* x0, const float* noise, float* out, const float* a, const float* b,
@@ -135,6 +137,11 @@ typedef struct b2d_conv_desc {
   int32_t in_f16, in_act;
   float in_eps;
   int32_t tune_flags;              /* B2D_TUNE_* bits (comparison arms of the tests / tools; 0 in production)      */
+  int32_t op_f16;                  /* the MMA operands -- in[] (after the fused input normalisation, if any) and weight --
+                                      hold IEEE fp16 instead of bf16 (tcgen05 kind::f16 takes either at the same rate);
+                                      the fused sampler update's 16-bit copy follows.  fp16's 10-bit mantissa is what
+                                      holds the 1e-2 end-to-end bound over 50 sampling steps; range is not a
+                                      concern because every operand is a normalised activation or a weight            */
   /* out_mode 3 -- the UNet's final_conv (unet/models.py:185) fused with the sampler update that consumes it
    * (diffusion.py:152-188 / :195-234): the epilogue computes eps = conv + bias for the cout (4, 8, 12 or 16) channels of
    * a pixel and applies b2d_scheduler_step's arithmetic (same operation order, same Philox counters: bit-identical to
@@ -155,7 +162,7 @@ typedef struct b2d_conv_desc {
   void* sched_x_bf16;              /* optional bf16 copy of the new latent (the UNet's input buffer)                */
   void* sched_x_bf16_lo;           /* optional x - bf16(x) (fp32x mode)                                             */
   int32_t sched_bf16_stride;       /* channel stride of that buffer                                                 */
-  int32_t reserved[3];
+  int32_t reserved[2];
 } b2d_conv_desc;
 
 #define B2D_TUNE_NO_HALO 1    /* generic tiles even where halo staging applies   */
@@ -183,11 +190,12 @@ B2D_API int b2d_conv_plan_info2(const b2d_conv_plan* plan, int32_t* out8);
 B2D_API int b2d_gn_apply(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int64_t P, int32_t C,
                  const double* stats, int32_t cpg, const float* gamma, const float* beta, float eps, int32_t act,
                  const float* temb_table, const int32_t* temb_row, int32_t temb_row_stride, int32_t temb_ld,
-                 int32_t temb_col, double* stats_out, int32_t in_f16 /* x holds fp16 (see b2d_conv_desc.out_f16) */, void* stream);
+                 int32_t temb_col, double* stats_out, int32_t in_f16 /* x holds fp16 (see b2d_conv_desc.out_f16) */,
+                 int32_t out_f16 /* y is stored as fp16 (and SiLU is evaluated to ~1e-6 instead of tanh.approx's 2^-11) */, void* stream);
 
 /* MaxPool2d(2,2) (unet/blocks.py:161-164,170) + GN(1,C) sums of the pooled map. bf16 NHWC. */
 B2D_API int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, void* y_lo, int32_t N, int32_t H, int32_t W,
-                         int32_t C, double* stats, void* stream);
+                         int32_t C, double* stats, int32_t f16 /* x and y hold fp16 instead of bf16 */, void* stream);
 
 /* Per-sample fused forms for small maps (one CTA per sample; a sample of at most 65536 elements, one GroupNorm group,
  * C/8 dividing 1024; bf16 channels-last, no hi/lo split).  B2D_E_UNSUPPORTED otherwise -- the caller uses the two-launch form.
@@ -196,9 +204,9 @@ B2D_API int b2d_maxpool2x2_stats(const void* x, const void* x_lo, void* y, void*
  *   b2d_maxpool2x2_gn: y = act(GN(maxpool2x2(x); gamma, beta))  -- Down (unet/blocks.py:161-174). */
 B2D_API int b2d_gn_gn_apply(const void* x, int32_t in_f16, void* y1, void* y2, int32_t N, int64_t P, int32_t C, const double* stats1,
                     const float* gamma1, const float* beta1, float eps1, int32_t act1, const float* gamma2, const float* beta2,
-                    float eps2, int32_t act2, void* stream);
+                    float eps2, int32_t act2, int32_t out_f16 /* y1, y2 hold fp16 */, void* stream);
 B2D_API int b2d_maxpool2x2_gn(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, const float* gamma, const float* beta,
-                      float eps, int32_t act, void* stream);
+                      float eps, int32_t act, int32_t f16 /* x and y hold fp16 */, void* stream);
 
 /* nearest-neighbour (1,2,2) upsample, nn.Upsample (vae/decoder.py:46,58). bf16 NDHWC, ND = N*D. */
 B2D_API int b2d_upsample2x_nearest(const void* x, void* y, int32_t ND, int32_t H, int32_t W, int32_t C, void* stream);
@@ -219,10 +227,10 @@ B2D_API int b2d_zstack_cl(const void* x, void* y, int32_t ND, int32_t D, int64_t
  * planar fp32 [N][C][P] (optionally divided by scale[c], MaxNormalizer normalizer.py:46-51)
  * -> channels-last bf16 [N][P][cpad] written at channel offset coff (pad channels untouched). */
 B2D_API int b2d_planar_to_cl(const float* x, void* y, void* y_lo, int32_t N, int32_t C, int64_t P, int32_t cpad, int32_t coff,
-                     const float* div_scale, void* stream);
+                     const float* div_scale, int32_t f16 /* y holds fp16 (no lo part) */, void* stream);
 /* channels-last bf16 [N][P][cstride] (channels coff..coff+C) -> planar fp32 [N][C][P] */
 B2D_API int b2d_cl_to_planar(const void* x, const void* x_lo, float* y, int32_t N, int32_t C, int64_t P, int32_t cstride,
-                     int32_t coff, void* stream);
+                     int32_t coff, int32_t f16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused small-sequence attention core: softmax(q k^T / sqrt(d)) v per (image, head).
@@ -230,7 +238,7 @@ B2D_API int b2d_cl_to_planar(const void* x, const void* x_lo, float* y, int32_t 
  * qkv: bf16 [N][T][3C] (q | k | v, heads contiguous inside each), out: bf16 [N][T][C].
  * ---------------------------------------------------------------------------------------- */
 B2D_API int b2d_attention(const void* qkv, const void* qkv_lo, void* out, void* out_lo, int32_t N, int32_t T, int32_t C,
-                  int32_t heads, void* stream);
+                  int32_t heads, int32_t f16 /* qkv and out hold fp16 (tensor-core path, no lo parts) */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Exact Euclidean distance transform of binary images (distance of every non-zero pixel to the

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 from diffusion_model_project_b200 import _lib, engine
 from diffusion_model_project_b200.engine import ConvPlan, new_act
-from util import bf16_round, from_act, no_tf32, rel_err, stats_ref, to_act
+from util import bf16_round, f16_round, from_act, no_tf32, rel_err, stats_ref, to_act
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
@@ -57,6 +57,51 @@ def test_conv2d_3x3_zero_padding_and_gn_sums(shape):
     assert rel_err(from_act(out, co)[:, :, 0], ref) < TOL_BF16
     sref = stats_ref(ref[:, :, None], 1)
     assert ((st - sref).abs().max() / sref.abs().max()).item() < 1e-4
+
+
+@pytest.mark.parametrize("kind,shape", [("3x3", (3, 64, 128, 32, 32)), ("3x3", (5, 256, 128, 8, 8)), ("3x3", (7, 1024, 512, 2, 2)),
+                                        ("1x1", (3, 256, 768, 16, 16)), ("convT", (3, 128, 64, 8, 8)), ("3d", (2, 128, 128, 16, 16))])
+def test_fp16_operands(kind, shape):
+    """b2d_conv_desc.op_f16: activations and weights stored as IEEE fp16 (the default 16-bit mode) through the same
+    kernels -- halo and generic staging, split-K, transposed-conv phases, 3x3x3 -- with fp16 and bf16 outputs, residual
+    and GroupNorm sums.  With fp16-rounded operands the only error left is the 16-bit rounding of the OUTPUT."""
+    no_tf32()
+    N, ci, co, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + len(kind))
+    D = 3 if kind == "3d" else 1
+    x = f16_round(_rnd(g, N, ci, D, H, W))
+    b = _rnd(g, co) if kind != "3x3" else None
+    if kind == "3x3":
+        w = f16_round(_rnd(g, co, ci, 3, 3, scale=(9 * ci) ** -0.5))
+        pw = engine.pack_conv2d(w, [ci], None, DEV, f16=True)
+        ref = F.conv2d(x[:, :, 0], w, None, padding=1)[:, :, None]
+    elif kind == "1x1":
+        w = f16_round(_rnd(g, co, ci, scale=ci ** -0.5))
+        pw = engine.pack_linear(w, b, DEV, f16=True)
+        ref = F.conv2d(x[:, :, 0], w[:, :, None, None], b)[:, :, None]
+    elif kind == "convT":
+        w = f16_round(_rnd(g, ci, co, 2, 2, scale=ci ** -0.5))
+        pw = engine.pack_convT2x2(w, b, DEV, f16=True)
+        ref = F.conv_transpose2d(x[:, :, 0], w, b, stride=2)[:, :, None]
+    else:
+        w = f16_round(_rnd(g, co, ci, 3, 3, 3, scale=(27 * ci) ** -0.5))
+        pw = engine.pack_conv3d(w, b, DEV, f16=True)
+        ref = F.conv3d(x, w, b, padding=1)
+    assert pw.f16
+    up = 2 if kind == "convT" else 1
+    res = f16_round(_rnd(g, *ref.shape))
+    for out_f16 in (True, False):
+        out = new_act(N, D, H * up, W * up, co, DEV, f16=out_f16)
+        st = torch.zeros(N, 1, 2, dtype=torch.float64, device=DEV)
+        plan = ConvPlan([to_act(x, f16=True)], pw, out, cout=co, nphase=4 if kind == "convT" else 1, stats=st, stats_cpg=co,
+                        residual=to_act(res, f16=True))
+        plan.run(_stream())
+        want = ref + res
+        assert rel_err(from_act(out, co), want) < (1.5e-3 if out_f16 else TOL_BF16)
+        sref = stats_ref(want, 1)
+        assert ((st - sref).abs().max() / sref.abs().max()).item() < 1e-4
+    with pytest.raises(AssertionError):   # operands and weights must share one 16-bit format
+        ConvPlan([to_act(x)], pw, new_act(N, D, H * up, W * up, co, DEV), cout=co, nphase=4 if kind == "convT" else 1)
 
 
 def test_concat_as_two_k_segments():

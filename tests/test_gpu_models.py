@@ -1,9 +1,11 @@
 """Model-level parity on the GPU: B200UNet / B200DualVAE / B200LatentDiffusionPredictor against the
 CPU oracle and the golden vectors generated from the reference itself.
 
-Tolerances are BASELINE.json's: per-step noise prediction max|err|/max|ref| <= 2e-2 in bf16 mode and
-<= 1e-3 in the fp32-class mode ("fp32x": bf16 hi/lo split operands, three tensor-core passes, fp32
-accumulation); final velocity field relative L2 <= 1e-2 against the reference's fp32 output."""
+Tolerances are BASELINE.json's: per-step noise prediction max|err|/max|ref| <= 2e-2 in the 16-bit modes
+("f16": IEEE fp16 operands, the default; "bf16": bf16 operands) and <= 1e-3 in the fp32-class mode
+("fp32x": bf16 hi/lo split operands, three tensor-core passes, fp32 accumulation); final velocity field
+relative L2 <= 1e-2 against the reference's fp32 output.  Where the f16 mode is an order of magnitude
+inside the bound, the test holds it to that."""
 import os
 
 import numpy as np
@@ -22,7 +24,8 @@ from util import rel_err, rel_l2
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 
-TOL_EPS = {"bf16": 2e-2, "fp32x": 1e-3}
+TOL_EPS = {"f16": 3e-3, "bf16": 2e-2, "fp32x": 1e-3}
+MODES = ["f16", "bf16", "fp32x"]
 
 
 @pytest.fixture(scope="module")
@@ -35,7 +38,7 @@ def vae_sd():
     return synth.synth_vae_state(seed=1)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+@pytest.mark.parametrize("precision", MODES)
 def test_unet_forward_vs_golden_and_oracle(unet_sd, golden_dir, precision):
     g = np.load(os.path.join(golden_dir, "unet.npz"))
     m = B200UNet(**synth.UNET_KWARGS, precision=precision, device="cuda").load_state_dict(unet_sd)
@@ -64,7 +67,7 @@ def test_unet_rejects_bad_inputs(unet_sd):
         m(torch.zeros(1, 16, 32, 32, device="cuda"), torch.zeros(1, dtype=torch.long, device="cuda"))
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+@pytest.mark.parametrize("precision", MODES)
 def test_vae_branches_vs_golden(vae_sd, golden_dir, precision):
     g = np.load(os.path.join(golden_dir, "vae.npz"))
     vae = B200DualVAE(3, 8, precision=precision, device="cuda").load_state_dict(vae_sd)
@@ -73,7 +76,7 @@ def test_vae_branches_vs_golden(vae_sd, golden_dir, precision):
     z, (mu, logvar) = vae.encode_2d_deterministic(xv.cuda())
     zl = torch.randn(1, 8, 3, 8, 8, generator=gen)
     dec = vae.decode_3d(zl.cuda())
-    tol = 3e-2 if precision == "bf16" else 1e-3
+    tol = {"bf16": 3e-2, "f16": 4e-3, "fp32x": 1e-3}[precision]
     assert rel_err(mu.cpu(), torch.from_numpy(g["mu"])) <= tol
     assert rel_err(logvar.cpu(), torch.from_numpy(g["logvar"])) <= tol
     assert rel_err(dec.cpu(), torch.from_numpy(g["dec"])) <= tol
@@ -103,7 +106,7 @@ def _predictor(unet_sd, vae_sd, precision, T=1000, graph=True, S=2, **kw):
         num_slices=S, num_timesteps=T, precision=precision, use_graph=graph, device="cuda", **kw)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+@pytest.mark.parametrize("precision", MODES)
 def test_predict_ddim_vs_golden(unet_sd, vae_sd, golden_dir, precision):
     g = np.load(os.path.join(golden_dir, "predict_ddim.npz"))
     img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=2024)
@@ -140,7 +143,7 @@ def test_predict_ddim_eta_host_noise(unet_sd, vae_sd, golden_dir):
     assert rel_l2(out, torch.from_numpy(g["out_eta07"])) <= 1e-2
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+@pytest.mark.parametrize("precision", MODES)
 def test_predict_ddpm_vs_golden(unet_sd, vae_sd, golden_dir, precision):
     g = np.load(os.path.join(golden_dir, "predict_ddpm.npz"))
     img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=2024)
@@ -156,7 +159,7 @@ def test_predict_batch2_matches_per_sample(unet_sd, vae_sd):
     """Samples are independent end to end: a batch of 2 == two batches of 1."""
     img, v2d = synth.synth_inputs(2, num_slices=2, size=128, seed=7)
     noise = synth.synth_noise(2, num_slices=2, latent_size=32, seed=1)
-    p = _predictor(unet_sd, vae_sd, "bf16")
+    p = _predictor(unet_sd, vae_sd, "f16")
     both = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()
     one = p.predict_ddim(img[1:].cuda(), v2d[1:].cuda(), num_steps=2, noise=noise[2:].cuda()).cpu()
     assert rel_l2(both[1:], one) <= 2e-3
@@ -169,7 +172,7 @@ def test_in_kernel_noise_is_seeded_and_fresh_per_call(unet_sd, vae_sd, fuse):
     manual_seed reproduces a run, consecutive calls and different seeds give different fields, without re-capture."""
     img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=3)
     noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=2)
-    p = _predictor(unet_sd, vae_sd, "bf16", T=4, fuse_scheduler=fuse)
+    p = _predictor(unet_sd, vae_sd, "f16", T=4, fuse_scheduler=fuse)
     torch.manual_seed(5)
     a = p.predict(img.cuda(), v2d.cuda(), noise=noise.cuda()).cpu()
     graph = p._session["graph"][1]
@@ -188,7 +191,7 @@ def test_in_kernel_noise_is_seeded_and_fresh_per_call(unet_sd, vae_sd, fuse):
     assert torch.isfinite(d1).all() and not torch.equal(d1, d2)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32x"])
+@pytest.mark.parametrize("precision", MODES)
 def test_fused_sampler_update_is_bit_identical_to_two_launches(unet_sd, vae_sd, precision):
     """final_conv (unet/models.py:185) with the DDPM / DDIM update (diffusion.py:152-234) in its epilogue
     against final_conv -> eps in HBM -> b2d_scheduler_step: same fp32 operation order, same Philox counters, so the
@@ -235,15 +238,15 @@ def test_micro_batched_vae_matches_single_pass(unet_sd, vae_sd):
     img, v2d = synth.synth_inputs(3, num_slices=2, size=128, seed=12)
     noise = synth.synth_noise(3, num_slices=2, latent_size=32, seed=13)
     outs = []
-    for chunk, precision in ((3, "bf16"), (2, "bf16"), (1, "bf16"), (3, "fp32x"), (2, "fp32x")):
+    for chunk, precision in ((3, "f16"), (2, "f16"), (1, "f16"), (3, "fp32x"), (2, "fp32x")):
         p = _predictor(unet_sd, vae_sd, precision, vae_chunk=chunk)
         outs.append(p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu())
         assert p._session["starts"] == {3: [0], 2: [0, 1], 1: [0, 1, 2]}[chunk]
     # a different chunk size changes the VAE tile / split choices (fp32 summation order) only
-    assert rel_l2(outs[1], outs[0]) <= 2e-3 and rel_l2(outs[2], outs[0]) <= 2e-3
+    assert rel_l2(outs[1], outs[0]) <= 1e-3 and rel_l2(outs[2], outs[0]) <= 1e-3
     assert rel_l2(outs[4], outs[3]) <= 1e-4
     ref = opred.predict_ddim(unet_sd, vae_sd, img, v2d, noise, num_steps=2, norm_factors=synth.NORM_FACTORS)
-    assert rel_l2(outs[1], ref) <= 1e-2 and rel_l2(outs[4], ref) <= 1e-3
+    assert rel_l2(outs[1], ref) <= 3e-3 and rel_l2(outs[4], ref) <= 1e-3
 
 
 def test_two_sampling_loops_on_two_streams(unet_sd, vae_sd):
@@ -254,7 +257,7 @@ def test_two_sampling_loops_on_two_streams(unet_sd, vae_sd):
     for k in range(2):
         img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=20 + k)
         noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=30 + k)
-        p = _predictor(unet_sd, vae_sd, "bf16", T=6)
+        p = _predictor(unet_sd, vae_sd, "f16", T=6)
         cases.append((p, img.cuda(), v2d.cuda(), noise.cuda()))
     serial = []
     for k, (p, img, v2d, noise) in enumerate(cases):
@@ -278,7 +281,7 @@ def test_broadcast_mask_and_input_validation(unet_sd, vae_sd):
     img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=14)
     img[:, 1] = img[:, 0]
     noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=15)
-    p = _predictor(unet_sd, vae_sd, "bf16")
+    p = _predictor(unet_sd, vae_sd, "f16")
     full = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()
     one = p.predict_ddim(img[:, :1].cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()   # (B,1,1,H,W) mask
     assert torch.equal(full, one)
@@ -357,7 +360,7 @@ def test_full_size_properties(unet_sd, vae_sd):
     and linearity of the final denormalisation in `norm_factors`."""
     img, v2d = synth.synth_inputs(2, num_slices=11, size=256, seed=11)
     noise = synth.synth_noise(2, num_slices=11, latent_size=64, seed=3)
-    p = _predictor(unet_sd, vae_sd, "bf16", S=11)
+    p = _predictor(unet_sd, vae_sd, "f16", S=11)
     a = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()
     b = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()
     assert a.shape == (2, 11, 3, 256, 256) and torch.isfinite(a).all()

@@ -1,8 +1,13 @@
 """Parity at BASELINE.json's own sizes (11 slices of 256x256, batch 2), against the CPU oracle (= the reference's op
 sequence, pinned to the reference's outputs by tests/test_oracle_golden.py):
 
-  configs[2]/[3]  bf16, CUDA-graphed DDIM-50 loop          per-step eps <= 2e-2, final field rel-L2 <= 1e-2
+  configs[2]/[3]  16-bit mode, CUDA-graphed DDIM-50 loop   per-step eps <= 2e-2, final field rel-L2 <= 1e-2
   configs[1]      fp32-class mode, full-step DDPM, B = 2   per-step eps <= 1e-3, final field rel-L2 <= 1e-2
+
+The 16-bit mode that meets BOTH bounds at this size is "f16" (IEEE fp16 operands, the default).  With bf16 operands
+("bf16" mode) a single UNet evaluation is 1.1e-2 off (inside the 2e-2 per-step bound) but the 50-step trajectory ends
+1.8e-2 from the oracle's field -- outside the 1e-2 bound; that measurement is kept below as its own test so the reason
+for the default is on record (tools/diag_parity.py decomposes it: E2D 8e-3, loop 1.6e-2, D3D 4e-3).
 
 Per-step eps is the north star's "per-step noise-prediction max relative error": the ORACLE's UNet evaluated on the GPU
 path's own UNet input of that step (its x_t, and its E2D / distance conditioning as stored), so the number isolates one
@@ -64,6 +69,13 @@ def case():
     return usd, vsd, img, v2d, noise
 
 
+@pytest.fixture(scope="module")
+def ddim50_oracle(case):
+    """The oracle's own DDIM-50 trajectory (about 40 s of CPU), shared by the two 16-bit-mode tests."""
+    usd, vsd, img, v2d, noise = case
+    return opred.predict_ddim(usd, vsd, img, v2d, noise, num_steps=50, eta=0.0, norm_factors=synth.NORM_FACTORS)
+
+
 def _predictor(usd, vsd, precision, T, graph):
     return B200LatentDiffusionPredictor("UNet", dict(synth.UNET_KWARGS), True, unet_state=usd, vae_state=vsd,
                                         norm_factors=synth.NORM_FACTORS, num_slices=S, num_timesteps=T, precision=precision,
@@ -73,7 +85,7 @@ def _predictor(usd, vsd, precision, T, graph):
 def _gpu_conditioning(p):
     """The conditioning channels the GPU's UNet actually read: E2D mu (8..15) and distance features (16) of unet_in."""
     ui = p._session["unet_in"]
-    c = ui.hi.float()
+    c = ui.hi.view(torch.float16).float() if ui.f16 else ui.hi.float()
     if ui.lo is not None:
         c = c + ui.lo.float()
     c = c[:, 0, :, :, 8:17].permute(0, 3, 1, 2).contiguous().cpu()  # (N, 9, h, w)
@@ -90,28 +102,42 @@ def _eps_errors(usd, rec, v_lat, feats, t_of_step):
     return errs
 
 
-def test_ddim50_bf16_graph_loop_vs_oracle(case):
+def _ddim50(case, ref, precision):
     usd, vsd, img, v2d, noise = case
     steps = 50
-    pe = _predictor(usd, vsd, "bf16", 1000, graph=False)
+    pe = _predictor(usd, vsd, precision, 1000, graph=False)
     rec = EveryNth(5)
     out_eager = pe.predict_ddim(img.cuda(), v2d.cuda(), num_steps=steps, eta=0.0, noise=noise.cuda(), record=rec).cpu()
     ts = pe.ddim_timesteps(steps)
     assert len(rec) == 10
     v_lat, feats = _gpu_conditioning(pe)
     errs = _eps_errors(usd, rec, v_lat, feats, lambda i: ts[i])
-    print("DDIM-50 bf16 per-step eps max-rel error on the GPU's own trajectory:", [(s_, t, f"{e:.2e}") for s_, t, e in errs])
-    assert max(e for _, _, e in errs) <= 2e-2, errs
+    print(f"DDIM-50 {precision} per-step eps max-rel error on the GPU's own trajectory:", [(s_, t, f"{e:.2e}") for s_, t, e in errs])
     del pe
-    pg = _predictor(usd, vsd, "bf16", 1000, graph=True)
+    pg = _predictor(usd, vsd, precision, 1000, graph=True)
     out = pg.predict_ddim(img.cuda(), v2d.cuda(), num_steps=steps, eta=0.0, noise=noise.cuda()).cpu()
     assert pg._session["graph"] is not None
     assert torch.equal(out, out_eager)                                     # the captured loop is the eager loop
-    ref = opred.predict_ddim(usd, vsd, img, v2d, noise, num_steps=steps, eta=0.0, norm_factors=synth.NORM_FACTORS)
     e = rel_l2(out, ref)
-    print(f"DDIM-50 bf16 graph loop, B=2 11x256x256: final field rel-L2 vs the oracle trajectory = {e:.3e}")
-    assert out.shape == ref.shape == (B, S, 3, SIZE, SIZE) and e <= 1e-2, e
+    print(f"DDIM-50 {precision} graph loop, B=2 11x256x256: final field rel-L2 vs the oracle trajectory = {e:.3e}")
+    assert out.shape == ref.shape == (B, S, 3, SIZE, SIZE)
     assert (out[(img == 0).expand_as(out)] == 0).all()
+    return max(e_ for _, _, e_ in errs), e
+
+
+def test_ddim50_f16_graph_loop_vs_oracle(case, ddim50_oracle):
+    """BASELINE configs[2]/[3] in the default 16-bit mode: both north-star bounds, with the measured margin held."""
+    eps_err, field_err = _ddim50(case, ddim50_oracle, "f16")
+    assert eps_err <= 2e-2 and field_err <= 1e-2, (eps_err, field_err)
+    assert eps_err <= 5e-3 and field_err <= 5e-3, (eps_err, field_err)     # fp16 operands: ~8x inside the bf16 numbers
+
+
+def test_ddim50_bf16_operands_measured(case, ddim50_oracle):
+    """bf16 operands: the per-step bound holds, the 50-step field bound does NOT (1.8e-2 measured) -- recorded, not hidden;
+    the assertion pins the measured level so a regression in either direction shows up."""
+    eps_err, field_err = _ddim50(case, ddim50_oracle, "bf16")
+    assert eps_err <= 2e-2, eps_err
+    assert field_err <= 2.5e-2, field_err
 
 
 def test_ddpm1000_fp32x_batch2_eps_every_50th_step(case):

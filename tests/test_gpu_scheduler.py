@@ -72,7 +72,7 @@ def test_device_step_counter_and_bf16_copy(sch):
     ts = [999, 500, 0]
     for i in range(3):
         _lib.call("b2d_scheduler_step", 1, x.data_ptr(), e.data_ptr(), None, x.data_ptr(), x.numel(), coef.data_ptr(),
-                  step.data_ptr(), 0, 1, 1, -30.0, 30.0, buf.data_ptr(), C, stride, 0, None, step.data_ptr() + 4, _lib.stream_ptr())
+                  step.data_ptr(), 0, 1, 1, -30.0, 30.0, buf.data_ptr(), C, stride, 0, None, step.data_ptr() + 4, 0, _lib.stream_ptr())
         xr = o.ddim_sample(e.cpu(), xr, ts[i], ts[i + 1] if i < 2 else -1)
         assert step.tolist() == [i + 1, 0]  # advanced once, ticket left at zero
         assert torch.equal(x.cpu(), xr)
@@ -89,7 +89,7 @@ def test_philox_noise_statistics(sch):
     for row in (0, 1):
         out = torch.empty(n, device="cuda")
         _lib.call("b2d_scheduler_step", 0, x.data_ptr(), e.data_ptr(), None, out.data_ptr(), n, coef.data_ptr(), None, row, 0,
-                  0, 0.0, 0.0, None, 0, 0, 1234, None, None, _lib.stream_ptr())
+                  0, 0.0, 0.0, None, 0, 0, 1234, None, None, 0, _lib.stream_ptr())
         outs.append(out)
     for z in outs:  # out = 0 + 1*z
         assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1) < 5e-3
@@ -101,4 +101,4 @@ def test_invalid_arguments(sch):
     x = torch.zeros(16, device="cuda")
     with pytest.raises(ValueError):
         _lib.call("b2d_scheduler_step", 2, x.data_ptr(), x.data_ptr(), None, x.data_ptr(), 16, x.data_ptr(), None, 0, 0, 0, 0.0,
-                  0.0, None, 0, 0, 0, None, None, _lib.stream_ptr())
+                  0.0, None, 0, 0, 0, None, None, 0, _lib.stream_ptr())

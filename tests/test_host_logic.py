@@ -129,9 +129,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_rejects_bad_arguments_without_a_gpu():
     lib = _lib.lib()
-    assert lib.b2d_scheduler_step(0, None, None, None, None, 16, None, None, 0, 0, 0, 0.0, 0.0, None, 0, 0, 0, None, None, None) == -1
+    assert lib.b2d_scheduler_step(0, None, None, None, None, 16, None, None, 0, 0, 0, 0.0, 0.0, None, 0, 0, 0, None, None, 0, None) == -1
     assert b"null" in lib.b2d_last_error()
-    assert lib.b2d_attention(1, None, 1, None, 1, 16, 100, 2, None) == -1  # d_head 50 not a multiple of 64
+    assert lib.b2d_attention(1, None, 1, None, 1, 16, 100, 2, 0, None) == -1  # d_head 50 not a multiple of 64
     d = _lib.ConvDesc()
     h = ctypes.c_void_p()
     assert lib.b2d_conv_plan_create(ctypes.byref(d), ctypes.byref(h)) == -1

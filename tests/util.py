@@ -17,12 +17,23 @@ def bf16_round(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).float()
 
 
-def to_act(x: torch.Tensor, split=False) -> Act:
-    """planar fp32 (N,C,D,H,W) -> channels-last Act [N,D,H,W,pad64(C)] on x.device."""
+def f16_round(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.float16).float()
+
+
+def fmt_round(x: torch.Tensor, f16: bool) -> torch.Tensor:
+    return f16_round(x) if f16 else bf16_round(x)
+
+
+def to_act(x: torch.Tensor, split=False, f16=False) -> Act:
+    """planar fp32 (N,C,D,H,W) -> channels-last Act [N,D,H,W,pad64(C)] on x.device (bf16, or IEEE fp16 if f16)."""
     N, C, D, H, W = x.shape
     cp = pad64(C)
     cl = torch.zeros(N, D, H, W, cp, dtype=torch.float32, device=x.device)
     cl[..., :C] = x.permute(0, 2, 3, 4, 1)
+    if f16:
+        assert not split
+        return Act(cl.to(torch.float16).contiguous().view(torch.bfloat16), None, True)
     hi = cl.to(torch.bfloat16).contiguous()
     lo = (cl - hi.float()).to(torch.bfloat16).contiguous() if split else None
     return Act(hi, lo)
@@ -30,7 +41,7 @@ def to_act(x: torch.Tensor, split=False) -> Act:
 
 def from_act(a: Act, C: int) -> torch.Tensor:
     """Act -> planar fp32 (N,C,D,H,W)."""
-    v = a.hi.float()
+    v = a.hi.view(torch.float16).float() if a.f16 else a.hi.float()
     if a.lo is not None:
         v = v + a.lo.float()
     return v[..., :C].permute(0, 4, 1, 2, 3).contiguous()

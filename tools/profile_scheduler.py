@@ -19,7 +19,7 @@ for kind, nz, bpe in ((0, zs, 16.0), (1, None, 12.0)):
     tab = coef if kind == 0 else sch.ddim_coef_rows([999, 500], 0.0).to(dev)
     row = 500 if kind == 0 else 0
     fn = lambda: _lib.call("b2d_scheduler_step", kind, xs.data_ptr(), es.data_ptr(), _lib.ptr(nz), xs.data_ptr(), n_el, tab.data_ptr(), None,
-                           row, 0, 1, -30.0, 30.0, None, 0, 0, 0, None, None, s)
+                           row, 0, 1, -30.0, 30.0, None, 0, 0, 0, None, None, 0, s)
     for _ in range(3):
         fn()
     torch.cuda.synchronize()

@@ -16,7 +16,7 @@ torch.set_grad_enabled(False)
 dev = torch.device("cuda", 0)
 pred = B200LatentDiffusionPredictor("UNet", dict(synth.UNET_KWARGS), True, unet_state=synth.synth_unet_state(seed=0),
                                     vae_state=synth.synth_vae_state(seed=1), norm_factors=synth.NORM_FACTORS, num_slices=11,
-                                    num_timesteps=1000, precision="bf16", device=dev)
+                                    num_timesteps=1000, precision="f16", device=dev)
 img, v2d = synth.synth_inputs(B, num_slices=11, size=256, seed=2024)
 noise = synth.synth_noise(B, num_slices=11, latent_size=64, seed=42)
 pred.predict_ddim(img.to(dev), v2d.to(dev), num_steps=2, eta=0.0, noise=noise.to(dev))
