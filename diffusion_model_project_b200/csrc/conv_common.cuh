@@ -19,6 +19,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle atom
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kThreads = 192;
+constexpr int kMaxPieces = 16;  // most items that may share one tile's K loop (split-K <= 16; stream-K is planned within it)
 
 // Division by a launch-constant through a precomputed multiplier (valid for 0 <= n < 2^31): the unit decode runs once
 // per work unit in every warp role, and a hardware-emulated integer division costs ~25 instructions.
@@ -33,8 +34,14 @@ struct FastDiv {
     mul = (uint32_t)(((1ull << p) + div - 1) / div);
     shr = p - 32;
   }
-  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d <= 1 ? n : (__umulhi(n, mul) >> shr); }
-  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    return d <= 1 ? n : (__umulhi(n, mul) >> shr);
+#else
+    return d <= 1 ? n : (uint32_t)(((uint64_t)n * mul) >> 32) >> shr;
+#endif
+  }
+  __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
 };
 
 __device__ __forceinline__ uint32_t pack_bf16_(float a, float b) {
@@ -82,6 +89,12 @@ struct ConvKParams {
   float* ws;         // [tile][ksplit][128][BLOCK_N] fp32 partial accumulators
   int* counters;     // [tile] arrival counters (self-resetting)
   FastDiv fd_ksplit, fd_ncol, fd_w, fd_h, fd_d;  // unit index -> (split, N tile, x, y, z, n tile)
+  // K loop of one tile in B-stage steps (conv_work.cuh): spg steps per A-operand load (halo: in-plane taps / taps per
+  // weight stage; generic: 1), ksteps = ngroups * spg.  streamk: the flat (tile, step) space of total_steps =
+  // tiles * ksteps steps is cut into gridDim.x equal contiguous ranges, one per CTA (tile boundaries inside a range
+  // are whole tiles; a tile cut by a range boundary is reduced through the workspace by whichever piece arrives last)
+  int spg, ksteps, streamk, total_steps;
+  FastDiv fd_ksteps, fd_total;
   // ---- fused input normalisation (halo mode): A tiles are raw pre-GroupNorm values; dedicated warps rewrite each
   // staged tile in shared memory as bf16 silu(gamma * (x - mean) * rstd + beta) before the MMAs read it ----
   int xform;                   // 1: enabled (single segment)

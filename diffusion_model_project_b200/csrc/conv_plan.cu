@@ -100,6 +100,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   // cost = waves over the SMs x (K-loop time of one unit + epilogue / split-K fix-up), in SM clocks.
   int bn = d->block_n;
   int ksplit_pick = 1;
+  bool streamk_pick = false;
   {
     const int sms = num_sms();
     const long long cols = (long long)d->cout * d->nphase;
@@ -114,6 +115,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     const int force_ks = d->tune_ksplit;  // tools/tune_conv.py: measure a given split count (0 = cost model)
     double best = 1e30;
     int best_bn = 0;
+    const bool sk_off = (d->tune_flags & B2D_TUNE_NO_STREAMK) != 0, sk_force = (d->tune_flags & B2D_TUNE_STREAMK) != 0;
     for (int ci = 0; ci < 4; ++ci) {
       const int b = cand[ci];
       if (d->block_n && d->block_n != b) continue;
@@ -133,7 +135,24 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
         const double unit = (double)((ngroups + ks - 1) / ks) * per_group + 1500.0 + 8.0 * b * mt + fix;
         const double waves = (double)((tiles * ks + sms - 1) / sms);
         const double cost = waves * unit;
-        if (cost < best * 0.999) { best = cost; best_bn = b; ksplit_pick = ks; }
+        if (cost < best * 0.999) { best = cost; best_bn = b; ksplit_pick = ks; streamk_pick = false; }
+      }
+      // stream-K: every CTA runs the same number of B-stage steps of the flat (tile, step) space; tiles cut by a range
+      // boundary go through the workspace (at most two partial tiles parked per CTA)
+      if (can_split && !sk_off && force_ks == 0) {
+        const int spg = halo ? gt / (b <= 16 ? 9 : b <= 64 ? 3 : 1) : 1;
+        const long long S = ngroups * spg, total = tiles * S;
+        const long long G = total < sms ? total : sms;
+        const long long per_cta = (total + G - 1) / G;
+        const long long pieces = total / G > 0 ? S / (total / G) + 2 : 99;  // bound on the CTAs that can share one tile
+        if (spg >= 1 && S >= 8 && total >= 2LL * sms && tiles * mt * 2 <= 4096 && total * G < (1LL << 31) && pieces <= kMaxPieces &&
+            16384 + G * 2 * mt * 128LL * b * 4 <= d->workspace_bytes) {
+          const double per_step = per_group / spg;
+          const double items = (double)tiles / (double)G + 1.0;  // epilogues or partial dumps per CTA
+          const double shared = pieces > 2 ? 3.0 : 2.0;          // partial tiles the reducing piece re-reads
+          const double cost = (double)per_cta * per_step + 1500.0 + items * 8.0 * b * mt + 6000.0 + (1.0 + shared) * 12.0 * b * mt;
+          if (sk_force ? (!streamk_pick || cost < best) : cost < best * 0.9) { best = cost; best_bn = b; ksplit_pick = 1; streamk_pick = true; }
+        }
       }
     }
     if (best_bn == 0)
@@ -300,6 +319,12 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     const int ksplit = ksplit_pick;
     constexpr long long kCounterBytes = 16384;
     k.ksplit = ksplit;
+    k.spg = halo ? gt / (bn <= 16 ? 9 : bn <= 64 ? 3 : 1) : 1;  // must match V2Cfg::TPB
+    k.ksteps = k.ngroups * k.spg;
+    k.streamk = streamk_pick ? 1 : 0;
+    k.total_steps = streamk_pick ? (int)(tiles * k.ksteps) : 0;
+    k.fd_ksteps.set((uint32_t)k.ksteps);
+    k.fd_total.set((uint32_t)(streamk_pick ? k.total_steps : 1));
     k.num_units = (int)(tiles * ksplit);
     k.fd_ksplit.set((uint32_t)ksplit); k.fd_ncol.set((uint32_t)k.tiles_ncol);
     k.fd_w.set((uint32_t)k.tiles_w); k.fd_h.set((uint32_t)k.tiles_h); k.fd_d.set((uint32_t)k.tiles_d);
@@ -310,6 +335,12 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
       pl->ws_bytes = kCounterBytes + tiles * ksplit * mt * 128LL * bn * 4;
     }
     pl->grid = dim3((unsigned)(k.num_units < sms ? k.num_units : sms), 1, 1);
+    if (streamk_pick) {
+      pl->grid = dim3((unsigned)(k.total_steps < sms ? k.total_steps : sms), 1, 1);
+      k.counters = reinterpret_cast<int*>(d->workspace);
+      k.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->workspace) + kCounterBytes);
+      pl->ws_bytes = kCounterBytes + (long long)pl->grid.x * 2 * mt * 128LL * bn * 4;
+    }
     // a strided walk changes sample at every unit when a sample has fewer units than the grid has CTAs (UNet levels):
     // every change costs a GroupNorm flush (two epilogue barriers + global atomics); walk contiguous ranges instead
     const int env_contig = (d->tune_flags & B2D_TUNE_CONTIG) ? 1 : (d->tune_flags & B2D_TUNE_STRIDED) ? 0 : -1;
@@ -344,7 +375,7 @@ extern "C" int b2d_conv_plan_info2(const b2d_conv_plan* plan, int32_t* out8) {
   if (!plan || !out8) return set_error(B2D_E_INVALID, "null argument");
   out8[0] = 2;  // engine generation (the one-tile-per-CTA first engine was retired in ABI 6)
   out8[1] = plan->kp.halo;
-  out8[2] = plan->kp.ksplit;
+  out8[2] = plan->kp.streamk ? -1 : plan->kp.ksplit;  // -1: stream-K
   out8[3] = plan->kp.num_units;
   out8[4] = (int32_t)(plan->grid.x * plan->grid.y);
   out8[5] = plan->block_n;

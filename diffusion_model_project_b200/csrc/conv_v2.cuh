@@ -1,6 +1,7 @@
 // Device-side body of the persistent implicit-GEMM conv engine (see conv_engine.cu for the design notes).
 #pragma once
 #include "conv_common.cuh"
+#include "conv_work.cuh"
 
 
 namespace b2d {
@@ -41,69 +42,6 @@ struct V2Cfg {
   static_assert(!HALO || 9 % TPB == 0, "taps per stage must divide 9");
 };
 
-struct UnitCoord {
-  int x0, y0, z0, n0, gcol0, ks, tile;  // tile = m_tile * tiles_ncol + n_tile
-};
-
-__device__ __forceinline__ UnitCoord decode_unit(const ConvKParams& p, int u) {
-  UnitCoord c;
-  uint32_t t, r;
-  p.fd_ksplit.divmod((uint32_t)u, t, r);
-  c.ks = (int)r;
-  c.tile = (int)t;
-  p.fd_ncol.divmod(t, t, r);
-  c.gcol0 = (int)r;
-  p.fd_w.divmod(t, t, r);
-  c.x0 = (int)r << p.lbw;
-  p.fd_h.divmod(t, t, r);
-  c.y0 = (int)r << p.lbh;
-  p.fd_d.divmod(t, t, r);
-  c.z0 = (int)r << p.lbd;
-  c.n0 = (int)t << p.lbn;
-  return c;
-}
-
-// the units one CTA executes: strided over the grid, or (contig) one contiguous range
-struct UnitWalk { int u, end, step; };
-__device__ __forceinline__ UnitWalk unit_walk(const ConvKParams& p) {
-  UnitWalk w;
-  if (p.contig) {
-    w.u = (int)((long long)blockIdx.x * p.num_units / gridDim.x);
-    w.end = (int)((long long)(blockIdx.x + 1) * p.num_units / gridDim.x);
-    w.step = 1;
-  } else {
-    w.u = blockIdx.x; w.end = p.num_units; w.step = gridDim.x;
-  }
-  return w;
-}
-
-// iterate the A-groups [g_lo, g_hi) of one unit as (segment, tap-or-ztap, chunk)
-struct GroupIter {
-  int s, t, c, g, g_hi;
-  __device__ __forceinline__ void init(const ConvKParams& p, int ks) {
-    if (p.ksplit == 1) {  // the common case: the whole K loop, no divisions
-      g = 0; g_hi = p.ngroups; s = 0; t = 0; c = 0;
-      return;
-    }
-    g = (int)p.fd_ksplit.div((uint32_t)(p.ngroups * ks));
-    g_hi = (int)p.fd_ksplit.div((uint32_t)(p.ngroups * (ks + 1)));
-    s = 0;
-    while (s + 1 < p.nseg && g >= p.goff[s + 1]) ++s;
-    const int r = g - p.goff[s];
-    t = r / p.cchunks[s];
-    c = r - t * p.cchunks[s];
-  }
-  __device__ __forceinline__ bool done() const { return g >= g_hi; }
-  __device__ __forceinline__ void next(const ConvKParams& p) {
-    ++g;
-    if (++c == p.cchunks[s]) {
-      c = 0;
-      ++t;
-      if (g == p.goff[s + 1]) { t = 0; ++s; }
-    }
-  }
-};
-
 // One planned convolution executed by the whole CTA (`p` lives in the kernel's parameter space: its TMA descriptors are
 // addressed in place).
 template <int BN, bool HALO, bool XFORM>
@@ -132,7 +70,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
   // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const UnitWalk uw = unit_walk(p);
+  const int cta = (int)blockIdx.x, ncta = (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], XFORM ? Cfg::XF_WARPS : 1); }
@@ -160,11 +98,12 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     int ast = 0, bst = 0;
     uint32_t aph = 0, bph = 0;
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-    for (int u = uw.u; u < uw.end; u += uw.step) {
-      const UnitCoord uc = decode_unit(p, u);
+    WorkIter wi;
+    UnitCoord uc;
+    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
       const int gcol0 = uc.gcol0 * BN;
       GroupIter it;
-      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
+      for (it.init(p, uc.k_lo, uc.k_hi); !it.done(); it.next(p)) {
         const int s = it.s;
         if constexpr (HALO) {
           // activation ring only: the weight ring is fed by its own warp (below) so that A tiles can be
@@ -203,17 +142,18 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     int bst = 0;
     uint32_t bph = 0;
     const uint32_t sB_u = smem_u32(sB);
-    for (int u = uw.u; u < uw.end; u += uw.step) {
-      const UnitCoord uc = decode_unit(p, u);
+    WorkIter wi;
+    UnitCoord uc;
+    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
       const int gcol0 = uc.gcol0 * BN;
       GroupIter it;
-      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
+      for (it.init(p, uc.k_lo, uc.k_hi); !it.done(); it.next(p)) {
         const int s = it.s;
         const int zz = uc.z0 + p.dz[it.t * p.gtaps];
         if (zz < 0 || zz >= p.D) continue;
         const int kb = p.kbase[s] + it.t * p.gtaps * p.cin[s] + it.c * kBlockK;
 #pragma unroll 1
-        for (int ip = 0; ip < p.gtaps; ip += Cfg::TPB) {
+        for (int ip = it.j0 * Cfg::TPB; ip < it.j1 * Cfg::TPB; ip += Cfg::TPB) {
           mbar_wait(&b_empty[bst], bph ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
@@ -237,14 +177,15 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     const uint32_t adesc_lo0 = (uint32_t)adesc0, bdesc_lo0 = (uint32_t)bdesc0;
     int ast = 0, bst = 0, acc = 0;
     uint32_t aph = 0, bph = 0, accph = 0;
-    for (int u = uw.u; u < uw.end; u += uw.step) {
-      const UnitCoord uc = decode_unit(p, u);
+    WorkIter wi;
+    UnitCoord uc;
+    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
       mbar_wait(&t_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
       uint32_t accum = 0;
       GroupIter it;
-      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
+      for (it.init(p, uc.k_lo, uc.k_hi); !it.done(); it.next(p)) {
         if constexpr (HALO) {
           const int zz = uc.z0 + p.dz[it.t * p.gtaps];
           if (zz < 0 || zz >= p.D) continue;
@@ -254,9 +195,10 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         }
         mbar_wait(XFORM ? &a_ready[ast] : &a_full[ast], aph);
         const uint32_t a_lo = adesc_lo0 + (uint32_t)(ast * (Cfg::A_STAGE >> 4));
-        const int GT = HALO ? p.gtaps : 1;  // in-plane taps fed by one staged box (9, or 4 for the upsample-folded convs)
+        // halo: the in-plane taps fed by one staged box (9, or 4 for the upsample-folded convs), restricted to the B-stage
+        // steps [j0, j1) of this group that belong to the item; generic: one step per group
 #pragma unroll 1
-        for (int ip = 0; ip < GT; ip += Cfg::TPB) {
+        for (int ip = it.j0 * Cfg::TPB; ip < it.j1 * Cfg::TPB; ip += Cfg::TPB) {
           mbar_wait(&b_full[bst], bph);
           tc_fence_after();
           const uint32_t b_lo = bdesc_lo0 + (uint32_t)(bst * (Cfg::B_STAGE >> 4));
@@ -357,8 +299,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     if constexpr (BN == 16) {
       if (p.out_mode == 3) { sched_ctx = sched_ctx_load(p); sched = &sched_ctx; }
     }
-    for (int u = uw.u; u < uw.end; u += uw.step) {
-      const UnitCoord uc = decode_unit(p, u);
+    WorkIter wi;
+    UnitCoord uc;
+    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
       if constexpr (SMEM_STATS) {
         if (uc.n0 != cur_n) { flush_stats(); cur_n = uc.n0; }
       }
@@ -413,15 +356,17 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
 #pragma unroll
         for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
       };
-      if (p.ksplit == 1) {
+      const PieceInfo pi = piece_info(p, uc, cta, ncta);
+      if (pi.npieces == 1) {
         conv_epilogue_row<BNG, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u, sched);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
       } else {
-        // ---- split-K: park the fp32 partial, the last split to arrive reduces in a fixed order ----
+        // ---- the tile's K loop is shared (split-K / stream-K): park the fp32 partial, the last piece to arrive reduces
+        // all of them in piece order (deterministic) ----
         // partial tile layout [column quad][row][4 floats]: a warp's 16-byte accesses cover 512 contiguous bytes
-        float4* wq = reinterpret_cast<float4*>(p.ws + (((long long)uc.tile * p.ksplit + uc.ks) * MT + mt) * (128LL * BN)) + r;
+        float4* wq = reinterpret_cast<float4*>(p.ws + ((long long)piece_slot(p, uc, pi, pi.piece, ncta) * MT + mt) * (128LL * BN)) + r;
 #pragma unroll 1
         for (int col0 = 0; col0 < BNG; col0 += CW) {
           float f[CW];
@@ -438,20 +383,21 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         if ((threadIdx.x & 127) == 64) {  // first thread of this four-warp group (warps 2.. start at thread 64)
           int* ctr = p.counters + (uc.tile * MT + mt) * Cfg::NCG + (HALO ? 0 : grp);  // one ticket per (tile, M half, column group)
           const int old = atomicAdd(ctr, 1);
-          const int last = (old == p.ksplit - 1) ? 1 : 0;
+          const int last = (old == pi.npieces - 1) ? 1 : 0;
           if (last) *ctr = 0;  // self-reset for the next launch
           last_flag[grp] = last;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         if (last_flag[grp]) {
           __threadfence();
-          const float4* wbase = reinterpret_cast<const float4*>(p.ws + (((long long)uc.tile * p.ksplit) * MT + mt) * (128LL * BN)) + r;
-          const long long ks_stride = (long long)MT * 32 * BN;  // float4 units between the partials of consecutive splits
+          const float4* wbase = reinterpret_cast<const float4*>(p.ws + (long long)mt * (128LL * BN)) + r;
+          const long long slot_stride = (long long)MT * 32 * BN;  // float4 units per slot
           auto load_ws = [&](int col0, float (&f)[CW]) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) f[j] = 0.f;
-            for (int ks = 0; ks < p.ksplit; ++ks) {
-              const float4* src = wbase + ks * ks_stride + ((col_off + col0) / 4) * 128;
+#pragma unroll 1
+            for (int ks = 0; ks < pi.npieces; ++ks) {
+              const float4* src = wbase + piece_slot(p, uc, pi, ks, ncta) * slot_stride + ((col_off + col0) / 4) * 128;
 #pragma unroll
               for (int q = 0; q < CW / 4; ++q) {
                 const float4 v = __ldcg(src + q * 128);
@@ -483,8 +429,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     const int op_f16 = p.op_f16;
     int ast = 0, cur_n = -1;
     uint32_t aph = 0;
-    for (int u = uw.u; u < uw.end; u += uw.step) {
-      const UnitCoord uc = decode_unit(p, u);
+    WorkIter wi;
+    UnitCoord uc;
+    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
       if (uc.n0 != cur_n) {
         // per-channel scale / shift of this sample from the producer's fp64 (sum, sumsq)
         asm volatile("bar.sync 4, 128;" ::: "memory");  // everyone is done with the previous table
@@ -508,7 +455,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         cur_n = uc.n0;
       }
       GroupIter it;
-      for (it.init(p, uc.ks); !it.done(); it.next(p)) {
+      for (it.init(p, uc.k_lo, uc.k_hi); !it.done(); it.next(p)) {
         const int zz = uc.z0 + p.dz[it.t * p.gtaps];
         if (zz < 0 || zz >= p.D) continue;
         mbar_wait(&a_full[ast], aph);

@@ -205,7 +205,7 @@ def pack_linear(w, bias, device, split=False, f16=False):
 # ------------------------------------------------------------------------------------------------
 # conv plans
 # ------------------------------------------------------------------------------------------------
-WORKSPACE_BYTES = 64 << 20
+WORKSPACE_BYTES = 96 << 20
 _DEFAULT_WS: dict = {}
 
 

@@ -309,6 +309,44 @@ def test_forced_k_split_matches_cost_model_choice():
     assert rel_err(outs[1], outs[0]) < 8e-3 and rel_err(outs[2], outs[0]) < 8e-3
 
 
+@pytest.mark.parametrize("N,ci,co,H,W,f16", [(88, 256, 256, 16, 16, True), (88, 128, 256, 16, 16, False), (88, 512, 512, 8, 8, True),
+                                              (88, 1024, 1024, 4, 4, True), (88, 2048, 2048, 2, 2, False), (22, 64, 64, 64, 64, True),
+                                              (7, 512, 1024, 4, 4, True), (88, 128, 128, 32, 32, True)])
+def test_stream_k_matches_unit_walk(N, ci, co, H, W, f16):
+    """Stream-K (csrc/conv_work.cuh: the flat (tile, K step) space cut into one equal range per CTA, shared tiles reduced
+    through the workspace in piece order) forced on, against the plain unit walk of the same plan: UNet layer shapes at
+    88 slice-images, halo and generic staging, GroupNorm sums.  Repeated launches are bit-identical (deterministic
+    reduction order) and the arrival counters return to zero."""
+    no_tf32()
+    g = torch.Generator().manual_seed(ci + co + H)
+    rnd = f16_round if f16 else bf16_round
+    x = rnd(_rnd(g, N, ci, 1, H, W))
+    w = rnd(_rnd(g, co, ci, 3, 3, scale=(9 * ci) ** -0.5))
+    pw = engine.pack_conv2d(w, [ci], None, DEV, f16=f16)
+    xa = to_act(x, f16=f16)
+    res = {}
+    for name, flags in (("unit", _lib.TUNE_NO_STREAMK | _lib.TUNE_NO_SPLITK), ("streamk", _lib.TUNE_STREAMK)):
+        ws = engine.new_workspace(DEV, 128 << 20)
+        out = new_act(N, 1, H, W, co, DEV, f16=True)
+        st = torch.zeros(N, 2, dtype=torch.float64, device=DEV)
+        plan = ConvPlan([xa], pw, out, cout=co, stats=st, stats_cpg=co, workspace=ws, tune_flags=flags)
+        info = plan.info2()
+        plan.run(_stream())
+        first, st_first = out.hi.clone(), st.clone()
+        if name == "streamk":
+            assert info["ksplit"] == -1 and info["ctas"] == torch.cuda.get_device_properties(0).multi_processor_count, info
+            for _ in range(2):
+                out.hi.zero_(); st.zero_()
+                plan.run(_stream())
+                assert torch.equal(out.hi, first)
+            assert int(ws[:16384].view(torch.int32).abs().sum()) == 0
+        res[name] = (from_act(out, co), st_first)
+    ref = F.conv2d(x[:, :, 0], w, None, padding=1)[:, :, None]
+    assert rel_err(res["streamk"][0], ref) < 1.5e-3                      # fp16 output rounding
+    assert rel_err(res["streamk"][0], res["unit"][0]) < 1.5e-3           # fp32 summation order only
+    assert ((res["streamk"][1] - res["unit"][1]).abs().max() / res["unit"][1].abs().max()).item() < 1e-5
+
+
 def test_split_k_is_deterministic_and_reuses_workspace():
     """Deep UNet level shape (M = 7*4 rows, K = 9*2048): the plan splits K, partials go through the shared workspace,
     the last arriver reduces in a fixed order -> repeated launches are bit-identical and the counters self-reset."""

@@ -45,8 +45,14 @@ plans = {}
 for k in st["keep"]:
     if hasattr(k, "info"):
         plans[id(k)] = k
-for n, t in zip(names, acc):
-    print(f"{t:9.1f} us  {n}")
+for (n, fn), t in zip(prog.steps, acc):
+    owner = getattr(fn, "__self__", None)
+    extra = ""
+    if owner is not None and hasattr(owner, "info2"):
+        i2 = owner.info2()
+        extra = (f"  {owner.flops / t / 1e6:7.1f} TFLOP/s  halo{i2['halo']} bn{i2['block_n']} ks{i2['ksplit']} units{i2['units']} ctas{i2['ctas']} "
+                 f"kgroups{i2['kgroups']}")
+    print(f"{t:9.1f} us  {n}{extra}")
 kinds = {}
 for n, t in zip(names, acc):
     k = n.rsplit(".", 1)[-1]
