@@ -113,8 +113,8 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     const int mt = halo ? 2 : 1;
     const int cand[4] = {256, 128, 64, 16};
     const int force_ks = d->tune_ksplit;  // tools/tune_conv.py: measure a given split count (0 = cost model)
-    double best = 1e30;
-    int best_bn = 0;
+    double best = 1e30, best_sk = 1e30;
+    int best_bn = 0, best_sk_bn = 0;
     const bool sk_off = (d->tune_flags & B2D_TUNE_NO_STREAMK) != 0, sk_force = (d->tune_flags & B2D_TUNE_STREAMK) != 0;
     for (int ci = 0; ci < 4; ++ci) {
       const int b = cand[ci];
@@ -123,7 +123,14 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
       if (halo && gt == 4 && b < 128) continue;  // narrow tiles batch 3 / 9 taps per weight stage
       const long long tiles = tiles_m2 * (b == 16 ? 1 : cols / b);
       const double t_kb = b == 256 ? 512.0 : b == 128 ? 256.0 : b == 64 ? 192.0 : 128.0;
+      // one A-operand group: tensor time of its MMAs, or the time to pull its operand bytes from L2 -- an SM reads about
+      // 40 B/clk through TMA (measured on the deep UNet levels, profiles/r2_tune_conv_88.txt: 128 x 128 tiles at K = 9216
+      // run at 6.5 TB/s over 88 SMs, 256-wide tiles with 3 K splits at 9-11 TB/s over 132), which is what bounds the
+      // generic tiles of the small-map layers and why wider N tiles and more K splits win there
+      constexpr double kL2BytesPerClk = 40.0;
+      const double group_bytes = halo ? 18.0 * 18.0 * 128.0 + gt * b * 128.0 : (128.0 + b) * 128.0;
       double per_group = (halo ? 2.0 * gt : 1.0) * t_kb;
+      if (per_group < group_bytes / kL2BytesPerClk) per_group = group_bytes / kL2BytesPerClk;
       if (d->in_stats && per_group < 6000.0) per_group = 6000.0;  // fused input normalisation: the tile rewrite bounds a group
       for (int ks = 1; ks <= 16; ++ks) {
         if (force_ks > 0 && ks < force_ks) continue;  // tools/tune_conv.py: measure a given split count
@@ -151,9 +158,16 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
           const double items = (double)tiles / (double)G + 1.0;  // epilogues or partial dumps per CTA
           const double shared = pieces > 2 ? 3.0 : 2.0;          // partial tiles the reducing piece re-reads
           const double cost = (double)per_cta * per_step + 1500.0 + items * 8.0 * b * mt + 6000.0 + (1.0 + shared) * 12.0 * b * mt;
-          if (sk_force ? (!streamk_pick || cost < best) : cost < best * 0.9) { best = cost; best_bn = b; ksplit_pick = 1; streamk_pick = true; }
+          if (cost < best_sk) { best_sk = cost; best_sk_bn = b; }
         }
       }
+    }
+    // stream-K only where forced (B2D_TUNE_STREAMK): measured against every (BLOCK_N, K split) choice on the UNet's
+    // layer shapes at 88 slice-images it wins nowhere by more than 1 % (profiles/r2_tune_conv_88.txt) -- parking and
+    // re-reading 128-256 KB partial tiles costs more than the wave quantisation it removes, and where K is long enough
+    // to amortise that, 3-way split-K fills the machine just as well
+    if (best_sk_bn != 0 && (sk_force || best_bn == 0)) {
+      best = best_sk; best_bn = best_sk_bn; ksplit_pick = 1; streamk_pick = true;
     }
     if (best_bn == 0)
       return set_error(B2D_E_INVALID, "cout=%d block_n=%d%s: need cout a multiple of 64 (or <= 16)", d->cout, d->block_n,

@@ -51,6 +51,7 @@ class B200UNet:
         self._programs: Dict[tuple, dict] = {}
         self.temb_table: Optional[torch.Tensor] = None
         self._temb_cols: Dict[str, int] = {}
+        self.conv_tune_flags = 0   # _lib.TUNE_* bits handed to every conv plan (A/B measurements; 0 in production)
 
     # ------------------------------------------------------------------------------ weights
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
@@ -190,7 +191,7 @@ class B200UNet:
             raw = new_act(N, 1, H * up, Wd * up, cout, dev, sp, f16=True)
             out = raw.as_fmt(F16)
             st = stats_view(stats_alloc(1), N * 2)
-            plan = ConvPlan(inputs, pw, raw, cout=cout, nphase=nphase, stats=st, stats_cpg=cout, workspace=ws)
+            plan = ConvPlan(inputs, pw, raw, cout=cout, nphase=nphase, stats=st, stats_cpg=cout, workspace=ws, tune_flags=self.conv_tune_flags)
             prog.flops += plan.flops
             prog.add(f"{name}.conv", plan.run)
             g, b = gnw
@@ -234,12 +235,12 @@ class B200UNet:
                 xn = new_act(N, 1, H, Wd, c, dev, sp, f16=F16)
                 prog.add(f"{prefix}.gn", lambda s: engine.gn_apply(x, xn, st_in, c, g, b, False, s))
             qkv = new_act(N, 1, H, Wd, 3 * c, dev, sp, f16=F16)
-            p1 = ConvPlan([xn], W_[f"{prefix}.in_proj"], qkv, cout=3 * c, workspace=ws)
+            p1 = ConvPlan([xn], W_[f"{prefix}.in_proj"], qkv, cout=3 * c, workspace=ws, tune_flags=self.conv_tune_flags)
             prog.add(f"{prefix}.in_proj", p1.run)
             ao = new_act(N, 1, H, Wd, c, dev, sp, f16=F16)
             prog.add(f"{prefix}.core", lambda s: _lib.call("b2d_attention", _lib.ptr(qkv.hi), _lib.ptr(qkv.lo), _lib.ptr(ao.hi),
                                                             _lib.ptr(ao.lo), N, T, c, heads, 1 if F16 else 0, s))
-            p2 = ConvPlan([ao], W_[f"{prefix}.out"], x, cout=c, residual=x, workspace=ws)
+            p2 = ConvPlan([ao], W_[f"{prefix}.out"], x, cout=c, residual=x, workspace=ws, tune_flags=self.conv_tune_flags)
             prog.add(f"{prefix}.out_proj", p2.run)
             prog.flops += p1.flops + p2.flops + 4.0 * N * T * T * c
             keep.extend([p1, p2, xn, qkv, ao])

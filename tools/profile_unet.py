@@ -1,5 +1,6 @@
 """Per-launch timing of one UNet step (N slice-images of 64x64 latent) with CUDA events, eager (no graph).
-usage: python tools/profile_unet.py [N] [reps]   -- also the target of the ncu launch-list pass."""
+usage: python tools/profile_unet.py [N] [reps] [nograph|graph] [tune_flags]   -- also the target of the ncu launch-list pass.
+tune_flags: _lib.TUNE_* bits for every conv plan (16 = stream-K wherever it applies, 32 = never)."""
 import os
 import sys
 
@@ -14,8 +15,9 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 88
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 torch.set_grad_enabled(False)
 m = B200UNet(**synth.UNET_KWARGS, device="cuda").load_state_dict(synth.synth_unet_state(seed=0))
+m.conv_tune_flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 st = m.build_program(N, 64, 64)
-st["x_in"].hi.copy_(torch.randn(N, 1, 64, 64, 64, device="cuda").to(torch.bfloat16))
+st["x_in"].hi.view(torch.float16).copy_(torch.randn(N, 1, 64, 64, 64, device="cuda").to(torch.float16))
 prog = st["program"]
 s = torch.cuda.current_stream().cuda_stream
 for _ in range(2):

@@ -45,36 +45,44 @@ for kind, cins, cout, H in shapes:
     g = torch.Generator().manual_seed(0)
     xs = []
     for ci in cins:
-        x = new_act(N, 1, H, H, ci, dev)
-        x.hi.copy_(torch.randn(N, 1, H, H, ci, generator=g).to(torch.bfloat16))
+        x = new_act(N, 1, H, H, ci, dev, f16=True)
+        x.hi.view(torch.float16).copy_(torch.randn(N, 1, H, H, ci, generator=g).to(torch.float16))
         xs.append(x)
     cin = sum(cins)
     nphase, up = 1, 1
     if kind == "3x3":
-        pw = engine.pack_conv2d(torch.randn(cout, cin, 3, 3, generator=g) * (9 * cin) ** -0.5, cins, None, dev)
+        pw = engine.pack_conv2d(torch.randn(cout, cin, 3, 3, generator=g) * (9 * cin) ** -0.5, cins, None, dev, f16=True)
     elif kind == "convT":
-        pw = engine.pack_convT2x2(torch.randn(cin, cout, 2, 2, generator=g) * cin ** -0.5, torch.zeros(cout), dev)
+        pw = engine.pack_convT2x2(torch.randn(cin, cout, 2, 2, generator=g) * cin ** -0.5, torch.zeros(cout), dev, f16=True)
         nphase, up = 4, 2
     else:
-        pw = engine.pack_linear(torch.randn(cout, cin, generator=g) * cin ** -0.5, torch.zeros(cout), dev)
-    out = new_act(N, 1, H * up, H * up, cout, dev, f16=(kind != "1x1"))
+        pw = engine.pack_linear(torch.randn(cout, cin, generator=g) * cin ** -0.5, torch.zeros(cout), dev, f16=True)
+    out = new_act(N, 1, H * up, H * up, cout, dev, f16=True)
     st = torch.zeros(N, 1, 2, dtype=torch.float64, device=dev) if kind != "1x1" else None
     kw = dict(cout=cout, nphase=nphase, stats=st, stats_cpg=cout if st is not None else 0)
-    auto = ConvPlan(xs, pw, out, **kw)
+    auto = ConvPlan(xs, pw, out, tune_flags=int(sys.argv[3]) if len(sys.argv) > 3 else 0, **kw)
     t_auto, info = timed(auto), auto.info2()
     rows = []
     for bn in (64, 128, 256):
         for ks in (1, 2, 3, 4, 6, 8):
             try:
-                p = ConvPlan(xs, pw, out, block_n=bn, tune_ksplit=ks, **kw)
+                p = ConvPlan(xs, pw, out, block_n=bn, tune_ksplit=ks, tune_flags=32, **kw)
             except (B2DError, ValueError, RuntimeError):
                 continue
             i2 = p.info2()
             if i2["block_n"] != bn or i2["ksplit"] != ks:
                 continue
             rows.append((timed(p), bn, ks, i2["units"]))
+    for bn in (64, 128, 256):  # stream-K at a forced tile width
+        try:
+            p = ConvPlan(xs, pw, out, block_n=bn, tune_flags=16, **kw)
+        except (B2DError, ValueError, RuntimeError):
+            continue
+        i2 = p.info2()
+        if i2["block_n"] == bn and i2["ksplit"] == -1:
+            rows.append((timed(p), bn, -1, i2["units"]))
     rows.sort()
     best = rows[0] if rows else (float("nan"), 0, 0, 0)
     print(f"{kind:5s} {'+'.join(map(str, cins)):>9s}->{cout:<4d} @{H:<2d}  auto bn{info['block_n']} ks{info['ksplit']} halo{info['halo']} "
           f"{t_auto:6.1f} us | best bn{best[1]} ks{best[2]} ({best[3]} units) {best[0]:6.1f} us | "
-          + "  ".join(f"bn{b}/ks{k}:{t:.1f}" for t, b, k, _ in rows[:6]), flush=True)
+          + "  ".join(f"bn{b}/{'sk' if k < 0 else 'ks' + str(k)}:{t:.1f}" for t, b, k, _ in rows[:8]), flush=True)
