@@ -94,6 +94,13 @@ _SIGNATURES = {
     "b2d_zstack_cl": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_void_p]),
     "b2d_zfold_combine": (c_int, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
                           c_void_p]),
+    "b2d_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                              c_i32, C.c_double, c_void_p]),
+    "b2d_nmse_loss": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2d_gn_silu_bwd": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32,
+                                c_void_p, c_void_p, c_void_p, c_float, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2d_conv_wgrad": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                               c_void_p, c_i32, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2d.so")
-SOURCES = ["api.cu", "scheduler.cu", "elementwise.cu", "conv_plan.cu", "conv_engine.cu", "attention.cu", "edt.cu"]
+SOURCES = ["api.cu", "scheduler.cu", "elementwise.cu", "conv_plan.cu", "conv_engine.cu", "attention.cu", "edt.cu", "train.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

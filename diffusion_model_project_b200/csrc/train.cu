@@ -1,0 +1,458 @@
+// First slice of the UNet training step (reference: Diffusion_model/src/predictor.py:722-748,
+// unet/metrics.py:337-402, helper.py:428-430, train.py:144-148):
+//   * b2d_adam_step        torch.optim.Adam's single-tensor update over a flat fp32 buffer (HBM-bound: 28 B / parameter)
+//   * b2d_nmse_loss        normalized_mse_loss_per_component forward + gradient w.r.t. the prediction
+//   * b2d_gn_silu_bwd      backward of y = silu(GroupNorm(1, C)(x)) (+ time embedding): dx, dgamma, dbeta, dtemb
+//   * b2d_conv_wgrad       3x3 conv weight gradient dW[co][ci][ky][kx] = sum_p dY[p][co] X[p + (ky-1, kx-1)][ci] on tcgen05:
+//                          both operands are read MN-major straight out of the channels-last tensors (pixels are K)
+// The data gradient of a 3x3 conv needs no new kernel: it is the forward engine run on dY with the taps mirrored and the
+// weight matrix transposed at pack time (engine.pack_conv2d_dgrad).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/b2d.h"
+#include "b2d_internal.h"
+#include "b2d_ptx.cuh"
+
+namespace b2d {
+
+static int grid_cap(long long work, int per_block) {
+  long long b = (work + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * 8;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : (int)b;
+}
+
+// ------------------------------------------------------------------------------------------- Adam
+// torch/optim/adam.py _single_tensor_adam, in its operation order:
+//   g' = g * grad_scale (+ wd * p);  m = m + (1 - b1) (g' - m)  [lerp];  v = v * b2 + ((1 - b2) * g') * g'  [addcmul]
+//   p = p + (-lr / (1 - b1^t)) * (m / (sqrt(v) / sqrt(1 - b2^t) + eps))                           [addcdiv]
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float neg_step, float w1, float b2,
+                                                   float w2, float bc2_sqrt, float eps, float wd,
+                                                   float gscale) {
+  const long long nvec = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto one = [&](float pp, float gg, float& mm, float& vv) {
+    float gr = gscale == 1.f ? gg : __fmul_rn(gg, gscale);
+    if (wd != 0.f) gr = __fadd_rn(gr, __fmul_rn(wd, pp));
+    mm = __fadd_rn(mm, __fmul_rn(w1, __fsub_rn(gr, mm)));
+    vv = __fadd_rn(__fmul_rn(vv, b2), __fmul_rn(__fmul_rn(w2, gr), gr));
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), bc2_sqrt), eps);
+    return __fadd_rn(pp, __fmul_rn(neg_step, __fdiv_rn(mm, denom)));
+  };
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    pp.x = one(pp.x, gg.x, mm.x, vv.x); pp.y = one(pp.y, gg.y, mm.y, vv.y);
+    pp.z = one(pp.z, gg.z, mm.z, vv.z); pp.w = one(pp.w, gg.w, mm.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = nvec * 4 + threadIdx.x;
+    float mm = m[i], vv = v[i];
+    p[i] = one(p[i], g[i], mm, vv);
+    m[i] = mm; v[i] = vv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- loss
+// One block per (sample, channel) row of P elements: err = mean((o - t)^2) / (mean(t^2) + eps) [* w_c / sum w], then the
+// gradient of the batch / channel mean w.r.t. o: 2 (o - t) / (P (mean(t^2) + eps)) [* w_c / sum w] / (C N).
+__global__ void __launch_bounds__(256) nmse_rows_kernel(const float* __restrict__ o, const float* __restrict__ t, int C, long long P,
+                                                        const float* __restrict__ weight, float eps, float* __restrict__ err,
+                                                        float* __restrict__ grad, int N) {
+  const int nc = blockIdx.x;
+  const int c = nc % C;
+  const float* orow = o + (long long)nc * P;
+  const float* trow = t + (long long)nc * P;
+  double s = 0.0, st = 0.0;
+  for (long long i = threadIdx.x; i < P; i += blockDim.x) {
+    const float d = orow[i] - trow[i];
+    s += (double)d * d;
+    st += (double)trow[i] * trow[i];
+  }
+  __shared__ double red[2][8];
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, k); st += __shfl_xor_sync(0xffffffffu, st, k); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = st; }
+  __syncthreads();
+  s = 0.0; st = 0.0;
+  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { s += red[0][k]; st += red[1][k]; }  // same order in every thread
+  float wfac = 1.f;
+  if (weight != nullptr) {
+    float ws = 0.f;
+    for (int k = 0; k < C; ++k) ws += weight[k];
+    wfac = weight[c] / ws;
+  }
+  const float mse = (float)(s / (double)P), norm = (float)(st / (double)P);
+  const float inv = 1.f / (norm + eps);
+  if (threadIdx.x == 0) err[nc] = mse * inv * wfac;
+  if (grad != nullptr) {
+    const float k2 = 2.f * inv * wfac / ((float)P * (float)C * (float)N);
+    float* grow = grad + (long long)nc * P;
+    for (long long i = threadIdx.x; i < P; i += blockDim.x) grow[i] = k2 * (orow[i] - trow[i]);
+  }
+}
+// loss[0] = mean over samples of loss[1 + n] = mean over channels of err[n][c]  (fixed summation order)
+__global__ void nmse_finish_kernel(const float* __restrict__ err, int N, int C, float* __restrict__ loss) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float tot = 0.f;
+  for (int n = 0; n < N; ++n) {
+    float e = 0.f;
+    for (int c = 0; c < C; ++c) e += err[n * C + c];
+    e /= (float)C;
+    loss[1 + n] = e;
+    tot += e;
+  }
+  loss[0] = tot / (float)N;
+}
+
+// ------------------------------------------------------------------------------------------- GroupNorm(1, C) + SiLU backward
+__device__ __forceinline__ float ld16(const uint16_t* p, long long i, int f16) {
+  const uint16_t u = p[i];
+  return f16 ? __half2float(__ushort_as_half(u)) : __uint_as_float((uint32_t)u << 16);
+}
+__device__ __forceinline__ float ld16x(const uint16_t* hi, const uint16_t* lo, long long i, int f16) {
+  float v = ld16(hi, i, f16);
+  if (lo != nullptr) v += ld16(lo, i, 0);
+  return v;
+}
+__device__ __forceinline__ void st16x(uint16_t* hi, uint16_t* lo, long long i, float v, int f16) {
+  if (f16) { hi[i] = __half_as_ushort(__float2half_rn(v)); return; }
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = __bfloat16_as_ushort(h);
+  if (lo != nullptr) lo[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+}
+// z = gamma_c xhat + beta_c, a = silu(z): da/dz = sig (1 + z (1 - sig))
+__device__ __forceinline__ float dsilu(float z) {
+  const float sg = 1.f / (1.f + __expf(-z));
+  return sg * (1.f + z * (1.f - sg));
+}
+
+struct GnBwdArgs {
+  const uint16_t *x_hi, *x_lo;   // raw pre-norm activations [N][P][C]
+  const uint16_t *dy_hi, *dy_lo; // upstream gradient of silu(GN(x)) (+temb), same layout
+  uint16_t *dx_hi, *dx_lo;
+  const double* stats;           // forward [N][2] (sum, sumsq)
+  const float *gamma, *beta;
+  double* sums;                  // [N][2]: sum(dxhat), sum(dxhat * xhat)
+  float *dgamma, *dbeta, *dtemb; // [C], [C], [N][C] (dtemb may be NULL), atomically accumulated
+  long long P;
+  int C, act, x_f16, dy_f16, dx_f16;
+  float eps;
+};
+
+// pass 1: per-sample sums of dxhat and dxhat * xhat, per-channel dgamma / dbeta (/ dtemb).  grid (blocks per sample, N)
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
+  extern __shared__ float sm_ch[];  // [3][C]
+  const int n = blockIdx.y, C = a.C;
+  for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) sm_ch[c] = 0.f;
+  __syncthreads();
+  const double cnt = (double)C * (double)a.P;
+  const double mean_d = a.stats[2 * n] / cnt;
+  double var = a.stats[2 * n + 1] / cnt - mean_d * mean_d;
+  if (var < 0) var = 0;
+  const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+  const long long total = a.P * C, base = (long long)n * total;
+  // blockDim.x (256) is a multiple of min(C, 256) for the UNet's channel counts, and the grid stride is a multiple of C
+  // whenever C <= 256 * gridDim.x: keep it simple and general -- shared-memory atomics per element group of one channel
+  double s1 = 0.0, s2 = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float x = ld16x(a.x_hi, a.x_lo, base + i, a.x_f16);
+    const float dy = ld16x(a.dy_hi, a.dy_lo, base + i, a.dy_f16);
+    const float xh = (x - mean) * rstd;
+    const float ga = a.gamma ? a.gamma[c] : 1.f, be = a.beta ? a.beta[c] : 0.f;
+    const float dz = a.act ? dy * dsilu(fmaf(ga, xh, be)) : dy;
+    const float dxh = dz * ga;
+    s1 += (double)dxh;
+    s2 += (double)dxh * xh;
+    atomicAdd(&sm_ch[c], dz * xh);
+    atomicAdd(&sm_ch[C + c], dz);
+    if (a.dtemb != nullptr) atomicAdd(&sm_ch[2 * C + c], dy);
+  }
+  __shared__ double red[2][8];
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, k); s2 += __shfl_xor_sync(0xffffffffu, s2, k); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { t1 += red[0][k]; t2 += red[1][k]; }
+    atomicAdd(a.sums + 2 * n, t1);
+    atomicAdd(a.sums + 2 * n + 1, t2);
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(a.dgamma + c, sm_ch[c]);
+    atomicAdd(a.dbeta + c, sm_ch[C + c]);
+    if (a.dtemb != nullptr) atomicAdd(a.dtemb + (long long)n * C + c, sm_ch[2 * C + c]);
+  }
+}
+// pass 2: dx = rstd (dxhat - mean(dxhat) - xhat mean(dxhat xhat))
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
+  const int n = blockIdx.y, C = a.C;
+  const double cnt = (double)C * (double)a.P;
+  const double mean_d = a.stats[2 * n] / cnt;
+  double var = a.stats[2 * n + 1] / cnt - mean_d * mean_d;
+  if (var < 0) var = 0;
+  const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+  const float m1 = (float)(a.sums[2 * n] / cnt), m2 = (float)(a.sums[2 * n + 1] / cnt);
+  const long long total = a.P * C, base = (long long)n * total;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float x = ld16x(a.x_hi, a.x_lo, base + i, a.x_f16);
+    const float dy = ld16x(a.dy_hi, a.dy_lo, base + i, a.dy_f16);
+    const float xh = (x - mean) * rstd;
+    const float ga = a.gamma ? a.gamma[c] : 1.f, be = a.beta ? a.beta[c] : 0.f;
+    const float dz = a.act ? dy * dsilu(fmaf(ga, xh, be)) : dy;
+    const float dxh = dz * ga;
+    st16x(a.dx_hi, a.dx_lo, base + i, rstd * (dxh - m1 - xh * m2), a.dx_f16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- conv weight gradient (tcgen05)
+constexpr int kWgK = 32;                       // pixels per K chunk (two K = 16 MMAs)
+constexpr int kWgAtom = kWgK * 128;            // bytes of one [32 px][64 ch] swizzled tile
+constexpr int kWgTile = 2 * kWgAtom;           // 128 channels
+constexpr int kWgStages = 3;
+constexpr int kWgThreads = 128;
+constexpr uint32_t kUmmaAMajorMN = 1u << 15;   // instruction-descriptor bit: A operand is MN-major
+constexpr uint32_t kUmmaBMajorMN2 = 1u << 16;
+
+struct WgradParams {
+  CUtensorMap tmY[2];  // dY hi / lo: dims (Cout_pad, W, H, 1, N), box (64, bw, bh, 1, bn), bw * bh * bn = 32
+  CUtensorMap tmX[2];  // X  hi / lo
+  float* dw;           // fp32 [cout][cin_total][3][3], atomically accumulated
+  int cout, cin, cin_off, cin_total;
+  int lbw, lbh, lbn, tiles_w, tiles_h, tiles_n;
+  int chunks, chunks_per_cta, nsrc, op_f16, ci_tiles;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t wg_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nsrc = p.nsrc;
+  const int stage_bytes = nsrc * kWgTile * 4;  // dY + 3 shifted X tiles per source
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
+  uint64_t* empty = full + kWgStages;
+  uint64_t* done = empty + kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5;
+  const int co0 = (blockIdx.x / p.ci_tiles) * 128, ci0 = (blockIdx.x % p.ci_tiles) * 128;
+  const int ky = blockIdx.y;
+  const int ch_lo = blockIdx.z * p.chunks_per_cta;
+  const int ch_hi = min(p.chunks, ch_lo + p.chunks_per_cta);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    for (int s = 0; s < nsrc; ++s) { prefetch_tmap(&p.tmY[s]); prefetch_tmap(&p.tmX[s]); }
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ---------------- TMA producer: per chunk, the dY tile and the three kx-shifted X tiles of this ky row ----------------
+    int st = 0;
+    uint32_t ph = 0;
+    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+      int t = ch;
+      const int x0 = (t % p.tiles_w) << p.lbw; t /= p.tiles_w;
+      const int y0 = (t % p.tiles_h) << p.lbh; t /= p.tiles_h;
+      const int n0 = t << p.lbn;
+      mbar_wait(&empty[st], ph ^ 1);
+      mbar_arrive_expect_tx(&full[st], (uint32_t)stage_bytes);
+      uint8_t* sb = smem + st * stage_bytes;
+      for (int s = 0; s < nsrc; ++s) {
+        uint8_t* yt = sb + s * (4 * kWgTile);
+        for (int a = 0; a < 2; ++a) tma_load_5d(yt + a * kWgAtom, &p.tmY[s], &full[st], co0 + 64 * a, x0, y0, 0, n0);
+        for (int kx = 0; kx < 3; ++kx)
+          for (int a = 0; a < 2; ++a)
+            tma_load_5d(yt + (1 + kx) * kWgTile + a * kWgAtom, &p.tmX[s], &full[st], ci0 + 64 * a, x0 + kx - 1, y0 + ky - 1, 0, n0);
+      }
+      if (++st == kWgStages) { st = 0; ph ^= 1; }
+    }
+  } else if (threadIdx.x == 32) {
+    // ---------------- MMA issuer: D_kx[co][ci] += dY^T X_kx over the chunk's 32 pixels (both operands MN-major) ----------
+    const uint32_t idesc = umma_idesc_16(128, 128, p.op_f16) | kUmmaAMajorMN | kUmmaBMajorMN2;
+    int st = 0;
+    uint32_t ph = 0, accum = 0;
+    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      const uint32_t sb = smem_u32(smem + st * stage_bytes);
+      // products: single source (y, x); split sources hi*hi + hi*lo + lo*hi
+      const int nprod = nsrc == 2 ? 3 : 1;
+      for (int pr = 0; pr < nprod; ++pr) {
+        const int ys = pr == 2 ? 1 : 0, xs = pr == 1 ? 1 : 0;
+        const uint32_t ya = sb + ys * (4 * kWgTile);
+        const uint32_t xa = sb + xs * (4 * kWgTile) + kWgTile;
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int k = 0; k < kWgK / 16; ++k) {
+            const uint64_t ad = umma_smem_desc_mn(ya + k * 16 * 128, kWgAtom, 1024, 2);
+            const uint64_t bd = umma_smem_desc_mn(xa + kx * kWgTile + k * 16 * 128, kWgAtom, 1024, 2);
+            umma_bf16(tmem_base + kx * 128, ad, bd, idesc, accum | (uint32_t)(pr > 0) | (uint32_t)(k > 0));
+          }
+        }
+      }
+      accum = 1;
+      umma_commit(&empty[st]);
+      if (++st == kWgStages) { st = 0; ph ^= 1; }
+    }
+    umma_commit(done);
+  }
+  __syncwarp();
+  // ---------------- epilogue: all four warps, thread = output channel row (TMEM lane) ----------------
+  if (ch_hi > ch_lo) {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int co = co0 + (int)threadIdx.x;
+    const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16);
+    for (int kx = 0; kx < 3; ++kx) {
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + kx * 128 + c0, v);
+        tmem_ld_wait();
+        if (co < p.cout) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ci = ci0 + c0 + j;
+            if (ci < p.cin) atomicAdd(p.dw + (((long long)co * p.cin_total + p.cin_off + ci) * 3 + ky) * 3 + kx, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiledT)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int ilog2_floor(int x) {
+  int l = 0;
+  while ((2 << l) <= x) ++l;
+  return l;
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+
+extern "C" int b2d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                             double beta2, double eps, double weight_decay, int32_t step, double grad_scale, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n < 1 || step < 1) return set_error(B2D_E_INVALID, "b2d_adam_step: bad argument");
+  if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15)
+    return set_error(B2D_E_INVALID, "b2d_adam_step: buffers must be 16-byte aligned");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  adam_kernel<<<grid_cap(n / 4 + 1, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, (long long)n, (float)(-(lr / bc1)), (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+      (float)sqrt(bc2), (float)eps, (float)weight_decay, (float)grad_scale);
+  return check_launch("adam_kernel");
+}
+
+extern "C" int b2d_nmse_loss(const float* pred, const float* target, int32_t N, int32_t C, int64_t P, const float* weight, float eps,
+                             float* err, float* loss, float* grad, void* stream) {
+  if (!pred || !target || !err || !loss || N < 1 || C < 1 || P < 1 || (long long)N * C > 0x7fffffff)
+    return set_error(B2D_E_INVALID, "b2d_nmse_loss: bad argument");
+  nmse_rows_kernel<<<N * C, 256, 0, (cudaStream_t)stream>>>(pred, target, C, (long long)P, weight, eps, err, grad, N);
+  nmse_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(err, N, C, loss);
+  return check_launch("nmse_loss kernels");
+}
+
+extern "C" int b2d_gn_silu_bwd(const void* x_hi, const void* x_lo, int32_t x_f16, const void* dy_hi, const void* dy_lo, int32_t dy_f16,
+                               void* dx_hi, void* dx_lo, int32_t dx_f16, int32_t N, int64_t P, int32_t C, const double* stats,
+                               const float* gamma, const float* beta, float eps, int32_t act, double* sums, float* dgamma, float* dbeta,
+                               float* dtemb, void* stream) {
+  if (!x_hi || !dy_hi || !dx_hi || !stats || !sums || !dgamma || !dbeta || N < 1 || N > 65535 || P < 1 || C < 1 || 3 * C * 4 > 48 * 1024)
+    return set_error(B2D_E_INVALID, "b2d_gn_silu_bwd: bad argument");
+  if ((x_f16 && x_lo) || (dy_f16 && dy_lo) || (dx_f16 && dx_lo)) return set_error(B2D_E_INVALID, "b2d_gn_silu_bwd: an fp16 tensor has no lo part");
+  GnBwdArgs a;
+  a.x_hi = (const uint16_t*)x_hi; a.x_lo = (const uint16_t*)x_lo; a.dy_hi = (const uint16_t*)dy_hi; a.dy_lo = (const uint16_t*)dy_lo;
+  a.dx_hi = (uint16_t*)dx_hi; a.dx_lo = (uint16_t*)dx_lo; a.stats = stats; a.gamma = gamma; a.beta = beta; a.sums = sums;
+  a.dgamma = dgamma; a.dbeta = dbeta; a.dtemb = dtemb; a.P = P; a.C = C; a.act = act ? 1 : 0;
+  a.x_f16 = x_f16 ? 1 : 0; a.dy_f16 = dy_f16 ? 1 : 0; a.dx_f16 = dx_f16 ? 1 : 0; a.eps = eps;
+  int bx = grid_cap(P * C, 256 * 8);
+  const int cap = (num_sms() * 8 + N - 1) / N;
+  if (bx > cap) bx = cap < 1 ? 1 : cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N, st);
+  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "b2d_gn_silu_bwd: memset: %s", cudaGetErrorString(e));
+  gn_bwd_reduce_kernel<<<dim3(bx, N), 256, 3 * C * sizeof(float), st>>>(a);
+  gn_bwd_apply_kernel<<<dim3(bx, N), 256, 0, st>>>(a);
+  return check_launch("gn_silu_bwd kernels");
+}
+
+extern "C" int b2d_conv_wgrad(const void* dy_hi, const void* dy_lo, int32_t cout_pad, const void* x_hi, const void* x_lo, int32_t cin_pad,
+                              int32_t N, int32_t H, int32_t W, int32_t cout, int32_t cin, int32_t cin_off, int32_t cin_total, float* dw,
+                              int32_t op_f16, void* stream) {
+  if (!dy_hi || !x_hi || !dw || N < 1 || H < 1 || W < 1 || cout < 1 || cin < 1 || cin_off < 0 || cin_off + cin > cin_total ||
+      (cout_pad % 64) || (cin_pad % 64) || cout > cout_pad || cin > cin_pad || ((dy_lo == nullptr) != (x_lo == nullptr)))
+    return set_error(B2D_E_INVALID, "b2d_conv_wgrad: bad argument");
+  if ((W & (W - 1)) || (H & (H - 1))) return set_error(B2D_E_UNSUPPORTED, "b2d_conv_wgrad: H, W must be powers of two (got %dx%d)", H, W);
+  if (op_f16 && dy_lo) return set_error(B2D_E_INVALID, "b2d_conv_wgrad: fp16 operands have no lo part");
+  PFN_encodeTiledT enc = reinterpret_cast<PFN_encodeTiledT>(tensor_map_encode_fn());
+  if (!enc) return set_error(B2D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available (no CUDA driver / too old)");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int lw = ilog2_floor(W); if (lw > 3) lw = 3;
+  int lh = ilog2_floor(H); if (lh > 5 - lw) lh = 5 - lw;
+  const int ln = 5 - lw - lh;
+  p.lbw = lw; p.lbh = lh; p.lbn = ln;
+  p.tiles_w = W >> lw; p.tiles_h = H >> lh; p.tiles_n = (N + (1 << ln) - 1) >> ln;
+  p.chunks = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.nsrc = dy_lo ? 2 : 1;
+  p.op_f16 = op_f16 ? 1 : 0;
+  p.dw = dw; p.cout = cout; p.cin = cin; p.cin_off = cin_off; p.cin_total = cin_total;
+  const void* ys[2] = {dy_hi, dy_lo};
+  const void* xs[2] = {x_hi, x_lo};
+  for (int s = 0; s < p.nsrc; ++s) {
+    for (int which = 0; which < 2; ++which) {
+      const int cpad = which == 0 ? cout_pad : cin_pad;
+      cuuint64_t dims[5] = {(cuuint64_t)cpad, (cuuint64_t)W, (cuuint64_t)H, 1, (cuuint64_t)N};
+      cuuint64_t strides[4] = {(cuuint64_t)cpad * 2, (cuuint64_t)cpad * 2 * W, (cuuint64_t)cpad * 2 * W * H, (cuuint64_t)cpad * 2 * W * H};
+      cuuint32_t box[5] = {64, (cuuint32_t)(1 << lw), (cuuint32_t)(1 << lh), 1, (cuuint32_t)(1 << ln)};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = enc(which == 0 ? &p.tmY[s] : &p.tmX[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(which == 0 ? ys[s] : xs[s]),
+                       dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(B2D_E_CUDA, "b2d_conv_wgrad: cuTensorMapEncodeTiled failed: %d", (int)r);
+    }
+  }
+  const int co_tiles = (cout + 127) / 128;
+  p.ci_tiles = (cin + 127) / 128;
+  int splits = (2 * num_sms()) / (co_tiles * p.ci_tiles * 3);
+  if (splits < 1) splits = 1;
+  if (splits > p.chunks) splits = p.chunks;
+  p.chunks_per_cta = (p.chunks + splits - 1) / splits;
+  splits = (p.chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
+  const int smem = kWgStages * p.nsrc * kWgTile * 4 + 256 + 1024;
+  static unsigned long long configured = 0;
+  cudaError_t e = smem_attr_once(conv_wgrad_kernel, 227 * 1024, configured);
+  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "b2d_conv_wgrad: smem attr: %s", cudaGetErrorString(e));
+  conv_wgrad_kernel<<<dim3(co_tiles * p.ci_tiles, 3, splits), kWgThreads, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("conv_wgrad_kernel");
+}

@@ -252,6 +252,37 @@ B2D_API int b2d_edt2d(const float* img, float* out, int32_t n_img, int32_t H, in
 B2D_API int b2d_bilinear_resize(const float* x, float* y, int32_t n_img, int32_t H, int32_t W, int32_t OH, int32_t OW,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training step, first slice (csrc/train.cu).  Reference: predictor.py:722-748 (q_sample, concat, eps-prediction),
+ * unet/metrics.py:337-402 (criterion), helper.py:428-430 (backward, optimizer.step), train.py:144-148 (Adam).
+ * The data gradient of a 3x3 conv is b2d_conv_run on dY with mirrored taps and a transposed weight pack.
+ * ---------------------------------------------------------------------------------------- */
+/* torch.optim.Adam, single-tensor form, over a flat fp32 buffer (16-byte aligned): grad * grad_scale (+ weight_decay * p),
+ * lerp / addcmul / addcdiv in torch's order, bias corrections from `step` (>= 1).  28 B of HBM traffic per parameter. */
+B2D_API int b2d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int32_t step, double grad_scale, void* stream);
+/* normalized_mse_loss_per_component (metrics.py:337-402) on planar fp32 [N][C][P]: err[n*C+c] = mean((o-t)^2) / (mean(t^2) + eps)
+ * [* w_c / sum w]; loss[0] = batch mean, loss[1 + n] = per-sample channel mean; grad (optional, same shape as pred) =
+ * d loss[0] / d pred.  weight: [C] or NULL. */
+B2D_API int b2d_nmse_loss(const float* pred, const float* target, int32_t N, int32_t C, int64_t P, const float* weight, float eps,
+                  float* err, float* loss, float* grad, void* stream);
+/* Backward of y = silu?(GroupNorm(1, C)(x)) [+ temb[n][c]] (unet/blocks.py:37-47, 98-105): x raw pre-norm values and dy the
+ * upstream gradient, channels-last [N][P][C] 16-bit (hi + optional bf16 lo; *_f16: the hi part holds fp16); stats = the
+ * forward (sum, sumsq) per sample.  Writes dx (same layout), accumulates dgamma[C], dbeta[C] and (optional) dtemb[N][C]
+ * atomically (zero them first); sums: [N][2] fp64 scratch. */
+B2D_API int b2d_gn_silu_bwd(const void* x_hi, const void* x_lo, int32_t x_f16, const void* dy_hi, const void* dy_lo, int32_t dy_f16,
+                    void* dx_hi, void* dx_lo, int32_t dx_f16, int32_t N, int64_t P, int32_t C, const double* stats,
+                    const float* gamma, const float* beta, float eps, int32_t act, double* sums, float* dgamma, float* dbeta,
+                    float* dtemb, void* stream);
+/* Weight gradient of a 3x3 zero-padded conv (unet/blocks.py:29-36) on tcgen05: dw[co][cin_off + ci][ky][kx] +=
+ * sum over pixels of dY[p][co] * X[p + (ky-1, kx-1)][ci]; dY [N][H][W][cout_pad], X [N][H][W][cin_pad] channels-last 16-bit
+ * (hi + optional bf16 lo: three products hi*hi + hi*lo + lo*hi), H and W powers of two.  dw: fp32 in the reference's
+ * (Cout, cin_total, 3, 3) layout, atomically accumulated (zero it first); cin_off selects the channel block of a
+ * concatenated input (torch.cat skip | up, unet/models.py:177). */
+B2D_API int b2d_conv_wgrad(const void* dy_hi, const void* dy_lo, int32_t cout_pad, const void* x_hi, const void* x_lo, int32_t cin_pad,
+                   int32_t N, int32_t H, int32_t W, int32_t cout, int32_t cin, int32_t cin_off, int32_t cin_total, float* dw,
+                   int32_t op_f16, void* stream);
+
 /* fill helpers used by the fused loop (graph-capturable) */
 B2D_API int b2d_zero(void* p, int64_t bytes, void* stream);
 

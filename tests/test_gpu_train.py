@@ -1,0 +1,157 @@
+"""Training-step slice on the GPU: the criterion, Adam, and the backward of one DoubleBlock
+(GroupNorm/SiLU backward, conv data gradient through the forward engine, tcgen05 weight gradient) against torch autograd
+through the oracle's functional UNet blocks and against the golden vectors of one training step of the unmodified
+reference (tests/golden/train_step.npz).  Bounds: loss <= 1e-5, gradients rel-L2 <= 2e-3 (fp32-class mode)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffusion_model_project_b200 import _lib, engine, synth, train
+from diffusion_model_project_b200.engine import new_act
+from oracle import train as otrain
+from oracle import unet as ounet
+from util import f16_round, from_act, no_tf32, rel_err, rel_l2, to_act
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "train_step.npz"))
+
+
+def test_nmse_loss_forward_and_gradient(golden_dir):
+    g = torch.Generator().manual_seed(3)
+    for shape, weight in (((4, 8, 32, 32), None), ((3, 5, 7, 9), torch.tensor([1.0, 2.0, 0.5, 1.5, 3.0])), ((2, 3, 4, 8, 8), None)):
+        o = torch.randn(*shape, generator=g)
+        t = torch.randn(*shape, generator=g) * 0.7
+        oo = o.clone().requires_grad_(True)
+        ref = otrain.normalized_mse_loss_per_component(oo, t, weight_per_channel=weight)
+        ref.backward()
+        per = otrain.normalized_mse_loss_per_component(o, t, reduce=False, weight_per_channel=weight)
+        loss, per_gpu, grad = train.nmse_loss(o.to(DEV), t.to(DEV), None if weight is None else weight.to(DEV))
+        assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+        assert rel_err(per_gpu.cpu(), per) <= 1e-5
+        assert rel_err(grad.cpu(), oo.grad) <= 1e-5
+    with torch.no_grad():
+        with pytest.raises(ValueError):
+            train.nmse_loss(torch.zeros(2, 3, 4, device=DEV), torch.zeros(2, 3, 4, device=DEV))   # metrics.py:369
+    # the reference's own training step: its eps-prediction and target noise give its loss
+    gd = _golden(golden_dir)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_train_golden", os.path.join(golden_dir, "make_train_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    import sys
+    saved = list(sys.path)
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path[:] = saved
+    _, _, _, noise, _ = mod.train_inputs()
+    loss, _, _ = train.nmse_loss(torch.from_numpy(gd["pred"]).to(DEV), noise.to(DEV), want_grad=False)
+    assert abs(loss.item() - float(gd["loss"])) <= 1e-5 * abs(float(gd["loss"]))
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_flat_adam_matches_torch_adam(wd, golden_dir):
+    g = torch.Generator().manual_seed(5)
+    params = {"a.weight": torch.randn(64, 17, 3, 3, generator=g) * 0.1, "a.bias": torch.randn(7, generator=g), "b": torch.randn(1001, generator=g)}
+    opt = train.FlatAdam(params, lr=1e-3, weight_decay=wd, device=DEV)
+    ref_p = [v.clone().to(DEV).requires_grad_(True) for v in params.values()]
+    ref = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=wd, foreach=False, fused=False)
+    for step in range(5):
+        grads = [torch.randn(v.shape, generator=g) * (0.5 ** step) for v in params.values()]
+        for k, gr, rp in zip(opt.names, grads, ref_p):
+            opt.view(opt.grad, k).copy_(gr)
+            rp.grad = gr.to(DEV)
+        opt.step()
+        ref.step()
+        for k, rp in zip(opt.names, ref_p):
+            assert (opt.view(opt.param, k) - rp.detach()).abs().max().item() <= 2e-7 * (1 + rp.detach().abs().max().item())
+    # padding between the 16-byte aligned segments never moves
+    assert opt.numel % 4 == 0 and opt.offsets["b"][0] % 4 == 0
+    # the reference's own first Adam step (lr 1e-4, weight_decay 0): parameter deltas of the golden gradients
+    if wd == 0.0:
+        gd = _golden(golden_dir)
+        names = [k[len("grad::"):] for k in gd.files if k.startswith("grad::")]
+        zeros = {k: torch.zeros(gd[f"grad::{k}"].shape) for k in names}
+        o2 = train.FlatAdam(zeros, lr=1e-4, device=DEV)
+        for k in names:
+            o2.view(o2.grad, k).copy_(torch.from_numpy(gd[f"grad::{k}"]))
+        o2.step()
+        for k in names:
+            assert (o2.view(o2.param, k).cpu() - torch.from_numpy(gd[f"delta::{k}"])).abs().max().item() <= 2e-8
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("N,co,ci,H,W", [(3, 128, 128, 16, 16), (2, 64, 17, 32, 32), (5, 256, 192, 8, 8), (9, 192, 320, 4, 4), (11, 128, 64, 2, 2)])
+def test_conv_wgrad(N, co, ci, H, W, split):
+    """dW of a 3x3 zero-padded conv against torch's conv2d weight gradient; split: bf16 hi + lo operands (fp32-class), else
+    IEEE fp16 operands.  Ragged channel counts (17, 192, 320), small maps with several images per pixel box, N not a multiple
+    of the box."""
+    no_tf32()
+    g = torch.Generator().manual_seed(N + co + ci)
+    x = (torch.randn(N, ci, 1, H, W, generator=g)).to(DEV)
+    dy = (torch.randn(N, co, 1, H, W, generator=g) * 0.3).to(DEV)
+    if not split:
+        x, dy = f16_round(x), f16_round(dy)
+    xa, dya = to_act(x, split=split, f16=not split), to_act(dy, split=split, f16=not split)
+    dw = torch.zeros(co, ci + 5, 3, 3, device=DEV)                       # a 5-channel block in front: cin_off
+    train.conv_wgrad(dya, xa, dw, co, ci, 5, _s())
+    ref = torch.nn.grad.conv2d_weight(x[:, :, 0], (co, ci, 3, 3), dy[:, :, 0], padding=1)
+    assert dw[:, :5].abs().max().item() == 0
+    assert rel_l2(dw[:, 5:], ref) <= (2e-5 if split else 1e-5), rel_l2(dw[:, 5:], ref)
+
+
+@pytest.mark.parametrize("N,segs,cmid,cout,H", [(3, [128], 128, 128, 16), (2, [64, 64], 64, 64, 32), (8, [256], 512, 512, 4), (2, [17], 64, 64, 32)])
+def test_double_block_backward_vs_autograd(N, segs, cmid, cout, H):
+    """One DoubleBlock (unet/blocks.py:50-107) forward + backward on the GPU against torch.autograd through the oracle's
+    functional block: encoder block, decoder block over a channel concatenation, a small-map level, and the UNet's first
+    block (17 input channels, no input gradient)."""
+    no_tf32()
+    g = torch.Generator().manual_seed(N + cmid + H)
+    cin = sum(segs)
+    sd = {"b.block1.conv.weight": torch.randn(cmid, cin, 3, 3, generator=g) * (9 * cin) ** -0.5,
+          "b.block1.norm.weight": 1 + 0.2 * torch.randn(cmid, generator=g), "b.block1.norm.bias": 0.2 * torch.randn(cmid, generator=g),
+          "b.block2.conv.weight": torch.randn(cout, cmid, 3, 3, generator=g) * (9 * cmid) ** -0.5,
+          "b.block2.norm.weight": 1 + 0.2 * torch.randn(cout, generator=g), "b.block2.norm.bias": 0.2 * torch.randn(cout, generator=g)}
+    x = torch.randn(N, cin, H, H, generator=g)
+    tc = torch.randn(N, cmid, generator=g) * 0.5
+    d_out = torch.randn(N, cout, H, H, generator=g)
+    # reference: autograd through the oracle block (time embedding entering as the already-projected per-channel vector)
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr, tr = x.clone().requires_grad_(True), tc.clone().requires_grad_(True)
+    h = ounet._block(P, "b.block1", xr) + tr[:, :, None, None]
+    out_ref = ounet._block(P, "b.block2", h)
+    out_ref.backward(d_out)
+    blk = train.DoubleBlockGrad(sd["b.block1.conv.weight"], sd["b.block1.norm.weight"], sd["b.block1.norm.bias"],
+                                sd["b.block2.conv.weight"], sd["b.block2.norm.weight"], sd["b.block2.norm.bias"], segs, device=DEV)
+    ins, c0 = [], 0
+    for cs in segs:
+        ins.append(to_act(x[:, c0:c0 + cs, None].to(DEV), split=True))
+        c0 += cs
+    out = blk.forward(ins, tc)
+    assert rel_err(from_act(out, cout)[:, :, 0].cpu(), out_ref.detach()) <= 1e-3
+    gr = blk.backward(to_act(d_out[:, :, None].to(DEV), split=True))
+    want = {"conv1.weight": P["b.block1.conv.weight"].grad, "norm1.weight": P["b.block1.norm.weight"].grad, "norm1.bias": P["b.block1.norm.bias"].grad,
+            "conv2.weight": P["b.block2.conv.weight"].grad, "norm2.weight": P["b.block2.norm.weight"].grad, "norm2.bias": P["b.block2.norm.bias"].grad,
+            "temb": tr.grad}
+    for k, ref in want.items():
+        e = rel_l2(gr[k].cpu(), ref)
+        assert e <= 2e-3, (k, e)
+        assert e <= 2e-4, (k, e)   # the measured level of the fp32-class mode, an order inside the bound
+    c0 = 0
+    for cs, dx in zip(segs, gr["inputs"]):
+        if cs % 64 == 0:
+            e = rel_l2(from_act(dx, cs)[:, :, 0].cpu(), xr.grad[:, c0:c0 + cs])
+            assert e <= 2e-4, e
+        else:
+            assert dx is None
+        c0 += cs

@@ -53,3 +53,36 @@ def test_gloo_world2_shard_and_gather(B):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, B), nprocs=2, join=True)
+
+
+
+def _allreduce_worker(rank, world, port):
+    from diffusion_model_project_b200.train import FlatAdam
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1)
+        params = {"w": torch.randn(5, 3, generator=g), "b": torch.randn(7, generator=g)}
+        opt = FlatAdam(params, device="cpu")
+        for k in opt.names:
+            opt.view(opt.grad, k).fill_(float(rank + 1))
+        scale = opt.allreduce_gradients()
+        assert scale == 0.5
+        assert opt.offsets["w"][:2] == (0, 15) and opt.offsets["b"][:2] == (16, 7)               # 16-byte aligned segments
+        assert torch.equal(opt.grad[0:15], torch.full((15,), 3.0)) and opt.grad[15] == 0         # 1 + 2; padding untouched
+        assert torch.equal(opt.grad[16:23], torch.full((7,), 3.0))
+        assert torch.equal(opt.state_dict()["w"], params["w"])
+        with pytest.raises(RuntimeError):
+            opt.step(scale)                                                                      # the update kernel is GPU-only
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2():
+    """Training slice: every parameter's gradient lives in ONE flat buffer, summed over the ranks by one
+    collective; the update then applies 1 / world.  Host logic on CPU with gloo (the Adam kernel itself is GPU-only)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_allreduce_worker, args=(2, port), nprocs=2, join=True)
