@@ -81,13 +81,15 @@ def test_flat_adam_matches_torch_adam(wd, golden_dir):
     if wd == 0.0:
         gd = _golden(golden_dir)
         names = [k[len("grad::"):] for k in gd.files if k.startswith("grad::")]
-        zeros = {k: torch.zeros(gd[f"grad::{k}"].shape) for k in names}
-        o2 = train.FlatAdam(zeros, lr=1e-4, device=DEV)
+        usd = synth.synth_unet_state(seed=0)           # the parameters the reference started from
+        before = {k: usd[k].clone() for k in names}
+        o2 = train.FlatAdam(before, lr=1e-4, device=DEV)
         for k in names:
             o2.view(o2.grad, k).copy_(torch.from_numpy(gd[f"grad::{k}"]))
         o2.step()
         for k in names:
-            assert (o2.view(o2.param, k).cpu() - torch.from_numpy(gd[f"delta::{k}"])).abs().max().item() <= 2e-8
+            delta = o2.view(o2.param, k).cpu() - before[k]
+            assert (delta - torch.from_numpy(gd[f"delta::{k}"])).abs().max().item() <= 2e-8
 
 
 @pytest.mark.parametrize("split", [True, False])
