@@ -369,6 +369,21 @@ def run_b200(args):
                                               n_el, coef.data_ptr(), None, 500, 0, 1, -30.0, 30.0, None, 0, 0, 0, None, None, 0, s), 20)
     hbm_ach = 16.0 * n_el / (t_sched * 1e-3) / 1e9
     del xs, es, zs
+    # training slice: the flat Adam update over the UNet's 139.8 M parameters, 28 B / parameter
+    n_par = 139810952
+    bufs = [torch.zeros(n_par + 8, device=dev) for _ in range(4)]
+    bufs[1].normal_()
+    t_adam = time_launches(lambda: _lib.call("b2d_adam_step", bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(),
+                                             n_par, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, s), 10)
+    adam_ach = 28.0 * n_par / (t_adam * 1e-3) / 1e9
+    del bufs
+    # the UNet's tensor-core launches alone (3x3 convs, transposed convs, projections): per-launch CUDA events, eager
+    conv_us, conv_flops = 0.0, 0.0
+    for name, fn in ses["unet"]["program"].steps:
+        plan = getattr(fn, "__self__", None)
+        if plan is not None and hasattr(plan, "flops"):
+            conv_us += time_launches(lambda: plan.run(s), 5) * 1e3
+            conv_flops += plan.flops
     scale = (S / 11.0) * (H / 256.0) ** 2
     unet_slices = ses["N"]
 
@@ -425,7 +440,12 @@ def run_b200(args):
             "roofline_scheduler": {"bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm"],
                                    "bytes_per_launch": 16.0 * n_el, "ms_per_launch": t_sched,
                                    "note": "DDPM step with host noise, 16 B/element, 64 samples (369 MB > L2)"},
+            "roofline_adam": {"bound": "hbm", "achieved": adam_ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": adam_ach / peaks["hbm"],
+                              "bytes_per_launch": 28.0 * n_par, "ms_per_launch": t_adam,
+                              "note": "training slice: torch.optim.Adam update of the UNet's 139.8 M fp32 parameters, 28 B/parameter"},
             "stages": {"e2d_ms": t_e2d, "unet_step_ms": t_unet, "d3d_ms": t_d3d,
+                       "unet_conv_us_eager_sum": conv_us, "unet_conv_tflops": conv_flops / conv_us / 1e6 if conv_us else None,
+                       "unet_conv_frac_of_sustained_peak": conv_flops / conv_us / 1e6 / peaks["tc_sustained"] if conv_us else None,
                        "unet_step_note": f"replayed timestep graph, {unet_slices} slice-images per launch",
                        "conditioning_ms": t_cond, "loop_ms": t_loop, "decode_ms": t_dec, "sum_ms": stage_sum,
                        "sum_over_ms_per_step": stage_sum / ms_step,
