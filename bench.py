@@ -408,12 +408,21 @@ def run_b200(args):
                 for _ in range(args.ddim_steps):
                     g2.replay() if g2 is not None else pred._one_step(ses2, 1, ses2["coef"], (-30.0, 30.0), s)
             t_unet_s = (time_launches(loop2, 2) - time_launches(lambda: pred._set_latent(ses2, nz, s), 2)) / args.ddim_steps
+            cu2, cf2 = 0.0, 0.0
+            for name, fn in ses2["unet"]["program"].steps:
+                plan = getattr(fn, "__self__", None)
+                if plan is not None and hasattr(plan, "flops"):
+                    cu2 += time_launches(lambda: plan.run(s), 3) * 1e3
+                    cf2 += plan.flops
+            sm["conv_tflops"] = cf2 / cu2 / 1e6 if cu2 else None
         strong = {"scaling": "strong", "global_batch": Gs, "samples_per_gpu": sm["per_rank"], "value": sm["value"], "unit": "predictions/s",
                   "ms_per_step": sm["ms_per_step"], "e2e": {"value": sm["e2e_value"], "unit": "predictions/s", "ms_per_step": sm["e2e_ms_per_step"],
                                                            "h2d_bytes_per_step": sm["h2d_bytes"], "d2h_bytes_per_step": sm["d2h_bytes"]},
                   "unet_step_ms": t_unet_s, "unet_slices_per_launch": sm["per_rank"] * S,
                   "unet_tflops": sm["per_rank"] * FLOP_UNET_STEP * scale / (t_unet_s * 1e-3) / 1e12,
                   "unet_frac_of_sustained_peak": sm["per_rank"] * FLOP_UNET_STEP * scale / (t_unet_s * 1e-3) / 1e12 / peaks["tc_sustained"],
+                  "unet_conv_tflops": sm.get("conv_tflops"),
+                  "unet_conv_frac_of_sustained_peak": (sm["conv_tflops"] / peaks["tc_sustained"]) if sm.get("conv_tflops") else None,
                   "vae_chunk": args.vae_chunk}
 
     if rank == 0:

@@ -19,6 +19,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _autograd_on():
+    """Other test modules switch autograd off process-wide at import; the references here are torch.autograd results."""
+    with torch.enable_grad():
+        yield
+
+
 def _s():
     return torch.cuda.current_stream().cuda_stream
 
