@@ -27,27 +27,27 @@ use_stats = int(a[8]) if len(a) > 8 else 1
 D = 11 if kind == "3d" else 1
 dev = "cuda"
 g = torch.Generator().manual_seed(0)
-x = new_act(N, D, H, H, cin, dev)
-x.hi.copy_(torch.randn(N, D, H, H, cin, generator=g).to(torch.bfloat16))
+x = new_act(N, D, H, H, cin, dev, f16=True)   # IEEE fp16 operands: the default 16-bit mode
+x.hi.view(torch.float16).copy_(torch.randn(N, D, H, H, cin, generator=g).to(torch.float16))
 if kind == "3d":
     w = torch.randn(cout, cin, 3, 3, 3, generator=g) * (27 * cin) ** -0.5
-    pw = engine.pack_conv3d(w, torch.zeros(cout), dev)
+    pw = engine.pack_conv3d(w, torch.zeros(cout), dev, f16=True)
     groups = 32
 elif kind == "convT":  # ConvTranspose2d k2 s2 (UNet Up): 4 phase GEMMs, bias, GroupNorm(1, C) sums
     w = torch.randn(cin, cout, 2, 2, generator=g) * cin ** -0.5
-    pw = engine.pack_convT2x2(w, torch.zeros(cout), dev)
+    pw = engine.pack_convT2x2(w, torch.zeros(cout), dev, f16=True)
     groups = 1
 elif kind == "1x1":  # attention projections (UNet in_proj / out_proj): bias, no GroupNorm sums
     w = torch.randn(cout, cin, generator=g) * cin ** -0.5
-    pw = engine.pack_linear(w, torch.zeros(cout), dev)
+    pw = engine.pack_linear(w, torch.zeros(cout), dev, f16=True)
     groups = 1
     use_stats = 0
 else:
     w = torch.randn(cout, cin, 3, 3, generator=g) * (9 * cin) ** -0.5
-    pw = engine.pack_conv2d(w, [cin], None, dev)
+    pw = engine.pack_conv2d(w, [cin], None, dev, f16=True)
     groups = 1
 up = 2 if kind == "convT" else 1
-out = new_act(N, D, H * up, H * up, cout, dev, f16=(kind == "convT"))
+out = new_act(N, D, H * up, H * up, cout, dev, f16=True)
 st = torch.zeros(N, groups, 2, dtype=torch.float64, device=dev)
 plan = ConvPlan([x], pw, out, cout=cout, nphase=4 if kind == "convT" else 1, stats=st if use_stats else None,
                 stats_cpg=cout // groups if use_stats else 0, block_n=bn, tune_flags=flags)
