@@ -106,8 +106,9 @@ class B200LatentDiffusionPredictor:
         self._session = None
         dev, sp = self.device, self.split
         lat = self.latent_channels
-        if H % 128 or W % 128:
-            raise ValueError(f"in-plane size {H}x{W} must be a multiple of 128 (latent /4, five UNet poolings)")
+        mult = 4 << len(self.model.features)
+        if H % mult or W % mult:
+            raise ValueError(f"in-plane size {H}x{W} must be a multiple of {mult} (latent /4, {len(self.model.features)} UNet poolings)")
         h, w = H // 4, W // 4
         N = B * S
         # micro-batching: the VAE passes run over `chunk` samples at a time against ONE set of activation buffers

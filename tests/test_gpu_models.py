@@ -277,6 +277,32 @@ def test_two_sampling_loops_on_two_streams(unet_sd, vae_sd):
             assert torch.equal(got[k][0], serial[k][0]) and torch.equal(got[k][1], serial[k][1])
 
 
+def test_from_reference_and_from_directory(tmp_path):
+    """The constructors a reference user calls: `from_reference` on an object with the reference
+    predictor's attributes, and `from_directory` on the reference's checkpoint layout (predictor.py:222-250, 476-566), give
+    the predictor that direct construction from the same state dicts gives."""
+    import types
+    from test_checkpoint import SMALL, _write_dirs
+    run, usd, vsd = _write_dirs(tmp_path, SMALL)
+    kw = dict(precision="f16", device="cuda")
+    direct = B200LatentDiffusionPredictor("UNet", dict(SMALL), True, unet_state=usd, vae_state=vsd, norm_factors=synth.NORM_FACTORS,
+                                          num_slices=11, num_timesteps=1000, **kw)
+    from_dir = B200LatentDiffusionPredictor.from_directory(str(run), **kw)
+    model = types.SimpleNamespace(in_channels=17, out_channels=8, features=[64, 128], kernel_size=3, padding_mode="zeros",
+                                  _activation="silu", _final_activation=None, attention="2..2", dropout=0.0, time_embedding_dim=64,
+                                  state_dict=lambda: usd)
+    ref_like = types.SimpleNamespace(model=model, vae=types.SimpleNamespace(state_dict=lambda: vsd), vae_is_dual=True,
+                                     distance_transform=torch.nn.Parameter(torch.tensor([1.0]), requires_grad=False),
+                                     normalizer={"output": types.SimpleNamespace(scale_factors=torch.tensor(synth.NORM_FACTORS))},
+                                     num_slices=11, num_timesteps=1000)
+    from_ref = B200LatentDiffusionPredictor.from_reference(ref_like, **kw)
+    img, v2d = synth.synth_inputs(1, num_slices=3, size=32, seed=4)
+    noise = synth.synth_noise(1, num_slices=3, latent_size=8, seed=5)
+    outs = [p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=3, noise=noise.cuda()).cpu() for p in (direct, from_dir, from_ref)]
+    assert torch.isfinite(outs[0]).all() and outs[0].abs().max() > 0
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 def test_broadcast_mask_and_input_validation(unet_sd, vae_sd):
     img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=14)
     img[:, 1] = img[:, 0]
