@@ -64,7 +64,7 @@ class ConvDesc(C.Structure):
     ]
 
 
-TUNE_NO_HALO, TUNE_NO_SPLITK, TUNE_CONTIG, TUNE_STRIDED, TUNE_STREAMK, TUNE_NO_STREAMK = 1, 2, 4, 8, 16, 32
+TUNE_NO_HALO, TUNE_NO_SPLITK, TUNE_CONTIG, TUNE_STRIDED, TUNE_STREAMK, TUNE_NO_STREAMK, TUNE_PAIR, TUNE_NO_PAIR = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 _SIGNATURES = {

@@ -94,6 +94,8 @@ struct ConvKParams {
   // tiles * ksteps steps is cut into gridDim.x equal contiguous ranges, one per CTA (tile boundaries inside a range
   // are whole tiles; a tile cut by a range boundary is reduced through the workspace by whichever piece arrives last)
   int spg, ksteps, streamk, total_steps;
+  int pair;          // 1: launched as clusters of two CTAs on 256-row M super-tiles (tcgen05 cta_group::2); the unit walk
+                     // then runs over PAIR tiles and num_units counts pair units
   FastDiv fd_ksteps, fd_total;
   // ---- fused input normalisation (halo mode): A tiles are raw pre-GroupNorm values; dedicated warps rewrite each
   // staged tile in shared memory as bf16 silu(gamma * (x - mean) * rstd + beta) before the MMAs read it ----

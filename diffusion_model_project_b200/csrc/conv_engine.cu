@@ -32,6 +32,34 @@ __global__ void __launch_bounds__(V2Cfg<BN, HALO, XFORM>::THREADS, 1) conv_v2_ke
   conv_v2_layer<BN, HALO, XFORM>(p, smem);
 }
 
+// CTA-pair variant (tcgen05 cta_group::2): launched as clusters of two, generic staging
+template <int BN>
+__global__ void __launch_bounds__(V2Cfg<BN, false, false, true>::THREADS, 1) conv_pair_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw3[];
+  // both CTAs of a pair must lay their stages out at the same shared-memory offsets: the dynamic segment starts at the
+  // same offset in every CTA of a kernel, so the same rounding gives the same offsets
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw3) + 1023) & ~uintptr_t(1023));
+  conv_v2_layer<BN, false, false, true>(p, smem);
+}
+
+template <int BN>
+static int launch_pair(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
+  using Cfg = V2Cfg<BN, false, false, true>;
+  static unsigned long long configured = 0;
+  cudaError_t e = smem_attr_once(conv_pair_kernel<BN>, Cfg::SMEM, configured);
+  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "cudaFuncSetAttribute(pair, smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = (size_t)Cfg::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<BN>, kp);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "conv_pair launch: %s", cudaGetErrorString(e));
+  return B2D_OK;
+}
+
 template <int BN, bool HALO, bool XFORM = false>
 static int launch_v2(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
   using Cfg = V2Cfg<BN, HALO, XFORM>;
@@ -46,6 +74,13 @@ static int launch_v2(const ConvKParams& kp, dim3 grid, cudaStream_t st) {
 
 int launch_conv_v2(const b2d_conv_plan* plan, cudaStream_t st) {
   const ConvKParams& kp = plan->kp;
+  if (kp.pair) {
+    switch (plan->block_n) {
+      case 128: return launch_pair<128>(kp, plan->grid, st);
+      case 256: return launch_pair<256>(kp, plan->grid, st);
+    }
+    return set_error(B2D_E_INVALID, "conv pair: bad block_n %d", plan->block_n);
+  }
   if (kp.halo && kp.xform) {
     switch (plan->block_n) {
       case 16: return launch_v2<16, true, true>(kp, plan->grid, st);

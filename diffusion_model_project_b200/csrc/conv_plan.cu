@@ -100,7 +100,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   // cost = waves over the SMs x (K-loop time of one unit + epilogue / split-K fix-up), in SM clocks.
   int bn = d->block_n;
   int ksplit_pick = 1;
-  bool streamk_pick = false;
+  bool streamk_pick = false, pair_pick = false;
   {
     const int sms = num_sms();
     const long long cols = (long long)d->cout * d->nphase;
@@ -116,6 +116,9 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     double best = 1e30, best_sk = 1e30;
     int best_bn = 0, best_sk_bn = 0;
     const bool sk_off = (d->tune_flags & B2D_TUNE_NO_STREAMK) != 0, sk_force = (d->tune_flags & B2D_TUNE_STREAMK) != 0;
+    const bool pair_off = (d->tune_flags & B2D_TUNE_NO_PAIR) != 0, pair_force = (d->tune_flags & B2D_TUNE_PAIR) != 0;
+    double best_pair = 1e30;
+    int best_pair_bn = 0, best_pair_ks = 1;
     for (int ci = 0; ci < 4; ++ci) {
       const int b = cand[ci];
       if (d->block_n && d->block_n != b) continue;
@@ -144,6 +147,27 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
         const double cost = waves * unit;
         if (cost < best * 0.999) { best = cost; best_bn = b; ksplit_pick = ks; streamk_pick = false; }
       }
+      // CTA pairs (tcgen05 cta_group::2, generic staging): 256-row M super-tiles, each SM stages its 128 A rows and HALF of
+      // the weight rows -- (128 + b / 2) x 128 B per K block instead of (128 + b) x 128 B through the 40 B/clk L2 port
+      if (!halo && !pair_off && (b == 256 || b == 128) && d->nphase == 1 && !d->in_stats && tiles_m2 >= 2) {
+        const long long pairs_m = (tiles_m2 + 1) / 2, ptiles = pairs_m * (cols / b);
+        double pg = t_kb;
+        const double pbytes = (128.0 + b / 2) * 128.0;
+        if (pg < pbytes / kL2BytesPerClk) pg = pbytes / kL2BytesPerClk;
+        const int clusters = sms / 2;
+        for (int ks = 1; ks <= 16; ++ks) {
+          if (force_ks > 0 && ks < force_ks) continue;
+          if (force_ks > 0 && ks > force_ks) break;
+          if (2 * ptiles * 2 > 4096) break;  // arrival counters: one per (tile, column group)
+          if (ks > 1 && (!can_split || ngroups / ks < 4 || ptiles >= 2LL * clusters ||
+                         16384 + 2 * ptiles * ks * 128LL * b * 4 > d->workspace_bytes)) break;
+          const double fix = ks > 1 ? 6000.0 + (1.0 + ks) * 12.0 * b : 0.0;
+          const double unit = (double)((ngroups + ks - 1) / ks) * pg + 2500.0 + 8.0 * b + fix;  // + the cluster handshakes
+          const double waves = (double)((ptiles * ks + clusters - 1) / clusters);
+          const double cost = waves * unit;
+          if (cost < best_pair) { best_pair = cost; best_pair_bn = b; best_pair_ks = ks; }
+        }
+      }
       // stream-K: every CTA runs the same number of B-stage steps of the flat (tile, step) space; tiles cut by a range
       // boundary go through the workspace (at most two partial tiles parked per CTA)
       if (can_split && !sk_off && force_ks == 0) {
@@ -168,6 +192,9 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     // to amortise that, 3-way split-K fills the machine just as well
     if (best_sk_bn != 0 && (sk_force || best_bn == 0)) {
       best = best_sk; best_bn = best_sk_bn; ksplit_pick = 1; streamk_pick = true;
+    }
+    if (best_pair_bn != 0 && !streamk_pick && (pair_force || best_pair < best * 0.92)) {
+      best = best_pair; best_bn = best_pair_bn; ksplit_pick = best_pair_ks; pair_pick = true;
     }
     if (best_bn == 0)
       return set_error(B2D_E_INVALID, "cout=%d block_n=%d%s: need cout a multiple of 64 (or <= 16)", d->cout, d->block_n,
@@ -340,15 +367,26 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     k.fd_ksteps.set((uint32_t)k.ksteps);
     k.fd_total.set((uint32_t)(streamk_pick ? k.total_steps : 1));
     k.num_units = (int)(tiles * ksplit);
+    k.pair = pair_pick ? 1 : 0;
+    long long ws_tiles = tiles;
+    if (pair_pick) {
+      // the walk runs over pair tiles; rank r of a cluster takes M tile 2 * pair + r (an odd last tile is all padding:
+      // TMA zero fill, rows masked in the epilogue).  Workspace / counters are indexed by the padded M tile count.
+      const long long tiles_m = (long long)k.tiles_w * k.tiles_h * k.tiles_d * k.tiles_n;
+      const long long pairs_m = (tiles_m + 1) / 2;
+      k.num_units = (int)(pairs_m * k.tiles_ncol * ksplit);
+      ws_tiles = 2 * pairs_m * k.tiles_ncol;
+    }
     k.fd_ksplit.set((uint32_t)ksplit); k.fd_ncol.set((uint32_t)k.tiles_ncol);
     k.fd_w.set((uint32_t)k.tiles_w); k.fd_h.set((uint32_t)k.tiles_h); k.fd_d.set((uint32_t)k.tiles_d);
     if ((long long)k.ngroups * (ksplit + 1) >= (1LL << 31)) { delete pl; return set_error(B2D_E_INVALID, "K loop too long"); }
     if (ksplit > 1) {
       k.counters = reinterpret_cast<int*>(d->workspace);
       k.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->workspace) + kCounterBytes);
-      pl->ws_bytes = kCounterBytes + tiles * ksplit * mt * 128LL * bn * 4;
+      pl->ws_bytes = kCounterBytes + ws_tiles * ksplit * mt * 128LL * bn * 4;
     }
     pl->grid = dim3((unsigned)(k.num_units < sms ? k.num_units : sms), 1, 1);
+    if (pair_pick) pl->grid = dim3(2u * (unsigned)(k.num_units < sms / 2 ? k.num_units : sms / 2), 1, 1);
     if (streamk_pick) {
       pl->grid = dim3((unsigned)(k.total_steps < sms ? k.total_steps : sms), 1, 1);
       k.counters = reinterpret_cast<int*>(d->workspace);
@@ -360,6 +398,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     const int env_contig = (d->tune_flags & B2D_TUNE_CONTIG) ? 1 : (d->tune_flags & B2D_TUNE_STRIDED) ? 0 : -1;
     const long long units_per_n = k.tiles_n > 0 ? k.num_units / k.tiles_n : k.num_units;
     k.contig = env_contig >= 0 ? env_contig : (units_per_n < (long long)pl->grid.x && k.num_units > (int)pl->grid.x) ? 1 : 0;
+    if (pair_pick) k.contig = 0;
   }
   *out_plan = pl;
   return B2D_OK;
@@ -387,7 +426,7 @@ extern "C" int b2d_conv_run(const b2d_conv_plan* plan, void* stream) {
 
 extern "C" int b2d_conv_plan_info2(const b2d_conv_plan* plan, int32_t* out8) {
   if (!plan || !out8) return set_error(B2D_E_INVALID, "null argument");
-  out8[0] = 2;  // engine generation (the one-tile-per-CTA first engine was retired in ABI 6)
+  out8[0] = plan->kp.pair ? 3 : 2;  // 2: one CTA per tile; 3: tcgen05 cta_group::2 CTA pairs on 256-row super-tiles
   out8[1] = plan->kp.halo;
   out8[2] = plan->kp.streamk ? -1 : plan->kp.ksplit;  // -1: stream-K
   out8[3] = plan->kp.num_units;

@@ -6,18 +6,24 @@
 
 namespace b2d {
 
-template <int BN, bool HALO, bool XFORM = false>
+// PAIR: two CTAs of a cluster form a tcgen05 cta_group::2 pair on a 256-row M super-tile (generic staging only): each
+// stages its own 128 A rows and HALF of the N tile's weight rows, the pair's even CTA issues M = 256 MMAs that read both
+// halves, each CTA's TMEM receives its own 128 x BN accumulator.  Per SM the operand bytes pulled from L2 per K block
+// drop from (128 + BN) x 128 B to (128 + BN / 2) x 128 B -- the bound of the small-map UNet layers (conv_plan.cu).
+template <int BN, bool HALO, bool XFORM = false, bool PAIR = false>
 struct V2Cfg {
   static_assert(HALO || !XFORM, "input transform needs halo staging");
+  static_assert(!PAIR || (!HALO && !XFORM && BN >= 128), "CTA pairs: generic staging, 128- or 256-wide N tiles");
   static constexpr int MT = HALO ? 2 : 1;                       // M = 128 halves per unit
   static constexpr int A_TILE = HALO ? 18 * 18 * 128 : kABytes;  // bytes landed per A load
   static constexpr int A_STAGE = (A_TILE + 1023) / 1024 * 1024;
   // weight taps per B stage: narrow N tiles batch several taps behind one mbarrier so the single
   // MMA-issuing thread is not handshake-bound (an N = 16 MMA lasts ~32 clocks)
   static constexpr int TPB = HALO ? (BN <= 16 ? 9 : BN <= 64 ? 3 : 1) : 1;
-  static constexpr int B_TILE = BN * kBlockK * 2;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;              // weight rows this CTA stages
+  static constexpr int B_TILE = B_ROWS * kBlockK * 2;
   static constexpr int B_STAGE = TPB * B_TILE;
-  static constexpr int NA = HALO ? ((BN >= 128 || XFORM) ? 2 : 3) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
+  static constexpr int NA = HALO ? ((BN >= 128 || XFORM) ? 2 : 3) : PAIR ? (BN == 256 ? 5 : 8) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
   static constexpr int NB = HALO ? (BN == 256 ? 4 : BN == 128 ? 6 : BN == 64 ? 4 : 3) : NA;
   static constexpr int BNC = BN < 32 ? 32 : BN;                  // TMEM columns of one M half
   static constexpr int ACC_COLS = MT * BNC;                      // one accumulator stage
@@ -44,10 +50,38 @@ struct V2Cfg {
 
 // One planned convolution executed by the whole CTA (`p` lives in the kernel's parameter space: its TMA descriptors are
 // addressed in place).
-template <int BN, bool HALO, bool XFORM>
+// the work items of this CTA: the unit / stream-K walk of conv_work.cuh; in PAIR mode the walk runs over PAIR tiles
+// (clusters instead of CTAs) and rank r takes M tile 2 * pair + r of the item
+template <bool PAIR>
+struct CtaWalk {
+  WorkIter wi;
+  int rank;
+  __device__ __forceinline__ void init(const ConvKParams& p) {
+    if constexpr (PAIR) {
+      rank = (int)cluster_ctarank();
+      wi.init(p, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1));
+    } else {
+      rank = 0;
+      wi.init(p, (int)blockIdx.x, (int)gridDim.x);
+    }
+  }
+  __device__ __forceinline__ bool next(const ConvKParams& p, UnitCoord& uc) {
+    if (!wi.next(p, uc)) return false;
+    if constexpr (PAIR) {
+      const int ncol = p.tiles_ncol;
+      const int pm = (uc.tile - uc.gcol0) / ncol;  // pair index along M (uc.tile = pm * ncol + n_tile)
+      const int ks = uc.ks, k_lo = uc.k_lo, k_hi = uc.k_hi;
+      decode_tile(p, (2 * pm + rank) * ncol + uc.gcol0, uc);
+      uc.ks = ks; uc.k_lo = k_lo; uc.k_hi = k_hi;
+    }
+    return true;
+  }
+};
+
+template <int BN, bool HALO, bool XFORM, bool PAIR = false>
 __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* smem) {
   const ConvKParams& tm = p;
-  using Cfg = V2Cfg<BN, HALO, XFORM>;
+  using Cfg = V2Cfg<BN, HALO, XFORM, PAIR>;
   constexpr int MT = Cfg::MT, NA = Cfg::NA, NB = Cfg::NB;
   constexpr int CW = BN < 32 ? 16 : 32;
 
@@ -70,12 +104,15 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
   // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int cta = (int)blockIdx.x, ncta = (int)gridDim.x;
+  // piece bookkeeping of shared tiles (split-K / stream-K) is per CTA of the plain grid, per cluster in PAIR mode
+  const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncta = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool leader = !PAIR || cluster_ctarank() == 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], XFORM ? Cfg::XF_WARPS : 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], Cfg::EPI_WARPS); }
+    // PAIR: the leader's MMA warp waits for the epilogue warps of BOTH CTAs before it reuses an accumulator stage
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], (PAIR ? 2 : 1) * Cfg::EPI_WARPS); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 64 * Cfg::EPI_WARPS; i += blockDim.x) sm_stats[i] = 0.0;
@@ -84,11 +121,12 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     prefetch_tmap(&tm.tmapB);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -98,9 +136,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     int ast = 0, bst = 0;
     uint32_t aph = 0, bph = 0;
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-    WorkIter wi;
+    CtaWalk<PAIR> wi;
     UnitCoord uc;
-    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
+    for (wi.init(p); wi.next(p, uc);) {
       const int gcol0 = uc.gcol0 * BN;
       GroupIter it;
       for (it.init(p, uc.k_lo, uc.k_hi); !it.done(); it.next(p)) {
@@ -126,10 +164,21 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
           mbar_wait(&a_empty[ast], aph ^ 1);
           mbar_wait(&b_empty[bst], bph ^ 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx(&a_full[ast], Cfg::A_TILE);
-            tma_load_5d_u(sA_u + ast * Cfg::A_STAGE, &tm.tmapA[s], smem_u32(&a_full[ast]), it.c * kBlockK, xx, yy, zz, uc.n0);
-            mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
-            tma_load_2d_u(sB_u + bst * Cfg::B_STAGE, &tm.tmapB, smem_u32(&b_full[bst]), p.kbase[s] + tp * p.cin[s] + it.c * kBlockK, gcol0);
+            if constexpr (PAIR) {
+              // both CTAs' bytes complete on the LEADER's barriers; only the leader posts the expectation (for both)
+              if (leader) {
+                mbar_arrive_expect_tx(&a_full[ast], 2 * Cfg::A_TILE);
+                mbar_arrive_expect_tx(&b_full[bst], 2 * Cfg::B_STAGE);
+              }
+              tma_load_5d_pair(sA_u + ast * Cfg::A_STAGE, &tm.tmapA[s], smem_u32(&a_full[ast]), it.c * kBlockK, xx, yy, zz, uc.n0);
+              tma_load_2d_pair(sB_u + bst * Cfg::B_STAGE, &tm.tmapB, smem_u32(&b_full[bst]), p.kbase[s] + tp * p.cin[s] + it.c * kBlockK,
+                               gcol0 + wi.rank * Cfg::B_ROWS);
+            } else {
+              mbar_arrive_expect_tx(&a_full[ast], Cfg::A_TILE);
+              tma_load_5d_u(sA_u + ast * Cfg::A_STAGE, &tm.tmapA[s], smem_u32(&a_full[ast]), it.c * kBlockK, xx, yy, zz, uc.n0);
+              mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
+              tma_load_2d_u(sB_u + bst * Cfg::B_STAGE, &tm.tmapB, smem_u32(&b_full[bst]), p.kbase[s] + tp * p.cin[s] + it.c * kBlockK, gcol0);
+            }
           }
           __syncwarp();
           if (++ast == NA) { ast = 0; aph ^= 1; }
@@ -142,9 +191,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     int bst = 0;
     uint32_t bph = 0;
     const uint32_t sB_u = smem_u32(sB);
-    WorkIter wi;
+    CtaWalk<PAIR> wi;
     UnitCoord uc;
-    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
+    for (wi.init(p); wi.next(p, uc);) {
       const int gcol0 = uc.gcol0 * BN;
       GroupIter it;
       for (it.init(p, uc.k_lo, uc.k_hi); !it.done(); it.next(p)) {
@@ -167,19 +216,20 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ===========================================
+    // ================================ MMA issuer (PAIR: the leader CTA's only) ==============
+    if (leader) {
     // Uniform loop; descriptors are 64-bit constants whose low word (start address >> 4) is the only
     // thing that moves, so the per-MMA work is one 32-bit uniform add.
-    const uint32_t idesc = umma_idesc_16(kBlockM, BN, p.op_f16);
+    const uint32_t idesc = umma_idesc_16(PAIR ? 2 * kBlockM : kBlockM, BN, p.op_f16);
     const uint64_t adesc0 = umma_smem_desc(smem_u32(sA), HALO ? 18 * 128 : 1024, 2);
     const uint64_t bdesc0 = umma_smem_desc(smem_u32(sB), 1024, 2);
     const uint32_t adesc_hi = (uint32_t)(adesc0 >> 32), bdesc_hi = (uint32_t)(bdesc0 >> 32);
     const uint32_t adesc_lo0 = (uint32_t)adesc0, bdesc_lo0 = (uint32_t)bdesc0;
     int ast = 0, bst = 0, acc = 0;
     uint32_t aph = 0, bph = 0, accph = 0;
-    WorkIter wi;
+    CtaWalk<PAIR> wi;
     UnitCoord uc;
-    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
+    for (wi.init(p); wi.next(p, uc);) {
       mbar_wait(&t_empty[acc], accph ^ 1);  // the epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
@@ -214,23 +264,25 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
                 for (int k = 0; k < kBlockK / 16; ++k) {
                   const uint64_t ad = ((uint64_t)adesc_hi << 32) | (a_tap + (uint32_t)(mt * 64 + 2 * k));
                   const uint64_t bd = ((uint64_t)bdesc_hi << 32) | (b_lo + (uint32_t)(j * (Cfg::B_TILE >> 4) + 2 * k));
-                  umma_bf16(d_tmem + mt * Cfg::BNC, ad, bd, idesc, (accum | (uint32_t)(j > 0)) | (uint32_t)(k > 0));
+                  if constexpr (PAIR) umma_f16_pair(d_tmem + mt * Cfg::BNC, ad, bd, idesc, (accum | (uint32_t)(j > 0)) | (uint32_t)(k > 0));
+                  else umma_bf16(d_tmem + mt * Cfg::BNC, ad, bd, idesc, (accum | (uint32_t)(j > 0)) | (uint32_t)(k > 0));
                 }
               }
             }
-            umma_commit(&b_empty[bst]);
+            if constexpr (PAIR) umma_commit_pair(&b_empty[bst]); else umma_commit(&b_empty[bst]);
           }
           __syncwarp();
           accum = 1;
           if (++bst == NB) { bst = 0; bph ^= 1; }
         }
-        if (elect_one()) umma_commit(&a_empty[ast]);
+        if (elect_one()) { if constexpr (PAIR) umma_commit_pair(&a_empty[ast]); else umma_commit(&a_empty[ast]); }
         __syncwarp();
         if (++ast == NA) { ast = 0; aph ^= 1; }
       }
-      if (elect_one()) umma_commit(&t_full[acc]);
+      if (elect_one()) { if constexpr (PAIR) umma_commit_pair(&t_full[acc]); else umma_commit(&t_full[acc]); }
       __syncwarp();
       if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
+    }
     }
   } else if (warp < 2 + Cfg::EPI_WARPS) {
     // ================================ epilogue ==============================================
@@ -299,9 +351,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     if constexpr (BN == 16) {
       if (p.out_mode == 3) { sched_ctx = sched_ctx_load(p); sched = &sched_ctx; }
     }
-    WorkIter wi;
+    CtaWalk<PAIR> wi;
     UnitCoord uc;
-    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
+    for (wi.init(p); wi.next(p, uc);) {
       if constexpr (SMEM_STATS) {
         if (uc.n0 != cur_n) { flush_stats(); cur_n = uc.n0; }
       }
@@ -361,7 +413,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         conv_epilogue_row<BNG, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_tmem, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u, sched);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[acc]);
+        if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(&t_empty[acc], 0); else mbar_arrive(&t_empty[acc]); }
       } else {
         // ---- the tile's K loop is shared (split-K / stream-K): park the fp32 partial, the last piece to arrive reduces
         // all of them in piece order (deterministic) ----
@@ -377,7 +429,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[acc]);
+        if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(&t_empty[acc], 0); else mbar_arrive(&t_empty[acc]); }
         __threadfence();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         if ((threadIdx.x & 127) == 64) {  // first thread of this four-warp group (warps 2.. start at thread 64)
@@ -429,9 +481,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     const int op_f16 = p.op_f16;
     int ast = 0, cur_n = -1;
     uint32_t aph = 0;
-    WorkIter wi;
+    CtaWalk<PAIR> wi;
     UnitCoord uc;
-    for (wi.init(p, cta, ncta); wi.next(p, uc);) {
+    for (wi.init(p); wi.next(p, uc);) {
       if (uc.n0 != cur_n) {
         // per-channel scale / shift of this sample from the producer's fp64 (sum, sumsq)
         asm volatile("bar.sync 4, 128;" ::: "memory");  // everyone is done with the previous table
@@ -524,9 +576,10 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // no remote arrival or MMA operand read may target a CTA that has exited
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   if constexpr (BN == 16) {
     // fused sampler update: the last CTA to finish advances the device step counter (every CTA has read it by then)

@@ -171,6 +171,8 @@ typedef struct b2d_conv_desc {
 #define B2D_TUNE_STRIDED 8    /* CTAs walk the unit list strided over the grid   */
 #define B2D_TUNE_STREAMK 16   /* stream-K wherever it applies                    */
 #define B2D_TUNE_NO_STREAMK 32 /* never stream-K                                  */
+#define B2D_TUNE_PAIR 64      /* CTA pairs (cta_group::2) wherever they apply    */
+#define B2D_TUNE_NO_PAIR 128  /* never CTA pairs                                 */
 
 typedef struct b2d_conv_plan b2d_conv_plan;
 B2D_API int b2d_conv_plan_create(const b2d_conv_desc* desc, b2d_conv_plan** plan);
@@ -178,7 +180,7 @@ B2D_API int b2d_conv_plan_destroy(b2d_conv_plan* plan);
 B2D_API int b2d_conv_run(const b2d_conv_plan* plan, void* stream);
 /* number of CTAs / block_n the plan launches with (introspection for tests and the bench) */
 B2D_API int b2d_conv_plan_info(const b2d_conv_plan* plan, int32_t* grid_m, int32_t* grid_n, int32_t* block_n, int32_t* kblocks);
-/* out[8] = {engine generation (2), halo, ksplit (-1: stream-K), work units, CTAs launched, block_n, K-loop groups, workspace bytes used (KiB)} */
+/* out[8] = {2 (one CTA per tile) or 3 (tcgen05 cta_group::2 CTA pairs), halo, ksplit (-1: stream-K), work units, CTAs launched, block_n, K-loop groups, workspace bytes used (KiB)} */
 B2D_API int b2d_conv_plan_info2(const b2d_conv_plan* plan, int32_t* out8);
 
 /* ------------------------------------------------------------------------------------------

@@ -347,6 +347,51 @@ def test_stream_k_matches_unit_walk(N, ci, co, H, W, f16):
     assert ((res["streamk"][1] - res["unit"][1]).abs().max() / res["unit"][1].abs().max()).item() < 5e-5  # sums of fp16-rounded values
 
 
+@pytest.mark.parametrize("kind,N,ci,co,H,W", [("3x3", 88, 512, 512, 8, 8), ("3x3", 88, 1024, 1024, 4, 4), ("3x3", 88, 2048, 2048, 2, 2),
+                                              ("3x3", 24, 512, 256, 4, 4), ("3x3", 5, 256, 512, 8, 8), ("1x1", 88, 256, 768, 16, 16),
+                                              ("1x1", 11, 1024, 1024, 4, 4)])
+def test_cta_pairs_match_single_cta_tiles(kind, N, ci, co, H, W):
+    """tcgen05 cta_group::2 (B2D_TUNE_PAIR: clusters of two CTAs on 256-row M super-tiles, each staging half of the weight
+    rows) against the one-CTA-per-tile plan of the same layer: deep UNet level shapes at 88 slice-images with and without
+    split-K, an odd number of M tiles (the pair's second tile is all padding), bias + residual, GroupNorm sums.  Repeated
+    launches are bit-identical."""
+    no_tf32()
+    g = torch.Generator().manual_seed(ci + co + H + N)
+    x = f16_round(_rnd(g, N, ci, 1, H, W))
+    if kind == "3x3":
+        w = f16_round(_rnd(g, co, ci, 3, 3, scale=(9 * ci) ** -0.5))
+        pw = engine.pack_conv2d(w, [ci], None, DEV, f16=True)
+        ref = F.conv2d(x[:, :, 0], w, None, padding=1)[:, :, None]
+        resid = None
+    else:
+        w = f16_round(_rnd(g, co, ci, scale=ci ** -0.5))
+        b = _rnd(g, co)
+        pw = engine.pack_linear(w, b, DEV, f16=True)
+        resid = f16_round(_rnd(g, N, co, 1, H, W))
+        ref = F.conv2d(x[:, :, 0], w[:, :, None, None], b)[:, :, None] + resid
+    xa = to_act(x, f16=True)
+    res = {}
+    for name, flags in (("single", _lib.TUNE_NO_PAIR), ("pair", _lib.TUNE_PAIR)):
+        out = new_act(N, 1, H, W, co, DEV, f16=True)
+        st = torch.zeros(N, 2, dtype=torch.float64, device=DEV)
+        ws = engine.new_workspace(DEV)
+        plan = ConvPlan([xa], pw, out, cout=co, stats=st, stats_cpg=co, workspace=ws, tune_flags=flags,
+                        residual=None if resid is None else to_act(resid, f16=True))
+        info = plan.info2()
+        assert info["engine"] == (3 if name == "pair" else 2), info
+        plan.run(_stream())
+        first, st_first = out.hi.clone(), st.clone()
+        for _ in range(2):
+            out.hi.zero_(); st.zero_()
+            plan.run(_stream())
+            assert torch.equal(out.hi, first)
+        assert int(ws[:16384].view(torch.int32).abs().sum()) == 0
+        res[name] = (from_act(out, co), st_first)
+    assert rel_err(res["pair"][0], ref) < 1.5e-3
+    assert rel_err(res["pair"][0], res["single"][0]) < 1.5e-3
+    assert ((res["pair"][1] - res["single"][1]).abs().max() / res["single"][1].abs().max()).item() < 5e-5
+
+
 def test_split_k_is_deterministic_and_reuses_workspace():
     """Deep UNet level shape (M = 7*4 rows, K = 9*2048): the plan splits K, partials go through the shared workspace,
     the last arriver reduces in a fixed order -> repeated launches are bit-identical and the counters self-reset."""

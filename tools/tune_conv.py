@@ -81,8 +81,17 @@ for kind, cins, cout, H in shapes:
         i2 = p.info2()
         if i2["block_n"] == bn and i2["ksplit"] == -1:
             rows.append((timed(p), bn, -1, i2["units"]))
-    rows.sort()
+    for bn in (128, 256):  # tcgen05 cta_group::2 CTA pairs, with the planner's own K split and with forced ones
+        for ks in (0, 1, 2, 3, 4, 6):
+            try:
+                p = ConvPlan(xs, pw, out, block_n=bn, tune_ksplit=ks, tune_flags=64 | 32, **kw)
+            except (B2DError, ValueError, RuntimeError):
+                continue
+            i2 = p.info2()
+            if i2["block_n"] == bn and i2["engine"] == 3 and (ks == 0 or i2["ksplit"] == ks):
+                rows.append((timed(p), bn, 100 + i2["ksplit"], i2["units"]))
+    rows = sorted(set(rows))
     best = rows[0] if rows else (float("nan"), 0, 0, 0)
     print(f"{kind:5s} {'+'.join(map(str, cins)):>9s}->{cout:<4d} @{H:<2d}  auto bn{info['block_n']} ks{info['ksplit']} halo{info['halo']} "
-          f"{t_auto:6.1f} us | best bn{best[1]} ks{best[2]} ({best[3]} units) {best[0]:6.1f} us | "
-          + "  ".join(f"bn{b}/{'sk' if k < 0 else 'ks' + str(k)}:{t:.1f}" for t, b, k, _ in rows[:8]), flush=True)
+          f"{t_auto:6.1f} us{' PAIR' if info['engine'] == 3 else ''} | best bn{best[1]} ks{best[2]} ({best[3]} units) {best[0]:6.1f} us | "
+          + "  ".join(f"bn{b}/{'sk' if k < 0 else ('pair-ks' + str(k - 100)) if k >= 100 else 'ks' + str(k)}:{t:.1f}" for t, b, k, _ in rows[:8]), flush=True)
