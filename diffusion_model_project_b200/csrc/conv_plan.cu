@@ -284,7 +284,7 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->ktot, (cuuint64_t)d->wrows};
     cuuint64_t strides[1] = {(cuuint64_t)d->ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(pair_pick ? bn / 2 : bn)};  // a CTA pair stages half of the rows each
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&k.tmapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->weight), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
