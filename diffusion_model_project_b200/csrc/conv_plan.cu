@@ -126,10 +126,10 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
       if (halo && gt == 4 && b < 128) continue;  // narrow tiles batch 3 / 9 taps per weight stage
       const long long tiles = tiles_m2 * (b == 16 ? 1 : cols / b);
       const double t_kb = b == 256 ? 512.0 : b == 128 ? 256.0 : b == 64 ? 192.0 : 128.0;
-      // one A-operand group: tensor time of its MMAs, or the time to pull its operand bytes from L2 -- an SM reads about
-      // 40 B/clk through TMA (measured on the deep UNet levels, profiles/r2_tune_conv_88.txt: 128 x 128 tiles at K = 9216
-      // run at 6.5 TB/s over 88 SMs, 256-wide tiles with 3 K splits at 9-11 TB/s over 132), which is what bounds the
-      // generic tiles of the small-map layers and why wider N tiles and more K splits win there
+      // one A-operand group: tensor time of its MMAs, or its operand bytes at 40 B/clk -- an EMPIRICAL rate that makes the
+      // model reproduce the measured ordering of (BLOCK_N, split) on the small-map layers (profiles/r2_tune_conv_88.txt:
+      // 128 x 128 tiles at K = 9216 sustain 6.5 TB/s of operand traffic over 88 SMs and lose to 256-wide tiles with three
+      // K splits).  It is not the L2 port: CTA pairs that halve the weight bytes per SM run no faster (see below)
       constexpr double kL2BytesPerClk = 40.0;
       const double group_bytes = halo ? 18.0 * 18.0 * 128.0 + gt * b * 128.0 : (128.0 + b) * 128.0;
       double per_group = (halo ? 2.0 * gt : 1.0) * t_kb;
@@ -193,7 +193,10 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     if (best_sk_bn != 0 && (sk_force || best_bn == 0)) {
       best = best_sk; best_bn = best_sk_bn; ksplit_pick = 1; streamk_pick = true;
     }
-    if (best_pair_bn != 0 && !streamk_pick && (pair_force || best_pair < best * 0.92)) {
+    // CTA pairs only where forced (B2D_TUNE_PAIR): parity-green, 25 % less L2 -> SM traffic in ncu
+    // (profiles/r2_deep_level_ncu.txt) and the same time to within 2 % on every layer at 88 and at 704 slice-images
+    // (profiles/r2_tune_conv_88_pairs.txt, r2_tune_conv_704_pairs.txt): these layers are not bound by operand bytes per SM
+    if (best_pair_bn != 0 && !streamk_pick && pair_force) {
       best = best_pair; best_bn = best_pair_bn; ksplit_pick = best_pair_ks; pair_pick = true;
     }
     if (best_bn == 0)

@@ -23,7 +23,7 @@ struct V2Cfg {
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;              // weight rows this CTA stages
   static constexpr int B_TILE = B_ROWS * kBlockK * 2;
   static constexpr int B_STAGE = TPB * B_TILE;
-  static constexpr int NA = HALO ? ((BN >= 128 || XFORM) ? 2 : 3) : PAIR ? (BN == 256 ? 5 : 8) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
+  static constexpr int NA = HALO ? ((BN >= 128 || XFORM) ? 2 : 3) : PAIR ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
   static constexpr int NB = HALO ? (BN == 256 ? 4 : BN == 128 ? 6 : BN == 64 ? 4 : 3) : NA;
   static constexpr int BNC = BN < 32 ? 32 : BN;                  // TMEM columns of one M half
   static constexpr int ACC_COLS = MT * BNC;                      // one accumulator stage
