@@ -9,7 +9,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2d.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 B2D_MAX_SEG = 6
 B2D_MAX_TAPS = 27
 
@@ -99,8 +99,13 @@ _SIGNATURES = {
     "b2d_nmse_loss": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2d_gn_silu_bwd": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32,
                                 c_void_p, c_void_p, c_void_p, c_float, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "b2d_conv_wgrad": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+    "b2d_conv_wgrad": (c_int, [c_i32, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                                c_void_p, c_i32, c_void_p]),
+    "b2d_channel_sum": (c_int, [c_void_p, c_void_p, c_i32, c_i64, c_i32, c_i32, c_void_p, c_void_p]),
+    "b2d_add16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_void_p]),
+    "b2d_maxpool2x2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p]),
+    "b2d_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32,
+                                  c_i32, c_i32, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())

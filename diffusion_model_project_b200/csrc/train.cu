@@ -219,7 +219,14 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
   }
 }
 
-// ------------------------------------------------------------------------------------------- conv weight gradient (tcgen05)
+// ------------------------------------------------------------------------------------------- weight gradients (tcgen05)
+// dW[m][n][ty][tx] = sum over pixels p of A[p][m] * B[s * p + (tx, ty) + pad][n]: the weight gradient of
+//   * Conv2d 3x3 / pad 1   (A = dY, B = X, pad -1, s 1):  dW[co][ci][ky][kx]
+//   * Linear / Conv1d k1   (A = dY, B = X, one tap):      dW[out][in]
+//   * ConvTranspose2d k2s2 (A = X,  B = dY, pad 0, s 2):  dW[ci][co][ky][kx]   (B is read with a TMA element stride of 2)
+// M = A channels (tiles of 128), N = B channels (tiles of 128), K = pixels: both operands are MN-major tiles of 32 pixels x
+// 64 channels (128B swizzle) loaded straight out of the channels-last tensors; TMA zero fill = the conv's zero padding.
+// One CTA = (M tile, N tile, tap row ty, pixel split): the taps of a row share the A tile and own 128 TMEM columns each.
 constexpr int kWgK = 32;                       // pixels per K chunk (two K = 16 MMAs)
 constexpr int kWgAtom = kWgK * 128;            // bytes of one [32 px][64 ch] swizzled tile
 constexpr int kWgTile = 2 * kWgAtom;           // 128 channels
@@ -229,26 +236,28 @@ constexpr uint32_t kUmmaAMajorMN = 1u << 15;   // instruction-descriptor bit: A 
 constexpr uint32_t kUmmaBMajorMN2 = 1u << 16;
 
 struct WgradParams {
-  CUtensorMap tmY[2];  // dY hi / lo: dims (Cout_pad, W, H, 1, N), box (64, bw, bh, 1, bn), bw * bh * bn = 32
-  CUtensorMap tmX[2];  // X  hi / lo
-  float* dw;           // fp32 [cout][cin_total][3][3], atomically accumulated
-  int cout, cin, cin_off, cin_total;
+  CUtensorMap tmA[2];  // A hi / lo: dims (Cpad, W, H, 1, N), box (64, bw, bh, 1, bn), bw * bh * bn = 32
+  CUtensorMap tmB[2];  // B hi / lo (element strides (1, s, s, 1, 1), box extents bw * s, bh * s)
+  float* dw;           // fp32 [m_valid][n_total][KH][KW], atomically accumulated
+  int m_valid, n_valid, n_off, n_total;
+  int KH, KW, bpad, bstride;
   int lbw, lbh, lbn, tiles_w, tiles_h, tiles_n;
-  int chunks, chunks_per_cta, nsrc, op_f16, ci_tiles;
+  int chunks, chunks_per_cta, nsrc, op_f16, n_tiles;
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t wg_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nsrc = p.nsrc;
-  const int stage_bytes = nsrc * kWgTile * 4;  // dY + 3 shifted X tiles per source
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
+  const int nsrc = p.nsrc, KW = p.KW;
+  const int src_bytes = (1 + KW) * kWgTile;    // the A tile + KW tap tiles of B
+  const int stage_bytes = nsrc * src_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgStages * nsrc * 4 * kWgTile);
   uint64_t* empty = full + kWgStages;
   uint64_t* done = empty + kWgStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5;
-  const int co0 = (blockIdx.x / p.ci_tiles) * 128, ci0 = (blockIdx.x % p.ci_tiles) * 128;
-  const int ky = blockIdx.y;
+  const int m0 = (blockIdx.x / p.n_tiles) * 128, n0c = (blockIdx.x % p.n_tiles) * 128;
+  const int ty = blockIdx.y;
   const int ch_lo = blockIdx.z * p.chunks_per_cta;
   const int ch_hi = min(p.chunks, ch_lo + p.chunks_per_cta);
 
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
     for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(done, 1);
     fence_barrier_init();
-    for (int s = 0; s < nsrc; ++s) { prefetch_tmap(&p.tmY[s]); prefetch_tmap(&p.tmX[s]); }
+    for (int s = 0; s < nsrc; ++s) { prefetch_tmap(&p.tmA[s]); prefetch_tmap(&p.tmB[s]); }
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (threadIdx.x == 0) {
-    // ---------------- TMA producer: per chunk, the dY tile and the three kx-shifted X tiles of this ky row ----------------
+    // ---------------- TMA producer: per chunk, the A tile and the KW shifted B tiles of this tap row ----------------
     int st = 0;
     uint32_t ph = 0;
     for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -278,37 +287,38 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
       const int n0 = t << p.lbn;
       mbar_wait(&empty[st], ph ^ 1);
       mbar_arrive_expect_tx(&full[st], (uint32_t)stage_bytes);
-      uint8_t* sb = smem + st * stage_bytes;
+      uint8_t* sb = smem + st * (nsrc * 4 * kWgTile);
       for (int s = 0; s < nsrc; ++s) {
-        uint8_t* yt = sb + s * (4 * kWgTile);
-        for (int a = 0; a < 2; ++a) tma_load_5d(yt + a * kWgAtom, &p.tmY[s], &full[st], co0 + 64 * a, x0, y0, 0, n0);
-        for (int kx = 0; kx < 3; ++kx)
+        uint8_t* at = sb + s * (4 * kWgTile);
+        for (int a = 0; a < 2; ++a) tma_load_5d(at + a * kWgAtom, &p.tmA[s], &full[st], m0 + 64 * a, x0, y0, 0, n0);
+        for (int tx = 0; tx < KW; ++tx)
           for (int a = 0; a < 2; ++a)
-            tma_load_5d(yt + (1 + kx) * kWgTile + a * kWgAtom, &p.tmX[s], &full[st], ci0 + 64 * a, x0 + kx - 1, y0 + ky - 1, 0, n0);
+            tma_load_5d(at + (1 + tx) * kWgTile + a * kWgAtom, &p.tmB[s], &full[st], n0c + 64 * a, x0 * p.bstride + tx + p.bpad,
+                        y0 * p.bstride + ty + p.bpad, 0, n0);
       }
       if (++st == kWgStages) { st = 0; ph ^= 1; }
     }
   } else if (threadIdx.x == 32) {
-    // ---------------- MMA issuer: D_kx[co][ci] += dY^T X_kx over the chunk's 32 pixels (both operands MN-major) ----------
+    // ---------------- MMA issuer: D_tx[m][n] += A^T B_tx over the chunk's 32 pixels (both operands MN-major) ----------
     const uint32_t idesc = umma_idesc_16(128, 128, p.op_f16) | kUmmaAMajorMN | kUmmaBMajorMN2;
     int st = 0;
     uint32_t ph = 0, accum = 0;
     for (int ch = ch_lo; ch < ch_hi; ++ch) {
       mbar_wait(&full[st], ph);
       tc_fence_after();
-      const uint32_t sb = smem_u32(smem + st * stage_bytes);
-      // products: single source (y, x); split sources hi*hi + hi*lo + lo*hi
+      const uint32_t sb = smem_u32(smem + st * (nsrc * 4 * kWgTile));
+      // products: single source (a, b); split sources hi*hi + hi*lo + lo*hi
       const int nprod = nsrc == 2 ? 3 : 1;
       for (int pr = 0; pr < nprod; ++pr) {
-        const int ys = pr == 2 ? 1 : 0, xs = pr == 1 ? 1 : 0;
-        const uint32_t ya = sb + ys * (4 * kWgTile);
-        const uint32_t xa = sb + xs * (4 * kWgTile) + kWgTile;
-        for (int kx = 0; kx < 3; ++kx) {
+        const int as = pr == 2 ? 1 : 0, bs = pr == 1 ? 1 : 0;
+        const uint32_t aa = sb + as * (4 * kWgTile);
+        const uint32_t ba = sb + bs * (4 * kWgTile) + kWgTile;
+        for (int tx = 0; tx < KW; ++tx) {
 #pragma unroll
           for (int k = 0; k < kWgK / 16; ++k) {
-            const uint64_t ad = umma_smem_desc_mn(ya + k * 16 * 128, kWgAtom, 1024, 2);
-            const uint64_t bd = umma_smem_desc_mn(xa + kx * kWgTile + k * 16 * 128, kWgAtom, 1024, 2);
-            umma_bf16(tmem_base + kx * 128, ad, bd, idesc, accum | (uint32_t)(pr > 0) | (uint32_t)(k > 0));
+            const uint64_t ad = umma_smem_desc_mn(aa + k * 16 * 128, kWgAtom, 1024, 2);
+            const uint64_t bd = umma_smem_desc_mn(ba + tx * kWgTile + k * 16 * 128, kWgAtom, 1024, 2);
+            umma_bf16(tmem_base + tx * 128, ad, bd, idesc, accum | (uint32_t)(pr > 0) | (uint32_t)(k > 0));
           }
         }
       }
@@ -319,22 +329,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
     umma_commit(done);
   }
   __syncwarp();
-  // ---------------- epilogue: all four warps, thread = output channel row (TMEM lane) ----------------
+  // ---------------- epilogue: all four warps, thread = output row m (TMEM lane) ----------------
   if (ch_hi > ch_lo) {
     mbar_wait(done, 0);
     tc_fence_after();
-    const int co = co0 + (int)threadIdx.x;
+    const int m = m0 + (int)threadIdx.x;
     const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16);
-    for (int kx = 0; kx < 3; ++kx) {
+    for (int tx = 0; tx < KW; ++tx) {
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(taddr + kx * 128 + c0, v);
+        tmem_ld_32x32(taddr + tx * 128 + c0, v);
         tmem_ld_wait();
-        if (co < p.cout) {
+        if (m < p.m_valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int ci = ci0 + c0 + j;
-            if (ci < p.cin) atomicAdd(p.dw + (((long long)co * p.cin_total + p.cin_off + ci) * 3 + ky) * 3 + kx, __uint_as_float(v[j]));
+            const int n = n0c + c0 + j;
+            if (n < p.n_valid) atomicAdd(p.dw + (((long long)m * p.n_total + p.n_off + n) * p.KH + ty) * KW + tx, __uint_as_float(v[j]));
           }
         }
       }
@@ -345,6 +355,169 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- small elementwise / reduction passes
+// out[c] += sum over rows of x[row][c]   (bias gradients: Conv2d / ConvTranspose2d / Linear bias = sum of dY over pixels)
+__global__ void __launch_bounds__(256) channel_sum_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int f16,
+                                                          long long rows, int C, int cvalid, float* __restrict__ out) {
+  // blockDim.x = 256 threads: thread -> channel (c = tid % Cb), row group (tid / Cb), Cb = min(C, 256)
+  const int Cb = C < 256 ? C : 256;
+  const int rg = blockDim.x / Cb;
+  for (int c0 = 0; c0 < C; c0 += Cb) {
+    const int c = c0 + (int)(threadIdx.x % Cb);
+    const int r0 = (int)(threadIdx.x / Cb);
+    if (r0 >= rg || c >= cvalid) continue;
+    float acc = 0.f;
+    for (long long r = (long long)blockIdx.x * rg + r0; r < rows; r += (long long)gridDim.x * rg) acc += ld16x(hi, lo, r * C + c, f16);
+    atomicAdd(out + c, acc);
+  }
+}
+// out = a + b, 16-bit hi (+ lo) storage: the two uses of a skip connection meet here (unet/models.py:150-177)
+__global__ void __launch_bounds__(256) add16_kernel(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo,
+                                                    uint16_t* o_hi, uint16_t* o_lo, int f16, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    st16x(o_hi, o_lo, i, ld16x(a_hi, a_lo, i, f16) + ld16x(b_hi, b_lo, i, f16), f16);
+}
+// MaxPool2d(2, 2) backward (unet/blocks.py:161-164): the gradient of a pooled pixel goes to the FIRST maximum of its 2x2
+// window in scan order (torch keeps the index of the first strictly greater value)
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi, const uint16_t* dy_lo,
+                                                          uint16_t* dx_hi, uint16_t* dx_lo, int f16, long long N, int H, int W, int C) {
+  const int OH = H >> 1, OW = W >> 1;
+  const long long total = N * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int ox = (int)(t % OW); t /= OW;
+    const int oy = (int)(t % OH);
+    const long long n = t / OH;
+    float best = 0.f;
+    int arg = 0;
+    long long idx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      idx[q] = ((n * H + 2 * oy + (q >> 1)) * W + 2 * ox + (q & 1)) * C + c;
+      const float v = ld16x(x_hi, x_lo, idx[q], f16);
+      if (q == 0 || v > best) { best = v; arg = q; }
+    }
+    const float g = ld16x(dy_hi, dy_lo, i, f16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st16x(dx_hi, dx_lo, idx[q], q == arg ? g : 0.f, f16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- attention core backward
+// softmax(q k^T / sqrt(d)) v per (image, head) (nn.MultiheadAttention's core, unet/blocks.py:196-227), fp32 CUDA cores:
+// T <= 256 tokens and the layer is ~1% of the step's flops, so exact fp32 arithmetic is worth more here than tensor cores.
+//   pass 0 (per query block): lse_i = logsumexp_j(s_ij), D_i = dO_i . O_i   (= sum_j P_ij dP_ij)
+//   pass 1 (per query block): dQ_i = scale * sum_j dS_ij K_j,   dS_ij = P_ij (dO_i . V_j - D_i),  P_ij = exp(s_ij - lse_i)
+//   pass 2 (per key block):   dK_j = scale * sum_i dS_ij Q_i,   dV_j = sum_i P_ij dO_i
+// One CTA = 16 "owner" rows (queries in pass 0/1, keys in pass 2) against all "other" rows in tiles of 16; thread (a, b)
+// computes the (owner a, other b) entry of the 16 x 16 score tile, then accumulates columns b, b + 16, ... of owner row a.
+constexpr int kAbR = 16;
+struct AttnBwdArgs {
+  const uint16_t *qkv_hi, *qkv_lo, *o_hi, *o_lo, *do_hi, *do_lo;
+  uint16_t *dqkv_hi, *dqkv_lo;
+  float* stats;  // [N][heads][T][2]: lse, D
+  int T, C, heads, d, f16;
+  float scale;
+};
+template <int MODE>
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdArgs a) {
+  extern __shared__ float ab_smem[];
+  const int d = a.d, ld = d + 1, T = a.T, C = a.C;
+  float* own1 = ab_smem;             // [16][ld]  pass 0/1: Q   pass 2: K
+  float* own2 = own1 + kAbR * ld;    //           pass 0/1: dO  pass 2: V
+  float* oth1 = own2 + kAbR * ld;    //           pass 0/1: K   pass 2: Q
+  float* oth2 = oth1 + kAbR * ld;    //           pass 0/1: V   pass 2: dO
+  float* tile_ds = oth2 + kAbR * ld; // [16][17]
+  float* tile_p = tile_ds + kAbR * 17;
+  const int n = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * kAbR;
+  const int ta = threadIdx.x >> 4, tb = threadIdx.x & 15;
+  const long long qkv_row = 3LL * C;
+  const uint16_t* qh = a.qkv_hi + (long long)n * T * qkv_row + h * d;
+  const uint16_t* ql = a.qkv_lo ? a.qkv_lo + (long long)n * T * qkv_row + h * d : nullptr;
+  const long long obase = (long long)n * T * C + h * d;
+  float* st = a.stats + ((long long)(n * a.heads + h) * T) * 2;
+  // which = 0 q, 1 k, 2 v, 3 dO, 4 O
+  auto load_rows = [&](float* dst, int which, int row0) {
+    for (int i = threadIdx.x; i < kAbR * d; i += 256) {
+      const int r = i / d, k = i - r * d;
+      float v;
+      if (which < 3) v = ld16x(qh, ql, (long long)(row0 + r) * qkv_row + which * C + k, a.f16);
+      else if (which == 3) v = ld16x(a.do_hi, a.do_lo, obase + (long long)(row0 + r) * C + k, a.f16);
+      else v = ld16x(a.o_hi, a.o_lo, obase + (long long)(row0 + r) * C + k, a.f16);
+      dst[r * ld + k] = v;
+    }
+  };
+  if (MODE == 2) { load_rows(own1, 1, r0); load_rows(own2, 2, r0); }
+  else { load_rows(own1, 0, r0); load_rows(own2, 3, r0); }
+  float acc1[32], acc2[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc1[i] = acc2[i] = 0.f;
+  float run_m = -INFINITY, run_l = 0.f;
+  float lse_own = 0.f, d_own = 0.f;
+  if (MODE == 1) { lse_own = st[(r0 + ta) * 2]; d_own = st[(r0 + ta) * 2 + 1]; }
+  for (int o0 = 0; o0 < T; o0 += kAbR) {
+    __syncthreads();
+    if (MODE == 2) { load_rows(oth1, 0, o0); load_rows(oth2, 3, o0); }
+    else { load_rows(oth1, 1, o0); if (MODE == 1) load_rows(oth2, 2, o0); }
+    __syncthreads();
+    float s = 0.f, dp = 0.f;
+    for (int k = 0; k < d; ++k) {
+      s = fmaf(own1[ta * ld + k], oth1[tb * ld + k], s);
+      if (MODE != 0) dp = fmaf(own2[ta * ld + k], oth2[tb * ld + k], dp);
+    }
+    s *= a.scale;
+    if (MODE == 0) {
+      float m = s;
+      for (int off = 8; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+      const float nm = fmaxf(run_m, m);
+      float e = expf(s - nm);
+      for (int off = 8; off; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+      run_l = run_l * expf(run_m - nm) + e;
+      run_m = nm;
+    } else {
+      float lse = lse_own, dd = d_own;
+      if (MODE == 2) { lse = st[(o0 + tb) * 2]; dd = st[(o0 + tb) * 2 + 1]; }
+      const float pr = expf(s - lse);
+      tile_p[ta * 17 + tb] = pr;
+      tile_ds[ta * 17 + tb] = pr * (dp - dd) * a.scale;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) {
+        if (kk * 16 >= d) break;
+        const int k = tb + kk * 16;
+        float x1 = acc1[kk], x2 = acc2[kk];
+#pragma unroll
+        for (int b = 0; b < kAbR; ++b) {
+          x1 = fmaf(tile_ds[ta * 17 + b], oth1[b * ld + k], x1);
+          if (MODE == 2) x2 = fmaf(tile_p[ta * 17 + b], oth2[b * ld + k], x2);
+        }
+        acc1[kk] = x1; acc2[kk] = x2;
+      }
+    }
+  }
+  if (MODE == 0) {
+    // D_a = dO_a . O_a: the 16 lanes of row a split the head dimension
+    __syncthreads();
+    load_rows(oth1, 4, r0);
+    __syncthreads();
+    float dd = 0.f;
+    for (int k = tb; k < d; k += 16) dd = fmaf(own2[ta * ld + k], oth1[ta * ld + k], dd);
+    for (int off = 8; off; off >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, off);
+    if (tb == 0) { st[(r0 + ta) * 2] = run_m + logf(run_l); st[(r0 + ta) * 2 + 1] = dd; }
+  } else {
+    uint16_t* oh = a.dqkv_hi + (long long)n * T * qkv_row + h * d + (long long)(r0 + ta) * qkv_row;
+    uint16_t* ol = a.dqkv_lo ? a.dqkv_lo + (long long)n * T * qkv_row + h * d + (long long)(r0 + ta) * qkv_row : nullptr;
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      if (kk * 16 >= d) break;
+      const int k = tb + kk * 16;
+      if (MODE == 1) st16x(oh, ol, k, acc1[kk], a.f16);
+      else { st16x(oh, ol, C + k, acc1[kk], a.f16); st16x(oh, ol, 2 * C + k, acc2[kk], a.f16); }
+    }
   }
 }
 
@@ -406,14 +579,16 @@ extern "C" int b2d_gn_silu_bwd(const void* x_hi, const void* x_lo, int32_t x_f16
   return check_launch("gn_silu_bwd kernels");
 }
 
-extern "C" int b2d_conv_wgrad(const void* dy_hi, const void* dy_lo, int32_t cout_pad, const void* x_hi, const void* x_lo, int32_t cin_pad,
-                              int32_t N, int32_t H, int32_t W, int32_t cout, int32_t cin, int32_t cin_off, int32_t cin_total, float* dw,
-                              int32_t op_f16, void* stream) {
+extern "C" int b2d_conv_wgrad(int32_t kind, const void* dy_hi, const void* dy_lo, int32_t cout_pad, const void* x_hi, const void* x_lo,
+                              int32_t cin_pad, int32_t N, int32_t H, int32_t W, int32_t cout, int32_t cin, int32_t cin_off, int32_t cin_total,
+                              float* dw, int32_t op_f16, void* stream) {
+  // H, W: extent of X (for kind 2, ConvTranspose2d k2s2, dY is 2H x 2W)
   if (!dy_hi || !x_hi || !dw || N < 1 || H < 1 || W < 1 || cout < 1 || cin < 1 || cin_off < 0 || cin_off + cin > cin_total ||
-      (cout_pad % 64) || (cin_pad % 64) || cout > cout_pad || cin > cin_pad || ((dy_lo == nullptr) != (x_lo == nullptr)))
+      (cout_pad % 64) || (cin_pad % 64) || cout > cout_pad || cin > cin_pad || ((dy_lo == nullptr) != (x_lo == nullptr)) || kind < 0 || kind > 2)
     return set_error(B2D_E_INVALID, "b2d_conv_wgrad: bad argument");
   if ((W & (W - 1)) || (H & (H - 1))) return set_error(B2D_E_UNSUPPORTED, "b2d_conv_wgrad: H, W must be powers of two (got %dx%d)", H, W);
   if (op_f16 && dy_lo) return set_error(B2D_E_INVALID, "b2d_conv_wgrad: fp16 operands have no lo part");
+  if (kind == 2 && cin_off != 0) return set_error(B2D_E_INVALID, "b2d_conv_wgrad: transposed conv takes no channel offset");
   PFN_encodeTiledT enc = reinterpret_cast<PFN_encodeTiledT>(tensor_map_encode_fn());
   if (!enc) return set_error(B2D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available (no CUDA driver / too old)");
   WgradParams p;
@@ -426,25 +601,37 @@ extern "C" int b2d_conv_wgrad(const void* dy_hi, const void* dy_lo, int32_t cout
   p.chunks = p.tiles_w * p.tiles_h * p.tiles_n;
   p.nsrc = dy_lo ? 2 : 1;
   p.op_f16 = op_f16 ? 1 : 0;
-  p.dw = dw; p.cout = cout; p.cin = cin; p.cin_off = cin_off; p.cin_total = cin_total;
-  const void* ys[2] = {dy_hi, dy_lo};
-  const void* xs[2] = {x_hi, x_lo};
+  p.dw = dw;
+  // roles: A = rows of dW, B = columns (read at the tap positions)
+  const void* a_src[2]; const void* b_src[2];
+  int a_pad, b_pad, a_W = W, a_H = H, b_W = W, b_H = H;
+  if (kind == 2) {  // dW[ci][co][ky][kx]: A = X, B = dY (2H x 2W, element stride 2)
+    a_src[0] = x_hi; a_src[1] = x_lo; b_src[0] = dy_hi; b_src[1] = dy_lo; a_pad = cin_pad; b_pad = cout_pad;
+    p.m_valid = cin; p.n_valid = cout; p.n_off = 0; p.n_total = cout; p.KH = 2; p.KW = 2; p.bpad = 0; p.bstride = 2;
+    b_W = 2 * W; b_H = 2 * H;
+  } else {          // dW[co][ci][ky][kx]: A = dY, B = X
+    a_src[0] = dy_hi; a_src[1] = dy_lo; b_src[0] = x_hi; b_src[1] = x_lo; a_pad = cout_pad; b_pad = cin_pad;
+    p.m_valid = cout; p.n_valid = cin; p.n_off = cin_off; p.n_total = cin_total; p.bstride = 1;
+    if (kind == 0) { p.KH = 3; p.KW = 3; p.bpad = -1; } else { p.KH = 1; p.KW = 1; p.bpad = 0; }
+  }
   for (int s = 0; s < p.nsrc; ++s) {
     for (int which = 0; which < 2; ++which) {
-      const int cpad = which == 0 ? cout_pad : cin_pad;
-      cuuint64_t dims[5] = {(cuuint64_t)cpad, (cuuint64_t)W, (cuuint64_t)H, 1, (cuuint64_t)N};
-      cuuint64_t strides[4] = {(cuuint64_t)cpad * 2, (cuuint64_t)cpad * 2 * W, (cuuint64_t)cpad * 2 * W * H, (cuuint64_t)cpad * 2 * W * H};
-      cuuint32_t box[5] = {64, (cuuint32_t)(1 << lw), (cuuint32_t)(1 << lh), 1, (cuuint32_t)(1 << ln)};
-      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-      CUresult r = enc(which == 0 ? &p.tmY[s] : &p.tmX[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(which == 0 ? ys[s] : xs[s]),
+      const int cpad = which == 0 ? a_pad : b_pad;
+      const int tw = which == 0 ? a_W : b_W, th = which == 0 ? a_H : b_H;
+      const int es = which == 0 ? 1 : p.bstride;
+      cuuint64_t dims[5] = {(cuuint64_t)cpad, (cuuint64_t)tw, (cuuint64_t)th, 1, (cuuint64_t)N};
+      cuuint64_t strides[4] = {(cuuint64_t)cpad * 2, (cuuint64_t)cpad * 2 * tw, (cuuint64_t)cpad * 2 * tw * th, (cuuint64_t)cpad * 2 * tw * th};
+      cuuint32_t box[5] = {64, (cuuint32_t)((1 << lw) * es), (cuuint32_t)((1 << lh) * es), 1, (cuuint32_t)(1 << ln)};
+      cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+      CUresult r = enc(which == 0 ? &p.tmA[s] : &p.tmB[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(which == 0 ? a_src[s] : b_src[s]),
                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return set_error(B2D_E_CUDA, "b2d_conv_wgrad: cuTensorMapEncodeTiled failed: %d", (int)r);
     }
   }
-  const int co_tiles = (cout + 127) / 128;
-  p.ci_tiles = (cin + 127) / 128;
-  int splits = (2 * num_sms()) / (co_tiles * p.ci_tiles * 3);
+  const int m_tiles = (p.m_valid + 127) / 128;
+  p.n_tiles = (p.n_valid + 127) / 128;
+  int splits = (2 * num_sms()) / (m_tiles * p.n_tiles * p.KH);
   if (splits < 1) splits = 1;
   if (splits > p.chunks) splits = p.chunks;
   p.chunks_per_cta = (p.chunks + splits - 1) / splits;
@@ -453,6 +640,57 @@ extern "C" int b2d_conv_wgrad(const void* dy_hi, const void* dy_lo, int32_t cout
   static unsigned long long configured = 0;
   cudaError_t e = smem_attr_once(conv_wgrad_kernel, 227 * 1024, configured);
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "b2d_conv_wgrad: smem attr: %s", cudaGetErrorString(e));
-  conv_wgrad_kernel<<<dim3(co_tiles * p.ci_tiles, 3, splits), kWgThreads, smem, (cudaStream_t)stream>>>(p);
+  conv_wgrad_kernel<<<dim3(m_tiles * p.n_tiles, p.KH, splits), kWgThreads, smem, (cudaStream_t)stream>>>(p);
   return check_launch("conv_wgrad_kernel");
+}
+
+extern "C" int b2d_channel_sum(const void* x_hi, const void* x_lo, int32_t f16, int64_t rows, int32_t C, int32_t cvalid, float* out, void* stream) {
+  if (!x_hi || !out || rows < 1 || C < 1 || cvalid < 1 || cvalid > C || (C > 256 && (C % 256)) || (C <= 256 && (256 % C)) || (f16 && x_lo))
+    return set_error(B2D_E_INVALID, "b2d_channel_sum: bad argument (C must divide 256 or be a multiple of it)");
+  const int rg = C < 256 ? 256 / C : 1;
+  channel_sum_kernel<<<grid_cap((rows + rg - 1) / rg, 8), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x_hi, (const uint16_t*)x_lo, f16 ? 1 : 0,
+                                                                                       (long long)rows, C, cvalid, out);
+  return check_launch("channel_sum_kernel");
+}
+
+extern "C" int b2d_add16(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* o_hi, void* o_lo, int32_t f16, int64_t n,
+                         void* stream) {
+  if (!a_hi || !b_hi || !o_hi || n < 1 || (f16 && (a_lo || b_lo || o_lo))) return set_error(B2D_E_INVALID, "b2d_add16: bad argument");
+  add16_kernel<<<grid_cap(n, 1024), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)a_hi, (const uint16_t*)a_lo, (const uint16_t*)b_hi,
+                                                                    (const uint16_t*)b_lo, (uint16_t*)o_hi, (uint16_t*)o_lo, f16 ? 1 : 0, (long long)n);
+  return check_launch("add16_kernel");
+}
+
+extern "C" int b2d_maxpool2x2_bwd(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, void* dx_hi, void* dx_lo, int32_t f16,
+                                  int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!x_hi || !dy_hi || !dx_hi || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 1 || (f16 && (x_lo || dy_lo || dx_lo)))
+    return set_error(B2D_E_INVALID, "b2d_maxpool2x2_bwd: bad argument");
+  maxpool_bwd_kernel<<<grid_cap((long long)N * (H / 2) * (W / 2) * C, 1024), 256, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)x_hi, (const uint16_t*)x_lo, (const uint16_t*)dy_hi, (const uint16_t*)dy_lo, (uint16_t*)dx_hi, (uint16_t*)dx_lo, f16 ? 1 : 0,
+      (long long)N, H, W, C);
+  return check_launch("maxpool_bwd_kernel");
+}
+
+extern "C" int b2d_attention_bwd(const void* qkv, const void* qkv_lo, const void* out, const void* out_lo, const void* dout, const void* dout_lo,
+                                 void* dqkv, void* dqkv_lo, float* stats, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t f16, void* stream) {
+  if (!qkv || !out || !dout || !dqkv || !stats || N < 1 || T < 16 || (T % 16) || heads < 1 || C < 16 || (C % heads) || (f16 && (qkv_lo || dqkv_lo)))
+    return set_error(B2D_E_INVALID, "b2d_attention_bwd: bad argument");
+  const int d = C / heads;
+  if ((d % 16) || d > 512) return set_error(B2D_E_UNSUPPORTED, "b2d_attention_bwd: head dim %d (need a multiple of 16, <= 512)", d);
+  AttnBwdArgs a;
+  a.qkv_hi = (const uint16_t*)qkv; a.qkv_lo = (const uint16_t*)qkv_lo; a.o_hi = (const uint16_t*)out; a.o_lo = (const uint16_t*)out_lo;
+  a.do_hi = (const uint16_t*)dout; a.do_lo = (const uint16_t*)dout_lo; a.dqkv_hi = (uint16_t*)dqkv; a.dqkv_lo = (uint16_t*)dqkv_lo;
+  a.stats = stats; a.T = T; a.C = C; a.heads = heads; a.d = d; a.f16 = f16 ? 1 : 0;
+  a.scale = 1.0f / sqrtf((float)d);
+  const int smem = (4 * kAbR * (d + 1) + 2 * kAbR * 17) * (int)sizeof(float);
+  static unsigned long long c0 = 0, c1 = 0, c2 = 0;
+  cudaError_t e = smem_attr_once(attn_bwd_kernel<0>, 200 * 1024, c0);
+  if (e == cudaSuccess) e = smem_attr_once(attn_bwd_kernel<1>, 200 * 1024, c1);
+  if (e == cudaSuccess) e = smem_attr_once(attn_bwd_kernel<2>, 200 * 1024, c2);
+  if (e != cudaSuccess) return set_error(B2D_E_CUDA, "b2d_attention_bwd: smem attr: %s", cudaGetErrorString(e));
+  const dim3 grid(T / kAbR, heads, N);
+  attn_bwd_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  attn_bwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  attn_bwd_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("attn_bwd_kernel");
 }

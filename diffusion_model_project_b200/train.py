@@ -118,13 +118,58 @@ def gn_silu_bwd(x: Act, dy: Act, dx: Act, stats: torch.Tensor, gamma, beta, act:
     return sums
 
 
-def conv_wgrad(dy: Act, x: Act, dw: torch.Tensor, cout: int, cin: int, cin_off: int, stream: int):
-    """dw (fp32, reference layout [Cout, Cin_total, 3, 3]) += the weight gradient of the input-channel block starting at cin_off."""
+WGRAD_CONV3X3, WGRAD_LINEAR, WGRAD_CONVT2X2 = 0, 1, 2
+
+
+def conv_wgrad(dy: Act, x: Act, dw: torch.Tensor, cout: int, cin: int, cin_off: int, stream: int, kind: int = WGRAD_CONV3X3):
+    """dw (fp32, the reference's parameter layout) += the weight gradient of the input-channel block starting at cin_off.
+    kind: WGRAD_CONV3X3 (dw [Cout, Cin_total, 3, 3]), WGRAD_LINEAR (dw [Cout, Cin_total]; Linear, Conv1d k1),
+    WGRAD_CONVT2X2 (dw [Cin, Cout, 2, 2]; dy is the 2H x 2W gradient of the transposed conv's output)."""
     N, D, H, W, _ = x.shape
-    assert D == 1 and dy.shape[:4] == x.shape[:4] and dw.dtype == torch.float32 and dw.is_contiguous()
+    up = 2 if kind == WGRAD_CONVT2X2 else 1
+    assert D == 1 and dy.shape[:4] == (N, 1, H * up, W * up) and dw.dtype == torch.float32 and dw.is_contiguous()
     assert x.f16 == dy.f16 and (x.lo is None) == (dy.lo is None)
-    call("b2d_conv_wgrad", ptr(dy.hi), ptr(dy.lo), dy.C, ptr(x.hi), ptr(x.lo), x.C, N, H, W, cout, cin, cin_off, dw.shape[1], dw.data_ptr(),
-         1 if x.f16 else 0, stream)
+    cin_total = dw.shape[0] if kind == WGRAD_CONVT2X2 else dw.shape[1]
+    call("b2d_conv_wgrad", kind, ptr(dy.hi), ptr(dy.lo), dy.C, ptr(x.hi), ptr(x.lo), x.C, N, H, W, cout, cin, cin_off, cin_total,
+         dw.data_ptr(), 1 if x.f16 else 0, stream)
+
+
+def channel_sum(x: Act, out: torch.Tensor, cvalid: int, stream: int):
+    """out[c] += sum of x over every position (bias gradients)."""
+    N, D, H, W, C = x.shape
+    assert out.dtype == torch.float32 and out.numel() >= cvalid
+    call("b2d_channel_sum", ptr(x.hi), ptr(x.lo), 1 if x.f16 else 0, N * D * H * W, C, cvalid, out.data_ptr(), stream)
+
+
+def add_acts(a: Act, b: Act, out: Act, stream: int):
+    """out = a + b (may alias either input)."""
+    assert a.shape == b.shape == out.shape and a.f16 == b.f16 == out.f16
+    call("b2d_add16", ptr(a.hi), ptr(a.lo), ptr(b.hi), ptr(b.lo), ptr(out.hi), ptr(out.lo), 1 if a.f16 else 0, a.hi.numel(), stream)
+
+
+def maxpool_bwd(x: Act, dy: Act, dx: Act, stream: int):
+    """MaxPool2d(2, 2) backward: x = the pooled layer's input, dy = gradient of its output."""
+    N, D, H, W, C = x.shape
+    assert D == 1 and dy.shape == (N, 1, H // 2, W // 2, C) and dx.shape == x.shape
+    call("b2d_maxpool2x2_bwd", ptr(x.hi), ptr(x.lo), ptr(dy.hi), ptr(dy.lo), ptr(dx.hi), ptr(dx.lo), 1 if x.f16 else 0, N, H, W, C, stream)
+
+
+def attention_bwd(qkv: Act, out: Act, d_out: Act, d_qkv: Act, heads: int, stream: int):
+    """Backward of engine's attention core (b2d_attention): d_qkv = (dq | dk | dv)."""
+    N, D, H, W, C3 = qkv.shape
+    C, T = C3 // 3, D * H * W
+    assert out.shape == d_out.shape == (N, D, H, W, C) and d_qkv.shape == qkv.shape
+    stats = torch.empty(N * heads * T * 2, dtype=torch.float32, device=qkv.hi.device)
+    call("b2d_attention_bwd", ptr(qkv.hi), ptr(qkv.lo), ptr(out.hi), ptr(out.lo), ptr(d_out.hi), ptr(d_out.lo), ptr(d_qkv.hi), ptr(d_qkv.lo),
+         stats.data_ptr(), N, T, C, heads, 1 if qkv.f16 else 0, stream, launches=3)
+
+
+def pack_convT2x2_dgrad(w: torch.Tensor, device, split=False, f16=False) -> engine.PackedWeight:
+    """Data gradient of nn.ConvTranspose2d k2 s2 (weight [Cin, Cout, 2, 2]): dX[p][ci] = sum_{ky,kx,co} dY[2p + (ky,kx)][co]
+    W[ci][co][ky][kx] -- a stride-2 conv with a 2x2 window (ConvPlan(..., stride=2))."""
+    ci, co = w.shape[:2]
+    taps = [(0, ky, kx) for ky in range(2) for kx in range(2)]
+    return engine.pack_weight(w.permute(0, 2, 3, 1).reshape(ci, 4, co), [co], taps, None, device, split, f16=f16)
 
 
 class DoubleBlockGrad:

@@ -34,7 +34,7 @@ extern "C" {
 #define B2D_API
 #endif
 
-#define B2D_VERSION 6
+#define B2D_VERSION 7
 #define B2D_MAX_SEG 6
 #define B2D_MAX_TAPS 27
 
@@ -276,14 +276,33 @@ B2D_API int b2d_gn_silu_bwd(const void* x_hi, const void* x_lo, int32_t x_f16, c
                     void* dx_hi, void* dx_lo, int32_t dx_f16, int32_t N, int64_t P, int32_t C, const double* stats,
                     const float* gamma, const float* beta, float eps, int32_t act, double* sums, float* dgamma, float* dbeta,
                     float* dtemb, void* stream);
-/* Weight gradient of a 3x3 zero-padded conv (unet/blocks.py:29-36) on tcgen05: dw[co][cin_off + ci][ky][kx] +=
- * sum over pixels of dY[p][co] * X[p + (ky-1, kx-1)][ci]; dY [N][H][W][cout_pad], X [N][H][W][cin_pad] channels-last 16-bit
- * (hi + optional bf16 lo: three products hi*hi + hi*lo + lo*hi), H and W powers of two.  dw: fp32 in the reference's
- * (Cout, cin_total, 3, 3) layout, atomically accumulated (zero it first); cin_off selects the channel block of a
- * concatenated input (torch.cat skip | up, unet/models.py:177). */
-B2D_API int b2d_conv_wgrad(const void* dy_hi, const void* dy_lo, int32_t cout_pad, const void* x_hi, const void* x_lo, int32_t cin_pad,
-                   int32_t N, int32_t H, int32_t W, int32_t cout, int32_t cin, int32_t cin_off, int32_t cin_total, float* dw,
-                   int32_t op_f16, void* stream);
+/* Weight gradients on tcgen05 (pixels are the GEMM K): dW[m][n][ty][tx] += sum over pixels of A[p][m] * B[s p + tap][n].
+ *   kind 0  Conv2d 3x3 pad 1 (unet/blocks.py:29-36):      dw[co][cin_off + ci][ky][kx] += dY[p][co] * X[p + (ky-1, kx-1)][ci]
+ *   kind 1  Linear / Conv1d k1 / 1x1 conv (blocks.py:247-258, models.py:122): dw[co][cin_off + ci] += dY[p][co] * X[p][ci]
+ *   kind 2  ConvTranspose2d k2 s2 (unet/blocks.py:205):   dw[ci][co][ky][kx] += X[p][ci] * dY[2p + (ky, kx)][co]
+ * dY [N][H'][W'][cout_pad], X [N][H][W][cin_pad] channels-last 16-bit (hi + optional bf16 lo: three products hi*hi + hi*lo
+ * + lo*hi); H, W = extent of X, powers of two (kind 2: dY is 2H x 2W).  dw: fp32 in the reference's parameter layout,
+ * atomically accumulated (zero it first); cin_off selects the channel block of a concatenated input (torch.cat skip | up,
+ * unet/models.py:177). */
+B2D_API int b2d_conv_wgrad(int32_t kind, const void* dy_hi, const void* dy_lo, int32_t cout_pad, const void* x_hi, const void* x_lo,
+                   int32_t cin_pad, int32_t N, int32_t H, int32_t W, int32_t cout, int32_t cin, int32_t cin_off, int32_t cin_total,
+                   float* dw, int32_t op_f16, void* stream);
+/* out[c] += sum over rows of x[row][c], c < cvalid (bias gradients = sum of dY over pixels); x [rows][C] 16-bit hi (+ lo),
+ * C a divisor or a multiple of 256. */
+B2D_API int b2d_channel_sum(const void* x_hi, const void* x_lo, int32_t f16, int64_t rows, int32_t C, int32_t cvalid, float* out, void* stream);
+/* o = a + b on 16-bit hi (+ lo) tensors of n elements: the two gradient paths of a skip connection (unet/models.py:150-177). */
+B2D_API int b2d_add16(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* o_hi, void* o_lo, int32_t f16, int64_t n,
+              void* stream);
+/* MaxPool2d(2, 2) backward (unet/blocks.py:161-164): x [N][H][W][C] = the pooled layer's input, dy [N][H/2][W/2][C]; the
+ * gradient goes to the first maximum of each window in scan order (torch's saved index), zeros elsewhere. */
+B2D_API int b2d_maxpool2x2_bwd(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, void* dx_hi, void* dx_lo, int32_t f16,
+                       int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* Backward of b2d_attention's core: given qkv, the forward output out and d loss / d out (all channels-last 16-bit hi + lo
+ * as in b2d_attention), writes dqkv [N][T][3C] (dq | dk | dv).  fp32 CUDA-core arithmetic; stats: [N][heads][T][2] fp32
+ * scratch (log-sum-exp and dO.O per query row).  T a multiple of 16, head dim a multiple of 16 and <= 512. */
+B2D_API int b2d_attention_bwd(const void* qkv, const void* qkv_lo, const void* out, const void* out_lo, const void* dout, const void* dout_lo,
+                      void* dqkv, void* dqkv_lo, float* stats, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t f16, void* stream);
 
 /* fill helpers used by the fused loop (graph-capturable) */
 B2D_API int b2d_zero(void* p, int64_t bytes, void* stream);

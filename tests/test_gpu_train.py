@@ -119,6 +119,86 @@ def test_conv_wgrad(N, co, ci, H, W, split):
     assert rel_l2(dw[:, 5:], ref) <= (2e-5 if split else 1e-5), rel_l2(dw[:, 5:], ref)
 
 
+@pytest.mark.parametrize("N,co,ci,H,W", [(2, 768, 256, 8, 8), (3, 64, 128, 1, 1), (2, 1024, 1024, 2, 2), (4, 200, 72, 4, 8)])
+def test_linear_wgrad(N, co, ci, H, W):
+    """dW of a 1x1 conv / Linear over tokens (in_proj, out_proj . proj_out): dW[o][i] = sum_p dY[p][o] X[p][i]."""
+    no_tf32()
+    g = torch.Generator().manual_seed(N + co + ci)
+    x = torch.randn(N, ci, 1, H, W, generator=g).to(DEV)
+    dy = (torch.randn(N, co, 1, H, W, generator=g) * 0.3).to(DEV)
+    dw = torch.zeros(co, ci, device=DEV)
+    train.conv_wgrad(to_act(dy, split=True), to_act(x, split=True), dw, co, ci, 0, _s(), kind=train.WGRAD_LINEAR)
+    ref = torch.einsum("nohw,nihw->oi", dy[:, :, 0].double(), x[:, :, 0].double()).float()
+    assert rel_l2(dw, ref) <= 2e-5, rel_l2(dw, ref)
+
+
+@pytest.mark.parametrize("N,ci,co,H,W", [(2, 128, 64, 16, 16), (3, 2048, 1024, 1, 1), (2, 256, 128, 4, 4), (5, 192, 72, 2, 8)])
+def test_conv_transpose_gradients(N, ci, co, H, W):
+    """ConvTranspose2d k2 s2 (unet/blocks.py:205): weight gradient [Cin, Cout, 2, 2] on the tcgen05 wgrad kernel (dY read
+    with a TMA element stride of 2), bias gradient, and the data gradient as a stride-2 2x2 conv on the forward engine."""
+    no_tf32()
+    g = torch.Generator().manual_seed(N + co + ci)
+    x = torch.randn(N, ci, H, W, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(ci, co, 2, 2, generator=g) / (ci ** 0.5)).to(DEV).requires_grad_(True)
+    b = torch.randn(co, generator=g).to(DEV).requires_grad_(True)
+    dy = (torch.randn(N, co, 2 * H, 2 * W, generator=g) * 0.3).to(DEV)
+    F.conv_transpose2d(x, w, b, stride=2).backward(dy)
+    xa, dya = to_act(x.detach()[:, :, None], split=True), to_act(dy[:, :, None], split=True)
+    dw = torch.zeros(ci, co, 2, 2, device=DEV)
+    train.conv_wgrad(dya, xa, dw, co, ci, 0, _s(), kind=train.WGRAD_CONVT2X2)
+    assert rel_l2(dw, w.grad) <= 2e-5, rel_l2(dw, w.grad)
+    db = torch.zeros(co, device=DEV)
+    train.channel_sum(dya, db, co, _s())
+    assert rel_l2(db, b.grad) <= 1e-5
+    if co % 64 == 0:
+        pd = train.pack_convT2x2_dgrad(w.detach().cpu(), DEV, split=True)
+        dx = new_act(N, 1, H, W, xa.C, DEV, split=True)
+        engine.ConvPlan([dya], pd, dx, cout=ci, stride=2).run(_s())
+        assert rel_l2(from_act(dx, ci)[:, :, 0], x.grad) <= 2e-5, rel_l2(from_act(dx, ci)[:, :, 0], x.grad)
+
+
+def test_add_and_maxpool_backward():
+    g = torch.Generator().manual_seed(5)
+    for N, C, H, W in ((2, 64, 32, 32), (3, 128, 4, 2), (1, 1024, 2, 2)):
+        x = torch.randn(N, C, H, W, generator=g)
+        x[:, :, 0, 0] = x[:, :, 0, 1]                       # ties: torch keeps the first maximum in scan order
+        x[:, : C // 2, 1, 0] = x[:, : C // 2, 1, 1] = 9.0
+        xa = to_act(x.to(DEV)[:, :, None], split=True)
+        xr = from_act(xa, C)[:, :, 0].clone().requires_grad_(True)   # the values the kernel sees
+        dy = torch.randn(N, C, H // 2, W // 2, generator=g).to(DEV)
+        F.max_pool2d(xr, 2, 2).backward(dy)
+        dya = to_act(dy[:, :, None], split=True)
+        dxa = new_act(N, 1, H, W, C, DEV, split=True)
+        train.maxpool_bwd(xa, dya, dxa, _s())
+        assert torch.equal(from_act(dxa, C)[:, :, 0], from_act(dya, C)[:, :, 0].repeat_interleave(2, 2).repeat_interleave(2, 3) * (xr.grad != 0))
+        assert rel_l2(from_act(dxa, C)[:, :, 0], xr.grad) <= 1e-5
+        # skip connection: the two gradient paths add
+        o = new_act(N, 1, H, W, C, DEV, split=True)
+        train.add_acts(xa, dxa, o, _s())
+        assert rel_l2(from_act(o, C), from_act(xa, C) + from_act(dxa, C)) <= 1e-5
+
+
+@pytest.mark.parametrize("N,T,C,heads", [(2, 64, 256, 2), (3, 256, 128, 1), (2, 16, 512, 1), (2, 16, 1024, 8), (1, 64, 1024, 2)])
+def test_attention_core_backward(N, T, C, heads):
+    """d(q | k | v) of softmax(q k^T / sqrt(d)) v against torch autograd (fp32)."""
+    no_tf32()
+    g = torch.Generator().manual_seed(T + C + heads)
+    qkv = torch.randn(N, T, 3 * C, generator=g).to(DEV).requires_grad_(True)
+    d_out = (torch.randn(N, T, C, generator=g) * 0.2).to(DEV)
+    d = C // heads
+    q, k, v = [t.reshape(N, T, heads, d).transpose(1, 2) for t in qkv.split(C, dim=2)]
+    out = (torch.softmax(q @ k.transpose(-1, -2) / d ** 0.5, dim=-1) @ v).transpose(1, 2).reshape(N, T, C)
+    out.backward(d_out)
+    cl = lambda t: to_act(t.detach().transpose(1, 2).reshape(N, -1, 1, 1, T), split=True)
+    qa, oa, da = cl(qkv), cl(out), cl(d_out)
+    dq = new_act(N, 1, 1, T, 3 * C, DEV, split=True)
+    train.attention_bwd(qa, oa, da, dq, heads, _s())
+    got = from_act(dq, 3 * C).reshape(N, 3 * C, T).transpose(1, 2)
+    for i, name in enumerate("qkv"):
+        e = rel_l2(got[..., i * C:(i + 1) * C], qkv.grad[..., i * C:(i + 1) * C])
+        assert e <= 2e-5, (name, e)
+
+
 @pytest.mark.parametrize("N,segs,cmid,cout,H", [(3, [128], 128, 128, 16), (2, [64, 64], 64, 64, 32), (8, [256], 512, 512, 4), (2, [17], 64, 64, 32)])
 def test_double_block_backward_vs_autograd(N, segs, cmid, cout, H):
     """One DoubleBlock (unet/blocks.py:50-107) forward + backward on the GPU against torch.autograd through the oracle's
