@@ -362,13 +362,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
 // out[c] += sum over rows of x[row][c]   (bias gradients: Conv2d / ConvTranspose2d / Linear bias = sum of dY over pixels)
 __global__ void __launch_bounds__(256) channel_sum_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int f16,
                                                           long long rows, int C, int cvalid, float* __restrict__ out) {
-  // blockDim.x = 256 threads: thread -> channel (c = tid % Cb), row group (tid / Cb), Cb = min(C, 256)
+  // 256 threads: thread -> (channel c0 + tid % Cb, row group tid / Cb), Cb = min(C, 256); leftover threads idle
   const int Cb = C < 256 ? C : 256;
-  const int rg = blockDim.x / Cb;
-  for (int c0 = 0; c0 < C; c0 += Cb) {
-    const int c = c0 + (int)(threadIdx.x % Cb);
-    const int r0 = (int)(threadIdx.x / Cb);
-    if (r0 >= rg || c >= cvalid) continue;
+  const int rg = 256 / Cb;
+  const int r0 = (int)threadIdx.x / Cb;
+  if (r0 >= rg) return;
+  for (int c0 = 0; c0 < cvalid; c0 += Cb) {
+    const int c = c0 + (int)threadIdx.x % Cb;
+    if (c >= cvalid) continue;
     float acc = 0.f;
     for (long long r = (long long)blockIdx.x * rg + r0; r < rows; r += (long long)gridDim.x * rg) acc += ld16x(hi, lo, r * C + c, f16);
     atomicAdd(out + c, acc);
@@ -445,7 +446,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdArgs a) {
     for (int i = threadIdx.x; i < kAbR * d; i += 256) {
       const int r = i / d, k = i - r * d;
       float v;
-      if (which < 3) v = ld16x(qh, ql, (long long)(row0 + r) * qkv_row + which * C + k, a.f16);
+      if (row0 + r >= T) v = 0.f;   // ragged T (2 x 2 maps): rows past the end are zero and masked below
+      else if (which < 3) v = ld16x(qh, ql, (long long)(row0 + r) * qkv_row + which * C + k, a.f16);
       else if (which == 3) v = ld16x(a.do_hi, a.do_lo, obase + (long long)(row0 + r) * C + k, a.f16);
       else v = ld16x(a.o_hi, a.o_lo, obase + (long long)(row0 + r) * C + k, a.f16);
       dst[r * ld + k] = v;
@@ -458,7 +460,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdArgs a) {
   for (int i = 0; i < 32; ++i) acc1[i] = acc2[i] = 0.f;
   float run_m = -INFINITY, run_l = 0.f;
   float lse_own = 0.f, d_own = 0.f;
-  if (MODE == 1) { lse_own = st[(r0 + ta) * 2]; d_own = st[(r0 + ta) * 2 + 1]; }
+  const bool own_ok = r0 + ta < T;
+  if (MODE == 1 && own_ok) { lse_own = st[(r0 + ta) * 2]; d_own = st[(r0 + ta) * 2 + 1]; }
   for (int o0 = 0; o0 < T; o0 += kAbR) {
     __syncthreads();
     if (MODE == 2) { load_rows(oth1, 0, o0); load_rows(oth2, 3, o0); }
@@ -470,7 +473,9 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdArgs a) {
       if (MODE != 0) dp = fmaf(own2[ta * ld + k], oth2[tb * ld + k], dp);
     }
     s *= a.scale;
+    const bool oth_ok = o0 + tb < T;
     if (MODE == 0) {
+      if (!oth_ok) s = -INFINITY;
       float m = s;
       for (int off = 8; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
       const float nm = fmaxf(run_m, m);
@@ -480,8 +485,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdArgs a) {
       run_m = nm;
     } else {
       float lse = lse_own, dd = d_own;
-      if (MODE == 2) { lse = st[(o0 + tb) * 2]; dd = st[(o0 + tb) * 2 + 1]; }
-      const float pr = expf(s - lse);
+      if (MODE == 2 && oth_ok) { lse = st[(o0 + tb) * 2]; dd = st[(o0 + tb) * 2 + 1]; }
+      const float pr = oth_ok ? expf(s - lse) : 0.f;
       tile_p[ta * 17 + tb] = pr;
       tile_ds[ta * 17 + tb] = pr * (dp - dd) * a.scale;
       __syncthreads();
@@ -507,8 +512,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdArgs a) {
     float dd = 0.f;
     for (int k = tb; k < d; k += 16) dd = fmaf(own2[ta * ld + k], oth1[ta * ld + k], dd);
     for (int off = 8; off; off >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, off);
-    if (tb == 0) { st[(r0 + ta) * 2] = run_m + logf(run_l); st[(r0 + ta) * 2 + 1] = dd; }
-  } else {
+    if (tb == 0 && own_ok) { st[(r0 + ta) * 2] = run_m + logf(run_l); st[(r0 + ta) * 2 + 1] = dd; }
+  } else if (own_ok) {
     uint16_t* oh = a.dqkv_hi + (long long)n * T * qkv_row + h * d + (long long)(r0 + ta) * qkv_row;
     uint16_t* ol = a.dqkv_lo ? a.dqkv_lo + (long long)n * T * qkv_row + h * d + (long long)(r0 + ta) * qkv_row : nullptr;
 #pragma unroll
@@ -645,8 +650,8 @@ extern "C" int b2d_conv_wgrad(int32_t kind, const void* dy_hi, const void* dy_lo
 }
 
 extern "C" int b2d_channel_sum(const void* x_hi, const void* x_lo, int32_t f16, int64_t rows, int32_t C, int32_t cvalid, float* out, void* stream) {
-  if (!x_hi || !out || rows < 1 || C < 1 || cvalid < 1 || cvalid > C || (C > 256 && (C % 256)) || (C <= 256 && (256 % C)) || (f16 && x_lo))
-    return set_error(B2D_E_INVALID, "b2d_channel_sum: bad argument (C must divide 256 or be a multiple of it)");
+  if (!x_hi || !out || rows < 1 || C < 1 || cvalid < 1 || cvalid > C || (f16 && x_lo))
+    return set_error(B2D_E_INVALID, "b2d_channel_sum: bad argument");
   const int rg = C < 256 ? 256 / C : 1;
   channel_sum_kernel<<<grid_cap((rows + rg - 1) / rg, 8), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x_hi, (const uint16_t*)x_lo, f16 ? 1 : 0,
                                                                                        (long long)rows, C, cvalid, out);
@@ -673,7 +678,7 @@ extern "C" int b2d_maxpool2x2_bwd(const void* x_hi, const void* x_lo, const void
 
 extern "C" int b2d_attention_bwd(const void* qkv, const void* qkv_lo, const void* out, const void* out_lo, const void* dout, const void* dout_lo,
                                  void* dqkv, void* dqkv_lo, float* stats, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t f16, void* stream) {
-  if (!qkv || !out || !dout || !dqkv || !stats || N < 1 || T < 16 || (T % 16) || heads < 1 || C < 16 || (C % heads) || (f16 && (qkv_lo || dqkv_lo)))
+  if (!qkv || !out || !dout || !dqkv || !stats || N < 1 || T < 1 || heads < 1 || C < 16 || (C % heads) || (f16 && (qkv_lo || dqkv_lo)))
     return set_error(B2D_E_INVALID, "b2d_attention_bwd: bad argument");
   const int d = C / heads;
   if ((d % 16) || d > 512) return set_error(B2D_E_UNSUPPORTED, "b2d_attention_bwd: head dim %d (need a multiple of 16, <= 512)", d);
@@ -688,7 +693,7 @@ extern "C" int b2d_attention_bwd(const void* qkv, const void* qkv_lo, const void
   if (e == cudaSuccess) e = smem_attr_once(attn_bwd_kernel<1>, 200 * 1024, c1);
   if (e == cudaSuccess) e = smem_attr_once(attn_bwd_kernel<2>, 200 * 1024, c2);
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "b2d_attention_bwd: smem attr: %s", cudaGetErrorString(e));
-  const dim3 grid(T / kAbR, heads, N);
+  const dim3 grid((T + kAbR - 1) / kAbR, heads, N);
   attn_bwd_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   attn_bwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   attn_bwd_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(a);

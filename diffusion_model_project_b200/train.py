@@ -177,11 +177,11 @@ class DoubleBlockGrad:
     parameter tensors: conv{1,2}.weight [C, Cin, 3, 3] (no bias), norm{1,2}.{weight, bias}; `temb` (N, Cmid) is the per-sample
     time embedding added after block1 (blocks.py:100-103).  Inputs may be a channel concatenation (decoder blocks)."""
 
-    def __init__(self, w1, g1, b1, w2, g2, b2, seg_sizes: Sequence[int], device="cuda"):
+    def __init__(self, w1, g1, b1, w2, g2, b2, seg_sizes: Sequence[int], device="cuda", workspace: Optional[torch.Tensor] = None):
         dev = torch.device(device)
         self.dev = dev
         self.seg_sizes = list(seg_sizes)
-        self.w1, self.w2 = w1.detach().float().cpu(), w2.detach().float().cpu()
+        self.w1, self.w2 = w1.detach().float(), w2.detach().float()
         self.cmid, self.cout = w1.shape[0], w2.shape[0]
         f = lambda t: t.detach().to(dev, torch.float32).contiguous()
         self.g1, self.b1, self.g2, self.b2 = f(g1), f(b1), f(g2), f(b2)
@@ -194,10 +194,11 @@ class DoubleBlockGrad:
             # 17 input channels and needs none: its input is data)
             self.pd1.append(pack_conv2d_dgrad(self.w1, (c0, c0 + cs), dev, split=True) if cs % 64 == 0 else None)
             c0 += cs
-        self.ws = engine.new_workspace(dev)
+        self.ws = workspace if workspace is not None else engine.new_workspace(dev)
         self.saved = None
 
-    def forward(self, inputs: Sequence[Act], temb: Optional[torch.Tensor] = None) -> Act:
+    def forward(self, inputs: Sequence[Act], temb: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None) -> Act:
+        """stats_out: (N, 2) fp64, receives (sum, sumsq) of the block's output (the next layer's GroupNorm statistics)."""
         N, D, H, W, _ = inputs[0].shape
         dev, s = self.dev, _lib.stream_ptr()
         st1 = torch.zeros(N, 2, dtype=torch.float64, device=dev)
@@ -211,7 +212,7 @@ class DoubleBlockGrad:
         tt = None if temb is None else temb.to(dev, torch.float32).contiguous()
         engine.gn_apply(raw1, a1, st1, self.cmid, self.g1, self.b1, True, s, temb=tt, temb_row=row, temb_row_stride=1)
         ConvPlan([a1], self.pw2, raw2, cout=self.cout, stats=st2, stats_cpg=self.cout, workspace=self.ws).run(s)
-        engine.gn_apply(raw2, out, st2, self.cout, self.g2, self.b2, True, s)
+        engine.gn_apply(raw2, out, st2, self.cout, self.g2, self.b2, True, s, stats_out=stats_out)
         self.saved = (list(inputs), raw1, st1, a1, raw2, st2, temb is not None)
         return out
 
@@ -244,3 +245,304 @@ class DoubleBlockGrad:
             c0 += cs
         g["inputs"] = d_inputs
         return g
+
+
+class AttentionGrad:
+    """Forward + backward of SelfAttention2d (unet/blocks.py:170-235): y = x + proj_out(out_proj(softmax(q k^T / sqrt(d)) v)),
+    (q | k | v) = in_proj(GroupNorm(1, C)(x)).  The two C x C output projections run folded (W = Wp Wo, b = Wp bo + bp) as in
+    the sampling path; their separate gradients follow from the folded ones by C x C parameter-space products."""
+
+    def __init__(self, c: int, heads: int, p: Dict[str, torch.Tensor], device="cuda", workspace: Optional[torch.Tensor] = None):
+        dev = torch.device(device)
+        f = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        self.dev, self.c, self.heads = dev, c, heads
+        self.g, self.b = f(p["norm.weight"]), f(p["norm.bias"])
+        self.w_in, self.b_in = f(p["mha.in_proj_weight"]), f(p["mha.in_proj_bias"])
+        self.wo, self.bo = f(p["mha.out_proj.weight"]), f(p["mha.out_proj.bias"])
+        self.wp, self.bp = f(p["proj_out.weight"])[:, :, 0], f(p["proj_out.bias"])
+        w_out = (self.wp.double() @ self.wo.double()).float()
+        b_out = (self.wp.double() @ self.bo.double() + self.bp.double()).float()
+        self.p_in = engine.pack_linear(self.w_in, self.b_in, dev, split=True)
+        self.p_out = engine.pack_linear(w_out, b_out, dev, split=True)
+        self.p_in_t = engine.pack_linear(self.w_in.t().contiguous(), None, dev, split=True)
+        self.p_out_t = engine.pack_linear(w_out.t().contiguous(), None, dev, split=True)
+        self.ws = workspace if workspace is not None else engine.new_workspace(dev)
+        self.saved = None
+
+    def forward(self, x: Act, st_x: torch.Tensor) -> Act:
+        """st_x: (N, 2) fp64 (sum, sumsq) of x per sample."""
+        N, D, H, W, c = x.shape
+        dev, s = self.dev, _lib.stream_ptr()
+        xn = new_act(N, 1, H, W, c, dev, split=True)
+        engine.gn_apply(x, xn, st_x, c, self.g, self.b, False, s)
+        qkv = new_act(N, 1, H, W, 3 * c, dev, split=True)
+        ConvPlan([xn], self.p_in, qkv, cout=3 * c, workspace=self.ws).run(s)
+        ao = new_act(N, 1, H, W, c, dev, split=True)
+        call("b2d_attention", ptr(qkv.hi), ptr(qkv.lo), ptr(ao.hi), ptr(ao.lo), N, H * W, c, self.heads, 0, s)
+        y = new_act(N, 1, H, W, c, dev, split=True)
+        ConvPlan([ao], self.p_out, y, cout=c, residual=x, workspace=self.ws).run(s)
+        self.saved = (x, st_x, xn, qkv, ao)
+        return y
+
+    def backward(self, d_y: Act) -> Tuple[dict, Act]:
+        x, st_x, xn, qkv, ao = self.saved
+        N, D, H, W, c = x.shape
+        dev, s = self.dev, _lib.stream_ptr()
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        d_wout, d_bout = z(c, c), z(c)
+        conv_wgrad(d_y, ao, d_wout, c, c, 0, s, kind=WGRAD_LINEAR)
+        channel_sum(d_y, d_bout, c, s)
+        d_ao = new_act(N, 1, H, W, c, dev, split=True)
+        ConvPlan([d_y], self.p_out_t, d_ao, cout=c, workspace=self.ws).run(s)
+        d_qkv = new_act(N, 1, H, W, 3 * c, dev, split=True)
+        attention_bwd(qkv, ao, d_ao, d_qkv, self.heads, s)
+        g = {"mha.in_proj_weight": z(3 * c, c), "mha.in_proj_bias": z(3 * c), "norm.weight": z(c), "norm.bias": z(c)}
+        conv_wgrad(d_qkv, xn, g["mha.in_proj_weight"], 3 * c, c, 0, s, kind=WGRAD_LINEAR)
+        channel_sum(d_qkv, g["mha.in_proj_bias"], 3 * c, s)
+        d_xn = new_act(N, 1, H, W, c, dev, split=True)
+        ConvPlan([d_qkv], self.p_in_t, d_xn, cout=c, workspace=self.ws).run(s)
+        d_x = new_act(N, 1, H, W, c, dev, split=True)
+        gn_silu_bwd(x, d_xn, d_x, st_x, self.g, self.b, False, g["norm.weight"], g["norm.bias"], None, s)
+        add_acts(d_x, d_y, d_x, s)
+        # W = Wp Wo, b = Wp bo + bp  ->  dWp = dW Wo^T + db bo^T, dWo = Wp^T dW, dbo = Wp^T db, dbp = db
+        dW, db = d_wout.double(), d_bout.double()
+        g["proj_out.weight"] = (dW @ self.wo.double().t() + torch.outer(db, self.bo.double())).float()[:, :, None]
+        g["proj_out.bias"] = d_bout
+        g["mha.out_proj.weight"] = (self.wp.double().t() @ dW).float()
+        g["mha.out_proj.bias"] = (self.wp.double().t() @ db).float()
+        return g, d_x
+
+
+class UNetTrainer:
+    """One optimisation step of the conditioned eps-prediction UNet (helper.py:420-431, predictor.py:722-748):
+
+        x_t = q_sample(x_start, t, noise);  pred = UNet(cat[x_t, cond, feats], t);  loss = criterion(pred, noise)
+        loss.backward();  optimizer.step()                                     (torch.optim.Adam, train.py:144-148)
+
+    in the fp32-class mode (bf16 hi + lo operands, three MMA passes): every layer's forward saves what its backward needs,
+    the backward walks the UNet (unet/models.py:131-188) in reverse -- final_conv, decoder levels (attention, DoubleBlock over
+    cat[skip, up], ConvTranspose2d + GroupNorm + SiLU), bottleneck, encoder levels (max-pool + GroupNorm + SiLU, attention,
+    DoubleBlock) -- writing each parameter's gradient into FlatAdam's flat buffer, which one launch then applies.
+    The sinusoid -> time_mlp -> per-block Linear chain ((N, 64) -> (N, 256) -> (N, Cmid): a few kFLOP) is evaluated and
+    differentiated with torch ops on the GPU; everything that touches a feature map is libb2d."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], *, in_channels=17, out_channels=8, features=(64, 128, 256, 512, 1024),
+                 attention: str = "", time_embedding_dim: Optional[int] = 64, num_timesteps: int = 1000, lr: float = 1e-4,
+                 weight_decay: float = 0.0, device="cuda", **_ignored):
+        from .scheduler import B200Scheduler
+        from .synth import attention_heads
+        if not torch.cuda.is_available():
+            raise RuntimeError("UNetTrainer runs on a CUDA device only (no CPU fallback)")
+        self.dev = torch.device(device)
+        self.in_channels, self.out_channels, self.features = in_channels, out_channels, list(features)
+        self.time_dim = time_embedding_dim
+        self.heads = attention_heads(attention, len(self.features))
+        self.opt = FlatAdam(state_dict, lr=lr, weight_decay=weight_decay, device=self.dev)
+        self.scheduler = B200Scheduler(num_timesteps=num_timesteps, device=self.dev)
+        self.ws = engine.new_workspace(self.dev)
+        self._layers = None
+
+    # -------------------------------------------------------------------------------- parameters
+    def P(self, name: str) -> torch.Tensor:
+        return self.opt.view(self.opt.param, name)
+
+    def G(self, name: str) -> torch.Tensor:
+        return self.opt.view(self.opt.grad, name)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return self.opt.state_dict()
+
+    def _sub(self, prefix: str, names: Sequence[str]) -> Dict[str, torch.Tensor]:
+        return {n: self.P(f"{prefix}.{n}") for n in names}
+
+    _ATTN = ("norm.weight", "norm.bias", "mha.in_proj_weight", "mha.in_proj_bias", "mha.out_proj.weight", "mha.out_proj.bias",
+             "proj_out.weight", "proj_out.bias")
+
+    def _build_layers(self):
+        """Operand forms of the current parameters (repacked after every optimizer step)."""
+        dev, ws, f = self.dev, self.ws, self.features
+        L = {}
+
+        def double(p, segs):
+            L[p] = DoubleBlockGrad(self.P(f"{p}.block1.conv.weight"), self.P(f"{p}.block1.norm.weight"), self.P(f"{p}.block1.norm.bias"),
+                                   self.P(f"{p}.block2.conv.weight"), self.P(f"{p}.block2.norm.weight"), self.P(f"{p}.block2.norm.bias"),
+                                   segs, dev, workspace=ws)
+
+        cin = self.in_channels
+        for lvl, c in enumerate(f):
+            double(f"encoder.{lvl}.0", [cin])
+            if self.heads[lvl] is not None:
+                L[f"encoder.{lvl}.1"] = AttentionGrad(c, self.heads[lvl], self._sub(f"encoder.{lvl}.1", self._ATTN), dev, ws)
+            cin = c
+        double("bottleneck", [f[-1]])
+        rheads = list(reversed(self.heads))
+        for lvl, c in enumerate(reversed(f)):
+            w = self.P(f"decoder.{lvl}.0.conv.weight")
+            L[f"decoder.{lvl}.0"] = (engine.pack_convT2x2(w, self.P(f"decoder.{lvl}.0.conv.bias"), dev, split=True),
+                                     pack_convT2x2_dgrad(w, dev, split=True))
+            double(f"decoder.{lvl}.1", [c, c])
+            if rheads[lvl] is not None:
+                L[f"decoder.{lvl}.2"] = AttentionGrad(c, rheads[lvl], self._sub(f"decoder.{lvl}.2", self._ATTN), dev, ws)
+        wf = self.P("final_conv.weight")
+        L["final_conv"] = (engine.pack_conv2d(wf, [f[0]], self.P("final_conv.bias"), dev, split=True),
+                           pack_conv2d_dgrad(wf, (0, f[0]), dev, split=True))
+        self._layers = L
+
+    # -------------------------------------------------------------------------------- time embedding chain (torch, tiny)
+    def _time_names(self):
+        nl = len(self.features)
+        return [f"encoder.{l}.0" for l in range(nl)] + ["bottleneck"] + [f"decoder.{l}.1" for l in range(nl)]
+
+    def _time_forward(self, t: torch.Tensor):
+        import math
+        import torch.nn.functional as F
+        leaves = {}
+
+        def leaf(name):
+            leaves[name] = self.P(name).detach().clone().requires_grad_(True)
+            return leaves[name]
+
+        with torch.enable_grad():
+            half = self.time_dim // 2
+            fr = torch.exp(torch.arange(half, device=self.dev, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+            e = t.to(self.dev, torch.float32)[:, None] * fr[None, :]
+            emb = torch.cat((e.sin(), e.cos()), dim=-1)                                  # models.py:14-26
+            emb = F.linear(emb, leaf("time_mlp.0.weight"), leaf("time_mlp.0.bias"))      # models.py:78-82
+            emb = F.linear(F.silu(emb), leaf("time_mlp.2.weight"), leaf("time_mlp.2.bias"))
+            a = F.silu(emb)                                                              # blocks.py:92-95
+            temb = {p: F.linear(a, leaf(f"{p}.time_mlp.1.weight"), leaf(f"{p}.time_mlp.1.bias")) for p in self._time_names()}
+        return temb, leaves
+
+    # -------------------------------------------------------------------------------- forward + backward
+    def forward_backward(self, x: torch.Tensor, t: torch.Tensor, target: torch.Tensor):
+        """x: (N, in_channels, h, w) fp32 on the GPU, t: (N,) timesteps, target: (N, out_channels, h, w).  Fills the flat
+        gradient buffer; returns (loss, pred)."""
+        if self._layers is None:
+            self._build_layers()
+        L, dev, f, s = self._layers, self.dev, self.features, _lib.stream_ptr()
+        N, _, h, w = x.shape
+        nl = len(f)
+        if h % (1 << nl) or w % (1 << nl):
+            raise ValueError(f"UNetTrainer: input {h}x{w} must be divisible by {1 << nl}")
+        self.opt.zero_grad()
+        z2 = lambda: torch.zeros(N, 2, dtype=torch.float64, device=dev)
+        temb, leaves = self._time_forward(t) if self.time_dim is not None else ({}, {})
+        x_in = new_act(N, 1, h, w, engine.pad64(self.in_channels), dev, split=True, zero=True)
+        engine.planar_to_cl(x.contiguous().float(), x_in, N, self.in_channels, h * w, 0, None, s)
+        # ---- forward (models.py:144-186)
+        a, H, Wd = x_in, h, w
+        skips, pools = [], []
+        for lvl, c in enumerate(f):
+            p = f"encoder.{lvl}.0"
+            st = z2() if self.heads[lvl] is not None else None
+            a = L[p].forward([a], temb.get(p).detach() if p in temb else None, stats_out=st)
+            if st is not None:
+                a = L[f"encoder.{lvl}.1"].forward(a, st)
+            skips.append(a)
+            praw = new_act(N, 1, H // 2, Wd // 2, c, dev, split=True)
+            pst = z2()
+            engine.maxpool_stats(a, praw, pst, s)
+            pa = new_act(N, 1, H // 2, Wd // 2, c, dev, split=True)
+            g, b = self.P(f"encoder.{lvl}.2.norm.weight"), self.P(f"encoder.{lvl}.2.norm.bias")
+            engine.gn_apply(praw, pa, pst, c, g, b, True, s)
+            pools.append((a, praw, pst))
+            a, H, Wd = pa, H // 2, Wd // 2
+        a = L["bottleneck"].forward([a], temb["bottleneck"].detach() if temb else None)
+        ups = []
+        rheads = list(reversed(self.heads))
+        for lvl, c in enumerate(reversed(f)):
+            pw, _ = L[f"decoder.{lvl}.0"]
+            raw = new_act(N, 1, 2 * H, 2 * Wd, c, dev, split=True)
+            ust = z2()
+            ConvPlan([a], pw, raw, cout=c, nphase=4, stats=ust, stats_cpg=c, workspace=self.ws).run(s)
+            up = new_act(N, 1, 2 * H, 2 * Wd, c, dev, split=True)
+            engine.gn_apply(raw, up, ust, c, self.P(f"decoder.{lvl}.0.norm.weight"), self.P(f"decoder.{lvl}.0.norm.bias"), True, s)
+            ups.append((a, raw, ust))
+            H, Wd = 2 * H, 2 * Wd
+            p = f"decoder.{lvl}.1"
+            st = z2() if rheads[lvl] is not None else None
+            a = L[p].forward([skips[nl - 1 - lvl], up], temb.get(p).detach() if p in temb else None, stats_out=st)
+            if st is not None:
+                a = L[f"decoder.{lvl}.2"].forward(a, st)
+        pred = torch.empty(N, self.out_channels, h, w, dtype=torch.float32, device=dev)
+        ConvPlan([a], L["final_conv"][0], pred, cout=self.out_channels, out_mode=1, out_cstride=self.out_channels, workspace=self.ws).run(s)
+        final_in = a
+        # ---- criterion (metrics.py:337-402)
+        loss, _, d_pred = nmse_loss(pred, target.to(dev))
+        # ---- backward
+        d_temb = {}
+        oc, c0 = self.out_channels, f[0]
+        d = new_act(N, 1, h, w, engine.pad64(oc), dev, split=True, zero=True)
+        engine.planar_to_cl(d_pred, d, N, oc, h * w, 0, None, s)
+        channel_sum(d, self.G("final_conv.bias"), oc, s)
+        conv_wgrad(d, final_in, self.G("final_conv.weight"), oc, c0, 0, s)
+        da = new_act(N, 1, h, w, c0, dev, split=True)
+        ConvPlan([d], L["final_conv"][1], da, cout=c0, workspace=self.ws).run(s)
+        d_skips = [None] * nl
+
+        def take_double(p, g):
+            self.G(f"{p}.block1.conv.weight").copy_(g["conv1.weight"])
+            self.G(f"{p}.block2.conv.weight").copy_(g["conv2.weight"])
+            for i in (1, 2):
+                self.G(f"{p}.block{i}.norm.weight").copy_(g[f"norm{i}.weight"])
+                self.G(f"{p}.block{i}.norm.bias").copy_(g[f"norm{i}.bias"])
+            if g["temb"] is not None:
+                d_temb[p] = g["temb"]
+
+        def take_attention(p, g):
+            for k, v in g.items():
+                self.G(f"{p}.{k}").copy_(v)
+
+        for lvl in reversed(range(nl)):
+            c = list(reversed(f))[lvl]
+            if rheads[lvl] is not None:
+                g, da = L[f"decoder.{lvl}.2"].backward(da)
+                take_attention(f"decoder.{lvl}.2", g)
+            g = L[f"decoder.{lvl}.1"].backward(da)
+            take_double(f"decoder.{lvl}.1", g)
+            d_skips[nl - 1 - lvl], d_up = g["inputs"]
+            x_lo, raw, ust = ups[lvl]
+            Nn, _, H2, W2, _ = raw.shape
+            d_raw = new_act(N, 1, H2, W2, c, dev, split=True)
+            gn_silu_bwd(raw, d_up, d_raw, ust, self.P(f"decoder.{lvl}.0.norm.weight"), self.P(f"decoder.{lvl}.0.norm.bias"), True,
+                        self.G(f"decoder.{lvl}.0.norm.weight"), self.G(f"decoder.{lvl}.0.norm.bias"), None, s)
+            conv_wgrad(d_raw, x_lo, self.G(f"decoder.{lvl}.0.conv.weight"), c, 2 * c, 0, s, kind=WGRAD_CONVT2X2)
+            channel_sum(d_raw, self.G(f"decoder.{lvl}.0.conv.bias"), c, s)
+            da = new_act(N, 1, H2 // 2, W2 // 2, 2 * c, dev, split=True)
+            ConvPlan([d_raw], L[f"decoder.{lvl}.0"][1], da, cout=2 * c, stride=2, workspace=self.ws).run(s)
+        g = L["bottleneck"].backward(da)
+        take_double("bottleneck", g)
+        da = g["inputs"][0]
+        for lvl in reversed(range(nl)):
+            c = f[lvl]
+            skip, praw, pst = pools[lvl]
+            d_praw = new_act(*praw.shape, dev, split=True)
+            gn_silu_bwd(praw, da, d_praw, pst, self.P(f"encoder.{lvl}.2.norm.weight"), self.P(f"encoder.{lvl}.2.norm.bias"), True,
+                        self.G(f"encoder.{lvl}.2.norm.weight"), self.G(f"encoder.{lvl}.2.norm.bias"), None, s)
+            da = new_act(*skip.shape, dev, split=True)
+            maxpool_bwd(skip, d_praw, da, s)
+            add_acts(da, d_skips[lvl], da, s)
+            if self.heads[lvl] is not None:
+                g, da = L[f"encoder.{lvl}.1"].backward(da)
+                take_attention(f"encoder.{lvl}.1", g)
+            g = L[f"encoder.{lvl}.0"].backward(da)
+            take_double(f"encoder.{lvl}.0", g)
+            da = g["inputs"][0]
+        if temb:
+            names = list(d_temb.keys())
+            torch.autograd.backward([temb[p] for p in names], [d_temb[p] for p in names])
+            for k, v in leaves.items():
+                self.G(k).copy_(v.grad)
+        return loss, pred
+
+    def training_step(self, x_start: torch.Tensor, cond: torch.Tensor, feats: torch.Tensor, t: torch.Tensor, noise: torch.Tensor,
+                      group=None):
+        """q_sample -> forward -> loss -> backward -> (gradient all-reduce) -> Adam.  Returns (loss, pred)."""
+        dev = self.dev
+        x_t = self.scheduler.q_sample(x_start.to(dev), t.to(dev), noise.to(dev))            # diffusion.py:78-101
+        x = torch.cat([x_t, cond.to(dev), feats.to(dev)], dim=1)                             # predictor.py:731-741
+        loss, pred = self.forward_backward(x, t, noise.to(dev))
+        scale = self.opt.allreduce_gradients(group)
+        self.opt.step(grad_scale=scale)
+        self._layers = None  # operands are stale now
+        return loss, pred

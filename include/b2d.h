@@ -288,7 +288,7 @@ B2D_API int b2d_conv_wgrad(int32_t kind, const void* dy_hi, const void* dy_lo, i
                    int32_t cin_pad, int32_t N, int32_t H, int32_t W, int32_t cout, int32_t cin, int32_t cin_off, int32_t cin_total,
                    float* dw, int32_t op_f16, void* stream);
 /* out[c] += sum over rows of x[row][c], c < cvalid (bias gradients = sum of dY over pixels); x [rows][C] 16-bit hi (+ lo),
- * C a divisor or a multiple of 256. */
+ * atomically accumulated (zero it first). */
 B2D_API int b2d_channel_sum(const void* x_hi, const void* x_lo, int32_t f16, int64_t rows, int32_t C, int32_t cvalid, float* out, void* stream);
 /* o = a + b on 16-bit hi (+ lo) tensors of n elements: the two gradient paths of a skip connection (unet/models.py:150-177). */
 B2D_API int b2d_add16(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* o_hi, void* o_lo, int32_t f16, int64_t n,
@@ -300,7 +300,7 @@ B2D_API int b2d_maxpool2x2_bwd(const void* x_hi, const void* x_lo, const void* d
 
 /* Backward of b2d_attention's core: given qkv, the forward output out and d loss / d out (all channels-last 16-bit hi + lo
  * as in b2d_attention), writes dqkv [N][T][3C] (dq | dk | dv).  fp32 CUDA-core arithmetic; stats: [N][heads][T][2] fp32
- * scratch (log-sum-exp and dO.O per query row).  T a multiple of 16, head dim a multiple of 16 and <= 512. */
+ * scratch (log-sum-exp and dO.O per query row).  Any T; head dim a multiple of 16 and <= 512. */
 B2D_API int b2d_attention_bwd(const void* qkv, const void* qkv_lo, const void* out, const void* out_lo, const void* dout, const void* dout_lo,
                       void* dqkv, void* dqkv_lo, float* stats, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t f16, void* stream);
 

@@ -178,7 +178,7 @@ def test_add_and_maxpool_backward():
         assert rel_l2(from_act(o, C), from_act(xa, C) + from_act(dxa, C)) <= 1e-5
 
 
-@pytest.mark.parametrize("N,T,C,heads", [(2, 64, 256, 2), (3, 256, 128, 1), (2, 16, 512, 1), (2, 16, 1024, 8), (1, 64, 1024, 2)])
+@pytest.mark.parametrize("N,T,C,heads", [(2, 64, 256, 2), (3, 256, 128, 1), (2, 16, 512, 1), (2, 16, 1024, 8), (1, 64, 1024, 2), (3, 4, 1024, 2), (2, 40, 128, 4)])
 def test_attention_core_backward(N, T, C, heads):
     """d(q | k | v) of softmax(q k^T / sqrt(d)) v against torch autograd (fp32)."""
     no_tf32()
@@ -244,3 +244,54 @@ def test_double_block_backward_vs_autograd(N, segs, cmid, cout, H):
         else:
             assert dx is None
         c0 += cs
+
+
+def _train_inputs(golden_dir):
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("make_train_golden", os.path.join(golden_dir, "make_train_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    saved = list(sys.path)
+    try:
+        spec.loader.exec_module(mod)   # train_inputs() / FULL only: the reference is not imported at module level
+    finally:
+        sys.path[:] = saved
+    return mod
+
+
+def test_unet_training_step_vs_reference(golden_dir):
+    """The whole training step (q_sample -> UNet -> criterion -> backward -> Adam) on the GPU against (a) the golden vectors
+    of the unmodified reference: loss, eps-prediction, the norm of every one of the 172 parameter gradients, nine full
+    gradient tensors and their post-Adam parameter deltas; (b) every gradient tensor of the oracle's autograd restatement
+    (itself pinned to the same golden file by tests/test_oracle_golden.py)."""
+    no_tf32()
+    mod = _train_inputs(golden_dir)
+    g = _golden(golden_dir)
+    sd = synth.synth_unet_state(seed=0)
+    x_start, cond, feats, noise, t = mod.train_inputs()
+    tr = train.UNetTrainer(sd, **synth.UNET_KWARGS, lr=1e-4, weight_decay=0.0, device=DEV)
+    before = {k: v.clone() for k, v in tr.state_dict().items()}
+    loss, pred = tr.training_step(x_start, cond, feats, t, noise)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"])), (loss.item(), float(g["loss"]))
+    assert rel_err(pred.cpu(), torch.from_numpy(g["pred"])) <= 1e-4
+    names = [str(n) for n in g["grad_names"]]
+    assert set(names) == set(tr.opt.names)
+    worst = 0.0
+    for n, ref_norm in zip(names, g["grad_norms"]):
+        got = float(tr.G(n).double().norm())
+        worst = max(worst, abs(got - ref_norm) / max(ref_norm, 1e-6))
+        assert abs(got - ref_norm) <= 2e-3 * max(ref_norm, 1e-6), (n, got, ref_norm)
+    for k in mod.FULL:
+        ref_g = torch.from_numpy(g[f"grad::{k}"])
+        assert rel_l2(tr.G(k).cpu(), ref_g) <= 2e-3, (k, rel_l2(tr.G(k).cpu(), ref_g))
+        ref_d = torch.from_numpy(g[f"delta::{k}"])
+        got_d = (tr.state_dict()[k] - before[k]).cpu()
+        # Adam's first step moves every weight by ~lr * sign(g); entries whose gradient is ~0 flip on rounding noise
+        big = ref_g.abs() > 1e-3 * ref_g.abs().max()
+        assert (got_d - ref_d)[big].abs().max().item() <= 2e-6, k
+    _, ograds, _ = otrain.training_loss_and_grads(sd, x_start, cond, feats, t, noise)
+    for n in names:
+        e = rel_l2(tr.G(n).cpu(), ograds[n])
+        assert e <= 2e-3, (n, e)
+    print(f"training step: loss {loss.item():.6f}, worst gradient-norm deviation {worst:.2e}")
