@@ -31,6 +31,7 @@ for stage in ("e2d", "unet", "d3d"):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
         evs[0].record()
         for i, (_, fn) in enumerate(prog.steps):
+            fn = fn[0] if isinstance(fn, list) else fn   # chunk variants: time the first chunk's binding
             fn(s)
             evs[i + 1].record()
         torch.cuda.synchronize()
@@ -48,6 +49,7 @@ for stage in ("e2d", "unet", "d3d"):
     for n, t in zip(names, acc):
         extra = ""
         fn = dict(prog.steps)[n]
+        fn = fn[0] if isinstance(fn, list) else fn
         owner = getattr(fn, "__self__", None)
         if owner is not None and hasattr(owner, "flops"):
             i2 = owner.info2(); extra = f"  {owner.flops / t / 1e6:7.1f} TFLOP/s  e{i2["engine"]} halo{i2["halo"]} ks{i2["ksplit"]} units{i2["units"]} ctas{i2["ctas"]} bn{i2["block_n"]} kg{i2["kgroups"]}"
