@@ -104,6 +104,7 @@ _SIGNATURES = {
     "b2d_channel_sum": (c_int, [c_void_p, c_void_p, c_i32, c_i64, c_i32, c_i32, c_void_p, c_void_p]),
     "b2d_add16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_void_p]),
     "b2d_maxpool2x2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p]),
+    "b2d_pack_weight": (c_int, [c_void_p, c_i32, c_i32, c_i64, c_i64, c_i32, c_i64, c_i32, c_i64, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_void_p]),
     "b2d_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32,
                                   c_i32, c_i32, c_void_p]),
 }

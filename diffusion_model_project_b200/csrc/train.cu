@@ -408,6 +408,31 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint16_t* x_hi, 
   }
 }
 
+// ------------------------------------------------------------------------------------------- operand refresh
+// After an optimizer step the engine's packed operands ([rows][K] 16-bit, K = kbase + tap * cpad + c; bf16 hi | lo or
+// fp16) are rewritten IN PLACE from the fp32 parameters, so plans (whose TMA descriptors hold the operand addresses) and
+// activation buffers stay valid across steps.  The source is addressed through strides, which covers every form the
+// step uses: forward (rows = Cout), data gradient (rows = Cin, taps mirrored: negative tap stride), transposed
+// matrices, and the phase-major rows of ConvTranspose2d (row = r1 * R2 + r2).
+struct PackArgs {
+  const float* src;
+  uint16_t *hi, *lo;
+  long long sr1, sr2, st, sc, ktot;
+  int R2, ntaps, cs, cpad, f16;
+  long long total;
+};
+__global__ void __launch_bounds__(256) pack_weight_kernel(const PackArgs a) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % a.cs);
+    long long t = i / a.cs;
+    const int tap = (int)(t % a.ntaps);
+    const long long row = t / a.ntaps;
+    const long long r1 = row / a.R2, r2 = row - r1 * a.R2;
+    const float v = a.src[r1 * a.sr1 + r2 * a.sr2 + tap * a.st + c * a.sc];
+    st16x(a.hi, a.lo, row * a.ktot + (long long)tap * a.cpad + c, v, a.f16);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- attention core backward
 // softmax(q k^T / sqrt(d)) v per (image, head) (nn.MultiheadAttention's core, unet/blocks.py:196-227), fp32 CUDA cores:
 // T <= 256 tokens and the layer is ~1% of the step's flops, so exact fp32 arithmetic is worth more here than tensor cores.
@@ -698,4 +723,17 @@ extern "C" int b2d_attention_bwd(const void* qkv, const void* qkv_lo, const void
   attn_bwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   attn_bwd_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   return check_launch("attn_bwd_kernel");
+}
+
+extern "C" int b2d_pack_weight(const float* src, int32_t R1, int32_t R2, int64_t sr1, int64_t sr2, int32_t ntaps, int64_t st, int32_t cs, int64_t sc,
+                               void* dst_hi, void* dst_lo, int64_t ktot, int32_t cpad, int32_t f16, void* stream) {
+  if (!src || !dst_hi || R1 < 1 || R2 < 1 || ntaps < 1 || cs < 1 || cs > cpad || ktot < (int64_t)ntaps * cpad || (f16 && dst_lo))
+    return set_error(B2D_E_INVALID, "b2d_pack_weight: bad argument");
+  PackArgs a;
+  a.src = src; a.hi = (uint16_t*)dst_hi; a.lo = (uint16_t*)dst_lo;
+  a.sr1 = sr1; a.sr2 = sr2; a.st = st; a.sc = sc; a.ktot = ktot;
+  a.R2 = R2; a.ntaps = ntaps; a.cs = cs; a.cpad = cpad; a.f16 = f16 ? 1 : 0;
+  a.total = (long long)R1 * R2 * ntaps * cs;
+  pack_weight_kernel<<<grid_cap(a.total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("pack_weight_kernel");
 }

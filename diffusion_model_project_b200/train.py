@@ -109,9 +109,10 @@ def pack_conv2d_dgrad(w: torch.Tensor, seg: Tuple[int, int], device, split=False
 
 
 def gn_silu_bwd(x: Act, dy: Act, dx: Act, stats: torch.Tensor, gamma, beta, act: bool, dgamma: torch.Tensor, dbeta: torch.Tensor,
-                dtemb: Optional[torch.Tensor], stream: int, eps: float = 1e-5):
+                dtemb: Optional[torch.Tensor], stream: int, eps: float = 1e-5, sums: Optional[torch.Tensor] = None):
     N, D, H, W, C = x.shape
-    sums = torch.empty(N, 2, dtype=torch.float64, device=x.hi.device)
+    if sums is None:
+        sums = torch.empty(N, 2, dtype=torch.float64, device=x.hi.device)
     call("b2d_gn_silu_bwd", ptr(x.hi), ptr(x.lo), 1 if x.f16 else 0, ptr(dy.hi), ptr(dy.lo), 1 if dy.f16 else 0, ptr(dx.hi), ptr(dx.lo),
          1 if dx.f16 else 0, N, D * H * W, C, stats.data_ptr(), ptr(gamma), ptr(beta), float(eps), 1 if act else 0, sums.data_ptr(),
          dgamma.data_ptr(), dbeta.data_ptr(), ptr(dtemb), stream, launches=3)
@@ -154,12 +155,13 @@ def maxpool_bwd(x: Act, dy: Act, dx: Act, stream: int):
     call("b2d_maxpool2x2_bwd", ptr(x.hi), ptr(x.lo), ptr(dy.hi), ptr(dy.lo), ptr(dx.hi), ptr(dx.lo), 1 if x.f16 else 0, N, H, W, C, stream)
 
 
-def attention_bwd(qkv: Act, out: Act, d_out: Act, d_qkv: Act, heads: int, stream: int):
+def attention_bwd(qkv: Act, out: Act, d_out: Act, d_qkv: Act, heads: int, stream: int, stats: Optional[torch.Tensor] = None):
     """Backward of engine's attention core (b2d_attention): d_qkv = (dq | dk | dv)."""
     N, D, H, W, C3 = qkv.shape
     C, T = C3 // 3, D * H * W
     assert out.shape == d_out.shape == (N, D, H, W, C) and d_qkv.shape == qkv.shape
-    stats = torch.empty(N * heads * T * 2, dtype=torch.float32, device=qkv.hi.device)
+    if stats is None:
+        stats = torch.empty(N * heads * T * 2, dtype=torch.float32, device=qkv.hi.device)
     call("b2d_attention_bwd", ptr(qkv.hi), ptr(qkv.lo), ptr(out.hi), ptr(out.lo), ptr(d_out.hi), ptr(d_out.lo), ptr(d_qkv.hi), ptr(d_qkv.lo),
          stats.data_ptr(), N, T, C, heads, 1 if qkv.f16 else 0, stream, launches=3)
 
@@ -172,75 +174,204 @@ def pack_convT2x2_dgrad(w: torch.Tensor, device, split=False, f16=False) -> engi
     return engine.pack_weight(w.permute(0, 2, 3, 1).reshape(ci, 4, co), [co], taps, None, device, split, f16=f16)
 
 
+# ------------------------------------------------------------------------------------------------ step-persistent state
+class LiveOperand:
+    """A packed conv operand (engine.PackedWeight) together with the recipe that rewrites it IN PLACE from its fp32 source
+    parameter (b2d_pack_weight): after an optimizer step `refresh` brings the operand up to date while every plan that
+    holds its address stays valid.  `parts`: one (src, elem_off, R1, R2, sr1, sr2, ntaps, st, cs, sc) per K segment."""
+
+    def __init__(self, pw: engine.PackedWeight, parts):
+        self.pw, self.parts = pw, parts
+
+    def refresh(self, stream: int):
+        pw = self.pw
+        for i, (src, off, R1, R2, sr1, sr2, ntaps, st, cs, sc) in enumerate(self.parts):
+            base = pw.w.data_ptr()
+            lo = base + 2 * pw.kbase_lo[i] if pw.split else None
+            call("b2d_pack_weight", src.data_ptr() + 4 * off, R1, R2, sr1, sr2, ntaps, st, cs, sc, base + 2 * pw.kbase[i], lo, pw.ktot,
+                 pw.cin_pad[i], 1 if pw.f16 else 0, stream)
+
+
+def live_conv2d(w: torch.Tensor, seg_sizes: Sequence[int], bias, device) -> LiveOperand:
+    """Forward operand of Conv2d 3x3, weight [Cout, Cin, 3, 3] (w: a contiguous fp32 view of the parameter)."""
+    co, ci = w.shape[:2]
+    parts, c0 = [], 0
+    for cs in seg_sizes:
+        parts.append((w, c0 * 9, 1, co, 0, ci * 9, 9, 1, cs, 9))
+        c0 += cs
+    return LiveOperand(engine.pack_conv2d(w, seg_sizes, bias, device, split=True), parts)
+
+
+def live_conv2d_dgrad(w: torch.Tensor, seg: Tuple[int, int], device) -> LiveOperand:
+    """Data-gradient operand for input channels [seg0, seg1): rows = Cin of the segment, taps mirrored, columns = Cout."""
+    co, ci = w.shape[:2]
+    c0, c1 = seg
+    return LiveOperand(pack_conv2d_dgrad(w, seg, device, split=True), [(w, c0 * 9 + 8, 1, c1 - c0, 0, 9, 9, -1, co, ci * 9)])
+
+
+def live_linear(w: torch.Tensor, bias, device, transpose=False) -> LiveOperand:
+    """nn.Linear / 1x1 weight [out, in]; transpose: the data-gradient operand [in, out]."""
+    o, i = w.shape
+    if transpose:
+        return LiveOperand(engine.pack_linear(w.t().contiguous(), None, device, split=True), [(w, 0, 1, i, 0, 1, 1, 0, o, i)])
+    return LiveOperand(engine.pack_linear(w, bias, device, split=True), [(w, 0, 1, o, 0, i, 1, 0, i, 1)])
+
+
+def live_convT2x2(w: torch.Tensor, bias, device) -> LiveOperand:
+    """Forward operand of ConvTranspose2d k2 s2, weight [Cin, Cout, 2, 2]: rows (phase, co), columns ci."""
+    ci, co = w.shape[:2]
+    return LiveOperand(engine.pack_convT2x2(w, bias, device, split=True), [(w, 0, 4, co, 1, 4, 1, 0, ci, co * 4)])
+
+
+def live_convT2x2_dgrad(w: torch.Tensor, device) -> LiveOperand:
+    ci, co = w.shape[:2]
+    return LiveOperand(pack_convT2x2_dgrad(w, device, split=True), [(w, 0, 1, ci, 0, co * 4, 4, 1, co, 4)])
+
+
+class StepCache:
+    """Buffers and plans of one training-step shape.  persistent=True: every activation, scratch tensor and conv plan is
+    created on first use and reused by the following steps (accumulators are carved from one pool that `begin_step`
+    clears with a single memset); persistent=False: allocate on every use (stand-alone block tests)."""
+
+    POOL_DOUBLES = 1 << 16
+
+    def __init__(self, device, persistent: bool):
+        self.dev, self.persistent = torch.device(device), persistent
+        self.store: dict = {}
+        self.pool = torch.zeros(self.POOL_DOUBLES, dtype=torch.float64, device=self.dev) if persistent else None
+        self.pool_used = 0
+
+    def get(self, key, make):
+        if not self.persistent:
+            return make()
+        if key not in self.store:
+            self.store[key] = make()
+        return self.store[key]
+
+    def act(self, key, N, H, W, C, zero=False) -> Act:
+        return self.get(key, lambda: new_act(N, 1, H, W, C, self.dev, split=True, zero=zero))
+
+    def empty(self, key, shape, dtype=torch.float32) -> torch.Tensor:
+        return self.get(key, lambda: torch.empty(shape, dtype=dtype, device=self.dev))
+
+    def zeros64(self, key, shape) -> torch.Tensor:
+        """An fp64 accumulator that is zero at the start of every step."""
+        def make():
+            if not self.persistent:
+                return torch.zeros(shape, dtype=torch.float64, device=self.dev)
+            n = 1
+            for d in shape:
+                n *= d
+            assert self.pool_used + n <= self.POOL_DOUBLES
+            t = self.pool[self.pool_used:self.pool_used + n].view(shape)
+            self.pool_used += n
+            return t
+        return self.get(key, make)
+
+    def plan(self, key, make) -> ConvPlan:
+        return self.get(key, make)
+
+    def reset(self):
+        """Forget every buffer and plan (a new batch shape); the accumulator pool is handed out again from a clean state."""
+        self.store.clear()
+        self.pool_used = 0
+        if self.pool is not None:
+            self.pool.zero_()
+
+    def begin_step(self):
+        if self.persistent and self.pool_used:
+            self.pool[:self.pool_used].zero_()
+
+
+def _grad_dest(grads: Optional[dict], key: str, shape, dev) -> torch.Tensor:
+    """Where a parameter gradient accumulates: the caller's (zeroed) destination, else a fresh zero tensor."""
+    if grads is not None and key in grads:
+        return grads[key]
+    return torch.zeros(*shape, dtype=torch.float32, device=dev)
+
+
 class DoubleBlockGrad:
     """Forward + backward of one DoubleBlock (unet/blocks.py:50-107) in the fp32-class mode, from the reference's own
     parameter tensors: conv{1,2}.weight [C, Cin, 3, 3] (no bias), norm{1,2}.{weight, bias}; `temb` (N, Cmid) is the per-sample
     time embedding added after block1 (blocks.py:100-103).  Inputs may be a channel concatenation (decoder blocks)."""
 
-    def __init__(self, w1, g1, b1, w2, g2, b2, seg_sizes: Sequence[int], device="cuda", workspace: Optional[torch.Tensor] = None):
+    def __init__(self, w1, g1, b1, w2, g2, b2, seg_sizes: Sequence[int], device="cuda", workspace: Optional[torch.Tensor] = None,
+                 cache: Optional[StepCache] = None, name: str = "double"):
         dev = torch.device(device)
-        self.dev = dev
+        self.dev, self.name = dev, name
         self.seg_sizes = list(seg_sizes)
-        self.w1, self.w2 = w1.detach().float(), w2.detach().float()
-        self.cmid, self.cout = w1.shape[0], w2.shape[0]
         f = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        self.w1, self.w2 = f(w1), f(w2)
+        self.cmid, self.cout = w1.shape[0], w2.shape[0]
         self.g1, self.b1, self.g2, self.b2 = f(g1), f(b1), f(g2), f(b2)
-        self.pw1 = engine.pack_conv2d(self.w1, self.seg_sizes, None, dev, split=True)
-        self.pw2 = engine.pack_conv2d(self.w2, [self.cmid], None, dev, split=True)
-        self.pd2 = pack_conv2d_dgrad(self.w2, (0, self.cmid), dev, split=True)
-        self.pd1, c0 = [], 0
+        self.l1 = live_conv2d(self.w1, self.seg_sizes, None, dev)
+        self.l2 = live_conv2d(self.w2, [self.cmid], None, dev)
+        self.ld2 = live_conv2d_dgrad(self.w2, (0, self.cmid), dev)
+        self.ld1, c0 = [], 0
         for cs in self.seg_sizes:
             # the data gradient of a segment is only defined for engine-sized channel counts (the UNet's first layer has
             # 17 input channels and needs none: its input is data)
-            self.pd1.append(pack_conv2d_dgrad(self.w1, (c0, c0 + cs), dev, split=True) if cs % 64 == 0 else None)
+            self.ld1.append(live_conv2d_dgrad(self.w1, (c0, c0 + cs), dev) if cs % 64 == 0 else None)
             c0 += cs
         self.ws = workspace if workspace is not None else engine.new_workspace(dev)
+        self.cache = cache if cache is not None else StepCache(dev, False)
         self.saved = None
+
+    def operands(self) -> List[LiveOperand]:
+        return [self.l1, self.l2, self.ld2] + [l for l in self.ld1 if l is not None]
 
     def forward(self, inputs: Sequence[Act], temb: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None) -> Act:
         """stats_out: (N, 2) fp64, receives (sum, sumsq) of the block's output (the next layer's GroupNorm statistics)."""
         N, D, H, W, _ = inputs[0].shape
-        dev, s = self.dev, _lib.stream_ptr()
-        st1 = torch.zeros(N, 2, dtype=torch.float64, device=dev)
-        st2 = torch.zeros(N, 2, dtype=torch.float64, device=dev)
-        raw1 = new_act(N, 1, H, W, self.cmid, dev, split=True)
-        a1 = new_act(N, 1, H, W, self.cmid, dev, split=True)
-        raw2 = new_act(N, 1, H, W, self.cout, dev, split=True)
-        out = new_act(N, 1, H, W, self.cout, dev, split=True)
-        ConvPlan(list(inputs), self.pw1, raw1, cout=self.cmid, stats=st1, stats_cpg=self.cmid, workspace=self.ws).run(s)
-        row = torch.arange(N, dtype=torch.int32, device=dev) if temb is not None else None
-        tt = None if temb is None else temb.to(dev, torch.float32).contiguous()
+        dev, s, c, k = self.dev, _lib.stream_ptr(), self.cache, self.name
+        st1, st2 = c.zeros64(f"{k}.st1", (N, 2)), c.zeros64(f"{k}.st2", (N, 2))
+        raw1, a1 = c.act(f"{k}.raw1", N, H, W, self.cmid), c.act(f"{k}.a1", N, H, W, self.cmid)
+        raw2, out = c.act(f"{k}.raw2", N, H, W, self.cout), c.act(f"{k}.out", N, H, W, self.cout)
+        c.plan(f"{k}.conv1", lambda: ConvPlan(list(inputs), self.l1.pw, raw1, cout=self.cmid, stats=st1, stats_cpg=self.cmid,
+                                              workspace=self.ws)).run(s)
+        row = c.get(f"{k}.row", lambda: torch.arange(N, dtype=torch.int32, device=dev)) if temb is not None else None
+        tt = None
+        if temb is not None:
+            tt = c.empty(f"{k}.temb", (N, self.cmid))
+            tt.copy_(temb)
         engine.gn_apply(raw1, a1, st1, self.cmid, self.g1, self.b1, True, s, temb=tt, temb_row=row, temb_row_stride=1)
-        ConvPlan([a1], self.pw2, raw2, cout=self.cout, stats=st2, stats_cpg=self.cout, workspace=self.ws).run(s)
+        c.plan(f"{k}.conv2", lambda: ConvPlan([a1], self.l2.pw, raw2, cout=self.cout, stats=st2, stats_cpg=self.cout,
+                                              workspace=self.ws)).run(s)
         engine.gn_apply(raw2, out, st2, self.cout, self.g2, self.b2, True, s, stats_out=stats_out)
         self.saved = (list(inputs), raw1, st1, a1, raw2, st2, temb is not None)
         return out
 
-    def backward(self, d_out: Act) -> dict:
+    def backward(self, d_out: Act, grads: Optional[dict] = None) -> dict:
         """Returns {'conv1.weight', 'norm1.weight', 'norm1.bias', 'conv2.weight', 'norm2.weight', 'norm2.bias', 'temb' (N, Cmid),
-        'inputs': [Act or None per segment]} -- the gradients torch.autograd gives for the same block."""
+        'inputs': [Act or None per segment]} -- the gradients torch.autograd gives for the same block.  `grads`: zeroed
+        destinations for the parameter gradients (same keys); missing ones are allocated."""
         inputs, raw1, st1, a1, raw2, st2, has_temb = self.saved
         N, D, H, W, _ = raw1.shape
-        dev, s = self.dev, _lib.stream_ptr()
-        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
-        g = {"norm2.weight": z(self.cout), "norm2.bias": z(self.cout), "norm1.weight": z(self.cmid), "norm1.bias": z(self.cmid),
-             "conv2.weight": z(self.cout, self.cmid, 3, 3), "conv1.weight": z(self.cmid, sum(self.seg_sizes), 3, 3),
-             "temb": z(N, self.cmid) if has_temb else None}
-        d_raw2 = new_act(N, 1, H, W, self.cout, dev, split=True)
-        gn_silu_bwd(raw2, d_out, d_raw2, st2, self.g2, self.b2, True, g["norm2.weight"], g["norm2.bias"], None, s)
+        dev, s, c, k = self.dev, _lib.stream_ptr(), self.cache, self.name
+        g = {"norm2.weight": _grad_dest(grads, "norm2.weight", (self.cout,), dev), "norm2.bias": _grad_dest(grads, "norm2.bias", (self.cout,), dev),
+             "norm1.weight": _grad_dest(grads, "norm1.weight", (self.cmid,), dev), "norm1.bias": _grad_dest(grads, "norm1.bias", (self.cmid,), dev),
+             "conv2.weight": _grad_dest(grads, "conv2.weight", (self.cout, self.cmid, 3, 3), dev),
+             "conv1.weight": _grad_dest(grads, "conv1.weight", (self.cmid, sum(self.seg_sizes), 3, 3), dev), "temb": None}
+        if has_temb:
+            g["temb"] = c.empty(f"{k}.dtemb", (N, self.cmid))
+            g["temb"].zero_()
+        d_raw2 = c.act(f"{k}.d_raw2", N, H, W, self.cout)
+        gn_silu_bwd(raw2, d_out, d_raw2, st2, self.g2, self.b2, True, g["norm2.weight"], g["norm2.bias"], None, s,
+                    sums=c.empty(f"{k}.sums2", (N, 2), torch.float64))
         conv_wgrad(d_raw2, a1, g["conv2.weight"], self.cout, self.cmid, 0, s)
-        d_a1 = new_act(N, 1, H, W, self.cmid, dev, split=True)
-        ConvPlan([d_raw2], self.pd2, d_a1, cout=self.cmid, workspace=self.ws).run(s)
-        d_raw1 = new_act(N, 1, H, W, self.cmid, dev, split=True)
-        gn_silu_bwd(raw1, d_a1, d_raw1, st1, self.g1, self.b1, True, g["norm1.weight"], g["norm1.bias"], g["temb"], s)
+        d_a1 = c.act(f"{k}.d_a1", N, H, W, self.cmid)
+        c.plan(f"{k}.dgrad2", lambda: ConvPlan([d_raw2], self.ld2.pw, d_a1, cout=self.cmid, workspace=self.ws)).run(s)
+        d_raw1 = c.act(f"{k}.d_raw1", N, H, W, self.cmid)
+        gn_silu_bwd(raw1, d_a1, d_raw1, st1, self.g1, self.b1, True, g["norm1.weight"], g["norm1.bias"], g["temb"], s,
+                    sums=c.empty(f"{k}.sums1", (N, 2), torch.float64))
         d_inputs, c0 = [], 0
-        for x, cs, pd in zip(inputs, self.seg_sizes, self.pd1):
+        for i, (x, cs, ld) in enumerate(zip(inputs, self.seg_sizes, self.ld1)):
             conv_wgrad(d_raw1, x, g["conv1.weight"], self.cmid, cs, c0, s)
-            if pd is None:
+            if ld is None:
                 d_inputs.append(None)
             else:
-                dx = new_act(N, 1, H, W, x.C, dev, split=True)
-                ConvPlan([d_raw1], pd, dx, cout=cs, workspace=self.ws).run(s)
+                dx = c.act(f"{k}.dx{i}", N, H, W, x.C)
+                c.plan(f"{k}.dgrad1.{i}", lambda: ConvPlan([d_raw1], ld.pw, dx, cout=cs, workspace=self.ws)).run(s)
                 d_inputs.append(dx)
             c0 += cs
         g["inputs"] = d_inputs
@@ -252,64 +383,84 @@ class AttentionGrad:
     (q | k | v) = in_proj(GroupNorm(1, C)(x)).  The two C x C output projections run folded (W = Wp Wo, b = Wp bo + bp) as in
     the sampling path; their separate gradients follow from the folded ones by C x C parameter-space products."""
 
-    def __init__(self, c: int, heads: int, p: Dict[str, torch.Tensor], device="cuda", workspace: Optional[torch.Tensor] = None):
+    def __init__(self, c: int, heads: int, p: Dict[str, torch.Tensor], device="cuda", workspace: Optional[torch.Tensor] = None,
+                 cache: Optional[StepCache] = None, name: str = "attn"):
         dev = torch.device(device)
         f = lambda t: t.detach().to(dev, torch.float32).contiguous()
-        self.dev, self.c, self.heads = dev, c, heads
+        self.dev, self.c, self.heads, self.name = dev, c, heads, name
         self.g, self.b = f(p["norm.weight"]), f(p["norm.bias"])
         self.w_in, self.b_in = f(p["mha.in_proj_weight"]), f(p["mha.in_proj_bias"])
         self.wo, self.bo = f(p["mha.out_proj.weight"]), f(p["mha.out_proj.bias"])
-        self.wp, self.bp = f(p["proj_out.weight"])[:, :, 0], f(p["proj_out.bias"])
-        w_out = (self.wp.double() @ self.wo.double()).float()
-        b_out = (self.wp.double() @ self.bo.double() + self.bp.double()).float()
-        self.p_in = engine.pack_linear(self.w_in, self.b_in, dev, split=True)
-        self.p_out = engine.pack_linear(w_out, b_out, dev, split=True)
-        self.p_in_t = engine.pack_linear(self.w_in.t().contiguous(), None, dev, split=True)
-        self.p_out_t = engine.pack_linear(w_out.t().contiguous(), None, dev, split=True)
+        self.wp3, self.bp = f(p["proj_out.weight"]), f(p["proj_out.bias"])
+        self.wp = self.wp3[:, :, 0]
+        self.w_out = torch.empty(c, c, dtype=torch.float32, device=dev)   # Wp Wo, recomputed by refresh_folded()
+        self.b_out = torch.empty(c, dtype=torch.float32, device=dev)
+        self.refresh_folded()
+        self.l_in = live_linear(self.w_in, self.b_in, dev)
+        self.l_out = live_linear(self.w_out, self.b_out, dev)
+        self.l_in_t = live_linear(self.w_in, None, dev, transpose=True)
+        self.l_out_t = live_linear(self.w_out, None, dev, transpose=True)
         self.ws = workspace if workspace is not None else engine.new_workspace(dev)
+        self.cache = cache if cache is not None else StepCache(dev, False)
         self.saved = None
+
+    def refresh_folded(self):
+        self.w_out.copy_(self.wp.double() @ self.wo.double())
+        self.b_out.copy_(self.wp.double() @ self.bo.double() + self.bp.double())
+
+    def operands(self) -> List[LiveOperand]:
+        return [self.l_in, self.l_out, self.l_in_t, self.l_out_t]
 
     def forward(self, x: Act, st_x: torch.Tensor) -> Act:
         """st_x: (N, 2) fp64 (sum, sumsq) of x per sample."""
         N, D, H, W, c = x.shape
-        dev, s = self.dev, _lib.stream_ptr()
-        xn = new_act(N, 1, H, W, c, dev, split=True)
+        dev, s, ch, k = self.dev, _lib.stream_ptr(), self.cache, self.name
+        xn = ch.act(f"{k}.xn", N, H, W, c)
         engine.gn_apply(x, xn, st_x, c, self.g, self.b, False, s)
-        qkv = new_act(N, 1, H, W, 3 * c, dev, split=True)
-        ConvPlan([xn], self.p_in, qkv, cout=3 * c, workspace=self.ws).run(s)
-        ao = new_act(N, 1, H, W, c, dev, split=True)
+        qkv = ch.act(f"{k}.qkv", N, H, W, 3 * c)
+        ch.plan(f"{k}.in", lambda: ConvPlan([xn], self.l_in.pw, qkv, cout=3 * c, workspace=self.ws)).run(s)
+        ao = ch.act(f"{k}.ao", N, H, W, c)
         call("b2d_attention", ptr(qkv.hi), ptr(qkv.lo), ptr(ao.hi), ptr(ao.lo), N, H * W, c, self.heads, 0, s)
-        y = new_act(N, 1, H, W, c, dev, split=True)
-        ConvPlan([ao], self.p_out, y, cout=c, residual=x, workspace=self.ws).run(s)
+        y = ch.act(f"{k}.y", N, H, W, c)
+        ch.plan(f"{k}.out", lambda: ConvPlan([ao], self.l_out.pw, y, cout=c, residual=x, workspace=self.ws)).run(s)
         self.saved = (x, st_x, xn, qkv, ao)
         return y
 
-    def backward(self, d_y: Act) -> Tuple[dict, Act]:
+    def backward(self, d_y: Act, grads: Optional[dict] = None) -> Tuple[dict, Act]:
         x, st_x, xn, qkv, ao = self.saved
         N, D, H, W, c = x.shape
-        dev, s = self.dev, _lib.stream_ptr()
-        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
-        d_wout, d_bout = z(c, c), z(c)
+        dev, s, ch, k = self.dev, _lib.stream_ptr(), self.cache, self.name
+        d_wout, d_bout = ch.empty(f"{k}.d_wout", (c, c)), ch.empty(f"{k}.d_bout", (c,))
+        d_wout.zero_()
+        d_bout.zero_()
         conv_wgrad(d_y, ao, d_wout, c, c, 0, s, kind=WGRAD_LINEAR)
         channel_sum(d_y, d_bout, c, s)
-        d_ao = new_act(N, 1, H, W, c, dev, split=True)
-        ConvPlan([d_y], self.p_out_t, d_ao, cout=c, workspace=self.ws).run(s)
-        d_qkv = new_act(N, 1, H, W, 3 * c, dev, split=True)
-        attention_bwd(qkv, ao, d_ao, d_qkv, self.heads, s)
-        g = {"mha.in_proj_weight": z(3 * c, c), "mha.in_proj_bias": z(3 * c), "norm.weight": z(c), "norm.bias": z(c)}
+        d_ao = ch.act(f"{k}.d_ao", N, H, W, c)
+        ch.plan(f"{k}.out_t", lambda: ConvPlan([d_y], self.l_out_t.pw, d_ao, cout=c, workspace=self.ws)).run(s)
+        d_qkv = ch.act(f"{k}.d_qkv", N, H, W, 3 * c)
+        attention_bwd(qkv, ao, d_ao, d_qkv, self.heads, s, stats=ch.empty(f"{k}.attn_stats", (N * self.heads * H * W * 2,)))
+        g = {"mha.in_proj_weight": _grad_dest(grads, "mha.in_proj_weight", (3 * c, c), dev),
+             "mha.in_proj_bias": _grad_dest(grads, "mha.in_proj_bias", (3 * c,), dev),
+             "norm.weight": _grad_dest(grads, "norm.weight", (c,), dev), "norm.bias": _grad_dest(grads, "norm.bias", (c,), dev)}
         conv_wgrad(d_qkv, xn, g["mha.in_proj_weight"], 3 * c, c, 0, s, kind=WGRAD_LINEAR)
         channel_sum(d_qkv, g["mha.in_proj_bias"], 3 * c, s)
-        d_xn = new_act(N, 1, H, W, c, dev, split=True)
-        ConvPlan([d_qkv], self.p_in_t, d_xn, cout=c, workspace=self.ws).run(s)
-        d_x = new_act(N, 1, H, W, c, dev, split=True)
-        gn_silu_bwd(x, d_xn, d_x, st_x, self.g, self.b, False, g["norm.weight"], g["norm.bias"], None, s)
+        d_xn = ch.act(f"{k}.d_xn", N, H, W, c)
+        ch.plan(f"{k}.in_t", lambda: ConvPlan([d_qkv], self.l_in_t.pw, d_xn, cout=c, workspace=self.ws)).run(s)
+        d_x = ch.act(f"{k}.d_x", N, H, W, c)
+        gn_silu_bwd(x, d_xn, d_x, st_x, self.g, self.b, False, g["norm.weight"], g["norm.bias"], None, s,
+                    sums=ch.empty(f"{k}.sums", (N, 2), torch.float64))
         add_acts(d_x, d_y, d_x, s)
         # W = Wp Wo, b = Wp bo + bp  ->  dWp = dW Wo^T + db bo^T, dWo = Wp^T dW, dbo = Wp^T db, dbp = db
         dW, db = d_wout.double(), d_bout.double()
-        g["proj_out.weight"] = (dW @ self.wo.double().t() + torch.outer(db, self.bo.double())).float()[:, :, None]
-        g["proj_out.bias"] = d_bout
-        g["mha.out_proj.weight"] = (self.wp.double().t() @ dW).float()
-        g["mha.out_proj.bias"] = (self.wp.double().t() @ db).float()
+        out = {"proj_out.weight": (dW @ self.wo.double().t() + torch.outer(db, self.bo.double())).float()[:, :, None],
+               "proj_out.bias": d_bout, "mha.out_proj.weight": (self.wp.double().t() @ dW).float(),
+               "mha.out_proj.bias": (self.wp.double().t() @ db).float()}
+        for key, v in out.items():
+            if grads is not None and key in grads:
+                grads[key].copy_(v)
+                g[key] = grads[key]
+            else:
+                g[key] = v
         return g, d_x
 
 
@@ -322,9 +473,16 @@ class UNetTrainer:
     in the fp32-class mode (bf16 hi + lo operands, three MMA passes): every layer's forward saves what its backward needs,
     the backward walks the UNet (unet/models.py:131-188) in reverse -- final_conv, decoder levels (attention, DoubleBlock over
     cat[skip, up], ConvTranspose2d + GroupNorm + SiLU), bottleneck, encoder levels (max-pool + GroupNorm + SiLU, attention,
-    DoubleBlock) -- writing each parameter's gradient into FlatAdam's flat buffer, which one launch then applies.
+    DoubleBlock) -- accumulating each parameter's gradient directly in FlatAdam's flat buffer, which one launch then applies.
+    Activations, scratch and conv plans are created by the first step of a shape and reused (StepCache); after the update
+    every packed operand is rewritten in place from the new parameters (LiveOperand).
     The sinusoid -> time_mlp -> per-block Linear chain ((N, 64) -> (N, 256) -> (N, Cmid): a few kFLOP) is evaluated and
     differentiated with torch ops on the GPU; everything that touches a feature map is libb2d."""
+
+    _ATTN = ("norm.weight", "norm.bias", "mha.in_proj_weight", "mha.in_proj_bias", "mha.out_proj.weight", "mha.out_proj.bias",
+             "proj_out.weight", "proj_out.bias")
+    _DOUBLE = {"conv1.weight": "block1.conv.weight", "conv2.weight": "block2.conv.weight", "norm1.weight": "block1.norm.weight",
+               "norm1.bias": "block1.norm.bias", "norm2.weight": "block2.norm.weight", "norm2.bias": "block2.norm.bias"}
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], *, in_channels=17, out_channels=8, features=(64, 128, 256, 512, 1024),
                  attention: str = "", time_embedding_dim: Optional[int] = 64, num_timesteps: int = 1000, lr: float = 1e-4,
@@ -340,7 +498,10 @@ class UNetTrainer:
         self.opt = FlatAdam(state_dict, lr=lr, weight_decay=weight_decay, device=self.dev)
         self.scheduler = B200Scheduler(num_timesteps=num_timesteps, device=self.dev)
         self.ws = engine.new_workspace(self.dev)
+        self.cache = StepCache(self.dev, True)
+        self._shape = None
         self._layers = None
+        self._build_layers()
 
     # -------------------------------------------------------------------------------- parameters
     def P(self, name: str) -> torch.Tensor:
@@ -352,41 +513,46 @@ class UNetTrainer:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return self.opt.state_dict()
 
-    def _sub(self, prefix: str, names: Sequence[str]) -> Dict[str, torch.Tensor]:
-        return {n: self.P(f"{prefix}.{n}") for n in names}
-
-    _ATTN = ("norm.weight", "norm.bias", "mha.in_proj_weight", "mha.in_proj_bias", "mha.out_proj.weight", "mha.out_proj.bias",
-             "proj_out.weight", "proj_out.bias")
-
     def _build_layers(self):
-        """Operand forms of the current parameters (repacked after every optimizer step)."""
-        dev, ws, f = self.dev, self.ws, self.features
+        """Operand forms of the parameters (built once; `refresh_operands` rewrites them in place after each update)."""
+        dev, ws, f, ch = self.dev, self.ws, self.features, self.cache
         L = {}
 
         def double(p, segs):
             L[p] = DoubleBlockGrad(self.P(f"{p}.block1.conv.weight"), self.P(f"{p}.block1.norm.weight"), self.P(f"{p}.block1.norm.bias"),
                                    self.P(f"{p}.block2.conv.weight"), self.P(f"{p}.block2.norm.weight"), self.P(f"{p}.block2.norm.bias"),
-                                   segs, dev, workspace=ws)
+                                   segs, dev, workspace=ws, cache=ch, name=p)
+
+        def attn(p, c, heads):
+            L[p] = AttentionGrad(c, heads, {n: self.P(f"{p}.{n}") for n in self._ATTN}, dev, ws, cache=ch, name=p)
 
         cin = self.in_channels
         for lvl, c in enumerate(f):
             double(f"encoder.{lvl}.0", [cin])
             if self.heads[lvl] is not None:
-                L[f"encoder.{lvl}.1"] = AttentionGrad(c, self.heads[lvl], self._sub(f"encoder.{lvl}.1", self._ATTN), dev, ws)
+                attn(f"encoder.{lvl}.1", c, self.heads[lvl])
             cin = c
         double("bottleneck", [f[-1]])
         rheads = list(reversed(self.heads))
         for lvl, c in enumerate(reversed(f)):
             w = self.P(f"decoder.{lvl}.0.conv.weight")
-            L[f"decoder.{lvl}.0"] = (engine.pack_convT2x2(w, self.P(f"decoder.{lvl}.0.conv.bias"), dev, split=True),
-                                     pack_convT2x2_dgrad(w, dev, split=True))
+            L[f"decoder.{lvl}.0"] = (live_convT2x2(w, self.P(f"decoder.{lvl}.0.conv.bias"), dev), live_convT2x2_dgrad(w, dev))
             double(f"decoder.{lvl}.1", [c, c])
             if rheads[lvl] is not None:
-                L[f"decoder.{lvl}.2"] = AttentionGrad(c, rheads[lvl], self._sub(f"decoder.{lvl}.2", self._ATTN), dev, ws)
+                attn(f"decoder.{lvl}.2", c, rheads[lvl])
         wf = self.P("final_conv.weight")
-        L["final_conv"] = (engine.pack_conv2d(wf, [f[0]], self.P("final_conv.bias"), dev, split=True),
-                           pack_conv2d_dgrad(wf, (0, f[0]), dev, split=True))
+        L["final_conv"] = (live_conv2d(wf, [f[0]], self.P("final_conv.bias"), dev), live_conv2d_dgrad(wf, (0, f[0]), dev))
         self._layers = L
+
+    def refresh_operands(self):
+        """Bring every packed operand up to date with the flat parameter buffer (after FlatAdam.step)."""
+        s = _lib.stream_ptr()
+        for layer in self._layers.values():
+            if isinstance(layer, AttentionGrad):
+                layer.refresh_folded()
+            ops = layer.operands() if hasattr(layer, "operands") else list(layer)
+            for op in ops:
+                op.refresh(s)
 
     # -------------------------------------------------------------------------------- time embedding chain (torch, tiny)
     def _time_names(self):
@@ -417,132 +583,125 @@ class UNetTrainer:
     def forward_backward(self, x: torch.Tensor, t: torch.Tensor, target: torch.Tensor):
         """x: (N, in_channels, h, w) fp32 on the GPU, t: (N,) timesteps, target: (N, out_channels, h, w).  Fills the flat
         gradient buffer; returns (loss, pred)."""
-        if self._layers is None:
-            self._build_layers()
         L, dev, f, s = self._layers, self.dev, self.features, _lib.stream_ptr()
         N, _, h, w = x.shape
         nl = len(f)
         if h % (1 << nl) or w % (1 << nl):
             raise ValueError(f"UNetTrainer: input {h}x{w} must be divisible by {1 << nl}")
+        if self._shape != (N, h, w):   # a new shape: new buffers and plans (the layers keep their operands)
+            self.cache.reset()
+            self._shape = (N, h, w)
+        ch = self.cache
+        ch.begin_step()
         self.opt.zero_grad()
-        z2 = lambda: torch.zeros(N, 2, dtype=torch.float64, device=dev)
+        G = self.G
         temb, leaves = self._time_forward(t) if self.time_dim is not None else ({}, {})
-        x_in = new_act(N, 1, h, w, engine.pad64(self.in_channels), dev, split=True, zero=True)
+        x_in = ch.act("x_in", N, h, w, engine.pad64(self.in_channels), zero=True)
         engine.planar_to_cl(x.contiguous().float(), x_in, N, self.in_channels, h * w, 0, None, s)
         # ---- forward (models.py:144-186)
         a, H, Wd = x_in, h, w
         skips, pools = [], []
         for lvl, c in enumerate(f):
             p = f"encoder.{lvl}.0"
-            st = z2() if self.heads[lvl] is not None else None
-            a = L[p].forward([a], temb.get(p).detach() if p in temb else None, stats_out=st)
+            st = ch.zeros64(f"{p}.st_out", (N, 2)) if self.heads[lvl] is not None else None
+            a = L[p].forward([a], temb[p].detach() if p in temb else None, stats_out=st)
             if st is not None:
                 a = L[f"encoder.{lvl}.1"].forward(a, st)
             skips.append(a)
-            praw = new_act(N, 1, H // 2, Wd // 2, c, dev, split=True)
-            pst = z2()
+            q = f"encoder.{lvl}.2"
+            praw, pst = ch.act(f"{q}.raw", N, H // 2, Wd // 2, c), ch.zeros64(f"{q}.st", (N, 2))
             engine.maxpool_stats(a, praw, pst, s)
-            pa = new_act(N, 1, H // 2, Wd // 2, c, dev, split=True)
-            g, b = self.P(f"encoder.{lvl}.2.norm.weight"), self.P(f"encoder.{lvl}.2.norm.bias")
-            engine.gn_apply(praw, pa, pst, c, g, b, True, s)
+            pa = ch.act(f"{q}.out", N, H // 2, Wd // 2, c)
+            engine.gn_apply(praw, pa, pst, c, self.P(f"{q}.norm.weight"), self.P(f"{q}.norm.bias"), True, s)
             pools.append((a, praw, pst))
             a, H, Wd = pa, H // 2, Wd // 2
         a = L["bottleneck"].forward([a], temb["bottleneck"].detach() if temb else None)
         ups = []
         rheads = list(reversed(self.heads))
         for lvl, c in enumerate(reversed(f)):
-            pw, _ = L[f"decoder.{lvl}.0"]
-            raw = new_act(N, 1, 2 * H, 2 * Wd, c, dev, split=True)
-            ust = z2()
-            ConvPlan([a], pw, raw, cout=c, nphase=4, stats=ust, stats_cpg=c, workspace=self.ws).run(s)
-            up = new_act(N, 1, 2 * H, 2 * Wd, c, dev, split=True)
-            engine.gn_apply(raw, up, ust, c, self.P(f"decoder.{lvl}.0.norm.weight"), self.P(f"decoder.{lvl}.0.norm.bias"), True, s)
+            q = f"decoder.{lvl}.0"
+            raw, ust = ch.act(f"{q}.raw", N, 2 * H, 2 * Wd, c), ch.zeros64(f"{q}.st", (N, 2))
+            ch.plan(f"{q}.conv", lambda: ConvPlan([a], L[q][0].pw, raw, cout=c, nphase=4, stats=ust, stats_cpg=c, workspace=self.ws)).run(s)
+            up = ch.act(f"{q}.out", N, 2 * H, 2 * Wd, c)
+            engine.gn_apply(raw, up, ust, c, self.P(f"{q}.norm.weight"), self.P(f"{q}.norm.bias"), True, s)
             ups.append((a, raw, ust))
             H, Wd = 2 * H, 2 * Wd
             p = f"decoder.{lvl}.1"
-            st = z2() if rheads[lvl] is not None else None
-            a = L[p].forward([skips[nl - 1 - lvl], up], temb.get(p).detach() if p in temb else None, stats_out=st)
+            st = ch.zeros64(f"{p}.st_out", (N, 2)) if rheads[lvl] is not None else None
+            a = L[p].forward([skips[nl - 1 - lvl], up], temb[p].detach() if p in temb else None, stats_out=st)
             if st is not None:
                 a = L[f"decoder.{lvl}.2"].forward(a, st)
-        pred = torch.empty(N, self.out_channels, h, w, dtype=torch.float32, device=dev)
-        ConvPlan([a], L["final_conv"][0], pred, cout=self.out_channels, out_mode=1, out_cstride=self.out_channels, workspace=self.ws).run(s)
+        pred = ch.empty("pred", (N, self.out_channels, h, w))
         final_in = a
+        ch.plan("final_conv", lambda: ConvPlan([final_in], L["final_conv"][0].pw, pred, cout=self.out_channels, out_mode=1,
+                                               out_cstride=self.out_channels, workspace=self.ws)).run(s)
         # ---- criterion (metrics.py:337-402)
         loss, _, d_pred = nmse_loss(pred, target.to(dev))
         # ---- backward
         d_temb = {}
         oc, c0 = self.out_channels, f[0]
-        d = new_act(N, 1, h, w, engine.pad64(oc), dev, split=True, zero=True)
+        d = ch.act("d_pred", N, h, w, engine.pad64(oc), zero=True)
         engine.planar_to_cl(d_pred, d, N, oc, h * w, 0, None, s)
-        channel_sum(d, self.G("final_conv.bias"), oc, s)
-        conv_wgrad(d, final_in, self.G("final_conv.weight"), oc, c0, 0, s)
-        da = new_act(N, 1, h, w, c0, dev, split=True)
-        ConvPlan([d], L["final_conv"][1], da, cout=c0, workspace=self.ws).run(s)
+        channel_sum(d, G("final_conv.bias"), oc, s)
+        conv_wgrad(d, final_in, G("final_conv.weight"), oc, c0, 0, s)
+        da = ch.act("d_final_in", N, h, w, c0)
+        ch.plan("final_conv.dgrad", lambda: ConvPlan([d], L["final_conv"][1].pw, da, cout=c0, workspace=self.ws)).run(s)
         d_skips = [None] * nl
 
-        def take_double(p, g):
-            self.G(f"{p}.block1.conv.weight").copy_(g["conv1.weight"])
-            self.G(f"{p}.block2.conv.weight").copy_(g["conv2.weight"])
-            for i in (1, 2):
-                self.G(f"{p}.block{i}.norm.weight").copy_(g[f"norm{i}.weight"])
-                self.G(f"{p}.block{i}.norm.bias").copy_(g[f"norm{i}.bias"])
+        def double_bwd(p, d_out):
+            g = L[p].backward(d_out, {k: G(f"{p}.{v}") for k, v in self._DOUBLE.items()})
             if g["temb"] is not None:
                 d_temb[p] = g["temb"]
+            return g["inputs"]
 
-        def take_attention(p, g):
-            for k, v in g.items():
-                self.G(f"{p}.{k}").copy_(v)
+        def attention_bwd_(p, d_out):
+            return L[p].backward(d_out, {n: G(f"{p}.{n}") for n in self._ATTN})[1]
 
-        for lvl in reversed(range(nl)):
-            c = list(reversed(f))[lvl]
+        for lvl in range(nl - 1, -1, -1):
+            c = f[nl - 1 - lvl]
             if rheads[lvl] is not None:
-                g, da = L[f"decoder.{lvl}.2"].backward(da)
-                take_attention(f"decoder.{lvl}.2", g)
-            g = L[f"decoder.{lvl}.1"].backward(da)
-            take_double(f"decoder.{lvl}.1", g)
-            d_skips[nl - 1 - lvl], d_up = g["inputs"]
+                da = attention_bwd_(f"decoder.{lvl}.2", da)
+            d_skips[nl - 1 - lvl], d_up = double_bwd(f"decoder.{lvl}.1", da)
+            q = f"decoder.{lvl}.0"
             x_lo, raw, ust = ups[lvl]
-            Nn, _, H2, W2, _ = raw.shape
-            d_raw = new_act(N, 1, H2, W2, c, dev, split=True)
-            gn_silu_bwd(raw, d_up, d_raw, ust, self.P(f"decoder.{lvl}.0.norm.weight"), self.P(f"decoder.{lvl}.0.norm.bias"), True,
-                        self.G(f"decoder.{lvl}.0.norm.weight"), self.G(f"decoder.{lvl}.0.norm.bias"), None, s)
-            conv_wgrad(d_raw, x_lo, self.G(f"decoder.{lvl}.0.conv.weight"), c, 2 * c, 0, s, kind=WGRAD_CONVT2X2)
-            channel_sum(d_raw, self.G(f"decoder.{lvl}.0.conv.bias"), c, s)
-            da = new_act(N, 1, H2 // 2, W2 // 2, 2 * c, dev, split=True)
-            ConvPlan([d_raw], L[f"decoder.{lvl}.0"][1], da, cout=2 * c, stride=2, workspace=self.ws).run(s)
-        g = L["bottleneck"].backward(da)
-        take_double("bottleneck", g)
-        da = g["inputs"][0]
-        for lvl in reversed(range(nl)):
+            _, _, H2, W2, _ = raw.shape
+            d_raw = ch.act(f"{q}.d_raw", N, H2, W2, c)
+            gn_silu_bwd(raw, d_up, d_raw, ust, self.P(f"{q}.norm.weight"), self.P(f"{q}.norm.bias"), True, G(f"{q}.norm.weight"),
+                        G(f"{q}.norm.bias"), None, s, sums=ch.empty(f"{q}.sums", (N, 2), torch.float64))
+            conv_wgrad(d_raw, x_lo, G(f"{q}.conv.weight"), c, 2 * c, 0, s, kind=WGRAD_CONVT2X2)
+            channel_sum(d_raw, G(f"{q}.conv.bias"), c, s)
+            da = ch.act(f"{q}.d_in", N, H2 // 2, W2 // 2, 2 * c)
+            d_in = da
+            ch.plan(f"{q}.dgrad", lambda: ConvPlan([d_raw], L[q][1].pw, d_in, cout=2 * c, stride=2, workspace=self.ws)).run(s)
+        da = double_bwd("bottleneck", da)[0]
+        for lvl in range(nl - 1, -1, -1):
             c = f[lvl]
+            q = f"encoder.{lvl}.2"
             skip, praw, pst = pools[lvl]
-            d_praw = new_act(*praw.shape, dev, split=True)
-            gn_silu_bwd(praw, da, d_praw, pst, self.P(f"encoder.{lvl}.2.norm.weight"), self.P(f"encoder.{lvl}.2.norm.bias"), True,
-                        self.G(f"encoder.{lvl}.2.norm.weight"), self.G(f"encoder.{lvl}.2.norm.bias"), None, s)
-            da = new_act(*skip.shape, dev, split=True)
+            d_praw = ch.act(f"{q}.d_raw", *praw.shape[:1], *praw.shape[2:])
+            gn_silu_bwd(praw, da, d_praw, pst, self.P(f"{q}.norm.weight"), self.P(f"{q}.norm.bias"), True, G(f"{q}.norm.weight"),
+                        G(f"{q}.norm.bias"), None, s, sums=ch.empty(f"{q}.sums", (N, 2), torch.float64))
+            da = ch.act(f"{q}.d_in", *skip.shape[:1], *skip.shape[2:])
             maxpool_bwd(skip, d_praw, da, s)
             add_acts(da, d_skips[lvl], da, s)
             if self.heads[lvl] is not None:
-                g, da = L[f"encoder.{lvl}.1"].backward(da)
-                take_attention(f"encoder.{lvl}.1", g)
-            g = L[f"encoder.{lvl}.0"].backward(da)
-            take_double(f"encoder.{lvl}.0", g)
-            da = g["inputs"][0]
+                da = attention_bwd_(f"encoder.{lvl}.1", da)
+            da = double_bwd(f"encoder.{lvl}.0", da)[0]
         if temb:
             names = list(d_temb.keys())
             torch.autograd.backward([temb[p] for p in names], [d_temb[p] for p in names])
             for k, v in leaves.items():
-                self.G(k).copy_(v.grad)
+                G(k).copy_(v.grad)
         return loss, pred
 
     def training_step(self, x_start: torch.Tensor, cond: torch.Tensor, feats: torch.Tensor, t: torch.Tensor, noise: torch.Tensor,
                       group=None):
-        """q_sample -> forward -> loss -> backward -> (gradient all-reduce) -> Adam.  Returns (loss, pred)."""
+        """q_sample -> forward -> loss -> backward -> (gradient all-reduce) -> Adam -> operand refresh.  Returns (loss, pred)."""
         dev = self.dev
         x_t = self.scheduler.q_sample(x_start.to(dev), t.to(dev), noise.to(dev))            # diffusion.py:78-101
         x = torch.cat([x_t, cond.to(dev), feats.to(dev)], dim=1)                             # predictor.py:731-741
         loss, pred = self.forward_backward(x, t, noise.to(dev))
         scale = self.opt.allreduce_gradients(group)
         self.opt.step(grad_scale=scale)
-        self._layers = None  # operands are stale now
+        self.refresh_operands()
         return loss, pred

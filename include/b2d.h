@@ -304,6 +304,13 @@ B2D_API int b2d_maxpool2x2_bwd(const void* x_hi, const void* x_lo, const void* d
 B2D_API int b2d_attention_bwd(const void* qkv, const void* qkv_lo, const void* out, const void* out_lo, const void* dout, const void* dout_lo,
                       void* dqkv, void* dqkv_lo, float* stats, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t f16, void* stream);
 
+/* Rewrite a packed conv operand in place from fp32 parameters (after an optimizer step; plans keep pointing at it):
+ * dst[(r1 * R2 + r2) * ktot + tap * cpad + c] = src[r1 * sr1 + r2 * sr2 + tap * st + c * sc] for c < cs, as bf16 hi (+ lo
+ * = the bf16 remainder) or fp16.  dst_hi / dst_lo already point at the segment's K offset; strides in elements, may be
+ * negative (mirrored taps of a data-gradient operand: pass src at the last tap).  Padding entries are not touched. */
+B2D_API int b2d_pack_weight(const float* src, int32_t R1, int32_t R2, int64_t sr1, int64_t sr2, int32_t ntaps, int64_t st, int32_t cs, int64_t sc,
+                    void* dst_hi, void* dst_lo, int64_t ktot, int32_t cpad, int32_t f16, void* stream);
+
 /* fill helpers used by the fused loop (graph-capturable) */
 B2D_API int b2d_zero(void* p, int64_t bytes, void* stream);
 

@@ -295,3 +295,46 @@ def test_unet_training_step_vs_reference(golden_dir):
         e = rel_l2(tr.G(n).cpu(), ograds[n])
         assert e <= 2e-3, (n, e)
     print(f"training step: loss {loss.item():.6f}, worst gradient-norm deviation {worst:.2e}")
+
+
+def test_operand_refresh_in_place():
+    """b2d_pack_weight rewrites every operand form of the step (forward / data-gradient conv, linear and its transpose,
+    transposed conv and its data gradient) bit-identically to a fresh engine.pack_* of the same parameters."""
+    g = torch.Generator().manual_seed(11)
+    s = _s()
+    w = torch.randn(96, 64 + 17, 3, 3, generator=g).to(DEV)
+    wl = torch.randn(200, 72, generator=g).to(DEV)
+    wt = torch.randn(128, 72, 2, 2, generator=g).to(DEV)
+    live = [train.live_conv2d(w, [64, 17], None, DEV), train.live_conv2d_dgrad(w, (0, 64), DEV), train.live_linear(wl, None, DEV),
+            train.live_linear(wl, None, DEV, transpose=True), train.live_convT2x2(wt, None, DEV), train.live_convT2x2_dgrad(wt, DEV)]
+    for t in (w, wl, wt):
+        t.copy_(torch.randn(t.shape, generator=g).to(DEV))         # "optimizer step"
+    fresh = [train.live_conv2d(w, [64, 17], None, DEV), train.live_conv2d_dgrad(w, (0, 64), DEV), train.live_linear(wl, None, DEV),
+             train.live_linear(wl, None, DEV, transpose=True), train.live_convT2x2(wt, None, DEV), train.live_convT2x2_dgrad(wt, DEV)]
+    for a, b in zip(live, fresh):
+        assert not torch.equal(a.pw.w.view(torch.int16), b.pw.w.view(torch.int16))
+        a.refresh(s)
+        assert torch.equal(a.pw.w.view(torch.int16), b.pw.w.view(torch.int16))
+
+
+def test_second_training_step_reuses_buffers_and_refreshed_operands(golden_dir):
+    """Step 2 of a trainer (cached buffers and plans, operands rewritten in place after step 1's update) against a trainer
+    built fresh from the step-1 parameters."""
+    no_tf32()
+    mod = _train_inputs(golden_dir)
+    x_start, cond, feats, noise, t = mod.train_inputs()
+    a = train.UNetTrainer(synth.synth_unet_state(seed=0), **synth.UNET_KWARGS, lr=1e-3, device=DEV)
+    a.training_step(x_start, cond, feats, t, noise)
+    b = train.UNetTrainer({k: v.clone() for k, v in a.state_dict().items()}, **synth.UNET_KWARGS, lr=1e-3, device=DEV)
+    x = torch.cat([x_start, cond, feats], dim=1).to(DEV)
+    la, pa = a.forward_backward(x, t, noise.to(DEV))
+    lb, pb = b.forward_backward(x, t, noise.to(DEV))
+    torch.cuda.synchronize()
+    assert abs(la.item() - lb.item()) <= 1e-6 * abs(lb.item())
+    assert torch.equal(pa, pb)                                       # the forward has no atomics: bit-identical
+    for n in a.opt.names:
+        assert rel_l2(a.G(n), b.G(n)) <= 1e-5, n                     # wgrad sums pixel splits with fp32 atomics
+    # a different batch shape on the same trainer: new buffers and plans, same operands
+    a.forward_backward(x[:1, :, :32, :32].contiguous(), t[:1], noise[:1].to(DEV))
+    l3, _ = a.forward_backward(x, t, noise.to(DEV))
+    assert abs(l3.item() - lb.item()) <= 1e-6 * abs(lb.item())
