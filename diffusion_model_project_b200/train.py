@@ -501,6 +501,8 @@ class UNetTrainer:
         self.cache = StepCache(self.dev, True)
         self._shape = None
         self._layers = None
+        self._graph = None
+        self._fb_launches = 0
         self._build_layers()
 
     # -------------------------------------------------------------------------------- parameters
@@ -591,6 +593,8 @@ class UNetTrainer:
         if self._shape != (N, h, w):   # a new shape: new buffers and plans (the layers keep their operands)
             self.cache.reset()
             self._shape = (N, h, w)
+            if self._graph is not None:
+                self._graph["fb"] = None   # captured over the old buffers
         ch = self.cache
         ch.begin_step()
         self.opt.zero_grad()
@@ -694,14 +698,53 @@ class UNetTrainer:
                 G(k).copy_(v.grad)
         return loss, pred
 
+    def _q_sample_forward_backward(self, x_start, cond, feats, t, noise):
+        x_t = self.scheduler.q_sample(x_start, t, noise)                                     # diffusion.py:78-101
+        return self.forward_backward(torch.cat([x_t, cond, feats], dim=1), t, noise)         # predictor.py:731-741
+
     def training_step(self, x_start: torch.Tensor, cond: torch.Tensor, feats: torch.Tensor, t: torch.Tensor, noise: torch.Tensor,
-                      group=None):
-        """q_sample -> forward -> loss -> backward -> (gradient all-reduce) -> Adam -> operand refresh.  Returns (loss, pred)."""
+                      group=None, use_graph: bool = True):
+        """q_sample -> forward -> loss -> backward -> (gradient all-reduce) -> Adam -> operand refresh.  Returns (loss, pred).
+        use_graph: replay the ~440 launches of q_sample .. backward and the ~180 of the operand refresh as two CUDA graphs
+        (captured on the second step of a batch shape, over the StepCache's static buffers); the all-reduce and the Adam
+        launch (whose bias corrections change every step) stay eager.  The returned tensors are then overwritten by the
+        next step."""
         dev = self.dev
-        x_t = self.scheduler.q_sample(x_start.to(dev), t.to(dev), noise.to(dev))            # diffusion.py:78-101
-        x = torch.cat([x_t, cond.to(dev), feats.to(dev)], dim=1)                             # predictor.py:731-741
-        loss, pred = self.forward_backward(x, t, noise.to(dev))
+        ins = [x_start, cond, feats, t, noise]
+        if not use_graph:
+            loss, pred = self._q_sample_forward_backward(*[v.to(dev) for v in ins])
+        else:
+            key = tuple(tuple(v.shape) for v in ins)
+            if self._graph is None or self._graph["key"] != key:
+                self._graph = {"key": key, "ins": [torch.empty(v.shape, dtype=v.dtype, device=dev) for v in ins], "fb": None}
+            gr = self._graph
+            for dst, v in zip(gr["ins"], ins):
+                dst.copy_(v, non_blocking=True)
+            if gr["fb"] is None and self._shape == (x_start.shape[0], x_start.shape[2], x_start.shape[3]):
+                # buffers and plans of this shape exist (an eager step ran): capture
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    fb = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(fb, stream=side):
+                        gr["out"] = self._q_sample_forward_backward(*gr["ins"])
+                    rf = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(rf, stream=side):
+                        self.refresh_operands()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                gr["fb"], gr["refresh"] = fb, rf
+            if gr["fb"] is not None:
+                gr["fb"].replay()
+                _lib.launch_count += self._fb_launches
+                loss, pred = gr["out"]
+            else:
+                n0 = _lib.launch_count
+                loss, pred = self._q_sample_forward_backward(*gr["ins"])
+                self._fb_launches = _lib.launch_count - n0
         scale = self.opt.allreduce_gradients(group)
         self.opt.step(grad_scale=scale)
-        self.refresh_operands()
+        if use_graph and self._graph["fb"] is not None:
+            self._graph["refresh"].replay()
+        else:
+            self.refresh_operands()
         return loss, pred
