@@ -192,40 +192,40 @@ class LiveOperand:
                  pw.cin_pad[i], 1 if pw.f16 else 0, stream)
 
 
-def live_conv2d(w: torch.Tensor, seg_sizes: Sequence[int], bias, device) -> LiveOperand:
+def live_conv2d(w: torch.Tensor, seg_sizes: Sequence[int], bias, device, split=True) -> LiveOperand:
     """Forward operand of Conv2d 3x3, weight [Cout, Cin, 3, 3] (w: a contiguous fp32 view of the parameter)."""
     co, ci = w.shape[:2]
     parts, c0 = [], 0
     for cs in seg_sizes:
         parts.append((w, c0 * 9, 1, co, 0, ci * 9, 9, 1, cs, 9))
         c0 += cs
-    return LiveOperand(engine.pack_conv2d(w, seg_sizes, bias, device, split=True), parts)
+    return LiveOperand(engine.pack_conv2d(w, seg_sizes, bias, device, split=split), parts)
 
 
-def live_conv2d_dgrad(w: torch.Tensor, seg: Tuple[int, int], device) -> LiveOperand:
+def live_conv2d_dgrad(w: torch.Tensor, seg: Tuple[int, int], device, split=True) -> LiveOperand:
     """Data-gradient operand for input channels [seg0, seg1): rows = Cin of the segment, taps mirrored, columns = Cout."""
     co, ci = w.shape[:2]
     c0, c1 = seg
-    return LiveOperand(pack_conv2d_dgrad(w, seg, device, split=True), [(w, c0 * 9 + 8, 1, c1 - c0, 0, 9, 9, -1, co, ci * 9)])
+    return LiveOperand(pack_conv2d_dgrad(w, seg, device, split=split), [(w, c0 * 9 + 8, 1, c1 - c0, 0, 9, 9, -1, co, ci * 9)])
 
 
-def live_linear(w: torch.Tensor, bias, device, transpose=False) -> LiveOperand:
+def live_linear(w: torch.Tensor, bias, device, transpose=False, split=True) -> LiveOperand:
     """nn.Linear / 1x1 weight [out, in]; transpose: the data-gradient operand [in, out]."""
     o, i = w.shape
     if transpose:
-        return LiveOperand(engine.pack_linear(w.t().contiguous(), None, device, split=True), [(w, 0, 1, i, 0, 1, 1, 0, o, i)])
-    return LiveOperand(engine.pack_linear(w, bias, device, split=True), [(w, 0, 1, o, 0, i, 1, 0, i, 1)])
+        return LiveOperand(engine.pack_linear(w.t().contiguous(), None, device, split=split), [(w, 0, 1, i, 0, 1, 1, 0, o, i)])
+    return LiveOperand(engine.pack_linear(w, bias, device, split=split), [(w, 0, 1, o, 0, i, 1, 0, i, 1)])
 
 
-def live_convT2x2(w: torch.Tensor, bias, device) -> LiveOperand:
+def live_convT2x2(w: torch.Tensor, bias, device, split=True) -> LiveOperand:
     """Forward operand of ConvTranspose2d k2 s2, weight [Cin, Cout, 2, 2]: rows (phase, co), columns ci."""
     ci, co = w.shape[:2]
-    return LiveOperand(engine.pack_convT2x2(w, bias, device, split=True), [(w, 0, 4, co, 1, 4, 1, 0, ci, co * 4)])
+    return LiveOperand(engine.pack_convT2x2(w, bias, device, split=split), [(w, 0, 4, co, 1, 4, 1, 0, ci, co * 4)])
 
 
-def live_convT2x2_dgrad(w: torch.Tensor, device) -> LiveOperand:
+def live_convT2x2_dgrad(w: torch.Tensor, device, split=True) -> LiveOperand:
     ci, co = w.shape[:2]
-    return LiveOperand(pack_convT2x2_dgrad(w, device, split=True), [(w, 0, 1, ci, 0, co * 4, 4, 1, co, 4)])
+    return LiveOperand(pack_convT2x2_dgrad(w, device, split=split), [(w, 0, 1, ci, 0, co * 4, 4, 1, co, 4)])
 
 
 class StepCache:
@@ -235,8 +235,8 @@ class StepCache:
 
     POOL_DOUBLES = 1 << 16
 
-    def __init__(self, device, persistent: bool):
-        self.dev, self.persistent = torch.device(device), persistent
+    def __init__(self, device, persistent: bool, split: bool = True):
+        self.dev, self.persistent, self.split = torch.device(device), persistent, split
         self.store: dict = {}
         self.pool = torch.zeros(self.POOL_DOUBLES, dtype=torch.float64, device=self.dev) if persistent else None
         self.pool_used = 0
@@ -249,7 +249,7 @@ class StepCache:
         return self.store[key]
 
     def act(self, key, N, H, W, C, zero=False) -> Act:
-        return self.get(key, lambda: new_act(N, 1, H, W, C, self.dev, split=True, zero=zero))
+        return self.get(key, lambda: new_act(N, 1, H, W, C, self.dev, split=self.split, zero=zero))
 
     def empty(self, key, shape, dtype=torch.float32) -> torch.Tensor:
         return self.get(key, lambda: torch.empty(shape, dtype=dtype, device=self.dev))
@@ -304,17 +304,18 @@ class DoubleBlockGrad:
         self.w1, self.w2 = f(w1), f(w2)
         self.cmid, self.cout = w1.shape[0], w2.shape[0]
         self.g1, self.b1, self.g2, self.b2 = f(g1), f(b1), f(g2), f(b2)
-        self.l1 = live_conv2d(self.w1, self.seg_sizes, None, dev)
-        self.l2 = live_conv2d(self.w2, [self.cmid], None, dev)
-        self.ld2 = live_conv2d_dgrad(self.w2, (0, self.cmid), dev)
+        self.cache = cache if cache is not None else StepCache(dev, False)
+        sp = self.cache.split
+        self.l1 = live_conv2d(self.w1, self.seg_sizes, None, dev, sp)
+        self.l2 = live_conv2d(self.w2, [self.cmid], None, dev, sp)
+        self.ld2 = live_conv2d_dgrad(self.w2, (0, self.cmid), dev, sp)
         self.ld1, c0 = [], 0
         for cs in self.seg_sizes:
             # the data gradient of a segment is only defined for engine-sized channel counts (the UNet's first layer has
             # 17 input channels and needs none: its input is data)
-            self.ld1.append(live_conv2d_dgrad(self.w1, (c0, c0 + cs), dev) if cs % 64 == 0 else None)
+            self.ld1.append(live_conv2d_dgrad(self.w1, (c0, c0 + cs), dev, sp) if cs % 64 == 0 else None)
             c0 += cs
         self.ws = workspace if workspace is not None else engine.new_workspace(dev)
-        self.cache = cache if cache is not None else StepCache(dev, False)
         self.saved = None
 
     def operands(self) -> List[LiveOperand]:
@@ -396,12 +397,13 @@ class AttentionGrad:
         self.w_out = torch.empty(c, c, dtype=torch.float32, device=dev)   # Wp Wo, recomputed by refresh_folded()
         self.b_out = torch.empty(c, dtype=torch.float32, device=dev)
         self.refresh_folded()
-        self.l_in = live_linear(self.w_in, self.b_in, dev)
-        self.l_out = live_linear(self.w_out, self.b_out, dev)
-        self.l_in_t = live_linear(self.w_in, None, dev, transpose=True)
-        self.l_out_t = live_linear(self.w_out, None, dev, transpose=True)
-        self.ws = workspace if workspace is not None else engine.new_workspace(dev)
         self.cache = cache if cache is not None else StepCache(dev, False)
+        sp = self.cache.split
+        self.l_in = live_linear(self.w_in, self.b_in, dev, split=sp)
+        self.l_out = live_linear(self.w_out, self.b_out, dev, split=sp)
+        self.l_in_t = live_linear(self.w_in, None, dev, transpose=True, split=sp)
+        self.l_out_t = live_linear(self.w_out, None, dev, transpose=True, split=sp)
+        self.ws = workspace if workspace is not None else engine.new_workspace(dev)
         self.saved = None
 
     def refresh_folded(self):
@@ -486,7 +488,9 @@ class UNetTrainer:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], *, in_channels=17, out_channels=8, features=(64, 128, 256, 512, 1024),
                  attention: str = "", time_embedding_dim: Optional[int] = 64, num_timesteps: int = 1000, lr: float = 1e-4,
-                 weight_decay: float = 0.0, device="cuda", **_ignored):
+                 weight_decay: float = 0.0, device="cuda", precision: str = "fp32x", **_ignored):
+        """precision: "fp32x" (bf16 hi + lo operands and activations, three MMA passes: the parity mode) or "bf16" (single
+        bf16 operands / activations / gradients, fp32 accumulate: a third of the MMA work, gradients to ~1e-2)."""
         from .scheduler import B200Scheduler
         from .synth import attention_heads
         if not torch.cuda.is_available():
@@ -498,7 +502,10 @@ class UNetTrainer:
         self.opt = FlatAdam(state_dict, lr=lr, weight_decay=weight_decay, device=self.dev)
         self.scheduler = B200Scheduler(num_timesteps=num_timesteps, device=self.dev)
         self.ws = engine.new_workspace(self.dev)
-        self.cache = StepCache(self.dev, True)
+        if precision not in ("fp32x", "bf16"):
+            raise ValueError(f"UNetTrainer precision must be 'fp32x' or 'bf16', got {precision!r}")
+        self.precision, self.split = precision, precision == "fp32x"
+        self.cache = StepCache(self.dev, True, self.split)
         self._shape = None
         self._layers = None
         self._graph = None
@@ -538,12 +545,13 @@ class UNetTrainer:
         rheads = list(reversed(self.heads))
         for lvl, c in enumerate(reversed(f)):
             w = self.P(f"decoder.{lvl}.0.conv.weight")
-            L[f"decoder.{lvl}.0"] = (live_convT2x2(w, self.P(f"decoder.{lvl}.0.conv.bias"), dev), live_convT2x2_dgrad(w, dev))
+            L[f"decoder.{lvl}.0"] = (live_convT2x2(w, self.P(f"decoder.{lvl}.0.conv.bias"), dev, self.split), live_convT2x2_dgrad(w, dev, self.split))
             double(f"decoder.{lvl}.1", [c, c])
             if rheads[lvl] is not None:
                 attn(f"decoder.{lvl}.2", c, rheads[lvl])
         wf = self.P("final_conv.weight")
-        L["final_conv"] = (live_conv2d(wf, [f[0]], self.P("final_conv.bias"), dev), live_conv2d_dgrad(wf, (0, f[0]), dev))
+        L["final_conv"] = (live_conv2d(wf, [f[0]], self.P("final_conv.bias"), dev, self.split),
+                           live_conv2d_dgrad(wf, (0, f[0]), dev, self.split))
         self._layers = L
 
     def refresh_operands(self):

@@ -20,6 +20,7 @@ ap.add_argument("--slices", type=int, default=22)
 ap.add_argument("--size", type=int, default=64)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--precision", default="fp32x", choices=["fp32x", "bf16"])
 ap.add_argument("--eager", action="store_true", help="no CUDA graphs: every launch issued from Python")
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -34,7 +35,7 @@ g = torch.Generator().manual_seed(100 + rank)
 x_start, cond = torch.randn(N, 8, S, S, generator=g).to(dev), torch.randn(N, 8, S, S, generator=g).to(dev)
 feats, noise = torch.rand(N, 1, S, S, generator=g).to(dev), torch.randn(N, 8, S, S, generator=g).to(dev)
 t = torch.randint(0, 1000, (N,), generator=g).to(dev)
-tr = train.UNetTrainer(synth.synth_unet_state(seed=0), **synth.UNET_KWARGS, lr=1e-4, device=dev)
+tr = train.UNetTrainer(synth.synth_unet_state(seed=0), **synth.UNET_KWARGS, lr=1e-4, device=dev, precision=args.precision)
 
 
 def ev():
@@ -93,7 +94,7 @@ if rank == 0:
     print(json.dumps({
         "metric": "UNet training steps/sec (forward + backward + gradient all-reduce + Adam)", "value": 1e3 / tm.item() * 1.0,
         "unit": "steps/s", "n_gpus": world, "ms_per_step": tm.item(), "wall_ms_per_step": wall, "host_issue_ms_per_step": host, "slices_per_gpu": N, "latent": S,
-        "samples_per_s": world * (N / 11.0) * 1e3 / tm.item(), "dtype": "fp32x (bf16 hi + lo operands, fp32 accumulate)",
+        "samples_per_s": world * (N / 11.0) * 1e3 / tm.item(), "dtype": "fp32x (bf16 hi + lo operands, fp32 accumulate)" if args.precision == "fp32x" else "bf16 (fp32 accumulate)",
         "parts_ms": {"forward_backward": parts[0], "allreduce": parts[1], "adam": parts[2], "operand_refresh": parts[3]},
         "algorithmic_tflops": flops / (parts[0] * 1e-3) / 1e12 if marks else None, "parameters": nparam, "gradient_bytes": 4 * tr.opt.numel,
         "allreduce_busbw_GBps": (2 * (world - 1) / world * 4 * tr.opt.numel / (parts[1] * 1e-3) / 1e9) if world > 1 else None,
