@@ -100,7 +100,7 @@ _SIGNATURES = {
     "b2d_gn_silu_bwd": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32,
                                 c_void_p, c_void_p, c_void_p, c_float, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2d_conv_wgrad": (c_int, [c_i32, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
-                               c_void_p, c_i32, c_void_p]),
+                               c_void_p, c_i32, c_i32, c_void_p]),
     "b2d_channel_sum": (c_int, [c_void_p, c_void_p, c_i32, c_i64, c_i32, c_i32, c_void_p, c_void_p]),
     "b2d_add16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_void_p]),
     "b2d_maxpool2x2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p]),

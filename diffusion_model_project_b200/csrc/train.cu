@@ -238,7 +238,8 @@ constexpr uint32_t kUmmaBMajorMN2 = 1u << 16;
 struct WgradParams {
   CUtensorMap tmA[2];  // A hi / lo: dims (Cpad, W, H, 1, N), box (64, bw, bh, 1, bn), bw * bh * bn = 32
   CUtensorMap tmB[2];  // B hi / lo (element strides (1, s, s, 1, 1), box extents bw * s, bh * s)
-  float* dw;           // fp32 [m_valid][n_total][KH][KW], atomically accumulated
+  float* dw;           // fp32, atomically accumulated: element (m, n, ty, tx) at m * sm + (n_off + n) * sn + ty * sty + tx * stx
+  long long sm, sn, sty, stx;   // reference layout [m][n][KH][KW], or "channels last" [m][KH][KW][n] (sn = 1: 16-byte atomics)
   int m_valid, n_valid, n_off, n_total;
   int KH, KW, bpad, bstride;
   int lbw, lbh, lbn, tiles_w, tiles_h, tiles_n;
@@ -341,13 +342,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
         tmem_ld_32x32(taddr + tx * 128 + c0, v);
         tmem_ld_wait();
         if (m < p.m_valid) {
+          float* row = p.dw + (long long)m * p.sm + (long long)ty * p.sty + (long long)tx * p.stx + (long long)(p.n_off + n0c + c0) * p.sn;
+          if (p.sn == 1 && n0c + c0 + 32 <= p.n_valid && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
+            // the 32 columns are contiguous: eight 16-byte reductions instead of 32 scalar ones
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0c + c0 + j;
-            if (n < p.n_valid) {
-              float* dst = p.dw + (((long long)m * p.n_total + p.n_off + n) * p.KH + ty) * KW + tx;
-              atomicAdd(dst, __uint_as_float(v[j]));   // (a plain read-modify-write for unsplit launches measured 5x slower)
-            }
+            for (int q = 0; q < 8; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + 4 * q), "f"(__uint_as_float(v[4 * q])),
+                           "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])), "f"(__uint_as_float(v[4 * q + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0c + c0 + j < p.n_valid) atomicAdd(row + (long long)j * p.sn, __uint_as_float(v[j]));
           }
         }
       }
@@ -435,6 +441,28 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const PackArgs a) {
     const float* sp = a.src + r1 * a.sr1 + r2 * a.sr2 + c * a.sc;
     const long long d0 = row * a.ktot + c;
     for (int tap = 0; tap < a.ntaps; ++tap) st16x(a.hi, a.lo, d0 + (long long)tap * a.cpad, sp[tap * a.st], a.f16);
+  }
+}
+
+// The transposing form: the source is contiguous along the operand's ROWS (sr2 == 1: data-gradient operands of channels-last
+// parameters, transposed matrices, the phase-major ConvTranspose2d rows) -- 32 x 32 tiles through shared memory so that
+// both the fp32 reads and the 16-bit writes are coalesced.  grid = (row tiles, column tiles, R1 * ntaps).
+__global__ void __launch_bounds__(256) pack_weight_t_kernel(const PackArgs a) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r1 = blockIdx.z / a.ntaps, tap = blockIdx.z - r1 * a.ntaps;
+  const int row0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* sp = a.src + r1 * a.sr1 + tap * a.st;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + ty + 8 * j, r2 = row0 + tx;
+    tile[ty + 8 * j][tx] = (c < a.cs && r2 < a.R2) ? sp[r2 + c * a.sc] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r2 = row0 + ty + 8 * j, c = c0 + tx;
+    if (r2 < a.R2 && c < a.cs) st16x(a.hi, a.lo, ((long long)r1 * a.R2 + r2) * a.ktot + (long long)tap * a.cpad + c, tile[tx][ty + 8 * j], a.f16);
   }
 }
 
@@ -666,7 +694,7 @@ extern "C" int b2d_gn_silu_bwd(const void* x_hi, const void* x_lo, int32_t x_f16
 
 extern "C" int b2d_conv_wgrad(int32_t kind, const void* dy_hi, const void* dy_lo, int32_t cout_pad, const void* x_hi, const void* x_lo,
                               int32_t cin_pad, int32_t N, int32_t H, int32_t W, int32_t cout, int32_t cin, int32_t cin_off, int32_t cin_total,
-                              float* dw, int32_t op_f16, void* stream) {
+                              float* dw, int32_t dw_channels_last, int32_t op_f16, void* stream) {
   // H, W: extent of X (for kind 2, ConvTranspose2d k2s2, dY is 2H x 2W)
   if (!dy_hi || !x_hi || !dw || N < 1 || H < 1 || W < 1 || cout < 1 || cin < 1 || cin_off < 0 || cin_off + cin > cin_total ||
       (cout_pad % 64) || (cin_pad % 64) || cout > cout_pad || cin > cin_pad || ((dy_lo == nullptr) != (x_lo == nullptr)) || kind < 0 || kind > 2)
@@ -714,6 +742,8 @@ extern "C" int b2d_conv_wgrad(int32_t kind, const void* dy_hi, const void* dy_lo
       if (r != CUDA_SUCCESS) return set_error(B2D_E_CUDA, "b2d_conv_wgrad: cuTensorMapEncodeTiled failed: %d", (int)r);
     }
   }
+  if (dw_channels_last) { p.sn = 1; p.stx = p.n_total; p.sty = (long long)p.KW * p.n_total; p.sm = (long long)p.KH * p.KW * p.n_total; }
+  else { p.stx = 1; p.sty = p.KW; p.sn = (long long)p.KH * p.KW; p.sm = (long long)p.n_total * p.KH * p.KW; }
   const int m_tiles = (p.m_valid + 127) / 128;
   p.n_tiles = (p.n_valid + 127) / 128;
   int splits = (2 * num_sms()) / (m_tiles * p.n_tiles * p.KH);
@@ -789,6 +819,9 @@ extern "C" int b2d_pack_weight(const float* src, int32_t R1, int32_t R2, int64_t
   a.sr1 = sr1; a.sr2 = sr2; a.st = st; a.sc = sc; a.ktot = ktot;
   a.R2 = R2; a.ntaps = ntaps; a.cs = cs; a.cpad = cpad; a.f16 = f16 ? 1 : 0;
   a.total = (long long)R1 * R2 * ntaps * cs;
-  pack_weight_kernel<<<grid_cap(a.total / ntaps, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  if (sr2 == 1 && sc != 1 && (long long)R1 * ntaps <= 65535)
+    pack_weight_t_kernel<<<dim3((R2 + 31) / 32, (cs + 31) / 32, R1 * ntaps), 256, 0, (cudaStream_t)stream>>>(a);
+  else
+    pack_weight_kernel<<<grid_cap(a.total / ntaps, 256), 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("pack_weight_kernel");
 }

@@ -122,7 +122,8 @@ def gn_silu_bwd(x: Act, dy: Act, dx: Act, stats: torch.Tensor, gamma, beta, act:
 WGRAD_CONV3X3, WGRAD_LINEAR, WGRAD_CONVT2X2 = 0, 1, 2
 
 
-def conv_wgrad(dy: Act, x: Act, dw: torch.Tensor, cout: int, cin: int, cin_off: int, stream: int, kind: int = WGRAD_CONV3X3):
+def conv_wgrad(dy: Act, x: Act, dw: torch.Tensor, cout: int, cin: int, cin_off: int, stream: int, kind: int = WGRAD_CONV3X3,
+               channels_last: bool = False):
     """dw (fp32, the reference's parameter layout) += the weight gradient of the input-channel block starting at cin_off.
     kind: WGRAD_CONV3X3 (dw [Cout, Cin_total, 3, 3]), WGRAD_LINEAR (dw [Cout, Cin_total]; Linear, Conv1d k1),
     WGRAD_CONVT2X2 (dw [Cin, Cout, 2, 2]; dy is the 2H x 2W gradient of the transposed conv's output)."""
@@ -130,9 +131,10 @@ def conv_wgrad(dy: Act, x: Act, dw: torch.Tensor, cout: int, cin: int, cin_off: 
     up = 2 if kind == WGRAD_CONVT2X2 else 1
     assert D == 1 and dy.shape[:4] == (N, 1, H * up, W * up) and dw.dtype == torch.float32 and dw.is_contiguous()
     assert x.f16 == dy.f16 and (x.lo is None) == (dy.lo is None)
-    cin_total = dw.shape[0] if kind == WGRAD_CONVT2X2 else dw.shape[1]
+    # channels_last: dw is [rows, KH, KW, cols] (16-byte vector reductions) instead of the reference's [rows, cols, KH, KW]
+    cin_total = dw.shape[0] if kind == WGRAD_CONVT2X2 else dw.shape[-1] if (channels_last and dw.dim() == 4) else dw.shape[1]
     call("b2d_conv_wgrad", kind, ptr(dy.hi), ptr(dy.lo), dy.C, ptr(x.hi), ptr(x.lo), x.C, N, H, W, cout, cin, cin_off, cin_total,
-         dw.data_ptr(), 1 if x.f16 else 0, stream)
+         dw.data_ptr(), 1 if channels_last else 0, 1 if x.f16 else 0, stream)
 
 
 def channel_sum(x: Act, out: torch.Tensor, cvalid: int, stream: int):
@@ -192,21 +194,25 @@ class LiveOperand:
                  pw.cin_pad[i], 1 if pw.f16 else 0, stream)
 
 
-def live_conv2d(w: torch.Tensor, seg_sizes: Sequence[int], bias, device, split=True) -> LiveOperand:
-    """Forward operand of Conv2d 3x3, weight [Cout, Cin, 3, 3] (w: a contiguous fp32 view of the parameter)."""
-    co, ci = w.shape[:2]
+def live_conv2d(w: torch.Tensor, seg_sizes: Sequence[int], bias, device, split=True, channels_last=False) -> LiveOperand:
+    """Forward operand of Conv2d 3x3 (w: a contiguous fp32 view of the parameter, [Cout, Cin, 3, 3], or [Cout, 3, 3, Cin] if
+    channels_last -- the layout train.UNetTrainer keeps its conv parameters in)."""
+    ref = w.permute(0, 3, 1, 2) if channels_last else w
+    co, ci = ref.shape[:2]
     parts, c0 = [], 0
     for cs in seg_sizes:
-        parts.append((w, c0 * 9, 1, co, 0, ci * 9, 9, 1, cs, 9))
+        parts.append((w, c0, 1, co, 0, ci * 9, 9, ci, cs, 1) if channels_last else (w, c0 * 9, 1, co, 0, ci * 9, 9, 1, cs, 9))
         c0 += cs
-    return LiveOperand(engine.pack_conv2d(w, seg_sizes, bias, device, split=split), parts)
+    return LiveOperand(engine.pack_conv2d(ref, seg_sizes, bias, device, split=split), parts)
 
 
-def live_conv2d_dgrad(w: torch.Tensor, seg: Tuple[int, int], device, split=True) -> LiveOperand:
+def live_conv2d_dgrad(w: torch.Tensor, seg: Tuple[int, int], device, split=True, channels_last=False) -> LiveOperand:
     """Data-gradient operand for input channels [seg0, seg1): rows = Cin of the segment, taps mirrored, columns = Cout."""
-    co, ci = w.shape[:2]
+    ref = w.permute(0, 3, 1, 2) if channels_last else w
+    co, ci = ref.shape[:2]
     c0, c1 = seg
-    return LiveOperand(pack_conv2d_dgrad(w, seg, device, split=split), [(w, c0 * 9 + 8, 1, c1 - c0, 0, 9, 9, -1, co, ci * 9)])
+    part = (w, c0 + 8 * ci, 1, c1 - c0, 0, 1, 9, -ci, co, ci * 9) if channels_last else (w, c0 * 9 + 8, 1, c1 - c0, 0, 9, 9, -1, co, ci * 9)
+    return LiveOperand(pack_conv2d_dgrad(ref, seg, device, split=split), [part])
 
 
 def live_linear(w: torch.Tensor, bias, device, transpose=False, split=True) -> LiveOperand:
@@ -217,15 +223,20 @@ def live_linear(w: torch.Tensor, bias, device, transpose=False, split=True) -> L
     return LiveOperand(engine.pack_linear(w, bias, device, split=split), [(w, 0, 1, o, 0, i, 1, 0, i, 1)])
 
 
-def live_convT2x2(w: torch.Tensor, bias, device, split=True) -> LiveOperand:
-    """Forward operand of ConvTranspose2d k2 s2, weight [Cin, Cout, 2, 2]: rows (phase, co), columns ci."""
-    ci, co = w.shape[:2]
-    return LiveOperand(engine.pack_convT2x2(w, bias, device, split=split), [(w, 0, 4, co, 1, 4, 1, 0, ci, co * 4)])
+def live_convT2x2(w: torch.Tensor, bias, device, split=True, channels_last=False) -> LiveOperand:
+    """Forward operand of ConvTranspose2d k2 s2, weight [Cin, Cout, 2, 2] ([Cin, 2, 2, Cout] if channels_last): rows
+    (phase, co), columns ci."""
+    ref = w.permute(0, 3, 1, 2) if channels_last else w
+    ci, co = ref.shape[:2]
+    part = (w, 0, 4, co, co, 1, 1, 0, ci, co * 4) if channels_last else (w, 0, 4, co, 1, 4, 1, 0, ci, co * 4)
+    return LiveOperand(engine.pack_convT2x2(ref, bias, device, split=split), [part])
 
 
-def live_convT2x2_dgrad(w: torch.Tensor, device, split=True) -> LiveOperand:
-    ci, co = w.shape[:2]
-    return LiveOperand(pack_convT2x2_dgrad(w, device, split=split), [(w, 0, 1, ci, 0, co * 4, 4, 1, co, 4)])
+def live_convT2x2_dgrad(w: torch.Tensor, device, split=True, channels_last=False) -> LiveOperand:
+    ref = w.permute(0, 3, 1, 2) if channels_last else w
+    ci, co = ref.shape[:2]
+    part = (w, 0, 1, ci, 0, co * 4, 4, co, co, 1) if channels_last else (w, 0, 1, ci, 0, co * 4, 4, 1, co, 4)
+    return LiveOperand(pack_convT2x2_dgrad(ref, device, split=split), [part])
 
 
 class StepCache:
@@ -296,9 +307,10 @@ class DoubleBlockGrad:
     time embedding added after block1 (blocks.py:100-103).  Inputs may be a channel concatenation (decoder blocks)."""
 
     def __init__(self, w1, g1, b1, w2, g2, b2, seg_sizes: Sequence[int], device="cuda", workspace: Optional[torch.Tensor] = None,
-                 cache: Optional[StepCache] = None, name: str = "double"):
+                 cache: Optional[StepCache] = None, name: str = "double", channels_last: bool = False):
+        """channels_last: w1 / w2 (and the conv weight gradients `backward` produces) are [Cout, 3, 3, Cin]."""
         dev = torch.device(device)
-        self.dev, self.name = dev, name
+        self.dev, self.name, self.cl = dev, name, channels_last
         self.seg_sizes = list(seg_sizes)
         f = lambda t: t.detach().to(dev, torch.float32).contiguous()
         self.w1, self.w2 = f(w1), f(w2)
@@ -306,14 +318,15 @@ class DoubleBlockGrad:
         self.g1, self.b1, self.g2, self.b2 = f(g1), f(b1), f(g2), f(b2)
         self.cache = cache if cache is not None else StepCache(dev, False)
         sp = self.cache.split
-        self.l1 = live_conv2d(self.w1, self.seg_sizes, None, dev, sp)
-        self.l2 = live_conv2d(self.w2, [self.cmid], None, dev, sp)
-        self.ld2 = live_conv2d_dgrad(self.w2, (0, self.cmid), dev, sp)
+        cl = channels_last
+        self.l1 = live_conv2d(self.w1, self.seg_sizes, None, dev, sp, cl)
+        self.l2 = live_conv2d(self.w2, [self.cmid], None, dev, sp, cl)
+        self.ld2 = live_conv2d_dgrad(self.w2, (0, self.cmid), dev, sp, cl)
         self.ld1, c0 = [], 0
         for cs in self.seg_sizes:
             # the data gradient of a segment is only defined for engine-sized channel counts (the UNet's first layer has
             # 17 input channels and needs none: its input is data)
-            self.ld1.append(live_conv2d_dgrad(self.w1, (c0, c0 + cs), dev, sp) if cs % 64 == 0 else None)
+            self.ld1.append(live_conv2d_dgrad(self.w1, (c0, c0 + cs), dev, sp, cl) if cs % 64 == 0 else None)
             c0 += cs
         self.ws = workspace if workspace is not None else engine.new_workspace(dev)
         self.saved = None
@@ -351,15 +364,16 @@ class DoubleBlockGrad:
         dev, s, c, k = self.dev, _lib.stream_ptr(), self.cache, self.name
         g = {"norm2.weight": _grad_dest(grads, "norm2.weight", (self.cout,), dev), "norm2.bias": _grad_dest(grads, "norm2.bias", (self.cout,), dev),
              "norm1.weight": _grad_dest(grads, "norm1.weight", (self.cmid,), dev), "norm1.bias": _grad_dest(grads, "norm1.bias", (self.cmid,), dev),
-             "conv2.weight": _grad_dest(grads, "conv2.weight", (self.cout, self.cmid, 3, 3), dev),
-             "conv1.weight": _grad_dest(grads, "conv1.weight", (self.cmid, sum(self.seg_sizes), 3, 3), dev), "temb": None}
+             "conv2.weight": _grad_dest(grads, "conv2.weight", (self.cout, 3, 3, self.cmid) if self.cl else (self.cout, self.cmid, 3, 3), dev),
+             "conv1.weight": _grad_dest(grads, "conv1.weight", (self.cmid, 3, 3, sum(self.seg_sizes)) if self.cl
+                                        else (self.cmid, sum(self.seg_sizes), 3, 3), dev), "temb": None}
         if has_temb:
             g["temb"] = c.empty(f"{k}.dtemb", (N, self.cmid))
             g["temb"].zero_()
         d_raw2 = c.act(f"{k}.d_raw2", N, H, W, self.cout)
         gn_silu_bwd(raw2, d_out, d_raw2, st2, self.g2, self.b2, True, g["norm2.weight"], g["norm2.bias"], None, s,
                     sums=c.empty(f"{k}.sums2", (N, 2), torch.float64))
-        conv_wgrad(d_raw2, a1, g["conv2.weight"], self.cout, self.cmid, 0, s)
+        conv_wgrad(d_raw2, a1, g["conv2.weight"], self.cout, self.cmid, 0, s, channels_last=self.cl)
         d_a1 = c.act(f"{k}.d_a1", N, H, W, self.cmid)
         c.plan(f"{k}.dgrad2", lambda: ConvPlan([d_raw2], self.ld2.pw, d_a1, cout=self.cmid, workspace=self.ws)).run(s)
         d_raw1 = c.act(f"{k}.d_raw1", N, H, W, self.cmid)
@@ -367,7 +381,7 @@ class DoubleBlockGrad:
                     sums=c.empty(f"{k}.sums1", (N, 2), torch.float64))
         d_inputs, c0 = [], 0
         for i, (x, cs, ld) in enumerate(zip(inputs, self.seg_sizes, self.ld1)):
-            conv_wgrad(d_raw1, x, g["conv1.weight"], self.cmid, cs, c0, s)
+            conv_wgrad(d_raw1, x, g["conv1.weight"], self.cmid, cs, c0, s, channels_last=self.cl)
             if ld is None:
                 d_inputs.append(None)
             else:
@@ -499,7 +513,12 @@ class UNetTrainer:
         self.in_channels, self.out_channels, self.features = in_channels, out_channels, list(features)
         self.time_dim = time_embedding_dim
         self.heads = attention_heads(attention, len(self.features))
-        self.opt = FlatAdam(state_dict, lr=lr, weight_decay=weight_decay, device=self.dev)
+        # 4-D parameters (Conv2d [Cout, Cin, 3, 3], ConvTranspose2d [Cin, Cout, 2, 2]) are kept with their second index last
+        # ([Cout, 3, 3, Cin], [Cin, 2, 2, Cout]): the order of the packed operands' K axis and of the weight-gradient
+        # kernel's accumulator rows, so refresh and wgrad move contiguous runs; P / G / state_dict present the
+        # reference's layout as views
+        self.opt = FlatAdam({k: (v.permute(0, 2, 3, 1).contiguous() if v.dim() == 4 else v) for k, v in state_dict.items()},
+                            lr=lr, weight_decay=weight_decay, device=self.dev)
         self.scheduler = B200Scheduler(num_timesteps=num_timesteps, device=self.dev)
         self.ws = engine.new_workspace(self.dev)
         if precision not in ("fp32x", "bf16"):
@@ -513,14 +532,26 @@ class UNetTrainer:
         self._build_layers()
 
     # -------------------------------------------------------------------------------- parameters
-    def P(self, name: str) -> torch.Tensor:
+    def _Pk(self, name: str) -> torch.Tensor:
         return self.opt.view(self.opt.param, name)
 
-    def G(self, name: str) -> torch.Tensor:
+    def _Gk(self, name: str) -> torch.Tensor:
         return self.opt.view(self.opt.grad, name)
 
+    @staticmethod
+    def _ref_layout(t: torch.Tensor) -> torch.Tensor:
+        return t.permute(0, 3, 1, 2) if t.dim() == 4 else t
+
+    def P(self, name: str) -> torch.Tensor:
+        """The parameter in the reference's layout (a view of the flat buffer)."""
+        return self._ref_layout(self._Pk(name))
+
+    def G(self, name: str) -> torch.Tensor:
+        """Its gradient, same layout."""
+        return self._ref_layout(self._Gk(name))
+
     def state_dict(self) -> Dict[str, torch.Tensor]:
-        return self.opt.state_dict()
+        return {k: self._ref_layout(v) for k, v in self.opt.state_dict().items()}
 
     def _build_layers(self):
         """Operand forms of the parameters (built once; `refresh_operands` rewrites them in place after each update)."""
@@ -528,9 +559,9 @@ class UNetTrainer:
         L = {}
 
         def double(p, segs):
-            L[p] = DoubleBlockGrad(self.P(f"{p}.block1.conv.weight"), self.P(f"{p}.block1.norm.weight"), self.P(f"{p}.block1.norm.bias"),
-                                   self.P(f"{p}.block2.conv.weight"), self.P(f"{p}.block2.norm.weight"), self.P(f"{p}.block2.norm.bias"),
-                                   segs, dev, workspace=ws, cache=ch, name=p)
+            L[p] = DoubleBlockGrad(self._Pk(f"{p}.block1.conv.weight"), self.P(f"{p}.block1.norm.weight"), self.P(f"{p}.block1.norm.bias"),
+                                   self._Pk(f"{p}.block2.conv.weight"), self.P(f"{p}.block2.norm.weight"), self.P(f"{p}.block2.norm.bias"),
+                                   segs, dev, workspace=ws, cache=ch, name=p, channels_last=True)
 
         def attn(p, c, heads):
             L[p] = AttentionGrad(c, heads, {n: self.P(f"{p}.{n}") for n in self._ATTN}, dev, ws, cache=ch, name=p)
@@ -544,14 +575,15 @@ class UNetTrainer:
         double("bottleneck", [f[-1]])
         rheads = list(reversed(self.heads))
         for lvl, c in enumerate(reversed(f)):
-            w = self.P(f"decoder.{lvl}.0.conv.weight")
-            L[f"decoder.{lvl}.0"] = (live_convT2x2(w, self.P(f"decoder.{lvl}.0.conv.bias"), dev, self.split), live_convT2x2_dgrad(w, dev, self.split))
+            w = self._Pk(f"decoder.{lvl}.0.conv.weight")
+            L[f"decoder.{lvl}.0"] = (live_convT2x2(w, self.P(f"decoder.{lvl}.0.conv.bias"), dev, self.split, True),
+                                     live_convT2x2_dgrad(w, dev, self.split, True))
             double(f"decoder.{lvl}.1", [c, c])
             if rheads[lvl] is not None:
                 attn(f"decoder.{lvl}.2", c, rheads[lvl])
-        wf = self.P("final_conv.weight")
-        L["final_conv"] = (live_conv2d(wf, [f[0]], self.P("final_conv.bias"), dev, self.split),
-                           live_conv2d_dgrad(wf, (0, f[0]), dev, self.split))
+        wf = self._Pk("final_conv.weight")
+        L["final_conv"] = (live_conv2d(wf, [f[0]], self.P("final_conv.bias"), dev, self.split, True),
+                           live_conv2d_dgrad(wf, (0, f[0]), dev, self.split, True))
         self._layers = L
 
     def refresh_operands(self):
@@ -606,7 +638,7 @@ class UNetTrainer:
         ch = self.cache
         ch.begin_step()
         self.opt.zero_grad()
-        G = self.G
+        G = self._Gk   # kernel layout: the weight-gradient kernel accumulates channels-last
         temb, leaves = self._time_forward(t) if self.time_dim is not None else ({}, {})
         x_in = ch.act("x_in", N, h, w, engine.pad64(self.in_channels), zero=True)
         engine.planar_to_cl(x.contiguous().float(), x_in, N, self.in_channels, h * w, 0, None, s)
@@ -655,7 +687,7 @@ class UNetTrainer:
         d = ch.act("d_pred", N, h, w, engine.pad64(oc), zero=True)
         engine.planar_to_cl(d_pred, d, N, oc, h * w, 0, None, s)
         channel_sum(d, G("final_conv.bias"), oc, s)
-        conv_wgrad(d, final_in, G("final_conv.weight"), oc, c0, 0, s)
+        conv_wgrad(d, final_in, G("final_conv.weight"), oc, c0, 0, s, channels_last=True)
         da = ch.act("d_final_in", N, h, w, c0)
         ch.plan("final_conv.dgrad", lambda: ConvPlan([d], L["final_conv"][1].pw, da, cout=c0, workspace=self.ws)).run(s)
         d_skips = [None] * nl
@@ -680,7 +712,7 @@ class UNetTrainer:
             d_raw = ch.act(f"{q}.d_raw", N, H2, W2, c)
             gn_silu_bwd(raw, d_up, d_raw, ust, self.P(f"{q}.norm.weight"), self.P(f"{q}.norm.bias"), True, G(f"{q}.norm.weight"),
                         G(f"{q}.norm.bias"), None, s, sums=ch.empty(f"{q}.sums", (N, 2), torch.float64))
-            conv_wgrad(d_raw, x_lo, G(f"{q}.conv.weight"), c, 2 * c, 0, s, kind=WGRAD_CONVT2X2)
+            conv_wgrad(d_raw, x_lo, G(f"{q}.conv.weight"), c, 2 * c, 0, s, kind=WGRAD_CONVT2X2, channels_last=True)
             channel_sum(d_raw, G(f"{q}.conv.bias"), c, s)
             da = ch.act(f"{q}.d_in", N, H2 // 2, W2 // 2, 2 * c)
             d_in = da

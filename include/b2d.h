@@ -283,10 +283,12 @@ B2D_API int b2d_gn_silu_bwd(const void* x_hi, const void* x_lo, int32_t x_f16, c
  * dY [N][H'][W'][cout_pad], X [N][H][W][cin_pad] channels-last 16-bit (hi + optional bf16 lo: three products hi*hi + hi*lo
  * + lo*hi); H, W = extent of X, powers of two (kind 2: dY is 2H x 2W).  dw: fp32 in the reference's parameter layout,
  * atomically accumulated (zero it first); cin_off selects the channel block of a concatenated input (torch.cat skip | up,
- * unet/models.py:177). */
+ * unet/models.py:177).  dw_channels_last: dw is [rows][KH][KW][cols] (the last index of the reference layout moved to the
+ * end: [Cout][3][3][Cin], [Cin][2][2][Cout]) -- a thread's 32 columns are then contiguous and go out as 16-byte vector
+ * reductions, a quarter of the atomic traffic that bounds this kernel (train.UNetTrainer keeps its parameters that way). */
 B2D_API int b2d_conv_wgrad(int32_t kind, const void* dy_hi, const void* dy_lo, int32_t cout_pad, const void* x_hi, const void* x_lo,
                    int32_t cin_pad, int32_t N, int32_t H, int32_t W, int32_t cout, int32_t cin, int32_t cin_off, int32_t cin_total,
-                   float* dw, int32_t op_f16, void* stream);
+                   float* dw, int32_t dw_channels_last, int32_t op_f16, void* stream);
 /* out[c] += sum over rows of x[row][c], c < cvalid (bias gradients = sum of dY over pixels); x [rows][C] 16-bit hi (+ lo),
  * atomically accumulated (zero it first). */
 B2D_API int b2d_channel_sum(const void* x_hi, const void* x_lo, int32_t f16, int64_t rows, int32_t C, int32_t cvalid, float* out, void* stream);

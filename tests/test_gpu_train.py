@@ -117,6 +117,12 @@ def test_conv_wgrad(N, co, ci, H, W, split):
     ref = torch.nn.grad.conv2d_weight(x[:, :, 0], (co, ci, 3, 3), dy[:, :, 0], padding=1)
     assert dw[:, :5].abs().max().item() == 0
     assert rel_l2(dw[:, 5:], ref) <= (2e-5 if split else 1e-5), rel_l2(dw[:, 5:], ref)
+    # the trainer's layout [Cout, 3, 3, Cin]: 16-byte vector reductions where a thread's 32 columns are aligned
+    for off in (0, 4, 5):
+        dwc = torch.zeros(co, 3, 3, ci + off, device=DEV)
+        train.conv_wgrad(dya, xa, dwc, co, ci, off, _s(), channels_last=True)
+        assert dwc[..., :off].abs().max().item() == 0 if off else True
+        assert rel_l2(dwc[..., off:].permute(0, 3, 1, 2), ref) <= (2e-5 if split else 1e-5)
 
 
 @pytest.mark.parametrize("N,co,ci,H,W", [(2, 768, 256, 8, 8), (3, 64, 128, 1, 1), (2, 1024, 1024, 2, 2), (4, 200, 72, 4, 8)])
@@ -147,6 +153,9 @@ def test_conv_transpose_gradients(N, ci, co, H, W):
     dw = torch.zeros(ci, co, 2, 2, device=DEV)
     train.conv_wgrad(dya, xa, dw, co, ci, 0, _s(), kind=train.WGRAD_CONVT2X2)
     assert rel_l2(dw, w.grad) <= 2e-5, rel_l2(dw, w.grad)
+    dwc = torch.zeros(ci, 2, 2, co, device=DEV)
+    train.conv_wgrad(dya, xa, dwc, co, ci, 0, _s(), kind=train.WGRAD_CONVT2X2, channels_last=True)
+    assert rel_l2(dwc.permute(0, 3, 1, 2), w.grad) <= 2e-5
     db = torch.zeros(co, device=DEV)
     train.channel_sum(dya, db, co, _s())
     assert rel_l2(db, b.grad) <= 1e-5
@@ -313,6 +322,15 @@ def test_operand_refresh_in_place():
              train.live_linear(wl, None, DEV, transpose=True), train.live_convT2x2(wt, None, DEV), train.live_convT2x2_dgrad(wt, DEV)]
     for a, b in zip(live, fresh):
         assert not torch.equal(a.pw.w.view(torch.int16), b.pw.w.view(torch.int16))
+        a.refresh(s)
+        assert torch.equal(a.pw.w.view(torch.int16), b.pw.w.view(torch.int16))
+    # the same operands from channels-last parameters ([Cout, 3, 3, Cin], [Cin, 2, 2, Cout]: the trainer's layout)
+    wc, wtc = w.permute(0, 2, 3, 1).contiguous(), wt.permute(0, 2, 3, 1).contiguous()
+    live_cl = [train.live_conv2d(wc, [64, 17], None, DEV, channels_last=True), train.live_conv2d_dgrad(wc, (0, 64), DEV, channels_last=True),
+               train.live_convT2x2(wtc, None, DEV, channels_last=True), train.live_convT2x2_dgrad(wtc, DEV, channels_last=True)]
+    for a, b in zip(live_cl, [fresh[0], fresh[1], fresh[4], fresh[5]]):
+        assert torch.equal(a.pw.w.view(torch.int16), b.pw.w.view(torch.int16))
+        a.pw.w.zero_()
         a.refresh(s)
         assert torch.equal(a.pw.w.view(torch.int16), b.pw.w.view(torch.int16))
 
