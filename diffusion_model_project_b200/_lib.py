@@ -9,7 +9,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2d.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 B2D_MAX_SEG = 6
 B2D_MAX_TAPS = 27
 
@@ -49,6 +49,11 @@ class ConvDesc(C.Structure):
         ("in_stats", c_void_p), ("in_gamma", c_void_p), ("in_beta", c_void_p),
         ("in_cpg", c_i32), ("in_creal", c_i32), ("in_f16", c_i32), ("in_act", c_i32),
         ("in_eps", c_float),
+        ("in_temb", c_void_p),
+        ("in_temb_row", c_void_p),
+        ("in_temb_row_stride", c_i32),
+        ("in_temb_ncols", c_i32),
+        ("in_temb_col", c_i32),
         ("tune_flags", c_i32),
         ("op_f16", c_i32),
         ("sched_kind", c_i32),

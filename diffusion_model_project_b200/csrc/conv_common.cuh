@@ -107,6 +107,9 @@ struct ConvKParams {
   int in_f16, in_act;          // raw values are fp16 (else bf16); apply SiLU
   float in_eps;
   double in_count;             // elements per (sample, group): in_cpg * D * H * W
+  const float* in_temb;        // optional per-(sample, channel) addend after the activation (time embedding)
+  const int* in_temb_row;
+  int in_temb_row_stride, in_temb_ncols, in_temb_col;
   // ---- out_mode 3: fused sampler update (b2d_conv_desc.sched_*) ----
   float* sch_x;
   const float* sch_noise;

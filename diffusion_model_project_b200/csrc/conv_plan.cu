@@ -339,6 +339,12 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
     k.in_cpg = d->in_cpg; k.in_creal = d->in_creal; k.in_f16 = d->in_f16 ? 1 : 0; k.in_act = d->in_act ? 1 : 0;
     k.in_eps = d->in_eps;
     k.in_count = (double)d->in_cpg * d->D * d->H * d->W;
+    k.in_temb = d->in_temb; k.in_temb_row = d->in_temb_row;
+    k.in_temb_row_stride = d->in_temb_row_stride; k.in_temb_ncols = d->in_temb_ncols; k.in_temb_col = d->in_temb_col;
+    if (k.in_temb && (!k.in_temb_row || k.in_temb_ncols < k.in_temb_col + d->in_creal || k.in_temb_col < 0)) {
+      delete pl;
+      return set_error(B2D_E_INVALID, "fused input normalisation: bad time-embedding arguments");
+    }
   }
 
   pl->block_n = bn;

@@ -42,7 +42,7 @@ struct V2Cfg {
   static constexpr int NBARS = 3 * NA + 2 * NB + 4;
   static constexpr int STAGE_BYTES = HALO ? 0 : 2048 * EPI_WARPS; // generic tiles: per-warp store staging (coalesced 16-bit stores)
   static constexpr int BIAS_BYTES = MT * BN * 4;                // per four-warp epilogue group: the tile's bias
-  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 * EPI_WARPS + (XFORM ? 2 * XF_MAXC * 4 + 16 : 0) + BIAS_BYTES + STAGE_BYTES + 16 + 1024;
+  static constexpr int SMEM = NA * A_STAGE + NB * B_STAGE + NBARS * 8 + 64 + 512 * EPI_WARPS + (XFORM ? 3 * XF_MAXC * 4 + 16 : 0) + BIAS_BYTES + STAGE_BYTES + 16 + 1024;
   static_assert(NACC * ACC_COLS <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static_assert(!HALO || 9 % TPB == 0, "taps per stage must divide 9");
@@ -97,8 +97,8 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [epilogue groups <= 2]
   double* sm_stats = reinterpret_cast<double*>(tmem_slot + 4);               // [EPI_WARPS][64] per-warp GroupNorm sums (halo mode)
-  float* sm_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_stats + 64 * Cfg::EPI_WARPS) + 15) & ~uintptr_t(15));  // XFORM: [2][XF_MAXC] scale, shift
-  float* sm_bias = sm_coef + (XFORM ? 2 * Cfg::XF_MAXC : 0);  // [MT][BN], 16-byte aligned
+  float* sm_coef = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm_stats + 64 * Cfg::EPI_WARPS) + 15) & ~uintptr_t(15));  // XFORM: [3][XF_MAXC] scale, shift, addend
+  float* sm_bias = sm_coef + (XFORM ? 3 * Cfg::XF_MAXC : 0);  // [MT][BN], 16-byte aligned
   uint8_t* sm_stage = reinterpret_cast<uint8_t*>(sm_bias + MT * BN);  // [EPI_WARPS][2048], generic tiles only
 
   // warp index through a shuffle: provably warp-uniform, so the role loops below run on the uniform datapath
@@ -474,7 +474,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     const int row0 = xt >> 3;                                 // 16 rows per pass
     float* coef_a = sm_coef;
     float* coef_b = sm_coef + Cfg::XF_MAXC;
-    const uint32_t coef_a_u = smem_u32(coef_a), coef_b_u = smem_u32(coef_b);
+    float* coef_c = sm_coef + 2 * Cfg::XF_MAXC;
+    const uint32_t coef_a_u = smem_u32(coef_a), coef_b_u = smem_u32(coef_b), coef_c_u = smem_u32(coef_c);
+    const bool has_add = p.in_temb != nullptr;
     const int cin_pad = p.cin[0];
     const int ngrp = p.in_creal / p.in_cpg;
     const bool act_on = p.in_act != 0, in_f16 = p.in_f16 != 0;
@@ -502,6 +504,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
           }
           coef_a[c] = act_on ? 0.5f * a : a;
           coef_b[c] = act_on ? 0.5f * b : b;
+          coef_c[c] = (has_add && c < p.in_creal)
+                          ? __ldg(p.in_temb + (long long)__ldg(p.in_temb_row + (long long)uc.n0 * p.in_temb_row_stride) * p.in_temb_ncols + p.in_temb_col + c)
+                          : 0.f;
         }
         asm volatile("bar.sync 4, 128;" ::: "memory");
         cur_n = uc.n0;
@@ -562,6 +567,10 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
                 asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(f[j]));
                 f[j] = fmaf(f[j], t, f[j]);
               }
+            }
+            if (has_add) {
+              const float4 d0 = lds128f(coef_c_u + c0[q] * 4), d1 = lds128f(coef_c_u + c0[q] * 4 + 16);
+              f[0] += d0.x; f[1] += d0.y; f[2] += d0.z; f[3] += d0.w; f[4] += d1.x; f[5] += d1.y; f[6] += d1.z; f[7] += d1.w;
             }
             if (live[q]) sts128(vaddr[q], make_uint4(pack16(f[0], f[1], op_f16), pack16(f[2], f[3], op_f16), pack16(f[4], f[5], op_f16), pack16(f[6], f[7], op_f16)));
           }

@@ -233,9 +233,11 @@ class ConvPlan:
                  out_mode: int = 0, out_geom=None, residual: Optional[Act] = None, stats: Optional[torch.Tensor] = None,
                  stats_cpg: int = 0, out_scale=None, out_mask=None, block_n: int = 0, out_cstride=None, out_coff: int = 0,
                  in_norm=None, workspace: Optional[torch.Tensor] = None, tune_flags: int = 0, tune_ksplit: int = 0,
-                 sched: Optional[dict] = None):
+                 sched: Optional[dict] = None, in_temb=None):
         """in_norm = (stats, cpg, gamma, beta, act[, eps]): inputs[0] is a RAW pre-GroupNorm tensor and the kernel applies
         GroupNorm (+SiLU) to each staged tile (halo staging only; see include/b2d.h).
+        in_temb = (table [T, ncols] fp32, row [N * stride] int32, row_stride, col): with in_norm, the DoubleBlock's time
+        embedding table[row[n * stride], col + c] is added after the activation.
         workspace: split-K scratch (new_workspace); default: the (device, current stream) one.
         sched: out_mode 3 -- fuse the sampler update into the epilogue (b2d_conv_desc.sched_*): dict(kind, x, coef, state
         [int32: step index, ticket, 64-bit seed at word 2], noise=None, clip=(lo, hi) or None, x_bf16: Act or None,
@@ -325,10 +327,15 @@ class ConvPlan:
             d.in_f16 = 1 if inputs[0].f16 else 0
             d.in_act = 1 if act_in else 0
             d.in_eps = in_norm[5] if len(in_norm) > 5 else 1e-5
+            if in_temb is not None:
+                tt, trow, tstride, tcol = in_temb
+                assert tt.dtype == torch.float32 and tt.is_contiguous() and trow.dtype == torch.int32
+                d.in_temb, d.in_temb_row = tt.data_ptr(), trow.data_ptr()
+                d.in_temb_row_stride, d.in_temb_ncols, d.in_temb_col = tstride, tt.shape[1], tcol
         ws = workspace if workspace is not None else default_workspace(inputs[0].hi.device)
         d.workspace = ws.data_ptr()
         d.workspace_bytes = ws.numel()
-        self._keep = (inputs, pw, out, residual, stats, out_scale, out_mask, in_norm, ws, sched)
+        self._keep = (inputs, pw, out, residual, stats, out_scale, out_mask, in_norm, ws, sched, in_temb)
         self.desc = d
         self.handle = C.c_void_p()
         _lib.check(_lib.lib().b2d_conv_plan_create(C.byref(d), C.byref(self.handle)), "b2d_conv_plan_create")

@@ -52,6 +52,11 @@ class B200UNet:
         self.temb_table: Optional[torch.Tensor] = None
         self._temb_cols: Dict[str, int] = {}
         self.conv_tune_flags = 0   # _lib.TUNE_* bits handed to every conv plan (A/B measurements; 0 in production)
+        # block2's halo-staged conv applies block1's GroupNorm + SiLU + time embedding to its staged tiles (16-bit modes,
+        # maps that are multiples of 16 x 16, <= 512 channels) instead of a separate pass.  Parity-green, measured SLOWER
+        # (UNet step 1841 -> 2006 us at 88 slice-images, 9689 -> 10417 at 704: the six convs lose more to the tile rewrite
+        # than the six norm passes cost; profiles/README.md): off
+        self.fuse_block1_norm = False
 
     # ------------------------------------------------------------------------------ weights
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
@@ -182,7 +187,8 @@ class B200UNet:
                                   dtype=torch.float32, device=dev)
         keep = []
 
-        def conv_gn_act(name, inputs, pw, cout, H, Wd, gnw, *, temb_col=None, stats_out=None, nphase=1, second=None):
+        def conv_gn_act(name, inputs, pw, cout, H, Wd, gnw, *, temb_col=None, stats_out=None, nphase=1, second=None, in_norm=None,
+                        in_temb=None, defer_norm=False):
             """conv (+GN sums in the epilogue) -> in-place GN apply + SiLU (+temb).  second = (name2, y2, gamma2, beta2): the
             same launch also writes y2 = GN(out; gamma2, beta2) (the attention pre-norm), per-sample fused form."""
             up = 2 if nphase == 4 else 1
@@ -191,10 +197,14 @@ class B200UNet:
             raw = new_act(N, 1, H * up, Wd * up, cout, dev, sp, f16=True)
             out = raw.as_fmt(F16)
             st = stats_view(stats_alloc(1), N * 2)
-            plan = ConvPlan(inputs, pw, raw, cout=cout, nphase=nphase, stats=st, stats_cpg=cout, workspace=ws, tune_flags=self.conv_tune_flags)
+            plan = ConvPlan(inputs, pw, raw, cout=cout, nphase=nphase, stats=st, stats_cpg=cout, workspace=ws, tune_flags=self.conv_tune_flags,
+                            in_norm=in_norm, in_temb=in_temb)
             prog.flops += plan.flops
             prog.add(f"{name}.conv", plan.run)
             g, b = gnw
+            if defer_norm:   # the consumer applies this layer's GroupNorm + SiLU (+ time embedding) to its staged tiles
+                keep.append(plan)
+                return raw, st
             if second is not None:
                 assert temb_col is None and stats_out is None
                 name2, y2, g2, b2 = second
@@ -209,6 +219,15 @@ class B200UNet:
 
         def double(prefix, inputs, cmid, cout, H, Wd, stats_out=None, second=None):
             tc = self._temb_cols.get(prefix) if temb_table is not None else None
+            if self.fuse_block1_norm and not sp and H % 16 == 0 and Wd % 16 == 0 and cmid <= 512:
+                # block2's conv is halo-staged: it normalises block1's raw output tile by tile in shared memory
+                # (b2d_conv_desc.in_stats / in_temb) -- one launch and one pass over the activation less
+                raw1, st1 = conv_gn_act(f"{prefix}.block1", inputs, W_[f"{prefix}.block1.conv"], cmid, H, Wd, W_[f"{prefix}.block1.norm"],
+                                        defer_norm=True)
+                g1, b1 = W_[f"{prefix}.block1.norm"]
+                return conv_gn_act(f"{prefix}.block2", [raw1], W_[f"{prefix}.block2.conv"], cout, H, Wd, W_[f"{prefix}.block2.norm"],
+                                   stats_out=stats_out, second=second, in_norm=(st1, cmid, g1, b1, True),
+                                   in_temb=(temb_table, temb_row, temb_row_stride, tc) if tc is not None else None)
             a = conv_gn_act(f"{prefix}.block1", inputs, W_[f"{prefix}.block1.conv"], cmid, H, Wd, W_[f"{prefix}.block1.norm"], temb_col=tc)
             return conv_gn_act(f"{prefix}.block2", [a], W_[f"{prefix}.block2.conv"], cout, H, Wd, W_[f"{prefix}.block2.norm"],
                                stats_out=stats_out, second=second)

@@ -34,7 +34,7 @@ extern "C" {
 #define B2D_API
 #endif
 
-#define B2D_VERSION 7
+#define B2D_VERSION 8
 #define B2D_MAX_SEG 6
 #define B2D_MAX_TAPS 27
 
@@ -136,6 +136,11 @@ typedef struct b2d_conv_desc {
   int32_t in_cpg, in_creal;        /* channels per group; real (unpadded) input channels                 */
   int32_t in_f16, in_act;
   float in_eps;
+  /* ... + the DoubleBlock's time embedding (unet/blocks.py:100-103), added after the activation:
+   * + in_temb[in_temb_row[n * in_temb_row_stride] * in_temb_ncols + in_temb_col + c]; NULL = none */
+  const float* in_temb;
+  const int32_t* in_temb_row;
+  int32_t in_temb_row_stride, in_temb_ncols, in_temb_col;
   int32_t tune_flags;              /* B2D_TUNE_* bits (comparison arms of the tests / tools; 0 in production)      */
   int32_t op_f16;                  /* the MMA operands -- in[] (after the fused input normalisation, if any) and weight --
                                       hold IEEE fp16 instead of bf16 (tcgen05 kind::f16 takes either at the same rate);

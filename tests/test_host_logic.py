@@ -124,7 +124,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.b2d_version() == _lib.ABI_VERSION == 7
+    assert lib.b2d_version() == _lib.ABI_VERSION == 8
 
 
 def test_abi_rejects_bad_arguments_without_a_gpu():

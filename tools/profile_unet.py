@@ -16,6 +16,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 torch.set_grad_enabled(False)
 m = B200UNet(**synth.UNET_KWARGS, device="cuda").load_state_dict(synth.synth_unet_state(seed=0))
 m.conv_tune_flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+m.fuse_block1_norm = len(sys.argv) > 5 and sys.argv[5] == "fuse1"   # block1's norm applied inside block2's conv
 st = m.build_program(N, 64, 64)
 st["x_in"].hi.view(torch.float16).copy_(torch.randn(N, 1, 64, 64, 64, device="cuda").to(torch.float16))
 prog = st["program"]
