@@ -249,7 +249,7 @@ class StepCache:
     def __init__(self, device, persistent: bool, split: bool = True):
         self.dev, self.persistent, self.split = torch.device(device), persistent, split
         self.store: dict = {}
-        self.pool = torch.zeros(self.POOL_DOUBLES, dtype=torch.float64, device=self.dev) if persistent else None
+        self.pools: List[torch.Tensor] = []   # fp64 accumulator pools (a new one is added when the last is full)
         self.pool_used = 0
 
     def get(self, key, make):
@@ -273,8 +273,10 @@ class StepCache:
             n = 1
             for d in shape:
                 n *= d
-            assert self.pool_used + n <= self.POOL_DOUBLES
-            t = self.pool[self.pool_used:self.pool_used + n].view(shape)
+            if not self.pools or self.pool_used + n > self.pools[-1].numel():
+                self.pools.append(torch.zeros(max(self.POOL_DOUBLES, n), dtype=torch.float64, device=self.dev))
+                self.pool_used = 0
+            t = self.pools[-1][self.pool_used:self.pool_used + n].view(shape)
             self.pool_used += n
             return t
         return self.get(key, make)
@@ -285,13 +287,12 @@ class StepCache:
     def reset(self):
         """Forget every buffer and plan (a new batch shape); the accumulator pool is handed out again from a clean state."""
         self.store.clear()
+        self.pools.clear()
         self.pool_used = 0
-        if self.pool is not None:
-            self.pool.zero_()
 
     def begin_step(self):
-        if self.persistent and self.pool_used:
-            self.pool[:self.pool_used].zero_()
+        for pool in self.pools:
+            pool.zero_()
 
 
 def _grad_dest(grads: Optional[dict], key: str, shape, dev) -> torch.Tensor:
@@ -509,6 +510,11 @@ class UNetTrainer:
         from .synth import attention_heads
         if not torch.cuda.is_available():
             raise RuntimeError("UNetTrainer runs on a CUDA device only (no CPU fallback)")
+        # the configurations B200UNet supports (the shipped model): anything else is refused, not approximated
+        bad = {k: v for k, v in _ignored.items() if (k, v) not in (("kernel_size", 3), ("padding_mode", "zeros"), ("activation", "silu"),
+                                                                    ("final_activation", None), ("dropout", 0.0))}
+        if bad:
+            raise NotImplementedError(f"UNetTrainer: unsupported model arguments {bad}")
         self.dev = torch.device(device)
         self.in_channels, self.out_channels, self.features = in_channels, out_channels, list(features)
         self.time_dim = time_embedding_dim

@@ -380,3 +380,5 @@ def test_bf16_training_step_tracks_the_reference(golden_dir):
     assert sorted(errs.values())[len(errs) // 2] <= 0.1
     with pytest.raises(ValueError):
         train.UNetTrainer(sd, **synth.UNET_KWARGS, device=DEV, precision="fp8")
+    with pytest.raises(NotImplementedError):
+        train.UNetTrainer(sd, **{**synth.UNET_KWARGS, "padding_mode": "reflect"}, device=DEV)
