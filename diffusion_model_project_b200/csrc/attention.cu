@@ -28,9 +28,8 @@
 
 namespace b2d {
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 512;                        // at most; the launch uses 128, 256 or 512 (what shared memory allows)
 constexpr int kQPW = 4;                                  // queries processed together by one warp
-constexpr int kQB = (kAttnThreads / 32) * kQPW;          // queries per CTA
 
 __device__ __forceinline__ float a_bflo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float a_bfhi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
@@ -70,7 +69,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __nv_bflo
   const int dp = d + 8;  // +16 bytes per row: lanes reading different rows hit different banks
   const int nh = blockIdx.y;
   const int n = nh / heads, h = nh - n * heads;
-  const int q0 = blockIdx.x * kQB;
+  const int kQB = (int)(blockDim.x >> 5) * kQPW;   // queries per CTA: every CTA stages all of K, then all of V -- the more
+  const int q0 = blockIdx.x * kQB;                 // queries share that, the less redundant staging
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   __nv_bfloat16* kv = reinterpret_cast<__nv_bfloat16*>(smem_attn);
@@ -283,8 +283,15 @@ extern "C" int b2d_attention(const void* qkv, const void* qkv_lo, void* out, voi
         p_bytes <= (size_t)dch * kQChunkBytes + (size_t)dch * T * 128 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
       return launch_attention_tc(qkv, out, N, T, C, heads, f16, (cudaStream_t)stream);
   }
-  const size_t smem = (size_t)T * (d + 8) * 2 * (split ? 2 : 1) + (size_t)kQB * T * 4 + (size_t)kQB * d * 4;
-  if (smem > 227 * 1024 - 1024) return set_error(B2D_E_INVALID, "b2d_attention: T=%d d=%d needs %zu bytes of shared memory", T, d, smem);
+  int threads = 512;
+  size_t smem = 0;
+  for (;; threads >>= 1) {   // the largest query block whose score tile and staged K / V fit
+    const int qb = (threads / 32) * kQPW;
+    smem = (size_t)T * (d + 8) * 2 * (split ? 2 : 1) + (size_t)qb * T * 4 + (size_t)qb * d * 4;
+    if (smem <= 227 * 1024 - 1024 && (qb < 2 * T || threads == 128)) break;
+    if (threads == 128) return set_error(B2D_E_INVALID, "b2d_attention: T=%d d=%d needs %zu bytes of shared memory", T, d, smem);
+  }
+  const int kQB = (threads / 32) * kQPW;
   dim3 grid((T + kQB - 1) / kQB, N * heads);
   const float scale = 1.0f / sqrtf((float)d);
   // opt in to the full dynamic shared-memory carve-out once per kernel variant (not a stream operation)
@@ -295,10 +302,10 @@ extern "C" int b2d_attention(const void* qkv, const void* qkv_lo, void* out, voi
     if (e != cudaSuccess) return set_error(B2D_E_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
   }
   if (split) {
-    attention_kernel<true><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(
+    attention_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_lo, (__nv_bfloat16*)out, (__nv_bfloat16*)out_lo, T, C, heads, scale, 0);
   } else {
-    attention_kernel<false><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(
+    attention_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)qkv, nullptr, (__nv_bfloat16*)out, nullptr, T, C, heads, scale, f16 ? 1 : 0);
   }
   return check_launch("attention_kernel");

@@ -176,6 +176,17 @@ def pack_convT2x2_dgrad(w: torch.Tensor, device, split=False, f16=False) -> engi
     return engine.pack_weight(w.permute(0, 2, 3, 1).reshape(ci, 4, co), [co], taps, None, device, split, f16=f16)
 
 
+class _no_tf32:
+    """The parameter-space products of the folded attention projections are IEEE fp32 whatever the process-wide setting."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 # ------------------------------------------------------------------------------------------------ step-persistent state
 class LiveOperand:
     """A packed conv operand (engine.PackedWeight) together with the recipe that rewrites it IN PLACE from its fp32 source
@@ -422,8 +433,10 @@ class AttentionGrad:
         self.saved = None
 
     def refresh_folded(self):
-        self.w_out.copy_(self.wp.double() @ self.wo.double())
-        self.b_out.copy_(self.wp.double() @ self.bo.double() + self.bp.double())
+        # fp32 products (IEEE, no TF32): the folded operand is rounded to bf16 hi + lo (2^-16) right after
+        with _no_tf32():
+            torch.matmul(self.wp, self.wo, out=self.w_out)
+            torch.addmv(self.bp, self.wp, self.bo, out=self.b_out)
 
     def operands(self) -> List[LiveOperand]:
         return [self.l_in, self.l_out, self.l_in_t, self.l_out_t]
@@ -468,10 +481,9 @@ class AttentionGrad:
                     sums=ch.empty(f"{k}.sums", (N, 2), torch.float64))
         add_acts(d_x, d_y, d_x, s)
         # W = Wp Wo, b = Wp bo + bp  ->  dWp = dW Wo^T + db bo^T, dWo = Wp^T dW, dbo = Wp^T db, dbp = db
-        dW, db = d_wout.double(), d_bout.double()
-        out = {"proj_out.weight": (dW @ self.wo.double().t() + torch.outer(db, self.bo.double())).float()[:, :, None],
-               "proj_out.bias": d_bout, "mha.out_proj.weight": (self.wp.double().t() @ dW).float(),
-               "mha.out_proj.bias": (self.wp.double().t() @ db).float()}
+        with _no_tf32():
+            out = {"proj_out.weight": torch.addmm(torch.outer(d_bout, self.bo), d_wout, self.wo.t())[:, :, None],
+                   "proj_out.bias": d_bout, "mha.out_proj.weight": self.wp.t() @ d_wout, "mha.out_proj.bias": self.wp.t() @ d_bout}
         for key, v in out.items():
             if grads is not None and key in grads:
                 grads[key].copy_(v)
