@@ -151,10 +151,51 @@ struct GnBwdArgs {
   float eps;
 };
 
-// pass 1: per-sample sums of dxhat and dxhat * xhat, per-channel dgamma / dbeta (/ dtemb).  grid (blocks per sample, N)
+// eight consecutive channels of a 16-bit hi (+ lo) tensor as fp32 (one 16-byte load per part)
+__device__ __forceinline__ void ld16x8(const uint16_t* hi, const uint16_t* lo, long long i, int f16, float (&f)[8]) {
+  const uint4 uh = __ldg(reinterpret_cast<const uint4*>(hi + i));
+  const uint32_t wh[4] = {uh.x, uh.y, uh.z, uh.w};
+  if (f16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(&wh[j]));
+      f[2 * j] = t2.x; f[2 * j + 1] = t2.y;
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(wh[j] << 16); f[2 * j + 1] = __uint_as_float(wh[j] & 0xFFFF0000u); }
+  if (lo != nullptr) {
+    const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lo + i));
+    const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] += __uint_as_float(wl[j] << 16); f[2 * j + 1] += __uint_as_float(wl[j] & 0xFFFF0000u); }
+  }
+}
+__device__ __forceinline__ void st16x8(uint16_t* hi, uint16_t* lo, long long i, int f16, const float (&f)[8]) {
+  uint32_t wh[4], wl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (f16) {
+      const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+      wh[j] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
+      wh[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
+      wl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+  }
+  *reinterpret_cast<uint4*>(hi + i) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+  if (!f16 && lo != nullptr) *reinterpret_cast<uint4*>(lo + i) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+}
+
+// pass 1: per-sample sums of dxhat and dxhat * xhat, per-channel dgamma / dbeta (/ dtemb).  grid (blocks per sample, N).
+// A thread owns one group of 8 channels for its whole walk (the grid stride, 256 * gridDim.x vectors, is a multiple of the
+// C / 8 vectors of a pixel): channel sums stay in registers and meet in shared memory once per thread.
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
   extern __shared__ float sm_ch[];  // [3][C]
-  const int n = blockIdx.y, C = a.C;
+  const int n = blockIdx.y, C = a.C, cv = C >> 3;
   for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) sm_ch[c] = 0.f;
   __syncthreads();
   const double cnt = (double)C * (double)a.P;
@@ -162,28 +203,49 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
   double var = a.stats[2 * n + 1] / cnt - mean_d * mean_d;
   if (var < 0) var = 0;
   const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var + (double)a.eps));
-  const long long total = a.P * C, base = (long long)n * total;
-  // blockDim.x (256) is a multiple of min(C, 256) for the UNet's channel counts, and the grid stride is a multiple of C
-  // whenever C <= 256 * gridDim.x: keep it simple and general -- shared-memory atomics per element group of one channel
-  double s1 = 0.0, s2 = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const float x = ld16x(a.x_hi, a.x_lo, base + i, a.x_f16);
-    const float dy = ld16x(a.dy_hi, a.dy_lo, base + i, a.dy_f16);
-    const float xh = (x - mean) * rstd;
-    const float ga = a.gamma ? a.gamma[c] : 1.f, be = a.beta ? a.beta[c] : 0.f;
-    const float dz = a.act ? dy * dsilu(fmaf(ga, xh, be)) : dy;
-    const float dxh = dz * ga;
-    s1 += (double)dxh;
-    s2 += (double)dxh * xh;
-    atomicAdd(&sm_ch[c], dz * xh);
-    atomicAdd(&sm_ch[C + c], dz);
-    if (a.dtemb != nullptr) atomicAdd(&sm_ch[2 * C + c], dy);
+  const long long nvec = a.P * cv, base = (long long)n * a.P * C;
+  const long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(v0 % cv) << 3;
+  float ga[8], be[8], acc_g[8], acc_b[8], acc_t[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ga[j] = a.gamma ? a.gamma[c0 + j] : 1.f;
+    be[j] = a.beta ? a.beta[c0 + j] : 0.f;
+    acc_g[j] = acc_b[j] = acc_t[j] = 0.f;
+  }
+  float s1 = 0.f, s2 = 0.f;   // per-thread partial sums stay small (a few hundred terms); the cross-thread sums are fp64
+  double d1 = 0.0, d2 = 0.0;
+  int since = 0;
+  for (long long v = v0; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    float x[8], dy[8];
+    ld16x8(a.x_hi, a.x_lo, base + (v << 3), a.x_f16, x);
+    ld16x8(a.dy_hi, a.dy_lo, base + (v << 3), a.dy_f16, dy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (x[j] - mean) * rstd;
+      const float dz = a.act ? dy[j] * dsilu(fmaf(ga[j], xh, be[j])) : dy[j];
+      const float dxh = dz * ga[j];
+      s1 += dxh;
+      s2 = fmaf(dxh, xh, s2);
+      acc_g[j] = fmaf(dz, xh, acc_g[j]);
+      acc_b[j] += dz;
+      acc_t[j] += dy[j];
+    }
+    if (++since == 32) { d1 += (double)s1; d2 += (double)s2; s1 = s2 = 0.f; since = 0; }
+  }
+  d1 += (double)s1; d2 += (double)s2;
+  if (v0 < nvec) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm_ch[c0 + j], acc_g[j]);
+      atomicAdd(&sm_ch[C + c0 + j], acc_b[j]);
+      if (a.dtemb != nullptr) atomicAdd(&sm_ch[2 * C + c0 + j], acc_t[j]);
+    }
   }
   __shared__ double red[2][8];
 #pragma unroll
-  for (int k = 16; k > 0; k >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, k); s2 += __shfl_xor_sync(0xffffffffu, s2, k); }
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  for (int k = 16; k > 0; k >>= 1) { d1 += __shfl_xor_sync(0xffffffffu, d1, k); d2 += __shfl_xor_sync(0xffffffffu, d2, k); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = d1; red[1][threadIdx.x >> 5] = d2; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t1 = 0.0, t2 = 0.0;
@@ -199,23 +261,30 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a) {
 }
 // pass 2: dx = rstd (dxhat - mean(dxhat) - xhat mean(dxhat xhat))
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a) {
-  const int n = blockIdx.y, C = a.C;
+  const int n = blockIdx.y, C = a.C, cv = C >> 3;
   const double cnt = (double)C * (double)a.P;
   const double mean_d = a.stats[2 * n] / cnt;
   double var = a.stats[2 * n + 1] / cnt - mean_d * mean_d;
   if (var < 0) var = 0;
   const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var + (double)a.eps));
   const float m1 = (float)(a.sums[2 * n] / cnt), m2 = (float)(a.sums[2 * n + 1] / cnt);
-  const long long total = a.P * C, base = (long long)n * total;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const float x = ld16x(a.x_hi, a.x_lo, base + i, a.x_f16);
-    const float dy = ld16x(a.dy_hi, a.dy_lo, base + i, a.dy_f16);
-    const float xh = (x - mean) * rstd;
-    const float ga = a.gamma ? a.gamma[c] : 1.f, be = a.beta ? a.beta[c] : 0.f;
-    const float dz = a.act ? dy * dsilu(fmaf(ga, xh, be)) : dy;
-    const float dxh = dz * ga;
-    st16x(a.dx_hi, a.dx_lo, base + i, rstd * (dxh - m1 - xh * m2), a.dx_f16);
+  const long long nvec = a.P * cv, base = (long long)n * a.P * C;
+  const long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(v0 % cv) << 3;
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ga[j] = a.gamma ? a.gamma[c0 + j] : 1.f; be[j] = a.beta ? a.beta[c0 + j] : 0.f; }
+  for (long long v = v0; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    float x[8], dy[8], o[8];
+    ld16x8(a.x_hi, a.x_lo, base + (v << 3), a.x_f16, x);
+    ld16x8(a.dy_hi, a.dy_lo, base + (v << 3), a.dy_f16, dy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (x[j] - mean) * rstd;
+      const float dz = a.act ? dy[j] * dsilu(fmaf(ga[j], xh, be[j])) : dy[j];
+      o[j] = rstd * (dz * ga[j] - m1 - xh * m2);
+    }
+    st16x8(a.dx_hi, a.dx_lo, base + (v << 3), a.dx_f16, o);
   }
 }
 
@@ -681,9 +750,15 @@ extern "C" int b2d_gn_silu_bwd(const void* x_hi, const void* x_lo, int32_t x_f16
   a.dx_hi = (uint16_t*)dx_hi; a.dx_lo = (uint16_t*)dx_lo; a.stats = stats; a.gamma = gamma; a.beta = beta; a.sums = sums;
   a.dgamma = dgamma; a.dbeta = dbeta; a.dtemb = dtemb; a.P = P; a.C = C; a.act = act ? 1 : 0;
   a.x_f16 = x_f16 ? 1 : 0; a.dy_f16 = dy_f16 ? 1 : 0; a.dx_f16 = dx_f16 ? 1 : 0; a.eps = eps;
-  int bx = grid_cap(P * C, 256 * 8);
+  if (C % 8) return set_error(B2D_E_UNSUPPORTED, "b2d_gn_silu_bwd: C = %d must be a multiple of 8 (16-byte channel vectors)", C);
+  int bx = grid_cap(P * C / 8, 256 * 4);
   const int cap = (num_sms() * 8 + N - 1) / N;
   if (bx > cap) bx = cap < 1 ? 1 : cap;
+  // a thread keeps one 8-channel group for its whole walk: the grid stride (256 * bx vectors) must be a multiple of C / 8
+  int cv = C / 8, g = 256, r = cv;
+  while (r) { const int t = g % r; g = r; r = t; }   // g = gcd(256, cv)
+  const int step = cv / g;
+  bx = bx < step ? step : bx / step * step;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N, st);
   if (e != cudaSuccess) return set_error(B2D_E_CUDA, "b2d_gn_silu_bwd: memset: %s", cudaGetErrorString(e));
