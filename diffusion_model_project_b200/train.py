@@ -546,6 +546,7 @@ class UNetTrainer:
         self._shape = None
         self._layers = None
         self._graph = None
+        self._comm_stream = None
         self._fb_launches = 0
         self._build_layers()
 
@@ -643,6 +644,15 @@ class UNetTrainer:
     def forward_backward(self, x: torch.Tensor, t: torch.Tensor, target: torch.Tensor):
         """x: (N, in_channels, h, w) fp32 on the GPU, t: (N,) timesteps, target: (N, out_channels, h, w).  Fills the flat
         gradient buffer; returns (loss, pred)."""
+        for _ in self._fb_phases(x, t, target):
+            pass
+        return self._fb_result
+
+    def _fb_phases(self, x: torch.Tensor, t: torch.Tensor, target: torch.Tensor):
+        """forward_backward as a generator that pauses where a contiguous block of the flat gradient is final -- after the
+        decoder's backward ("decoder": decoder.* and final_conv.*, the tail of the buffer) and after the bottleneck's
+        ("bottleneck") -- so that training_step can start reducing those blocks while the rest of the backward runs.
+        The stream is read again after every pause (each phase may be captured on its own)."""
         L, dev, f, s = self._layers, self.dev, self.features, _lib.stream_ptr()
         N, _, h, w = x.shape
         nl = len(f)
@@ -735,7 +745,27 @@ class UNetTrainer:
             da = ch.act(f"{q}.d_in", N, H2 // 2, W2 // 2, 2 * c)
             d_in = da
             ch.plan(f"{q}.dgrad", lambda: ConvPlan([d_raw], L[q][1].pw, d_in, cout=2 * c, stride=2, workspace=self.ws)).run(s)
+        def time_bwd(prefixes, last):
+            """Backward of the time-embedding chain for these blocks' Linear layers (their gradients live inside the blocks'
+            region of the flat buffer); the shared time_mlp accumulates in the leaves until the last call."""
+            if not temb:
+                return
+            ps = [p for p in prefixes if p in d_temb]
+            torch.autograd.backward([temb[p] for p in ps], [d_temb[p] for p in ps], retain_graph=not last)
+            for p in ps:
+                for k in (f"{p}.time_mlp.1.weight", f"{p}.time_mlp.1.bias"):
+                    G(k).copy_(leaves[k].grad)
+            if last:
+                for k in ("time_mlp.0.weight", "time_mlp.0.bias", "time_mlp.2.weight", "time_mlp.2.bias"):
+                    G(k).copy_(leaves[k].grad)
+
+        time_bwd([f"decoder.{l}.1" for l in range(nl)], False)
+        yield "decoder"
+        s = _lib.stream_ptr()
         da = double_bwd("bottleneck", da)[0]
+        time_bwd(["bottleneck"], False)
+        yield "bottleneck"
+        s = _lib.stream_ptr()
         for lvl in range(nl - 1, -1, -1):
             c = f[lvl]
             q = f"encoder.{lvl}.2"
@@ -749,29 +779,53 @@ class UNetTrainer:
             if self.heads[lvl] is not None:
                 da = attention_bwd_(f"encoder.{lvl}.1", da)
             da = double_bwd(f"encoder.{lvl}.0", da)[0]
-        if temb:
-            names = list(d_temb.keys())
-            torch.autograd.backward([temb[p] for p in names], [d_temb[p] for p in names])
-            for k, v in leaves.items():
-                G(k).copy_(v.grad)
-        return loss, pred
+        time_bwd([f"encoder.{l}.0" for l in range(nl)], True)
+        self._fb_result = (loss, pred)
 
-    def _q_sample_forward_backward(self, x_start, cond, feats, t, noise):
+    def _q_sample_phases(self, x_start, cond, feats, t, noise):
         x_t = self.scheduler.q_sample(x_start, t, noise)                                     # diffusion.py:78-101
-        return self.forward_backward(torch.cat([x_t, cond, feats], dim=1), t, noise)         # predictor.py:731-741
+        yield from self._fb_phases(torch.cat([x_t, cond, feats], dim=1), t, noise)           # predictor.py:731-741
+
+    def _buckets(self):
+        """The flat gradient in the order its blocks become final during the backward: [decoder.* + final_conv.*],
+        [bottleneck.*], [time_mlp.* + encoder.*] as (start, end) element ranges (the parameters are stored in the reference's
+        order: time_mlp, encoder, bottleneck, decoder, final_conv)."""
+        off = self.opt.offsets
+        first = lambda prefix: min(off[k][0] for k in self.opt.names if k.startswith(prefix))
+        b0, d0 = first("bottleneck."), first("decoder.")
+        assert 0 < b0 < d0 < self.opt.numel
+        return [(d0, self.opt.numel), (b0, d0), (0, b0)]
 
     def training_step(self, x_start: torch.Tensor, cond: torch.Tensor, feats: torch.Tensor, t: torch.Tensor, noise: torch.Tensor,
                       group=None, use_graph: bool = True):
-        """q_sample -> forward -> loss -> backward -> (gradient all-reduce) -> Adam -> operand refresh.  Returns (loss, pred).
-        use_graph: replay the ~440 launches of q_sample .. backward and the ~180 of the operand refresh as two CUDA graphs
-        (captured on the second step of a batch shape, over the StepCache's static buffers); the all-reduce and the Adam
-        launch (whose bias corrections change every step) stay eager.  The returned tensors are then overwritten by the
-        next step."""
+        """q_sample -> forward -> loss -> backward -> gradient all-reduce -> Adam -> operand refresh.  Returns (loss, pred).
+        The backward pauses where a block of the flat gradient is final (decoder + final_conv, then the bottleneck); with more
+        than one rank those blocks are all-reduced on a side stream while the rest of the backward runs, and only the last
+        block (time MLP + encoder, a fifth of the parameters) is reduced after it.
+        use_graph: from the second step of a batch shape the ~440 launches of q_sample .. backward replay as three CUDA
+        graphs (one per phase) and the ~90 of the operand refresh as a fourth, over the StepCache's static buffers; the
+        all-reduces and the Adam launch (whose bias corrections change every step) stay eager.  The returned tensors are
+        then overwritten by the next step."""
+        import torch.distributed as dist
         dev = self.dev
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         ins = [x_start, cond, feats, t, noise]
-        if not use_graph:
-            loss, pred = self._q_sample_forward_backward(*[v.to(dev) for v in ins])
-        else:
+        main = torch.cuda.current_stream(dev)
+        if world > 1 and self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=dev)
+        buckets = self._buckets()
+
+        def reduce_async(i):
+            """all-reduce bucket i on the side stream once everything issued so far on the main stream is done"""
+            if world == 1:
+                return
+            lo, hi = buckets[i]
+            self._comm_stream.wait_stream(main)
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(self.opt.grad[lo:hi], group=group)
+
+        gr = None
+        if use_graph:
             key = tuple(tuple(v.shape) for v in ins)
             if self._graph is None or self._graph["key"] != key:
                 self._graph = {"key": key, "ins": [torch.empty(v.shape, dtype=v.dtype, device=dev) for v in ins], "fb": None}
@@ -779,30 +833,48 @@ class UNetTrainer:
             for dst, v in zip(gr["ins"], ins):
                 dst.copy_(v, non_blocking=True)
             if gr["fb"] is None and self._shape == (x_start.shape[0], x_start.shape[2], x_start.shape[3]):
-                # buffers and plans of this shape exist (an eager step ran): capture
+                # buffers and plans of this shape exist (an eager step ran): capture the three phases and the refresh
                 side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
+                side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    fb = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(fb, stream=side):
-                        gr["out"] = self._q_sample_forward_backward(*gr["ins"])
+                    gen = self._q_sample_phases(*gr["ins"])
+                    graphs, pool = [], None
+                    for _ in range(3):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=side, pool=pool):
+                            next(gen, None)
+                        pool = g.pool()
+                        graphs.append(g)
+                    assert next(gen, "done") == "done"
+                    gr["out"] = self._fb_result
                     rf = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(rf, stream=side):
+                    with torch.cuda.graph(rf, stream=side, pool=pool):
                         self.refresh_operands()
-                torch.cuda.current_stream(dev).wait_stream(side)
-                gr["fb"], gr["refresh"] = fb, rf
-            if gr["fb"] is not None:
-                gr["fb"].replay()
-                _lib.launch_count += self._fb_launches
-                loss, pred = gr["out"]
-            else:
-                n0 = _lib.launch_count
-                loss, pred = self._q_sample_forward_backward(*gr["ins"])
-                self._fb_launches = _lib.launch_count - n0
-        scale = self.opt.allreduce_gradients(group)
+                main.wait_stream(side)
+                gr["fb"], gr["refresh"] = graphs, rf
+        if gr is not None and gr["fb"] is not None:
+            for i, g in enumerate(gr["fb"]):
+                g.replay()
+                if i < 2:
+                    reduce_async(i)
+            _lib.launch_count += self._fb_launches
+            loss, pred = gr["out"]
+        else:
+            n0 = _lib.launch_count
+            gen = self._q_sample_phases(*(gr["ins"] if gr is not None else [v.to(dev) for v in ins]))
+            for i, _ in enumerate(gen):
+                reduce_async(i)
+            loss, pred = self._fb_result
+            self._fb_launches = _lib.launch_count - n0
+        scale = 1.0
+        if world > 1:
+            lo, hi = buckets[2]
+            dist.all_reduce(self.opt.grad[lo:hi], group=group)      # the last block, on the main stream
+            main.wait_stream(self._comm_stream)
+            scale = 1.0 / world
         self.opt.step(grad_scale=scale)
-        if use_graph and self._graph["fb"] is not None:
-            self._graph["refresh"].replay()
+        if gr is not None and gr["fb"] is not None:
+            gr["refresh"].replay()
         else:
             self.refresh_operands()
         return loss, pred

@@ -42,48 +42,48 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-def step(marks=None):
-    """train.UNetTrainer.training_step with event marks between its phases (graph replays unless --eager)."""
-    e = [ev() for _ in range(5)] if marks is not None else None
-    gr = tr._graph
-    if e: e[0].record()
-    if args.eager or gr is None or gr["fb"] is None:
-        loss, _ = tr.training_step(x_start, cond, feats, t, noise, use_graph=not args.eager)
-        return loss
-    for dst, v in zip(gr["ins"], (x_start, cond, feats, t, noise)):
-        dst.copy_(v, non_blocking=True)
-    gr["fb"].replay()
-    loss = gr["out"][0]
-    if e: e[1].record()
-    scale = tr.opt.allreduce_gradients()
-    if e: e[2].record()
-    tr.opt.step(grad_scale=scale)
-    if e: e[3].record()
-    gr["refresh"].replay()
-    if e:
-        e[4].record()
-        marks.append(e)
-    return loss
+def step():
+    return tr.training_step(x_start, cond, feats, t, noise, use_graph=not args.eager)[0]
 
 
-for _ in range(args.warmup):
+def timed(fn, reps):
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+for _ in range(max(args.warmup, 2)):   # the second step of a shape captures the graphs
     step()
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
-launches0 = _lib.launch_count
-marks = []
 t0 = time.perf_counter()
 a, b = ev(), ev()
 a.record()
 for _ in range(args.steps):
-    loss = step(marks)
+    loss = step()
 b.record()
 host = (time.perf_counter() - t0) * 1e3 / args.steps   # launch-side time: if it equals the step time the host is the limiter
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) * 1e3 / args.steps
 ms = a.elapsed_time(b) / args.steps
-parts = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / max(len(marks), 1) for i in range(4)] if marks else [float("nan")] * 4
+# the step's pieces, each timed alone (in the step the first two all-reduce buckets run under the backward)
+gr = tr._graph
+parts = {}
+if gr is not None and gr.get("fb"):
+    parts["forward_backward"] = timed(lambda: [g.replay() for g in gr["fb"]], args.steps)
+    parts["operand_refresh"] = timed(gr["refresh"].replay, args.steps)
+else:
+    parts["forward_backward"] = timed(lambda: tr._q_sample_phases and [None for _ in tr._q_sample_phases(x_start, cond, feats, t, noise)], args.steps)
+    parts["operand_refresh"] = timed(tr.refresh_operands, args.steps)
+parts["adam"] = timed(lambda: tr.opt.step(grad_scale=0.0), 3)   # grad_scale 0 and lr untouched: moments decay, parameters move by ~0
+parts["allreduce_alone"] = timed(lambda: dist.all_reduce(tr.opt.grad), 5) if world > 1 else 0.0
+parts["allreduce_exposed"] = max(0.0, ms - parts["forward_backward"] - parts["operand_refresh"] - parts["adam"])
 tm = torch.tensor([ms], device=dev)
 if world > 1:
     dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -95,9 +95,10 @@ if rank == 0:
         "metric": "UNet training steps/sec (forward + backward + gradient all-reduce + Adam)", "value": 1e3 / tm.item() * 1.0,
         "unit": "steps/s", "n_gpus": world, "ms_per_step": tm.item(), "wall_ms_per_step": wall, "host_issue_ms_per_step": host, "slices_per_gpu": N, "latent": S,
         "samples_per_s": world * (N / 11.0) * 1e3 / tm.item(), "dtype": "fp32x (bf16 hi + lo operands, fp32 accumulate)" if args.precision == "fp32x" else "bf16 (fp32 accumulate)",
-        "parts_ms": {"forward_backward": parts[0], "allreduce": parts[1], "adam": parts[2], "operand_refresh": parts[3]},
-        "algorithmic_tflops": flops / (parts[0] * 1e-3) / 1e12 if marks else None, "parameters": nparam, "gradient_bytes": 4 * tr.opt.numel,
-        "allreduce_busbw_GBps": (2 * (world - 1) / world * 4 * tr.opt.numel / (parts[1] * 1e-3) / 1e9) if world > 1 else None,
+        "parts_ms": parts,
+        "algorithmic_tflops": flops / (parts["forward_backward"] * 1e-3) / 1e12, "parameters": nparam, "gradient_bytes": 4 * tr.opt.numel,
+        "allreduce_busbw_GBps": (2 * (world - 1) / world * 4 * tr.opt.numel / (parts["allreduce_alone"] * 1e-3) / 1e9) if world > 1 else None,
+        "allreduce": "three buckets in backward order; the first two (decoder + final_conv, bottleneck) on a side stream under the backward",
         "gpu_launches_per_step": tr._fb_launches + 1 + sum(len(o.parts) for l in tr._layers.values() for o in (l.operands() if hasattr(l, "operands") else l)), "cuda_graphs": not args.eager, "loss": loss.item(), "data": "synthetic"}))
 if world > 1:
     dist.destroy_process_group()
