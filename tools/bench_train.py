@@ -1,7 +1,10 @@
 """BASELINE.json configs[4]: one UNet training step per GPU on 2 samples (22 slice-images of 8x64x64 latents), gradients
 all-reduced over NCCL, Adam, operand refresh (train.UNetTrainer.training_step).  One JSON line from rank 0.
 usage: python tools/bench_train.py [--slices 22] [--size 64] [--steps 10] [--warmup 3]
-       python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_train.py"""
+       python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_train.py
+parts_ms: the step's pieces each timed ALONE after the timed loop (forward_backward = the three phase graphs back to back;
+allreduce_alone = one all-reduce of the whole flat gradient); allreduce_exposed = ms_per_step minus the other pieces, i.e.
+what the bucketed all-reduce adds to the step with its first two buckets running under the backward."""
 import argparse
 import json
 import os
