@@ -90,6 +90,26 @@ class FlatAdam:
         dist.all_reduce(self.grad, group=group)
         return 1.0 / dist.get_world_size(group)
 
+    def backward_order_buckets(self, boundaries: Sequence[str]) -> List[Tuple[int, int]]:
+        """Contiguous element ranges of the flat buffer cut at the first parameter of each prefix in `boundaries` (given in
+        storage order), returned LAST range first: the order in which a backward pass finishes them when the parameters are
+        stored in forward order.  E.g. ("bottleneck.", "decoder.") -> [decoder.. end), [bottleneck.. decoder), [0, bottleneck)."""
+        cuts = []
+        for prefix in boundaries:
+            offs = [self.offsets[k][0] for k in self.names if k.startswith(prefix)]
+            if not offs:
+                raise KeyError(f"no parameter starts with {prefix!r}")
+            cuts.append(min(offs))
+        if cuts != sorted(cuts) or (cuts and cuts[0] <= 0) or len(set(cuts)) != len(cuts):
+            raise ValueError(f"bucket boundaries {list(boundaries)} are not in storage order")
+        edges = [0] + cuts + [self.numel]
+        return [(edges[i], edges[i + 1]) for i in range(len(edges) - 2, -1, -1)]
+
+    def allreduce_bucket(self, bucket: Tuple[int, int], group=None):
+        """Sum one range of the flat gradient over the ranks (a view: no copy)."""
+        import torch.distributed as dist
+        dist.all_reduce(self.grad[bucket[0]:bucket[1]], group=group)
+
     def step(self, grad_scale: float = 1.0):
         if not self.param.is_cuda:
             raise RuntimeError("FlatAdam.step runs on a CUDA device only (no CPU fallback)")
@@ -788,13 +808,9 @@ class UNetTrainer:
 
     def _buckets(self):
         """The flat gradient in the order its blocks become final during the backward: [decoder.* + final_conv.*],
-        [bottleneck.*], [time_mlp.* + encoder.*] as (start, end) element ranges (the parameters are stored in the reference's
-        order: time_mlp, encoder, bottleneck, decoder, final_conv)."""
-        off = self.opt.offsets
-        first = lambda prefix: min(off[k][0] for k in self.opt.names if k.startswith(prefix))
-        b0, d0 = first("bottleneck."), first("decoder.")
-        assert 0 < b0 < d0 < self.opt.numel
-        return [(d0, self.opt.numel), (b0, d0), (0, b0)]
+        [bottleneck.*], [time_mlp.* + encoder.*] (the parameters are stored in the reference's order: time_mlp, encoder,
+        bottleneck, decoder, final_conv)."""
+        return self.opt.backward_order_buckets(("bottleneck.", "decoder."))
 
     def training_step(self, x_start: torch.Tensor, cond: torch.Tensor, feats: torch.Tensor, t: torch.Tensor, noise: torch.Tensor,
                       group=None, use_graph: bool = True):
@@ -819,10 +835,9 @@ class UNetTrainer:
             """all-reduce bucket i on the side stream once everything issued so far on the main stream is done"""
             if world == 1:
                 return
-            lo, hi = buckets[i]
             self._comm_stream.wait_stream(main)
             with torch.cuda.stream(self._comm_stream):
-                dist.all_reduce(self.opt.grad[lo:hi], group=group)
+                self.opt.allreduce_bucket(buckets[i], group)
 
         gr = None
         if use_graph:
@@ -868,8 +883,7 @@ class UNetTrainer:
             self._fb_launches = _lib.launch_count - n0
         scale = 1.0
         if world > 1:
-            lo, hi = buckets[2]
-            dist.all_reduce(self.opt.grad[lo:hi], group=group)      # the last block, on the main stream
+            self.opt.allreduce_bucket(buckets[2], group)            # the last block, on the main stream
             main.wait_stream(self._comm_stream)
             scale = 1.0 / world
         self.opt.step(grad_scale=scale)

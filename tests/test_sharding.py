@@ -75,6 +75,23 @@ def _allreduce_worker(rank, world, port):
         assert torch.equal(opt.state_dict()["w"], params["w"])
         with pytest.raises(RuntimeError):
             opt.step(scale)                                                                      # the update kernel is GPU-only
+        # the training step's bucketed form: ranges in backward order, reduced one by one, equal one whole-buffer all-reduce
+        names = ["time_mlp.0.weight", "encoder.0.w", "encoder.1.w", "bottleneck.a", "bottleneck.b", "decoder.0.w", "final_conv.weight"]
+        gg = torch.Generator().manual_seed(7)
+        big = FlatAdam({k: torch.randn(3 + 2 * i, 5, generator=gg) for i, k in enumerate(names)}, device="cpu")
+        buckets = big.backward_order_buckets(("bottleneck.", "decoder."))
+        assert buckets[0] == (big.offsets["decoder.0.w"][0], big.numel) and buckets[1][0] == big.offsets["bottleneck.a"][0]
+        assert buckets[2] == (0, big.offsets["bottleneck.a"][0]) and [b[1] for b in buckets[1:]] == [b[0] for b in buckets[:-1]]
+        big.grad.copy_(torch.arange(big.numel, dtype=torch.float32) * (rank + 1))
+        whole = big.grad.clone()
+        dist.all_reduce(whole)
+        for b in buckets:
+            big.allreduce_bucket(b)
+        assert torch.equal(big.grad, whole)
+        with pytest.raises(ValueError):
+            big.backward_order_buckets(("decoder.", "bottleneck."))
+        with pytest.raises(KeyError):
+            big.backward_order_buckets(("nothing.",))
     finally:
         dist.destroy_process_group()
 
