@@ -46,14 +46,29 @@ __global__ void __launch_bounds__(256) edt_rows_kernel(const int* __restrict__ g
   const int* gr = g + row * W;
   for (int x = threadIdx.x; x < W; x += blockDim.x) sg[x] = gr[x];
   __syncthreads();
+  // squared distances fit 32 bits whenever the image does (H, W <= 16384: dx^2 + g^2 < 2^29); columns without a
+  // background pixel carry kEdtInf and are clamped to a value no candidate can beat
+  const bool small = H <= 16384 && W <= 16384;
   for (int x = threadIdx.x; x < W; x += blockDim.x) {
     long long best = (long long)kEdtInf * kEdtInf;
-    for (int xp = 0; xp < W; ++xp) {
-      const long long gv = sg[xp];
-      if (gv >= kEdtInf) continue;
-      const long long dx = x - xp;
-      const long long d2 = dx * dx + gv * gv;
-      best = d2 < best ? d2 : best;
+    if (small) {
+      unsigned int b32 = 0xFFFFFFFFu;
+#pragma unroll 8
+      for (int xp = 0; xp < W; ++xp) {
+        const int gv = sg[xp];
+        const int dx = x - xp;
+        const unsigned int d2 = gv >= kEdtInf ? 0xFFFFFFFFu : (unsigned int)(dx * dx + gv * gv);
+        b32 = d2 < b32 ? d2 : b32;
+      }
+      if (b32 != 0xFFFFFFFFu) best = b32;
+    } else {
+      for (int xp = 0; xp < W; ++xp) {
+        const long long gv = sg[xp];
+        if (gv >= kEdtInf) continue;
+        const long long dx = x - xp;
+        const long long d2 = dx * dx + gv * gv;
+        best = d2 < best ? d2 : best;
+      }
     }
     out[row * W + x] = (float)sqrt((double)best);
   }
