@@ -5,7 +5,7 @@ encode/decode and the predict / predict_ddim loops, over hand-written sm_100a CU
 Importing the package does not load the CUDA library; the first kernel call does, and raises if it
 is missing -- there is no CPU or PyTorch fallback on this path.
 """
-__all__ = ["B200UNet", "B200Scheduler", "B200DualVAE", "B200LatentDiffusionPredictor"]
+__all__ = ["B200UNet", "B200Scheduler", "B200DualVAE", "B200LatentDiffusionPredictor", "UNetTrainer", "LatentDiffusionTrainer"]
 
 
 def __getattr__(name):
@@ -21,4 +21,7 @@ def __getattr__(name):
     if name == "B200LatentDiffusionPredictor":
         from .predictor import B200LatentDiffusionPredictor
         return B200LatentDiffusionPredictor
+    if name in ("UNetTrainer", "LatentDiffusionTrainer"):
+        from . import train
+        return getattr(train, name)
     raise AttributeError(name)

@@ -317,6 +317,42 @@ class B200LatentDiffusionPredictor:
         mu, _ = self.vae.encode_3d_deterministic(x, div_scale=self.normalizer["output"].scale_factors)
         return mu.permute(0, 2, 1, 3, 4)
 
+    def conditioning_latents(self, img: torch.Tensor, velocity_2d: torch.Tensor):
+        """The conditioning the reference builds at the top of forward() / predict() (predictor.py:646-719 = :927-962):
+        the frozen E2D encoder's mu of the normalised 2D velocity and the EDT features of the mask, bilinearly resized to
+        the latent grid (the depth interpolation of :707-715 is the identity: the latent keeps the slice count).
+        Returns fp32 (cond (N, latent, h, w), feats (N, 1, h, w)), N = batch * num_slices."""
+        B, S, H, W = self._check_inputs(img, velocity_2d)
+        ses = self._get_session(B, S, H, W)
+        self._conditioning(ses, img.to(self.device), velocity_2d.to(self.device), _lib.stream_ptr())
+        lat, ui = self.latent_channels, ses["unet_in"]
+        raw = ui.hi[..., lat:2 * lat]
+        cond = raw.view(torch.float16).float() if ui.f16 else raw.float()
+        if ui.lo is not None:
+            cond = cond + ui.lo[..., lat:2 * lat].float()
+        cond = cond.reshape(ses["N"], ses["h"], ses["w"], lat).permute(0, 3, 1, 2).contiguous()
+        return cond, ses["feats"].reshape(ses["N"], 1, ses["h"], ses["w"]).clone()
+
+    def forward(self, img: torch.Tensor, velocity_2d: torch.Tensor, x_start: Optional[torch.Tensor] = None,
+                noise: Optional[torch.Tensor] = None, *, t: Optional[torch.Tensor] = None):
+        """predictor.py:636-751, the noise prediction of the training / validation loop (helper.py:277-320): conditioning
+        as above, `t = randint(0, T, (N,))` (:736; `t=` injects it, like `noise=`), `x_t = q_sample(x_start, t, noise)`,
+        `noise_pred = UNet(cat[x_t, cond, feats], t)`.  Returns (noise_pred, noise), both (N, latent, h, w).
+        No autograd graph is attached: optimisation steps go through `train.LatentDiffusionTrainer`."""
+        if x_start is None:
+            raise ValueError("forward() requires x_start (target latents) for training. Use predict() for inference.")  # :750
+        cond, feats = self.conditioning_latents(img, velocity_2d)
+        N, lat, h, w = cond.shape
+        x0 = x_start.to(self.device, torch.float32).reshape(N, lat, h, w)
+        noise = torch.randn_like(x0) if noise is None else noise.to(self.device, torch.float32).reshape(N, lat, h, w)
+        if t is None:
+            t = torch.randint(0, self.num_timesteps, (N,), device=self.device).long()
+        t = t.to(self.device).long()
+        x_t = self.scheduler.q_sample(x0, t, noise)
+        return self.model(torch.cat([x_t, cond, feats], dim=1), t), noise
+
+    __call__ = forward
+
     def ddim_timesteps(self, num_steps: int) -> List[int]:
         """predictor.py:965: `torch.linspace(T-1, 0, num_steps, device=device).long()` -- built on the CUDA device like
         the reference's production path, so the integer rounding is the same kernel's."""

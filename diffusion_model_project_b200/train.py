@@ -1,15 +1,19 @@
-"""First slice of the UNet training step over libb2d:
+"""The UNet training step over libb2d:
 
     q_sample(target latents) -> concat -> UNet eps-prediction -> normalized_mse_loss_per_component -> backward -> Adam
     (Diffusion_model/src/predictor.py:722-748, unet/metrics.py:337-402, helper.py:428-430, train.py:144-148)
 
-What exists: the criterion (forward + gradient), torch.optim.Adam's update over flat fp32 parameter / moment buffers with
-the gradient all-reduce that precedes it, and the backward of one DoubleBlock (unet/blocks.py:50-107: conv3x3 -> GroupNorm(1,C)
--> SiLU (+ time embedding) -> conv3x3 -> GroupNorm -> SiLU): GroupNorm/SiLU backward, the 3x3 conv's data gradient (the forward
-engine on dY with mirrored taps and transposed weights) and its weight gradient (a tcgen05 kernel reading both operands
-MN-major out of the channels-last tensors).  What does not exist yet: attention / max-pool / transposed-conv backward and
-the time-MLP chain, i.e. the whole-UNet backward.  Gradients are carried in the fp32-class format (bf16 hi + lo): IEEE
-fp16 would underflow them without loss scaling.
+* `nmse_loss`: the criterion, forward + gradient.
+* `FlatAdam`: torch.optim.Adam's update over flat fp32 parameter / moment buffers, with the gradient all-reduce (whole, or
+  by backward-order buckets) that precedes it.
+* `DoubleBlockGrad`, `AttentionGrad` and the helpers above them: forward with saved activations and backward of the UNet's
+  blocks -- GroupNorm / SiLU backward, conv / ConvTranspose2d / Linear data gradients (the forward engine on dY with mirrored
+  taps and transposed weights), weight gradients (a tcgen05 kernel reading both operands MN-major out of the channels-last
+  tensors), max-pool and attention-core backward.
+* `UNetTrainer`: one whole optimisation step from latents, replayed as CUDA graphs, operands rewritten in place.
+* `LatentDiffusionTrainer`: the reference's training loop body from the FIELDS (helper.py:277-430): frozen-VAE target
+  latents and conditioning from a `B200LatentDiffusionPredictor`, then `UNetTrainer.training_step`.
+Gradients are carried in the fp32-class format (bf16 hi + lo): IEEE fp16 would underflow them without loss scaling.
 """
 from __future__ import annotations
 
@@ -892,3 +896,55 @@ class UNetTrainer:
         else:
             self.refresh_operands()
         return loss, pred
+
+
+class LatentDiffusionTrainer:
+    """The 'latent-diffusion' branch of the reference's training loop body (helper.py:277-430, default losses: the noise
+    criterion only -- physics / velocity losses are out of scope), from the fields a data loader yields:
+
+        target_latents = predictor.encode_target(targets, velocity_2d)             # frozen E3D      (helper.py:288)
+        noise = randn_like(target_latents);  t = randint(0, T, (N,))                #                 (:299, predictor.py:736)
+        preds, noise = predictor(img, velocity_2d, x_start=target_latents, noise)   # frozen E2D conditioning + EDT
+                                                                                    # features + q_sample + UNet (:636-751)
+        loss = criterion(preds, noise);  zero_grad();  loss.backward();  optimizer.step()            (helper.py:428-430)
+
+    `predictor` supplies the frozen VAE passes (its E2D / E3D programs, EDT and bilinear kernels) and is not updated;
+    `unet` is the `UNetTrainer` that owns the parameters being optimised (built from the predictor's UNet state unless
+    given).  `sync_predictor()` hands the trained parameters back to the predictor's sampling UNet."""
+
+    def __init__(self, predictor, unet: Optional[UNetTrainer] = None, *, unet_state: Optional[Dict[str, torch.Tensor]] = None,
+                 lr: float = 1e-4, weight_decay: float = 0.0, precision: str = "fp32x"):
+        self.predictor = predictor
+        if unet is None:
+            if unet_state is None:
+                raise ValueError("LatentDiffusionTrainer needs the UNet parameters: pass `unet` (a UNetTrainer) or `unet_state`")
+            m = predictor.model
+            unet = UNetTrainer(unet_state, in_channels=m.in_channels, out_channels=m.out_channels, features=tuple(m.features),
+                               attention=m.attention, time_embedding_dim=m.time_embedding_dim, num_timesteps=predictor.num_timesteps,
+                               lr=lr, weight_decay=weight_decay, device=predictor.device, precision=precision)
+        self.unet = unet
+
+    def latents(self, img: torch.Tensor, velocity_2d: torch.Tensor, targets: torch.Tensor):
+        """(x_start, cond, feats), each fp32 (N, C, h, w): the frozen-VAE side of the step.  They depend on the sample only,
+        not on the UNet: a data pipeline may compute them once per sample and cache them."""
+        p = self.predictor
+        x_start = p.encode_target(targets.to(p.device), velocity_2d)
+        cond, feats = p.conditioning_latents(img, velocity_2d)
+        return x_start.reshape(cond.shape).contiguous(), cond, feats
+
+    def train_step(self, img: torch.Tensor, velocity_2d: torch.Tensor, targets: torch.Tensor, *, t: Optional[torch.Tensor] = None,
+                   noise: Optional[torch.Tensor] = None, group=None, use_graph: bool = True):
+        """One iteration of the loop body.  t / noise inject the reference's randint / randn_like draws (parity tests).
+        Returns (loss, noise_pred, noise)."""
+        x_start, cond, feats = self.latents(img, velocity_2d, targets)
+        dev = x_start.device
+        noise = torch.randn_like(x_start) if noise is None else noise.to(dev, torch.float32).reshape(x_start.shape)
+        if t is None:
+            t = torch.randint(0, self.predictor.num_timesteps, (x_start.shape[0],), device=dev).long()
+        loss, pred = self.unet.training_step(x_start, cond, feats, t.to(dev).long(), noise, group=group, use_graph=use_graph)
+        return loss, pred, noise
+
+    def sync_predictor(self):
+        """Load the optimised parameters into the predictor's sampling UNet (repacks its operands, rebuilds the time table)."""
+        self.predictor.model.load_state_dict({k: v.detach().clone() for k, v in self.unet.state_dict().items()})
+        self.predictor._session = None  # programs hold the old operands' addresses

@@ -56,6 +56,25 @@ def training_loss_and_grads(sd: Dict[str, torch.Tensor], x_start: torch.Tensor, 
     return loss.detach(), out, pred.detach()
 
 
+def training_step_from_fields(unet_sd: Dict[str, torch.Tensor], vae_sd: Dict[str, torch.Tensor], img: torch.Tensor,
+                              velocity_2d: torch.Tensor, velocity_3d: torch.Tensor, t: torch.Tensor, noise: torch.Tensor,
+                              norm_factors, num_timesteps: int = 1000):
+    """The 'latent-diffusion' branch of the training loop body, helper.py:277-430 with its default losses, from the fields:
+    target latents = encode_target(velocity_3d) (predictor.py:1042-1085, helper.py:288), then predictor.forward
+    (predictor.py:636-751): frozen E2D mu of the normalised 2D velocity + EDT features as conditioning, q_sample at the
+    given timesteps (the reference draws them with randint, :736 -- injected here), UNet, criterion, backward.
+    noise: (B, S, 8, h, w) like helper.py:299.  Returns (loss, {param: grad}, noise_pred, (x_start, cond, feats))."""
+    from . import predictor as opred
+    with torch.no_grad():
+        latents = opred.encode_target(vae_sd, velocity_3d, norm_factors)           # (B, S, 8, h, w)
+        cond, feats = opred.conditioning(vae_sd, img, velocity_2d, norm_factors)    # (N, 8, h, w), (N, 1, h, w)
+    N = cond.shape[0]
+    x_start = latents.reshape(N, *latents.shape[2:])
+    noise_flat = noise.reshape(x_start.shape)
+    loss, grads, pred = training_loss_and_grads(unet_sd, x_start, cond, feats, t, noise_flat, num_timesteps)
+    return loss, grads, pred, (x_start, cond, feats)
+
+
 def adam_step(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float = 1e-4,
               betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
     """torch.optim.Adam (train.py:144-148), single-tensor form: L2 weight decay folded into the gradient, bias-corrected

@@ -97,6 +97,67 @@ def main_encode_target():
     print("encode_target", tuple(lat.shape), lat.abs().max().item())
 
 
+def field_inputs():
+    """Shared with the tests: ONE sample of 2 slices at 128x128 (latent 32x32, the smallest five max-pools allow): mask,
+    2D velocity (synth), a 3D velocity target in physical units, the injected noise, and the seed under which the
+    reference's forward() draws its timesteps."""
+    img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=2024)
+    g = torch.Generator().manual_seed(53)
+    target = torch.randn(1, 2, 3, 128, 128, generator=g) * torch.tensor(synth.NORM_FACTORS).view(1, 1, 3, 1, 1) * img
+    noise = torch.randn(1, 2, 8, 32, 32, generator=g)
+    return img, v2d, target, noise, 1234
+
+
+def main_train_from_fields():
+    """The 'latent-diffusion' branch of the reference's training loop body (helper.py:277-430 with its defaults: no physics /
+    velocity loss) on the UNMODIFIED reference predictor: target latents = encode_target(targets) (frozen E3D),
+    preds, noise = predictor(img, velocity_2d, x_start=latents, noise=noise)  (predictor.py:636-751: frozen E2D conditioning,
+    EDT features, randint timesteps, q_sample, UNet), criterion, backward, Adam -> tests/golden/train_from_fields.npz."""
+    import tempfile
+    sys.path.insert(0, HERE)
+    from make_golden import build_reference_predictor
+    from src.unet.metrics import cost_function
+    vsd = synth.synth_vae_state(seed=1, branches=("encoder_2d", "encoder_3d", "decoder_3d"))
+    with tempfile.TemporaryDirectory() as tmp:
+        pred = build_reference_predictor(tmp, num_slices=2)
+    pred.vae.encoder_3d.load_state_dict({k[len("encoder_3d."):]: v for k, v in vsd.items() if k.startswith("encoder_3d.")})
+    img, v2d, target, noise, seed = field_inputs()
+    pred.train()                                   # helper.py:273
+    for p in pred.vae.parameters():                # the VAE is frozen (predictor.py:568-571)
+        assert not p.requires_grad
+    criterion = cost_function("normalized_mse_loss_per_component")
+    opt = torch.optim.Adam([p for p in pred.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.0)
+    before = {k: v.detach().clone() for k, v in pred.model.named_parameters()}
+    with torch.enable_grad():
+        latents = pred.encode_target(target, v2d)  # helper.py:288
+        torch.manual_seed(seed)                    # forward() draws t = randint(...) from the default generator (:736)
+        preds, target_noise = pred(img, v2d, x_start=latents, noise=noise)
+        loss = criterion(output=preds, target=target_noise)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    torch.manual_seed(seed)
+    t = torch.randint(0, pred.num_timesteps, (2,)).long()
+    out = {"loss": np.float64(loss.item()), "pred": preds.detach().numpy(), "t": t.numpy(), "latents": latents.detach().numpy()}
+    names, norms = [], []
+    for k, p in pred.model.named_parameters():
+        names.append(k)
+        norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array(norms)
+    params = dict(pred.model.named_parameters())
+    for k in ("final_conv.weight", "encoder.0.0.block1.conv.weight", "bottleneck.block2.norm.weight"):
+        out[f"grad::{k}"] = params[k].grad.numpy()
+        out[f"delta::{k}"] = (params[k].detach() - before[k]).numpy()
+    np.savez_compressed(os.path.join(HERE, "train_from_fields.npz"), **out)
+    print("train_from_fields: loss", loss.item(), "t", t.tolist(), "max grad norm", max(norms))
+
+
 if __name__ == "__main__":
-    main()
-    main_encode_target()
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "step"):
+        main()
+    if which in ("all", "target"):
+        main_encode_target()
+    if which in ("all", "fields"):
+        main_train_from_fields()

@@ -413,3 +413,88 @@ def test_training_step_at_baseline_size():
     # windows), while the fp32 oracle is within 4.5e-6 of fp64.  Bound: 5e-3 on the worst tensor, 3e-4 on the median.
     assert errs[worst] <= 5e-3, (worst, errs[worst])
     assert sorted(errs.values())[len(errs) // 2] <= 3e-4
+
+
+def _field_predictor(precision):
+    from diffusion_model_project_b200.predictor import B200LatentDiffusionPredictor
+    vsd = synth.synth_vae_state(seed=1, branches=("encoder_2d", "encoder_3d", "decoder_3d"))
+    return B200LatentDiffusionPredictor("UNet", dict(synth.UNET_KWARGS), True, unet_state=synth.synth_unet_state(seed=0), vae_state=vsd,
+                                        norm_factors=synth.NORM_FACTORS, num_slices=2, num_timesteps=1000, precision=precision, device=DEV)
+
+
+@pytest.mark.parametrize("precision,bound", [("fp32x", 1e-3), ("f16", 2e-2)])
+def test_predictor_forward_vs_reference(golden_dir, precision, bound):
+    """`predictor(img, velocity_2d, x_start=latents, noise=noise)` (predictor.py:636-751: frozen E2D conditioning + EDT
+    features, q_sample at the drawn timesteps, UNet) against the unmodified reference's own forward() on the same fields,
+    target latents, noise and timesteps (tests/golden/train_from_fields.npz).  Bound: BASELINE's per-step noise-prediction
+    tolerance of the mode (max relative error)."""
+    no_tf32()
+    mod = _train_inputs(golden_dir)
+    g = np.load(os.path.join(golden_dir, "train_from_fields.npz"))
+    img, v2d, target, noise, _ = mod.field_inputs()
+    t = torch.from_numpy(g["t"])
+    with torch.no_grad():
+        p = _field_predictor(precision)
+        lat = p.encode_target(target.to(DEV), v2d.to(DEV))
+        ref_lat = torch.from_numpy(g["latents"])
+        e_lat = rel_err(lat.cpu(), ref_lat)
+        pred, nz = p(img.to(DEV), v2d.to(DEV), x_start=torch.from_numpy(g["latents"]).to(DEV), noise=noise.to(DEV), t=t)
+        torch.cuda.synchronize()
+        e = rel_err(pred.cpu(), torch.from_numpy(g["pred"]))
+        print(f"predictor.forward [{precision}]: encode_target max-rel {e_lat:.2e}, noise prediction max-rel {e:.2e} (bound {bound:g})")
+        assert e_lat <= (1e-3 if precision == "fp32x" else 1e-2)
+        assert e <= bound
+        assert torch.equal(nz.cpu(), noise.reshape(nz.shape))
+        with pytest.raises(ValueError):
+            p(img.to(DEV), v2d.to(DEV))  # predictor.py:750: forward() without x_start
+        # without injection the timesteps and the noise are drawn per call, like the reference's randint / randn_like
+        a, na = p(img.to(DEV), v2d.to(DEV), x_start=lat)
+        b, nb = p(img.to(DEV), v2d.to(DEV), x_start=lat)
+        assert not torch.equal(na, nb) and not torch.equal(a, b)
+
+
+def test_training_step_from_fields_vs_reference(golden_dir):
+    """The reference's training loop body from the fields (helper.py:277-430: encode_target -> predictor.forward ->
+    criterion -> backward -> Adam) as `LatentDiffusionTrainer.train_step`: frozen E3D / E2D passes, EDT and bilinear
+    features of the B200 predictor (fp32-class mode), then the UNetTrainer step -- against one iteration of the unmodified
+    reference predictor + torch.optim.Adam on the same fields, timesteps and noise (tests/golden/train_from_fields.npz)."""
+    no_tf32()
+    mod = _train_inputs(golden_dir)
+    g = np.load(os.path.join(golden_dir, "train_from_fields.npz"))
+    img, v2d, target, noise, _ = mod.field_inputs()
+    t = torch.from_numpy(g["t"])
+    usd = synth.synth_unet_state(seed=0)
+    with torch.no_grad():
+        p = _field_predictor("fp32x")
+        lt = train.LatentDiffusionTrainer(p, unet_state=usd, lr=1e-4, weight_decay=0.0)
+        before = {k: v.clone() for k, v in lt.unet.state_dict().items()}
+        loss, pred, nz = lt.train_step(img.to(DEV), v2d.to(DEV), target.to(DEV), t=t, noise=noise)
+        torch.cuda.synchronize()
+    e_loss = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+    e_pred = rel_err(pred.cpu(), torch.from_numpy(g["pred"]))
+    names = [str(n) for n in g["grad_names"]]
+    assert set(names) == set(lt.unet.opt.names)
+    worst, worst_n = 0.0, ""
+    for n, ref_norm in zip(names, g["grad_norms"]):
+        d = abs(float(lt.unet.G(n).double().norm()) - ref_norm) / max(ref_norm, 1e-6)
+        if d > worst:
+            worst, worst_n = d, n
+    full = {}
+    for k in ("final_conv.weight", "encoder.0.0.block1.conv.weight", "bottleneck.block2.norm.weight"):
+        ref_g = torch.from_numpy(g[f"grad::{k}"])
+        full[k] = rel_l2(lt.unet.G(k).cpu(), ref_g)
+        ref_d = torch.from_numpy(g[f"delta::{k}"])
+        got_d = (lt.unet.state_dict()[k] - before[k]).cpu()
+        big = ref_g.abs() > 1e-2 * ref_g.abs().max()
+        assert (got_d - ref_d)[big].abs().max().item() <= 5e-6, k
+    print(f"training step from fields: loss {loss.item():.6f} vs {float(g['loss']):.6f} (rel {e_loss:.2e}), noise prediction max-rel {e_pred:.2e}, "
+          f"worst gradient-norm deviation {worst:.2e} ({worst_n}), full gradients rel-L2 {', '.join(f'{v:.2e}' for v in full.values())}")
+    # measured on a B200: loss 2.2e-7, noise prediction 5.5e-5, worst gradient norm 7.3e-5, full gradients <= 5.3e-4
+    assert e_loss <= 1e-5 and e_pred <= 5e-4
+    assert worst <= 2e-3, (worst_n, worst)
+    assert max(full.values()) <= 5e-3, full
+    # the optimised parameters go back into the predictor's sampling UNet
+    lt.sync_predictor()
+    with torch.no_grad():
+        pred2, _ = p(img.to(DEV), v2d.to(DEV), x_start=torch.from_numpy(g["latents"]).to(DEV), noise=noise.to(DEV), t=t)
+    assert torch.isfinite(pred2).all() and not torch.equal(pred2, pred)

@@ -176,3 +176,32 @@ def test_encode_target_vs_reference(golden_dir):
     ref = torch.from_numpy(g["latents"])
     assert lat.shape == ref.shape == (2, 3, 8, 8, 8)
     assert (lat - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+def test_training_step_from_fields_vs_reference(golden_dir):
+    """The caller of row f4: the reference's training loop body from the FIELDS (helper.py:277-430: encode_target, then
+    predictor.forward = frozen-VAE conditioning + randint t + q_sample + UNet, predictor.py:636-751; criterion; backward)
+    -- oracle composition against the unmodified reference predictor (tests/golden/train_from_fields.npz)."""
+    from oracle import train as otrain
+    mod = _load_train_golden_module(golden_dir)
+    g = _load(golden_dir, "train_from_fields.npz")
+    img, v2d, target, noise, seed = mod.field_inputs()
+    torch.manual_seed(seed)
+    t = torch.randint(0, 1000, (2,)).long()
+    assert np.array_equal(t.numpy(), g["t"])
+    usd = synth.synth_unet_state(seed=0)
+    vsd = synth.synth_vae_state(seed=1, branches=("encoder_2d", "encoder_3d", "decoder_3d"))
+    loss, grads, pred, (x_start, _, _) = otrain.training_step_from_fields(usd, vsd, img, v2d, target, t, noise, synth.NORM_FACTORS)
+    ref_lat = torch.from_numpy(g["latents"])
+    assert (x_start.reshape(ref_lat.shape) - ref_lat).abs().max().item() <= 2e-5 * ref_lat.abs().max().item()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    ref_pred = torch.from_numpy(g["pred"])
+    assert (pred - ref_pred).abs().max().item() <= 5e-5 * ref_pred.abs().max().item()
+    names = [str(n) for n in g["grad_names"]]
+    assert set(names) == set(usd.keys())
+    for n, ref_norm in zip(names, g["grad_norms"]):
+        got = float(grads[n].double().norm())
+        assert abs(got - ref_norm) <= 2e-3 * max(ref_norm, 1e-6), (n, got, ref_norm)
+    for k in ("final_conv.weight", "encoder.0.0.block1.conv.weight", "bottleneck.block2.norm.weight"):
+        ref_g = torch.from_numpy(g[f"grad::{k}"])
+        assert (grads[k] - ref_g).abs().max().item() <= 2e-3 * max(ref_g.abs().max().item(), 1e-12), k
