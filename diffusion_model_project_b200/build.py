@@ -31,17 +31,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, *, extra_flags=(), lib_path: str = LIB, obj_dir: str = "build") -> str:
+    """extra_flags / lib_path / obj_dir: debug variants (tools/timeline_conv.py) built next to, never instead of, libb2d.so."""
+    if lib_path == LIB and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
-    tmp = os.path.join(HERE, "build")
+    tmp = os.path.join(HERE, obj_dir)
     os.makedirs(tmp, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(tmp, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -52,11 +53,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -107,3 +107,21 @@ int launch_conv_v2(const b2d_conv_plan* plan, cudaStream_t st) {
 }
 
 }  // namespace b2d
+
+#ifdef B2D_TIMELINE
+// debug library only (tools/timeline_conv.py): clear / read the per-CTA stamps
+extern "C" __attribute__((visibility("default"))) int b2d_debug_timeline(unsigned long long* host, int clear) {
+  if (clear == -1)  // CTA 0's per-iteration log
+    return cudaMemcpyFromSymbol(host, b2d::g_tl_iter, sizeof(b2d::g_tl_iter)) == cudaSuccess ? 0 : -1;
+  if (clear >= 16) {  // 16 + ablation mode
+    const int mode = clear - 16;
+    return cudaMemcpyToSymbol(b2d::g_tl_mode, &mode, sizeof(int)) == cudaSuccess ? 0 : -1;
+  }
+  if (clear) {
+    void* d = nullptr;
+    if (cudaGetSymbolAddress(&d, b2d::g_timeline) != cudaSuccess) return -1;
+    return cudaMemset(d, 0, sizeof(b2d::g_timeline)) == cudaSuccess ? 0 : -1;
+  }
+  return cudaMemcpyFromSymbol(host, b2d::g_timeline, sizeof(b2d::g_timeline)) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -126,14 +126,21 @@ extern "C" int b2d_conv_plan_create(const b2d_conv_desc* d, b2d_conv_plan** out_
       if (halo && gt == 4 && b < 128) continue;  // narrow tiles batch 3 / 9 taps per weight stage
       const long long tiles = tiles_m2 * (b == 16 ? 1 : cols / b);
       const double t_kb = b == 256 ? 512.0 : b == 128 ? 256.0 : b == 64 ? 192.0 : 128.0;
-      // one A-operand group: tensor time of its MMAs, or its operand bytes at 40 B/clk -- an EMPIRICAL rate that makes the
-      // model reproduce the measured ordering of (BLOCK_N, split) on the small-map layers (profiles/r2_tune_conv_88.txt:
-      // 128 x 128 tiles at K = 9216 sustain 6.5 TB/s of operand traffic over 88 SMs and lose to 256-wide tiles with three
-      // K splits).  It is not the L2 port: CTA pairs that halve the weight bytes per SM run no faster (see below)
-      constexpr double kL2BytesPerClk = 40.0;
+      // one A-operand group: tensor time of its MMAs, bounded below by what the role warps can turn around.
+      //  * generic tiles: a K step costs the producer / MMA warps ~350-390 clocks of loop instructions and barrier round
+      //    trips whatever the tile width (tools/timeline_conv.py, profiles/r2_timeline_conv.txt: 525 clocks per step at
+      //    BLOCK_N = 256 = its four MMAs; ~390 at BLOCK_N = 128 against 256 clocks of MMAs).  Until the lean K loop of
+      //    conv_v2.cuh the same step took 890-960 clocks at every width, which an earlier version of this model had
+      //    fitted as "operand bytes at 40 B/clk".
+      //  * halo tiles: operand bytes at 40 B/clk per SM (fitted on the 128-wide VAE tiles, which sit at that bound)
+      constexpr double kL2BytesPerClk = 40.0, kGenericStepFloor = 380.0;
       const double group_bytes = halo ? 18.0 * 18.0 * 128.0 + gt * b * 128.0 : (128.0 + b) * 128.0;
       double per_group = (halo ? 2.0 * gt : 1.0) * t_kb;
-      if (per_group < group_bytes / kL2BytesPerClk) per_group = group_bytes / kL2BytesPerClk;
+      if (halo) {
+        if (per_group < group_bytes / kL2BytesPerClk) per_group = group_bytes / kL2BytesPerClk;
+      } else if (per_group < kGenericStepFloor) {
+        per_group = kGenericStepFloor;
+      }
       if (d->in_stats && per_group < 6000.0) per_group = 6000.0;  // fused input normalisation: the tile rewrite bounds a group
       for (int ks = 1; ks <= 16; ++ks) {
         if (force_ks > 0 && ks < force_ks) continue;  // tools/tune_conv.py: measure a given split count

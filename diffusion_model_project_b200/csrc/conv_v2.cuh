@@ -6,6 +6,31 @@
 
 namespace b2d {
 
+// Debug timeline (tools/timeline_conv.py builds a separate library with -DB2D_TIMELINE; the shipped libb2d.so has none of
+// it): per CTA, {globaltimer ns, clock64} at a few points of the unit a CTA runs last.
+#ifdef B2D_TIMELINE
+constexpr int kTlSlots = 16;
+__device__ unsigned long long g_timeline[296 * kTlSlots * 2];
+__device__ __forceinline__ void tl_stamp(int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_timeline[((size_t)blockIdx.x * kTlSlots + slot) * 2] = t;
+  g_timeline[((size_t)blockIdx.x * kTlSlots + slot) * 2 + 1] = (unsigned long long)clock64();
+}
+#define B2D_TL(slot, pred) do { if (pred) tl_stamp(slot); } while (0)
+// ablation switches of the debug build (generic staging): 1 = issue no MMAs, 2 = load no A tiles, 4 = load no B tiles
+__device__ int g_tl_mode;
+#define B2D_TL_MODE() (g_tl_mode)
+// CTA 0's first 128 K iterations (generic staging): clock64 when the producer holds both free stages, when the MMA warp
+// sees both full barriers, and after it has issued the iteration's commits
+__device__ long long g_tl_iter[3][128];
+#define B2D_TL_ITER(row, n, pred) do { if ((pred) && blockIdx.x == 0 && (n) < 128) g_tl_iter[row][n] = clock64(); } while (0)
+#else
+#define B2D_TL(slot, pred) do { } while (0)
+#define B2D_TL_MODE() 0
+#define B2D_TL_ITER(row, n, pred) do { } while (0)
+#endif
+
 // PAIR: two CTAs of a cluster form a tcgen05 cta_group::2 pair on a 256-row M super-tile (generic staging only): each
 // stages its own 128 A rows and HALF of the N tile's weight rows, the pair's even CTA issues M = 256 MMAs that read both
 // halves, each CTA's TMEM receives its own 128 x BN accumulator.  Per SM the operand bytes pulled from L2 per K block
@@ -108,6 +133,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
   const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncta = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const bool leader = !PAIR || cluster_ctarank() == 0;
 
+  B2D_TL(0, threadIdx.x == 0);  // kernel entry
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], XFORM ? Cfg::XF_WARPS : 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -129,6 +155,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
   if constexpr (PAIR) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  B2D_TL(1, threadIdx.x == 0);  // set-up done
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
@@ -140,6 +167,53 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
     UnitCoord uc;
     for (wi.init(p); wi.next(p, uc);) {
       const int gcol0 = uc.gcol0 * BN;
+      if constexpr (!HALO && !PAIR) {
+        // Lean generic walk.  One K step is 4 MMAs of BN / 2 clocks, and this warp runs alone on its scheduler: every
+        // instruction of the loop is paid at its full latency.  The general (segment, tap, chunk) iterator costs ~110
+        // dependent instructions per step (indexed parameter loads, tap geometry, two barrier pairs) = 650-800 clocks,
+        // MORE than the step's 512 clocks of tensor work at BN = 256 (tools/timeline_conv.py, profiles/r2_timeline_*).
+        // Here the per-(segment, tap) work is hoisted out of the chunk loop, and since the A and B rings advance in
+        // lockstep (NA == NB) both tiles of a step complete on ONE barrier (a_full) and are released by ONE commit.
+        static_assert(NA == NB, "generic staging: the A and B rings advance in lockstep");
+        GroupIter it;
+        it.init(p, uc.k_lo, uc.k_hi);
+        int s = it.s, t = it.t, c = it.c, g = it.g;
+        int left = uc.k_hi - uc.k_lo;
+        while (left > 0) {
+          const int nch = p.cchunks[s] - c;
+          const int nc = nch < left ? nch : left;
+          const int zz = uc.z0 + p.dz[t];
+          if (!(p.skip_z && (zz < 0 || zz >= p.D))) {
+            const int xx = uc.x0 * p.stride_w + p.dx[t];
+            const int yy = uc.y0 * p.stride_h + p.dy[t];
+            int cc = c * kBlockK;
+            int kc = p.kbase[s] + t * p.cin[s] + cc;
+            const void* tmA = &tm.tmapA[s];
+            const int tlm = B2D_TL_MODE();
+            const uint32_t tx = ((tlm & 2) ? 0u : (uint32_t)Cfg::A_TILE) + ((tlm & 4) ? 0u : (uint32_t)Cfg::B_STAGE);
+#pragma unroll 1
+            for (int i = 0; i < nc; ++i) {
+              mbar_wait(&a_empty[ast], aph ^ 1);
+              B2D_TL_ITER(0, g + i, lane == 0);
+              if (elect_one()) {
+                const uint32_t bar = smem_u32(&a_full[ast]);
+                mbar_arrive_expect_tx(&a_full[ast], tx);
+                if (!(tlm & 2)) tma_load_5d_u(sA_u + ast * Cfg::A_STAGE, tmA, bar, cc, xx, yy, zz, uc.n0);
+                if (!(tlm & 4)) tma_load_2d_u(sB_u + ast * Cfg::B_STAGE, &tm.tmapB, bar, kc, gcol0);
+              }
+              __syncwarp();
+              cc += kBlockK;
+              kc += kBlockK;
+              if (++ast == NA) { ast = 0; aph ^= 1; }
+            }
+          }
+          left -= nc;
+          g += nc;
+          c = 0;
+          ++t;
+          if (g == p.goff[s + 1]) { t = 0; ++s; }
+        }
+      } else {
       GroupIter it;
       for (it.init(p, uc.k_lo, uc.k_hi); !it.done(); it.next(p)) {
         const int s = it.s;
@@ -173,11 +247,6 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
               tma_load_5d_pair(sA_u + ast * Cfg::A_STAGE, &tm.tmapA[s], smem_u32(&a_full[ast]), it.c * kBlockK, xx, yy, zz, uc.n0);
               tma_load_2d_pair(sB_u + bst * Cfg::B_STAGE, &tm.tmapB, smem_u32(&b_full[bst]), p.kbase[s] + tp * p.cin[s] + it.c * kBlockK,
                                gcol0 + wi.rank * Cfg::B_ROWS);
-            } else {
-              mbar_arrive_expect_tx(&a_full[ast], Cfg::A_TILE);
-              tma_load_5d_u(sA_u + ast * Cfg::A_STAGE, &tm.tmapA[s], smem_u32(&a_full[ast]), it.c * kBlockK, xx, yy, zz, uc.n0);
-              mbar_arrive_expect_tx(&b_full[bst], Cfg::B_STAGE);
-              tma_load_2d_u(sB_u + bst * Cfg::B_STAGE, &tm.tmapB, smem_u32(&b_full[bst]), p.kbase[s] + tp * p.cin[s] + it.c * kBlockK, gcol0);
             }
           }
           __syncwarp();
@@ -185,7 +254,9 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
           if (++bst == NB) { bst = 0; bph ^= 1; }
         }
       }
+      }
     }
+    B2D_TL(8, lane == 0);  // every load issued
   } else if (HALO && warp == Cfg::BP_WARP) {
     // ================================ weight (B) producer, halo mode ========================
     int bst = 0;
@@ -234,6 +305,48 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
       uint32_t accum = 0;
+      if constexpr (!HALO && !PAIR) {
+        // lean generic loop (see the producer): one barrier wait, four MMAs and one commit per K step
+        GroupIter it;
+        it.init(p, uc.k_lo, uc.k_hi);
+        int s = it.s, t = it.t, c = it.c, g = it.g;
+        int left = uc.k_hi - uc.k_lo;
+        const bool no_mma = (B2D_TL_MODE() & 1) != 0;
+        while (left > 0) {
+          const int nch = p.cchunks[s] - c;
+          const int nc = nch < left ? nch : left;
+          const int zz = uc.z0 + p.dz[t];
+          if (!(p.skip_z && (zz < 0 || zz >= p.D))) {
+#pragma unroll 1
+            for (int i = 0; i < nc; ++i) {
+              mbar_wait(&a_full[ast], aph);
+              tc_fence_after();
+              B2D_TL(2, lane == 0 && accum == 0);  // first operands of the unit have landed
+              B2D_TL_ITER(1, g + i, lane == 0);
+              if (elect_one()) {
+                const uint32_t a_lo = adesc_lo0 + (uint32_t)(ast * (Cfg::A_STAGE >> 4));
+                const uint32_t b_lo = bdesc_lo0 + (uint32_t)(ast * (Cfg::B_STAGE >> 4));
+                if (!no_mma) {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_bf16(d_tmem, ((uint64_t)adesc_hi << 32) | (a_lo + (uint32_t)(2 * k)), ((uint64_t)bdesc_hi << 32) | (b_lo + (uint32_t)(2 * k)),
+                              idesc, accum | (uint32_t)(k > 0));
+                }
+                umma_commit(&a_empty[ast]);
+              }
+              __syncwarp();
+              B2D_TL_ITER(2, g + i, lane == 0);
+              accum = 1;
+              if (++ast == NA) { ast = 0; aph ^= 1; }
+            }
+          }
+          left -= nc;
+          g += nc;
+          c = 0;
+          ++t;
+          if (g == p.goff[s + 1]) { t = 0; ++s; }
+        }
+      } else {
       GroupIter it;
       for (it.init(p, uc.k_lo, uc.k_hi); !it.done(); it.next(p)) {
         if constexpr (HALO) {
@@ -244,6 +357,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
           if (p.skip_z && (zz < 0 || zz >= p.D)) continue;
         }
         mbar_wait(XFORM ? &a_ready[ast] : &a_full[ast], aph);
+        B2D_TL(2, lane == 0 && accum == 0);  // first operands of the unit have landed
         const uint32_t a_lo = adesc_lo0 + (uint32_t)(ast * (Cfg::A_STAGE >> 4));
         // halo: the in-plane taps fed by one staged box (9, or 4 for the upsample-folded convs), restricted to the B-stage
         // steps [j0, j1) of this group that belong to the item; generic: one step per group
@@ -251,8 +365,10 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         for (int ip = it.j0 * Cfg::TPB; ip < it.j1 * Cfg::TPB; ip += Cfg::TPB) {
           mbar_wait(&b_full[bst], bph);
           tc_fence_after();
+          B2D_TL_ITER(1, it.g, lane == 0 && !HALO);
           const uint32_t b_lo = bdesc_lo0 + (uint32_t)(bst * (Cfg::B_STAGE >> 4));
           if (elect_one()) {
+            if (!(B2D_TL_MODE() & 1))
 #pragma unroll
             for (int j = 0; j < Cfg::TPB; ++j) {
               // tap (dy,dx) = row offset ((1+dy)*18 + (1+dx)) * 128 B into the staged halo box (8 = 128 B >> 4)
@@ -277,10 +393,13 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         }
         if (elect_one()) { if constexpr (PAIR) umma_commit_pair(&a_empty[ast]); else umma_commit(&a_empty[ast]); }
         __syncwarp();
+        B2D_TL_ITER(2, it.g, lane == 0 && !HALO);
         if (++ast == NA) { ast = 0; aph ^= 1; }
+      }
       }
       if (elect_one()) { if constexpr (PAIR) umma_commit_pair(&t_full[acc]); else umma_commit(&t_full[acc]); }
       __syncwarp();
+      B2D_TL(3, lane == 0);  // last MMA of the unit issued
       if (++acc == Cfg::NACC) { acc = 0; accph ^= 1; }
     }
     }
@@ -398,8 +517,10 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         sm_bias_u = smem_u32(sb);
       }
 
+      B2D_TL(9, ew == 0 && lane == 0);  // epilogue warp ready (bias staged), waiting for the accumulator
       mbar_wait(&t_full[acc], accph);
       tc_fence_after();
+      B2D_TL(4, ew == 0 && lane == 0);  // accumulator complete
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * Cfg::ACC_COLS + mt * Cfg::BNC + col_off);
       auto load_tmem = [&](int col0, float (&f)[CW]) {
         uint32_t v[32];
@@ -414,6 +535,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(&t_empty[acc], 0); else mbar_arrive(&t_empty[acc]); }
+        B2D_TL(7, ew == 0 && lane == 0);  // unit's epilogue done (unshared tile)
       } else {
         // ---- the tile's K loop is shared (split-K / stream-K): park the fp32 partial, the last piece to arrive reduces
         // all of them in piece order (deterministic) ----
@@ -431,6 +553,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
         __syncwarp();
         if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(&t_empty[acc], 0); else mbar_arrive(&t_empty[acc]); }
         __threadfence();
+        B2D_TL(5, ew == 0 && lane == 0);  // partial tile parked
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         if ((threadIdx.x & 127) == 64) {  // first thread of this four-warp group (warps 2.. start at thread 64)
           int* ctr = p.counters + (uc.tile * MT + mt) * Cfg::NCG + (HALO ? 0 : grp);  // one ticket per (tile, M half, column group)
@@ -440,6 +563,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
           last_flag[grp] = last;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        B2D_TL(6, ew == 0 && lane == 0);  // ticket taken
         if (last_flag[grp]) {
           __threadfence();
           const float4* wbase = reinterpret_cast<const float4*>(p.ws + (long long)mt * (128LL * BN)) + r;
@@ -447,8 +571,28 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
           auto load_ws = [&](int col0, float (&f)[CW]) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) f[j] = 0.f;
+            // two pieces' loads in flight at a time (each is an L2 round trip of ~1000 clocks for this lone warp group);
+            // the additions keep the piece order, so the sum is bit-identical to the one-at-a-time loop
+            int ks = 0;
 #pragma unroll 1
-            for (int ks = 0; ks < pi.npieces; ++ks) {
+            for (; ks + 1 < pi.npieces; ks += 2) {
+              const float4* s0 = wbase + piece_slot(p, uc, pi, ks, ncta) * slot_stride + ((col_off + col0) / 4) * 128;
+              const float4* s1 = wbase + piece_slot(p, uc, pi, ks + 1, ncta) * slot_stride + ((col_off + col0) / 4) * 128;
+              float4 v0[CW / 4], v1[CW / 4];
+#pragma unroll
+              for (int q = 0; q < CW / 4; ++q) v0[q] = __ldcg(s0 + q * 128);
+#pragma unroll
+              for (int q = 0; q < CW / 4; ++q) v1[q] = __ldcg(s1 + q * 128);
+#pragma unroll
+              for (int q = 0; q < CW / 4; ++q) {
+                f[4 * q] += v0[q].x; f[4 * q + 1] += v0[q].y; f[4 * q + 2] += v0[q].z; f[4 * q + 3] += v0[q].w;
+              }
+#pragma unroll
+              for (int q = 0; q < CW / 4; ++q) {
+                f[4 * q] += v1[q].x; f[4 * q + 1] += v1[q].y; f[4 * q + 2] += v1[q].z; f[4 * q + 3] += v1[q].w;
+              }
+            }
+            if (ks < pi.npieces) {
               const float4* src = wbase + piece_slot(p, uc, pi, ks, ncta) * slot_stride + ((col_off + col0) / 4) * 128;
 #pragma unroll
               for (int q = 0; q < CW / 4; ++q) {
@@ -458,6 +602,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
             }
           };
           conv_epilogue_row<BNG, CW, SMEM_STATS, !HALO>(p, rw, co_base, lane, seg, sm_stats + ew * 64, load_ws, (one_group || one_group_w) ? thr_acc : nullptr, sm_bias_u, sm_stage_u);
+          B2D_TL(7, ew == 0 && lane == 0);  // shared tile reduced and stored by this (last) piece
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // last_flag is reused by the next unit
       }
@@ -585,6 +730,7 @@ __device__ __forceinline__ void conv_v2_layer(const ConvKParams& p, uint8_t* sme
 
   tc_fence_before();
   __syncthreads();
+  B2D_TL(10, threadIdx.x == 0);  // every role done
   if constexpr (PAIR) cluster_sync_all();  // no remote arrival or MMA operand read may target a CTA that has exited
   if (warp == 1) {
     tc_fence_after();
