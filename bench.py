@@ -182,7 +182,10 @@ def workload_config(args):
     return {"workload": f"predict_ddim DDIM-{args.ddim_steps} end to end (E2D encode -> conditioned-UNet loop -> D3D decode) on synthetic "
                         f"microstructures of {args.slices}x{args.size}x{args.size}, UNet in17/out8 k3 zeros-pad attn 3..2 + dual-branch VAE, "
                         "random-init weights (BASELINE.json configs[2]/[3])",
-            "ddim_steps": args.ddim_steps, "slices": args.slices, "size": args.size}
+            "ddim_steps": args.ddim_steps, "slices": args.slices, "size": args.size,
+            "l2": "no explicit flush between timed steps: a step streams activation tensors of "
+                  f"{min(args.batch_per_gpu, args.vae_chunk) * args.slices * args.size ** 2 * 128 * 2 / 1e9:.2f} GB each (GPU arm, "
+                  "128-channel VAE maps) through the 126 MB L2"}
 
 
 def run_b200(args):

@@ -305,6 +305,11 @@ class B200LatentDiffusionPredictor:
             raise ValueError(f"shape mismatch: img {tuple(img.shape)} velocity_2d {tuple(velocity_2d.shape)}")
         return B, S, img.shape[3], img.shape[4]
 
+    def _empty_fields(self, S, H, W):
+        """An empty batch (a rank's shard when the batch is smaller than the world, sharding.predict_sharded): the
+        reference's modules map (0, ...) to (0, ...); no kernel is launched."""
+        return torch.empty(0, S, 3, H, W, dtype=torch.float32, device=self.device)
+
     def encode_target(self, velocity_3d: torch.Tensor, velocity_2d: Optional[torch.Tensor] = None) -> torch.Tensor:
         """predictor.py:1042-1085: 3D velocity target (B, S, 3, H, W) -> E3D latents (B, S, latent, H/4, W/4): permute to
         (B, 3, S, H, W), MaxNormalizer (fused into the layout pass), deterministic E3D encoding (mu), permute back.
@@ -361,6 +366,8 @@ class B200LatentDiffusionPredictor:
     def predict_ddim(self, img, velocity_2d, num_steps: int = 50, eta: float = 0.0, noise=None, *, step_noise=None, record=None):
         """predictor.py:898-1023."""
         B, S, H, W = self._check_inputs(img, velocity_2d)
+        if B == 0:
+            return self._empty_fields(S, H, W)
         ses = self._get_session(B, S, H, W)
         s = _lib.stream_ptr()
         timesteps = self.ddim_timesteps(num_steps)
@@ -385,6 +392,8 @@ class B200LatentDiffusionPredictor:
     def predict(self, img, velocity_2d, noise=None, *, step_noise=None, record=None):
         """predictor.py:754-896 (multi-step branch; num_timesteps == 1 takes the one-shot branch :823-838)."""
         B, S, H, W = self._check_inputs(img, velocity_2d)
+        if B == 0:
+            return self._empty_fields(S, H, W)
         ses = self._get_session(B, S, H, W)
         s = _lib.stream_ptr()
         T = self.num_timesteps

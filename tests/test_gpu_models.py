@@ -331,6 +331,12 @@ def test_broadcast_mask_and_input_validation(unet_sd, vae_sd):
     full = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()
     one = p.predict_ddim(img[:, :1].cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()   # (B,1,1,H,W) mask
     assert torch.equal(full, one)
+    # an empty batch (a rank's shard of a batch smaller than the world) comes back as an empty field tensor
+    for fn in (p.predict_ddim, p.predict):
+        empty = fn(img.cuda()[:0], v2d.cuda()[:0])
+        assert tuple(empty.shape) == (0, 2, 3, 128, 128) and empty.is_cuda and empty.dtype == torch.float32
+    again = p.predict_ddim(img.cuda(), v2d.cuda(), num_steps=2, noise=noise.cuda()).cpu()          # the session is untouched
+    assert torch.equal(full, again)
     with pytest.raises(ValueError):
         p.predict_ddim(img.cuda()[..., :64], v2d.cuda(), num_steps=2)
     m = p.model

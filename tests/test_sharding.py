@@ -24,7 +24,9 @@ def test_shard_range_covers_batch():
 
 class _FakePredictor:
     def predict_ddim(self, img, v2d, noise=None, **kw):
-        return v2d * 2 + (0 if noise is None else noise.reshape(v2d.shape[0], v2d.shape[1], -1).sum(-1)[:, :, None, None, None])
+        if noise is None:
+            return v2d * 2
+        return v2d * 2 + noise.reshape(v2d.shape[0], v2d.shape[1], noise.shape[1:].numel()).sum(-1)[:, :, None, None, None]
 
 
 def _worker(rank, world, port, B):
@@ -47,8 +49,10 @@ def _worker(rank, world, port, B):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B", [4, 5])
+@pytest.mark.parametrize("B", [4, 5, 1])
 def test_gloo_world2_shard_and_gather(B):
+    """Even, ragged, and fewer samples than ranks (rank 1's shard is empty: the predictor hands back an empty field tensor
+    and the gather pads it)."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
