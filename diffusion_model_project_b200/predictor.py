@@ -29,7 +29,7 @@ from typing import Dict, List, Optional, Sequence
 
 import torch
 
-from . import _lib, checkpoint, engine
+from . import _lib, checkpoint, engine, sharding
 from .engine import Act, new_act
 from .scheduler import B200Scheduler
 from .unet import B200UNet
@@ -114,9 +114,7 @@ class B200LatentDiffusionPredictor:
         # micro-batching: the VAE passes run over `chunk` samples at a time against ONE set of activation buffers
         # (25 GB per 8 samples of 11x256x256); a ragged tail re-runs the last `chunk` samples (idempotent)
         chunk = min(B, self.vae_chunk)
-        starts = list(range(0, B - chunk + 1, chunk))
-        if starts[-1] + chunk < B:
-            starts.append(B - chunk)
+        starts = sharding.chunk_starts(B, chunk)
         ses = dict(key=key, B=B, S=S, H=H, W=W, h=h, w=w, N=N, chunk=chunk, starts=starts)
         # everything two concurrent sampling loops must not share lives in the session: split-K scratch + arrival
         # counters, and the loop state {step index, ticket, 64-bit Philox seed} the kernels read and advance

@@ -19,6 +19,18 @@ def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def chunk_starts(batch: int, chunk: int) -> List[int]:
+    """First samples of the micro-batches a VAE pass runs over (predictor._get_session): windows of exactly `chunk`
+    samples (one set of activation buffers and plans serves them all), back to back from 0; a ragged tail is covered
+    by one more window that ENDS at the batch's last sample and so re-computes up to chunk-1 samples (idempotent)."""
+    if batch < 1 or chunk < 1 or chunk > batch:
+        raise ValueError(f"chunk_starts: need 1 <= chunk <= batch, got chunk={chunk} batch={batch}")
+    starts = list(range(0, batch - chunk + 1, chunk))
+    if starts[-1] + chunk < batch:
+        starts.append(batch - chunk)
+    return starts
+
+
 def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     lo, hi = shard_range(t.shape[0], rank, world)
     return t[lo:hi]

@@ -22,6 +22,25 @@ def test_shard_range_covers_batch():
         sharding.shard_range(4, 2, 2)
 
 
+def test_chunk_starts_cover_every_sample_with_full_windows():
+    """The VAE micro-batching of predict / predict_ddim (B = 64 on one GPU in chunks of 8; ragged tails)."""
+    assert sharding.chunk_starts(64, 8) == list(range(0, 64, 8))
+    assert sharding.chunk_starts(3, 2) == [0, 1] and sharding.chunk_starts(3, 1) == [0, 1, 2] and sharding.chunk_starts(5, 5) == [0]
+    assert sharding.chunk_starts(19, 8) == [0, 8, 11]
+    for B in range(1, 70):
+        for chunk in range(1, min(B, 9) + 1):
+            st = sharding.chunk_starts(B, chunk)
+            assert st[0] == 0 and st == sorted(set(st)) and all(0 <= c0 and c0 + chunk <= B for c0 in st)
+            covered = set()
+            for c0 in st:
+                covered.update(range(c0, c0 + chunk))
+            assert covered == set(range(B))
+            assert len(st) == -(-B // chunk)                       # no more passes than a ragged split would need
+    for bad in ((0, 1), (4, 0), (4, 5)):
+        with pytest.raises(ValueError):
+            sharding.chunk_starts(*bad)
+
+
 class _FakePredictor:
     def predict_ddim(self, img, v2d, noise=None, **kw):
         if noise is None:
