@@ -6,7 +6,7 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
 
 One "step" = one full `predict_ddim` (E2D encode -> 50 DDIM steps of the conditioned UNet -> D3D
-decode) over this rank's batch of synthetic 256x256x11 microstructures, bf16, random-init weights of
+decode) over this rank's batch of synthetic 256x256x11 microstructures, IEEE-fp16 operands (`--precision`), random-init weights of
 the named architecture (no dataset/checkpoint is reachable offline).  Default: weak scaling, every
 rank owns `--batch-per-gpu` samples (BASELINE configs[2]: 64 samples over 8 GPUs = 8 per GPU); the
 same line also carries `strong`: a FIXED global batch (`--strong-batch`, default 64 = configs[3], the
@@ -72,7 +72,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.mark_idx = index, None, [], 0
 
     def start(self):
         try:
@@ -87,6 +87,11 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark(self):
+        """The timed region starts here: the sampler has been running since before the warm-up steps (same workload), so
+        a region shorter than nvidia-smi's start-up + sampling period still gets its samples."""
+        self.mark_idx = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -97,7 +102,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines, window = self.lines[self.mark_idx:], "timed region"
+        if not any(len(ln.split(",")) >= 7 for ln in lines) and self.mark_idx > 0:
+            # a timed region shorter than one sampling period: the last samples of the warm-up steps just before it
+            lines, window = self.lines[max(0, self.mark_idx - 3):self.mark_idx], "warm-up steps just before the timed region (region shorter than one 200 ms sample)"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -109,7 +118,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+                "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -228,7 +237,7 @@ def run_b200(args):
     def timed(fn, steps, sampler=None):
         sync_all()
         if sampler:
-            sampler.start()
+            sampler.mark()
             torch.cuda.profiler.start()  # no-op unless run under `ncu --profile-from-start off` (profiles/ launch list)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count
@@ -274,6 +283,8 @@ def run_b200(args):
             if out is not None:
                 out_h.copy_(out, non_blocking=True)
 
+        if sampler:
+            sampler.start()  # before the warm-up steps; timed() marks where the timed region begins
         for _ in range(warmup):
             step_resident()
         ms, launches, clocks = timed(step_resident, steps, sampler)

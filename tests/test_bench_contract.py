@@ -82,3 +82,52 @@ def test_gpu_arm_refuses_to_run_without_a_device():
     r = _bench("--steps", "1", "--warmup", "1", *TINY)
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CPU fallback" in r.stderr
+
+
+_FAKE_SMI = """#!/bin/sh
+# prints one CSV sample every 50 ms like `nvidia-smi --query-gpu=... -lms`
+i=0
+while true; do
+  i=$((i+1))
+  echo "$((1500+i)), 1965, Not Active, Not Active, Not Active, Active, 900.5"
+  sleep 0.05
+done
+"""
+
+
+def _fake_smi(tmp_path, monkeypatch):
+    exe = tmp_path / "nvidia-smi"
+    exe.write_text(_FAKE_SMI)
+    exe.chmod(0o755)
+    monkeypatch.setenv("PATH", f"{tmp_path}{os.pathsep}{os.environ['PATH']}")
+
+
+def test_clock_sampler_windows(tmp_path, monkeypatch):
+    """`clocks` comes from the samples taken DURING the timed region; a region shorter than one sampling period falls back
+    to the last warm-up samples (same workload) and says so; no nvidia-smi -> stated, not invented."""
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    _fake_smi(tmp_path, monkeypatch)
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.4)           # warm-up steps
+    s.mark()
+    n_before = s.mark_idx
+    time.sleep(0.4)           # timed region
+    c = s.stop()
+    assert n_before >= 2 and c["window"] == "timed region" and c["samples"] >= 2
+    assert c["sm_max_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"] and c["power_w_max"] == 900.5
+    assert c["sm_mhz"] > 1500 + n_before                       # only samples after the mark count
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.4)
+    s.mark()
+    c = s.stop()              # an (almost) empty timed region
+    if c["window"] != "timed region":                          # (a sample may still slip in between mark and stop)
+        assert "warm-up" in c["window"] and 1 <= c["samples"] <= 3 and c["sm_mhz"] is not None
+    monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
+    s = bench.ClockSampler(0)
+    s.start()
+    s.mark()
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"]
