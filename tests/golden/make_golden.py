@@ -20,6 +20,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.environ.get("B2D_GOLDEN_OUT", HERE)  # where the vectors are written (tests/test_golden_regen.py redirects it)
 sys.path.insert(0, ROOT)
 sys.path[:0] = ["/root/reference", "/root/reference/Diffusion_model"]
 os.environ["PYTHONDONTWRITEBYTECODE"] = "1"
@@ -89,7 +90,7 @@ def main():
         "unet": [[k, list(v.shape)] for k, v in unet.state_dict().items()],
         "vae": [[k, list(v.shape)] for k, v in vae.state_dict().items()],
     }
-    with open(os.path.join(HERE, "reference_keys.json"), "w") as f:
+    with open(os.path.join(OUT, "reference_keys.json"), "w") as f:
         json.dump(keys, f)
 
     # ---- 2. scheduler -----------------------------------------------------------------------
@@ -118,7 +119,7 @@ def main():
         out[f"ddim_{t}_{tp}"] = sch.ddim_sample(eps, x, t, tp, eta=0.0).numpy()
         with NoiseFeeder([z]):
             out[f"ddim_eta05_{t}_{tp}"] = sch.ddim_sample(eps, x, t, tp, eta=0.5).numpy()
-    np.savez_compressed(os.path.join(HERE, "scheduler.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "scheduler.npz"), **out)
 
     # ---- 3. UNet forward ---------------------------------------------------------------------
     unet.load_state_dict(synth.synth_unet_state(seed=0))
@@ -127,7 +128,7 @@ def main():
     xin = torch.randn(2, 17, 32, 32, generator=g)
     tt = torch.tensor([999, 500], dtype=torch.long)
     eps_out = unet(xin, tt)
-    np.savez_compressed(os.path.join(HERE, "unet.npz"), eps=eps_out.numpy(), t=tt.numpy())
+    np.savez_compressed(os.path.join(OUT, "unet.npz"), eps=eps_out.numpy(), t=tt.numpy())
     print("unet eps", eps_out.abs().max().item(), eps_out.std().item())
 
     # ---- 4. VAE branches -----------------------------------------------------------------------
@@ -140,7 +141,7 @@ def main():
     zz, (mu, logvar) = vae.encode_2d_deterministic(xv)
     zl = torch.randn(1, 8, 3, 8, 8, generator=g)
     dec = vae.decode_3d(zl)
-    np.savez_compressed(os.path.join(HERE, "vae.npz"), mu=mu.numpy(), logvar=logvar.numpy(), dec=dec.numpy())
+    np.savez_compressed(os.path.join(OUT, "vae.npz"), mu=mu.numpy(), logvar=logvar.numpy(), dec=dec.numpy())
     print("vae mu", mu.abs().max().item(), "dec", dec.abs().max().item())
 
     # ---- 5. predict_ddim / predict end to end (small) --------------------------------------------
@@ -164,7 +165,7 @@ def main():
         with NoiseFeeder(zs):
             out_ddim_eta = pred.predict_ddim(img, v2d, num_steps=3, eta=0.7, noise=noise.clone())
         rec.clear()
-        np.savez_compressed(os.path.join(HERE, "predict_ddim.npz"), out=out_ddim.numpy(), eps_steps=eps_steps.numpy(),
+        np.savez_compressed(os.path.join(OUT, "predict_ddim.npz"), out=out_ddim.numpy(), eps_steps=eps_steps.numpy(),
                             out_eta07=out_ddim_eta.numpy())
         print("ddim out", out_ddim.abs().max().item())
 
@@ -174,7 +175,7 @@ def main():
         zs = [torch.randn(2, 8, 32, 32, generator=g) for _ in range(12)]
         with NoiseFeeder(zs):
             out_ddpm = pred.predict(img, v2d, noise=noise.clone())
-        np.savez_compressed(os.path.join(HERE, "predict_ddpm.npz"), out=out_ddpm.numpy())
+        np.savez_compressed(os.path.join(OUT, "predict_ddpm.npz"), out=out_ddpm.numpy())
         print("ddpm out", out_ddpm.abs().max().item())
 
 

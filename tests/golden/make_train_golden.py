@@ -17,6 +17,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.environ.get("B2D_GOLDEN_OUT", HERE)  # where the vectors are written (tests/test_golden_regen.py redirects it)
 sys.path.insert(0, ROOT)
 sys.path[:0] = ["/root/reference", "/root/reference/Diffusion_model"]
 os.environ["PYTHONDONTWRITEBYTECODE"] = "1"
@@ -71,7 +72,7 @@ def main():
     for k in FULL:
         out[f"grad::{k}"] = params[k].grad.numpy()
         out[f"delta::{k}"] = (params[k].detach() - before[k]).numpy()
-    np.savez_compressed(os.path.join(HERE, "train_step.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "train_step.npz"), **out)
     print("loss", loss.item(), "params", len(names), "max grad norm", max(norms))
 
 
@@ -93,7 +94,7 @@ def main_encode_target():
     pred.vae.encoder_3d.load_state_dict({k[len("encoder_3d."):]: v for k, v in vsd.items() if k.startswith("encoder_3d.")})
     with torch.no_grad():
         lat = pred.encode_target(target_inputs())
-    np.savez_compressed(os.path.join(HERE, "encode_target.npz"), latents=lat.numpy())
+    np.savez_compressed(os.path.join(OUT, "encode_target.npz"), latents=lat.numpy())
     print("encode_target", tuple(lat.shape), lat.abs().max().item())
 
 
@@ -149,7 +150,7 @@ def main_train_from_fields():
     for k in ("final_conv.weight", "encoder.0.0.block1.conv.weight", "bottleneck.block2.norm.weight"):
         out[f"grad::{k}"] = params[k].grad.numpy()
         out[f"delta::{k}"] = (params[k].detach() - before[k]).numpy()
-    np.savez_compressed(os.path.join(HERE, "train_from_fields.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "train_from_fields.npz"), **out)
     print("train_from_fields: loss", loss.item(), "t", t.tolist(), "max grad norm", max(norms))
 
 
