@@ -1,0 +1,58 @@
+"""The oracle against the UNMODIFIED reference at BASELINE.json's own size -- one microstructure of 11 x 256 x 256, DDIM-50,
+configs[0], the case bench.py's CPU arm times.  The committed fixtures pin the oracle at 2 slices of 128 x 128 (they have to
+stay small); the GPU suite compares the CUDA path with the oracle at 11 x 256 x 256 (tests/test_gpu_parity_full.py).  This
+test closes the chain where the reference tree is present (the build container): reference == oracle at the full size, per
+step and on the final field, so "CUDA vs oracle" there means "CUDA vs reference"."""
+import os
+import sys
+import tempfile
+
+import pytest
+import torch
+
+from diffusion_model_project_b200 import synth
+from oracle import predictor as opred
+
+REFERENCE = "/root/reference"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "Diffusion_model")), reason="the reference tree is only present in the build container")
+def test_oracle_equals_reference_ddim50_at_11x256x256():
+    sys.path.insert(0, GOLDEN)
+    import make_golden  # puts /root/reference on sys.path; build_reference_predictor() = the unmodified LatentDiffusionPredictor
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    try:
+        S, H, steps = 11, 256, 50
+        img, v2d = synth.synth_inputs(1, num_slices=S, size=H, seed=2024)
+        noise = synth.synth_noise(1, num_slices=S, latent_size=H // 4, seed=42)
+        with tempfile.TemporaryDirectory() as tmp:
+            ref = make_golden.build_reference_predictor(tmp, num_timesteps=1000, num_slices=S)
+            ref_eps, fwd = [], ref.model.forward
+
+            def spy(x, t):
+                e = fwd(x, t)
+                ref_eps.append((int(t[0]), x[:, :8].clone(), e.clone()))
+                return e
+            ref.model.forward = spy
+            out_ref = ref.predict_ddim(img, v2d, num_steps=steps, eta=0.0, noise=noise.clone())
+            del ref
+        rec = []
+        out = opred.predict_ddim(synth.synth_unet_state(seed=0), synth.synth_vae_state(seed=1), img, v2d, noise.clone(), num_steps=steps,
+                                 eta=0.0, norm_factors=synth.NORM_FACTORS, record=rec)
+    finally:
+        torch.set_grad_enabled(prev)
+    assert out.shape == out_ref.shape == (1, S, 3, H, H)
+    assert len(rec) == len(ref_eps) == steps
+    worst_eps = worst_x = 0.0
+    for (t_o, x_o, e_o, _), (t_r, x_r, e_r) in zip(rec, ref_eps):
+        assert t_o == t_r                                            # the DDIM-50 schedule of predictor.py:965
+        worst_x = max(worst_x, ((x_o - x_r).abs().max() / x_r.abs().max()).item())
+        worst_eps = max(worst_eps, ((e_o - e_r).abs().max() / e_r.abs().max()).item())
+    field = ((out - out_ref).norm() / out_ref.norm()).item()
+    print(f"oracle vs reference at 11x256x256, DDIM-50: eps max-rel {worst_eps:.2e}, x_t max-rel {worst_x:.2e}, field rel-L2 {field:.2e}")
+    # same fp32 ATen ops in the same order: agreement is at rounding level (thread-count dependent reductions only)
+    assert worst_eps <= 1e-4 and worst_x <= 1e-4 and field <= 1e-5
+    solid = (img == 0).expand_as(out)
+    assert (out[solid] == 0).all() and (out_ref[solid] == 0).all()  # the mask multiply of predictor.py:1021
