@@ -56,3 +56,41 @@ def test_oracle_equals_reference_ddim50_at_11x256x256():
     assert worst_eps <= 1e-4 and worst_x <= 1e-4 and field <= 1e-5
     solid = (img == 0).expand_as(out)
     assert (out[solid] == 0).all() and (out_ref[solid] == 0).all()  # the mask multiply of predictor.py:1021
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "Diffusion_model")), reason="the reference tree is only present in the build container")
+def test_oracle_training_step_equals_reference_at_22x64x64():
+    """BASELINE configs[4]'s per-GPU step (2 samples = 22 slice-images of 8 x 64 x 64 latents), the inputs of
+    tests/test_gpu_train.py::test_training_step_at_baseline_size: the unmodified reference modules (UNet, q_sample, the
+    default criterion, loss.backward()) against the oracle's step -- loss, eps and every one of the 172 parameter gradients."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden  # noqa: F401  (puts /root/reference on sys.path)
+    from src.unet.models import UNet
+    from src.diffusion import DiffusionScheduler
+    from src.unet.metrics import cost_function
+    from oracle import train as otrain
+
+    g = torch.Generator().manual_seed(77)
+    N, S = 22, 64
+    x_start, cond = torch.randn(N, 8, S, S, generator=g), torch.randn(N, 8, S, S, generator=g)
+    feats, noise = torch.rand(N, 1, S, S, generator=g), torch.randn(N, 8, S, S, generator=g)
+    t = torch.randint(0, 1000, (N,), generator=g)
+    sd = synth.synth_unet_state(seed=0)
+    with torch.enable_grad():
+        unet = UNet(**synth.UNET_KWARGS)
+        unet.load_state_dict(sd)
+        unet.train()                                                  # helper.py:273 (dropout p = 0)
+        x_t = DiffusionScheduler(1000, device="cpu").q_sample(x_start, t, noise)
+        pred = unet(torch.cat([x_t, cond, feats], dim=1), t)          # predictor.py:743-746
+        loss = cost_function("normalized_mse_loss_per_component")(output=pred, target=noise)
+        loss.backward()                                               # helper.py:429
+    ref_grads = {k: p.grad.detach() for k, p in unet.named_parameters()}
+    oloss, ograds, opred = otrain.training_loss_and_grads(sd, x_start, cond, feats, t, noise)
+    assert len(ref_grads) == 172 and set(ref_grads) == set(ograds)
+    assert abs(oloss.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    assert ((opred - pred.detach()).abs().max() / pred.detach().abs().max()).item() <= 1e-5
+    errs = {k: ((ograds[k] - ref_grads[k]).norm() / ref_grads[k].norm().clamp_min(1e-30)).item() for k in ref_grads}
+    worst = max(errs, key=errs.get)
+    print(f"oracle vs reference training step at 22x64x64: loss {loss.item():.6f} vs {oloss.item():.6f}, worst gradient rel-L2 "
+          f"{errs[worst]:.2e} ({worst}), median {sorted(errs.values())[len(errs) // 2]:.2e}")
+    assert errs[worst] <= 1e-4, (worst, errs[worst])
