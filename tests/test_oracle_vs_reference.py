@@ -94,3 +94,28 @@ def test_oracle_training_step_equals_reference_at_22x64x64():
     print(f"oracle vs reference training step at 22x64x64: loss {loss.item():.6f} vs {oloss.item():.6f}, worst gradient rel-L2 "
           f"{errs[worst]:.2e} ({worst}), median {sorted(errs.values())[len(errs) // 2]:.2e}")
     assert errs[worst] <= 1e-4, (worst, errs[worst])
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "Diffusion_model")), reason="the reference tree is only present in the build container")
+def test_oracle_one_shot_branch_equals_reference():
+    """`predict` with num_timesteps == 1 (predictor.py:823-838): one UNet call at t = 0, x0 from alphas_cumprod[0], clamp,
+    decode.  No committed fixture covers this branch; the GPU test (test_predict_one_shot_branch) compares with the oracle,
+    so the oracle is held to the unmodified reference here (2 slices of 128 x 128, the fixtures' size)."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    try:
+        img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=2024)
+        noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=42)
+        with tempfile.TemporaryDirectory() as tmp:
+            ref = make_golden.build_reference_predictor(tmp, num_timesteps=1, num_slices=2)
+            out_ref = ref.predict(img, v2d, noise=noise.clone())
+        out = opred.predict(synth.synth_unet_state(seed=0), synth.synth_vae_state(seed=1), img, v2d, noise.clone(), None,
+                            norm_factors=synth.NORM_FACTORS, num_timesteps=1)
+    finally:
+        torch.set_grad_enabled(prev)
+    assert out.shape == out_ref.shape == (1, 2, 3, 128, 128) and out_ref.abs().max() > 0
+    err = ((out - out_ref).norm() / out_ref.norm()).item()
+    print(f"oracle vs reference, one-shot predict: field rel-L2 {err:.2e}")
+    assert err <= 1e-5
