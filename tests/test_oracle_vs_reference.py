@@ -119,3 +119,29 @@ def test_oracle_one_shot_branch_equals_reference():
     err = ((out - out_ref).norm() / out_ref.norm()).item()
     print(f"oracle vs reference, one-shot predict: field rel-L2 {err:.2e}")
     assert err <= 1e-5
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "Diffusion_model")), reason="the reference tree is only present in the build container")
+def test_oracle_without_distance_transform_equals_reference():
+    """distance_transform = False (predictor.py:1035-1036 skipped): the mask itself, bilinearly resized, is the feature
+    channel.  The fixtures all use the distance transform; this holds the oracle's `use_edt=False` branch to the reference."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    try:
+        img, v2d = synth.synth_inputs(1, num_slices=2, size=128, seed=2024)
+        noise = synth.synth_noise(1, num_slices=2, latent_size=32, seed=42)
+        with tempfile.TemporaryDirectory() as tmp:
+            ref = make_golden.build_reference_predictor(tmp, num_timesteps=1000, num_slices=2)
+            ref.distance_transform = torch.nn.Parameter(torch.Tensor([False]), requires_grad=False)   # predictor.py:145-148
+            out_ref = ref.predict_ddim(img, v2d, num_steps=2, eta=0.0, noise=noise.clone())
+        usd, vsd = synth.synth_unet_state(seed=0), synth.synth_vae_state(seed=1)
+        out = opred.predict_ddim(usd, vsd, img, v2d, noise.clone(), num_steps=2, eta=0.0, norm_factors=synth.NORM_FACTORS, use_edt=False)
+        with_edt = opred.predict_ddim(usd, vsd, img, v2d, noise.clone(), num_steps=2, eta=0.0, norm_factors=synth.NORM_FACTORS)
+    finally:
+        torch.set_grad_enabled(prev)
+    err = ((out - out_ref).norm() / out_ref.norm()).item()
+    other = ((with_edt - out_ref).norm() / out_ref.norm()).item()
+    print(f"oracle vs reference without the distance transform: field rel-L2 {err:.2e} (with it: {other:.2e})")
+    assert err <= 1e-5 and other > 1e-3          # and the switch matters
