@@ -1,7 +1,7 @@
 """Where does the bf16 path's end-to-end error come from?  One sample of 11x256x256, DDIM-N: the GPU path against the CPU
 oracle, stage by stage -- conditioning (E2D mu, distance features), the latent after the loop, the decode alone (D3D of the
 ORACLE's final latent), and the loop alone (GPU loop started from the oracle's conditioning).
-usage: python tools/diag_parity.py [steps=50] [precision=bf16] [B=1]"""
+usage: python tests/diag_parity.py [steps=50] [precision=bf16] [B=1]"""
 import os
 import sys
 
@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from diffusion_model_project_b200 import _lib, engine, synth  # noqa: E402
 from diffusion_model_project_b200.predictor import B200LatentDiffusionPredictor  # noqa: E402
 from oracle import predictor as opred  # noqa: E402

@@ -7,7 +7,7 @@ sequence, pinned to the reference's outputs by tests/test_oracle_golden.py):
 The 16-bit mode that meets BOTH bounds at this size is "f16" (IEEE fp16 operands, the default).  With bf16 operands
 ("bf16" mode) a single UNet evaluation is 1.1e-2 off (inside the 2e-2 per-step bound) but the 50-step trajectory ends
 1.8e-2 from the oracle's field -- outside the 1e-2 bound; that measurement is kept below as its own test so the reason
-for the default is on record (tools/diag_parity.py decomposes it: E2D 8e-3, loop 1.6e-2, D3D 4e-3).
+for the default is on record (tests/diag_parity.py decomposes it: E2D 8e-3, loop 1.6e-2, D3D 4e-3).
 
 Per-step eps is the north star's "per-step noise-prediction max relative error": the ORACLE's UNet evaluated on the GPU
 path's own UNet input of that step (its x_t, and its E2D / distance conditioning as stored), so the number isolates one
