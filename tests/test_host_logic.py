@@ -234,3 +234,24 @@ def test_zstack_conv_in_weights_match_reference_math():
     xs = torch.cat([xp[:, :, kz:kz + D] for kz in range(3)], dim=1)                     # [1, 3*ci, D, H, W], channel kz*ci + c
     got = torch.stack([F.conv2d(xs[:, :, z], w2d, b, padding=1) for z in range(D)], dim=2)
     assert (got - ref).abs().max() <= 2e-2 * ref.abs().max()  # bf16-rounded packed weights
+
+
+def test_only_the_checkers_import_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs (one function) may import
+    it -- never the product package or the measurement tools."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    offenders = []
+    for sub in ("diffusion_model_project_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith(".py") and pat.search(open(os.path.join(dirpath, f)).read()):
+                    offenders.append(os.path.join(sub, f))
+    assert offenders == []
+    bench = open(os.path.join(root, "bench.py")).read()
+    hits = [m.start() for m in pat.finditer(bench)]
+    fn = bench.index("def cpu_reference_prediction"), bench.index("def run_reference")
+    assert len(hits) == 1 and fn[0] < hits[0] < fn[1]          # inside cpu_reference_prediction() only
+    entry = open(os.path.join(root, "__graft_entry__.py")).read()
+    assert all(entry.rfind("\ndef ", 0, m.start()) >= entry.index("\ndef build") for m in pat.finditer(entry))  # inside build() / smoke()
